@@ -1,0 +1,93 @@
+"""ctypes loader for libfmm_b200.so (the C-ABI CUDA library declared in include/fmm_b200.h).
+
+There is deliberately NO fallback: if the shared object is missing or the device is not an
+sm_100 part, every op raises.  PyTorch is only used for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfmm_b200.so"
+_lib = None
+
+DT_BF16 = 0
+DT_F32 = 1
+
+c_void_p = C.c_void_p
+c_int = C.c_int
+c_ll = C.c_longlong
+c_float = C.c_float
+
+
+def dt_of(t: torch.dtype) -> int:
+    if t == torch.bfloat16:
+        return DT_BF16
+    if t == torch.float32:
+        return DT_F32
+    raise TypeError(f"libfmm_b200 activations must be bf16 or fp32, got {t}")
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the library (once). Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} not found: build it with `python -m fall_multimodal_b200.build` "
+            "(there is no CPU/PyTorch fallback for the CUDA path)")
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.fmm_last_error.restype = C.c_char_p
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().fmm_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libfmm_b200 {what} failed (status {status}): {msg}")
+
+
+def ptr(t) -> int | None:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_device(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("libfmm_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+_P = c_void_p
+_SIGNATURES = {
+    "fmm_version": [],
+    "fmm_device_supported": [],
+    "fmm_tapconv_bn": [c_int],
+    "fmm_tapconv_packed_bytes": [c_int, c_int, c_int, c_int],
+    "fmm_tapconv_pack": [_P, _P, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_int,
+                         C.POINTER(c_int), c_int, _P],
+    "fmm_tapconv": [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                    c_int, c_int, c_int, c_int, C.POINTER(c_int), c_int, _P, _P],
+}
+_RESTYPES = {"fmm_tapconv_packed_bytes": c_ll}
+
+
+def int_array(vals):
+    arr = (c_int * len(vals))(*vals)
+    return arr

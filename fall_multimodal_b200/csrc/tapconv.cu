@@ -1,0 +1,522 @@
+// tapconv: the forward/dgrad GEMM engine of the ST-GCN blocks on tcgen05 tensor cores.
+//
+// Computes, for channels-last activations X[(n,t,v)][Cin] -> Out[(n,t',v)][Cout]:
+//     Out[n, j*os+oo, v, co] = bias[co] + sum_{m<ntaps} sum_ci  f(X[n, j*is+shift[m], v, ci]) * W[m][co][ci]
+// with f(x) = relu?(x*in_scale[ci] + in_shift[ci]) and f := 0 outside [0,Tin) (zero padding is
+// applied AFTER the BatchNorm+ReLU prologue, as nn.Conv2d pads its already-normalised input).
+//
+// One kernel serves (reference call sites, /root/reference/Fall_2_Spatial_Temporal_SR/Model/stgcan.py):
+//   * the 9x1 temporal conv, stride 1|2, with the BN->ReLU of tcn[0..1] fused in the prologue (:112-118)
+//   * its dgrad (transposed conv; stride 2 as two parity phases)
+//   * the 1x1 graph-conv channel mix on the adjacency-aggregated input (:42-54, reassociated)
+//   * the 1x1 strided residual conv (:128-131) and the dgrads of both 1x1 convs.
+//
+// Tiling ("column groups"): a column is one (n,v) pair = a time series; 8 consecutive columns form
+// a group. An M=128 MMA tile is 16 output positions j x 8 columns. The input window of a tile is
+// staged ONCE in shared memory as [time step][8 columns][64 channels] bf16 in the canonical
+// SWIZZLE_128B K-major image (one 1024-byte atom per time step), so every tap is the same image
+// read through a descriptor whose start address is shifted by whole atoms (no im2col copies),
+// and a temporal stride is just SBO = is*1024.
+//
+// Warp roles (320 threads, persistent over tiles): 0-3 window producers (global -> BN/ReLU ->
+// bf16 parts -> swizzled smem), 4-7 epilogue (TMEM -> regs -> bias -> global), 8 weight loader
+// (bulk async copies of pre-packed weight images), 9 MMA issuer (one thread) + TMEM allocator.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fmm {
+
+struct TapConvParams {
+  const void* x;
+  void* out;
+  const void* wpk;
+  const float* in_scale;
+  const float* in_shift;
+  const float* bias;
+  int in_relu;
+  int N, V, Tin, Tout, Cin, Cout;
+  int Tj, istride, ostride, ooff;
+  int ntaps;
+  int shift[9];
+  int minshift, win_atoms;
+  int BN, ntiles_n, nchunks;
+  int ncols, ngroups, ntchunks, total_tiles;
+  int nslots, nbstages;
+  unsigned* err;
+};
+
+constexpr int kTapThreads = 320;
+
+template <typename T>
+__global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
+  constexpr int kParts = ActTraits<T>::kParts;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t slot_bytes = static_cast<uint32_t>(kParts) * p.win_atoms * 1024u;
+  const uint32_t part_bytes_a = static_cast<uint32_t>(p.win_atoms) * 1024u;
+  const uint32_t bstage_bytes = static_cast<uint32_t>(kParts) * p.BN * 128u;
+  const uint32_t part_bytes_b = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t slots0 = smem_base;
+  const uint32_t bst0 = slots0 + p.nslots * slot_bytes;
+  const uint32_t bars0 = bst0 + p.nbstages * bstage_bytes;
+  // barrier map (8 bytes each)
+  auto win_full = [&](int s) { return bars0 + 8u * s; };
+  auto win_empty = [&](int s) { return bars0 + 8u * (p.nslots + s); };
+  auto b_full = [&](int s) { return bars0 + 8u * (2 * p.nslots + s); };
+  auto b_empty = [&](int s) { return bars0 + 8u * (2 * p.nslots + p.nbstages + s); };
+  auto acc_full = [&](int s) { return bars0 + 8u * (2 * p.nslots + 2 * p.nbstages + s); };
+  auto acc_empty = [&](int s) { return bars0 + 8u * (2 * p.nslots + 2 * p.nbstages + 2 + s); };
+  const uint32_t tmem_slot = bars0 + 8u * (2 * p.nslots + 2 * p.nbstages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * p.BN) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslots; ++s) {
+      mbar_init(win_full(s), 128);
+      mbar_init(win_empty(s), 1);
+    }
+    for (int s = 0; s < p.nbstages; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int first_tile = blockIdx.x;
+  const int tile_step = gridDim.x;
+
+  if (warp < 4) {
+    // ------------------------------ window producers ------------------------------
+    const T* __restrict__ X = reinterpret_cast<const T*>(p.x);
+    const int pt = threadIdx.x;       // 0..127
+    const int pc = pt & 7;            // 16-byte chunk = 8 channels
+    const int q = (pt >> 3) & 7;      // column inside the group
+    const int a0 = pt >> 6;           // atoms a0, a0+2, ...
+    const bool vec_ok = (p.Cin % 8) == 0;
+    int slot = 0;
+    uint32_t ph = 0;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      const int rest = tile / p.ntiles_n;
+      const int tchunk = rest % p.ntchunks;
+      const int group = rest / p.ntchunks;
+      const int col = group * 8 + q;
+      const bool col_ok = col < p.ncols;
+      const int n = col_ok ? col / p.V : 0;
+      const int v = col_ok ? col % p.V : 0;
+      const int t_lo = tchunk * 16 * p.istride + p.minshift;
+      for (int c = 0; c < p.nchunks; ++c) {
+        const int cb = c * 64 + pc * 8;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = (cb + i) < p.Cin;
+          sc[i] = (p.in_scale && ok) ? p.in_scale[cb + i] : 1.f;
+          sh[i] = (p.in_shift && ok) ? p.in_shift[cb + i] : 0.f;
+        }
+        mbar_wait(win_empty(slot), ph ^ 1u, p.err, 1);
+        const uint32_t sbase = slots0 + slot * slot_bytes + q * 128u + ((pc ^ q) << 4);
+#pragma unroll 2
+        for (int a = a0; a < p.win_atoms; a += 2) {
+          const int ti = t_lo + a;
+          float f[8];
+          const bool ok = col_ok && ti >= 0 && ti < p.Tin && cb < p.Cin;
+          if (ok) {
+            const T* src = X + (static_cast<size_t>(n) * p.Tin + ti) * p.V * p.Cin +
+                           static_cast<size_t>(v) * p.Cin + cb;
+            if (vec_ok) {
+              load8(src, f);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = (cb + i) < p.Cin ? to_f32(src[i]) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float y = fmaf(f[i], sc[i], sh[i]);
+              if (p.in_relu) y = fmaxf(y, 0.f);
+              f[i] = ((cb + i) < p.Cin) ? y : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = 0.f;
+          }
+          const uint32_t dst = sbase + a * 1024u;
+          if (kParts == 1) {
+            uint4 u = pack8_bf16(f);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(u.x), "r"(u.y),
+                         "r"(u.z), "r"(u.w)
+                         : "memory");
+          } else {
+#pragma unroll
+            for (int part = 0; part < kParts; ++part) {
+              uint4 u = split8_bf16(f);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + part * part_bytes_a),
+                           "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                           : "memory");
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(win_full(slot));
+        if (++slot == p.nslots) {
+          slot = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ---------------------------------- epilogue ----------------------------------
+    T* __restrict__ O = reinterpret_cast<T*>(p.out);
+    const int quad = warp - 4;
+    const int r = quad * 32 + lane;
+    const int q = r & 7;
+    int as = 0;
+    uint32_t aph = 0;
+    const bool vec_ok = (p.Cout % 8) == 0;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      const int ntile = tile % p.ntiles_n;
+      const int rest = tile / p.ntiles_n;
+      const int tchunk = rest % p.ntchunks;
+      const int group = rest / p.ntchunks;
+      const int col = group * 8 + q;
+      const int j = tchunk * 16 + (r >> 3);
+      const bool row_ok = (col < p.ncols) && (j < p.Tj);
+      const int n = row_ok ? col / p.V : 0;
+      const int v = row_ok ? col % p.V : 0;
+      T* orow = O + (static_cast<size_t>(n) * p.Tout + (j * p.ostride + p.ooff)) * p.V * p.Cout +
+                static_cast<size_t>(v) * p.Cout;
+      mbar_wait(acc_full(as), aph, p.err, 2);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * p.BN) + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int cg = 0; cg < p.BN / 32; ++cg) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + cg * 32, acc);
+        tmem_ld_wait();
+        const int co0 = ntile * p.BN + cg * 32;
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int co = co0 + g * 8 + i;
+              float b = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
+              f[i] = __uint_as_float(acc[g * 8 + i]) + b;
+            }
+            const int co = co0 + g * 8;
+            if (vec_ok && co + 8 <= p.Cout) {
+              store8(orow + co, f);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (co + i < p.Cout) orow[co + i] = from_f32<T>(f[i]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty(as));
+      if (++as == 2) {
+        as = 0;
+        aph ^= 1u;
+      }
+    }
+  } else if (warp == 8) {
+    // -------------------------------- weight loader --------------------------------
+    if (lane == 0) {
+      const uint8_t* W = reinterpret_cast<const uint8_t*>(p.wpk);
+      int bs = 0;
+      uint32_t bph = 0;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        const int ntile = tile % p.ntiles_n;
+        for (int c = 0; c < p.nchunks; ++c) {
+          for (int m = 0; m < p.ntaps; ++m) {
+            mbar_wait(b_empty(bs), bph ^ 1u, p.err, 3);
+            mbar_arrive_expect_tx(b_full(bs), bstage_bytes);
+            const size_t off = ((static_cast<size_t>(ntile) * p.nchunks + c) * p.ntaps + m) * bstage_bytes;
+            bulk_g2s(bst0 + bs * bstage_bytes, W + off, bstage_bytes, b_full(bs));
+            if (++bs == p.nbstages) {
+              bs = 0;
+              bph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------- MMA issuer ----------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(p.BN, 0, 0);
+      const uint32_t a_sbo = static_cast<uint32_t>(p.istride) * 1024u;
+      int slot = 0, bs = 0, as = 0;
+      uint32_t wph = 0, bph = 0, aph = 0;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.BN);
+        uint32_t accum = 0;
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(win_full(slot), wph, p.err, 5);
+          tc_fence_after();
+          const uint32_t a_slot = slots0 + slot * slot_bytes;
+          for (int m = 0; m < p.ntaps; ++m) {
+            mbar_wait(b_full(bs), bph, p.err, 6);
+            tc_fence_after();
+            const uint32_t a_tap = a_slot + static_cast<uint32_t>(p.shift[m] - p.minshift) * 1024u;
+            const uint32_t b_st = bst0 + bs * bstage_bytes;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kParts == 1) {
+                umma_bf16(d_tmem, make_smem_desc(a_tap + kk * 32u, 16, a_sbo),
+                          make_smem_desc(b_st + kk * 32u, 16, 1024), idesc, accum);
+                accum = 1;
+              } else {
+                // (a0+a1+a2)(b0+b1+b2) ~ a0b0 + a0b1 + a1b0 + a1b1 + a0b2 + a2b0 (rel. err ~2^-24)
+                const int pa[6] = {2, 0, 1, 1, 0, 0};
+                const int pb[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+                for (int e = 0; e < 6; ++e) {
+                  umma_bf16(d_tmem, make_smem_desc(a_tap + pa[e] * part_bytes_a + kk * 32u, 16, a_sbo),
+                            make_smem_desc(b_st + pb[e] * part_bytes_b + kk * 32u, 16, 1024), idesc,
+                            accum);
+                  accum = 1;
+                }
+              }
+            }
+            umma_commit(b_empty(bs));
+            if (++bs == p.nbstages) {
+              bs = 0;
+              bph ^= 1u;
+            }
+          }
+          umma_commit(win_empty(slot));
+          if (++slot == p.nslots) {
+            slot = 0;
+            wph ^= 1u;
+          }
+        }
+        umma_commit(acc_full(as));
+        if (++as == 2) {
+          as = 0;
+          aph ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: W (fp32, arbitrary 2-level strides) -> per-(ntile, chunk, tap, part) images
+// [BN rows (co)][64 k (ci)] bf16, SWIZZLE_128B, zero padded.
+//   n = n1*N2 + n2  -> offset n1*sn1 + n2*sn2 ;  k = k1*K2 + k2 -> offset k1*sk1 + k2*sk2
+//   tap m -> offset tapmap[m]*sm
+// ------------------------------------------------------------------------------------------
+struct PackParams {
+  const float* w;
+  void* out;
+  int Nout, Kin, N2, K2;
+  long long sn1, sn2, sk1, sk2, sm;
+  int ntaps;
+  int tapmap[9];
+  int BN, ntiles_n, nchunks, nparts;
+};
+
+__global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
+  // one thread per (image, row, 16-byte chunk)
+  const long long total = static_cast<long long>(p.ntiles_n) * p.nchunks * p.ntaps * p.BN * 8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pc = static_cast<int>(idx & 7);
+    long long r0 = idx >> 3;
+    const int row = static_cast<int>(r0 % p.BN);
+    r0 /= p.BN;
+    const int m = static_cast<int>(r0 % p.ntaps);
+    r0 /= p.ntaps;
+    const int c = static_cast<int>(r0 % p.nchunks);
+    const int ntile = static_cast<int>(r0 / p.nchunks);
+    const int n = ntile * p.BN + row;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = c * 64 + pc * 8 + i;
+      float val = 0.f;
+      if (n < p.Nout && k < p.Kin) {
+        const long long off = (n / p.N2) * p.sn1 + (n % p.N2) * p.sn2 + (k / p.K2) * p.sk1 +
+                              (k % p.K2) * p.sk2 + p.tapmap[m] * p.sm;
+        val = p.w[off];
+      }
+      f[i] = val;
+    }
+    const size_t img = ((static_cast<size_t>(ntile) * p.nchunks + c) * p.ntaps + m) * p.nparts;
+    uint8_t* base = reinterpret_cast<uint8_t*>(p.out) + img * (static_cast<size_t>(p.BN) * 128u);
+    for (int part = 0; part < p.nparts; ++part) {
+      uint4 u = split8_bf16(f);
+      *reinterpret_cast<uint4*>(base + static_cast<size_t>(part) * p.BN * 128u + sw128_off(row, pc)) = u;
+    }
+  }
+}
+
+static int pick_bn(int cout) {
+  // largest tile <= 256 that is a multiple of 32 and divides the 32-padded channel count evenly
+  const int c32 = (cout + 31) / 32 * 32;
+  if (c32 <= 256) return c32;
+  for (int bn = 256; bn >= 32; bn -= 32)
+    if (c32 % bn == 0) return bn;
+  return 32;
+}
+
+}  // namespace fmm
+
+using namespace fmm;
+
+extern "C" {
+
+// Geometry shared by pack + launch so both sides agree on the packed layout.
+int fmm_tapconv_bn(int cout) { return pick_bn(cout); }
+
+long long fmm_tapconv_packed_bytes(int cin, int cout, int ntaps, int dtype) {
+  const int bn = pick_bn(cout);
+  const int ntiles = ((cout + 31) / 32 * 32 + bn - 1) / bn;
+  const int nchunks = (cin + 63) / 64;
+  const int nparts = dtype == FMM_DT_F32 ? 3 : 1;
+  return static_cast<long long>(ntiles) * nchunks * ntaps * nparts * bn * 128;
+}
+
+int fmm_tapconv_pack(const float* w, void* out, int cout, int cin, int n2, int k2, long long sn1,
+                     long long sn2, long long sk1, long long sk2, long long sm, int ntaps,
+                     const int* tapmap, int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(w && out && cout > 0 && cin > 0 && ntaps >= 1 && ntaps <= 9 && n2 > 0 && k2 > 0,
+                "tapconv_pack: bad arguments");
+  PackParams p;
+  p.w = w;
+  p.out = out;
+  p.Nout = cout;
+  p.Kin = cin;
+  p.N2 = n2;
+  p.K2 = k2;
+  p.sn1 = sn1;
+  p.sn2 = sn2;
+  p.sk1 = sk1;
+  p.sk2 = sk2;
+  p.sm = sm;
+  p.ntaps = ntaps;
+  for (int i = 0; i < 9; ++i) p.tapmap[i] = i < ntaps ? tapmap[i] : 0;
+  p.BN = pick_bn(cout);
+  p.ntiles_n = ((cout + 31) / 32 * 32 + p.BN - 1) / p.BN;
+  p.nchunks = (cin + 63) / 64;
+  p.nparts = dtype == FMM_DT_F32 ? 3 : 1;
+  const long long total = static_cast<long long>(p.ntiles_n) * p.nchunks * ntaps * p.BN * 8;
+  const int threads = 256;
+  const int blocks = static_cast<int>((total + threads - 1) / threads < 1184 ? (total + threads - 1) / threads : 1184);
+  pack_weights_kernel<<<blocks, threads, 0, stream>>>(p);
+  FMM_CHECK_LAUNCH("tapconv_pack");
+  return FMM_OK;
+}
+
+int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale,
+                const float* in_shift, int in_relu, const float* bias, int N, int V, int Tin,
+                int Tout, int Cin, int Cout, int Tj, int istride, int ostride, int ooff, int ntaps,
+                const int* shifts, int dtype, unsigned* err, cudaStream_t stream) {
+  FMM_CHECK_ARG(x && out && wpk, "tapconv: null pointer");
+  FMM_CHECK_ARG(N > 0 && V > 0 && Tin > 0 && Tout > 0 && Cin > 0 && Cout > 0 && Tj > 0, "tapconv: bad shape");
+  FMM_CHECK_ARG(ntaps >= 1 && ntaps <= 9 && istride >= 1 && istride <= 2 && ostride >= 1,
+                "tapconv: bad taps/stride");
+  FMM_CHECK_ARG(dtype == FMM_DT_BF16 || dtype == FMM_DT_F32, "tapconv: bad dtype");
+  FMM_CHECK_ARG((Tj - 1) * ostride + ooff < Tout, "tapconv: output positions exceed Tout");
+  TapConvParams p;
+  p.x = x;
+  p.out = out;
+  p.wpk = wpk;
+  p.in_scale = in_scale;
+  p.in_shift = in_shift;
+  p.bias = bias;
+  p.in_relu = in_relu;
+  p.N = N;
+  p.V = V;
+  p.Tin = Tin;
+  p.Tout = Tout;
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.Tj = Tj;
+  p.istride = istride;
+  p.ostride = ostride;
+  p.ooff = ooff;
+  p.ntaps = ntaps;
+  int mn = shifts[0], mx = shifts[0];
+  for (int i = 0; i < 9; ++i) {
+    p.shift[i] = i < ntaps ? shifts[i] : 0;
+    if (i < ntaps) {
+      mn = shifts[i] < mn ? shifts[i] : mn;
+      mx = shifts[i] > mx ? shifts[i] : mx;
+    }
+  }
+  p.minshift = mn;
+  p.win_atoms = 15 * istride + (mx - mn) + 1;
+  p.BN = pick_bn(Cout);
+  p.ntiles_n = ((Cout + 31) / 32 * 32 + p.BN - 1) / p.BN;
+  p.nchunks = (Cin + 63) / 64;
+  p.ncols = N * V;
+  p.ngroups = (p.ncols + 7) / 8;
+  p.ntchunks = (Tj + 15) / 16;
+  p.total_tiles = p.ngroups * p.ntchunks * p.ntiles_n;
+  p.err = err;
+  const int nparts = dtype == FMM_DT_F32 ? 3 : 1;
+  const size_t slot_bytes = static_cast<size_t>(nparts) * p.win_atoms * 1024;
+  const size_t bstage_bytes = static_cast<size_t>(nparts) * p.BN * 128;
+  const size_t budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
+  // ring depths: prefer 4 weight stages + as many window slots as fit (max 4), shrink if needed
+  int nb = 4, ns = 4;
+  while (nb > 2 && nb * bstage_bytes + 2 * slot_bytes > budget) --nb;
+  while (ns > 1 && nb * bstage_bytes + ns * slot_bytes > budget) --ns;
+  FMM_CHECK_ARG(nb * bstage_bytes + ns * slot_bytes <= budget,
+                "tapconv: tile does not fit shared memory (win_atoms=%d BN=%d parts=%d)", p.win_atoms,
+                p.BN, nparts);
+  p.nslots = ns;
+  p.nbstages = nb;
+  const size_t smem = nb * bstage_bytes + ns * slot_bytes + 1024 + 512;
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  cudaError_t e;
+  if (dtype == FMM_DT_BF16) {
+    e = cudaFuncSetAttribute(tapconv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_last_error("tapconv: smem attribute: %s", cudaGetErrorString(e));
+      return FMM_ERR_SMEM;
+    }
+    tapconv_kernel<__nv_bfloat16><<<grid, kTapThreads, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(tapconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_last_error("tapconv: smem attribute: %s", cudaGetErrorString(e));
+      return FMM_ERR_SMEM;
+    }
+    tapconv_kernel<float><<<grid, kTapThreads, smem, stream>>>(p);
+  }
+  FMM_CHECK_LAUNCH("tapconv");
+  return FMM_OK;
+}
+
+}  // extern "C"

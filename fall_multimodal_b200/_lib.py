@@ -78,12 +78,14 @@ _P = c_void_p
 _SIGNATURES = {
     "fmm_version": [],
     "fmm_device_supported": [],
-    "fmm_tapconv_bn": [c_int],
+    "fmm_tapconv_bn": [c_int, c_int],
     "fmm_tapconv_packed_bytes": [c_int, c_int, c_int, c_int],
     "fmm_tapconv_pack": [_P, _P, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_int,
                          C.POINTER(c_int), c_int, _P],
     "fmm_tapconv": [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                     c_int, c_int, c_int, c_int, C.POINTER(c_int), c_int, _P, _P],
+    "fmm_wgrad": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                  C.POINTER(c_int), c_int, c_ll, c_ll, c_ll, c_ll, c_int, _P, _P],
 }
 _RESTYPES = {"fmm_tapconv_packed_bytes": c_ll}
 

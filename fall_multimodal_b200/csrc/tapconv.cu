@@ -380,11 +380,13 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
   }
 }
 
-static int pick_bn(int cout) {
-  // largest tile <= 256 that is a multiple of 32 and divides the 32-padded channel count evenly
+static int pick_bn(int cout, int dtype) {
+  // largest tile <= cap that is a multiple of 32 and divides the 32-padded channel count evenly
+  // (fp32 activations carry 3 bf16 parts per operand, so their tiles are capped at 128 columns)
+  const int cap = dtype == FMM_DT_F32 ? 128 : 256;
   const int c32 = (cout + 31) / 32 * 32;
-  if (c32 <= 256) return c32;
-  for (int bn = 256; bn >= 32; bn -= 32)
+  if (c32 <= cap) return c32;
+  for (int bn = cap; bn >= 32; bn -= 32)
     if (c32 % bn == 0) return bn;
   return 32;
 }
@@ -396,10 +398,10 @@ using namespace fmm;
 extern "C" {
 
 // Geometry shared by pack + launch so both sides agree on the packed layout.
-int fmm_tapconv_bn(int cout) { return pick_bn(cout); }
+int fmm_tapconv_bn(int cout, int dtype) { return pick_bn(cout, dtype); }
 
 long long fmm_tapconv_packed_bytes(int cin, int cout, int ntaps, int dtype) {
-  const int bn = pick_bn(cout);
+  const int bn = pick_bn(cout, dtype);
   const int ntiles = ((cout + 31) / 32 * 32 + bn - 1) / bn;
   const int nchunks = (cin + 63) / 64;
   const int nparts = dtype == FMM_DT_F32 ? 3 : 1;
@@ -425,7 +427,7 @@ int fmm_tapconv_pack(const float* w, void* out, int cout, int cin, int n2, int k
   p.sm = sm;
   p.ntaps = ntaps;
   for (int i = 0; i < 9; ++i) p.tapmap[i] = i < ntaps ? tapmap[i] : 0;
-  p.BN = pick_bn(cout);
+  p.BN = pick_bn(cout, dtype);
   p.ntiles_n = ((cout + 31) / 32 * 32 + p.BN - 1) / p.BN;
   p.nchunks = (cin + 63) / 64;
   p.nparts = dtype == FMM_DT_F32 ? 3 : 1;
@@ -476,7 +478,7 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   }
   p.minshift = mn;
   p.win_atoms = 15 * istride + (mx - mn) + 1;
-  p.BN = pick_bn(Cout);
+  p.BN = pick_bn(Cout, dtype);
   p.ntiles_n = ((Cout + 31) / 32 * 32 + p.BN - 1) / p.BN;
   p.nchunks = (Cin + 63) / 64;
   p.ncols = N * V;

@@ -1,0 +1,383 @@
+// wgrad: weight-gradient GEMMs of the ST-GCN blocks on tcgen05 tensor cores.
+//
+//   dW[m][ci][co] += sum_{n,v,j}  f(X[n, j*is+shift[m], v, ci]) * dY[n, j, v, co]
+//
+// i.e. the contraction runs over the (huge) row dimension and the result is a small matrix, the
+// mirror image of csrc/tapconv.cu. Both operands are activations, read channels-last, and both are
+// staged in the SAME shared-memory images as the forward engine ([time step][8 columns][64 ch],
+// SWIZZLE_128B): what is a K-major A tile for the forward GEMM is an MN-major operand here
+// (M' = channels, K' = rows), so taps are again whole-atom descriptor shifts and stride is SBO.
+//
+// Serves: tcn 9x1 conv wgrad (BN+ReLU of the saved pre-activation fused in the prologue, as in
+// stgcan.py:112-118), the 1x1 gcn conv wgrad on the aggregated input (:42-54) and the strided
+// residual 1x1 conv wgrad (:128-131).
+//
+// Work split: item = (ci tile, tap group, co tile) keeps TG accumulators [128 x BN] resident in
+// TMEM; the row dimension is sliced across CTAs and the partial results are added to global
+// memory with fp32 atomics (dW must be zeroed by the caller).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fmm {
+
+struct WgradParams {
+  const void* x;
+  const void* dy;
+  float* dw;
+  const float* in_scale;
+  const float* in_shift;
+  int in_relu;
+  int N, V, Tin, Tj, Cin, Cout;
+  int istride;
+  int ntaps;
+  int shift[9];
+  int minshift, win_atoms;
+  int JT;                 // positions per unit (16 or 8) -> K' = 8*JT rows
+  int MCH;                // 64-channel chunks per ci tile (1 or 2)
+  int BN, TG;             // co tile width, taps per item
+  int ci_tiles, tap_groups, co_tiles, items, slices;
+  int ncols, ngroups, njchunks, total_units;
+  int nstages;
+  int C2;                 // ci = c1*C2 + c2
+  long long s_m, s_c1, s_c2, s_co;
+  unsigned* err;
+};
+
+constexpr int kWgThreads = 192;  // warps 0-3 producers (+ epilogue at the end), 4 = MMA, 5 spare
+
+template <typename T>
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int kParts = ActTraits<T>::kParts;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_part = static_cast<uint32_t>(p.MCH) * p.win_atoms * 1024u;
+  const uint32_t b_part = static_cast<uint32_t>(p.BN / 64) * p.JT * 1024u;
+  const uint32_t a_bytes = a_part * kParts;
+  const uint32_t b_bytes = b_part * kParts;
+  const uint32_t stage_bytes = a_bytes + b_bytes + 1024u;  // +1 atom of slack: MCH=1 reads one atom past A
+  const uint32_t bars0 = smem_base + p.nstages * stage_bytes;
+  auto full = [&](int s) { return bars0 + 8u * s; };
+  auto empty = [&](int s) { return bars0 + 8u * (p.nstages + s); };
+  const uint32_t acc_full = bars0 + 8u * (2 * p.nstages);
+  const uint32_t tmem_slot = acc_full + 8u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(p.TG * p.BN)) tmem_cols <<= 1;
+
+  const int item = blockIdx.x % p.items;
+  const int slice = blockIdx.x / p.items;
+  const int co_tile = item % p.co_tiles;
+  const int tg = (item / p.co_tiles) % p.tap_groups;
+  const int ci_tile = item / (p.co_tiles * p.tap_groups);
+  const int m0 = tg * p.TG;
+  const int mt = (p.ntaps - m0) < p.TG ? (p.ntaps - m0) : p.TG;  // taps of this item
+  const int my_units = slice < p.total_units ? (p.total_units - slice + p.slices - 1) / p.slices : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      mbar_init(full(s), 128);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (my_units > 0) {
+    if (warp < 4) {
+      // ------------------------------ producers ------------------------------
+      const T* __restrict__ X = reinterpret_cast<const T*>(p.x);
+      const T* __restrict__ DY = reinterpret_cast<const T*>(p.dy);
+      const int pt = threadIdx.x;
+      const int pc = pt & 7;
+      const int q = (pt >> 3) & 7;
+      const int a0 = pt >> 6;
+      const bool xvec = (p.Cin % 8) == 0;
+      const bool yvec = (p.Cout % 8) == 0;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int u = slice; u < p.total_units; u += p.slices) {
+        const int jchunk = u % p.njchunks;
+        const int group = u / p.njchunks;
+        const int col = group * 8 + q;
+        const bool col_ok = col < p.ncols;
+        const int n = col_ok ? col / p.V : 0;
+        const int v = col_ok ? col % p.V : 0;
+        const int j0 = jchunk * p.JT;
+        const int t_lo = j0 * p.istride + p.minshift;
+        mbar_wait(empty(st), ph ^ 1u, p.err, 11);
+        const uint32_t a_base = smem_base + st * stage_bytes;
+        const uint32_t b_base = a_base + a_bytes;
+        // A' : X window, MCH chunks
+        for (int h = 0; h < p.MCH; ++h) {
+          const int cb = (ci_tile * p.MCH + h) * 64 + pc * 8;
+          float sc[8], sh[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = (cb + i) < p.Cin;
+            sc[i] = (p.in_scale && ok) ? p.in_scale[cb + i] : 1.f;
+            sh[i] = (p.in_shift && ok) ? p.in_shift[cb + i] : 0.f;
+          }
+          const uint32_t sbase = a_base + h * p.win_atoms * 1024u + q * 128u + ((pc ^ q) << 4);
+#pragma unroll 2
+          for (int a = a0; a < p.win_atoms; a += 2) {
+            const int ti = t_lo + a;
+            float f[8];
+            const bool ok = col_ok && ti >= 0 && ti < p.Tin && cb < p.Cin;
+            if (ok) {
+              const T* src = X + (static_cast<size_t>(n) * p.Tin + ti) * p.V * p.Cin +
+                             static_cast<size_t>(v) * p.Cin + cb;
+              if (xvec) {
+                load8(src, f);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = (cb + i) < p.Cin ? to_f32(src[i]) : 0.f;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float y = fmaf(f[i], sc[i], sh[i]);
+                if (p.in_relu) y = fmaxf(y, 0.f);
+                f[i] = ((cb + i) < p.Cin) ? y : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = 0.f;
+            }
+            const uint32_t dst = sbase + a * 1024u;
+#pragma unroll
+            for (int part = 0; part < kParts; ++part) {
+              uint4 w = (kParts == 1) ? pack8_bf16(f) : split8_bf16(f);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + part * a_part), "r"(w.x),
+                           "r"(w.y), "r"(w.z), "r"(w.w)
+                           : "memory");
+            }
+          }
+        }
+        // B' : dY tile, BN/64 chunks x JT atoms
+        for (int h = 0; h < p.BN / 64; ++h) {
+          const int cb = co_tile * p.BN + h * 64 + pc * 8;
+          const uint32_t sbase = b_base + h * p.JT * 1024u + q * 128u + ((pc ^ q) << 4);
+#pragma unroll 2
+          for (int a = a0; a < p.JT; a += 2) {
+            const int j = j0 + a;
+            float f[8];
+            const bool ok = col_ok && j < p.Tj && cb < p.Cout;
+            if (ok) {
+              const T* src = DY + (static_cast<size_t>(n) * p.Tj + j) * p.V * p.Cout +
+                             static_cast<size_t>(v) * p.Cout + cb;
+              if (yvec) {
+                load8(src, f);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = (cb + i) < p.Cout ? to_f32(src[i]) : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = 0.f;
+            }
+            const uint32_t dst = sbase + a * 1024u;
+#pragma unroll
+            for (int part = 0; part < kParts; ++part) {
+              uint4 w = (kParts == 1) ? pack8_bf16(f) : split8_bf16(f);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + part * b_part), "r"(w.x),
+                           "r"(w.y), "r"(w.z), "r"(w.w)
+                           : "memory");
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(full(st));
+        if (++st == p.nstages) {
+          st = 0;
+          ph ^= 1u;
+        }
+      }
+      // ------------------------------ epilogue (same warps) ------------------------------
+      mbar_wait(acc_full, 0, p.err, 12);
+      tc_fence_after();
+      const int row = warp * 32 + lane;  // channel inside the ci tile
+      const int ci = ci_tile * p.MCH * 64 + row;
+      const bool ci_ok = row < p.MCH * 64 && ci < p.Cin;
+      const long long ci_off = ci_ok ? (ci / p.C2) * p.s_c1 + (ci % p.C2) * p.s_c2 : 0;
+      for (int t = 0; t < mt; ++t) {
+        for (int cg = 0; cg < p.BN / 32; ++cg) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + static_cast<uint32_t>(t * p.BN + cg * 32) + (static_cast<uint32_t>(warp * 32) << 16), acc);
+          tmem_ld_wait();
+          if (ci_ok) {
+            float* dst = p.dw + (m0 + t) * p.s_m + ci_off;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int co = co_tile * p.BN + cg * 32 + i;
+              if (co < p.Cout) atomicAdd(dst + co * p.s_co, __uint_as_float(acc[i]));
+            }
+          }
+        }
+      }
+    } else if (warp == 4) {
+      // ---------------------------------- MMA issuer ----------------------------------
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(p.BN, 1, 1);
+        const uint32_t a_sbo = static_cast<uint32_t>(p.istride) * 1024u;
+        const uint32_t a_lbo = p.MCH == 2 ? static_cast<uint32_t>(p.win_atoms) * 1024u : 1024u;
+        const uint32_t b_lbo = static_cast<uint32_t>(p.JT) * 1024u;
+        int st = 0;
+        uint32_t ph = 0;
+        uint32_t accum = 0;
+        for (int it = 0; it < my_units; ++it) {
+          mbar_wait(full(st), ph, p.err, 13);
+          tc_fence_after();
+          const uint32_t a_base = smem_base + st * stage_bytes;
+          const uint32_t b_base = a_base + a_bytes;
+          for (int kk = 0; kk < p.JT / 2; ++kk) {
+            for (int t = 0; t < mt; ++t) {
+              const uint32_t a_tap = a_base + static_cast<uint32_t>(p.shift[m0 + t] - p.minshift) * 1024u +
+                                     static_cast<uint32_t>(kk) * 2u * a_sbo;
+              const uint32_t b_k = b_base + static_cast<uint32_t>(kk) * 2048u;
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(t * p.BN);
+              if (kParts == 1) {
+                umma_bf16(d_tmem, make_smem_desc(a_tap, a_lbo, a_sbo), make_smem_desc(b_k, b_lbo, 1024),
+                          idesc, accum);
+              } else {
+                const int pa[6] = {2, 0, 1, 1, 0, 0};
+                const int pb[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+                for (int e = 0; e < 6; ++e)
+                  umma_bf16(d_tmem, make_smem_desc(a_tap + pa[e] * a_part, a_lbo, a_sbo),
+                            make_smem_desc(b_k + pb[e] * b_part, b_lbo, 1024), idesc, (e > 0) ? 1u : accum);
+              }
+            }
+            accum = 1;
+          }
+          umma_commit(empty(st));
+          if (++st == p.nstages) {
+            st = 0;
+            ph ^= 1u;
+          }
+        }
+        umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace fmm
+
+using namespace fmm;
+
+extern "C" {
+
+int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, const float* in_shift,
+              int in_relu, int N, int V, int Tin, int Tj, int Cin, int Cout, int istride, int ntaps,
+              const int* shifts, int c2, long long s_m, long long s_c1, long long s_c2, long long s_co,
+              int dtype, unsigned* err, cudaStream_t stream) {
+  FMM_CHECK_ARG(x && dy && dw, "wgrad: null pointer");
+  FMM_CHECK_ARG(N > 0 && V > 0 && Tin > 0 && Tj > 0 && Cin > 0 && Cout > 0 && c2 > 0, "wgrad: bad shape");
+  FMM_CHECK_ARG(ntaps >= 1 && ntaps <= 9 && istride >= 1 && istride <= 2, "wgrad: bad taps/stride");
+  FMM_CHECK_ARG(dtype == FMM_DT_BF16 || dtype == FMM_DT_F32, "wgrad: bad dtype");
+  WgradParams p;
+  p.x = x;
+  p.dy = dy;
+  p.dw = dw;
+  p.in_scale = in_scale;
+  p.in_shift = in_shift;
+  p.in_relu = in_relu;
+  p.N = N;
+  p.V = V;
+  p.Tin = Tin;
+  p.Tj = Tj;
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.istride = istride;
+  p.ntaps = ntaps;
+  int mn = shifts[0], mx = shifts[0];
+  for (int i = 0; i < 9; ++i) {
+    p.shift[i] = i < ntaps ? shifts[i] : 0;
+    if (i < ntaps) {
+      mn = shifts[i] < mn ? shifts[i] : mn;
+      mx = shifts[i] > mx ? shifts[i] : mx;
+    }
+  }
+  const int nparts = dtype == FMM_DT_F32 ? 3 : 1;
+  const int cout64 = (Cout + 63) / 64 * 64;
+  if (nparts == 1) {
+    p.JT = 16;
+    p.MCH = Cin > 64 ? 2 : 1;
+    p.BN = ntaps > 1 ? 64 : (cout64 < 256 ? cout64 : 256);
+  } else {
+    p.JT = 8;
+    p.MCH = 1;
+    p.BN = ntaps > 1 ? 64 : (cout64 < 128 ? cout64 : 128);
+  }
+  const int max_tg = 512 / p.BN;
+  const int ngrp = (ntaps + max_tg - 1) / max_tg;
+  p.TG = (ntaps + ngrp - 1) / ngrp;
+  p.tap_groups = (ntaps + p.TG - 1) / p.TG;
+  p.minshift = mn;
+  p.win_atoms = (p.JT - 1) * istride + (mx - mn) + 1;
+  p.ci_tiles = (Cin + 64 * p.MCH - 1) / (64 * p.MCH);
+  p.co_tiles = (Cout + p.BN - 1) / p.BN;
+  p.items = p.ci_tiles * p.tap_groups * p.co_tiles;
+  p.ncols = N * V;
+  p.ngroups = (p.ncols + 7) / 8;
+  p.njchunks = (Tj + p.JT - 1) / p.JT;
+  p.total_units = p.ngroups * p.njchunks;
+  int slices = num_sms() / p.items;
+  if (slices < 1) slices = 1;
+  if (slices > p.total_units) slices = p.total_units;
+  p.slices = slices;
+  p.C2 = c2;
+  p.s_m = s_m;
+  p.s_c1 = s_c1;
+  p.s_c2 = s_c2;
+  p.s_co = s_co;
+  p.err = err;
+  const size_t a_bytes = static_cast<size_t>(nparts) * p.MCH * p.win_atoms * 1024;
+  const size_t b_bytes = static_cast<size_t>(nparts) * (p.BN / 64) * p.JT * 1024;
+  const size_t stage = a_bytes + b_bytes + 1024;
+  const size_t budget = 227 * 1024 - 1024 - 256;
+  int ns = 3;
+  while (ns > 1 && ns * stage > budget) --ns;
+  FMM_CHECK_ARG(ns * stage <= budget, "wgrad: stage does not fit shared memory (%zu bytes)", stage);
+  p.nstages = ns;
+  const size_t smem = ns * stage + 1024 + 256;
+  const int grid = p.items * p.slices;
+  cudaError_t e;
+  if (dtype == FMM_DT_BF16) {
+    e = cudaFuncSetAttribute(wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_last_error("wgrad: smem attribute: %s", cudaGetErrorString(e));
+      return FMM_ERR_SMEM;
+    }
+    wgrad_kernel<__nv_bfloat16><<<grid, kWgThreads, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_last_error("wgrad: smem attribute: %s", cudaGetErrorString(e));
+      return FMM_ERR_SMEM;
+    }
+    wgrad_kernel<float><<<grid, kWgThreads, smem, stream>>>(p);
+  }
+  FMM_CHECK_LAUNCH("wgrad");
+  return FMM_OK;
+}
+
+}  // extern "C"

@@ -65,3 +65,25 @@ def tapconv(x: torch.Tensor, pw: PackedWeight, out: torch.Tensor, *, shifts, tj:
                          L.ptr(err_word(x.device)), L.stream())
     L.check(st, "tapconv")
     return out
+
+
+def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, shifts, istride: int = 1,
+          in_scale=None, in_shift=None, in_relu: bool = False, c2: int | None = None,
+          s_m: int, s_c1: int = 0, s_c2: int, s_co: int) -> torch.Tensor:
+    """dw[m, ci, co] += sum_{n,v,j} f(x[n, j*istride+shifts[m], v, ci]) * dy[n, j, v, co].
+
+    ``dw`` is an fp32 buffer addressed as ``m*s_m + (ci//c2)*s_c1 + (ci%c2)*s_c2 + co*s_co`` and is
+    accumulated into with atomics: zero it first.
+    """
+    L.require_device(x)
+    assert x.is_contiguous() and dy.is_contiguous() and x.dtype == dy.dtype and dw.dtype == torch.float32
+    N, Tin, V, Cin = x.shape
+    Ny, Tj, Vy, Cout = dy.shape
+    assert (Ny, Vy) == (N, V)
+    lib = L.load()
+    st = lib.fmm_wgrad(L.ptr(x), L.ptr(dy), L.ptr(dw), L.ptr(in_scale), L.ptr(in_shift), int(in_relu),
+                       N, V, Tin, Tj, Cin, Cout, istride, len(shifts), L.int_array(list(shifts)),
+                       c2 if c2 is not None else Cin, s_m, s_c1, s_c2, s_co, L.dt_of(x.dtype),
+                       L.ptr(err_word(x.device)), L.stream())
+    L.check(st, "wgrad")
+    return dw

@@ -1,0 +1,154 @@
+"""ORACLE tooling — generates tests/golden/*.pt by RUNNING THE REFERENCE in the build container.
+
+    python oracle/make_golden.py
+
+Every fixture holds: the config, the reference state_dict key->shape list, the recipe seeds, and
+the reference outputs (logits, loss, gradient tensors or their summaries, BN running-stat updates).
+Weights and inputs are NOT stored: both sides regenerate them with
+``stgcn_oracle.fill_state_dict`` / ``synthetic_batch`` (order-independent, seeded per key).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_import, stgcn_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+FULL_LIMIT = 2048
+
+
+def summarize(t: torch.Tensor, key: str):
+    t = t.detach().double().flatten()
+    if t.numel() <= FULL_LIMIT:
+        return {"full": t.float().clone()}
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(key.encode()) % (2 ** 31))
+    idx = torch.randint(0, t.numel(), (64,), generator=g)
+    return {"sum": t.sum().item(), "l1": t.abs().sum().item(), "l2": t.norm().item(),
+            "amax": t.abs().max().item(), "idx": idx, "vals": t[idx].float().clone()}
+
+
+def fill_module(mod, seed):
+    sd = mod.state_dict()
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    filled = O.fill_state_dict(shapes, seed)
+    for k, v in filled.items():
+        sd[k] = v
+    mod.load_state_dict(sd)
+    return shapes
+
+
+def run_train_step(mod, call, target):
+    mod.train()
+    mod.zero_grad()
+    before = {k: v.clone() for k, v in mod.state_dict().items() if "running_" in k}
+    logits = call()
+    loss = torch.nn.CrossEntropyLoss()(logits, target) if target is not None else logits.square().mean()
+    loss.backward()
+    grads = {k: summarize(p.grad, k) for k, p in mod.named_parameters() if p.grad is not None}
+    running = {k: summarize(v, k) for k, v in mod.state_dict().items() if "running_" in k}
+    mod.eval()
+    with torch.no_grad():
+        # eval with the ORIGINAL running stats (the train step above updated them in place)
+        sd = mod.state_dict()
+        after = {k: sd[k].clone() for k in before}
+        for k, v in before.items():
+            sd[k].copy_(v)
+        ev = call()
+        for k, v in after.items():
+            sd[k].copy_(v)
+    return {"logits": logits.detach().clone(), "loss": float(loss), "grads": grads, "running": running,
+            "eval_logits": ev.detach().clone()}
+
+
+def main():
+    assert ref_import.available(), "reference tree not mounted"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(4)
+    stg, g, bl, comb = ref_import.load_gstcan()
+    n33, e33, c33 = O.LAYOUTS["mediapipe33"]
+    ref_import.install_layout(stg, g, "mediapipe33", n33, e33, c33)
+    comb.STGCAN = stg.STGCAN
+
+    # ---- adjacency matrices ---------------------------------------------------------------
+    adj = {}
+    for layout in ("coco_cut", "coco_mmpose", "mediapipe33"):
+        for strategy in ("uniform", "distance", "spatial"):
+            adj[f"{layout}/{strategy}"] = torch.tensor(stg.Graph(layout=layout, strategy=strategy).A)
+    torch.save(adj, os.path.join(OUT, "graph_A.pt"))
+
+    # ---- parameter-count known answers ----------------------------------
+    counts = {}
+    m = comb.TwoStreamSTGCAN_BiLSTM(3, {"layout": "coco_cut", "strategy": "spatial"}, 11, 15)
+    counts["TwoStreamSTGCAN_BiLSTM"] = sum(p.numel() for p in m.parameters())
+    m = bl.BiLSTM(15, 64, 1, 0.3, 11, "mean")
+    counts["BiLSTM"] = sum(p.numel() for p in m.parameters())
+    m = stg.STGCAN(3, {"layout": "coco_cut", "strategy": "spatial"}, 11)
+    counts["STGCAN"] = sum(p.numel() for p in m.parameters())
+    counts["STGCAN_keys"] = len(m.state_dict())
+    nbs = ref_import.load_notebook_sensor()
+    counts["CNN1D"] = sum(p.numel() for p in nbs["CNN1D"]().parameters())
+    assert counts["TwoStreamSTGCAN_BiLSTM"] == 4298291 and counts["BiLSTM"] == 47387, counts
+    assert counts["CNN1D"] == 11104, counts  # 3904 conv+bn params + the unused fc(224->32)
+    torch.save(counts, os.path.join(OUT, "param_counts.pt"))
+
+    # ---- GSTCAN cases -----------------------------------------------------------------------
+    cases = [
+        ("stgcan_coco_spatial", dict(in_ch=3, layout="coco_cut", strategy="spatial", num_class=11, N=4, T=12)),
+        ("stgcan_mp33_spatial", dict(in_ch=3, layout="mediapipe33", strategy="spatial", num_class=11, N=2, T=16)),
+        ("stgcan_mmpose_uniform_feat", dict(in_ch=2, layout="coco_mmpose", strategy="uniform", num_class=None, N=3, T=9)),
+    ]
+    for name, c in cases:
+        mod = stg.STGCAN(c["in_ch"], {"layout": c["layout"], "strategy": c["strategy"]}, num_class=c["num_class"])
+        shapes = fill_module(mod, seed=1)
+        V = mod.A.shape[1]
+        skel, _, target, _ = O.synthetic_batch(c["N"], c["T"], V, 11, seed=7)
+        skel = skel[:, : c["in_ch"]].contiguous()
+        res = run_train_step(mod, lambda: mod(skel, None), target if c["num_class"] else None)
+        torch.save({"config": c, "shapes": shapes, "fill_seed": 1, "batch_seed": 7, **res},
+                   os.path.join(OUT, name + ".pt"))
+        print(name, "loss", res["loss"])
+
+    # ---- BiLSTM ---------------------------------------------------------------------------------
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = bl.BiLSTM(15, 64, 1, 0.3, 11, "mean")
+    shapes = fill_module(mod, seed=2)
+    _, sensor, target, _ = O.synthetic_batch(6, 4, 14, 11, sensor_len=30, sensor_ch=15, seed=8)
+    res = run_train_step(mod, lambda: mod(None, sensor), target)
+    torch.save({"config": dict(I=15, H=64, num_class=11, N=6, L=30), "shapes": shapes, "fill_seed": 2,
+                "batch_seed": 8, **res}, os.path.join(OUT, "bilstm_mean.pt"))
+    print("bilstm loss", res["loss"])
+
+    # ---- CNN1D (notebook) -----------------------------------------------------------------------
+    mod = nbs["CNN1D"]()
+    shapes = fill_module(mod, seed=3)
+    _, sensor, _, _ = O.synthetic_batch(5, 4, 14, 11, sensor_len=30, sensor_ch=15, seed=9)
+    xin = sensor.permute(0, 2, 1).contiguous()
+    res = run_train_step(mod, lambda: mod(xin), None)
+    torch.save({"config": dict(Cin=15, L=30, N=5), "shapes": shapes, "fill_seed": 3, "batch_seed": 9, **res},
+               os.path.join(OUT, "cnn1d.pt"))
+    print("cnn1d loss", res["loss"])
+
+    # ---- fusion: TwoStreamSTGCAN_BiLSTM ----------------------------------------------------------
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = comb.TwoStreamSTGCAN_BiLSTM(3, {"layout": "coco_cut", "strategy": "spatial"}, 11, 15)
+    shapes = fill_module(mod, seed=4)
+    skel, sensor, target, _ = O.synthetic_batch(4, 10, 14, 11, sensor_len=30, sensor_ch=15, seed=10)
+    res = run_train_step(mod, lambda: mod(skel, sensor), target)
+    torch.save({"config": dict(layout="coco_cut", strategy="spatial", num_class=11, N=4, T=10, L=30, I=15),
+                "shapes": shapes, "fill_seed": 4, "batch_seed": 10, **res},
+               os.path.join(OUT, "two_stream_bilstm.pt"))
+    print("fusion loss", res["loss"])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""ORACLE tooling — imports the UNMODIFIED reference modules from /root/reference.
+
+Only usable in the build container (the reference tree does not travel to the GPU box); used by
+``oracle/make_golden.py`` to generate the committed fixtures and by the optional local
+cross-check in ``tests/test_oracle.py``. Import recipe: SURVEY.md section 8(c).
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.util
+import json
+import os
+import sys
+import types
+
+REF = os.environ.get("FMM_REFERENCE_ROOT", "/root/reference")
+F2 = os.path.join(REF, "Fall_2_Spatial_Temporal_SR")
+
+
+def available() -> bool:
+    return os.path.isdir(F2)
+
+
+def load_gstcan():
+    """Returns (stgcan, graph, bilstm, combination) reference modules."""
+    if F2 not in sys.path:
+        sys.path.insert(0, F2)
+    stg = importlib.import_module("Model.stgcan")
+    g = importlib.import_module("Model.graph")
+    bl = importlib.import_module("Model.bilstm")
+    shim = types.ModuleType("Model.st_gcn")
+    shim.__path__ = []
+    sys.modules.update({"Model.st_gcn": shim, "Model.st_gcn.stgcan": stg, "Model.st_gcn.graph": g})
+    comb = importlib.import_module("Model.combination")
+    return stg, g, bl, comb
+
+
+def install_layout(stg, g, name, num_node, neighbor_link, center):
+    """Teach the reference Graph an extra layout by subclassing it."""
+    base = g.Graph
+
+    class GraphX(base):
+        def get_edge(self, layout):
+            if layout == name:
+                self.num_node = num_node
+                self.edge = [(i, i) for i in range(num_node)] + list(neighbor_link)
+                self.center = center
+            else:
+                base.get_edge(self, layout)
+
+    stg.Graph = GraphX
+    return GraphX
+
+
+def load_notebook_sensor():
+    """exec() the sensor-branch cell of the notebook: CNN1D, BiLSTM, CNN_BiLSTM classes."""
+    nb = json.load(open(os.path.join(REF, "GSTCAN_HAR_conv_10kfold.ipynb")))
+    ns: dict = {}
+    exec("".join(nb["cells"][2]["source"]), ns)
+    return ns

@@ -1,0 +1,6 @@
+"""fall_multimodal_b200 — B200-native (sm_100a) training/inference step of the ST-GCN fall/HAR
+classifiers of musaru/Fall_Multimodal, behind the reference's PyTorch module API."""
+from .graph import Graph, register_layout  # noqa: F401
+from .stgcan import STGCAN, Channel_Attention, GraphConvolution, st_gcan  # noqa: F401
+
+__all__ = ["Graph", "register_layout", "STGCAN", "st_gcan", "GraphConvolution", "Channel_Attention"]

@@ -1,0 +1,609 @@
+// Memory-bound kernels of the ST-GCN block (everything that touches a full activation but is not
+// a GEMM): adjacency aggregation, BatchNorm/SE statistics, the fused block output, and the
+// elementwise halves of the BatchNorm / ReLU / SE / residual backward.
+//
+// Layout: activations are channels-last [N][T][V][C]; a frame (one n,t) is V*C contiguous
+// elements. All kernels use the same mapping: grid = (time chunks, N); inside a block a thread
+// owns a fixed (v, 8-channel group) "pair" and walks over the frames of its chunk, so global
+// accesses are perfectly coalesced 16/32-byte vectors and per-channel coefficients stay in
+// registers. Reductions over frames are kept in registers, reduced across the block in shared
+// memory and committed with one atomic per (block, output element).
+//
+// Reference call sites: /root/reference/Fall_2_Spatial_Temporal_SR/Model/stgcan.py
+//   :54 (einsum nkctv,kvw->nctw, reassociated onto the input), :63-73 (SE pooling and scale),
+//   :112-119 (BatchNorm2d/ReLU around the temporal conv), :138-144 (attention, residual, ReLU).
+#include "common.cuh"
+
+namespace fmm {
+
+constexpr int kEwThreads = 256;
+
+__device__ __forceinline__ void atomic_add_f64(double* p, double v) { atomicAdd(p, v); }
+
+// ------------------------------------------------------------------------------------------
+// agg_fwd:  Xa[(n,t,w), k*Cin+ci] = sum_{e in in(k,w)} coef[e] * x[(n,t,src[e]), ci]
+// CSR over (k,w): rowptr[K*V+1], src[E], coef[E].
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void agg_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ xa, const int* __restrict__ rowptr,
+                                   const int* __restrict__ src, const float* __restrict__ coef, int Tn, int V,
+                                   int Cin, int K, int tchunk) {
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  const int c8n = Cin / 8;
+  const int pairs = V * K * c8n;
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+    const int c8 = i % c8n;
+    const int k = (i / c8n) % K;
+    const int w = i / (c8n * K);
+    const int e0 = rowptr[k * V + w], e1 = rowptr[k * V + w + 1];
+    for (int t = t0; t < t1; ++t) {
+      const size_t frame = static_cast<size_t>(n) * Tn + t;
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int e = e0; e < e1; ++e) {
+        float f[8];
+        load8(x + (frame * V + src[e]) * Cin + c8 * 8, f);
+        const float cf = coef[e];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(cf, f[j], acc[j]);
+      }
+      store8(xa + (frame * V + w) * (static_cast<size_t>(K) * Cin) + k * Cin + c8 * 8, acc);
+    }
+  }
+}
+
+template <typename T>
+__global__ void agg_fwd_scalar_kernel(const T* __restrict__ x, T* __restrict__ xa, const int* __restrict__ rowptr,
+                                      const int* __restrict__ src, const float* __restrict__ coef, int Tn, int V,
+                                      int Cin, int K, int tchunk) {
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  const int per_frame = V * K * Cin;
+  const int total = (t1 - t0) * per_frame;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int t = t0 + i / per_frame;
+    const int r = i % per_frame;
+    const int ci = r % Cin;
+    const int k = (r / Cin) % K;
+    const int w = r / (Cin * K);
+    const size_t frame = static_cast<size_t>(n) * Tn + t;
+    float acc = 0.f;
+    for (int e = rowptr[k * V + w]; e < rowptr[k * V + w + 1]; ++e)
+      acc = fmaf(coef[e], to_f32(x[(frame * V + src[e]) * Cin + ci]), acc);
+    xa[(frame * V + w) * (static_cast<size_t>(K) * Cin) + k * Cin + ci] = from_f32<T>(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// agg_bwd: dx[(n,t,v), ci] = addend + sum_{e in out(v)} coef[e] * P[(n,t,dst[e]), kk[e]*Cin+ci]
+// CSR over v: rowptr[V+1], dst[E], kk[E], coef[E].
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void agg_bwd_vec_kernel(const T* __restrict__ P, const T* __restrict__ addend, T* __restrict__ dx,
+                                   const int* __restrict__ rowptr, const int* __restrict__ dst,
+                                   const int* __restrict__ kk, const float* __restrict__ coef, int Tn, int V,
+                                   int Cin, int K, int tchunk) {
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  const int c8n = Cin / 8;
+  const int pairs = V * c8n;
+  const size_t prow = static_cast<size_t>(K) * Cin;
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+    const int c8 = i % c8n;
+    const int v = i / c8n;
+    const int e0 = rowptr[v], e1 = rowptr[v + 1];
+    for (int t = t0; t < t1; ++t) {
+      const size_t frame = static_cast<size_t>(n) * Tn + t;
+      float acc[8];
+      if (addend) {
+        load8(addend + (frame * V + v) * Cin + c8 * 8, acc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      }
+      for (int e = e0; e < e1; ++e) {
+        float f[8];
+        load8(P + (frame * V + dst[e]) * prow + kk[e] * Cin + c8 * 8, f);
+        const float cf = coef[e];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(cf, f[j], acc[j]);
+      }
+      store8(dx + (frame * V + v) * Cin + c8 * 8, acc);
+    }
+  }
+}
+
+template <typename T>
+__global__ void agg_bwd_scalar_kernel(const T* __restrict__ P, const T* __restrict__ addend, T* __restrict__ dx,
+                                      const int* __restrict__ rowptr, const int* __restrict__ dst,
+                                      const int* __restrict__ kk, const float* __restrict__ coef, int Tn, int V,
+                                      int Cin, int K, int tchunk) {
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  const int per_frame = V * Cin;
+  const int total = (t1 - t0) * per_frame;
+  const size_t prow = static_cast<size_t>(K) * Cin;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int t = t0 + i / per_frame;
+    const int r = i % per_frame;
+    const int ci = r % Cin;
+    const int v = r / Cin;
+    const size_t frame = static_cast<size_t>(n) * Tn + t;
+    float acc = addend ? to_f32(addend[(frame * V + v) * Cin + ci]) : 0.f;
+    for (int e = rowptr[v]; e < rowptr[v + 1]; ++e)
+      acc = fmaf(coef[e], to_f32(P[(frame * V + dst[e]) * prow + kk[e] * Cin + ci]), acc);
+    dx[(frame * V + v) * Cin + ci] = from_f32<T>(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// agg_dcoef: dcoef[e] += sum_{n,t,ci} x[(n,t,src[e]),ci] * P[(n,t,dst[e]), kk[e]*Cin+ci]
+// (edge lists in any order). One warp per (edge, frame range); lanes stride the channels.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void agg_dcoef_kernel(const T* __restrict__ x, const T* __restrict__ P, float* __restrict__ dcoef,
+                                 const int* __restrict__ src, const int* __restrict__ dst,
+                                 const int* __restrict__ kk, int E, int Tn, int V, int Cin, int K, int tchunk) {
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const size_t prow = static_cast<size_t>(K) * Cin;
+  for (int e = warp; e < E; e += nwarps) {
+    const int v = src[e], w = dst[e], k = kk[e];
+    float acc = 0.f;
+    for (int t = t0; t < t1; ++t) {
+      const size_t frame = static_cast<size_t>(n) * Tn + t;
+      const T* xr = x + (frame * V + v) * Cin;
+      const T* pr = P + (frame * V + w) * prow + static_cast<size_t>(k) * Cin;
+      for (int ci = lane; ci < Cin; ci += 32) acc = fmaf(to_f32(xr[ci]), to_f32(pr[ci]), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(dcoef + e, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Block-wide reduction helper: every thread holds NV partial values for channel group c8 of
+// pair i (pairs i = v*c8n + c8). Sums over v (and the block's strided pairs) are done through
+// shared memory: red[c8n*8][NV].
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void smem_accumulate(float* red, int c, const float (&val)[NV]) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) atomicAdd(red + c * NV + j, val[j]);
+}
+
+// colstats: per-channel sum / sum of squares (double) and optional per-(n,c) sums (float) of X.
+template <typename T>
+__global__ void colstats_kernel(const T* __restrict__ X, double* __restrict__ ch_sum, double* __restrict__ ch_sq,
+                                float* __restrict__ nc_sum, int Tn, int V, int C, int tchunk) {
+  extern __shared__ float red[];  // [C][2]
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int c8n = C / 8;
+  const int pairs = V * c8n;
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+    const int c8 = i % c8n;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = t0; t < t1; ++t) {
+      float f[8];
+      load8(X + (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] = fmaf(f[j], f[j], q[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(red + (c8 * 8 + j) * 2, s[j]);
+      atomicAdd(red + (c8 * 8 + j) * 2 + 1, q[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float s = red[2 * c], q = red[2 * c + 1];
+    if (ch_sum) atomic_add_f64(ch_sum + c, static_cast<double>(s));
+    if (ch_sq) atomic_add_f64(ch_sq + c, static_cast<double>(q));
+    if (nc_sum) atomicAdd(nc_sum + static_cast<size_t>(n) * C + c, s);
+  }
+}
+
+// block_out: y = relu(k1[n,c]*U + k0[n,c] + res), res = 0 | X | ar[c]*R + br[c]
+template <typename T>
+__global__ void block_out_kernel(const T* __restrict__ U, const float* __restrict__ k1, const float* __restrict__ k0,
+                                 const T* __restrict__ res, const float* __restrict__ ar,
+                                 const float* __restrict__ br, T* __restrict__ Y, int Tn, int V, int C, int tchunk) {
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  const int c8n = C / 8;
+  const int pairs = V * c8n;
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+    const int c0 = (i % c8n) * 8;
+    float a[8], b[8], ra[8], rb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = k1[static_cast<size_t>(n) * C + c0 + j];
+      b[j] = k0[static_cast<size_t>(n) * C + c0 + j];
+      ra[j] = ar ? ar[c0 + j] : 1.f;
+      rb[j] = br ? br[c0 + j] : 0.f;
+    }
+    for (int t = t0; t < t1; ++t) {
+      const size_t off = (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8;
+      float u[8], r[8], y[8];
+      load8(U + off, u);
+      if (res) load8(res + off, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = fmaf(a[j], u[j], b[j]);
+        if (res) v += fmaf(ra[j], r[j], rb[j]);
+        y[j] = fmaxf(v, 0.f);
+      }
+      store8(Y + off, y);
+    }
+  }
+}
+
+// blockout_bwd_reduce: dpre = dY*(Y>0); S1[n,c]=sum dpre; S2[n,c]=sum dpre*U; S3[n,c]=sum dpre*R
+template <typename T>
+__global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ U,
+                                           const T* __restrict__ R, float* __restrict__ S1, float* __restrict__ S2,
+                                           float* __restrict__ S3, int Tn, int V, int C, int tchunk) {
+  extern __shared__ float red[];  // [C][3]
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int c8n = C / 8;
+  const int pairs = V * c8n;
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+    const int c0 = (i % c8n) * 8;
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s3[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = t0; t < t1; ++t) {
+      const size_t off = (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8;
+      float g[8], y[8], u[8], r[8];
+      load8(dY + off, g);
+      load8(Y + off, y);
+      load8(U + off, u);
+      if (R) load8(R + off, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = y[j] > 0.f ? g[j] : 0.f;
+        s1[j] += d;
+        s2[j] = fmaf(d, u[j], s2[j]);
+        if (R) s3[j] = fmaf(d, r[j], s3[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(red + (c0 + j) * 3, s1[j]);
+      atomicAdd(red + (c0 + j) * 3 + 1, s2[j]);
+      if (R) atomicAdd(red + (c0 + j) * 3 + 2, s3[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(S1 + static_cast<size_t>(n) * C + c, red[3 * c]);
+    atomicAdd(S2 + static_cast<size_t>(n) * C + c, red[3 * c + 1]);
+    if (R) atomicAdd(S3 + static_cast<size_t>(n) * C + c, red[3 * c + 2]);
+  }
+}
+
+// bn2_bwd_apply: dpre = dY*(Y>0)
+//   dU = k1[n,c]*dpre + k2[c]*U + k3[n,c]        (always)
+//   dR = r1[c]*dpre + r2[c]*R + r3[c]            (if R)
+//   dPre = dpre                                   (if dPre: identity residual)
+//   colsum_dU[c] += sum dU (as stored), colsum_dR[c] += sum dR   (optional, double)
+template <typename T>
+__global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ U,
+                                     const T* __restrict__ R, const float* __restrict__ k1,
+                                     const float* __restrict__ k2, const float* __restrict__ k3,
+                                     const float* __restrict__ r1, const float* __restrict__ r2,
+                                     const float* __restrict__ r3, T* __restrict__ dU, T* __restrict__ dR,
+                                     T* __restrict__ dPre, double* __restrict__ sum_dU,
+                                     double* __restrict__ sum_dR, int Tn, int V, int C, int tchunk) {
+  extern __shared__ float red[];  // [C][2]
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int c8n = C / 8;
+  const int pairs = V * c8n;
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+    const int c0 = (i % c8n) * 8;
+    float a1[8], a2[8], a3[8], b1[8], b2[8], b3[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a1[j] = k1[static_cast<size_t>(n) * C + c0 + j];
+      a2[j] = k2[c0 + j];
+      a3[j] = k3[static_cast<size_t>(n) * C + c0 + j];
+      b1[j] = R ? r1[c0 + j] : 0.f;
+      b2[j] = R ? r2[c0 + j] : 0.f;
+      b3[j] = R ? r3[c0 + j] : 0.f;
+    }
+    float su[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = t0; t < t1; ++t) {
+      const size_t off = (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8;
+      float g[8], y[8], u[8], r[8], ou[8], orr[8], d[8];
+      load8(dY + off, g);
+      load8(Y + off, y);
+      load8(U + off, u);
+      if (R) load8(R + off, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d[j] = y[j] > 0.f ? g[j] : 0.f;
+        ou[j] = fmaf(a1[j], d[j], fmaf(a2[j], u[j], a3[j]));
+        su[j] += to_f32(from_f32<T>(ou[j]));
+        if (R) {
+          orr[j] = fmaf(b1[j], d[j], fmaf(b2[j], r[j], b3[j]));
+          sr[j] += to_f32(from_f32<T>(orr[j]));
+        }
+      }
+      store8(dU + off, ou);
+      if (R) store8(dR + off, orr);
+      if (dPre) store8(dPre + off, d);
+    }
+    if (sum_dU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(red + (c0 + j) * 2, su[j]);
+    }
+    if (sum_dR) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(red + (c0 + j) * 2 + 1, sr[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (sum_dU) atomic_add_f64(sum_dU + c, static_cast<double>(red[2 * c]));
+    if (sum_dR) atomic_add_f64(sum_dR + c, static_cast<double>(red[2 * c + 1]));
+  }
+}
+
+// bn1_bwd_reduce: y1 = a1*G+b1; dy1 = dH*(y1>0); T1[c] += sum dy1; T2[c] += sum dy1*G
+template <typename T>
+__global__ void bn1_bwd_reduce_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
+                                      const float* __restrict__ b1, double* __restrict__ T1,
+                                      double* __restrict__ T2, int Tn, int V, int C, int tchunk) {
+  extern __shared__ float red[];  // [C][2]
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int c8n = C / 8;
+  const int pairs = V * c8n;
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+    const int c0 = (i % c8n) * 8;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = a1[c0 + j];
+      b[j] = b1[c0 + j];
+    }
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = t0; t < t1; ++t) {
+      const size_t off = (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8;
+      float g[8], h[8];
+      load8(dH + off, h);
+      load8(G + off, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = fmaf(a[j], g[j], b[j]) > 0.f ? h[j] : 0.f;
+        s1[j] += d;
+        s2[j] = fmaf(d, g[j], s2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(red + (c0 + j) * 2, s1[j]);
+      atomicAdd(red + (c0 + j) * 2 + 1, s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomic_add_f64(T1 + c, static_cast<double>(red[2 * c]));
+    atomic_add_f64(T2 + c, static_cast<double>(red[2 * c + 1]));
+  }
+}
+
+// bn1_bwd_apply: dG = c1[c]*dy1 + c2[c]*G + c3[c]  (dy1 as above); Tbl[v][c] += sum_{n,t} dG
+template <typename T>
+__global__ void bn1_bwd_apply_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
+                                     const float* __restrict__ b1, const float* __restrict__ c1,
+                                     const float* __restrict__ c2, const float* __restrict__ c3, T* __restrict__ dG,
+                                     float* __restrict__ Tbl, int Tn, int V, int C, int tchunk) {
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tchunk;
+  const int t1 = min(t0 + tchunk, Tn);
+  const int c8n = C / 8;
+  const int pairs = V * c8n;
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+    const int c0 = (i % c8n) * 8;
+    float a[8], b[8], k1[8], k2[8], k3[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = a1[c0 + j];
+      b[j] = b1[c0 + j];
+      k1[j] = c1[c0 + j];
+      k2[j] = c2[c0 + j];
+      k3[j] = c3[c0 + j];
+    }
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = t0; t < t1; ++t) {
+      const size_t off = (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8;
+      float g[8], h[8], o[8];
+      load8(dH + off, h);
+      load8(G + off, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = fmaf(a[j], g[j], b[j]) > 0.f ? h[j] : 0.f;
+        o[j] = fmaf(k1[j], d, fmaf(k2[j], g[j], k3[j]));
+        acc[j] += to_f32(from_f32<T>(o[j]));
+      }
+      store8(dG + off, o);
+    }
+    if (Tbl) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(Tbl + static_cast<size_t>(i) * 8 + j, acc[j]);
+    }
+  }
+}
+
+static inline int pick_tchunk(int N, int Tn) {
+  // enough blocks to fill the machine a few times over, but long enough frame walks per thread
+  int chunk = Tn;
+  while (chunk > 4 && static_cast<long long>(N) * ((Tn + chunk - 1) / chunk) < 4LL * num_sms()) chunk = (chunk + 1) / 2;
+  return chunk;
+}
+
+}  // namespace fmm
+
+using namespace fmm;
+
+#define FMM_DISPATCH(dtype, ...)                          \
+  if ((dtype) == FMM_DT_BF16) {                           \
+    using T = __nv_bfloat16;                              \
+    __VA_ARGS__                                           \
+  } else if ((dtype) == FMM_DT_F32) {                     \
+    using T = float;                                      \
+    __VA_ARGS__                                           \
+  } else {                                                \
+    fmm::set_last_error("bad dtype %d", (int)(dtype));    \
+    return FMM_ERR_ARG;                                   \
+  }
+
+extern "C" {
+
+int fmm_agg_fwd(const void* x, void* xa, const int* rowptr, const int* src, const float* coef, int N, int Tn,
+                int V, int Cin, int K, int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(x && xa && rowptr && src && coef && N > 0 && Tn > 0 && V > 0 && Cin > 0 && K > 0, "agg_fwd: bad args");
+  const int tchunk = pick_tchunk(N, Tn);
+  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  FMM_DISPATCH(dtype, {
+    if (Cin % 8 == 0)
+      agg_fwd_vec_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)x, (T*)xa, rowptr, src, coef, Tn, V, Cin, K, tchunk);
+    else
+      agg_fwd_scalar_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)x, (T*)xa, rowptr, src, coef, Tn, V, Cin, K, tchunk);
+  })
+  FMM_CHECK_LAUNCH("agg_fwd");
+  return FMM_OK;
+}
+
+int fmm_agg_bwd(const void* P, const void* addend, void* dx, const int* rowptr, const int* dst, const int* kk,
+                const float* coef, int N, int Tn, int V, int Cin, int K, int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(P && dx && rowptr && dst && kk && coef && N > 0 && Tn > 0 && V > 0 && Cin > 0 && K > 0, "agg_bwd: bad args");
+  const int tchunk = pick_tchunk(N, Tn);
+  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  FMM_DISPATCH(dtype, {
+    if (Cin % 8 == 0)
+      agg_bwd_vec_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)P, (const T*)addend, (T*)dx, rowptr, dst, kk, coef, Tn, V, Cin, K, tchunk);
+    else
+      agg_bwd_scalar_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)P, (const T*)addend, (T*)dx, rowptr, dst, kk, coef, Tn, V, Cin, K, tchunk);
+  })
+  FMM_CHECK_LAUNCH("agg_bwd");
+  return FMM_OK;
+}
+
+int fmm_agg_dcoef(const void* x, const void* P, float* dcoef, const int* src, const int* dst, const int* kk, int E,
+                  int N, int Tn, int V, int Cin, int K, int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(x && P && dcoef && src && dst && kk && E > 0 && N > 0 && Tn > 0, "agg_dcoef: bad args");
+  const int tchunk = pick_tchunk(N, Tn);
+  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  FMM_DISPATCH(dtype, {
+    agg_dcoef_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)x, (const T*)P, dcoef, src, dst, kk, E, Tn, V, Cin, K, tchunk);
+  })
+  FMM_CHECK_LAUNCH("agg_dcoef");
+  return FMM_OK;
+}
+
+int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, int N, int Tn, int V, int C, int dtype,
+                 cudaStream_t stream) {
+  FMM_CHECK_ARG(X && N > 0 && Tn > 0 && V > 0 && C > 0 && C % 8 == 0, "colstats: bad args (C must be a multiple of 8)");
+  const int tchunk = pick_tchunk(N, Tn);
+  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  FMM_DISPATCH(dtype, {
+    colstats_kernel<T><<<grid, kEwThreads, 2 * C * sizeof(float), stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, Tn, V, C, tchunk);
+  })
+  FMM_CHECK_LAUNCH("colstats");
+  return FMM_OK;
+}
+
+int fmm_block_out(const void* U, const float* k1, const float* k0, const void* res, const float* ar, const float* br,
+                  void* Y, int N, int Tn, int V, int C, int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(U && k1 && k0 && Y && C % 8 == 0, "block_out: bad args");
+  const int tchunk = pick_tchunk(N, Tn);
+  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  FMM_DISPATCH(dtype, {
+    block_out_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)U, k1, k0, (const T*)res, ar, br, (T*)Y, Tn, V, C, tchunk);
+  })
+  FMM_CHECK_LAUNCH("block_out");
+  return FMM_OK;
+}
+
+int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const void* R, float* S1, float* S2,
+                            float* S3, int N, int Tn, int V, int C, int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(dY && Y && U && S1 && S2 && C % 8 == 0 && (!R || S3), "blockout_bwd_reduce: bad args");
+  const int tchunk = pick_tchunk(N, Tn);
+  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  FMM_DISPATCH(dtype, {
+    blockout_bwd_reduce_kernel<T><<<grid, kEwThreads, 3 * C * sizeof(float), stream>>>(
+        (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, S1, S2, S3, Tn, V, C, tchunk);
+  })
+  FMM_CHECK_LAUNCH("blockout_bwd_reduce");
+  return FMM_OK;
+}
+
+int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* R, const float* k1, const float* k2,
+                      const float* k3, const float* r1, const float* r2, const float* r3, void* dU, void* dR,
+                      void* dPre, double* sum_dU, double* sum_dR, int N, int Tn, int V, int C, int dtype,
+                      cudaStream_t stream) {
+  FMM_CHECK_ARG(dY && Y && U && k1 && k2 && k3 && dU && C % 8 == 0, "bn2_bwd_apply: bad args");
+  FMM_CHECK_ARG(!R || (r1 && r2 && r3 && dR), "bn2_bwd_apply: residual branch needs r1..r3 and dR");
+  const int tchunk = pick_tchunk(N, Tn);
+  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  FMM_DISPATCH(dtype, {
+    bn2_bwd_apply_kernel<T><<<grid, kEwThreads, 2 * C * sizeof(float), stream>>>(
+        (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, k1, k2, k3, r1, r2, r3, (T*)dU, (T*)dR, (T*)dPre, sum_dU,
+        sum_dR, Tn, V, C, tchunk);
+  })
+  FMM_CHECK_LAUNCH("bn2_bwd_apply");
+  return FMM_OK;
+}
+
+int fmm_bn1_bwd_reduce(const void* dH, const void* G, const float* a1, const float* b1, double* T1, double* T2, int N,
+                       int Tn, int V, int C, int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(dH && G && a1 && b1 && T1 && T2 && C % 8 == 0, "bn1_bwd_reduce: bad args");
+  const int tchunk = pick_tchunk(N, Tn);
+  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  FMM_DISPATCH(dtype, {
+    bn1_bwd_reduce_kernel<T><<<grid, kEwThreads, 2 * C * sizeof(float), stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, Tn, V, C, tchunk);
+  })
+  FMM_CHECK_LAUNCH("bn1_bwd_reduce");
+  return FMM_OK;
+}
+
+int fmm_bn1_bwd_apply(const void* dH, const void* G, const float* a1, const float* b1, const float* c1,
+                      const float* c2, const float* c3, void* dG, float* Tbl, int N, int Tn, int V, int C, int dtype,
+                      cudaStream_t stream) {
+  FMM_CHECK_ARG(dH && G && a1 && b1 && c1 && c2 && c3 && dG && C % 8 == 0, "bn1_bwd_apply: bad args");
+  const int tchunk = pick_tchunk(N, Tn);
+  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  FMM_DISPATCH(dtype, {
+    bn1_bwd_apply_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)dH, (const T*)G, a1, b1, c1, c2, c3, (T*)dG, Tbl, Tn, V, C, tchunk);
+  })
+  FMM_CHECK_LAUNCH("bn1_bwd_apply");
+  return FMM_OK;
+}
+
+}  // extern "C"

@@ -33,6 +33,7 @@ struct TapConvParams {
   const float* in_scale;
   const float* in_shift;
   const float* bias;
+  int bias_vstride;  // 0: bias[co]; Cout: bias[v][co] (per-joint bias of the reassociated graph conv)
   int in_relu;
   int N, V, Tin, Tout, Cin, Cout;
   int Tj, istride, ostride, ooff;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int co = co0 + g * 8 + i;
-              float b = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
+              float b = (p.bias && co < p.Cout) ? p.bias[v * p.bias_vstride + co] : 0.f;
               f[i] = __uint_as_float(acc[g * 8 + i]) + b;
             }
             const int co = co0 + g * 8;
@@ -440,7 +441,7 @@ int fmm_tapconv_pack(const float* w, void* out, int cout, int cin, int n2, int k
 }
 
 int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale,
-                const float* in_shift, int in_relu, const float* bias, int N, int V, int Tin,
+                const float* in_shift, int in_relu, const float* bias, int bias_per_joint, int N, int V, int Tin,
                 int Tout, int Cin, int Cout, int Tj, int istride, int ostride, int ooff, int ntaps,
                 const int* shifts, int dtype, unsigned* err, cudaStream_t stream) {
   FMM_CHECK_ARG(x && out && wpk, "tapconv: null pointer");
@@ -456,6 +457,7 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   p.in_scale = in_scale;
   p.in_shift = in_shift;
   p.bias = bias;
+  p.bias_vstride = bias_per_joint ? Cout : 0;
   p.in_relu = in_relu;
   p.N = N;
   p.V = V;

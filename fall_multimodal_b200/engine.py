@@ -1,0 +1,334 @@
+"""Kernel sequencing for one GSTCAN trunk: forward and hand-written backward.
+
+This is the host-side mirror of ``STGCAN.forward`` (``/root/reference/Fall_2_Spatial_Temporal_SR/
+Model/stgcan.py:210-228``) and of what autograd would do for it, expressed as launches of the
+C-ABI kernels (csrc/*.cu). Per block (stgcan.py:138-144):
+
+    Xa = aggregate(x, A*importance)           agg_fwd           (einsum :54, reassociated onto the input)
+    G  = Xa @ Wg + bias_eff[v]                tapconv 1x1       (conv :51)
+    U  = conv9x1(relu(bn1(G)), stride)        colstats + bn_finalize + tapconv (BN/ReLU in the prologue)
+    s  = SE(mean_tv(bn2(U)))                  colstats(+pool) + bn_finalize + se_fwd
+    y  = relu(s*bn2(U) + res)                 block_out         (res: none | x | bn_r(conv1x1_s(x)))
+
+All tensors are allocated by PyTorch; the kernels only see raw pointers. Tiny once-per-step glue
+(data_bn on the 3-channel input, the adjacency coefficient prep, the classifier head) is torch.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .graph import adjacency_csr
+
+BLOCK_PLAN = [(None, 64, 1, "none"), (64, 64, 1, "identity"), (64, 64, 1, "identity"), (64, 128, 2, "conv"),
+              (128, 128, 1, "identity"), (128, 256, 2, "conv"), (256, 256, 1, "identity")]
+EPS = 1e-5
+MOMENTUM = 0.1
+
+
+class _Arena:
+    """One zero-filled fp64 and one fp32 buffer per pass, carved into accumulators (one memset each)."""
+
+    def __init__(self, device, n64, n32):
+        self.b64 = torch.zeros(n64, dtype=torch.float64, device=device)
+        self.b32 = torch.zeros(n32, dtype=torch.float32, device=device)
+        self.o64 = 0
+        self.o32 = 0
+
+    def f64(self, n):
+        out = self.b64[self.o64:self.o64 + n]
+        self.o64 += n
+        assert self.o64 <= self.b64.numel()
+        return out
+
+    def f32(self, *shape):
+        n = 1
+        for s in shape:
+            n *= s
+        out = self.b32[self.o32:self.o32 + n]
+        self.o32 += (n + 3) // 4 * 4
+        assert self.o32 <= self.b32.numel()
+        return out.view(*shape)
+
+
+class TrunkEngine:
+    """Static plan of one trunk: block shapes and the sparse adjacency, per device."""
+
+    def __init__(self, A: torch.Tensor, in_channels: int, block_key: str = "st_gcan_networks"):
+        self.K, self.V, _ = A.shape
+        self.in_channels = in_channels
+        self.block_key = block_key
+        self.blocks = [(in_channels if cin is None else cin, cout, s, res) for cin, cout, s, res in BLOCK_PLAN]
+        self._csr_np = adjacency_csr(A.detach().cpu().double().numpy())
+        self.E = len(self._csr_np["fwd_src"])
+        self._dev = {}
+
+    def csr(self, device):
+        key = str(device)
+        if key not in self._dev:
+            c = self._csr_np
+            t = lambda a, dt=torch.int32: torch.as_tensor(a).to(device=device, dtype=dt)
+            d = {"fwd_rowptr": t(c["fwd_rowptr"]), "fwd_src": t(c["fwd_src"]), "dst": t(c["dst"]), "kk": t(c["kk"]),
+                 "dense_idx": t(c["dense_idx"], torch.int64), "bwd_rowptr": t(c["bwd_rowptr"]),
+                 "bwd_perm": t(c["bwd_perm"], torch.int64)}
+            d["dst_b"] = d["dst"][d["bwd_perm"]].contiguous()
+            d["kk_b"] = d["kk"][d["bwd_perm"]].contiguous()
+            self._dev[key] = d
+        return self._dev[key]
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, P: dict, skel: torch.Tensor, training: bool, dt: torch.dtype, need_grad: bool):
+        """Returns (pooled feature (N,256) fp32, saved-state dict for backward)."""
+        dev = skel.device
+        N, C, T, V = skel.shape
+        assert C == self.in_channels and V == self.V, "input does not match the trunk's channels / joints"
+        K = self.K
+        csr = self.csr(dev)
+        A = P["A"]
+        arena = _Arena(dev, 16384, 8 * N * 256 + 4096)
+        sv = {"blocks": [], "N": N, "dt": dt, "training": training}
+
+        # ---- data_bn (stgcan.py:213-218): per-(v,c) BatchNorm1d over (N,T); tiny, torch ----
+        g0 = P["data_bn.weight"].view(V, C)
+        be0 = P["data_bn.bias"].view(V, C)
+        xp = skel.float().permute(0, 2, 3, 1)  # (N,T,V,C) view
+        if training:
+            var, mean = torch.var_mean(xp, dim=(0, 1), unbiased=False)
+            cnt = N * T
+            with torch.no_grad():
+                P["data_bn.running_mean"].mul_(1 - MOMENTUM).add_(mean.flatten(), alpha=MOMENTUM)
+                P["data_bn.running_var"].mul_(1 - MOMENTUM).add_(var.flatten() * (cnt / max(cnt - 1, 1)), alpha=MOMENTUM)
+        else:
+            mean = P["data_bn.running_mean"].view(V, C)
+            var = P["data_bn.running_var"].view(V, C)
+        rstd0 = (var + EPS).rsqrt()
+        a0 = g0 * rstd0
+        x = (xp * a0 + (be0 - mean * a0)).to(dt).contiguous()
+        sv["data_bn"] = (xp, mean, rstd0)
+
+        for i, (Cin, Cout, s, reskind) in enumerate(self.blocks):
+            pre = f"{self.block_key}.{i}."
+            b = {"T": T}
+            imp = P[f"edge_importance.{i}"]
+            Ahat = A * imp
+            coef_f = Ahat.flatten()[csr["dense_idx"]].contiguous()
+            colsum = Ahat.sum(1)                                   # (K, V): sum over source joints
+            bg = P[pre + "gcn.conv.bias"].view(K, Cout)
+            bias_eff = (colsum.t() @ bg).contiguous()              # (V, Cout)
+            Wg = P[pre + "gcn.conv.weight"]
+            Xa = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
+            ops.agg_fwd(x, Xa, csr["fwd_rowptr"], csr["fwd_src"], coef_f, K)
+            pw_g = ops.tapconv_pack(Wg, Cout, K * Cin, Cout, Cin, 0, Cin, Cout * Cin, 1, 0, [0], dt)
+            G = torch.empty(N, T, V, Cout, dtype=dt, device=dev)
+            ops.tapconv(Xa, pw_g, G, shifts=[0], tj=T, bias=bias_eff, bias_per_joint=True)
+
+            # BN1 statistics (stgcan.py:112), applied inside the temporal conv's prologue
+            a1, b1, mean1, rstd1 = (torch.empty(Cout, dtype=torch.float32, device=dev) for _ in range(4))
+            st = arena.f64(2 * Cout)
+            if training:
+                ops.colstats(G, st[:Cout], st[Cout:])
+            ops.bn_finalize(st[:Cout], st[Cout:], N * T * V, P[pre + "tcn.0.weight"], P[pre + "tcn.0.bias"],
+                            P[pre + "tcn.0.running_mean"], P[pre + "tcn.0.running_var"], training, a1, b1, mean1, rstd1)
+
+            # temporal conv 9x1 (stgcan.py:114-118)
+            To = (T - 1) // s + 1
+            Wt = P[pre + "tcn.2.weight"]
+            pw_t = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, Cout * 9, 0, 9, 1, list(range(9)), dt)
+            U = torch.empty(N, To, V, Cout, dtype=dt, device=dev)
+            ops.tapconv(G, pw_t, U, shifts=list(range(-4, 5)), tj=To, istride=s, in_scale=a1, in_shift=b1,
+                        in_relu=True, bias=P[pre + "tcn.2.bias"])
+
+            # BN2 statistics (:119) + SE pooling (:64) in one pass over U
+            a2, b2, mean2, rstd2 = (torch.empty(Cout, dtype=torch.float32, device=dev) for _ in range(4))
+            st2 = arena.f64(2 * Cout)
+            pool = arena.f32(N, Cout)
+            if training:
+                ops.colstats(U, st2[:Cout], st2[Cout:], pool)
+            else:
+                ops.colstats(U, None, None, pool)
+            ops.bn_finalize(st2[:Cout], st2[Cout:], N * To * V, P[pre + "tcn.3.weight"], P[pre + "tcn.3.bias"],
+                            P[pre + "tcn.3.running_mean"], P[pre + "tcn.3.running_var"], training, a2, b2, mean2, rstd2)
+
+            # squeeze-excite (stgcan.py:63-70)
+            C4 = int(Cout / 4)
+            ca = pre + "channel_attention_module.atten."
+            f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
+            p_, h_, s_, k1, k0 = f32(N, Cout), f32(N, C4), f32(N, Cout), f32(N, Cout), f32(N, Cout)
+            ah, bh, hmean, hrstd = f32(C4), f32(C4), f32(C4), f32(C4)
+            M = To * V
+            ops.se_fwd(pool, a2, b2, 1.0 / M, P[ca + "1.weight"], P[ca + "1.bias"], P[ca + "2.weight"],
+                       P[ca + "2.bias"], P[ca + "2.running_mean"], P[ca + "2.running_var"], training,
+                       P[ca + "4.weight"], P[ca + "4.bias"], p_, h_, ah, bh, hmean, hrstd, s_, k1, k0)
+
+            # residual branch (stgcan.py:123-133)
+            R = ar = br = meanr = rstdr = pw_r = None
+            if reskind == "conv":
+                Wr = P[pre + "residual.0.weight"]
+                pw_r = ops.tapconv_pack(Wr, Cout, Cin, Cout, Cin, 0, Cin, 0, 1, 0, [0], dt)
+                R = torch.empty(N, To, V, Cout, dtype=dt, device=dev)
+                ops.tapconv(x, pw_r, R, shifts=[0], tj=To, istride=s, bias=P[pre + "residual.0.bias"])
+                ar, br, meanr, rstdr = f32(Cout), f32(Cout), f32(Cout), f32(Cout)
+                st3 = arena.f64(2 * Cout)
+                if training:
+                    ops.colstats(R, st3[:Cout], st3[Cout:])
+                ops.bn_finalize(st3[:Cout], st3[Cout:], N * To * V, P[pre + "residual.1.weight"],
+                                P[pre + "residual.1.bias"], P[pre + "residual.1.running_mean"],
+                                P[pre + "residual.1.running_var"], training, ar, br, meanr, rstdr)
+                res = R
+            elif reskind == "identity":
+                res = x
+            else:
+                res = None
+            Y = torch.empty(N, To, V, Cout, dtype=dt, device=dev)
+            ops.block_out(U, k1, k0, res, ar, br, Y)
+
+            if need_grad:
+                b.update(x=x, Xa=Xa, G=G, U=U, R=R, Y=Y, a1=a1, b1=b1, mean1=mean1, rstd1=rstd1, a2=a2, b2=b2,
+                         mean2=mean2, rstd2=rstd2, pool=pool, p=p_, h=h_, s=s_, ah=ah, bh=bh, hmean=hmean,
+                         hrstd=hrstd, ar=ar, meanr=meanr, rstdr=rstdr, coef_f=coef_f, colsum=colsum, To=To)
+                sv["blocks"].append(b)
+            x, T = Y, To
+
+        M = T * V
+        poolY = arena.f32(N, 256)
+        ops.colstats(x, None, None, poolY)
+        feat = poolY / M
+        sv["M_last"], sv["T_last"] = M, T
+        if training:
+            with torch.no_grad():
+                torch._foreach_add_([v for k, v in P.items() if k.endswith("num_batches_tracked")], 1)
+        return feat, sv
+
+    # ------------------------------------------------------------------------------------------
+    def backward(self, P: dict, sv: dict, dfeat: torch.Tensor) -> dict:
+        """dfeat: (N,256) fp32 gradient of the pooled feature. Returns {param name: fp32 gradient}."""
+        dev = dfeat.device
+        N, dt, training = sv["N"], sv["dt"], sv["training"]
+        K, V = self.K, self.V
+        csr = self.csr(dev)
+        A = P["A"]
+        grads = {}
+        arena = _Arena(dev, 32768, 40 * N * 256 + 16 * V * 256 + 7 * 2 * 256 * 64 + 65536)
+        f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
+        z32 = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)
+        dY = (dfeat / sv["M_last"]).to(dt)[:, None, None, :].expand(N, sv["T_last"], V, 256).contiguous()
+
+        for i in reversed(range(len(self.blocks))):
+            Cin, Cout, s, reskind = self.blocks[i]
+            pre = f"{self.block_key}.{i}."
+            b = sv["blocks"][i]
+            T, To = b["T"], b["To"]
+            x, Xa, G, U, R, Y = b["x"], b["Xa"], b["G"], b["U"], b["R"], b["Y"]
+            C4 = int(Cout / 4)
+            M = To * V
+            ca = pre + "channel_attention_module.atten."
+
+            # ---- relu / residual / SE scale: per-(n,c) reductions of dpre = dY*(Y>0) ----
+            S1, S2 = arena.f32(N, Cout), arena.f32(N, Cout)
+            S3 = arena.f32(N, Cout) if R is not None else None
+            ops.blockout_bwd_reduce(dY, Y, U, R, S1, S2, S3)
+
+            # ---- SE backward (tiny) ----
+            dq, dp = f32(N, Cout), f32(N, Cout)
+            dhr, r_, dh = f32(N, C4), f32(N, C4), f32(N, C4)
+            dW1, db1, dgh, dbh = arena.f32(C4, Cout), arena.f32(C4), arena.f32(C4), arena.f32(C4)
+            dW2, db2se = arena.f32(Cout, C4), arena.f32(Cout)
+            ops.se_bwd(S1, S2, b["a2"], b["b2"], b["s"], b["p"], b["h"], b["ah"], b["bh"], b["hmean"], b["hrstd"],
+                       P[ca + "1.weight"], P[ca + "4.weight"], training, dq, dhr, r_, dh, dp, dW1, db1, dgh, dbh,
+                       dW2, db2se)
+            grads[ca + "1.weight"] = dW1.view(C4, Cout, 1, 1)
+            grads[ca + "1.bias"] = db1
+            grads[ca + "2.weight"] = dgh
+            grads[ca + "2.bias"] = dbh
+            grads[ca + "4.weight"] = dW2.view(Cout, C4, 1, 1)
+            grads[ca + "4.bias"] = db2se
+
+            # ---- BN2 (+ residual BN) backward folded into affine coefficients ----
+            k1, k3, k2 = f32(N, Cout), f32(N, Cout), f32(Cout)
+            dg2, db2 = arena.f32(Cout), arena.f32(Cout)
+            r1 = r2 = r3 = dgr = dbr = None
+            if R is not None:
+                r1, r2, r3 = f32(Cout), f32(Cout), f32(Cout)
+                dgr, dbr = arena.f32(Cout), arena.f32(Cout)
+            ops.bn2_bwd_coef(S1, S2, S3, b["pool"], dp, b["s"], b["a2"], b["mean2"], b["rstd2"], b["ar"],
+                             b["meanr"], b["rstdr"], M, N * M, training, k1, k2, k3, r1, r2, r3, dg2, db2, dgr, dbr)
+            grads[pre + "tcn.3.weight"], grads[pre + "tcn.3.bias"] = dg2, db2
+            dU = torch.empty_like(U)
+            dR = torch.empty_like(R) if R is not None else None
+            dPre = torch.empty_like(Y) if reskind == "identity" else None
+            sum_dU = arena.f64(Cout)
+            sum_dR = arena.f64(Cout) if R is not None else None
+            ops.bn2_bwd_apply(dY, Y, U, R, k1, k2, k3, r1, r2, r3, dU, dR, dPre, sum_dU, sum_dR)
+            grads[pre + "tcn.2.bias"] = sum_dU.float()
+
+            # ---- temporal conv: wgrad + dgrad ----
+            Wt = P[pre + "tcn.2.weight"]
+            dWt = z32(Cout, Cout, 9, 1)
+            ops.wgrad(G, dU, dWt, shifts=list(range(-4, 5)), istride=s, in_scale=b["a1"], in_shift=b["b1"],
+                      in_relu=True, s_m=1, s_c2=9, s_co=Cout * 9)
+            grads[pre + "tcn.2.weight"] = dWt
+            dH = torch.empty_like(G)
+            if s == 1:
+                pw = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, 9, 0, Cout * 9, 1, list(range(9)), dt)
+                ops.tapconv(dU, pw, dH, shifts=[4 - m for m in range(9)], tj=T)
+            else:
+                pw = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, 9, 0, Cout * 9, 1, [0, 2, 4, 6, 8], dt)
+                ops.tapconv(dU, pw, dH, shifts=[2, 1, 0, -1, -2], tj=(T + 1) // 2, ostride=2, ooff=0)
+                if T // 2 > 0:
+                    pw = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, 9, 0, Cout * 9, 1, [1, 3, 5, 7], dt)
+                    ops.tapconv(dU, pw, dH, shifts=[2, 1, 0, -1], tj=T // 2, ostride=2, ooff=1)
+
+            # ---- BN1 + ReLU backward ----
+            T1, T2 = arena.f64(Cout), arena.f64(Cout)
+            ops.bn1_bwd_reduce(dH, G, b["a1"], b["b1"], T1, T2)
+            c1, c2, c3 = f32(Cout), f32(Cout), f32(Cout)
+            dg1, db1n = arena.f32(Cout), arena.f32(Cout)
+            ops.bn1_bwd_coef(T1, T2, b["a1"], b["mean1"], b["rstd1"], N * T * V, training, c1, c2, c3, dg1, db1n)
+            grads[pre + "tcn.0.weight"], grads[pre + "tcn.0.bias"] = dg1, db1n
+            dG = torch.empty_like(G)
+            Tbl = arena.f32(V, Cout)
+            ops.bn1_bwd_apply(dH, G, b["a1"], b["b1"], c1, c2, c3, dG, Tbl)
+
+            # ---- graph conv: wgrad, bias, dgrad through the weights, edge importance ----
+            Wg = P[pre + "gcn.conv.weight"]
+            dWg = z32(K * Cout, Cin, 1, 1)
+            ops.wgrad(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
+            grads[pre + "gcn.conv.weight"] = dWg
+            grads[pre + "gcn.conv.bias"] = (b["colsum"] @ Tbl).flatten()
+            pw_gT = ops.tapconv_pack(Wg, K * Cin, Cout, Cin, Cout, Cout * Cin, 1, 0, Cin, 0, [0], dt)
+            Pm = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
+            ops.tapconv(dG, pw_gT, Pm, shifts=[0], tj=T)
+            dcoef = arena.f32(self.E)
+            ops.agg_dcoef(x, Pm, dcoef, csr["fwd_src"], csr["dst"], csr["kk"], K)
+            bg = P[pre + "gcn.conv.bias"].view(K, Cout)
+            dA = torch.zeros(K * V * V, dtype=torch.float32, device=dev)
+            dA[csr["dense_idx"]] = dcoef
+            grads[f"edge_importance.{i}"] = A * (dA.view(K, V, V) + (bg @ Tbl.t())[:, None, :])
+
+            # ---- residual branch ----
+            addend = None
+            if reskind == "identity":
+                addend = dPre
+            elif reskind == "conv":
+                Wr = P[pre + "residual.0.weight"]
+                dWr = z32(Cout, Cin, 1, 1)
+                ops.wgrad(x, dR, dWr, shifts=[0], istride=s, s_m=0, s_c2=1, s_co=Cin)
+                grads[pre + "residual.0.weight"] = dWr
+                grads[pre + "residual.0.bias"] = sum_dR.float()
+                grads[pre + "residual.1.weight"], grads[pre + "residual.1.bias"] = dgr, dbr
+                pw_rT = ops.tapconv_pack(Wr, Cin, Cout, Cin, Cout, 0, 1, 0, Cin, 0, [0], dt)
+                addend = torch.zeros_like(x)
+                ops.tapconv(dR, pw_rT, addend, shifts=[0], tj=To, ostride=s, ooff=0)
+
+            dx = torch.empty_like(x)
+            coef_b = b["coef_f"][csr["bwd_perm"]].contiguous()
+            ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K)
+            dY = dx
+
+        # ---- data_bn backward (input itself needs no gradient) ----
+        xp, mean0, rstd0 = sv["data_bn"]
+        dxf = dY.float()
+        xhat = (xp - mean0) * rstd0
+        grads["data_bn.weight"] = (dxf * xhat).sum((0, 1)).flatten()
+        grads["data_bn.bias"] = dxf.sum((0, 1)).flatten()
+        return grads

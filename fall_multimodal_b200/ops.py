@@ -51,7 +51,7 @@ def tapconv_pack(w: torch.Tensor, cout: int, cin: int, n2: int, k2: int, sn1: in
 
 def tapconv(x: torch.Tensor, pw: PackedWeight, out: torch.Tensor, *, shifts, tj: int,
             istride: int = 1, ostride: int = 1, ooff: int = 0, in_scale=None, in_shift=None,
-            in_relu: bool = False, bias=None) -> torch.Tensor:
+            in_relu: bool = False, bias=None, bias_per_joint: bool = False) -> torch.Tensor:
     """out[n, j*ostride+ooff, v, :] = bias + sum_m f(x[n, j*istride+shifts[m], v, :]) @ W[m]^T."""
     L.require_device(x)
     assert x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype == pw.dtype
@@ -60,7 +60,7 @@ def tapconv(x: torch.Tensor, pw: PackedWeight, out: torch.Tensor, *, shifts, tj:
     assert (No, Vo) == (N, V) and Cin == pw.cin and Cout == pw.cout and len(shifts) == pw.ntaps
     lib = L.load()
     st = lib.fmm_tapconv(L.ptr(x), L.ptr(out), L.ptr(pw.buf), L.ptr(in_scale), L.ptr(in_shift),
-                         int(in_relu), L.ptr(bias), N, V, Tin, Tout, Cin, Cout, tj, istride, ostride,
+                         int(in_relu), L.ptr(bias), int(bias_per_joint), N, V, Tin, Tout, Cin, Cout, tj, istride, ostride,
                          ooff, len(shifts), L.int_array(list(shifts)), L.dt_of(x.dtype),
                          L.ptr(err_word(x.device)), L.stream())
     L.check(st, "tapconv")
@@ -87,3 +87,126 @@ def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, shifts, istrid
                        L.ptr(err_word(x.device)), L.stream())
     L.check(st, "wgrad")
     return dw
+
+
+# ---------------------------------------------------------------------------------------------
+# memory-bound kernels (csrc/elementwise.cu) and per-channel/per-clip kernels (csrc/tiny.cu)
+# ---------------------------------------------------------------------------------------------
+def _shape4(x):
+    N, Tn, V, C = x.shape
+    return N, Tn, V, C
+
+
+def agg_fwd(x, xa, rowptr, src, coef, K):
+    N, Tn, V, Cin = _shape4(x)
+    assert xa.shape == (N, Tn, V, K * Cin) and x.is_contiguous() and xa.is_contiguous()
+    L.check(L.load().fmm_agg_fwd(L.ptr(x), L.ptr(xa), L.ptr(rowptr), L.ptr(src), L.ptr(coef), N, Tn, V, Cin, K,
+                                 L.dt_of(x.dtype), L.stream()), "agg_fwd")
+    return xa
+
+
+def agg_bwd(P, addend, dx, rowptr, dst, kk, coef, K):
+    N, Tn, V, Cin = _shape4(dx)
+    assert P.shape == (N, Tn, V, K * Cin) and P.is_contiguous() and dx.is_contiguous()
+    assert addend is None or (addend.shape == dx.shape and addend.is_contiguous())
+    L.check(L.load().fmm_agg_bwd(L.ptr(P), L.ptr(addend), L.ptr(dx), L.ptr(rowptr), L.ptr(dst), L.ptr(kk),
+                                 L.ptr(coef), N, Tn, V, Cin, K, L.dt_of(dx.dtype), L.stream()), "agg_bwd")
+    return dx
+
+
+def agg_dcoef(x, P, dcoef, src, dst, kk, K):
+    N, Tn, V, Cin = _shape4(x)
+    assert P.shape == (N, Tn, V, K * Cin)
+    L.check(L.load().fmm_agg_dcoef(L.ptr(x), L.ptr(P), L.ptr(dcoef), L.ptr(src), L.ptr(dst), L.ptr(kk),
+                                   dcoef.numel(), N, Tn, V, Cin, K, L.dt_of(x.dtype), L.stream()), "agg_dcoef")
+    return dcoef
+
+
+def colstats(x, ch_sum=None, ch_sq=None, nc_sum=None):
+    N, Tn, V, C = _shape4(x)
+    assert x.is_contiguous()
+    L.check(L.load().fmm_colstats(L.ptr(x), L.ptr(ch_sum), L.ptr(ch_sq), L.ptr(nc_sum), N, Tn, V, C,
+                                  L.dt_of(x.dtype), L.stream()), "colstats")
+
+
+def block_out(U, k1, k0, res, ar, br, Y):
+    N, Tn, V, C = _shape4(U)
+    L.check(L.load().fmm_block_out(L.ptr(U), L.ptr(k1), L.ptr(k0), L.ptr(res), L.ptr(ar), L.ptr(br), L.ptr(Y),
+                                   N, Tn, V, C, L.dt_of(U.dtype), L.stream()), "block_out")
+    return Y
+
+
+def blockout_bwd_reduce(dY, Y, U, R, S1, S2, S3):
+    N, Tn, V, C = _shape4(U)
+    assert dY.is_contiguous() and dY.shape == U.shape
+    L.check(L.load().fmm_blockout_bwd_reduce(L.ptr(dY), L.ptr(Y), L.ptr(U), L.ptr(R), L.ptr(S1), L.ptr(S2),
+                                             L.ptr(S3), N, Tn, V, C, L.dt_of(U.dtype), L.stream()),
+            "blockout_bwd_reduce")
+
+
+def bn2_bwd_apply(dY, Y, U, R, k1, k2, k3, r1, r2, r3, dU, dR, dPre, sum_dU, sum_dR):
+    N, Tn, V, C = _shape4(U)
+    L.check(L.load().fmm_bn2_bwd_apply(L.ptr(dY), L.ptr(Y), L.ptr(U), L.ptr(R), L.ptr(k1), L.ptr(k2), L.ptr(k3),
+                                       L.ptr(r1), L.ptr(r2), L.ptr(r3), L.ptr(dU), L.ptr(dR), L.ptr(dPre),
+                                       L.ptr(sum_dU), L.ptr(sum_dR), N, Tn, V, C, L.dt_of(U.dtype), L.stream()),
+            "bn2_bwd_apply")
+
+
+def bn1_bwd_reduce(dH, G, a1, b1, T1, T2):
+    N, Tn, V, C = _shape4(G)
+    assert dH.is_contiguous() and dH.shape == G.shape
+    L.check(L.load().fmm_bn1_bwd_reduce(L.ptr(dH), L.ptr(G), L.ptr(a1), L.ptr(b1), L.ptr(T1), L.ptr(T2), N, Tn, V,
+                                        C, L.dt_of(G.dtype), L.stream()), "bn1_bwd_reduce")
+
+
+def bn1_bwd_apply(dH, G, a1, b1, c1, c2, c3, dG, Tbl):
+    N, Tn, V, C = _shape4(G)
+    L.check(L.load().fmm_bn1_bwd_apply(L.ptr(dH), L.ptr(G), L.ptr(a1), L.ptr(b1), L.ptr(c1), L.ptr(c2), L.ptr(c3),
+                                       L.ptr(dG), L.ptr(Tbl), N, Tn, V, C, L.dt_of(G.dtype), L.stream()),
+            "bn1_bwd_apply")
+
+
+def bn_finalize(ch_sum, ch_sq, count, gamma, beta, rmean, rvar, training, a, b, mean_out, rstd_out,
+                momentum=0.1, eps=1e-5):
+    C = a.numel()
+    L.check(L.load().fmm_bn_finalize(L.ptr(ch_sum), L.ptr(ch_sq), float(count), L.ptr(gamma), L.ptr(beta),
+                                     L.ptr(rmean), L.ptr(rvar), momentum, eps, int(training), L.ptr(a), L.ptr(b),
+                                     L.ptr(mean_out), L.ptr(rstd_out), C, L.stream()), "bn_finalize")
+
+
+def se_fwd(pool, a2, b2, invM, W1, b1, gamma, beta, rmean, rvar, training, W2, b2se, p, h, ah, bh, hmean, hrstd,
+           s, k1, k0, momentum=0.1, eps=1e-5):
+    N, C = pool.shape
+    C4 = h.shape[1]
+    L.check(L.load().fmm_se_fwd(L.ptr(pool), L.ptr(a2), L.ptr(b2), invM, L.ptr(W1), L.ptr(b1), L.ptr(gamma),
+                                L.ptr(beta), L.ptr(rmean), L.ptr(rvar), momentum, eps, int(training), L.ptr(W2),
+                                L.ptr(b2se), L.ptr(p), L.ptr(h), L.ptr(ah), L.ptr(bh), L.ptr(hmean), L.ptr(hrstd),
+                                L.ptr(s), L.ptr(k1), L.ptr(k0), N, C, C4, L.stream()), "se_fwd")
+
+
+def se_bwd(S1, S2, a2, b2, s, p, h, ah, bh, hmean, hrstd, W1, W2, training, dq, dhr, r, dh, dp, dW1, db1, dgamma,
+           dbeta, dW2, db2se):
+    N, C = S1.shape
+    C4 = h.shape[1]
+    L.check(L.load().fmm_se_bwd(L.ptr(S1), L.ptr(S2), L.ptr(a2), L.ptr(b2), L.ptr(s), L.ptr(p), L.ptr(h), L.ptr(ah),
+                                L.ptr(bh), L.ptr(hmean), L.ptr(hrstd), L.ptr(W1), L.ptr(W2), int(training),
+                                L.ptr(dq), L.ptr(dhr), L.ptr(r), L.ptr(dh), L.ptr(dp), L.ptr(dW1), L.ptr(db1),
+                                L.ptr(dgamma), L.ptr(dbeta), L.ptr(dW2), L.ptr(db2se), N, C, C4, L.stream()),
+            "se_bwd")
+
+
+def bn2_bwd_coef(S1, S2, S3, pool, dp, s, a2, mean2, rstd2, ar, meanr, rstdr, M, count, training, k1, k2, k3, r1,
+                 r2, r3, dgamma2, dbeta2, dgammar, dbetar):
+    N, C = S1.shape
+    L.check(L.load().fmm_bn2_bwd_coef(L.ptr(S1), L.ptr(S2), L.ptr(S3), L.ptr(pool), L.ptr(dp), L.ptr(s), L.ptr(a2),
+                                      L.ptr(mean2), L.ptr(rstd2), L.ptr(ar), L.ptr(meanr), L.ptr(rstdr), float(M),
+                                      float(count), int(training), L.ptr(k1), L.ptr(k2), L.ptr(k3), L.ptr(r1),
+                                      L.ptr(r2), L.ptr(r3), L.ptr(dgamma2), L.ptr(dbeta2), L.ptr(dgammar),
+                                      L.ptr(dbetar), N, C, L.stream()), "bn2_bwd_coef")
+
+
+def bn1_bwd_coef(T1, T2, a1, mean1, rstd1, count, training, c1, c2, c3, dgamma, dbeta):
+    C = a1.numel()
+    L.check(L.load().fmm_bn1_bwd_coef(L.ptr(T1), L.ptr(T2), L.ptr(a1), L.ptr(mean1), L.ptr(rstd1), float(count),
+                                      int(training), L.ptr(c1), L.ptr(c2), L.ptr(c3), L.ptr(dgamma), L.ptr(dbeta),
+                                      C, L.stream()), "bn1_bwd_coef")

@@ -71,8 +71,12 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // fp32 mode: the dominant hi*hi products and the five small correction terms accumulate in
+  // SEPARATE TMEM tiles (summed in the epilogue). The tensor core truncates its fp32 accumulator on
+  // every MMA; keeping the small terms out of the big accumulator cuts those truncations 6x.
+  const uint32_t acc_stride = (kParts == 1 ? 1u : 2u) * static_cast<uint32_t>(p.BN);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * p.BN) tmem_cols <<= 1;
+  while (tmem_cols < 2u * acc_stride) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslots; ++s) {
@@ -203,11 +207,18 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
                 static_cast<size_t>(v) * p.Cout;
       mbar_wait(acc_full(as), aph, p.err, 2);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * p.BN) + (static_cast<uint32_t>(quad * 32) << 16);
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as) * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
       for (int cg = 0; cg < p.BN / 32; ++cg) {
         uint32_t acc[32];
         tmem_ld32(taddr + cg * 32, acc);
         tmem_ld_wait();
+        if (kParts != 1) {
+          uint32_t corr[32];
+          tmem_ld32(taddr + p.BN + cg * 32, corr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(corr[i]));
+        }
         const int co0 = ntile * p.BN + cg * 32;
         if (row_ok) {
 #pragma unroll
@@ -270,8 +281,8 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.BN);
-        uint32_t accum = 0;
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * acc_stride;
+        uint32_t accum = 0, accum_c = 0;
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(win_full(slot), wph, p.err, 5);
           tc_fence_after();
@@ -288,16 +299,19 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
                           make_smem_desc(b_st + kk * 32u, 16, 1024), idesc, accum);
                 accum = 1;
               } else {
-                // (a0+a1+a2)(b0+b1+b2) ~ a0b0 + a0b1 + a1b0 + a1b1 + a0b2 + a2b0 (rel. err ~2^-24)
-                const int pa[6] = {2, 0, 1, 1, 0, 0};
-                const int pb[6] = {0, 2, 1, 0, 1, 0};
+                // (a0+a1+a2)(b0+b1+b2) ~ a0b0 + [a0b1 + a1b0 + a1b1 + a0b2 + a2b0] (rel. err ~2^-24)
+                const int pa[5] = {2, 0, 1, 1, 0};
+                const int pb[5] = {0, 2, 1, 0, 1};
 #pragma unroll
-                for (int e = 0; e < 6; ++e) {
-                  umma_bf16(d_tmem, make_smem_desc(a_tap + pa[e] * part_bytes_a + kk * 32u, 16, a_sbo),
+                for (int e = 0; e < 5; ++e) {
+                  umma_bf16(d_tmem + p.BN, make_smem_desc(a_tap + pa[e] * part_bytes_a + kk * 32u, 16, a_sbo),
                             make_smem_desc(b_st + pb[e] * part_bytes_b + kk * 32u, 16, 1024), idesc,
-                            accum);
-                  accum = 1;
+                            accum_c);
+                  accum_c = 1;
                 }
+                umma_bf16(d_tmem, make_smem_desc(a_tap + kk * 32u, 16, a_sbo),
+                          make_smem_desc(b_st + kk * 32u, 16, 1024), idesc, accum);
+                accum = 1;
               }
             }
             umma_commit(b_empty(bs));

@@ -63,8 +63,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // fp32 mode: main (hi*hi) and correction terms in separate TMEM tiles, see csrc/tapconv.cu
+  const uint32_t acc_stride = (kParts == 1 ? 1u : 2u) * static_cast<uint32_t>(p.BN);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(p.TG * p.BN)) tmem_cols <<= 1;
+  while (tmem_cols < static_cast<uint32_t>(p.TG) * acc_stride) tmem_cols <<= 1;
 
   const int item = blockIdx.x % p.items;
   const int slice = blockIdx.x / p.items;
@@ -212,8 +214,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       for (int t = 0; t < mt; ++t) {
         for (int cg = 0; cg < p.BN / 32; ++cg) {
           uint32_t acc[32];
-          tmem_ld32(tmem_base + static_cast<uint32_t>(t * p.BN + cg * 32) + (static_cast<uint32_t>(warp * 32) << 16), acc);
+          const uint32_t taddr = tmem_base + static_cast<uint32_t>(t) * acc_stride + static_cast<uint32_t>(cg * 32) +
+                                 (static_cast<uint32_t>(warp * 32) << 16);
+          tmem_ld32(taddr, acc);
           tmem_ld_wait();
+          if (kParts != 1) {
+            uint32_t corr[32];
+            tmem_ld32(taddr + p.BN, corr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(corr[i]));
+          }
           if (ci_ok) {
             float* dst = p.dw + (m0 + t) * p.s_m + ci_off;
 #pragma unroll
@@ -244,17 +255,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
               const uint32_t a_tap = a_base + static_cast<uint32_t>(p.shift[m0 + t] - p.minshift) * 1024u +
                                      static_cast<uint32_t>(kk) * 2u * a_sbo;
               const uint32_t b_k = b_base + static_cast<uint32_t>(kk) * 2048u;
-              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(t * p.BN);
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(t) * acc_stride;
               if (kParts == 1) {
                 umma_bf16(d_tmem, make_smem_desc(a_tap, a_lbo, a_sbo), make_smem_desc(b_k, b_lbo, 1024),
                           idesc, accum);
               } else {
-                const int pa[6] = {2, 0, 1, 1, 0, 0};
-                const int pb[6] = {0, 2, 1, 0, 1, 0};
+                const int pa[5] = {2, 0, 1, 1, 0};
+                const int pb[5] = {0, 2, 1, 0, 1};
 #pragma unroll
-                for (int e = 0; e < 6; ++e)
-                  umma_bf16(d_tmem, make_smem_desc(a_tap + pa[e] * a_part, a_lbo, a_sbo),
+                for (int e = 0; e < 5; ++e)
+                  umma_bf16(d_tmem + p.BN, make_smem_desc(a_tap + pa[e] * a_part, a_lbo, a_sbo),
                             make_smem_desc(b_k + pb[e] * b_part, b_lbo, 1024), idesc, (e > 0) ? 1u : accum);
+                umma_bf16(d_tmem, make_smem_desc(a_tap, a_lbo, a_sbo), make_smem_desc(b_k, b_lbo, 1024), idesc, accum);
               }
             }
             accum = 1;
@@ -327,7 +339,7 @@ int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, c
     p.MCH = 1;
     p.BN = ntaps > 1 ? 64 : (cout64 < 128 ? cout64 : 128);
   }
-  const int max_tg = 512 / p.BN;
+  const int max_tg = 512 / (p.BN * (nparts == 1 ? 1 : 2));
   const int ngrp = (ntaps + max_tg - 1) / max_tg;
   p.TG = (ntaps + ngrp - 1) / ngrp;
   p.tap_groups = (ntaps + p.TG - 1) / p.TG;

@@ -62,6 +62,7 @@ class TrunkEngine:
         self._csr_np = adjacency_csr(A.detach().cpu().double().numpy())
         self.E = len(self._csr_np["fwd_src"])
         self._dev = {}
+        self.debug = None  # dev aid: set to a dict to capture backward intermediates per block
 
     def csr(self, device):
         key = str(device)
@@ -323,6 +324,9 @@ class TrunkEngine:
             dx = torch.empty_like(x)
             coef_b = b["coef_f"][csr["bwd_perm"]].contiguous()
             ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K)
+            if self.debug is not None:
+                self.debug[i] = dict(dY=dY, dU=dU, dH=dH, dG=dG, P=Pm, dx=dx, S1=S1, S2=S2, dp=dp, dR=dR, c1=c1, c2=c2,
+                                     c3=c3, T1=T1, T2=T2, saved=b)
             dY = dx
 
         # ---- data_bn backward (input itself needs no gradient) ----

@@ -74,7 +74,7 @@ class _TrunkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, names, training, dt, skel, *tensors):
         P = dict(zip(names, tensors))
-        need_grad = any(t.requires_grad for t in tensors) and torch.is_grad_enabled()
+        need_grad = any(ctx.needs_input_grad)
         with torch.autocast("cuda", enabled=False):
             feat, sv = engine.forward(P, skel, training, dt, need_grad)
         ctx.engine, ctx.names, ctx.P, ctx.sv = engine, names, P, sv

@@ -100,9 +100,9 @@ def main():
 
     # ---- GSTCAN cases -----------------------------------------------------------------------
     cases = [
-        ("stgcan_coco_spatial", dict(in_ch=3, layout="coco_cut", strategy="spatial", num_class=11, N=4, T=12)),
-        ("stgcan_mp33_spatial", dict(in_ch=3, layout="mediapipe33", strategy="spatial", num_class=11, N=2, T=16)),
-        ("stgcan_mmpose_uniform_feat", dict(in_ch=2, layout="coco_mmpose", strategy="uniform", num_class=None, N=3, T=9)),
+        ("stgcan_coco_spatial", dict(in_ch=3, layout="coco_cut", strategy="spatial", num_class=11, N=8, T=12)),
+        ("stgcan_mp33_spatial", dict(in_ch=3, layout="mediapipe33", strategy="spatial", num_class=11, N=6, T=16)),
+        ("stgcan_mmpose_uniform_feat", dict(in_ch=2, layout="coco_mmpose", strategy="uniform", num_class=None, N=5, T=9)),
     ]
     for name, c in cases:
         mod = stg.STGCAN(c["in_ch"], {"layout": c["layout"], "strategy": c["strategy"]}, num_class=c["num_class"])
@@ -142,9 +142,9 @@ def main():
         warnings.simplefilter("ignore")
         mod = comb.TwoStreamSTGCAN_BiLSTM(3, {"layout": "coco_cut", "strategy": "spatial"}, 11, 15)
     shapes = fill_module(mod, seed=4)
-    skel, sensor, target, _ = O.synthetic_batch(4, 10, 14, 11, sensor_len=30, sensor_ch=15, seed=10)
+    skel, sensor, target, _ = O.synthetic_batch(6, 10, 14, 11, sensor_len=30, sensor_ch=15, seed=10)
     res = run_train_step(mod, lambda: mod(skel, sensor), target)
-    torch.save({"config": dict(layout="coco_cut", strategy="spatial", num_class=11, N=4, T=10, L=30, I=15),
+    torch.save({"config": dict(layout="coco_cut", strategy="spatial", num_class=11, N=6, T=10, L=30, I=15),
                 "shapes": shapes, "fill_seed": 4, "batch_seed": 10, **res},
                os.path.join(OUT, "two_stream_bilstm.pt"))
     print("fusion loss", res["loss"])

@@ -183,7 +183,19 @@ def channel_attention(x, sd, prefix, training, update=None):
     return x * torch.sigmoid(s)
 
 
-def st_gcan_block(x, A, sd, prefix, stride, residual, training, attention=True, update=None):
+def _relu(x, masks, site):
+    """ReLU; with ``masks`` the 0/1 decision is taken from the given tensor instead of sign(x).
+
+    Used by the parity tests to compare gradients GIVEN IDENTICAL ReLU DECISIONS: two correct fp32
+    implementations disagree on sign(x) for the handful of elements with |x| ~ 1e-7*max, and each
+    such flip moves a gradient by one whole element, which no tolerance on the sums can absorb.
+    """
+    if masks is None:
+        return F.relu(x)
+    return x * masks[site].to(x.dtype)
+
+
+def st_gcan_block(x, A, sd, prefix, stride, residual, training, attention=True, update=None, masks=None, site=0):
     """st_gcan.forward, stgcan.py:138-144: relu(CA(tcn(gcn(x, A))) + res)."""
     if not residual:
         res = 0
@@ -194,15 +206,15 @@ def st_gcan_block(x, A, sd, prefix, stride, residual, training, attention=True, 
         res = x
     y = graph_conv(x, A, sd[prefix + "gcn.conv.weight"], sd[prefix + "gcn.conv.bias"])
     y = _bn(y, sd, prefix + "tcn.0.", training, update=update)            # stgcan.py:112
-    y = F.relu(y)                                                         # :113
+    y = _relu(y, masks, site)                                             # :113
     y = F.conv2d(y, sd[prefix + "tcn.2.weight"], sd[prefix + "tcn.2.bias"], stride=(stride, 1), padding=(4, 0))  # :114-118
     y = _bn(y, sd, prefix + "tcn.3.", training, update=update)            # :119 (Dropout p=0 is identity)
     if attention:
         y = channel_attention(y, sd, prefix + "channel_attention_module.", training, update=update)
-    return F.relu(y + res)
+    return _relu(y + res, masks, site + 1)
 
 
-def stgcan_forward(sd, skel, training=True, update=None, block_key="st_gcan_networks"):
+def stgcan_forward(sd, skel, training=True, update=None, block_key="st_gcan_networks", masks=None):
     """STGCAN.forward, stgcan.py:210-228. ``sd``: state_dict-like mapping of tensors.
 
     Returns (N, num_class) logits, or the (N, 256) pooled feature when the dict has no ``cls.*``.
@@ -214,7 +226,7 @@ def stgcan_forward(sd, skel, training=True, update=None, block_key="st_gcan_netw
     A = sd["A"]
     for i, (cin, cout, stride, res) in enumerate(BLOCK_PLAN):
         x = st_gcan_block(x, A * sd[f"edge_importance.{i}"], sd, f"{block_key}.{i}.", stride, res,
-                          training, update=update)                        # :221-222
+                          training, update=update, masks=masks, site=2 * i)  # :221-222
     x = F.avg_pool2d(x, x.shape[2:])                                      # :224
     if "cls.weight" in sd:
         x = F.conv2d(x, sd["cls.weight"], sd["cls.bias"])                 # :225
@@ -341,13 +353,25 @@ def fill_state_dict(shapes, seed=0):
     return sd
 
 
-def synthetic_batch(N, T, V, num_class=11, sensor_len=30, sensor_ch=15, seed=42):
-    """xy ~ U(-1,1), score ~ U(0,1), sensor ~ N(0,1), label-smoothed soft targets."""
+def synthetic_batch(N, T, V, num_class=11, sensor_len=30, sensor_ch=15, seed=42, per_clip=True):
+    """xy in [-1,1], score ~ U(0,1), sensor ~ N(0,1), label-smoothed soft targets.
+
+    ``per_clip`` gives every clip its own pose scale/offset and sensor gain (different subjects at
+    different positions). Without it all clips have near-identical pooled statistics and the
+    squeeze-excite BatchNorm over N (stgcan.py:66) becomes ill-conditioned: its output is then
+    dominated by fp32 rounding and no two correct fp32 implementations agree to 1e-4.
+    """
     g = torch.Generator().manual_seed(seed)
     skel = torch.empty(N, 3, T, V)
     skel[:, :2] = torch.rand(N, 2, T, V, generator=g) * 2 - 1
     skel[:, 2] = torch.rand(N, T, V, generator=g)
     sensor = torch.randn(N, sensor_len, sensor_ch, generator=g)
+    if per_clip:
+        scale = 0.3 + 0.7 * torch.rand(N, 1, 1, 1, generator=g)
+        off = torch.rand(N, 2, 1, 1, generator=g) - 0.5
+        skel[:, :2] = (skel[:, :2] * scale * 0.5 + off).clamp(-1, 1)
+        skel[:, 2:] = skel[:, 2:] * (0.5 + 0.5 * torch.rand(N, 1, 1, 1, generator=g))
+        sensor = sensor * (0.5 + torch.rand(N, 1, 1, generator=g)) + 0.3 * torch.randn(N, 1, sensor_ch, generator=g)
     labels = torch.randint(0, num_class, (N,), generator=g)
     eps = 0.1
     target = torch.full((N, num_class), eps / (num_class - 1))

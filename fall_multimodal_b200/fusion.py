@@ -1,0 +1,85 @@
+"""Late-fusion models over the B200 trunks.
+
+* ``TwoStreamSTGCAN`` / ``TwoStreamSTGCAN_CNN1D`` mirror
+  ``/root/reference/Fall_2_Spatial_Temporal_SR/Model/combination.py`` (:9-46): joint stream on
+  ``skel`` (3 ch), motion stream on the frame difference of xy (2 ch, T-1 frames), optional sensor
+  branch, ``cat -> Linear``. State-dict prefixes ``stgcan_1.``, ``stgcan_2.``, ``fc.`` as there.
+* ``TwoStreamSTGCAN_CNN1D`` is BASELINE.json's config 2 ("skeleton+accelerometer fusion, GCN +
+  1D-CNN sensor branch"): the notebook ``TwoStreamSpatialTemporalGraph`` pattern
+  (GSTCAN_HAR_conv_10kfold.ipynb#cell1:L362-416) with the notebook ``CNN1D`` as the sensor branch.
+The two trunks and the sensor branch are independent until the concat, so they are issued on
+separate CUDA streams.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .sensor import CNN1D
+from .stgcan import STGCAN, _compute_dtype
+
+
+class _Streams:
+    """Side streams for the independent branches of a fusion model (one set per device)."""
+
+    def __init__(self):
+        self._s = {}
+
+    def get(self, device, n):
+        key = str(device)
+        if key not in self._s or len(self._s[key]) < n:
+            self._s[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+        return self._s[key][:n]
+
+
+class TwoStreamSTGCAN(nn.Module):
+    def __init__(self, in_channels, graph_args, num_class):
+        super().__init__()
+        self.stgcan_1 = STGCAN(3, graph_args, num_class=None)
+        self.stgcan_2 = STGCAN(2, graph_args, num_class=None)
+        self.fc = nn.Linear(256 * 2, num_class)
+        self.compute_dtype = None
+        self.concurrent_streams = False  # opt-in: run the independent branches on side streams
+        self._streams = _Streams()
+
+    def _branches(self, skel, sensor):
+        return []
+
+    def forward(self, skel, sensor=None):
+        dt = _compute_dtype(self)
+        self.stgcan_1.compute_dtype = self.stgcan_2.compute_dtype = dt
+        mot = skel[:, :2, 1:] - skel[:, :2, :-1]          # combination.py:13,39
+        extra = self._branches(skel, sensor)
+        jobs = [lambda: self.stgcan_1.features(skel), lambda: self.stgcan_2.features(mot)] + extra
+        if self.concurrent_streams and skel.is_cuda:
+            cur = torch.cuda.current_stream()
+            outs = []
+            for job, st in zip(jobs, self._streams.get(skel.device, len(jobs))):
+                st.wait_stream(cur)
+                for t in (skel, mot, sensor):
+                    if t is not None:
+                        t.record_stream(st)
+                with torch.cuda.stream(st):
+                    outs.append(job())
+            for o, st in zip(outs, self._streams.get(skel.device, len(jobs))):
+                cur.wait_stream(st)
+                o.record_stream(cur)
+        else:
+            outs = [job() for job in jobs]
+        x = torch.cat([o.float() for o in outs], dim=-1)
+        with torch.autocast("cuda", enabled=False):
+            out = torch.addmm(self.fc.bias, x, self.fc.weight.t())
+        return out.to(dt) if dt == torch.bfloat16 else out
+
+
+class TwoStreamSTGCAN_CNN1D(TwoStreamSTGCAN):
+    def __init__(self, in_channels, graph_args, num_class, sensor_channels=15, sensor_len=30):
+        super().__init__(in_channels, graph_args, num_class)
+        self.cnn = CNN1D(sensor_channels, sensor_len)
+        self.fc = nn.Linear(256 * 2 + 32 * (sensor_len // 4), num_class)
+
+    def _branches(self, skel, sensor):
+        def run():
+            f = self.cnn.forward_channels_last(sensor)        # (N, L/4, 32)
+            return f.permute(0, 2, 1).flatten(1)               # torch's (N, 32, L/4).flatten(1) order
+        return [run]

@@ -210,3 +210,36 @@ def bn1_bwd_coef(T1, T2, a1, mean1, rstd1, count, training, c1, c2, c3, dgamma, 
     L.check(L.load().fmm_bn1_bwd_coef(L.ptr(T1), L.ptr(T2), L.ptr(a1), L.ptr(mean1), L.ptr(rstd1), float(count),
                                       int(training), L.ptr(c1), L.ptr(c2), L.ptr(c3), L.ptr(dgamma), L.ptr(dbeta),
                                       C, L.stream()), "bn1_bwd_coef")
+
+
+# ---------------------------------------------------------------------------------------------
+# sensor branch (csrc/sensor.cu): channels-last fp32 windows x[N][L][C]
+# ---------------------------------------------------------------------------------------------
+def conv1d_k5_fwd(x, w, b, y):
+    N, Ln, Ci = x.shape
+    Co = w.shape[0]
+    assert x.dtype == torch.float32 and x.is_contiguous() and y.shape == (N, Ln, Co) and w.is_contiguous()
+    L.check(L.load().fmm_conv1d_k5_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), N, Ln, Ci, Co, L.stream()), "conv1d_k5_fwd")
+    return y
+
+
+def bn_relu_pool2_fwd(y, a, b, out):
+    N, Ln, C = y.shape
+    assert out.shape == (N, Ln // 2, C)
+    L.check(L.load().fmm_bn_relu_pool2_fwd(L.ptr(y), L.ptr(a), L.ptr(b), L.ptr(out), N, Ln, C, L.stream()), "bn_relu_pool2_fwd")
+    return out
+
+
+def pool2_bwd(y, a, b, dout, dh):
+    N, Ln, C = y.shape
+    assert dout.is_contiguous() and dout.shape == (N, Ln // 2, C) and dh.shape == y.shape
+    L.check(L.load().fmm_pool2_bwd(L.ptr(y), L.ptr(a), L.ptr(b), L.ptr(dout), L.ptr(dh), N, Ln, C, L.stream()), "pool2_bwd")
+    return dh
+
+
+def conv1d_k5_bwd(x, dy, w, dx, dw, db):
+    N, Ln, Ci = x.shape
+    Co = w.shape[0]
+    assert dy.is_contiguous() and dy.shape == (N, Ln, Co)
+    L.check(L.load().fmm_conv1d_k5_bwd(L.ptr(x), L.ptr(dy), L.ptr(w), L.ptr(dx), L.ptr(dw), L.ptr(db), N, Ln, Ci, Co,
+                                       L.stream()), "conv1d_k5_bwd")

@@ -195,7 +195,11 @@ def test_stgcan_bf16_within_tolerance(layout, N, T):
     oa, auto = oracle_run(torch.float32, True)
     err = (out.double() - o64).abs().max().item() / o64.abs().max().item()
     assert err < BF16_TOL, f"bf16 logits err {err:.3e}"
-    assert torch.equal(out.float().argmax(-1), o64.argmax(-1))
+    # identical labels wherever the exact top-2 margin is larger than the bf16 logit tolerance
+    top2 = o64.topk(2, dim=-1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 2 * BF16_TOL * o64.abs().max()
+    assert torch.equal(out.float().argmax(-1)[decided], o64.argmax(-1)[decided])
+    assert decided.float().mean() > 0.5
     e_mine, e_auto = _rel_errors(grads, truth), _rel_errors(auto, truth)
     med_mine, med_auto = statistics.median(e_mine.values()), statistics.median(e_auto.values())
     print(f"{layout} N={N}: bf16 logits err {err:.2e}; grad err median {med_mine:.2e} (torch autocast {med_auto:.2e}), "

@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Headline benchmark: train clips/sec (fwd + bwd + RMSprop step) of the GSTCAN fusion model.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): two GSTCAN trunks
+(joints 3ch T=64, motion 2ch T=63, V=33 MediaPipe layout, spatial partitioning) + the 1-D CNN
+accelerometer branch (30x15 windows) + late-fusion Linear, bf16 autocast, 256 clips per GPU,
+synthetic data (SURVEY.md 8(d) recipe), random-init weights. One step = zero_grad -> forward ->
+CrossEntropy(soft targets) -> backward -> RMSprop(lr 1e-3).step(), as F2/main.py:104-132.
+
+    python bench.py --gpus N --steps K --warmup W            our CUDA path (N>1: under torchrun)
+    python bench.py --impl reference ...                     the reference algorithm on the host CPU
+
+Prints ONE JSON line (rank 0). `value` = whole-job clips/s with inputs resident in HBM; `e2e` =
+the same step fed from pinned host memory with the loss read back every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_CLASS = 11
+T, V, SENSOR_L, SENSOR_C = 64, 33, 30, 15
+LAYOUT = "mediapipe33"
+WORKLOAD = ("two-stream GSTCAN (joints 3x64x33 + motion 2x63x33, spatial K=3) + CNN1D sensor 30x15, "
+            "train step fwd+bwd+RMSprop")
+
+
+def synthetic(n, seed, device="cpu"):
+    """xy ~ U(-1,1), score ~ U(0,1), sensor ~ N(0,1), label-smoothed soft targets."""
+    g = torch.Generator().manual_seed(seed)
+    skel = torch.empty(n, 3, T, V)
+    skel[:, :2] = torch.rand(n, 2, T, V, generator=g) * 2 - 1
+    skel[:, 2] = torch.rand(n, T, V, generator=g)
+    sensor = torch.randn(n, SENSOR_L, SENSOR_C, generator=g)
+    labels = torch.randint(0, NUM_CLASS, (n,), generator=g)
+    target = torch.full((n, NUM_CLASS), 0.1 / (NUM_CLASS - 1))
+    target[torch.arange(n), labels] = 0.9
+    return skel.to(device), sensor.to(device), target.to(device)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference algorithm on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_step_factory(n, threads):
+    from oracle import stgcn_oracle as O
+
+    torch.set_num_threads(threads)
+    A = torch.tensor(O.build_adjacency(LAYOUT, "spatial"), dtype=torch.float32)
+    shapes = {}
+    for pre, cin in (("stgcan_1.", 3), ("stgcan_2.", 2)):
+        for k, s in O.stgcan_param_shapes(cin, V, A.shape[0], None).items():
+            shapes[pre + k] = s
+    shapes.update({"cnn.layer1.0.weight": (16, SENSOR_C, 5), "cnn.layer1.0.bias": (16,), "cnn.layer1.1.weight": (16,),
+                   "cnn.layer1.1.bias": (16,), "cnn.layer1.1.running_mean": (16,), "cnn.layer1.1.running_var": (16,),
+                   "cnn.layer2.0.weight": (32, 16, 5), "cnn.layer2.0.bias": (32,), "cnn.layer2.1.weight": (32,),
+                   "cnn.layer2.1.bias": (32,), "cnn.layer2.1.running_mean": (32,), "cnn.layer2.1.running_var": (32,),
+                   "fc.weight": (NUM_CLASS, 512 + 32 * (SENSOR_L // 4)), "fc.bias": (NUM_CLASS,)})
+    sd = O.fill_state_dict(shapes, 0)
+    sd["stgcan_1.A"] = A
+    sd["stgcan_2.A"] = A.clone()
+    params = [v.requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and "running_" not in k and not k.endswith(".A")]
+    opt = torch.optim.RMSprop(params, lr=1e-3)
+    skel, sensor, target = synthetic(n, 42)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = O.two_stream_cnn_forward(sd, skel, sensor, training=True)
+        loss = O.soft_ce(out, target)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return step
+
+
+def time_cpu(n, steps, warmup, threads):
+    step = cpu_step_factory(n, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.cpu_clips
+    value, dt = time_cpu(n, args.steps, args.warmup, threads)
+    line = {"metric": "train clips/sec fwd+bwd (GSTCAN, Bx3xT64xV33)", "value": value, "unit": "clips/s",
+            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_step": n, "T": T, "V": V, "impl": "oracle port of the "
+                       "reference PyTorch modules on the host CPU (the reference tree does not travel to the box)"},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} steps of {n} clips after {args.warmup} warm-up"},
+            "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    import fall_multimodal_b200 as fmm
+    from fall_multimodal_b200 import _lib, ops
+    from fall_multimodal_b200.parallel import GradBuckets
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(42)
+    model = fmm.TwoStreamSTGCAN_CNN1D(3, {"layout": LAYOUT, "strategy": "spatial"}, NUM_CLASS, SENSOR_C, SENSOR_L).to(dev)
+    model.train()
+    model.concurrent_streams = bool(args.streams)
+    if world > 1:  # identical replicas
+        for p in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(p.data, 0)
+    opt = torch.optim.RMSprop(model.parameters(), lr=1e-3)
+    buckets = GradBuckets([list(model.fc.parameters()) + list(model.cnn.parameters()),
+                           list(model.stgcan_2.parameters()), list(model.stgcan_1.parameters())])
+    loss_fn = torch.nn.CrossEntropyLoss()
+    skel_h, sensor_h, target_h = synthetic(B, 42 + rank)
+    skel_h, sensor_h, target_h = skel_h.pin_memory(), sensor_h.pin_memory(), target_h.pin_memory()
+    skel, sensor, target = skel_h.to(dev), sensor_h.to(dev), target_h.to(dev)
+
+    def step(sk, se, tg):
+        buckets.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(sk, se)
+        loss = loss_fn(out.float(), tg)
+        loss.backward()
+        buckets.wait()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step(skel, sensor, target)
+    # ---- device-resident throughput (+ per-launch timing of the GEMM kernels for the roofline) ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ops.profile = []
+    launches0 = _lib.launch_count
+    ms = timed(lambda: step(skel, sensor, target), args.steps)
+    launches = _lib.launch_count - launches0
+    prof, ops.profile = ops.profile, None
+    clk = clocks.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end: pinned host -> device every step, loss back to the host every step ----
+    def e2e_step():
+        sk = skel_h.to(dev, non_blocking=True)
+        se = sensor_h.to(dev, non_blocking=True)
+        tg = target_h.to(dev, non_blocking=True)
+        return step(sk, se, tg).item()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = skel_h.numel() * 4 + sensor_h.numel() * 4 + target_h.numel() * 4
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md sustained)"
+        roof = None
+        if prof:
+            tot = {}
+            for kind, flops, a, b in prof:
+                t = tot.setdefault(kind, [0.0, 0.0, 0])
+                t[0] += flops
+                t[1] += a.elapsed_time(b) * 1e-3
+                t[2] += 1
+            kind = max(tot, key=lambda k: tot[k][1])
+            fl, sec, cnt = tot[kind]
+            ach = fl / sec / 1e12
+            roof = {"bound": "tensor", "kernel": f"{kind}_kernel<bf16> ({cnt} launches in the timed region)",
+                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "peak_source": peak_src, "share_of_step": sec / (ms / 1e3),
+                    "by_kernel": {k: {"tflops": v[0] / v[1] / 1e12, "share_of_step": v[1] / (ms / 1e3), "launches": v[2]}
+                                  for k, v in tot.items()}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, dt = time_cpu(args.cpu_clips, 2, 1, threads)
+            cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
+                   "sample": f"2 steps of {args.cpu_clips} clips after 1 warm-up ({dt:.1f} s/step), same model/shape"}
+        line = {"metric": "train clips/sec fwd+bwd (GSTCAN, Bx3xT64xV33)", "value": value, "unit": "clips/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "clips_per_gpu": B, "global_batch": world * B, "T": T, "V": V,
+                           "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) >> 126 MB L2",
+                           "bn": "per-shard statistics", "streams": bool(args.streams)},
+                "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
+    ap.add_argument("--cpu-clips", type=int, default=8, help="clips per CPU-baseline step (bounded sample)")
+    ap.add_argument("--streams", type=int, default=0, help="1: run the independent branches on side streams")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -53,7 +53,14 @@ def load() -> C.CDLL:
     return lib
 
 
+# number of kernels each C entry point launches (default 1); used for the launch counter
+_KERNELS_PER_CALL = {"se_fwd": 3, "se_bwd": 5, "conv1d_k5_bwd": 2}
+launch_count = 0
+
+
 def check(status: int, what: str) -> None:
+    global launch_count
+    launch_count += _KERNELS_PER_CALL.get(what, 1)
     if status != 0:
         msg = load().fmm_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"libfmm_b200 {what} failed (status {status}): {msg}")

@@ -21,6 +21,24 @@ def err_word(device: torch.device) -> torch.Tensor:
     return _err_words[idx]
 
 
+# ---------------------------------------------------------------------------------------------
+# optional per-launch timing of the GEMM-class kernels (bench.py's roofline leg): CUDA events on
+# the launching stream around every tapconv / wgrad call while ``profile`` is a list.
+# ---------------------------------------------------------------------------------------------
+profile = None
+
+
+def _timed(kind, flops, fn):
+    if profile is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    profile.append((kind, flops, e0, e1))
+    return out
+
+
 class PackedWeight:
     """Weights of one tap-conv, converted to the tensor-core shared-memory images."""
 
@@ -59,12 +77,16 @@ def tapconv(x: torch.Tensor, pw: PackedWeight, out: torch.Tensor, *, shifts, tj:
     No, Tout, Vo, Cout = out.shape
     assert (No, Vo) == (N, V) and Cin == pw.cin and Cout == pw.cout and len(shifts) == pw.ntaps
     lib = L.load()
-    st = lib.fmm_tapconv(L.ptr(x), L.ptr(out), L.ptr(pw.buf), L.ptr(in_scale), L.ptr(in_shift),
-                         int(in_relu), L.ptr(bias), int(bias_per_joint), N, V, Tin, Tout, Cin, Cout, tj, istride, ostride,
-                         ooff, len(shifts), L.int_array(list(shifts)), L.dt_of(x.dtype),
-                         L.ptr(err_word(x.device)), L.stream())
-    L.check(st, "tapconv")
-    return out
+
+    def run():
+        st = lib.fmm_tapconv(L.ptr(x), L.ptr(out), L.ptr(pw.buf), L.ptr(in_scale), L.ptr(in_shift),
+                             int(in_relu), L.ptr(bias), int(bias_per_joint), N, V, Tin, Tout, Cin, Cout, tj, istride,
+                             ostride, ooff, len(shifts), L.int_array(list(shifts)), L.dt_of(x.dtype),
+                             L.ptr(err_word(x.device)), L.stream())
+        L.check(st, "tapconv")
+        return out
+
+    return _timed("tapconv", 2.0 * N * V * tj * Cin * Cout * len(shifts), run)
 
 
 def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, shifts, istride: int = 1,
@@ -81,12 +103,16 @@ def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, shifts, istrid
     Ny, Tj, Vy, Cout = dy.shape
     assert (Ny, Vy) == (N, V)
     lib = L.load()
-    st = lib.fmm_wgrad(L.ptr(x), L.ptr(dy), L.ptr(dw), L.ptr(in_scale), L.ptr(in_shift), int(in_relu),
-                       N, V, Tin, Tj, Cin, Cout, istride, len(shifts), L.int_array(list(shifts)),
-                       c2 if c2 is not None else Cin, s_m, s_c1, s_c2, s_co, L.dt_of(x.dtype),
-                       L.ptr(err_word(x.device)), L.stream())
-    L.check(st, "wgrad")
-    return dw
+
+    def run():
+        st = lib.fmm_wgrad(L.ptr(x), L.ptr(dy), L.ptr(dw), L.ptr(in_scale), L.ptr(in_shift), int(in_relu),
+                           N, V, Tin, Tj, Cin, Cout, istride, len(shifts), L.int_array(list(shifts)),
+                           c2 if c2 is not None else Cin, s_m, s_c1, s_c2, s_co, L.dt_of(x.dtype),
+                           L.ptr(err_word(x.device)), L.stream())
+        L.check(st, "wgrad")
+        return dw
+
+    return _timed("wgrad", 2.0 * N * V * Tj * Cin * Cout * len(shifts), run)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -18,10 +18,11 @@
 // read through a descriptor whose start address is shifted by whole atoms (no im2col copies),
 // and a temporal stride is just SBO = is*1024.
 //
-// Warp roles (320 threads, persistent over tiles): 0-3 window producers (global -> BN/ReLU ->
-// bf16 parts -> swizzled smem), 4-7 epilogue (TMEM -> regs -> bias -> global), 8 weight loader
-// (bulk async copies of pre-packed weight images), 9 MMA issuer (one thread) + TMEM allocator.
+// Warp roles (448 threads, persistent over tiles): 0-7 window producers (global -> BN/ReLU ->
+// bf16 parts -> swizzled smem), 8-11 epilogue (TMEM -> regs -> bias -> global), 12 weight loader
+// (bulk async copies of pre-packed weight images), 13 MMA issuer (one thread) + TMEM allocator.
 #include "common.cuh"
+#include "producer.cuh"
 #include "ptx.cuh"
 
 namespace fmm {
@@ -46,7 +47,8 @@ struct TapConvParams {
   unsigned* err;
 };
 
-constexpr int kTapThreads = 320;
+constexpr int kTapThreads = 448;
+constexpr int kTapProducers = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslots; ++s) {
-      mbar_init(win_full(s), 128);
+      mbar_init(win_full(s), kTapProducers);
       mbar_init(win_empty(s), 1);
     }
     for (int s = 0; s < p.nbstages; ++s) {
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
     }
     mbar_fence_init();
   }
-  if (warp == 9) {
+  if (warp == 13) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
@@ -106,14 +108,16 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
   const int first_tile = blockIdx.x;
   const int tile_step = gridDim.x;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ------------------------------ window producers ------------------------------
     const T* __restrict__ X = reinterpret_cast<const T*>(p.x);
-    const int pt = threadIdx.x;       // 0..127
-    const int pc = pt & 7;            // 16-byte chunk = 8 channels
+    const int pt = threadIdx.x;       // 0..255
+    const int pc = pt & 7;            // 16-byte piece = 8 channels
     const int q = (pt >> 3) & 7;      // column inside the group
-    const int a0 = pt >> 6;           // atoms a0, a0+2, ...
+    const int a0 = pt >> 6;           // atoms a0, a0+4, ...
     const bool vec_ok = (p.Cin % 8) == 0;
+    const bool affine = p.in_scale != nullptr;
+    const size_t pitch_t = static_cast<size_t>(p.V) * p.Cin;
     int slot = 0;
     uint32_t ph = 0;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
@@ -125,57 +129,24 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
       const int n = col_ok ? col / p.V : 0;
       const int v = col_ok ? col % p.V : 0;
       const int t_lo = tchunk * 16 * p.istride + p.minshift;
+      const T* colp = X + static_cast<size_t>(n) * p.Tin * pitch_t + static_cast<size_t>(v) * p.Cin;
       for (int c = 0; c < p.nchunks; ++c) {
         const int cb = c * 64 + pc * 8;
         float sc[8], sh[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const bool ok = (cb + i) < p.Cin;
-          sc[i] = (p.in_scale && ok) ? p.in_scale[cb + i] : 1.f;
-          sh[i] = (p.in_shift && ok) ? p.in_shift[cb + i] : 0.f;
+          const bool ok = affine && (cb + i) < p.Cin;
+          sc[i] = ok ? p.in_scale[cb + i] : 1.f;
+          sh[i] = ok ? p.in_shift[cb + i] : 0.f;
         }
         mbar_wait(win_empty(slot), ph ^ 1u, p.err, 1);
-        const uint32_t sbase = slots0 + slot * slot_bytes + q * 128u + ((pc ^ q) << 4);
-#pragma unroll 2
-        for (int a = a0; a < p.win_atoms; a += 2) {
-          const int ti = t_lo + a;
-          float f[8];
-          const bool ok = col_ok && ti >= 0 && ti < p.Tin && cb < p.Cin;
-          if (ok) {
-            const T* src = X + (static_cast<size_t>(n) * p.Tin + ti) * p.V * p.Cin +
-                           static_cast<size_t>(v) * p.Cin + cb;
-            if (vec_ok) {
-              load8(src, f);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = (cb + i) < p.Cin ? to_f32(src[i]) : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float y = fmaf(f[i], sc[i], sh[i]);
-              if (p.in_relu) y = fmaxf(y, 0.f);
-              f[i] = ((cb + i) < p.Cin) ? y : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = 0.f;
-          }
-          const uint32_t dst = sbase + a * 1024u;
-          if (kParts == 1) {
-            uint4 u = pack8_bf16(f);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(u.x), "r"(u.y),
-                         "r"(u.z), "r"(u.w)
-                         : "memory");
-          } else {
-#pragma unroll
-            for (int part = 0; part < kParts; ++part) {
-              uint4 u = split8_bf16(f);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + part * part_bytes_a),
-                           "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
-                           : "memory");
-            }
-          }
-        }
+        const uint32_t sdst = slots0 + slot * slot_bytes + q * 128u + ((pc ^ q) << 4);
+        if (affine)
+          produce_chunk<T, kParts, true>(colp + cb, pitch_t, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4, p.Cin - cb, vec_ok,
+                                         sc, sh, p.in_relu != 0, sdst, part_bytes_a);
+        else
+          produce_chunk<T, kParts, false>(colp + cb, pitch_t, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4, p.Cin - cb, vec_ok,
+                                          sc, sh, false, sdst, part_bytes_a);
         fence_proxy_async_smem();
         mbar_arrive(win_full(slot));
         if (++slot == p.nslots) {
@@ -184,10 +155,10 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     // ---------------------------------- epilogue ----------------------------------
     T* __restrict__ O = reinterpret_cast<T*>(p.out);
-    const int quad = warp - 4;
+    const int quad = warp - 8;
     const int r = quad * 32 + lane;
     const int q = r & 7;
     int as = 0;
@@ -248,7 +219,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
         aph ^= 1u;
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // -------------------------------- weight loader --------------------------------
     if (lane == 0) {
       const uint8_t* W = reinterpret_cast<const uint8_t*>(p.wpk);
@@ -338,7 +309,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 13) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }

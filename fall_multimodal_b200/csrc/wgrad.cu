@@ -16,6 +16,7 @@
 // TMEM; the row dimension is sliced across CTAs and the partial results are added to global
 // memory with fp32 atomics (dW must be zeroed by the caller).
 #include "common.cuh"
+#include "producer.cuh"
 #include "ptx.cuh"
 
 namespace fmm {
@@ -43,7 +44,8 @@ struct WgradParams {
   unsigned* err;
 };
 
-constexpr int kWgThreads = 192;  // warps 0-3 producers (+ epilogue at the end), 4 = MMA, 5 spare
+constexpr int kWgThreads = 288;  // warps 0-7 producers (0-3 also run the epilogue), 8 = MMA issuer
+constexpr int kWgProducers = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
@@ -79,13 +81,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstages; ++s) {
-      mbar_init(full(s), 128);
+      mbar_init(full(s), kWgProducers);
       mbar_init(empty(s), 1);
     }
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (my_units > 0) {
-    if (warp < 4) {
+    if (warp < 8) {
       // ------------------------------ producers ------------------------------
       const T* __restrict__ X = reinterpret_cast<const T*>(p.x);
       const T* __restrict__ DY = reinterpret_cast<const T*>(p.dy);
@@ -106,6 +108,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       const int a0 = pt >> 6;
       const bool xvec = (p.Cin % 8) == 0;
       const bool yvec = (p.Cout % 8) == 0;
+      const bool affine = p.in_scale != nullptr;
+      const size_t xpitch = static_cast<size_t>(p.V) * p.Cin;
+      const size_t ypitch = static_cast<size_t>(p.V) * p.Cout;
+      const float one[8] = {1, 1, 1, 1, 1, 1, 1, 1}, zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       int st = 0;
       uint32_t ph = 0;
       for (int u = slice; u < p.total_units; u += p.slices) {
@@ -120,82 +126,32 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         mbar_wait(empty(st), ph ^ 1u, p.err, 11);
         const uint32_t a_base = smem_base + st * stage_bytes;
         const uint32_t b_base = a_base + a_bytes;
+        const T* xcol = X + static_cast<size_t>(n) * p.Tin * xpitch + static_cast<size_t>(v) * p.Cin;
+        const T* ycol = DY + static_cast<size_t>(n) * p.Tj * ypitch + static_cast<size_t>(v) * p.Cout;
         // A' : X window, MCH chunks
         for (int h = 0; h < p.MCH; ++h) {
           const int cb = (ci_tile * p.MCH + h) * 64 + pc * 8;
           float sc[8], sh[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const bool ok = (cb + i) < p.Cin;
-            sc[i] = (p.in_scale && ok) ? p.in_scale[cb + i] : 1.f;
-            sh[i] = (p.in_shift && ok) ? p.in_shift[cb + i] : 0.f;
+            const bool ok = affine && (cb + i) < p.Cin;
+            sc[i] = ok ? p.in_scale[cb + i] : 1.f;
+            sh[i] = ok ? p.in_shift[cb + i] : 0.f;
           }
-          const uint32_t sbase = a_base + h * p.win_atoms * 1024u + q * 128u + ((pc ^ q) << 4);
-#pragma unroll 2
-          for (int a = a0; a < p.win_atoms; a += 2) {
-            const int ti = t_lo + a;
-            float f[8];
-            const bool ok = col_ok && ti >= 0 && ti < p.Tin && cb < p.Cin;
-            if (ok) {
-              const T* src = X + (static_cast<size_t>(n) * p.Tin + ti) * p.V * p.Cin +
-                             static_cast<size_t>(v) * p.Cin + cb;
-              if (xvec) {
-                load8(src, f);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = (cb + i) < p.Cin ? to_f32(src[i]) : 0.f;
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float y = fmaf(f[i], sc[i], sh[i]);
-                if (p.in_relu) y = fmaxf(y, 0.f);
-                f[i] = ((cb + i) < p.Cin) ? y : 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = 0.f;
-            }
-            const uint32_t dst = sbase + a * 1024u;
-#pragma unroll
-            for (int part = 0; part < kParts; ++part) {
-              uint4 w = (kParts == 1) ? pack8_bf16(f) : split8_bf16(f);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + part * a_part), "r"(w.x),
-                           "r"(w.y), "r"(w.z), "r"(w.w)
-                           : "memory");
-            }
-          }
+          const uint32_t sdst = a_base + h * p.win_atoms * 1024u + q * 128u + ((pc ^ q) << 4);
+          if (affine)
+            produce_chunk<T, kParts, true>(xcol + cb, xpitch, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4, p.Cin - cb, xvec, sc,
+                                           sh, p.in_relu != 0, sdst, a_part);
+          else
+            produce_chunk<T, kParts, false>(xcol + cb, xpitch, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4, p.Cin - cb, xvec,
+                                            sc, sh, false, sdst, a_part);
         }
         // B' : dY tile, BN/64 chunks x JT atoms
         for (int h = 0; h < p.BN / 64; ++h) {
           const int cb = co_tile * p.BN + h * 64 + pc * 8;
-          const uint32_t sbase = b_base + h * p.JT * 1024u + q * 128u + ((pc ^ q) << 4);
-#pragma unroll 2
-          for (int a = a0; a < p.JT; a += 2) {
-            const int j = j0 + a;
-            float f[8];
-            const bool ok = col_ok && j < p.Tj && cb < p.Cout;
-            if (ok) {
-              const T* src = DY + (static_cast<size_t>(n) * p.Tj + j) * p.V * p.Cout +
-                             static_cast<size_t>(v) * p.Cout + cb;
-              if (yvec) {
-                load8(src, f);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = (cb + i) < p.Cout ? to_f32(src[i]) : 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = 0.f;
-            }
-            const uint32_t dst = sbase + a * 1024u;
-#pragma unroll
-            for (int part = 0; part < kParts; ++part) {
-              uint4 w = (kParts == 1) ? pack8_bf16(f) : split8_bf16(f);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + part * b_part), "r"(w.x),
-                           "r"(w.y), "r"(w.z), "r"(w.w)
-                           : "memory");
-            }
-          }
+          const uint32_t sdst = b_base + h * p.JT * 1024u + q * 128u + ((pc ^ q) << 4);
+          produce_chunk<T, kParts, false>(ycol + cb, ypitch, col_ok, p.Tj, j0, p.JT, a0, 4, p.Cout - cb, yvec, one, zero,
+                                          false, sdst, b_part);
         }
         fence_proxy_async_smem();
         mbar_arrive(full(st));
@@ -204,6 +160,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           ph ^= 1u;
         }
       }
+    }
+    if (warp < 4) {
       // ------------------------------ epilogue (same warps) ------------------------------
       mbar_wait(acc_full, 0, p.err, 12);
       tc_fence_after();
@@ -235,7 +193,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           }
         }
       }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
       // ---------------------------------- MMA issuer ----------------------------------
       if (lane == 0) {
         const uint32_t idesc = make_idesc_bf16(p.BN, 1, 1);
@@ -285,7 +243,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }

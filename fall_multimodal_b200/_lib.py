@@ -92,7 +92,7 @@ _SIGNATURES = {
     "fmm_tapconv": [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                     c_int, c_int, c_int, c_int, C.POINTER(c_int), c_int, _P, _P],
     "fmm_agg_fwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
-    "fmm_agg_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_agg_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_dcoef": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_colstats": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_block_out": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],

@@ -80,38 +80,84 @@ __global__ void agg_fwd_scalar_kernel(const T* __restrict__ x, T* __restrict__ x
 // agg_bwd: dx[(n,t,v), ci] = addend + sum_{e in out(v)} coef[e] * P[(n,t,dst[e]), kk[e]*Cin+ci]
 // CSR over v: rowptr[V+1], dst[E], kk[E], coef[E].
 // ------------------------------------------------------------------------------------------
+// With `x` given, the same pass also accumulates the edge-coefficient gradient
+//   dcoef[eid[e]] += sum_{n,t,ci} x[(n,t,v),ci] * P[(n,t,dst[e]), kk[e]*Cin+ci]
+// (every P piece is read exactly once by the thread that needs it for dx, so this costs no traffic).
+constexpr int kMaxOutEdges = 8;
 template <typename T>
 __global__ void agg_bwd_vec_kernel(const T* __restrict__ P, const T* __restrict__ addend, T* __restrict__ dx,
                                    const int* __restrict__ rowptr, const int* __restrict__ dst,
-                                   const int* __restrict__ kk, const float* __restrict__ coef, int Tn, int V,
-                                   int Cin, int K, int tchunk) {
+                                   const int* __restrict__ kk, const float* __restrict__ coef,
+                                   const T* __restrict__ x, const int* __restrict__ eid, float* __restrict__ dcoef,
+                                   int Tn, int V, int Cin, int K, int tchunk) {
   const int n = blockIdx.y;
   const int t0 = blockIdx.x * tchunk;
   const int t1 = min(t0 + tchunk, Tn);
   const int c8n = Cin / 8;
   const int pairs = V * c8n;
   const size_t prow = static_cast<size_t>(K) * Cin;
-  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
-    const int c8 = i % c8n;
-    const int v = i / c8n;
-    const int e0 = rowptr[v], e1 = rowptr[v + 1];
-    for (int t = t0; t < t1; ++t) {
+  const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32;
+  for (int i0 = 0; i0 < pairs; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const bool active = i < pairs;
+    const int c8 = active ? i % c8n : 0;
+    const int v = active ? i / c8n : 0;
+    const int e0 = active ? rowptr[v] : 0, e1 = active ? rowptr[v + 1] : 0;
+    float dc[kMaxOutEdges];
+#pragma unroll
+    for (int j = 0; j < kMaxOutEdges; ++j) dc[j] = 0.f;
+    for (int t = t0; t < t1 && active; ++t) {
       const size_t frame = static_cast<size_t>(n) * Tn + t;
-      float acc[8];
+      float acc[8], xv[8];
       if (addend) {
         load8(addend + (frame * V + v) * Cin + c8 * 8, acc);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
       }
-      for (int e = e0; e < e1; ++e) {
+      if (x) load8(x + (frame * V + v) * Cin + c8 * 8, xv);
+#pragma unroll
+      for (int j = 0; j < kMaxOutEdges; ++j) {
+        const int e = e0 + j;
+        if (e < e1) {
+          float f[8];
+          load8(P + (frame * V + dst[e]) * prow + kk[e] * Cin + c8 * 8, f);
+          const float cf = coef[e];
+          float d = 0.f;
+#pragma unroll
+          for (int l = 0; l < 8; ++l) {
+            acc[l] = fmaf(cf, f[l], acc[l]);
+            if (x) d = fmaf(xv[l], f[l], d);
+          }
+          dc[j] += d;
+        }
+      }
+      for (int e = e0 + kMaxOutEdges; e < e1; ++e) {  // rare: joints with more than 8 out-edges
         float f[8];
         load8(P + (frame * V + dst[e]) * prow + kk[e] * Cin + c8 * 8, f);
         const float cf = coef[e];
+        float d = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(cf, f[j], acc[j]);
+        for (int l = 0; l < 8; ++l) {
+          acc[l] = fmaf(cf, f[l], acc[l]);
+          if (x) d = fmaf(xv[l], f[l], d);
+        }
+        if (x) atomicAdd(dcoef + eid[e], d);
       }
       store8(dx + (frame * V + v) * Cin + c8 * 8, acc);
+    }
+    if (x) {
+      // reduce over the channel groups of one joint (consecutive lanes), one atomic per (block, edge)
+#pragma unroll
+      for (int j = 0; j < kMaxOutEdges; ++j) {
+        float d = dc[j];
+        if (pow2) {
+          for (int off = c8n >> 1; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+          if (active && c8 == 0 && e0 + j < e1) atomicAdd(dcoef + eid[e0 + j], d);
+        } else if (active && e0 + j < e1) {
+          atomicAdd(dcoef + eid[e0 + j], d);
+        }
+      }
     }
   }
 }
@@ -168,14 +214,30 @@ __global__ void agg_dcoef_kernel(const T* __restrict__ x, const T* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// Block-wide reduction helper: every thread holds NV partial values for channel group c8 of
-// pair i (pairs i = v*c8n + c8). Sums over v (and the block's strided pairs) are done through
-// shared memory: red[c8n*8][NV].
+// Row-walk mapping for everything that needs no per-joint output: a block owns the contiguous rows
+// [t0*V, t1*V) of clip n; thread = (8-channel group c8 = tid % c8n, row lane = tid / c8n) walks
+// the rows with stride blockDim/c8n. Perfectly balanced for any V, coalesced, per-channel
+// coefficients in registers. Per-channel partial sums are reduced with warp shuffles over the lanes
+// that share c8, then shared-memory atomics across warps, then ONE global atomic per channel.
 // ------------------------------------------------------------------------------------------
 template <int NV>
-__device__ __forceinline__ void smem_accumulate(float* red, int c, const float (&val)[NV]) {
+__device__ __forceinline__ void block_channel_reduce(float (&val)[NV][8], float* red, int c8, int c8n) {
+  const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32;
+  const int lane = threadIdx.x & 31;
+  if (pow2) {
+    for (int off = 16; off >= c8n; off >>= 1) {
 #pragma unroll
-  for (int j = 0; j < NV; ++j) atomicAdd(red + c * NV + j, val[j]);
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) val[v][j] += __shfl_xor_sync(0xffffffffu, val[v][j], off);
+    }
+  }
+  if (!pow2 || lane < c8n) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(red + (c8 * 8 + j) * NV + v, val[v][j]);
+  }
 }
 
 // colstats: per-channel sum / sum of squares (double) and optional per-(n,c) sums (float) of X.
@@ -184,30 +246,27 @@ __global__ void colstats_kernel(const T* __restrict__ X, double* __restrict__ ch
                                 float* __restrict__ nc_sum, int Tn, int V, int C, int tchunk) {
   extern __shared__ float red[];  // [C][2]
   const int n = blockIdx.y;
-  const int t0 = blockIdx.x * tchunk;
-  const int t1 = min(t0 + tchunk, Tn);
+  const int r0 = blockIdx.x * tchunk * V;
+  const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int c8n = C / 8;
-  const int pairs = V * c8n;
-  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
-    const int c8 = i % c8n;
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = t0; t < t1; ++t) {
-      float f[8];
-      load8(X + (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8, f);
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
+  const T* base = X + static_cast<size_t>(n) * Tn * V * C + c8 * 8;
+  float acc[2][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += f[j];
-        q[j] = fmaf(f[j], f[j], q[j]);
-      }
-    }
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+#pragma unroll 4
+  for (int r = r0 + rl; r < r1; r += RL) {
+    float f[8];
+    load8(base + static_cast<size_t>(r) * C, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(red + (c8 * 8 + j) * 2, s[j]);
-      atomicAdd(red + (c8 * 8 + j) * 2 + 1, q[j]);
+      acc[0][j] += f[j];
+      acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
     }
   }
+  block_channel_reduce<2>(acc, red, c8, c8n);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float s = red[2 * c], q = red[2 * c + 1];
@@ -223,33 +282,33 @@ __global__ void block_out_kernel(const T* __restrict__ U, const float* __restric
                                  const T* __restrict__ res, const float* __restrict__ ar,
                                  const float* __restrict__ br, T* __restrict__ Y, int Tn, int V, int C, int tchunk) {
   const int n = blockIdx.y;
-  const int t0 = blockIdx.x * tchunk;
-  const int t1 = min(t0 + tchunk, Tn);
+  const int r0 = blockIdx.x * tchunk * V;
+  const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
   const int c8n = C / 8;
-  const int pairs = V * c8n;
-  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
-    const int c0 = (i % c8n) * 8;
-    float a[8], b[8], ra[8], rb[8];
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
+  const int c0 = c8 * 8;
+  float a[8], b[8], ra[8], rb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = k1[static_cast<size_t>(n) * C + c0 + j];
+    b[j] = k0[static_cast<size_t>(n) * C + c0 + j];
+    ra[j] = ar ? ar[c0 + j] : 1.f;
+    rb[j] = br ? br[c0 + j] : 0.f;
+  }
+  const size_t base = static_cast<size_t>(n) * Tn * V * C + c0;
+#pragma unroll 4
+  for (int r = r0 + rl; r < r1; r += RL) {
+    const size_t off = base + static_cast<size_t>(r) * C;
+    float u[8], rr[8], y[8];
+    load8(U + off, u);
+    if (res) load8(res + off, rr);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      a[j] = k1[static_cast<size_t>(n) * C + c0 + j];
-      b[j] = k0[static_cast<size_t>(n) * C + c0 + j];
-      ra[j] = ar ? ar[c0 + j] : 1.f;
-      rb[j] = br ? br[c0 + j] : 0.f;
+      float v = fmaf(a[j], u[j], b[j]);
+      if (res) v += fmaf(ra[j], rr[j], rb[j]);
+      y[j] = fmaxf(v, 0.f);
     }
-    for (int t = t0; t < t1; ++t) {
-      const size_t off = (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8;
-      float u[8], r[8], y[8];
-      load8(U + off, u);
-      if (res) load8(res + off, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v = fmaf(a[j], u[j], b[j]);
-        if (res) v += fmaf(ra[j], r[j], rb[j]);
-        y[j] = fmaxf(v, 0.f);
-      }
-      store8(Y + off, y);
-    }
+    store8(Y + off, y);
   }
 }
 
@@ -260,37 +319,33 @@ __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __
                                            float* __restrict__ S3, int Tn, int V, int C, int tchunk) {
   extern __shared__ float red[];  // [C][3]
   const int n = blockIdx.y;
-  const int t0 = blockIdx.x * tchunk;
-  const int t1 = min(t0 + tchunk, Tn);
+  const int r0 = blockIdx.x * tchunk * V;
+  const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int c8n = C / 8;
-  const int pairs = V * c8n;
-  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
-    const int c0 = (i % c8n) * 8;
-    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s3[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = t0; t < t1; ++t) {
-      const size_t off = (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8;
-      float g[8], y[8], u[8], r[8];
-      load8(dY + off, g);
-      load8(Y + off, y);
-      load8(U + off, u);
-      if (R) load8(R + off, r);
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
+  const size_t base = static_cast<size_t>(n) * Tn * V * C + c8 * 8;
+  float acc[3][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = y[j] > 0.f ? g[j] : 0.f;
-        s1[j] += d;
-        s2[j] = fmaf(d, u[j], s2[j]);
-        if (R) s3[j] = fmaf(d, r[j], s3[j]);
-      }
-    }
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
+#pragma unroll 2
+  for (int r = r0 + rl; r < r1; r += RL) {
+    const size_t off = base + static_cast<size_t>(r) * C;
+    float g[8], y[8], u[8], rr[8];
+    load8(dY + off, g);
+    load8(Y + off, y);
+    load8(U + off, u);
+    if (R) load8(R + off, rr);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(red + (c0 + j) * 3, s1[j]);
-      atomicAdd(red + (c0 + j) * 3 + 1, s2[j]);
-      if (R) atomicAdd(red + (c0 + j) * 3 + 2, s3[j]);
+      const float d = y[j] > 0.f ? g[j] : 0.f;
+      acc[0][j] += d;
+      acc[1][j] = fmaf(d, u[j], acc[1][j]);
+      if (R) acc[2][j] = fmaf(d, rr[j], acc[2][j]);
     }
   }
+  block_channel_reduce<3>(acc, red, c8, c8n);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     atomicAdd(S1 + static_cast<size_t>(n) * C + c, red[3 * c]);
@@ -314,55 +369,50 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
                                      double* __restrict__ sum_dR, int Tn, int V, int C, int tchunk) {
   extern __shared__ float red[];  // [C][2]
   const int n = blockIdx.y;
-  const int t0 = blockIdx.x * tchunk;
-  const int t1 = min(t0 + tchunk, Tn);
+  const int r0 = blockIdx.x * tchunk * V;
+  const int r1r = min((blockIdx.x + 1) * tchunk, Tn) * V;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int c8n = C / 8;
-  const int pairs = V * c8n;
-  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
-    const int c0 = (i % c8n) * 8;
-    float a1[8], a2[8], a3[8], b1[8], b2[8], b3[8];
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
+  const int c0 = c8 * 8;
+  float a1[8], a2[8], a3[8], b1[8], b2[8], b3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a1[j] = k1[static_cast<size_t>(n) * C + c0 + j];
+    a2[j] = k2[c0 + j];
+    a3[j] = k3[static_cast<size_t>(n) * C + c0 + j];
+    b1[j] = R ? r1[c0 + j] : 0.f;
+    b2[j] = R ? r2[c0 + j] : 0.f;
+    b3[j] = R ? r3[c0 + j] : 0.f;
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  const size_t base = static_cast<size_t>(n) * Tn * V * C + c0;
+#pragma unroll 2
+  for (int r = r0 + rl; r < r1r; r += RL) {
+    const size_t off = base + static_cast<size_t>(r) * C;
+    float g[8], y[8], u[8], rr[8], ou[8], orr[8], d[8];
+    load8(dY + off, g);
+    load8(Y + off, y);
+    load8(U + off, u);
+    if (R) load8(R + off, rr);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      a1[j] = k1[static_cast<size_t>(n) * C + c0 + j];
-      a2[j] = k2[c0 + j];
-      a3[j] = k3[static_cast<size_t>(n) * C + c0 + j];
-      b1[j] = R ? r1[c0 + j] : 0.f;
-      b2[j] = R ? r2[c0 + j] : 0.f;
-      b3[j] = R ? r3[c0 + j] : 0.f;
-    }
-    float su[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = t0; t < t1; ++t) {
-      const size_t off = (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8;
-      float g[8], y[8], u[8], r[8], ou[8], orr[8], d[8];
-      load8(dY + off, g);
-      load8(Y + off, y);
-      load8(U + off, u);
-      if (R) load8(R + off, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        d[j] = y[j] > 0.f ? g[j] : 0.f;
-        ou[j] = fmaf(a1[j], d[j], fmaf(a2[j], u[j], a3[j]));
-        su[j] += to_f32(from_f32<T>(ou[j]));
-        if (R) {
-          orr[j] = fmaf(b1[j], d[j], fmaf(b2[j], r[j], b3[j]));
-          sr[j] += to_f32(from_f32<T>(orr[j]));
-        }
+      d[j] = y[j] > 0.f ? g[j] : 0.f;
+      ou[j] = fmaf(a1[j], d[j], fmaf(a2[j], u[j], a3[j]));
+      acc[0][j] += to_f32(from_f32<T>(ou[j]));
+      if (R) {
+        orr[j] = fmaf(b1[j], d[j], fmaf(b2[j], rr[j], b3[j]));
+        acc[1][j] += to_f32(from_f32<T>(orr[j]));
       }
-      store8(dU + off, ou);
-      if (R) store8(dR + off, orr);
-      if (dPre) store8(dPre + off, d);
     }
-    if (sum_dU) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(red + (c0 + j) * 2, su[j]);
-    }
-    if (sum_dR) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(red + (c0 + j) * 2 + 1, sr[j]);
-    }
+    store8(dU + off, ou);
+    if (R) store8(dR + off, orr);
+    if (dPre) store8(dPre + off, d);
   }
+  if (sum_dU || sum_dR) block_channel_reduce<2>(acc, red, c8, c8n);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     if (sum_dU) atomic_add_f64(sum_dU + c, static_cast<double>(red[2 * c]));
@@ -377,39 +427,36 @@ __global__ void bn1_bwd_reduce_kernel(const T* __restrict__ dH, const T* __restr
                                       double* __restrict__ T2, int Tn, int V, int C, int tchunk) {
   extern __shared__ float red[];  // [C][2]
   const int n = blockIdx.y;
-  const int t0 = blockIdx.x * tchunk;
-  const int t1 = min(t0 + tchunk, Tn);
+  const int r0 = blockIdx.x * tchunk * V;
+  const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int c8n = C / 8;
-  const int pairs = V * c8n;
-  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
-    const int c0 = (i % c8n) * 8;
-    float a[8], b[8];
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = a1[c8 * 8 + j];
+    b[j] = b1[c8 * 8 + j];
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  const size_t base = static_cast<size_t>(n) * Tn * V * C + c8 * 8;
+#pragma unroll 4
+  for (int r = r0 + rl; r < r1; r += RL) {
+    const size_t off = base + static_cast<size_t>(r) * C;
+    float g[8], h[8];
+    load8(dH + off, h);
+    load8(G + off, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      a[j] = a1[c0 + j];
-      b[j] = b1[c0 + j];
-    }
-    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = t0; t < t1; ++t) {
-      const size_t off = (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8;
-      float g[8], h[8];
-      load8(dH + off, h);
-      load8(G + off, g);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = fmaf(a[j], g[j], b[j]) > 0.f ? h[j] : 0.f;
-        s1[j] += d;
-        s2[j] = fmaf(d, g[j], s2[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(red + (c0 + j) * 2, s1[j]);
-      atomicAdd(red + (c0 + j) * 2 + 1, s2[j]);
+      const float d = fmaf(a[j], g[j], b[j]) > 0.f ? h[j] : 0.f;
+      acc[0][j] += d;
+      acc[1][j] = fmaf(d, g[j], acc[1][j]);
     }
   }
+  block_channel_reduce<2>(acc, red, c8, c8n);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     atomic_add_f64(T1 + c, static_cast<double>(red[2 * c]));
@@ -460,6 +507,19 @@ __global__ void bn1_bwd_apply_kernel(const T* __restrict__ dH, const T* __restri
   }
 }
 
+// threads for the row-walk kernels: a multiple of the channel groups (fixed c8 per thread)
+static inline int rowwalk_threads(int C) {
+  const int c8n = C / 8;
+  int t = (kEwThreads / c8n) * c8n;
+  return t < c8n ? c8n : t;
+}
+// threads for the (joint, channel-group) pair kernels: balance the strided loop over the pairs
+static inline int pair_threads(int pairs) {
+  const int iters = (pairs + 511) / 512;
+  int t = ((pairs + iters - 1) / iters + 31) / 32 * 32;
+  return t > 1024 ? 1024 : t;
+}
+
 static inline int pick_tchunk(int N, int Tn) {
   // enough blocks to fill the machine a few times over, but long enough frame walks per thread
   int chunk = Tn;
@@ -492,7 +552,7 @@ int fmm_agg_fwd(const void* x, void* xa, const int* rowptr, const int* src, cons
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
     if (Cin % 8 == 0)
-      agg_fwd_vec_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)x, (T*)xa, rowptr, src, coef, Tn, V, Cin, K, tchunk);
+      agg_fwd_vec_kernel<T><<<grid, pair_threads(V * K * (Cin / 8)), 0, stream>>>((const T*)x, (T*)xa, rowptr, src, coef, Tn, V, Cin, K, tchunk);
     else
       agg_fwd_scalar_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)x, (T*)xa, rowptr, src, coef, Tn, V, Cin, K, tchunk);
   })
@@ -501,13 +561,16 @@ int fmm_agg_fwd(const void* x, void* xa, const int* rowptr, const int* src, cons
 }
 
 int fmm_agg_bwd(const void* P, const void* addend, void* dx, const int* rowptr, const int* dst, const int* kk,
-                const float* coef, int N, int Tn, int V, int Cin, int K, int dtype, cudaStream_t stream) {
+                const float* coef, const void* x, const int* eid, float* dcoef, int N, int Tn, int V, int Cin, int K,
+                int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(!x || (eid && dcoef), "agg_bwd: dcoef accumulation needs eid and dcoef");
+  FMM_CHECK_ARG(!x || Cin % 8 == 0, "agg_bwd: fused dcoef needs Cin %% 8 == 0 (use agg_dcoef)");
   FMM_CHECK_ARG(P && dx && rowptr && dst && kk && coef && N > 0 && Tn > 0 && V > 0 && Cin > 0 && K > 0, "agg_bwd: bad args");
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
     if (Cin % 8 == 0)
-      agg_bwd_vec_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)P, (const T*)addend, (T*)dx, rowptr, dst, kk, coef, Tn, V, Cin, K, tchunk);
+      agg_bwd_vec_kernel<T><<<grid, pair_threads(V * (Cin / 8)), 0, stream>>>((const T*)P, (const T*)addend, (T*)dx, rowptr, dst, kk, coef, (const T*)x, eid, dcoef, Tn, V, Cin, K, tchunk);
     else
       agg_bwd_scalar_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)P, (const T*)addend, (T*)dx, rowptr, dst, kk, coef, Tn, V, Cin, K, tchunk);
   })
@@ -533,7 +596,7 @@ int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, in
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    colstats_kernel<T><<<grid, kEwThreads, 2 * C * sizeof(float), stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, Tn, V, C, tchunk);
+    colstats_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, Tn, V, C, tchunk);
   })
   FMM_CHECK_LAUNCH("colstats");
   return FMM_OK;
@@ -545,7 +608,7 @@ int fmm_block_out(const void* U, const float* k1, const float* k0, const void* r
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    block_out_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)U, k1, k0, (const T*)res, ar, br, (T*)Y, Tn, V, C, tchunk);
+    block_out_kernel<T><<<grid, rowwalk_threads(C), 0, stream>>>((const T*)U, k1, k0, (const T*)res, ar, br, (T*)Y, Tn, V, C, tchunk);
   })
   FMM_CHECK_LAUNCH("block_out");
   return FMM_OK;
@@ -557,7 +620,7 @@ int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const 
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    blockout_bwd_reduce_kernel<T><<<grid, kEwThreads, 3 * C * sizeof(float), stream>>>(
+    blockout_bwd_reduce_kernel<T><<<grid, rowwalk_threads(C), 3 * C * sizeof(float), stream>>>(
         (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, S1, S2, S3, Tn, V, C, tchunk);
   })
   FMM_CHECK_LAUNCH("blockout_bwd_reduce");
@@ -573,7 +636,7 @@ int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* 
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    bn2_bwd_apply_kernel<T><<<grid, kEwThreads, 2 * C * sizeof(float), stream>>>(
+    bn2_bwd_apply_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>(
         (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, k1, k2, k3, r1, r2, r3, (T*)dU, (T*)dR, (T*)dPre, sum_dU,
         sum_dR, Tn, V, C, tchunk);
   })
@@ -587,7 +650,7 @@ int fmm_bn1_bwd_reduce(const void* dH, const void* G, const float* a1, const flo
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    bn1_bwd_reduce_kernel<T><<<grid, kEwThreads, 2 * C * sizeof(float), stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, Tn, V, C, tchunk);
+    bn1_bwd_reduce_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, Tn, V, C, tchunk);
   })
   FMM_CHECK_LAUNCH("bn1_bwd_reduce");
   return FMM_OK;
@@ -600,7 +663,7 @@ int fmm_bn1_bwd_apply(const void* dH, const void* G, const float* a1, const floa
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    bn1_bwd_apply_kernel<T><<<grid, kEwThreads, 0, stream>>>((const T*)dH, (const T*)G, a1, b1, c1, c2, c3, (T*)dG, Tbl, Tn, V, C, tchunk);
+    bn1_bwd_apply_kernel<T><<<grid, pair_threads(V * (C / 8)), 0, stream>>>((const T*)dH, (const T*)G, a1, b1, c1, c2, c3, (T*)dG, Tbl, Tn, V, C, tchunk);
   })
   FMM_CHECK_LAUNCH("bn1_bwd_apply");
   return FMM_OK;

@@ -231,19 +231,39 @@ __global__ void se_bwd_dp_kernel(const float* __restrict__ dh, const float* __re
   }
 }
 
-// out[p][q] += sum_n A[n][p] * B[n][q]  and (optional) colsum[p] += sum_n A[n][p]   (grid = P)
+// out[p][q] += sum_n A[n][p] * B[n][q]  and (optional) colsum[p] += sum_n A[n][p]   (grid = P, 256 threads:
+// q lanes x n-splits, reduced through shared memory)
 __global__ void small_tn_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out,
                                      float* __restrict__ colsum, int N, int P, int Q) {
+  __shared__ float red[256];
+  __shared__ float cs[256];
   const int pp = blockIdx.x;
-  for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+  const int qn = Q < 256 ? Q : 256;
+  const int ns = 256 / qn;
+  const int ql = threadIdx.x % qn, sl = threadIdx.x / qn;
+  float csum = 0.f;
+  for (int q0 = 0; q0 < Q; q0 += qn) {
+    const int q = q0 + ql;
     float acc = 0.f;
-    for (int n = 0; n < N; ++n) acc = fmaf(A[static_cast<size_t>(n) * P + pp], B[static_cast<size_t>(n) * Q + q], acc);
-    out[static_cast<size_t>(pp) * Q + q] += acc;
+    if (sl < ns && q < Q)
+      for (int n = sl; n < N; n += ns) acc = fmaf(A[static_cast<size_t>(n) * P + pp], B[static_cast<size_t>(n) * Q + q], acc);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (sl == 0 && q < Q) {
+      for (int k = 1; k < ns; ++k) acc += red[k * qn + ql];
+      out[static_cast<size_t>(pp) * Q + q] += acc;
+    }
+    __syncthreads();
   }
-  if (colsum && threadIdx.x == 0) {
-    float acc = 0.f;
-    for (int n = 0; n < N; ++n) acc += A[static_cast<size_t>(n) * P + pp];
-    colsum[pp] += acc;
+  if (colsum) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) csum += A[static_cast<size_t>(n) * P + pp];
+    cs[threadIdx.x] = csum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int k = 0; k < 256; ++k) t += cs[k];
+      colsum[pp] += t;
+    }
   }
 }
 
@@ -386,7 +406,7 @@ int fmm_se_bwd(const float* S1, const float* S2, const float* a2, const float* b
   se_bwd_a_kernel<<<N, 256, C * sizeof(float), stream>>>(S1, S2, a2, b2, s, h, ah, bh, W2, dq, dhr, r, C, C4);
   se_bwd_bn_kernel<<<C4, 128, 0, stream>>>(dhr, h, ah, hmean, hrstd, training, dh, dgamma, dbeta, N, C4);
   se_bwd_dp_kernel<<<N, 256, C4 * sizeof(float), stream>>>(dh, W1, dp, C, C4);
-  small_tn_gemm_kernel<<<C, 64, 0, stream>>>(dq, r, dW2, db2se, N, C, C4);   // dW2[c][j] = sum_n dq[n,c] r[n,j]
+  small_tn_gemm_kernel<<<C, 256, 0, stream>>>(dq, r, dW2, db2se, N, C, C4);   // dW2[c][j] = sum_n dq[n,c] r[n,j]
   small_tn_gemm_kernel<<<C4, 256, 0, stream>>>(dh, p, dW1, db1, N, C4, C);   // dW1[j][c] = sum_n dh[n,j] p[n,c]
   FMM_CHECK_LAUNCH("se_bwd");
   return FMM_OK;

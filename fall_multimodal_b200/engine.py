@@ -72,6 +72,7 @@ class TrunkEngine:
             d = {"fwd_rowptr": t(c["fwd_rowptr"]), "fwd_src": t(c["fwd_src"]), "dst": t(c["dst"]), "kk": t(c["kk"]),
                  "dense_idx": t(c["dense_idx"], torch.int64), "bwd_rowptr": t(c["bwd_rowptr"]),
                  "bwd_perm": t(c["bwd_perm"], torch.int64)}
+            d["eid_b"] = d["bwd_perm"].to(torch.int32).contiguous()
             d["dst_b"] = d["dst"][d["bwd_perm"]].contiguous()
             d["kk_b"] = d["kk"][d["bwd_perm"]].contiguous()
             self._dev[key] = d
@@ -300,11 +301,9 @@ class TrunkEngine:
             Pm = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
             ops.tapconv(dG, pw_gT, Pm, shifts=[0], tj=T)
             dcoef = arena.f32(self.E)
-            ops.agg_dcoef(x, Pm, dcoef, csr["fwd_src"], csr["dst"], csr["kk"], K)
-            bg = P[pre + "gcn.conv.bias"].view(K, Cout)
-            dA = torch.zeros(K * V * V, dtype=torch.float32, device=dev)
-            dA[csr["dense_idx"]] = dcoef
-            grads[f"edge_importance.{i}"] = A * (dA.view(K, V, V) + (bg @ Tbl.t())[:, None, :])
+            fused_dcoef = Cin % 8 == 0
+            if not fused_dcoef:
+                ops.agg_dcoef(x, Pm, dcoef, csr["fwd_src"], csr["dst"], csr["kk"], K)
 
             # ---- residual branch ----
             addend = None
@@ -323,7 +322,15 @@ class TrunkEngine:
 
             dx = torch.empty_like(x)
             coef_b = b["coef_f"][csr["bwd_perm"]].contiguous()
-            ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K)
+            if fused_dcoef:
+                ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K, x=x,
+                            eid=csr["eid_b"], dcoef=dcoef)
+            else:
+                ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K)
+            bg = P[pre + "gcn.conv.bias"].view(K, Cout)
+            dA = torch.zeros(K * V * V, dtype=torch.float32, device=dev)
+            dA[csr["dense_idx"]] = dcoef
+            grads[f"edge_importance.{i}"] = A * (dA.view(K, V, V) + (bg @ Tbl.t())[:, None, :])
             if self.debug is not None:
                 self.debug[i] = dict(dY=dY, dU=dU, dH=dH, dG=dG, P=Pm, dx=dx, S1=S1, S2=S2, dp=dp, dR=dR, c1=c1, c2=c2,
                                      c3=c3, T1=T1, T2=T2, saved=b)

@@ -131,12 +131,15 @@ def agg_fwd(x, xa, rowptr, src, coef, K):
     return xa
 
 
-def agg_bwd(P, addend, dx, rowptr, dst, kk, coef, K):
+def agg_bwd(P, addend, dx, rowptr, dst, kk, coef, K, x=None, eid=None, dcoef=None):
+    """dx = addend + A^T-aggregate(P); with ``x`` also dcoef[eid[e]] += <x[src e], P[dst e, k e]> (fused)."""
     N, Tn, V, Cin = _shape4(dx)
     assert P.shape == (N, Tn, V, K * Cin) and P.is_contiguous() and dx.is_contiguous()
     assert addend is None or (addend.shape == dx.shape and addend.is_contiguous())
+    assert x is None or (x.shape == dx.shape and x.is_contiguous())
     L.check(L.load().fmm_agg_bwd(L.ptr(P), L.ptr(addend), L.ptr(dx), L.ptr(rowptr), L.ptr(dst), L.ptr(kk),
-                                 L.ptr(coef), N, Tn, V, Cin, K, L.dt_of(dx.dtype), L.stream()), "agg_bwd")
+                                 L.ptr(coef), L.ptr(x), L.ptr(eid), L.ptr(dcoef), N, Tn, V, Cin, K,
+                                 L.dt_of(dx.dtype), L.stream()), "agg_bwd")
     return dx
 
 

@@ -1,0 +1,139 @@
+/* libfmm_b200 — C ABI of the B200-native (sm_100a) kernels behind the GSTCAN fall/HAR train step.
+ *
+ * The reference (musaru/Fall_Multimodal) is pure PyTorch: it has no operator/FFI layer, its hot path
+ * is whatever ATen dispatches for the call sites below. This header is therefore the boundary a
+ * maintainer binds INSTEAD of those torch calls (ctypes stub: fall_multimodal_b200/_lib.py; see
+ * INTEGRATION.md). Reference file:line citations are relative to
+ * /root/reference/Fall_2_Spatial_Temporal_SR/Model/ unless stated otherwise.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (allocated by PyTorch's caching
+ *     allocator); the library never allocates, frees or keeps device memory;
+ *   - activations are channels-last [N][T][V][C] contiguous, dtype FMM_DT_BF16 or FMM_DT_F32
+ *     (fp32 activations run the tensor cores in a bf16x3 split with fp32-grade products);
+ *     statistics, coefficients and parameter gradients are fp32 / fp64 as noted;
+ *   - all launches go to the given stream and return immediately; return 0 on success, a negative
+ *     status otherwise (fmm_last_error() has the text). There is NO CPU fallback;
+ *   - `err` (may be NULL) is a device word the GEMM kernels write before trapping if an mbarrier
+ *     wait exceeds ~2 s (protocol watchdog: a bug becomes a CUDA error, not a hung GPU).
+ */
+#ifndef FMM_B200_H
+#define FMM_B200_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMM_DT_BF16 0
+#define FMM_DT_F32 1
+
+const char* fmm_last_error(void);
+int fmm_version(void);
+int fmm_device_supported(void); /* 1 iff the current device is sm_100 */
+
+/* ---------------------------------------------------------------------------------------------
+ * tcgen05 GEMM engines
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[n, j*ostride+ooff, v, co] = bias + sum_{m<ntaps} sum_ci f(x[n, j*istride+shifts[m], v, ci]) * W[m][co][ci]
+ * f(x) = relu?(x*in_scale[ci]+in_shift[ci]); zero outside [0,Tin) (padding after the prologue).
+ * Replaces: nn.Conv2d (9,1) stride (s,1) pad (4,0) with the preceding BatchNorm2d+ReLU (stgcan.py:112-118),
+ * the 1x1 conv of GraphConvolution on the aggregated input (stgcan.py:51-54, reassociated), the strided
+ * residual 1x1 conv (stgcan.py:128-131), and the dgrads of all three (autograd of the same lines).
+ * `wpk` comes from fmm_tapconv_pack; bias_per_joint: bias is [V][Cout] (the graph-conv bias folded through
+ * the adjacency column sums). */
+int fmm_tapconv_bn(int cout, int dtype);
+long long fmm_tapconv_packed_bytes(int cin, int cout, int ntaps, int dtype);
+int fmm_tapconv_pack(const float* w, void* out, int cout, int cin, int n2, int k2, long long sn1, long long sn2,
+                     long long sk1, long long sk2, long long sm, int ntaps, const int* tapmap, int dtype,
+                     cudaStream_t stream);
+int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale, const float* in_shift, int in_relu,
+                const float* bias, int bias_per_joint, int N, int V, int Tin, int Tout, int Cin, int Cout, int Tj,
+                int istride, int ostride, int ooff, int ntaps, const int* shifts, int dtype, unsigned* err,
+                cudaStream_t stream);
+
+/* dw[m*s_m + (ci/c2)*s_c1 + (ci%c2)*s_c2 + co*s_co] += sum_{n,v,j} f(x[n, j*istride+shifts[m], v, ci]) * dy[n,j,v,co]
+ * (fp32 atomics: zero dw first). Replaces the weight gradients autograd computes for the three convs above. */
+int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, const float* in_shift, int in_relu,
+              int N, int V, int Tin, int Tj, int Cin, int Cout, int istride, int ntaps, const int* shifts, int c2,
+              long long s_m, long long s_c1, long long s_c2, long long s_co, int dtype, unsigned* err,
+              cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * memory-bound kernels (one pass over an activation each)
+ * ------------------------------------------------------------------------------------------- */
+
+/* xa[(n,t,w), k*Cin+ci] = sum_{e in in(k,w)} coef[e] * x[(n,t,src[e]), ci]   — einsum 'nkctv,kvw->nctw'
+ * (stgcan.py:54) with A*importance (stgcan.py:222) in CSR form, applied to the INPUT channels. */
+int fmm_agg_fwd(const void* x, void* xa, const int* rowptr, const int* src, const float* coef, int N, int T, int V,
+                int Cin, int K, int dtype, cudaStream_t stream);
+/* dx = addend + A^T-aggregate(P); with x != NULL also dcoef[eid[e]] += <x[src e], P[dst e, k e]> (edge-importance grad) */
+int fmm_agg_bwd(const void* P, const void* addend, void* dx, const int* rowptr, const int* dst, const int* kk,
+                const float* coef, const void* x, const int* eid, float* dcoef, int N, int T, int V, int Cin, int K,
+                int dtype, cudaStream_t stream);
+int fmm_agg_dcoef(const void* x, const void* P, float* dcoef, const int* src, const int* dst, const int* kk, int E,
+                  int N, int T, int V, int Cin, int K, int dtype, cudaStream_t stream);
+
+/* per-channel sum / sum of squares (fp64 accumulators) and per-(n,c) sums: BatchNorm2d batch statistics
+ * (stgcan.py:112,119,132) and the AdaptiveAvgPool2d of Channel_Attention (stgcan.py:64) in one pass. */
+int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, int N, int T, int V, int C, int dtype,
+                 cudaStream_t stream);
+/* Y = relu(k1[n,c]*U + k0[n,c] + res): BN2 + SE scale + residual + ReLU of st_gcan.forward (stgcan.py:138-144) */
+int fmm_block_out(const void* U, const float* k1, const float* k0, const void* res, const float* ar, const float* br,
+                  void* Y, int N, int T, int V, int C, int dtype, cudaStream_t stream);
+int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const void* R, float* S1, float* S2,
+                            float* S3, int N, int T, int V, int C, int dtype, cudaStream_t stream);
+int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* R, const float* k1, const float* k2,
+                      const float* k3, const float* r1, const float* r2, const float* r3, void* dU, void* dR,
+                      void* dPre, double* sum_dU, double* sum_dR, int N, int T, int V, int C, int dtype,
+                      cudaStream_t stream);
+int fmm_bn1_bwd_reduce(const void* dH, const void* G, const float* a1, const float* b1, double* T1, double* T2, int N,
+                       int T, int V, int C, int dtype, cudaStream_t stream);
+int fmm_bn1_bwd_apply(const void* dH, const void* G, const float* a1, const float* b1, const float* c1,
+                      const float* c2, const float* c3, void* dG, float* Tbl, int N, int T, int V, int C, int dtype,
+                      cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * per-channel / per-clip kernels
+ * ------------------------------------------------------------------------------------------- */
+/* nn.BatchNorm*: statistics -> scale/shift (+ running stats, momentum/eps as torch) */
+int fmm_bn_finalize(const double* ch_sum, const double* ch_sq, double count, const float* gamma, const float* beta,
+                    float* rmean, float* rvar, float momentum, float eps, int training, float* a, float* b,
+                    float* mean_out, float* rstd_out, int C, cudaStream_t stream);
+/* Channel_Attention MLP (stgcan.py:63-70): pooled sums -> s[n,c] and the fused output coefficients k1, k0 */
+int fmm_se_fwd(const float* pool, const float* a2, const float* b2, float invM, const float* W1, const float* b1,
+               const float* gamma, const float* beta, float* rmean, float* rvar, float momentum, float eps,
+               int training, const float* W2, const float* b2se, float* p, float* h, float* ah, float* bh,
+               float* hmean, float* hrstd, float* s, float* k1, float* k0, int N, int C, int C4, cudaStream_t stream);
+int fmm_se_bwd(const float* S1, const float* S2, const float* a2, const float* b2, const float* s, const float* p,
+               const float* h, const float* ah, const float* bh, const float* hmean, const float* hrstd,
+               const float* W1, const float* W2, int training, float* dq, float* dhr, float* r, float* dh, float* dp,
+               float* dW1, float* db1, float* dgamma, float* dbeta, float* dW2, float* db2se, int N, int C, int C4,
+               cudaStream_t stream);
+int fmm_bn2_bwd_coef(const float* S1, const float* S2, const float* S3, const float* pool, const float* dp,
+                     const float* s, const float* a2, const float* mean2, const float* rstd2, const float* ar,
+                     const float* meanr, const float* rstdr, float M, double count, int training, float* k1, float* k2,
+                     float* k3, float* r1, float* r2, float* r3, float* dgamma2, float* dbeta2, float* dgammar,
+                     float* dbetar, int N, int C, cudaStream_t stream);
+int fmm_bn1_bwd_coef(const double* T1, const double* T2, const float* a1, const float* mean1, const float* rstd1,
+                     double count, int training, float* c1, float* c2, float* c3, float* dgamma, float* dbeta, int C,
+                     cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * accelerometer branch: notebook CNN1D (GSTCAN_HAR_conv_10kfold.ipynb#cell2:L6-27), fp32 [N][L][C]
+ * ------------------------------------------------------------------------------------------- */
+int fmm_conv1d_k5_fwd(const float* x, const float* w, const float* b, float* y, int N, int L, int Ci, int Co,
+                      cudaStream_t stream);
+int fmm_bn_relu_pool2_fwd(const float* y, const float* a, const float* b, float* out, int N, int L, int C,
+                          cudaStream_t stream);
+int fmm_pool2_bwd(const float* y, const float* a, const float* b, const float* dout, float* dh, int N, int L, int C,
+                  cudaStream_t stream);
+int fmm_conv1d_k5_bwd(const float* x, const float* dy, const float* w, float* dx, float* dw, float* db, int N, int L,
+                      int Ci, int Co, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMM_B200_H */

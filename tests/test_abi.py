@@ -1,0 +1,73 @@
+"""CPU tests of the C-ABI boundary: the shared library builds, loads, and exports exactly the
+entry points include/fmm_b200.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fmm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fmm_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fall_multimodal_b200 import build
+
+    path = build.build()
+    return ctypes.CDLL(str(path))
+
+
+def test_header_symbols_are_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 26
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/fmm_b200.h but not exported: {missing}"
+
+
+def test_binding_table_matches_header():
+    from fall_multimodal_b200 import _lib
+
+    bound = set(_lib._SIGNATURES) | {"fmm_last_error"}
+    assert bound == set(declared_symbols())
+
+
+def test_version_and_error_text(lib):
+    lib.fmm_last_error.restype = ctypes.c_char_p
+    assert lib.fmm_version() >= 100
+    assert isinstance(lib.fmm_last_error(), bytes)
+
+
+def test_bad_arguments_are_rejected_without_a_gpu(lib):
+    """Argument validation happens on the host before any launch: NULL pointers -> status -1."""
+    lib.fmm_last_error.restype = ctypes.c_char_p
+    st = lib.fmm_colstats(None, None, None, None, 1, 1, 1, 8, 0, None)
+    assert st == -1 and b"colstats" in lib.fmm_last_error()
+    st = lib.fmm_tapconv_pack(None, None, 64, 64, 64, 64, 0, 64, 0, 1, 0, 1, None, 0, None)
+    assert st == -1
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+
+    import fall_multimodal_b200 as fmm
+
+    m = fmm.STGCAN(3, {"layout": "coco_cut", "strategy": "spatial"}, num_class=11)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 3, 8, 14), None)
+    c = fmm.CNN1D()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c(torch.zeros(2, 15, 30))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "fall_multimodal_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().lower().replace("# oracle", ""), f

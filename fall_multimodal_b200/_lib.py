@@ -84,6 +84,8 @@ def require_device(t: torch.Tensor) -> None:
 _P = c_void_p
 _SIGNATURES = {
     "fmm_version": [],
+    "fmm_debug_mma_probe": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "fmm_debug_wait_profile": [c_int, _P],
     "fmm_device_supported": [],
     "fmm_tapconv_bn": [c_int, c_int],
     "fmm_tapconv_packed_bytes": [c_int, c_int, c_int, c_int],

@@ -22,7 +22,7 @@ LIB = LIBDIR / "libfmm_b200.so"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC", "-rdc=true",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
@@ -80,7 +80,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             f.unlink()
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(lambda s: _compile_one(nvcc, s, hdr_digest), _sources()))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", str(LIB),
+           *map(str, objs), "-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stderr}")

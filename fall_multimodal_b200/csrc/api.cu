@@ -5,6 +5,9 @@
 
 namespace fmm {
 
+__device__ int g_wait_prof_enable = 0;
+__device__ unsigned long long g_wait_prof[32];
+
 static thread_local char g_last_error[512] = "";
 
 void set_last_error(const char* fmt, ...) {
@@ -33,6 +36,19 @@ extern "C" {
 const char* fmm_last_error(void) { return fmm::g_last_error; }
 
 int fmm_version(void) { return 100; }
+
+// dev aid: enable/reset (enable >= 0) and read back the per-wait-site blocked-cycle counters
+int fmm_debug_wait_profile(int enable, unsigned long long* out32) {
+  if (out32) {
+    if (cudaMemcpyFromSymbol(out32, fmm::g_wait_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return FMM_ERR_CUDA;
+  }
+  if (enable >= 0) {
+    unsigned long long zero[32] = {0};
+    if (cudaMemcpyToSymbol(fmm::g_wait_prof, zero, sizeof(zero)) != cudaSuccess) return FMM_ERR_CUDA;
+    if (cudaMemcpyToSymbol(fmm::g_wait_prof_enable, &enable, sizeof(int)) != cudaSuccess) return FMM_ERR_CUDA;
+  }
+  return FMM_OK;
+}
 
 // 1 if the current device can run the sm_100a kernels of this library.
 int fmm_device_supported(void) {

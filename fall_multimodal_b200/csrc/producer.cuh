@@ -106,3 +106,72 @@ __device__ __forceinline__ void produce_chunk(const T* __restrict__ col_base, si
 }
 
 }  // namespace fmm
+
+namespace fmm {
+
+// ------------------------------------------------------------------------------------------
+// cp.async (LDGSTS) path for bf16 windows with 16-byte aligned rows: the copies of several
+// window slots are in flight at once (no registers held), which is what hides the global-memory
+// latency; an optional per-channel affine(+ReLU) is then applied IN PLACE by the thread that
+// issued the copy (its own completed cp.async data is visible to it after wait_group).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    default: cp_async_wait<6>(); break;
+  }
+}
+
+// issue the copies of atoms a0, a0+astep, ... of one chunk (zero fill outside [0,Tn) / invalid column)
+__device__ __forceinline__ void cpasync_issue_chunk(const __nv_bfloat16* __restrict__ col_base, size_t pitch_t,
+                                                    bool col_ok, int Tn, int t_lo, int natoms, int a0, int astep,
+                                                    uint32_t sdst) {
+  for (int a = a0; a < natoms; a += astep) {
+    const int ti = t_lo + a;
+    const bool ok = col_ok && ti >= 0 && ti < Tn;
+    const __nv_bfloat16* src = ok ? col_base + static_cast<size_t>(ti) * pitch_t : col_base;
+    cp_async16(sdst + static_cast<uint32_t>(a) * 1024u, src, ok ? 16u : 0u);
+  }
+}
+
+// y = relu?(x*sc + sh) in place on the pieces this thread copied (padding pieces stay zero)
+__device__ __forceinline__ void inplace_affine_chunk(bool col_ok, int Tn, int t_lo, int natoms, int a0, int astep,
+                                                     const float (&sc)[8], const float (&sh)[8], bool relu,
+                                                     uint32_t sdst) {
+  for (int a = a0; a < natoms; a += astep) {
+    const int ti = t_lo + a;
+    if (!(col_ok && ti >= 0 && ti < Tn)) continue;
+    const uint32_t addr = sdst + static_cast<uint32_t>(a) * 1024u;
+    uint4 u;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+    float f[8];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = fmaf(f[i], sc[i], sh[i]);
+      f[i] = relu ? fmaxf(y, 0.f) : y;
+    }
+    sts128(addr, pack8_bf16(f));
+  }
+}
+
+}  // namespace fmm

@@ -55,10 +55,14 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// Optional wait-time profile (dev aid): cycles spent blocked per wait site `tag`, summed over threads.
+extern __device__ int g_wait_prof_enable;
+extern __device__ unsigned long long g_wait_prof[32];
+
 // Bounded wait. `tag` identifies the wait site in the error word.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned* err, unsigned tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  // note: try_wait itself suspends the thread for a bounded time, so the clock starts before it
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > FMM_WAIT_LIMIT_CYCLES) {
       if (err) atomicCAS(err, 0u, 0x80000000u | (tag << 16) | (blockIdx.x & 0xffffu));
@@ -66,6 +70,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
       asm volatile("trap;");
     }
   }
+  if (g_wait_prof_enable && (threadIdx.x & 31) == 0) atomicAdd(&g_wait_prof[tag & 31], static_cast<unsigned long long>(clock64() - t0));
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)
@@ -116,6 +121,37 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same MMA with the descriptors passed as (lo, hi) 32-bit halves: the hi half (SBO, version, swizzle
+// mode) is loop invariant and the lo half (start address >> 4 | LBO << 16) advances by plain 32-bit
+// adds, which keeps the single issuing thread's instruction stream short.
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3ffffu) >> 4) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);  // version 1, SWIZZLE_128B
+}
+// One lane of a converged warp (the idiom nvcc recognises: the guarded region needs no divergence handling).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // mbarrier arrive once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)

@@ -120,6 +120,73 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
     const size_t pitch_t = static_cast<size_t>(p.V) * p.Cin;
     int slot = 0;
     uint32_t ph = 0;
+    const bool use_cpasync = (kParts == 1) && vec_ok;
+    if (use_cpasync) {
+      // ---- cp.async software pipeline: copies of up to D = nslots-1 later items are in flight ----
+      const __nv_bfloat16* __restrict__ Xb = reinterpret_cast<const __nv_bfloat16*>(p.x);
+      const int D = p.nslots - 1;
+      // issue-side iterator (runs D items ahead of the completion-side iterator)
+      int i_tile = first_tile, i_c = 0, i_slot = 0;
+      uint32_t i_ph = 0;
+      auto issue_one = [&]() {
+        if (i_tile < p.total_tiles) {
+          const int rest = i_tile / p.ntiles_n;
+          const int tchunk = rest % p.ntchunks;
+          const int group = rest / p.ntchunks;
+          const int col = group * 8 + q;
+          const bool col_ok = col < p.ncols && (i_c * 64 + pc * 8) < p.Cin;
+          const int n = col_ok ? col / p.V : 0;
+          const int v = col_ok ? col % p.V : 0;
+          const int t_lo = tchunk * 16 * p.istride + p.minshift;
+          const __nv_bfloat16* colp = Xb + static_cast<size_t>(n) * p.Tin * pitch_t + static_cast<size_t>(v) * p.Cin +
+                                      (col_ok ? i_c * 64 + pc * 8 : 0);
+          mbar_wait(win_empty(i_slot), i_ph ^ 1u, p.err, 1);
+          cpasync_issue_chunk(colp, pitch_t, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4,
+                              slots0 + i_slot * slot_bytes + q * 128u + ((pc ^ q) << 4));
+          if (++i_slot == p.nslots) {
+            i_slot = 0;
+            i_ph ^= 1u;
+          }
+          if (++i_c == p.nchunks) {
+            i_c = 0;
+            i_tile += tile_step;
+          }
+        }
+        cp_async_commit();
+      };
+      for (int d = 0; d < (D > 0 ? D : 1); ++d) issue_one();
+      int slot = 0;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        const int rest = tile / p.ntiles_n;
+        const int tchunk = rest % p.ntchunks;
+        const int group = rest / p.ntchunks;
+        const int col = group * 8 + q;
+        const int t_lo = tchunk * 16 * p.istride + p.minshift;
+        for (int c = 0; c < p.nchunks; ++c) {
+          // finish item (tile, c) FIRST and only then queue the copies of item +D: queueing needs the
+          // slot the MMAs of the previous item are still reading, and waiting for it before the
+          // transform would serialise the transform with the tensor core.
+          cp_async_wait_dyn(D > 0 ? D - 1 : 0);  // the copies of (tile, c) have landed
+          if (affine) {
+            const int cb = c * 64 + pc * 8;
+            const bool col_ok = col < p.ncols && cb < p.Cin;
+            float sc[8], sh[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool ok = (cb + i) < p.Cin;
+              sc[i] = ok ? p.in_scale[cb + i] : 1.f;
+              sh[i] = ok ? p.in_shift[cb + i] : 0.f;
+            }
+            inplace_affine_chunk(col_ok, p.Tin, t_lo, p.win_atoms, a0, 4, sc, sh, p.in_relu != 0,
+                                 slots0 + slot * slot_bytes + q * 128u + ((pc ^ q) << 4));
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(win_full(slot));
+          if (++slot == p.nslots) slot = 0;
+          issue_one();
+        }
+      }
+    } else {
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
       const int rest = tile / p.ntiles_n;
       const int tchunk = rest % p.ntchunks;
@@ -154,6 +221,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
           ph ^= 1u;
         }
       }
+    }
     }
   } else if (warp < 12) {
     // ---------------------------------- epilogue ----------------------------------
@@ -244,60 +312,61 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
     __syncwarp();
   } else {
     // ---------------------------------- MMA issuer ----------------------------------
-    if (lane == 0) {
+    // The warp walks the loops converged; each group of MMAs (+ its commit) is issued inside ONE
+    // elect_one() region with (lo, hi) descriptor halves: ~15 instructions per MMA instead of the
+    // ~40 (and a divergence waterfall) a per-thread branch costs, which matters for narrow tiles.
+    {
       const uint32_t idesc = make_idesc_bf16(p.BN, 0, 0);
       const uint32_t a_sbo = static_cast<uint32_t>(p.istride) * 1024u;
+      const uint32_t a_hi = desc_hi(a_sbo), b_hi = desc_hi(1024);
+      const uint32_t pa_lo = part_bytes_a >> 4, pb_lo = part_bytes_b >> 4;
       int slot = 0, bs = 0, as = 0;
       uint32_t wph = 0, bph = 0, aph = 0;
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * acc_stride;
-        uint32_t accum = 0, accum_c = 0;
+        uint32_t accum = 0;
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(win_full(slot), wph, p.err, 5);
-          tc_fence_after();
           const uint32_t a_slot = slots0 + slot * slot_bytes;
           for (int m = 0; m < p.ntaps; ++m) {
             mbar_wait(b_full(bs), bph, p.err, 6);
             tc_fence_after();
-            const uint32_t a_tap = a_slot + static_cast<uint32_t>(p.shift[m] - p.minshift) * 1024u;
-            const uint32_t b_st = bst0 + bs * bstage_bytes;
+            const uint32_t a_lo = desc_lo(a_slot + static_cast<uint32_t>(p.shift[m] - p.minshift) * 1024u, 16);
+            const uint32_t b_lo = desc_lo(bst0 + bs * bstage_bytes, 16);
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              if (kParts == 1) {
-                umma_bf16(d_tmem, make_smem_desc(a_tap + kk * 32u, 16, a_sbo),
-                          make_smem_desc(b_st + kk * 32u, 16, 1024), idesc, accum);
-                accum = 1;
-              } else {
-                // (a0+a1+a2)(b0+b1+b2) ~ a0b0 + [a0b1 + a1b0 + a1b1 + a0b2 + a2b0] (rel. err ~2^-24)
-                const int pa[5] = {2, 0, 1, 1, 0};
-                const int pb[5] = {0, 2, 1, 0, 1};
+              for (uint32_t kk = 0; kk < 4; ++kk) {
+                if (kParts == 1) {
+                  umma_bf16_lh(d_tmem, a_lo + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | kk);
+                } else {
+                  // (a0+a1+a2)(b0+b1+b2) ~ a0b0 + [a0b1 + a1b0 + a1b1 + a0b2 + a2b0] (rel. err ~2^-24)
+                  const uint32_t pa[5] = {2, 0, 1, 1, 0};
+                  const uint32_t pb[5] = {0, 2, 1, 0, 1};
 #pragma unroll
-                for (int e = 0; e < 5; ++e) {
-                  umma_bf16(d_tmem + p.BN, make_smem_desc(a_tap + pa[e] * part_bytes_a + kk * 32u, 16, a_sbo),
-                            make_smem_desc(b_st + pb[e] * part_bytes_b + kk * 32u, 16, 1024), idesc,
-                            accum_c);
-                  accum_c = 1;
+                  for (int e = 0; e < 5; ++e)
+                    umma_bf16_lh(d_tmem + p.BN, a_lo + pa[e] * pa_lo + kk * 2u, a_hi, b_lo + pb[e] * pb_lo + kk * 2u, b_hi,
+                                 idesc, accum | kk | static_cast<uint32_t>(e));
+                  umma_bf16_lh(d_tmem, a_lo + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | kk);
                 }
-                umma_bf16(d_tmem, make_smem_desc(a_tap + kk * 32u, 16, a_sbo),
-                          make_smem_desc(b_st + kk * 32u, 16, 1024), idesc, accum);
-                accum = 1;
               }
+              umma_commit(b_empty(bs));
+              if (m == p.ntaps - 1) umma_commit(win_empty(slot));
+              if (m == p.ntaps - 1 && c == p.nchunks - 1) umma_commit(acc_full(as));
             }
-            umma_commit(b_empty(bs));
+            __syncwarp();
+            accum = 1;
             if (++bs == p.nbstages) {
               bs = 0;
               bph ^= 1u;
             }
           }
-          umma_commit(win_empty(slot));
           if (++slot == p.nslots) {
             slot = 0;
             wph ^= 1u;
           }
         }
-        umma_commit(acc_full(as));
         if (++as == 2) {
           as = 0;
           aph ^= 1u;

@@ -112,6 +112,78 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       const size_t xpitch = static_cast<size_t>(p.V) * p.Cin;
       const size_t ypitch = static_cast<size_t>(p.V) * p.Cout;
       const float one[8] = {1, 1, 1, 1, 1, 1, 1, 1}, zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const bool use_cpasync = (kParts == 1) && xvec && yvec;
+      if (use_cpasync) {
+        // ---- cp.async software pipeline over the units of this CTA (D = nstages-1 units in flight) ----
+        const __nv_bfloat16* __restrict__ Xb = reinterpret_cast<const __nv_bfloat16*>(p.x);
+        const __nv_bfloat16* __restrict__ Yb = reinterpret_cast<const __nv_bfloat16*>(p.dy);
+        const int D = p.nstages - 1;
+        int i_u = slice, i_st = 0;
+        uint32_t i_ph = 0;
+        auto issue_one = [&]() {
+          if (i_u < p.total_units) {
+            const int jchunk = i_u % p.njchunks;
+            const int group = i_u / p.njchunks;
+            const int col = group * 8 + q;
+            const bool col_ok = col < p.ncols;
+            const int n = col_ok ? col / p.V : 0;
+            const int v = col_ok ? col % p.V : 0;
+            const int j0 = jchunk * p.JT;
+            const int t_lo = j0 * p.istride + p.minshift;
+            mbar_wait(empty(i_st), i_ph ^ 1u, p.err, 11);
+            const uint32_t a_base = smem_base + i_st * stage_bytes;
+            const uint32_t b_base = a_base + a_bytes;
+            const __nv_bfloat16* xcol = Xb + static_cast<size_t>(n) * p.Tin * xpitch + static_cast<size_t>(v) * p.Cin;
+            const __nv_bfloat16* ycol = Yb + static_cast<size_t>(n) * p.Tj * ypitch + static_cast<size_t>(v) * p.Cout;
+            for (int h = 0; h < p.MCH; ++h) {
+              const int cb = (ci_tile * p.MCH + h) * 64 + pc * 8;
+              const bool ok = col_ok && cb < p.Cin;
+              cpasync_issue_chunk(xcol + (ok ? cb : 0), xpitch, ok, p.Tin, t_lo, p.win_atoms, a0, 4,
+                                  a_base + h * p.win_atoms * 1024u + q * 128u + ((pc ^ q) << 4));
+            }
+            for (int h = 0; h < p.BN / 64; ++h) {
+              const int cb = co_tile * p.BN + h * 64 + pc * 8;
+              const bool ok = col_ok && cb < p.Cout;
+              cpasync_issue_chunk(ycol + (ok ? cb : 0), ypitch, ok, p.Tj, j0, p.JT, a0, 4,
+                                  b_base + h * p.JT * 1024u + q * 128u + ((pc ^ q) << 4));
+            }
+            if (++i_st == p.nstages) {
+              i_st = 0;
+              i_ph ^= 1u;
+            }
+            i_u += p.slices;
+          }
+          cp_async_commit();
+        };
+        for (int d = 0; d < (D > 0 ? D : 1); ++d) issue_one();
+        int st = 0;
+        for (int u = slice; u < p.total_units; u += p.slices) {
+          cp_async_wait_dyn(D > 0 ? D - 1 : 0);  // finish unit u first, queue unit +D afterwards (see tapconv.cu)
+          if (affine) {
+            const int jchunk = u % p.njchunks;
+            const int group = u / p.njchunks;
+            const int col = group * 8 + q;
+            const int t_lo = jchunk * p.JT * p.istride + p.minshift;
+            const uint32_t a_base = smem_base + st * stage_bytes;
+            for (int h = 0; h < p.MCH; ++h) {
+              const int cb = (ci_tile * p.MCH + h) * 64 + pc * 8;
+              float sc[8], sh[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const bool ok = (cb + i) < p.Cin;
+                sc[i] = ok ? p.in_scale[cb + i] : 1.f;
+                sh[i] = ok ? p.in_shift[cb + i] : 0.f;
+              }
+              inplace_affine_chunk(col < p.ncols && cb < p.Cin, p.Tin, t_lo, p.win_atoms, a0, 4, sc, sh, p.in_relu != 0,
+                                   a_base + h * p.win_atoms * 1024u + q * 128u + ((pc ^ q) << 4));
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(full(st));
+          if (++st == p.nstages) st = 0;
+          issue_one();
+        }
+      } else {
       int st = 0;
       uint32_t ph = 0;
       for (int u = slice; u < p.total_units; u += p.slices) {
@@ -160,6 +232,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           ph ^= 1u;
         }
       }
+      }
     }
     if (warp < 4) {
       // ------------------------------ epilogue (same warps) ------------------------------
@@ -194,12 +267,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         }
       }
     } else if (warp == 8) {
-      // ---------------------------------- MMA issuer ----------------------------------
-      if (lane == 0) {
+      // ---------------------------------- MMA issuer (warp converged, elect_one regions) ---------------
+      {
         const uint32_t idesc = make_idesc_bf16(p.BN, 1, 1);
         const uint32_t a_sbo = static_cast<uint32_t>(p.istride) * 1024u;
         const uint32_t a_lbo = p.MCH == 2 ? static_cast<uint32_t>(p.win_atoms) * 1024u : 1024u;
         const uint32_t b_lbo = static_cast<uint32_t>(p.JT) * 1024u;
+        const uint32_t a_hi = desc_hi(a_sbo), b_hi = desc_hi(1024);
+        const uint32_t a_kstep = (2u * a_sbo) >> 4, b_kstep = 2048u >> 4;
+        const uint32_t pa_lo = a_part >> 4, pb_lo = b_part >> 4;
         int st = 0;
         uint32_t ph = 0;
         uint32_t accum = 0;
@@ -207,35 +283,37 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           mbar_wait(full(st), ph, p.err, 13);
           tc_fence_after();
           const uint32_t a_base = smem_base + st * stage_bytes;
-          const uint32_t b_base = a_base + a_bytes;
-          for (int kk = 0; kk < p.JT / 2; ++kk) {
+          const uint32_t b_lo0 = desc_lo(a_base + a_bytes, b_lbo);
+          if (elect_one()) {
             for (int t = 0; t < mt; ++t) {
-              const uint32_t a_tap = a_base + static_cast<uint32_t>(p.shift[m0 + t] - p.minshift) * 1024u +
-                                     static_cast<uint32_t>(kk) * 2u * a_sbo;
-              const uint32_t b_k = b_base + static_cast<uint32_t>(kk) * 2048u;
+              const uint32_t a_lo0 = desc_lo(a_base + static_cast<uint32_t>(p.shift[m0 + t] - p.minshift) * 1024u, a_lbo);
               const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(t) * acc_stride;
-              if (kParts == 1) {
-                umma_bf16(d_tmem, make_smem_desc(a_tap, a_lbo, a_sbo), make_smem_desc(b_k, b_lbo, 1024),
-                          idesc, accum);
-              } else {
-                const int pa[5] = {2, 0, 1, 1, 0};
-                const int pb[5] = {0, 2, 1, 0, 1};
+              for (int kk = 0; kk < p.JT / 2; ++kk) {
+                const uint32_t a_lo = a_lo0 + kk * a_kstep, b_lo = b_lo0 + kk * b_kstep;
+                const uint32_t acc = accum | static_cast<uint32_t>(kk);
+                if (kParts == 1) {
+                  umma_bf16_lh(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                } else {
+                  const uint32_t pa[5] = {2, 0, 1, 1, 0};
+                  const uint32_t pb[5] = {0, 2, 1, 0, 1};
 #pragma unroll
-                for (int e = 0; e < 5; ++e)
-                  umma_bf16(d_tmem + p.BN, make_smem_desc(a_tap + pa[e] * a_part, a_lbo, a_sbo),
-                            make_smem_desc(b_k + pb[e] * b_part, b_lbo, 1024), idesc, (e > 0) ? 1u : accum);
-                umma_bf16(d_tmem, make_smem_desc(a_tap, a_lbo, a_sbo), make_smem_desc(b_k, b_lbo, 1024), idesc, accum);
+                  for (int e = 0; e < 5; ++e)
+                    umma_bf16_lh(d_tmem + p.BN, a_lo + pa[e] * pa_lo, a_hi, b_lo + pb[e] * pb_lo, b_hi, idesc,
+                                 acc | static_cast<uint32_t>(e));
+                  umma_bf16_lh(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                }
               }
             }
-            accum = 1;
+            umma_commit(empty(st));
+            if (it == my_units - 1) umma_commit(acc_full);
           }
-          umma_commit(empty(st));
+          __syncwarp();
+          accum = 1;
           if (++st == p.nstages) {
             st = 0;
             ph ^= 1u;
           }
         }
-        umma_commit(acc_full);
       }
       __syncwarp();
     }

@@ -32,6 +32,11 @@ extern "C" {
 const char* fmm_last_error(void);
 int fmm_version(void);
 int fmm_device_supported(void); /* 1 iff the current device is sm_100 */
+/* dev aid: per-wait-site blocked cycles of the GEMM kernels' mbarrier waits (enable>=0: reset + set; out32: 32 counters) */
+int fmm_debug_wait_profile(int enable, unsigned long long* out32);
+/* dev aid: cycles for `iters` back-to-back tcgen05.mma (M=128,K=16) per CTA: out2 = {issue cycles, issue+drain cycles} */
+int fmm_debug_mma_probe(int N, int iters, int a_mn, int b_mn, int distinct_acc, int ctas, unsigned long long* out2_dev,
+                        cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * tcgen05 GEMM engines

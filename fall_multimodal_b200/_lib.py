@@ -96,18 +96,18 @@ _SIGNATURES = {
     "fmm_agg_fwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_dcoef": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
-    "fmm_colstats": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_colstats": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_block_out": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_blockout_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
-    "fmm_bn2_bwd_apply": [_P] * 15 + [c_int, c_int, c_int, c_int, c_int, _P],
-    "fmm_bn1_bwd_reduce": [_P] * 6 + [c_int, c_int, c_int, c_int, c_int, _P],
-    "fmm_bn1_bwd_apply": [_P] * 9 + [c_int, c_int, c_int, c_int, c_int, _P],
-    "fmm_bn_finalize": [_P, _P, C.c_double, _P, _P, _P, _P, c_float, c_float, c_int, _P, _P, _P, _P, c_int, _P],
+    "fmm_bn2_bwd_apply": [_P] * 15 + [c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_bn1_bwd_reduce": [_P] * 6 + [c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_bn1_bwd_apply": [_P] * 9 + [c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_bn_finalize": [_P, _P, c_int, C.c_double, _P, _P, _P, _P, c_float, c_float, c_int, _P, _P, _P, _P, c_int, _P],
     "fmm_se_fwd": [_P, _P, _P, c_float, _P, _P, _P, _P, _P, _P, c_float, c_float, c_int] + [_P] * 11 +
                   [c_int, c_int, c_int, _P],
     "fmm_se_bwd": [_P] * 13 + [c_int] + [_P] * 11 + [c_int, c_int, c_int, _P],
     "fmm_bn2_bwd_coef": [_P] * 12 + [c_float, C.c_double, c_int] + [_P] * 10 + [c_int, c_int, _P],
-    "fmm_bn1_bwd_coef": [_P] * 5 + [C.c_double, c_int] + [_P] * 5 + [c_int, _P],
+    "fmm_bn1_bwd_coef": [_P, _P, c_int, _P, _P, _P, C.c_double, c_int] + [_P] * 5 + [c_int, _P],
     "fmm_conv1d_k5_fwd": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
     "fmm_bn_relu_pool2_fwd": [_P, _P, _P, _P, c_int, c_int, c_int, _P],
     "fmm_pool2_bwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P],

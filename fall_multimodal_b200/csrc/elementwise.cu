@@ -19,6 +19,10 @@ namespace fmm {
 constexpr int kEwThreads = 256;
 
 __device__ __forceinline__ void atomic_add_f64(double* p, double v) { atomicAdd(p, v); }
+// Cross-block accumulators ([C] doubles, [V][C] floats) are replicated `nrep` times ([nrep][...]);
+// a block adds into replica (linear block id % nrep) and the consumer sums the replicas. Thousands
+// of blocks hitting the same few hundred addresses otherwise serialise in the L2 atomic units.
+__device__ __forceinline__ int replica_of_block(int nrep) { return (blockIdx.x + blockIdx.y * gridDim.x) % nrep; }
 
 // ------------------------------------------------------------------------------------------
 // agg_fwd:  Xa[(n,t,w), k*Cin+ci] = sum_{e in in(k,w)} coef[e] * x[(n,t,src[e]), ci]
@@ -243,7 +247,7 @@ __device__ __forceinline__ void block_channel_reduce(float (&val)[NV][8], float*
 // colstats: per-channel sum / sum of squares (double) and optional per-(n,c) sums (float) of X.
 template <typename T>
 __global__ void colstats_kernel(const T* __restrict__ X, double* __restrict__ ch_sum, double* __restrict__ ch_sq,
-                                float* __restrict__ nc_sum, int Tn, int V, int C, int tchunk) {
+                                float* __restrict__ nc_sum, int Tn, int V, int C, int tchunk, int nrep) {
   extern __shared__ float red[];  // [C][2]
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * tchunk * V;
@@ -270,8 +274,9 @@ __global__ void colstats_kernel(const T* __restrict__ X, double* __restrict__ ch
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float s = red[2 * c], q = red[2 * c + 1];
-    if (ch_sum) atomic_add_f64(ch_sum + c, static_cast<double>(s));
-    if (ch_sq) atomic_add_f64(ch_sq + c, static_cast<double>(q));
+    const size_t ro = static_cast<size_t>(replica_of_block(nrep)) * C;
+    if (ch_sum) atomic_add_f64(ch_sum + ro + c, static_cast<double>(s));
+    if (ch_sq) atomic_add_f64(ch_sq + ro + c, static_cast<double>(q));
     if (nc_sum) atomicAdd(nc_sum + static_cast<size_t>(n) * C + c, s);
   }
 }
@@ -366,7 +371,7 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
                                      const float* __restrict__ r1, const float* __restrict__ r2,
                                      const float* __restrict__ r3, T* __restrict__ dU, T* __restrict__ dR,
                                      T* __restrict__ dPre, double* __restrict__ sum_dU,
-                                     double* __restrict__ sum_dR, int Tn, int V, int C, int tchunk) {
+                                     double* __restrict__ sum_dR, int Tn, int V, int C, int tchunk, int nrep) {
   extern __shared__ float red[];  // [C][2]
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * tchunk * V;
@@ -415,8 +420,9 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
   if (sum_dU || sum_dR) block_channel_reduce<2>(acc, red, c8, c8n);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    if (sum_dU) atomic_add_f64(sum_dU + c, static_cast<double>(red[2 * c]));
-    if (sum_dR) atomic_add_f64(sum_dR + c, static_cast<double>(red[2 * c + 1]));
+    const size_t ro = static_cast<size_t>(replica_of_block(nrep)) * C;
+    if (sum_dU) atomic_add_f64(sum_dU + ro + c, static_cast<double>(red[2 * c]));
+    if (sum_dR) atomic_add_f64(sum_dR + ro + c, static_cast<double>(red[2 * c + 1]));
   }
 }
 
@@ -424,7 +430,7 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
 template <typename T>
 __global__ void bn1_bwd_reduce_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
                                       const float* __restrict__ b1, double* __restrict__ T1,
-                                      double* __restrict__ T2, int Tn, int V, int C, int tchunk) {
+                                      double* __restrict__ T2, int Tn, int V, int C, int tchunk, int nrep) {
   extern __shared__ float red[];  // [C][2]
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * tchunk * V;
@@ -459,8 +465,9 @@ __global__ void bn1_bwd_reduce_kernel(const T* __restrict__ dH, const T* __restr
   block_channel_reduce<2>(acc, red, c8, c8n);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomic_add_f64(T1 + c, static_cast<double>(red[2 * c]));
-    atomic_add_f64(T2 + c, static_cast<double>(red[2 * c + 1]));
+    const size_t ro = static_cast<size_t>(replica_of_block(nrep)) * C;
+    atomic_add_f64(T1 + ro + c, static_cast<double>(red[2 * c]));
+    atomic_add_f64(T2 + ro + c, static_cast<double>(red[2 * c + 1]));
   }
 }
 
@@ -469,7 +476,7 @@ template <typename T>
 __global__ void bn1_bwd_apply_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
                                      const float* __restrict__ b1, const float* __restrict__ c1,
                                      const float* __restrict__ c2, const float* __restrict__ c3, T* __restrict__ dG,
-                                     float* __restrict__ Tbl, int Tn, int V, int C, int tchunk) {
+                                     float* __restrict__ Tbl, int Tn, int V, int C, int tchunk, int nrep) {
   const int n = blockIdx.y;
   const int t0 = blockIdx.x * tchunk;
   const int t1 = min(t0 + tchunk, Tn);
@@ -502,7 +509,8 @@ __global__ void bn1_bwd_apply_kernel(const T* __restrict__ dH, const T* __restri
     }
     if (Tbl) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(Tbl + static_cast<size_t>(i) * 8 + j, acc[j]);
+      for (int j = 0; j < 8; ++j)
+        atomicAdd(Tbl + static_cast<size_t>(replica_of_block(nrep)) * V * C + static_cast<size_t>(i) * 8 + j, acc[j]);
     }
   }
 }
@@ -590,13 +598,14 @@ int fmm_agg_dcoef(const void* x, const void* P, float* dcoef, const int* src, co
   return FMM_OK;
 }
 
-int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, int N, int Tn, int V, int C, int dtype,
-                 cudaStream_t stream) {
+int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, int nrep, int N, int Tn, int V, int C,
+                 int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(nrep >= 1, "colstats: nrep");
   FMM_CHECK_ARG(X && N > 0 && Tn > 0 && V > 0 && C > 0 && C % 8 == 0, "colstats: bad args (C must be a multiple of 8)");
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    colstats_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, Tn, V, C, tchunk);
+    colstats_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, Tn, V, C, tchunk, nrep);
   })
   FMM_CHECK_LAUNCH("colstats");
   return FMM_OK;
@@ -629,8 +638,9 @@ int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const 
 
 int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* R, const float* k1, const float* k2,
                       const float* k3, const float* r1, const float* r2, const float* r3, void* dU, void* dR,
-                      void* dPre, double* sum_dU, double* sum_dR, int N, int Tn, int V, int C, int dtype,
+                      void* dPre, double* sum_dU, double* sum_dR, int nrep, int N, int Tn, int V, int C, int dtype,
                       cudaStream_t stream) {
+  FMM_CHECK_ARG(nrep >= 1, "bn2_bwd_apply: nrep");
   FMM_CHECK_ARG(dY && Y && U && k1 && k2 && k3 && dU && C % 8 == 0, "bn2_bwd_apply: bad args");
   FMM_CHECK_ARG(!R || (r1 && r2 && r3 && dR), "bn2_bwd_apply: residual branch needs r1..r3 and dR");
   const int tchunk = pick_tchunk(N, Tn);
@@ -638,32 +648,34 @@ int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* 
   FMM_DISPATCH(dtype, {
     bn2_bwd_apply_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>(
         (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, k1, k2, k3, r1, r2, r3, (T*)dU, (T*)dR, (T*)dPre, sum_dU,
-        sum_dR, Tn, V, C, tchunk);
+        sum_dR, Tn, V, C, tchunk, nrep);
   })
   FMM_CHECK_LAUNCH("bn2_bwd_apply");
   return FMM_OK;
 }
 
-int fmm_bn1_bwd_reduce(const void* dH, const void* G, const float* a1, const float* b1, double* T1, double* T2, int N,
-                       int Tn, int V, int C, int dtype, cudaStream_t stream) {
+int fmm_bn1_bwd_reduce(const void* dH, const void* G, const float* a1, const float* b1, double* T1, double* T2,
+                       int nrep, int N, int Tn, int V, int C, int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(nrep >= 1, "bn1_bwd_reduce: nrep");
   FMM_CHECK_ARG(dH && G && a1 && b1 && T1 && T2 && C % 8 == 0, "bn1_bwd_reduce: bad args");
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    bn1_bwd_reduce_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, Tn, V, C, tchunk);
+    bn1_bwd_reduce_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, Tn, V, C, tchunk, nrep);
   })
   FMM_CHECK_LAUNCH("bn1_bwd_reduce");
   return FMM_OK;
 }
 
 int fmm_bn1_bwd_apply(const void* dH, const void* G, const float* a1, const float* b1, const float* c1,
-                      const float* c2, const float* c3, void* dG, float* Tbl, int N, int Tn, int V, int C, int dtype,
-                      cudaStream_t stream) {
+                      const float* c2, const float* c3, void* dG, float* Tbl, int nrep, int N, int Tn, int V, int C,
+                      int dtype, cudaStream_t stream) {
+  FMM_CHECK_ARG(nrep >= 1, "bn1_bwd_apply: nrep");
   FMM_CHECK_ARG(dH && G && a1 && b1 && c1 && c2 && c3 && dG && C % 8 == 0, "bn1_bwd_apply: bad args");
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    bn1_bwd_apply_kernel<T><<<grid, pair_threads(V * (C / 8)), 0, stream>>>((const T*)dH, (const T*)G, a1, b1, c1, c2, c3, (T*)dG, Tbl, Tn, V, C, tchunk);
+    bn1_bwd_apply_kernel<T><<<grid, pair_threads(V * (C / 8)), 0, stream>>>((const T*)dH, (const T*)G, a1, b1, c1, c2, c3, (T*)dG, Tbl, Tn, V, C, tchunk, nrep);
   })
   FMM_CHECK_LAUNCH("bn1_bwd_apply");
   return FMM_OK;

@@ -131,7 +131,8 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
     case 3: cp_async_wait<3>(); break;
     case 4: cp_async_wait<4>(); break;
     case 5: cp_async_wait<5>(); break;
-    default: cp_async_wait<6>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
   }
 }
 

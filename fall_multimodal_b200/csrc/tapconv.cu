@@ -18,9 +18,10 @@
 // read through a descriptor whose start address is shifted by whole atoms (no im2col copies),
 // and a temporal stride is just SBO = is*1024.
 //
-// Warp roles (448 threads, persistent over tiles): 0-7 window producers (global -> BN/ReLU ->
-// bf16 parts -> swizzled smem), 8-11 epilogue (TMEM -> regs -> bias -> global), 12 weight loader
-// (bulk async copies of pre-packed weight images), 13 MMA issuer (one thread) + TMEM allocator.
+// Warp roles (576 threads, persistent over tiles): 0-7 window producers (cp.async global -> smem,
+// optional BN/ReLU in place), 8-15 epilogue (two warps per TMEM lane quadrant, alternating 32-column
+// groups: TMEM -> regs -> bias -> global), 16 weight loader (bulk async copies of pre-packed weight
+// images), 17 MMA issuer (one elected lane) + TMEM allocator.
 #include "common.cuh"
 #include "producer.cuh"
 #include "ptx.cuh"
@@ -44,14 +45,18 @@ struct TapConvParams {
   int BN, ntiles_n, nchunks;
   int ncols, ngroups, ntchunks, total_tiles;
   int nslots, nbstages;
+  int resident;  // 1: every weight image of the launch stays in shared memory for the CTA's lifetime
   unsigned* err;
 };
 
-constexpr int kTapThreads = 448;
+constexpr int kTapMaxThreads = 576;  // 8 producer + kEpi epilogue + loader + MMA warps
 constexpr int kTapProducers = 256;
 
-template <typename T>
-__global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
+// kEpi = 4 | 8 epilogue warps: wide output tiles (BN >= 128) are epilogue-bound and take two warps per
+// TMEM lane quadrant; narrow tiles run with 4 (fewer warps competing with the producers for issue slots).
+template <typename T, int kEpi>
+__global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
+  constexpr int kLoaderWarp = 8 + kEpi, kMmaWarp = 9 + kEpi;
   constexpr int kParts = ActTraits<T>::kParts;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -91,11 +96,11 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), 128);
+      mbar_init(acc_empty(s), kEpi * 32);
     }
     mbar_fence_init();
   }
-  if (warp == 13) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
@@ -128,20 +133,29 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
       // issue-side iterator (runs D items ahead of the completion-side iterator)
       int i_tile = first_tile, i_c = 0, i_slot = 0;
       uint32_t i_ph = 0;
+      // per-tile decode of the issue-side iterator, refreshed only when it moves to a new tile (the
+      // integer divisions are a real cost for the 1x1 GEMMs, whose items are only 16 KB each)
+      bool i_colok = false;
+      int i_tlo = 0;
+      const __nv_bfloat16* i_colp = Xb;
+      auto decode_tile = [&]() {
+        const int rest = i_tile / p.ntiles_n;
+        const int tchunk = rest % p.ntchunks;
+        const int group = rest / p.ntchunks;
+        const int col = group * 8 + q;
+        i_colok = col < p.ncols;
+        const int n = i_colok ? col / p.V : 0;
+        const int v = i_colok ? col - n * p.V : 0;
+        i_tlo = tchunk * 16 * p.istride + p.minshift;
+        i_colp = Xb + static_cast<size_t>(n) * p.Tin * pitch_t + static_cast<size_t>(v) * p.Cin;
+      };
+      if (i_tile < p.total_tiles) decode_tile();
       auto issue_one = [&]() {
         if (i_tile < p.total_tiles) {
-          const int rest = i_tile / p.ntiles_n;
-          const int tchunk = rest % p.ntchunks;
-          const int group = rest / p.ntchunks;
-          const int col = group * 8 + q;
-          const bool col_ok = col < p.ncols && (i_c * 64 + pc * 8) < p.Cin;
-          const int n = col_ok ? col / p.V : 0;
-          const int v = col_ok ? col % p.V : 0;
-          const int t_lo = tchunk * 16 * p.istride + p.minshift;
-          const __nv_bfloat16* colp = Xb + static_cast<size_t>(n) * p.Tin * pitch_t + static_cast<size_t>(v) * p.Cin +
-                                      (col_ok ? i_c * 64 + pc * 8 : 0);
+          const int cb = i_c * 64 + pc * 8;
+          const bool col_ok = i_colok && cb < p.Cin;
           mbar_wait(win_empty(i_slot), i_ph ^ 1u, p.err, 1);
-          cpasync_issue_chunk(colp, pitch_t, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4,
+          cpasync_issue_chunk(i_colp + (col_ok ? cb : 0), pitch_t, col_ok, p.Tin, i_tlo, p.win_atoms, a0, 4,
                               slots0 + i_slot * slot_bytes + q * 128u + ((pc ^ q) << 4));
           if (++i_slot == p.nslots) {
             i_slot = 0;
@@ -150,6 +164,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
           if (++i_c == p.nchunks) {
             i_c = 0;
             i_tile += tile_step;
+            if (i_tile < p.total_tiles) decode_tile();
           }
         }
         cp_async_commit();
@@ -223,10 +238,11 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
       }
     }
     }
-  } else if (warp < 12) {
+  } else if (warp < 8 + kEpi) {
     // ---------------------------------- epilogue ----------------------------------
     T* __restrict__ O = reinterpret_cast<T*>(p.out);
-    const int quad = warp - 8;
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int half = (warp - 8) >> 2;   // which 32-column groups it takes (even / odd when kEpi == 8)
     const int r = quad * 32 + lane;
     const int q = r & 7;
     int as = 0;
@@ -247,7 +263,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
       mbar_wait(acc_full(as), aph, p.err, 2);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(as) * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
-      for (int cg = 0; cg < p.BN / 32; ++cg) {
+      for (int cg = half; cg < p.BN / 32; cg += kEpi / 4) {
         uint32_t acc[32];
         tmem_ld32(taddr + cg * 32, acc);
         tmem_ld_wait();
@@ -259,7 +275,27 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
           for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(corr[i]));
         }
         const int co0 = ntile * p.BN + cg * 32;
-        if (row_ok) {
+        if (row_ok && vec_ok && co0 + 32 <= p.Cout) {
+          // fast path: whole 32-column group in range
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(v) * p.bias_vstride + co0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 b = bp[g];
+              acc[4 * g + 0] = __float_as_uint(__uint_as_float(acc[4 * g + 0]) + b.x);
+              acc[4 * g + 1] = __float_as_uint(__uint_as_float(acc[4 * g + 1]) + b.y);
+              acc[4 * g + 2] = __float_as_uint(__uint_as_float(acc[4 * g + 2]) + b.z);
+              acc[4 * g + 3] = __float_as_uint(__uint_as_float(acc[4 * g + 3]) + b.w);
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(acc[g * 8 + i]);
+            store8(orow + co0 + g * 8, f);
+          }
+        } else if (row_ok) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];
@@ -287,12 +323,20 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
         aph ^= 1u;
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == kLoaderWarp) {
     // -------------------------------- weight loader --------------------------------
     if (lane == 0) {
       const uint8_t* W = reinterpret_cast<const uint8_t*>(p.wpk);
       int bs = 0;
       uint32_t bph = 0;
+      if (p.resident) {
+        // all images once: one transaction barrier, one bulk copy per image
+        if (first_tile < p.total_tiles) {
+          mbar_arrive_expect_tx(b_full(0), static_cast<uint32_t>(p.nbstages) * bstage_bytes);
+          for (int i = 0; i < p.nbstages; ++i)
+            bulk_g2s(bst0 + i * bstage_bytes, W + static_cast<size_t>(i) * bstage_bytes, bstage_bytes, b_full(0));
+        }
+      } else
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const int ntile = tile % p.ntiles_n;
         for (int c = 0; c < p.nchunks; ++c) {
@@ -322,7 +366,9 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
       const uint32_t pa_lo = part_bytes_a >> 4, pb_lo = part_bytes_b >> 4;
       int slot = 0, bs = 0, as = 0;
       uint32_t wph = 0, bph = 0, aph = 0;
+      if (p.resident && first_tile < p.total_tiles) mbar_wait(b_full(0), 0, p.err, 6);
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        const int ntile = tile % p.ntiles_n;
         mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * acc_stride;
@@ -331,10 +377,11 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
           mbar_wait(win_full(slot), wph, p.err, 5);
           const uint32_t a_slot = slots0 + slot * slot_bytes;
           for (int m = 0; m < p.ntaps; ++m) {
-            mbar_wait(b_full(bs), bph, p.err, 6);
+            if (!p.resident) mbar_wait(b_full(bs), bph, p.err, 6);
             tc_fence_after();
             const uint32_t a_lo = desc_lo(a_slot + static_cast<uint32_t>(p.shift[m] - p.minshift) * 1024u, 16);
-            const uint32_t b_lo = desc_lo(bst0 + bs * bstage_bytes, 16);
+            const uint32_t b_img = p.resident ? static_cast<uint32_t>((ntile * p.nchunks + c) * p.ntaps + m) : static_cast<uint32_t>(bs);
+            const uint32_t b_lo = desc_lo(bst0 + b_img * bstage_bytes, 16);
             if (elect_one()) {
 #pragma unroll
               for (uint32_t kk = 0; kk < 4; ++kk) {
@@ -351,7 +398,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
                   umma_bf16_lh(d_tmem, a_lo + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | kk);
                 }
               }
-              umma_commit(b_empty(bs));
+              if (!p.resident) umma_commit(b_empty(bs));
               if (m == p.ntaps - 1) umma_commit(win_empty(slot));
               if (m == p.ntaps - 1 && c == p.nchunks - 1) umma_commit(acc_full(as));
             }
@@ -378,7 +425,7 @@ __global__ void __launch_bounds__(kTapThreads, 1) tapconv_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -545,34 +592,47 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   const int nparts = dtype == FMM_DT_F32 ? 3 : 1;
   const size_t slot_bytes = static_cast<size_t>(nparts) * p.win_atoms * 1024;
   const size_t bstage_bytes = static_cast<size_t>(nparts) * p.BN * 128;
-  const size_t budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
-  // ring depths: prefer 4 weight stages + as many window slots as fit (max 4), shrink if needed
-  int nb = 4, ns = 4;
-  while (nb > 2 && nb * bstage_bytes + 2 * slot_bytes > budget) --nb;
-  while (ns > 1 && nb * bstage_bytes + ns * slot_bytes > budget) --ns;
-  FMM_CHECK_ARG(nb * bstage_bytes + ns * slot_bytes <= budget,
-                "tapconv: tile does not fit shared memory (win_atoms=%d BN=%d parts=%d)", p.win_atoms,
-                p.BN, nparts);
+  const size_t budget = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers*/;
+  // Weights: keep every image resident when they fit next to >= 3 window slots (no per-tap barrier
+  // round trips at all); otherwise stream them through as deep a ring as fits beside 4 slots.
+  const int nimg = p.ntiles_n * p.nchunks * ntaps;
+  int nb, ns;
+  p.resident = (nimg <= 96 && nimg * bstage_bytes + 3 * slot_bytes <= budget) ? 1 : 0;
+  if (p.resident) {
+    nb = nimg;
+    ns = static_cast<int>((budget - nb * bstage_bytes) / slot_bytes);
+    if (ns > 8) ns = 8;  // more window slots = more cp.async bytes in flight (the 1x1 GEMMs are streaming kernels)
+  } else {
+    ns = 4;
+    while (ns > 1 && 2 * bstage_bytes + ns * slot_bytes > budget) --ns;
+    nb = static_cast<int>((budget - ns * slot_bytes) / bstage_bytes);
+    if (nb > 12) nb = 12;
+    FMM_CHECK_ARG(nb >= 2 || (nb >= 1 && ns >= 1 && nb * bstage_bytes + ns * slot_bytes <= budget),
+                  "tapconv: tile does not fit shared memory (win_atoms=%d BN=%d parts=%d)", p.win_atoms, p.BN, nparts);
+  }
+  FMM_CHECK_ARG(nb >= 1 && ns >= 1 && nb * bstage_bytes + ns * slot_bytes <= budget,
+                "tapconv: tile does not fit shared memory (win_atoms=%d BN=%d parts=%d)", p.win_atoms, p.BN, nparts);
   p.nslots = ns;
   p.nbstages = nb;
-  const size_t smem = nb * bstage_bytes + ns * slot_bytes + 1024 + 512;
+  const size_t smem = nb * bstage_bytes + ns * slot_bytes + 1024 + 2048;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  cudaError_t e;
+  const bool wide = p.BN >= 128;
+#define FMM_LAUNCH_TAPCONV(TT, EPI)                                                                              \
+  do {                                                                                                           \
+    cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<TT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                         (int)smem);                                                             \
+    if (e != cudaSuccess) {                                                                                      \
+      set_last_error("tapconv: smem attribute: %s", cudaGetErrorString(e));                                      \
+      return FMM_ERR_SMEM;                                                                                       \
+    }                                                                                                            \
+    tapconv_kernel<TT, EPI><<<grid, (10 + EPI) * 32, smem, stream>>>(p);                                         \
+  } while (0)
   if (dtype == FMM_DT_BF16) {
-    e = cudaFuncSetAttribute(tapconv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_last_error("tapconv: smem attribute: %s", cudaGetErrorString(e));
-      return FMM_ERR_SMEM;
-    }
-    tapconv_kernel<__nv_bfloat16><<<grid, kTapThreads, smem, stream>>>(p);
+    if (wide) FMM_LAUNCH_TAPCONV(__nv_bfloat16, 8); else FMM_LAUNCH_TAPCONV(__nv_bfloat16, 4);
   } else {
-    e = cudaFuncSetAttribute(tapconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_last_error("tapconv: smem attribute: %s", cudaGetErrorString(e));
-      return FMM_ERR_SMEM;
-    }
-    tapconv_kernel<float><<<grid, kTapThreads, smem, stream>>>(p);
+    if (wide) FMM_LAUNCH_TAPCONV(float, 8); else FMM_LAUNCH_TAPCONV(float, 4);
   }
+#undef FMM_LAUNCH_TAPCONV
   FMM_CHECK_LAUNCH("tapconv");
   return FMM_OK;
 }

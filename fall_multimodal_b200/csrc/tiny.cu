@@ -13,7 +13,7 @@ namespace fmm {
 // ---------------------------------------------------------------------------------------------
 // bn_finalize: (sum, sumsq, count) -> mean, rstd, scale a = gamma*rstd, shift b = beta - mean*a
 // ---------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const double* __restrict__ ch_sum, const double* __restrict__ ch_sq, double count,
+__global__ void bn_finalize_kernel(const double* __restrict__ ch_sum, const double* __restrict__ ch_sq, int nrep, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
                                    int training, float* __restrict__ a, float* __restrict__ b,
@@ -22,8 +22,13 @@ __global__ void bn_finalize_kernel(const double* __restrict__ ch_sum, const doub
   if (c >= C) return;
   double mean, var;
   if (training) {
-    mean = ch_sum[c] / count;
-    var = ch_sq[c] / count - mean * mean;
+    double s = 0, q = 0;
+    for (int r = 0; r < nrep; ++r) {
+      s += ch_sum[static_cast<size_t>(r) * C + c];
+      q += ch_sq[static_cast<size_t>(r) * C + c];
+    }
+    mean = s / count;
+    var = q / count - mean * mean;
     if (var < 0) var = 0;
     if (rmean) {
       const double unb = count > 1 ? var * count / (count - 1) : var;
@@ -345,7 +350,7 @@ __global__ void bn2_bwd_coef_kernel(const float* __restrict__ S1, const float* _
 
 // bn1_bwd_coef: per channel, from T1 = sum dy1, T2 = sum dy1*G:
 //   dG = c1*dy1 + c2*G + c3 ; dgamma1 = rstd*(T2 - mu*T1) ; dbeta1 = T1
-__global__ void bn1_bwd_coef_kernel(const double* __restrict__ T1, const double* __restrict__ T2,
+__global__ void bn1_bwd_coef_kernel(const double* __restrict__ T1r, const double* __restrict__ T2r, int nrep,
                                     const float* __restrict__ a1, const float* __restrict__ mean1,
                                     const float* __restrict__ rstd1, double count, int training,
                                     float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ c3,
@@ -353,7 +358,12 @@ __global__ void bn1_bwd_coef_kernel(const double* __restrict__ T1, const double*
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mu = mean1[c], rs = rstd1[c], A1 = a1[c];
-  const double t1 = T1[c], t2 = (T2[c] - mu * T1[c]) * rs;
+  double t1 = 0, t2raw = 0;
+  for (int r = 0; r < nrep; ++r) {
+    t1 += T1r[static_cast<size_t>(r) * C + c];
+    t2raw += T2r[static_cast<size_t>(r) * C + c];
+  }
+  const double t2 = (t2raw - mu * t1) * rs;
   dbeta[c] += static_cast<float>(t1);
   dgamma[c] += static_cast<float>(t2);
   const double m1 = training ? t1 / count : 0.0, m2 = training ? t2 / count : 0.0;
@@ -368,11 +378,11 @@ using namespace fmm;
 
 extern "C" {
 
-int fmm_bn_finalize(const double* ch_sum, const double* ch_sq, double count, const float* gamma, const float* beta,
+int fmm_bn_finalize(const double* ch_sum, const double* ch_sq, int nrep, double count, const float* gamma, const float* beta,
                     float* rmean, float* rvar, float momentum, float eps, int training, float* a, float* b,
                     float* mean_out, float* rstd_out, int C, cudaStream_t stream) {
   FMM_CHECK_ARG(a && b && C > 0 && (training ? (ch_sum && ch_sq) : (rmean && rvar)), "bn_finalize: bad args");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ch_sum, ch_sq, count, gamma, beta, rmean, rvar, momentum, eps,
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ch_sum, ch_sq, nrep, count, gamma, beta, rmean, rvar, momentum, eps,
                                                           training, a, b, mean_out, rstd_out, C);
   FMM_CHECK_LAUNCH("bn_finalize");
   return FMM_OK;
@@ -426,11 +436,11 @@ int fmm_bn2_bwd_coef(const float* S1, const float* S2, const float* S3, const fl
   return FMM_OK;
 }
 
-int fmm_bn1_bwd_coef(const double* T1, const double* T2, const float* a1, const float* mean1, const float* rstd1,
+int fmm_bn1_bwd_coef(const double* T1, const double* T2, int nrep, const float* a1, const float* mean1, const float* rstd1,
                      double count, int training, float* c1, float* c2, float* c3, float* dgamma, float* dbeta, int C,
                      cudaStream_t stream) {
   FMM_CHECK_ARG(T1 && T2 && a1 && mean1 && rstd1 && c1 && c2 && c3 && dgamma && dbeta, "bn1_bwd_coef: bad args");
-  bn1_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, stream>>>(T1, T2, a1, mean1, rstd1, count, training, c1, c2, c3, dgamma,
+  bn1_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, stream>>>(T1, T2, nrep, a1, mean1, rstd1, count, training, c1, c2, c3, dgamma,
                                                            dbeta, C);
   FMM_CHECK_LAUNCH("bn1_bwd_coef");
   return FMM_OK;

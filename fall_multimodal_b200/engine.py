@@ -87,7 +87,8 @@ class TrunkEngine:
         K = self.K
         csr = self.csr(dev)
         A = P["A"]
-        arena = _Arena(dev, 16384, 8 * N * 256 + 4096)
+        NR = ops.NREP
+        arena = _Arena(dev, 7 * 6 * NR * 256 + 4096, 8 * N * 256 + 4096)
         sv = {"blocks": [], "N": N, "dt": dt, "training": training}
 
         # ---- data_bn (stgcan.py:213-218): per-(v,c) BatchNorm1d over (N,T); tiny, torch ----
@@ -126,10 +127,10 @@ class TrunkEngine:
 
             # BN1 statistics (stgcan.py:112), applied inside the temporal conv's prologue
             a1, b1, mean1, rstd1 = (torch.empty(Cout, dtype=torch.float32, device=dev) for _ in range(4))
-            st = arena.f64(2 * Cout)
+            st = arena.f64(2 * NR * Cout)
             if training:
-                ops.colstats(G, st[:Cout], st[Cout:])
-            ops.bn_finalize(st[:Cout], st[Cout:], N * T * V, P[pre + "tcn.0.weight"], P[pre + "tcn.0.bias"],
+                ops.colstats(G, st[:NR * Cout], st[NR * Cout:])
+            ops.bn_finalize(st[:NR * Cout], st[NR * Cout:], N * T * V, P[pre + "tcn.0.weight"], P[pre + "tcn.0.bias"],
                             P[pre + "tcn.0.running_mean"], P[pre + "tcn.0.running_var"], training, a1, b1, mean1, rstd1)
 
             # temporal conv 9x1 (stgcan.py:114-118)
@@ -142,13 +143,13 @@ class TrunkEngine:
 
             # BN2 statistics (:119) + SE pooling (:64) in one pass over U
             a2, b2, mean2, rstd2 = (torch.empty(Cout, dtype=torch.float32, device=dev) for _ in range(4))
-            st2 = arena.f64(2 * Cout)
+            st2 = arena.f64(2 * NR * Cout)
             pool = arena.f32(N, Cout)
             if training:
-                ops.colstats(U, st2[:Cout], st2[Cout:], pool)
+                ops.colstats(U, st2[:NR * Cout], st2[NR * Cout:], pool)
             else:
                 ops.colstats(U, None, None, pool)
-            ops.bn_finalize(st2[:Cout], st2[Cout:], N * To * V, P[pre + "tcn.3.weight"], P[pre + "tcn.3.bias"],
+            ops.bn_finalize(st2[:NR * Cout], st2[NR * Cout:], N * To * V, P[pre + "tcn.3.weight"], P[pre + "tcn.3.bias"],
                             P[pre + "tcn.3.running_mean"], P[pre + "tcn.3.running_var"], training, a2, b2, mean2, rstd2)
 
             # squeeze-excite (stgcan.py:63-70)
@@ -170,10 +171,10 @@ class TrunkEngine:
                 R = torch.empty(N, To, V, Cout, dtype=dt, device=dev)
                 ops.tapconv(x, pw_r, R, shifts=[0], tj=To, istride=s, bias=P[pre + "residual.0.bias"])
                 ar, br, meanr, rstdr = f32(Cout), f32(Cout), f32(Cout), f32(Cout)
-                st3 = arena.f64(2 * Cout)
+                st3 = arena.f64(2 * NR * Cout)
                 if training:
-                    ops.colstats(R, st3[:Cout], st3[Cout:])
-                ops.bn_finalize(st3[:Cout], st3[Cout:], N * To * V, P[pre + "residual.1.weight"],
+                    ops.colstats(R, st3[:NR * Cout], st3[NR * Cout:])
+                ops.bn_finalize(st3[:NR * Cout], st3[NR * Cout:], N * To * V, P[pre + "residual.1.weight"],
                                 P[pre + "residual.1.bias"], P[pre + "residual.1.running_mean"],
                                 P[pre + "residual.1.running_var"], training, ar, br, meanr, rstdr)
                 res = R
@@ -210,7 +211,8 @@ class TrunkEngine:
         csr = self.csr(dev)
         A = P["A"]
         grads = {}
-        arena = _Arena(dev, 32768, 40 * N * 256 + 16 * V * 256 + 7 * 2 * 256 * 64 + 65536)
+        NR = ops.NREP
+        arena = _Arena(dev, 7 * 4 * NR * 256 + 4096, 40 * N * 256 + 7 * NR * V * 256 + 7 * 2 * 256 * 64 + 65536)
         f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
         z32 = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)
         dY = (dfeat / sv["M_last"]).to(dt)[:, None, None, :].expand(N, sv["T_last"], V, 256).contiguous()
@@ -258,10 +260,10 @@ class TrunkEngine:
             dU = torch.empty_like(U)
             dR = torch.empty_like(R) if R is not None else None
             dPre = torch.empty_like(Y) if reskind == "identity" else None
-            sum_dU = arena.f64(Cout)
-            sum_dR = arena.f64(Cout) if R is not None else None
+            sum_dU = arena.f64(NR * Cout)
+            sum_dR = arena.f64(NR * Cout) if R is not None else None
             ops.bn2_bwd_apply(dY, Y, U, R, k1, k2, k3, r1, r2, r3, dU, dR, dPre, sum_dU, sum_dR)
-            grads[pre + "tcn.2.bias"] = sum_dU.float()
+            grads[pre + "tcn.2.bias"] = sum_dU.view(NR, Cout).sum(0).float()
 
             # ---- temporal conv: wgrad + dgrad ----
             Wt = P[pre + "tcn.2.weight"]
@@ -281,15 +283,16 @@ class TrunkEngine:
                     ops.tapconv(dU, pw, dH, shifts=[2, 1, 0, -1], tj=T // 2, ostride=2, ooff=1)
 
             # ---- BN1 + ReLU backward ----
-            T1, T2 = arena.f64(Cout), arena.f64(Cout)
+            T1, T2 = arena.f64(NR * Cout), arena.f64(NR * Cout)
             ops.bn1_bwd_reduce(dH, G, b["a1"], b["b1"], T1, T2)
             c1, c2, c3 = f32(Cout), f32(Cout), f32(Cout)
             dg1, db1n = arena.f32(Cout), arena.f32(Cout)
             ops.bn1_bwd_coef(T1, T2, b["a1"], b["mean1"], b["rstd1"], N * T * V, training, c1, c2, c3, dg1, db1n)
             grads[pre + "tcn.0.weight"], grads[pre + "tcn.0.bias"] = dg1, db1n
             dG = torch.empty_like(G)
-            Tbl = arena.f32(V, Cout)
-            ops.bn1_bwd_apply(dH, G, b["a1"], b["b1"], c1, c2, c3, dG, Tbl)
+            TblR = arena.f32(NR, V, Cout)
+            ops.bn1_bwd_apply(dH, G, b["a1"], b["b1"], c1, c2, c3, dG, TblR)
+            Tbl = TblR.sum(0)
 
             # ---- graph conv: wgrad, bias, dgrad through the weights, edge importance ----
             Wg = P[pre + "gcn.conv.weight"]
@@ -314,7 +317,7 @@ class TrunkEngine:
                 dWr = z32(Cout, Cin, 1, 1)
                 ops.wgrad(x, dR, dWr, shifts=[0], istride=s, s_m=0, s_c2=1, s_co=Cin)
                 grads[pre + "residual.0.weight"] = dWr
-                grads[pre + "residual.0.bias"] = sum_dR.float()
+                grads[pre + "residual.0.bias"] = sum_dR.view(NR, Cout).sum(0).float()
                 grads[pre + "residual.1.weight"], grads[pre + "residual.1.bias"] = dgr, dbr
                 pw_rT = ops.tapconv_pack(Wr, Cin, Cout, Cin, Cout, 0, 1, 0, Cin, 0, [0], dt)
                 addend = torch.zeros_like(x)

@@ -151,10 +151,21 @@ def agg_dcoef(x, P, dcoef, src, dst, kk, K):
     return dcoef
 
 
+NREP = 16  # replication of the cross-block accumulators (see csrc/elementwise.cu: replica_of_block)
+
+
+def _nrep(buf, per_replica):
+    if buf is None:
+        return 1
+    assert buf.numel() % per_replica == 0
+    return buf.numel() // per_replica
+
+
 def colstats(x, ch_sum=None, ch_sq=None, nc_sum=None):
+    """ch_sum / ch_sq: fp64 [nrep][C] (nrep inferred from the buffer size); nc_sum: fp32 [N][C]."""
     N, Tn, V, C = _shape4(x)
     assert x.is_contiguous()
-    L.check(L.load().fmm_colstats(L.ptr(x), L.ptr(ch_sum), L.ptr(ch_sq), L.ptr(nc_sum), N, Tn, V, C,
+    L.check(L.load().fmm_colstats(L.ptr(x), L.ptr(ch_sum), L.ptr(ch_sq), L.ptr(nc_sum), _nrep(ch_sum, C), N, Tn, V, C,
                                   L.dt_of(x.dtype), L.stream()), "colstats")
 
 
@@ -177,28 +188,29 @@ def bn2_bwd_apply(dY, Y, U, R, k1, k2, k3, r1, r2, r3, dU, dR, dPre, sum_dU, sum
     N, Tn, V, C = _shape4(U)
     L.check(L.load().fmm_bn2_bwd_apply(L.ptr(dY), L.ptr(Y), L.ptr(U), L.ptr(R), L.ptr(k1), L.ptr(k2), L.ptr(k3),
                                        L.ptr(r1), L.ptr(r2), L.ptr(r3), L.ptr(dU), L.ptr(dR), L.ptr(dPre),
-                                       L.ptr(sum_dU), L.ptr(sum_dR), N, Tn, V, C, L.dt_of(U.dtype), L.stream()),
+                                       L.ptr(sum_dU), L.ptr(sum_dR), _nrep(sum_dU, C), N, Tn, V, C, L.dt_of(U.dtype),
+                                       L.stream()),
             "bn2_bwd_apply")
 
 
 def bn1_bwd_reduce(dH, G, a1, b1, T1, T2):
     N, Tn, V, C = _shape4(G)
     assert dH.is_contiguous() and dH.shape == G.shape
-    L.check(L.load().fmm_bn1_bwd_reduce(L.ptr(dH), L.ptr(G), L.ptr(a1), L.ptr(b1), L.ptr(T1), L.ptr(T2), N, Tn, V,
-                                        C, L.dt_of(G.dtype), L.stream()), "bn1_bwd_reduce")
+    L.check(L.load().fmm_bn1_bwd_reduce(L.ptr(dH), L.ptr(G), L.ptr(a1), L.ptr(b1), L.ptr(T1), L.ptr(T2), _nrep(T1, C),
+                                        N, Tn, V, C, L.dt_of(G.dtype), L.stream()), "bn1_bwd_reduce")
 
 
 def bn1_bwd_apply(dH, G, a1, b1, c1, c2, c3, dG, Tbl):
     N, Tn, V, C = _shape4(G)
     L.check(L.load().fmm_bn1_bwd_apply(L.ptr(dH), L.ptr(G), L.ptr(a1), L.ptr(b1), L.ptr(c1), L.ptr(c2), L.ptr(c3),
-                                       L.ptr(dG), L.ptr(Tbl), N, Tn, V, C, L.dt_of(G.dtype), L.stream()),
+                                       L.ptr(dG), L.ptr(Tbl), _nrep(Tbl, V * C), N, Tn, V, C, L.dt_of(G.dtype), L.stream()),
             "bn1_bwd_apply")
 
 
 def bn_finalize(ch_sum, ch_sq, count, gamma, beta, rmean, rvar, training, a, b, mean_out, rstd_out,
                 momentum=0.1, eps=1e-5):
     C = a.numel()
-    L.check(L.load().fmm_bn_finalize(L.ptr(ch_sum), L.ptr(ch_sq), float(count), L.ptr(gamma), L.ptr(beta),
+    L.check(L.load().fmm_bn_finalize(L.ptr(ch_sum), L.ptr(ch_sq), _nrep(ch_sum, C), float(count), L.ptr(gamma), L.ptr(beta),
                                      L.ptr(rmean), L.ptr(rvar), momentum, eps, int(training), L.ptr(a), L.ptr(b),
                                      L.ptr(mean_out), L.ptr(rstd_out), C, L.stream()), "bn_finalize")
 
@@ -236,7 +248,7 @@ def bn2_bwd_coef(S1, S2, S3, pool, dp, s, a2, mean2, rstd2, ar, meanr, rstdr, M,
 
 def bn1_bwd_coef(T1, T2, a1, mean1, rstd1, count, training, c1, c2, c3, dgamma, dbeta):
     C = a1.numel()
-    L.check(L.load().fmm_bn1_bwd_coef(L.ptr(T1), L.ptr(T2), L.ptr(a1), L.ptr(mean1), L.ptr(rstd1), float(count),
+    L.check(L.load().fmm_bn1_bwd_coef(L.ptr(T1), L.ptr(T2), _nrep(T1, C), L.ptr(a1), L.ptr(mean1), L.ptr(rstd1), float(count),
                                       int(training), L.ptr(c1), L.ptr(c2), L.ptr(c3), L.ptr(dgamma), L.ptr(dbeta),
                                       C, L.stream()), "bn1_bwd_coef")
 

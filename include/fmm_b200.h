@@ -81,10 +81,12 @@ int fmm_agg_bwd(const void* P, const void* addend, void* dx, const int* rowptr, 
 int fmm_agg_dcoef(const void* x, const void* P, float* dcoef, const int* src, const int* dst, const int* kk, int E,
                   int N, int T, int V, int Cin, int K, int dtype, cudaStream_t stream);
 
+/* Cross-block accumulators (ch_sum, ch_sq, T1, T2, sum_dU, sum_dR: [nrep][C] doubles; Tbl: [nrep][V][C] floats) are
+ * replicated nrep times to spread the atomics; consumers sum the replicas. */
 /* per-channel sum / sum of squares (fp64 accumulators) and per-(n,c) sums: BatchNorm2d batch statistics
  * (stgcan.py:112,119,132) and the AdaptiveAvgPool2d of Channel_Attention (stgcan.py:64) in one pass. */
-int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, int N, int T, int V, int C, int dtype,
-                 cudaStream_t stream);
+int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, int nrep, int N, int T, int V, int C,
+                 int dtype, cudaStream_t stream);
 /* Y = relu(k1[n,c]*U + k0[n,c] + res): BN2 + SE scale + residual + ReLU of st_gcan.forward (stgcan.py:138-144) */
 int fmm_block_out(const void* U, const float* k1, const float* k0, const void* res, const float* ar, const float* br,
                   void* Y, int N, int T, int V, int C, int dtype, cudaStream_t stream);
@@ -92,19 +94,19 @@ int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const 
                             float* S3, int N, int T, int V, int C, int dtype, cudaStream_t stream);
 int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* R, const float* k1, const float* k2,
                       const float* k3, const float* r1, const float* r2, const float* r3, void* dU, void* dR,
-                      void* dPre, double* sum_dU, double* sum_dR, int N, int T, int V, int C, int dtype,
+                      void* dPre, double* sum_dU, double* sum_dR, int nrep, int N, int T, int V, int C, int dtype,
                       cudaStream_t stream);
-int fmm_bn1_bwd_reduce(const void* dH, const void* G, const float* a1, const float* b1, double* T1, double* T2, int N,
-                       int T, int V, int C, int dtype, cudaStream_t stream);
+int fmm_bn1_bwd_reduce(const void* dH, const void* G, const float* a1, const float* b1, double* T1, double* T2,
+                       int nrep, int N, int T, int V, int C, int dtype, cudaStream_t stream);
 int fmm_bn1_bwd_apply(const void* dH, const void* G, const float* a1, const float* b1, const float* c1,
-                      const float* c2, const float* c3, void* dG, float* Tbl, int N, int T, int V, int C, int dtype,
-                      cudaStream_t stream);
+                      const float* c2, const float* c3, void* dG, float* Tbl, int nrep, int N, int T, int V, int C,
+                      int dtype, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * per-channel / per-clip kernels
  * ------------------------------------------------------------------------------------------- */
 /* nn.BatchNorm*: statistics -> scale/shift (+ running stats, momentum/eps as torch) */
-int fmm_bn_finalize(const double* ch_sum, const double* ch_sq, double count, const float* gamma, const float* beta,
+int fmm_bn_finalize(const double* ch_sum, const double* ch_sq, int nrep, double count, const float* gamma, const float* beta,
                     float* rmean, float* rvar, float momentum, float eps, int training, float* a, float* b,
                     float* mean_out, float* rstd_out, int C, cudaStream_t stream);
 /* Channel_Attention MLP (stgcan.py:63-70): pooled sums -> s[n,c] and the fused output coefficients k1, k0 */
@@ -122,7 +124,7 @@ int fmm_bn2_bwd_coef(const float* S1, const float* S2, const float* S3, const fl
                      const float* meanr, const float* rstdr, float M, double count, int training, float* k1, float* k2,
                      float* k3, float* r1, float* r2, float* r3, float* dgamma2, float* dbeta2, float* dgammar,
                      float* dbetar, int N, int C, cudaStream_t stream);
-int fmm_bn1_bwd_coef(const double* T1, const double* T2, const float* a1, const float* mean1, const float* rstd1,
+int fmm_bn1_bwd_coef(const double* T1, const double* T2, int nrep, const float* a1, const float* mean1, const float* rstd1,
                      double count, int training, float* c1, float* c2, float* c3, float* dgamma, float* dbeta, int C,
                      cudaStream_t stream);
 

@@ -224,23 +224,23 @@ __global__ void agg_dcoef_kernel(const T* __restrict__ x, const T* __restrict__ 
 // coefficients in registers. Per-channel partial sums are reduced with warp shuffles over the lanes
 // that share c8, then shared-memory atomics across warps, then ONE global atomic per channel.
 // ------------------------------------------------------------------------------------------
+// Every thread holds NV x 8 partial sums for channel group c8 (row lane rl). They are staged as
+// scratch[rl][c8n*8][NV] with plain conflict-free stores and summed over rl by C*NV threads:
+// shared-memory atomics cost ~2 cycles per lane and serialise the whole SM at the end of each block.
 template <int NV>
-__device__ __forceinline__ void block_channel_reduce(float (&val)[NV][8], float* red, int c8, int c8n) {
-  const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32;
-  const int lane = threadIdx.x & 31;
-  if (pow2) {
-    for (int off = 16; off >= c8n; off >>= 1) {
+__device__ __forceinline__ void block_channel_reduce(const float (&val)[NV][8], float* scratch, float* red, int c8,
+                                                     int c8n, int rl, int RL) {
+  const int C = c8n * 8;
+  float* mine = scratch + (static_cast<size_t>(rl) * C + c8 * 8) * NV;
 #pragma unroll
-      for (int v = 0; v < NV; ++v)
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) val[v][j] += __shfl_xor_sync(0xffffffffu, val[v][j], off);
-    }
-  }
-  if (!pow2 || lane < c8n) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(red + (c8 * 8 + j) * NV + v, val[v][j]);
+    for (int v = 0; v < NV; ++v) mine[j * NV + v] = val[v][j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * NV; i += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < RL; ++r) acc += scratch[static_cast<size_t>(r) * C * NV + i];
+    red[i] = acc;
   }
 }
 
@@ -248,12 +248,11 @@ __device__ __forceinline__ void block_channel_reduce(float (&val)[NV][8], float*
 template <typename T>
 __global__ void colstats_kernel(const T* __restrict__ X, double* __restrict__ ch_sum, double* __restrict__ ch_sq,
                                 float* __restrict__ nc_sum, int Tn, int V, int C, int tchunk, int nrep) {
-  extern __shared__ float red[];  // [C][2]
+  extern __shared__ float red[];  // [C][2] followed by the [RL][C][2] staging area
+  float* scratch = red + 2 * C;
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * tchunk * V;
   const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
   const int c8n = C / 8;
   const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
   const T* base = X + static_cast<size_t>(n) * Tn * V * C + c8 * 8;
@@ -270,7 +269,7 @@ __global__ void colstats_kernel(const T* __restrict__ X, double* __restrict__ ch
       acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
     }
   }
-  block_channel_reduce<2>(acc, red, c8, c8n);
+  block_channel_reduce<2>(acc, scratch, red, c8, c8n, rl, RL);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float s = red[2 * c], q = red[2 * c + 1];
@@ -322,12 +321,11 @@ template <typename T>
 __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ U,
                                            const T* __restrict__ R, float* __restrict__ S1, float* __restrict__ S2,
                                            float* __restrict__ S3, int Tn, int V, int C, int tchunk) {
-  extern __shared__ float red[];  // [C][3]
+  extern __shared__ float red[];  // [C][3] followed by the [RL][C][3] staging area
+  float* scratch = red + 3 * C;
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * tchunk * V;
   const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
   const int c8n = C / 8;
   const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
   const size_t base = static_cast<size_t>(n) * Tn * V * C + c8 * 8;
@@ -350,7 +348,7 @@ __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __
       if (R) acc[2][j] = fmaf(d, rr[j], acc[2][j]);
     }
   }
-  block_channel_reduce<3>(acc, red, c8, c8n);
+  block_channel_reduce<3>(acc, scratch, red, c8, c8n, rl, RL);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     atomicAdd(S1 + static_cast<size_t>(n) * C + c, red[3 * c]);
@@ -372,12 +370,11 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
                                      const float* __restrict__ r3, T* __restrict__ dU, T* __restrict__ dR,
                                      T* __restrict__ dPre, double* __restrict__ sum_dU,
                                      double* __restrict__ sum_dR, int Tn, int V, int C, int tchunk, int nrep) {
-  extern __shared__ float red[];  // [C][2]
+  extern __shared__ float red[];  // [C][2] followed by the [RL][C][2] staging area
+  float* scratch = red + 2 * C;
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * tchunk * V;
   const int r1r = min((blockIdx.x + 1) * tchunk, Tn) * V;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
   const int c8n = C / 8;
   const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
   const int c0 = c8 * 8;
@@ -417,7 +414,7 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
     if (R) store8(dR + off, orr);
     if (dPre) store8(dPre + off, d);
   }
-  if (sum_dU || sum_dR) block_channel_reduce<2>(acc, red, c8, c8n);
+  block_channel_reduce<2>(acc, scratch, red, c8, c8n, rl, RL);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const size_t ro = static_cast<size_t>(replica_of_block(nrep)) * C;
@@ -431,12 +428,11 @@ template <typename T>
 __global__ void bn1_bwd_reduce_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
                                       const float* __restrict__ b1, double* __restrict__ T1,
                                       double* __restrict__ T2, int Tn, int V, int C, int tchunk, int nrep) {
-  extern __shared__ float red[];  // [C][2]
+  extern __shared__ float red[];  // [C][2] followed by the [RL][C][2] staging area
+  float* scratch = red + 2 * C;
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * tchunk * V;
   const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
   const int c8n = C / 8;
   const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
   float a[8], b[8];
@@ -462,7 +458,7 @@ __global__ void bn1_bwd_reduce_kernel(const T* __restrict__ dH, const T* __restr
       acc[1][j] = fmaf(d, g[j], acc[1][j]);
     }
   }
-  block_channel_reduce<2>(acc, red, c8, c8n);
+  block_channel_reduce<2>(acc, scratch, red, c8, c8n, rl, RL);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const size_t ro = static_cast<size_t>(replica_of_block(nrep)) * C;
@@ -605,7 +601,7 @@ int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, in
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    colstats_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, Tn, V, C, tchunk, nrep);
+    colstats_kernel<T><<<grid, rowwalk_threads(C), (2 * C + rowwalk_threads(C) * 16) * sizeof(float), stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, Tn, V, C, tchunk, nrep);
   })
   FMM_CHECK_LAUNCH("colstats");
   return FMM_OK;
@@ -629,7 +625,7 @@ int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const 
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    blockout_bwd_reduce_kernel<T><<<grid, rowwalk_threads(C), 3 * C * sizeof(float), stream>>>(
+    blockout_bwd_reduce_kernel<T><<<grid, rowwalk_threads(C), (3 * C + rowwalk_threads(C) * 24) * sizeof(float), stream>>>(
         (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, S1, S2, S3, Tn, V, C, tchunk);
   })
   FMM_CHECK_LAUNCH("blockout_bwd_reduce");
@@ -646,7 +642,7 @@ int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* 
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    bn2_bwd_apply_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>(
+    bn2_bwd_apply_kernel<T><<<grid, rowwalk_threads(C), (2 * C + rowwalk_threads(C) * 16) * sizeof(float), stream>>>(
         (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, k1, k2, k3, r1, r2, r3, (T*)dU, (T*)dR, (T*)dPre, sum_dU,
         sum_dR, Tn, V, C, tchunk, nrep);
   })
@@ -661,7 +657,7 @@ int fmm_bn1_bwd_reduce(const void* dH, const void* G, const float* a1, const flo
   const int tchunk = pick_tchunk(N, Tn);
   dim3 grid((Tn + tchunk - 1) / tchunk, N);
   FMM_DISPATCH(dtype, {
-    bn1_bwd_reduce_kernel<T><<<grid, rowwalk_threads(C), 2 * C * sizeof(float), stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, Tn, V, C, tchunk, nrep);
+    bn1_bwd_reduce_kernel<T><<<grid, rowwalk_threads(C), (2 * C + rowwalk_threads(C) * 16) * sizeof(float), stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, Tn, V, C, tchunk, nrep);
   })
   FMM_CHECK_LAUNCH("bn1_bwd_reduce");
   return FMM_OK;

@@ -29,6 +29,7 @@ class GradBuckets:
         self._pending = []
         self._handles = []
         self._comm_stream = None
+        self._comm_used = False  # anything queued on the comm stream since the last wait()
         for params in groups:
             params = [p for p in params if p.requires_grad]
             if not params:
@@ -62,6 +63,7 @@ class GradBuckets:
         op = dist.ReduceOp.AVG if (self.average and flat.is_cuda) else dist.ReduceOp.SUM
         if self._comm_stream is not None:
             self._comm_stream.wait_stream(torch.cuda.current_stream(flat.device))
+            self._comm_used = True
             with torch.cuda.stream(self._comm_stream):
                 self._handles.append(dist.all_reduce(flat, op=op, group=self.pg, async_op=True))
         else:
@@ -83,5 +85,6 @@ class GradBuckets:
         for h in self._handles:
             h.wait()
         self._handles.clear()
-        if self._comm_stream is not None:
+        if self._comm_stream is not None and self._comm_used:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._comm_used = False

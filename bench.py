@@ -312,7 +312,13 @@ def run_ours(args):
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured NCCL collectives keep the communicator busy at teardown: destroy_process_group() was
+        # seen to hang after the result line. Drain, rendezvous once more and leave without it.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .sensor import CNN1D
+from .sensor import CNN1D, BiLSTM
 from .stgcan import STGCAN, _compute_dtype
 
 
@@ -83,3 +83,18 @@ class TwoStreamSTGCAN_CNN1D(TwoStreamSTGCAN):
             f = self.cnn.forward_channels_last(sensor)        # (N, L/4, 32)
             return f.permute(0, 2, 1).flatten(1)               # torch's (N, 32, L/4).flatten(1) order
         return [run]
+
+
+class TwoStreamSTGCAN_BiLSTM(TwoStreamSTGCAN):
+    """Reference ``TwoStreamSTGCAN_BiLSTM(in_channels, graph_args, num_class, bilstm_input_size=15)``
+    (combination.py:27-46): the sensor branch contributes its ``num_class`` logits to the concat;
+    state-dict prefixes ``stgcan_1.``, ``stgcan_2.``, ``lstm.``, ``fc.``."""
+
+    def __init__(self, in_channels, graph_args, num_class, bilstm_input_size=15):
+        super().__init__(in_channels, graph_args, num_class)
+        self.lstm = BiLSTM(input_size=bilstm_input_size, hidden_size=64, num_layers=1, dropout_prob=0.3,
+                           num_classes=num_class, feature="mean")
+        self.fc = nn.Linear(256 * 2 + num_class, num_class)
+
+    def _branches(self, skel, sensor):
+        return [lambda: self.lstm(None, sensor)]

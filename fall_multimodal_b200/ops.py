@@ -284,3 +284,23 @@ def conv1d_k5_bwd(x, dy, w, dx, dw, db):
     assert dy.is_contiguous() and dy.shape == (N, Ln, Co)
     L.check(L.load().fmm_conv1d_k5_bwd(L.ptr(x), L.ptr(dy), L.ptr(w), L.ptr(dx), L.ptr(dw), L.ptr(db), N, Ln, Ci, Co,
                                        L.stream()), "conv1d_k5_bwd")
+
+
+# ---------------------------------------------------------------------------------------------
+# LSTM recurrence (csrc/lstm.cu), fp32, weights stacked per direction
+# ---------------------------------------------------------------------------------------------
+def lstm_fwd(x, w_ih, w_hh, b_ih, b_hh, out, gates=None, cseq=None):
+    N, Tn, I = x.shape
+    ndir, G, H = w_hh.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.shape == (N, Tn, ndir * H)
+    L.check(L.load().fmm_lstm_fwd(L.ptr(x), L.ptr(w_ih), L.ptr(w_hh), L.ptr(b_ih), L.ptr(b_hh), L.ptr(out), L.ptr(gates),
+                                  L.ptr(cseq), N, Tn, I, H, ndir, L.stream()), "lstm_fwd")
+    return out
+
+
+def lstm_bwd(x, w_ih, w_hh, out, gates, cseq, dout, dw_ih, dw_hh, db, dx=None):
+    N, Tn, I = x.shape
+    ndir, G, H = w_hh.shape
+    assert dout.is_contiguous() and dout.shape == out.shape
+    L.check(L.load().fmm_lstm_bwd(L.ptr(x), L.ptr(w_ih), L.ptr(w_hh), L.ptr(out), L.ptr(gates), L.ptr(cseq), L.ptr(dout),
+                                  L.ptr(dw_ih), L.ptr(dw_hh), L.ptr(db), L.ptr(dx), N, Tn, I, H, ndir, L.stream()), "lstm_bwd")

@@ -101,3 +101,87 @@ class CNN1D(nn.Module):
     def forward(self, x):
         """x: (N, Cin, L) like the reference; returns (N, 32, L//4)."""
         return self.forward_channels_last(x.permute(0, 2, 1)).permute(0, 2, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# BiLSTM sensor branch (reference: F2/Model/bilstm.py:5-58)
+# ------------------------------------------------------------------------------------------------
+class _LSTMFn(torch.autograd.Function):
+    """Bidirectional single-layer LSTM from zero state: x (N,T,I) -> (N,T,2H), persistent-CTA kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        with torch.autocast("cuda", enabled=False):
+            x = x.float().contiguous()
+            wi = torch.stack([w_ih, w_ih_r]).float().contiguous()
+            wh = torch.stack([w_hh, w_hh_r]).float().contiguous()
+            bi = torch.stack([b_ih, b_ih_r]).float().contiguous()
+            bh = torch.stack([b_hh, b_hh_r]).float().contiguous()
+            N, Tn, _ = x.shape
+            H = wh.shape[2]
+            out = torch.empty(N, Tn, 2 * H, device=x.device)
+            need = any(ctx.needs_input_grad)
+            gates = torch.empty(2, N, Tn, 4 * H, device=x.device) if need else None
+            cseq = torch.empty(2, N, Tn, H, device=x.device) if need else None
+            ops.lstm_fwd(x, wi, wh, bi, bh, out, gates, cseq)
+        ctx.saved = (x, wi, wh, out, gates, cseq)
+        ctx.need_dx = ctx.needs_input_grad[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wi, wh, out, gates, cseq = ctx.saved
+        with torch.autocast("cuda", enabled=False):
+            dwi, dwh = torch.zeros_like(wi), torch.zeros_like(wh)
+            db = torch.zeros(wi.shape[0], wi.shape[1], device=x.device)
+            dx = torch.zeros_like(x) if ctx.need_dx else None
+            ops.lstm_bwd(x, wi, wh, out, gates, cseq, dout.float().contiguous(), dwi, dwh, db, dx)
+        ctx.saved = None
+        return dx, dwi[0], dwh[0], db[0], db[0], dwi[1], dwh[1], db[1], db[1]
+
+
+class ChannelAttention(nn.Module):
+    """Parameter container of the sensor-branch gate (bilstm.py:5-19)."""
+
+    def __init__(self, input_size, reduce_rate=1 / 8):
+        super().__init__()
+        self.attention = nn.Sequential(nn.Linear(input_size, int(input_size * reduce_rate)), nn.ReLU(),
+                                       nn.Linear(int(input_size * reduce_rate), input_size), nn.Sigmoid())
+
+
+class BiLSTM(nn.Module):
+    """``BiLSTM(input_size, hidden_size, num_layers, dropout_prob, num_classes=1, feature='last'|'mean')``
+    with the reference's state_dict keys (bilstm.py:21-39); ``forward(skel, sensor)`` ignores ``skel``
+    (bilstm.py:41). The recurrence runs in csrc/lstm.cu; the (N,128) tail (mean/last, BatchNorm1d,
+    channel gate, Linear) is a handful of tiny torch ops in fp32."""
+
+    def __init__(self, input_size, hidden_size, num_layers, dropout_prob, num_classes=1, feature="last"):
+        super().__init__()
+        if num_layers != 1 or hidden_size != 64:
+            raise NotImplementedError("the persistent LSTM kernel implements the reference configuration: 1 layer, H=64")
+        self.input_size, self.hidden_size, self.num_layers, self.num_classes = input_size, hidden_size, num_layers, num_classes
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # dropout with one layer is a no-op, as in the reference
+            self.lstm1 = nn.LSTM(input_size, hidden_size, num_layers, batch_first=True, bidirectional=True,
+                                 dropout=dropout_prob)
+        self.batchnorm = nn.BatchNorm1d(hidden_size * 2)
+        self.channelattention = ChannelAttention(hidden_size * 2)
+        self.feature = feature
+        self.fc = nn.Sequential(nn.Flatten(), nn.Linear(hidden_size * 2, num_classes))
+
+    def features(self, sensor):
+        if not sensor.is_cuda:
+            raise RuntimeError("fall_multimodal_b200.BiLSTM runs on CUDA (sm_100a) only; there is no CPU fallback")
+        l = self.lstm1
+        out = _LSTMFn.apply(sensor, l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0, l.weight_ih_l0_reverse,
+                            l.weight_hh_l0_reverse, l.bias_ih_l0_reverse, l.bias_hh_l0_reverse)
+        return out[:, -1, :] if self.feature == "last" else out.mean(dim=1)      # bilstm.py:52-55
+
+    def forward(self, skel, sensor):
+        with torch.autocast("cuda", enabled=False):
+            out = self.features(sensor)
+            out = self.batchnorm(out)                                             # bilstm.py:56
+            att = self.channelattention.attention
+            out = out * att(out)                                                  # bilstm.py:16-19
+            return self.fc(out)                                                   # bilstm.py:58

@@ -140,6 +140,18 @@ int fmm_pool2_bwd(const float* y, const float* a, const float* b, const float* d
 int fmm_conv1d_k5_bwd(const float* x, const float* dy, const float* w, float* dx, float* dw, float* db, int N, int L,
                       int Ci, int Co, cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * accelerometer branch: nn.LSTM(I, H=64, 1 layer, batch_first, bidirectional) of BiLSTM (bilstm.py:29,48),
+ * persistent-CTA recurrence, fp32. Weights stacked per direction ([ndir][4H][I], [ndir][4H][H], [ndir][4H]);
+ * out [N][T][ndir*H]; gates [ndir][N][T][4H] / cseq [ndir][N][T][H] are saved for BPTT when non-NULL.
+ * lstm_bwd ACCUMULATES dw_ih, dw_hh, db (zero first); dx (optional, zero first) is the input gradient.
+ * ------------------------------------------------------------------------------------------- */
+int fmm_lstm_fwd(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                 float* out, float* gates, float* cseq, int N, int T, int I, int H, int ndir, cudaStream_t stream);
+int fmm_lstm_bwd(const float* x, const float* w_ih, const float* w_hh, const float* out, const float* gates,
+                 const float* cseq, const float* dout, float* dw_ih, float* dw_hh, float* db, float* dx, int N,
+                 int T, int I, int H, int ndir, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

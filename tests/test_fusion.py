@@ -85,3 +85,92 @@ def test_two_stream_cnn_matches_oracle(dtype, concurrent):
             worst = max(worst, (p.grad.double() - r).abs().max().item() / scale)
         print(f"fusion fp32: logits {err:.2e}, worst grad err {worst:.2e} (natural ReLU decisions)")
         assert worst < 5e-2  # single ReLU-decision flips allowed here; the strict check is in test_stgcan.py
+
+
+@gpu
+def test_bilstm_matches_reference_fixture():
+    from fall_multimodal_b200 import BiLSTM
+
+    dev = torch.device("cuda:0")
+    fx = load("bilstm_mean")
+    m = BiLSTM(15, 64, 1, 0.3, 11, "mean")
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == fx["shapes"]
+    sd.update(O.fill_state_dict(fx["shapes"], fx["fill_seed"]))
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    _, sensor, target, _ = O.synthetic_batch(6, 4, 14, 11, sensor_len=30, sensor_ch=15, seed=fx["batch_seed"])
+    sensor, target = sensor.to(dev), target.to(dev)
+    out = m(None, sensor)
+    loss = torch.nn.CrossEntropyLoss()(out, target)
+    loss.backward()
+    ref = fx["logits"].to(dev)
+    assert (out - ref).abs().max().item() / ref.abs().max().item() < 1e-4
+    assert abs(loss.item() - fx["loss"]) < 1e-4
+    worst = check_grads({k: p.grad for k, p in m.named_parameters()}, fx["grads"], 1e-4)
+    print("bilstm worst grad err", worst)
+    m.eval()
+    sd2 = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ev = m(None, sensor)
+        evo = O.bilstm_forward(sd2, sensor.cpu(), training=False)
+    assert (ev.cpu() - evo).abs().max().item() / evo.abs().max().item() < 1e-4
+
+
+@gpu
+@pytest.mark.parametrize("N,L,I,feature", [(40, 128, 6, "mean"), (5, 30, 4, "last"), (33, 7, 32, "mean")])
+def test_bilstm_shapes_against_oracle(N, L, I, feature):
+    """HAR30-like 128x6 windows, UR-Fall 30x4, and the CNN->LSTM chain's 7x32 (input gradient needed)."""
+    from fall_multimodal_b200 import BiLSTM
+
+    dev = torch.device("cuda:0")
+    m = BiLSTM(I, 64, 1, 0.3, 11, feature)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = m.state_dict()
+    sd.update(O.fill_state_dict(shapes, 12))
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, L, I, generator=g).to(dev).requires_grad_(True)
+    osd = {k: (v.detach().double().clone() if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    for k, v in osd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    xo = x.detach().double().requires_grad_(True)
+    oo = O.bilstm_forward(osd, xo, training=True, feature=feature)
+    oo.square().mean().backward()
+    out = m(None, x)
+    out.square().mean().backward()
+    assert (out.double() - oo).abs().max().item() / oo.abs().max().item() < 1e-4
+    for k, p in m.named_parameters():
+        r = osd[k].grad
+        assert (p.grad.double() - r).abs().max().item() / max(r.abs().max().item(), 1e-12) < 2e-4, k
+    assert (x.grad.double() - xo.grad).abs().max().item() / xo.grad.abs().max().item() < 2e-4
+
+
+@gpu
+def test_two_stream_bilstm_matches_reference_fixture():
+    """The reference's own fusion class (combination.py:27-46) against its golden outputs."""
+    from fall_multimodal_b200 import TwoStreamSTGCAN_BiLSTM
+
+    dev = torch.device("cuda:0")
+    fx = load("two_stream_bilstm")
+    c = fx["config"]
+    m = TwoStreamSTGCAN_BiLSTM(3, {"layout": c["layout"], "strategy": c["strategy"]}, c["num_class"], c["I"])
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == fx["shapes"]
+    sd.update(O.fill_state_dict(fx["shapes"], fx["fill_seed"]))
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    m.compute_dtype = torch.float32
+    skel, sensor, target, _ = O.synthetic_batch(c["N"], c["T"], 14, 11, sensor_len=c["L"], sensor_ch=c["I"], seed=fx["batch_seed"])
+    skel, sensor, target = skel.to(dev), sensor.to(dev), target.to(dev)
+    out = m(skel, sensor)
+    loss = torch.nn.CrossEntropyLoss()(out, target)
+    loss.backward()
+    ref = fx["logits"].to(dev)
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-4 and abs(loss.item() - fx["loss"]) < 1e-4
+    assert torch.equal(out.argmax(-1), ref.argmax(-1))
+    worst = check_grads({k: p.grad for k, p in m.named_parameters()}, fx["grads"], 5e-2)  # ReLU-flip tolerant
+    print(f"two_stream_bilstm: logits {err:.2e}, worst grad err vs reference fixture {worst:.2e}")

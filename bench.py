@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips per CPU-baseline step (bounded sample)")
-    ap.add_argument("--streams", type=int, default=0, help="1: run the independent branches on side streams")
+    ap.add_argument("--streams", type=int, default=1, help="1: run the independent branches (two trunks, sensor) on side streams")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the whole train step as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

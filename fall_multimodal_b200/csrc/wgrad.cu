@@ -35,7 +35,9 @@ struct WgradParams {
   int minshift, win_atoms;
   int JT;                 // positions per unit (16 or 8) -> K' = 8*JT rows
   int MCH;                // 64-channel chunks per ci tile (1 or 2)
-  int BN, TG;             // co tile width, taps per item
+  int BN, TG;             // co tile width, accumulators (taps, or tap pairs) per item
+  int pair;               // 1: Cin <= 64, one M=128 MMA covers taps (m, m+1): rows 64..127 read the window one atom later
+  int nacc_total;         // accumulators over all items: ntaps, or ceil(ntaps/2) in pair mode
   int ci_tiles, tap_groups, co_tiles, items, slices;
   int ncols, ngroups, njchunks, total_units;
   int nstages;
@@ -75,8 +77,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   const int co_tile = item % p.co_tiles;
   const int tg = (item / p.co_tiles) % p.tap_groups;
   const int ci_tile = item / (p.co_tiles * p.tap_groups);
-  const int m0 = tg * p.TG;
-  const int mt = (p.ntaps - m0) < p.TG ? (p.ntaps - m0) : p.TG;  // taps of this item
+  const int acc0 = tg * p.TG;                                                    // first accumulator of this item
+  const int mt = (p.nacc_total - acc0) < p.TG ? (p.nacc_total - acc0) : p.TG;   // accumulators of this item
+  const int m0 = p.pair ? 2 * acc0 : acc0;                                       // first tap of this item
+  const int tstep = p.pair ? 2 : 1;
   const int my_units = slice < p.total_units ? (p.total_units - slice + p.slices - 1) / p.slices : 0;
 
   if (threadIdx.x == 0) {
@@ -238,9 +242,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       // ------------------------------ epilogue (same warps) ------------------------------
       mbar_wait(acc_full, 0, p.err, 12);
       tc_fence_after();
-      const int row = warp * 32 + lane;  // channel inside the ci tile
-      const int ci = ci_tile * p.MCH * 64 + row;
-      const bool ci_ok = row < p.MCH * 64 && ci < p.Cin;
+      const int row = warp * 32 + lane;  // channel inside the ci tile (pair mode: rows 64..127 = next tap)
+      const int second = (p.pair && row >= 64) ? 1 : 0;
+      const int ci = ci_tile * p.MCH * 64 + (second ? row - 64 : row);
+      const bool ci_ok = (p.pair || row < p.MCH * 64) && ci < p.Cin;
       const long long ci_off = ci_ok ? (ci / p.C2) * p.s_c1 + (ci % p.C2) * p.s_c2 : 0;
       for (int t = 0; t < mt; ++t) {
         for (int cg = 0; cg < p.BN / 32; ++cg) {
@@ -256,8 +261,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(corr[i]));
           }
-          if (ci_ok) {
-            float* dst = p.dw + (m0 + t) * p.s_m + ci_off;
+          if (ci_ok && m0 + t * tstep + second < p.ntaps) {
+            float* dst = p.dw + (m0 + t * tstep + second) * p.s_m + ci_off;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int co = co_tile * p.BN + cg * 32 + i;
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           const uint32_t b_lo0 = desc_lo(a_base + a_bytes, b_lbo);
           if (elect_one()) {
             for (int t = 0; t < mt; ++t) {
-              const uint32_t a_lo0 = desc_lo(a_base + static_cast<uint32_t>(p.shift[m0 + t] - p.minshift) * 1024u, a_lbo);
+              const uint32_t a_lo0 = desc_lo(a_base + static_cast<uint32_t>(p.shift[m0 + t * tstep] - p.minshift) * 1024u, a_lbo);
               const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(t) * acc_stride;
               for (int kk = 0; kk < p.JT / 2; ++kk) {
                 const uint32_t a_lo = a_lo0 + kk * a_kstep, b_lo = b_lo0 + kk * b_kstep;
@@ -375,10 +380,14 @@ int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, c
     p.MCH = 1;
     p.BN = ntaps > 1 ? 64 : (cout64 < 128 ? cout64 : 128);
   }
+  bool consecutive = ntaps > 1;
+  for (int i = 1; i < ntaps; ++i) consecutive = consecutive && (shifts[i] == shifts[i - 1] + 1);
+  p.pair = (nparts == 1 && p.MCH == 1 && consecutive) ? 1 : 0;
+  p.nacc_total = p.pair ? (ntaps + 1) / 2 : ntaps;
   const int max_tg = 512 / (p.BN * (nparts == 1 ? 1 : 2));
-  const int ngrp = (ntaps + max_tg - 1) / max_tg;
-  p.TG = (ntaps + ngrp - 1) / ngrp;
-  p.tap_groups = (ntaps + p.TG - 1) / p.TG;
+  const int ngrp = (p.nacc_total + max_tg - 1) / max_tg;
+  p.TG = (p.nacc_total + ngrp - 1) / ngrp;
+  p.tap_groups = (p.nacc_total + p.TG - 1) / p.TG;
   p.minshift = mn;
   p.win_atoms = (p.JT - 1) * istride + (mx - mn) + 1;
   p.ci_tiles = (Cin + 64 * p.MCH - 1) / (64 * p.MCH);

@@ -98,3 +98,57 @@ class TwoStreamSTGCAN_BiLSTM(TwoStreamSTGCAN):
 
     def _branches(self, skel, sensor):
         return [lambda: self.lstm(None, sensor)]
+
+
+def bone_stream(skel: torch.Tensor, parents: torch.Tensor) -> torch.Tensor:
+    """bone[v] = joint[v] - joint[parent(v)] over the layout's neighbour links (root: zero vector)."""
+    return skel - skel.index_select(3, parents)
+
+
+def layout_parents(layout: str) -> list:
+    """Parent joint of every joint: breadth-first tree from the layout's centre over its neighbour links."""
+    from collections import deque
+
+    from .graph import _LAYOUTS
+
+    num_node, links, center = _LAYOUTS[layout]
+    nbr = [[] for _ in range(num_node)]
+    for i, j in links:
+        nbr[i].append(j)
+        nbr[j].append(i)
+    parent = list(range(num_node))
+    seen, q = {center}, deque([center])
+    while q:
+        u = q.popleft()
+        for w in sorted(nbr[u]):
+            if w not in seen:
+                seen.add(w)
+                parent[w] = u
+                q.append(w)
+    return parent
+
+
+class ThreeStreamSTGCAN(nn.Module):
+    """Joint / bone / motion 3-stream GCN of BASELINE config 3. The reference file ``3_stream_fall.py`` is
+    empty: this follows ``TwoStreamSTGCAN`` (combination.py:9-25) with a third trunk on the
+    bone vectors; joint and motion streams are pinned by the reference, the bone stream is not."""
+
+    def __init__(self, in_channels, graph_args, num_class):
+        super().__init__()
+        self.stgcan_1 = STGCAN(3, graph_args, num_class=None)   # joints (x, y, score)
+        self.stgcan_2 = STGCAN(2, graph_args, num_class=None)   # motion (dx, dy), T-1 frames
+        self.stgcan_3 = STGCAN(3, graph_args, num_class=None)   # bones
+        self.fc = nn.Linear(256 * 3, num_class)
+        self.register_buffer("parents", torch.tensor(layout_parents(graph_args["layout"]), dtype=torch.long))
+        self.compute_dtype = None
+
+    def forward(self, skel, sensor=None):
+        dt = _compute_dtype(self)
+        for m in (self.stgcan_1, self.stgcan_2, self.stgcan_3):
+            m.compute_dtype = dt
+        mot = skel[:, :2, 1:] - skel[:, :2, :-1]
+        bone = bone_stream(skel, self.parents)
+        x = torch.cat([self.stgcan_1.features(skel), self.stgcan_2.features(mot), self.stgcan_3.features(bone)], dim=-1)
+        with torch.autocast("cuda", enabled=False):
+            out = torch.addmm(self.fc.bias, x.float(), self.fc.weight.t())
+        return out.to(dt) if dt == torch.bfloat16 else out

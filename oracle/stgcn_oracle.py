@@ -306,6 +306,17 @@ def two_stream_cnn_forward(sd, skel, sensor, training=True, update=None):
     return F.linear(x, sd["fc.weight"], sd["fc.bias"])
 
 
+def three_stream_forward(sd, skel, parents, training=True, update=None):
+    """BASELINE config 3 (bone stream NOT in the reference, SURVEY D1: parity unpinned for it):
+    joints + motion as combination.py:9-25, plus bones = joint - joint[parent]; cat -> Linear(768, C)."""
+    mot = skel[:, :2, 1:] - skel[:, :2, :-1]
+    bone = skel - skel.index_select(3, parents)
+    f1 = stgcan_forward(_sub(sd, "stgcan_1."), skel, training, _PrefixDict(update, "stgcan_1."))
+    f2 = stgcan_forward(_sub(sd, "stgcan_2."), mot, training, _PrefixDict(update, "stgcan_2."))
+    f3 = stgcan_forward(_sub(sd, "stgcan_3."), bone, training, _PrefixDict(update, "stgcan_3."))
+    return F.linear(torch.cat((f1, f2, f3), dim=-1), sd["fc.weight"], sd["fc.bias"])
+
+
 class _PrefixDict:
     """Writes ``update[prefix + k] = v`` into a parent dict (running-stat updates of sub-modules)."""
 

@@ -174,3 +174,28 @@ def test_two_stream_bilstm_matches_reference_fixture():
     assert torch.equal(out.argmax(-1), ref.argmax(-1))
     worst = check_grads({k: p.grad for k, p in m.named_parameters()}, fx["grads"], 5e-2)  # ReLU-flip tolerant
     print(f"two_stream_bilstm: logits {err:.2e}, worst grad err vs reference fixture {worst:.2e}")
+
+
+@gpu
+def test_three_stream_matches_oracle():
+    """Config 3 (joint/bone/motion). Bone stream: same torch expression on both sides (unpinned by the reference)."""
+    from fall_multimodal_b200 import ThreeStreamSTGCAN
+
+    dev = torch.device("cuda:0")
+    N, T, V = 6, 12, 18
+    m = ThreeStreamSTGCAN(3, {"layout": "coco_mmpose", "strategy": "spatial"}, 11)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if k != "parents"}
+    sd = m.state_dict()
+    sd.update(O.fill_state_dict(shapes, 17))
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    m.compute_dtype = torch.float32
+    skel, _, target, _ = O.synthetic_batch(N, T, V, 11, seed=23)
+    skel, target = skel.to(dev), target.to(dev)
+    osd = {k: (v.detach().double().clone() if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    oout = O.three_stream_forward(osd, skel.double(), m.parents, training=True)
+    out = m(skel, None)
+    torch.nn.CrossEntropyLoss()(out, target).backward()
+    err = (out.double() - oout).abs().max().item() / oout.abs().max().item()
+    assert err < 1e-4, err
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())

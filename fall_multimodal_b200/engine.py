@@ -212,7 +212,10 @@ class TrunkEngine:
         A = P["A"]
         grads = {}
         NR = ops.NREP
-        arena = _Arena(dev, 7 * 4 * NR * 256 + 4096, 40 * N * 256 + 7 * NR * V * 256 + 7 * 2 * 256 * 64 + 65536)
+        wsize = sum(9 * co * co + K * co * ci + (co * ci if r == "conv" else 0) + 4 * K * V * V
+                    for ci, co, _, r in self.blocks)
+        arena = _Arena(dev, 7 * 4 * NR * 256 + 4096,
+                       40 * N * 256 + 7 * NR * V * 256 + 7 * 2 * 256 * 64 + 65536 + wsize + 64 * len(self.blocks))
         f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
         z32 = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)
         dY = (dfeat / sv["M_last"]).to(dt)[:, None, None, :].expand(N, sv["T_last"], V, 256).contiguous()
@@ -267,7 +270,7 @@ class TrunkEngine:
 
             # ---- temporal conv: wgrad + dgrad ----
             Wt = P[pre + "tcn.2.weight"]
-            dWt = z32(Cout, Cout, 9, 1)
+            dWt = arena.f32(Cout, Cout, 9, 1)
             ops.wgrad(G, dU, dWt, shifts=list(range(-4, 5)), istride=s, in_scale=b["a1"], in_shift=b["b1"],
                       in_relu=True, s_m=1, s_c2=9, s_co=Cout * 9)
             grads[pre + "tcn.2.weight"] = dWt
@@ -296,7 +299,7 @@ class TrunkEngine:
 
             # ---- graph conv: wgrad, bias, dgrad through the weights, edge importance ----
             Wg = P[pre + "gcn.conv.weight"]
-            dWg = z32(K * Cout, Cin, 1, 1)
+            dWg = arena.f32(K * Cout, Cin, 1, 1)
             ops.wgrad(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
             grads[pre + "gcn.conv.weight"] = dWg
             grads[pre + "gcn.conv.bias"] = (b["colsum"] @ Tbl).flatten()
@@ -314,7 +317,7 @@ class TrunkEngine:
                 addend = dPre
             elif reskind == "conv":
                 Wr = P[pre + "residual.0.weight"]
-                dWr = z32(Cout, Cin, 1, 1)
+                dWr = arena.f32(Cout, Cin, 1, 1)
                 ops.wgrad(x, dR, dWr, shifts=[0], istride=s, s_m=0, s_c2=1, s_co=Cin)
                 grads[pre + "residual.0.weight"] = dWr
                 grads[pre + "residual.0.bias"] = sum_dR.view(NR, Cout).sum(0).float()
@@ -331,7 +334,7 @@ class TrunkEngine:
             else:
                 ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K)
             bg = P[pre + "gcn.conv.bias"].view(K, Cout)
-            dA = torch.zeros(K * V * V, dtype=torch.float32, device=dev)
+            dA = arena.f32(K * V * V)
             dA[csr["dense_idx"]] = dcoef
             grads[f"edge_importance.{i}"] = A * (dA.view(K, V, V) + (bg @ Tbl.t())[:, None, :])
             if self.debug is not None:

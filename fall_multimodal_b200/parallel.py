@@ -2,11 +2,16 @@
 
 The reference is single-process / single-device; the only place its hot path
 shards naturally is the batch, with ONE exchange step: the gradient sum. One process per GPU
-(torchrun), replicated weights, contiguous batch shards. Gradients live in a few flat buckets
-(``p.grad`` are views into them); a post-accumulate hook counts a bucket's parameters down and, when
-the last one has its gradient, queues ``all_reduce(AVG)`` for the whole bucket on a communication
-stream, so the exchange of one trunk overlaps the backward kernels of the next.
-``wait()`` joins the communication stream before the optimizer step.
+(torchrun), replicated weights, contiguous batch shards.
+
+Gradients are grouped into a few buckets (here: fusion head + sensor branch, motion trunk, joint
+trunk). ``zero_grad()`` sets ``p.grad = None`` so autograd hands every produced gradient tensor over
+without an accumulate kernel; a post-accumulate hook counts a bucket's parameters down and, when the
+last one has its gradient, packs the bucket into its flat buffer (one multi-tensor copy), re-points
+``p.grad`` at views of that buffer and queues ``all_reduce(AVG)`` on a communication stream, so the
+exchange of one trunk overlaps the backward kernels of the next. ``wait()`` flushes buckets that never
+filled up (parameters without a gradient) and joins the communication stream before the optimizer
+step. With a single rank nothing is copied or exchanged at all.
 
 BatchNorm statistics are per shard (each rank normalises over its own clips), i.e. DP parity is
 "every shard matches the single-device result on that shard, gradients are the mean of the shard
@@ -26,40 +31,52 @@ class GradBuckets:
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.buckets = []
-        self._pending = []
-        self._handles = []
         self._comm_stream = None
         self._comm_used = False  # anything queued on the comm stream since the last wait()
+        self._handles = []
         for params in groups:
             params = [p for p in params if p.requires_grad]
             if not params:
                 continue
-            total = sum(p.numel() for p in params)
-            flat = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
-            off = 0
-            for p in params:
-                p.grad = flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
+            b = {"params": params, "pending": len(params), "launched": False, "flat": None, "views": None}
+            if self.world > 1:
+                total = sum(p.numel() for p in params)
+                b["flat"] = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
+                off, views = 0, []
+                for p in params:
+                    views.append(b["flat"][off:off + p.numel()].view_as(p))
+                    off += p.numel()
+                b["views"] = views
             idx = len(self.buckets)
-            self.buckets.append({"flat": flat, "params": params, "n": len(params)})
-            self._pending.append(len(params))
+            self.buckets.append(b)
             for p in params:
                 p.register_post_accumulate_grad_hook(self._make_hook(idx))
-        dev = self.buckets[0]["flat"].device if self.buckets else torch.device("cpu")
-        if dev.type == "cuda":
+        dev = self.buckets[0]["params"][0].device if self.buckets else torch.device("cpu")
+        if dev.type == "cuda" and self.world > 1:
             self._comm_stream = torch.cuda.Stream(device=dev)
 
     def _make_hook(self, idx):
         def hook(param):
-            self._pending[idx] -= 1
-            if self._pending[idx] == 0:
-                self._launch(idx)
+            b = self.buckets[idx]
+            b["pending"] -= 1
+            if b["pending"] == 0:
+                self._launch(b)
         return hook
 
-    def _launch(self, idx):
-        flat = self.buckets[idx]["flat"]
-        if self.world == 1:
+    def _launch(self, b):
+        if self.world == 1 or b["launched"]:
             return
+        b["launched"] = True
+        have = [(v, p.grad) for v, p in zip(b["views"], b["params"]) if p.grad is not None]
+        missing = [v for v, p in zip(b["views"], b["params"]) if p.grad is None]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for v in missing:
+            v.zero_()
+        for v, p in zip(b["views"], b["params"]):
+            if p.grad is not None:
+                p.grad = v
+        flat = b["flat"]
         op = dist.ReduceOp.AVG if (self.average and flat.is_cuda) else dist.ReduceOp.SUM
         if self._comm_stream is not None:
             self._comm_stream.wait_stream(torch.cuda.current_stream(flat.device))
@@ -72,16 +89,18 @@ class GradBuckets:
                 flat.div_(self.world)
 
     def zero_grad(self):
-        """Call instead of ``model.zero_grad()`` (keeps ``p.grad`` pointing into the buckets)."""
-        for i, b in enumerate(self.buckets):
-            b["flat"].zero_()
-            self._pending[i] = b["n"]
+        """Call instead of ``model.zero_grad()``: gradients become None (no zero-fill, no accumulate kernels)."""
+        for b in self.buckets:
+            b["pending"] = len(b["params"])
+            b["launched"] = False
             for p in b["params"]:
-                if p.grad is None or p.grad.data_ptr() < b["flat"].data_ptr():
-                    raise RuntimeError("p.grad was detached from its bucket (use GradBuckets.zero_grad)")
+                p.grad = None
 
     def wait(self):
-        """Join the gradient exchange before the optimizer step."""
+        """Flush incomplete buckets and join the gradient exchange before the optimizer step."""
+        for b in self.buckets:
+            if not b["launched"]:
+                self._launch(b)
         for h in self._handles:
             h.wait()
         self._handles.clear()

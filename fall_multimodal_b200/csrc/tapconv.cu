@@ -45,6 +45,7 @@ struct TapConvParams {
   int BN, ntiles_n, nchunks;
   int ncols, ngroups, ntchunks, total_tiles;
   int nslots, nbstages;
+  int tps;       // taps per streamed weight stage (one barrier round trip per `tps` taps)
   int resident;  // 1: every weight image of the launch stays in shared memory for the CTA's lifetime
   unsigned* err;
 };
@@ -66,7 +67,8 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
   const uint32_t part_bytes_b = static_cast<uint32_t>(p.BN) * 128u;
   const uint32_t slots0 = smem_base;
   const uint32_t bst0 = slots0 + p.nslots * slot_bytes;
-  const uint32_t bars0 = bst0 + p.nbstages * bstage_bytes;
+  const uint32_t bring_bytes = bstage_bytes * static_cast<uint32_t>(p.tps);  // one ring stage = tps images
+  const uint32_t bars0 = bst0 + p.nbstages * bring_bytes;
   // barrier map (8 bytes each)
   auto win_full = [&](int s) { return bars0 + 8u * s; };
   auto win_empty = [&](int s) { return bars0 + 8u * (p.nslots + s); };
@@ -340,11 +342,12 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const int ntile = tile % p.ntiles_n;
         for (int c = 0; c < p.nchunks; ++c) {
-          for (int m = 0; m < p.ntaps; ++m) {
+          for (int m = 0; m < p.ntaps; m += p.tps) {
+            const uint32_t ntp = static_cast<uint32_t>(p.ntaps - m < p.tps ? p.ntaps - m : p.tps);
             mbar_wait(b_empty(bs), bph ^ 1u, p.err, 3);
-            mbar_arrive_expect_tx(b_full(bs), bstage_bytes);
+            mbar_arrive_expect_tx(b_full(bs), ntp * bstage_bytes);
             const size_t off = ((static_cast<size_t>(ntile) * p.nchunks + c) * p.ntaps + m) * bstage_bytes;
-            bulk_g2s(bst0 + bs * bstage_bytes, W + off, bstage_bytes, b_full(bs));
+            bulk_g2s(bst0 + bs * bring_bytes, W + off, ntp * bstage_bytes, b_full(bs));
             if (++bs == p.nbstages) {
               bs = 0;
               bph ^= 1u;
@@ -367,6 +370,49 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       int slot = 0, bs = 0, as = 0;
       uint32_t wph = 0, bph = 0, aph = 0;
       if (p.resident && first_tile < p.total_tiles) mbar_wait(b_full(0), 0, p.err, 6);
+      if (p.resident && kParts == 1) {
+        // Resident weights: nothing to wait for between taps, so ALL MMAs of a (tile, chunk) item are
+        // issued back to back from one elected lane (2 adds per MMA); narrow tiles are otherwise bound
+        // by the issue loop, not by the tensor pipe.
+        uint32_t tap_lo[9];
+#pragma unroll
+        for (int m = 0; m < 9; ++m) tap_lo[m] = static_cast<uint32_t>(p.shift[m] - p.minshift) * 64u;  // atoms, 16-byte units
+        const uint32_t img_lo = bstage_bytes >> 4;
+        for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+          const int ntile = tile % p.ntiles_n;
+          mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * acc_stride;
+          for (int c = 0; c < p.nchunks; ++c) {
+            mbar_wait(win_full(slot), wph, p.err, 5);
+            tc_fence_after();
+            const uint32_t a_lo0 = desc_lo(slots0 + slot * slot_bytes, 16);
+            const uint32_t b_lo0 = desc_lo(bst0, 16) + static_cast<uint32_t>((ntile * p.nchunks + c) * p.ntaps) * img_lo;
+            if (elect_one()) {
+#pragma unroll
+              for (int m = 0; m < 9; ++m) {
+                if (m < p.ntaps) {
+#pragma unroll
+                  for (uint32_t kk = 0; kk < 4; ++kk)
+                    umma_bf16_lh(d_tmem, a_lo0 + tap_lo[m] + kk * 2u, a_hi, b_lo0 + m * img_lo + kk * 2u, b_hi, idesc,
+                                 static_cast<uint32_t>(c) | static_cast<uint32_t>(m) | kk);
+                }
+              }
+              umma_commit(win_empty(slot));
+              if (c == p.nchunks - 1) umma_commit(acc_full(as));
+            }
+            __syncwarp();
+            if (++slot == p.nslots) {
+              slot = 0;
+              wph ^= 1u;
+            }
+          }
+          if (++as == 2) {
+            as = 0;
+            aph ^= 1u;
+          }
+        }
+      } else
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const int ntile = tile % p.ntiles_n;
         mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
@@ -376,35 +422,40 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(win_full(slot), wph, p.err, 5);
           const uint32_t a_slot = slots0 + slot * slot_bytes;
-          for (int m = 0; m < p.ntaps; ++m) {
+          for (int m0 = 0; m0 < p.ntaps; m0 += p.tps) {
+            const int ntp = p.ntaps - m0 < p.tps ? p.ntaps - m0 : p.tps;
             if (!p.resident) mbar_wait(b_full(bs), bph, p.err, 6);
             tc_fence_after();
-            const uint32_t a_lo = desc_lo(a_slot + static_cast<uint32_t>(p.shift[m] - p.minshift) * 1024u, 16);
-            const uint32_t b_img = p.resident ? static_cast<uint32_t>((ntile * p.nchunks + c) * p.ntaps + m) : static_cast<uint32_t>(bs);
-            const uint32_t b_lo = desc_lo(bst0 + b_img * bstage_bytes, 16);
+            const uint32_t b_img = p.resident ? static_cast<uint32_t>((ntile * p.nchunks + c) * p.ntaps + m0) : 0u;
+            const uint32_t b_lo0 = desc_lo(p.resident ? bst0 + b_img * bstage_bytes : bst0 + bs * bring_bytes, 16);
+            const bool last = m0 + ntp == p.ntaps;
             if (elect_one()) {
+              for (int mm = 0; mm < ntp; ++mm) {
+                const uint32_t a_lo = desc_lo(a_slot + static_cast<uint32_t>(p.shift[m0 + mm] - p.minshift) * 1024u, 16);
+                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(mm) * (bstage_bytes >> 4);
 #pragma unroll
-              for (uint32_t kk = 0; kk < 4; ++kk) {
-                if (kParts == 1) {
-                  umma_bf16_lh(d_tmem, a_lo + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | kk);
-                } else {
-                  // (a0+a1+a2)(b0+b1+b2) ~ a0b0 + [a0b1 + a1b0 + a1b1 + a0b2 + a2b0] (rel. err ~2^-24)
-                  const uint32_t pa[5] = {2, 0, 1, 1, 0};
-                  const uint32_t pb[5] = {0, 2, 1, 0, 1};
+                for (uint32_t kk = 0; kk < 4; ++kk) {
+                  if (kParts == 1) {
+                    umma_bf16_lh(d_tmem, a_lo + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | static_cast<uint32_t>(mm) | kk);
+                  } else {
+                    // (a0+a1+a2)(b0+b1+b2) ~ a0b0 + [a0b1 + a1b0 + a1b1 + a0b2 + a2b0] (rel. err ~2^-24)
+                    const uint32_t pa[5] = {2, 0, 1, 1, 0};
+                    const uint32_t pb[5] = {0, 2, 1, 0, 1};
 #pragma unroll
-                  for (int e = 0; e < 5; ++e)
-                    umma_bf16_lh(d_tmem + p.BN, a_lo + pa[e] * pa_lo + kk * 2u, a_hi, b_lo + pb[e] * pb_lo + kk * 2u, b_hi,
-                                 idesc, accum | kk | static_cast<uint32_t>(e));
-                  umma_bf16_lh(d_tmem, a_lo + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | kk);
+                    for (int e = 0; e < 5; ++e)
+                      umma_bf16_lh(d_tmem + p.BN, a_lo + pa[e] * pa_lo + kk * 2u, a_hi, b_lo + pb[e] * pb_lo + kk * 2u, b_hi,
+                                   idesc, accum | static_cast<uint32_t>(mm) | kk | static_cast<uint32_t>(e));
+                    umma_bf16_lh(d_tmem, a_lo + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | static_cast<uint32_t>(mm) | kk);
+                  }
                 }
               }
               if (!p.resident) umma_commit(b_empty(bs));
-              if (m == p.ntaps - 1) umma_commit(win_empty(slot));
-              if (m == p.ntaps - 1 && c == p.nchunks - 1) umma_commit(acc_full(as));
+              if (last) umma_commit(win_empty(slot));
+              if (last && c == p.nchunks - 1) umma_commit(acc_full(as));
             }
             __syncwarp();
             accum = 1;
-            if (++bs == p.nbstages) {
+            if (!p.resident && ++bs == p.nbstages) {
               bs = 0;
               bph ^= 1u;
             }
@@ -598,23 +649,29 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   const int nimg = p.ntiles_n * p.nchunks * ntaps;
   int nb, ns;
   p.resident = (nimg <= 96 && nimg * bstage_bytes + 3 * slot_bytes <= budget) ? 1 : 0;
+  p.tps = 1;
   if (p.resident) {
     nb = nimg;
     ns = static_cast<int>((budget - nb * bstage_bytes) / slot_bytes);
     if (ns > 8) ns = 8;  // more window slots = more cp.async bytes in flight (the 1x1 GEMMs are streaming kernels)
   } else {
+    // several taps per ring stage (<= 48 KB) when the images are small: one barrier round trip per stage
+    if (nparts == 1) {
+      p.tps = static_cast<int>((48 * 1024) / bstage_bytes);
+      if (p.tps > ntaps) p.tps = ntaps;
+      if (p.tps < 1) p.tps = 1;
+    }
+    const size_t ring = bstage_bytes * p.tps;
     ns = 4;
-    while (ns > 1 && 2 * bstage_bytes + ns * slot_bytes > budget) --ns;
-    nb = static_cast<int>((budget - ns * slot_bytes) / bstage_bytes);
-    if (nb > 12) nb = 12;
-    FMM_CHECK_ARG(nb >= 2 || (nb >= 1 && ns >= 1 && nb * bstage_bytes + ns * slot_bytes <= budget),
-                  "tapconv: tile does not fit shared memory (win_atoms=%d BN=%d parts=%d)", p.win_atoms, p.BN, nparts);
+    while (ns > 1 && 2 * ring + ns * slot_bytes > budget) --ns;
+    nb = static_cast<int>((budget - ns * slot_bytes) / ring);
+    if (nb > 8) nb = 8;
   }
-  FMM_CHECK_ARG(nb >= 1 && ns >= 1 && nb * bstage_bytes + ns * slot_bytes <= budget,
+  FMM_CHECK_ARG(nb >= 1 && ns >= 1 && nb * bstage_bytes * p.tps + ns * slot_bytes <= budget,
                 "tapconv: tile does not fit shared memory (win_atoms=%d BN=%d parts=%d)", p.win_atoms, p.BN, nparts);
   p.nslots = ns;
   p.nbstages = nb;
-  const size_t smem = nb * bstage_bytes + ns * slot_bytes + 1024 + 2048;
+  const size_t smem = nb * bstage_bytes * p.tps + ns * slot_bytes + 1024 + 2048;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   const bool wide = p.BN >= 128;
 #define FMM_LAUNCH_TAPCONV(TT, EPI)                                                                              \

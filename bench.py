@@ -288,8 +288,16 @@ def run_ours(args):
             kind = max(tot, key=lambda k: tot[k][1])
             fl, sec, cnt = tot[kind]
             ach = fl / sec / 1e12
+            traffic = None
+            try:  # DRAM bytes per launch of the same kernel from the committed ncu capture of one step
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")))[kind][
+                    "avg_dram_bytes_per_launch"]
+            except (OSError, KeyError, ValueError):
+                pass
             roof = {"bound": "tensor", "kernel": f"{kind}_kernel<bf16> ({cnt} launches in the timed region)",
-                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                    "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_gemm_dram_traffic.json)",
+                    "flops_per_launch": fl / cnt,
                     "peak_source": peak_src, "share_of_step": sec / prof_steps / (ms / args.steps / 1e3),
                     "timed_on": "eager steps next to the graph-replayed timed region" if args.graph else "the timed region",
                     "by_kernel": {k: {"tflops": v[0] / v[1] / 1e12,

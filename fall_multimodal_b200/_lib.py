@@ -97,6 +97,7 @@ _SIGNATURES = {
     "fmm_agg_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_dcoef": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_colstats": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_affine_relu": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_block_out": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_blockout_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_bn2_bwd_apply": [_P] * 15 + [c_int, c_int, c_int, c_int, c_int, c_int, _P],

@@ -316,6 +316,34 @@ __global__ void block_out_kernel(const T* __restrict__ U, const float* __restric
   }
 }
 
+// affine_relu: H = relu(a[c]*X + b[c])  (BatchNorm + ReLU of tcn[0..1], stgcan.py:112-113, materialised once per
+// block so that the temporal conv and its weight gradient stream H with plain async copies)
+template <typename T>
+__global__ void affine_relu_kernel(const T* __restrict__ X, const float* __restrict__ a, const float* __restrict__ b,
+                                   T* __restrict__ H, int Tn, int V, int C, int tchunk) {
+  const int n = blockIdx.y;
+  const int r0 = blockIdx.x * tchunk * V;
+  const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
+  const int c8n = C / 8;
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sa[j] = a[c8 * 8 + j];
+    sb[j] = b[c8 * 8 + j];
+  }
+  const size_t base = static_cast<size_t>(n) * Tn * V * C + c8 * 8;
+#pragma unroll 4
+  for (int r = r0 + rl; r < r1; r += RL) {
+    const size_t off = base + static_cast<size_t>(r) * C;
+    float f[8];
+    load8(X + off, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(sa[j], f[j], sb[j]), 0.f);
+    store8(H + off, f);
+  }
+}
+
 // blockout_bwd_reduce: dpre = dY*(Y>0); S1[n,c]=sum dpre; S2[n,c]=sum dpre*U; S3[n,c]=sum dpre*R
 template <typename T>
 __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ U,
@@ -616,6 +644,18 @@ int fmm_block_out(const void* U, const float* k1, const float* k0, const void* r
     block_out_kernel<T><<<grid, rowwalk_threads(C), 0, stream>>>((const T*)U, k1, k0, (const T*)res, ar, br, (T*)Y, Tn, V, C, tchunk);
   })
   FMM_CHECK_LAUNCH("block_out");
+  return FMM_OK;
+}
+
+int fmm_affine_relu(const void* X, const float* a, const float* b, void* H, int N, int Tn, int V, int C, int dtype,
+                    cudaStream_t stream) {
+  FMM_CHECK_ARG(X && a && b && H && C % 8 == 0, "affine_relu: bad args");
+  const int tchunk = pick_tchunk(N, Tn);
+  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  FMM_DISPATCH(dtype, {
+    affine_relu_kernel<T><<<grid, rowwalk_threads(C), 0, stream>>>((const T*)X, a, b, (T*)H, Tn, V, C, tchunk);
+  })
+  FMM_CHECK_LAUNCH("affine_relu");
   return FMM_OK;
 }
 

@@ -63,6 +63,11 @@ class TrunkEngine:
         self.E = len(self._csr_np["fwd_src"])
         self._dev = {}
         self.debug = None  # dev aid: set to a dict to capture backward intermediates per block
+        # Weight gradients are only needed when backward returns: they are queued on a side stream so
+        # they overlap the dgrad -> BatchNorm-backward -> aggregation chain of the same and later blocks.
+        self.materialize_h = True  # bf16: write relu(bn1(G)) once instead of transforming it in two GEMM prologues
+        self.overlap_wgrad = False  # measured: no gain, two persistent GEMM CTAs cannot share an SM
+        self._wstreams = {}
 
     def csr(self, device):
         key = str(device)
@@ -138,8 +143,14 @@ class TrunkEngine:
             Wt = P[pre + "tcn.2.weight"]
             pw_t = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, Cout * 9, 0, 9, 1, list(range(9)), dt)
             U = torch.empty(N, To, V, Cout, dtype=dt, device=dev)
-            ops.tapconv(G, pw_t, U, shifts=list(range(-4, 5)), tj=To, istride=s, in_scale=a1, in_shift=b1,
-                        in_relu=True, bias=P[pre + "tcn.2.bias"])
+            Hm = None
+            if self.materialize_h and dt == torch.bfloat16:
+                # H = relu(bn1(G)) written once: the conv (and later its wgrad) stream it with plain cp.async
+                Hm = ops.affine_relu(G, a1, b1, torch.empty_like(G))
+                ops.tapconv(Hm, pw_t, U, shifts=list(range(-4, 5)), tj=To, istride=s, bias=P[pre + "tcn.2.bias"])
+            else:
+                ops.tapconv(G, pw_t, U, shifts=list(range(-4, 5)), tj=To, istride=s, in_scale=a1, in_shift=b1,
+                            in_relu=True, bias=P[pre + "tcn.2.bias"])
 
             # BN2 statistics (:119) + SE pooling (:64) in one pass over U
             a2, b2, mean2, rstd2 = (torch.empty(Cout, dtype=torch.float32, device=dev) for _ in range(4))
@@ -186,7 +197,7 @@ class TrunkEngine:
             ops.block_out(U, k1, k0, res, ar, br, Y)
 
             if need_grad:
-                b.update(x=x, Xa=Xa, G=G, U=U, R=R, Y=Y, a1=a1, b1=b1, mean1=mean1, rstd1=rstd1, a2=a2, b2=b2,
+                b.update(x=x, Xa=Xa, G=G, H=Hm, U=U, R=R, Y=Y, a1=a1, b1=b1, mean1=mean1, rstd1=rstd1, a2=a2, b2=b2,
                          mean2=mean2, rstd2=rstd2, pool=pool, p=p_, h=h_, s=s_, ah=ah, bh=bh, hmean=hmean,
                          hrstd=hrstd, ar=ar, meanr=meanr, rstdr=rstdr, coef_f=coef_f, colsum=colsum, To=To)
                 sv["blocks"].append(b)
@@ -219,6 +230,22 @@ class TrunkEngine:
         f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
         z32 = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)
         dY = (dfeat / sv["M_last"]).to(dt)[:, None, None, :].expand(N, sv["T_last"], V, 256).contiguous()
+        cur = torch.cuda.current_stream(dev)
+        ws = None
+        if self.overlap_wgrad:
+            key = (str(dev), cur.cuda_stream)
+            if key not in self._wstreams:
+                self._wstreams[key] = torch.cuda.Stream(device=dev)
+            ws = self._wstreams[key]
+        keep = []  # operands of side-stream launches stay referenced until the join below
+
+        def wgrad_async(*args, **kw):
+            if ws is None:
+                return ops.wgrad(*args, **kw)
+            ws.wait_stream(cur)
+            keep.append(args)
+            with torch.cuda.stream(ws):
+                return ops.wgrad(*args, **kw)
 
         for i in reversed(range(len(self.blocks))):
             Cin, Cout, s, reskind = self.blocks[i]
@@ -271,8 +298,11 @@ class TrunkEngine:
             # ---- temporal conv: wgrad + dgrad ----
             Wt = P[pre + "tcn.2.weight"]
             dWt = arena.f32(Cout, Cout, 9, 1)
-            ops.wgrad(G, dU, dWt, shifts=list(range(-4, 5)), istride=s, in_scale=b["a1"], in_shift=b["b1"],
-                      in_relu=True, s_m=1, s_c2=9, s_co=Cout * 9)
+            if b["H"] is not None:
+                wgrad_async(b["H"], dU, dWt, shifts=list(range(-4, 5)), istride=s, s_m=1, s_c2=9, s_co=Cout * 9)
+            else:
+                wgrad_async(G, dU, dWt, shifts=list(range(-4, 5)), istride=s, in_scale=b["a1"], in_shift=b["b1"],
+                            in_relu=True, s_m=1, s_c2=9, s_co=Cout * 9)
             grads[pre + "tcn.2.weight"] = dWt
             dH = torch.empty_like(G)
             if s == 1:
@@ -300,7 +330,7 @@ class TrunkEngine:
             # ---- graph conv: wgrad, bias, dgrad through the weights, edge importance ----
             Wg = P[pre + "gcn.conv.weight"]
             dWg = arena.f32(K * Cout, Cin, 1, 1)
-            ops.wgrad(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
+            wgrad_async(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
             grads[pre + "gcn.conv.weight"] = dWg
             grads[pre + "gcn.conv.bias"] = (b["colsum"] @ Tbl).flatten()
             pw_gT = ops.tapconv_pack(Wg, K * Cin, Cout, Cin, Cout, Cout * Cin, 1, 0, Cin, 0, [0], dt)
@@ -318,7 +348,7 @@ class TrunkEngine:
             elif reskind == "conv":
                 Wr = P[pre + "residual.0.weight"]
                 dWr = arena.f32(Cout, Cin, 1, 1)
-                ops.wgrad(x, dR, dWr, shifts=[0], istride=s, s_m=0, s_c2=1, s_co=Cin)
+                wgrad_async(x, dR, dWr, shifts=[0], istride=s, s_m=0, s_c2=1, s_co=Cin)
                 grads[pre + "residual.0.weight"] = dWr
                 grads[pre + "residual.0.bias"] = sum_dR.view(NR, Cout).sum(0).float()
                 grads[pre + "residual.1.weight"], grads[pre + "residual.1.bias"] = dgr, dbr
@@ -342,6 +372,9 @@ class TrunkEngine:
                                      c3=c3, T1=T1, T2=T2, saved=b)
             dY = dx
 
+        if ws is not None:
+            cur.wait_stream(ws)
+            keep.clear()
         # ---- data_bn backward (input itself needs no gradient) ----
         xp, mean0, rstd0 = sv["data_bn"]
         dxf = dY.float()

@@ -169,6 +169,14 @@ def colstats(x, ch_sum=None, ch_sq=None, nc_sum=None):
                                   L.dt_of(x.dtype), L.stream()), "colstats")
 
 
+def affine_relu(X, a, b, H):
+    N, Tn, V, C = _shape4(X)
+    assert X.is_contiguous() and H.shape == X.shape
+    L.check(L.load().fmm_affine_relu(L.ptr(X), L.ptr(a), L.ptr(b), L.ptr(H), N, Tn, V, C, L.dt_of(X.dtype), L.stream()),
+            "affine_relu")
+    return H
+
+
 def block_out(U, k1, k0, res, ar, br, Y):
     N, Tn, V, C = _shape4(U)
     L.check(L.load().fmm_block_out(L.ptr(U), L.ptr(k1), L.ptr(k0), L.ptr(res), L.ptr(ar), L.ptr(br), L.ptr(Y),

@@ -90,6 +90,9 @@ int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, in
 /* Y = relu(k1[n,c]*U + k0[n,c] + res): BN2 + SE scale + residual + ReLU of st_gcan.forward (stgcan.py:138-144) */
 int fmm_block_out(const void* U, const float* k1, const float* k0, const void* res, const float* ar, const float* br,
                   void* Y, int N, int T, int V, int C, int dtype, cudaStream_t stream);
+/* H = relu(a[c]*X + b[c]): BatchNorm2d + ReLU of tcn[0..1] (stgcan.py:112-113), materialised once per block */
+int fmm_affine_relu(const void* X, const float* a, const float* b, void* H, int N, int T, int V, int C, int dtype,
+                    cudaStream_t stream);
 int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const void* R, float* S1, float* S2,
                             float* S3, int N, int T, int V, int C, int dtype, cudaStream_t stream);
 int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* R, const float* k1, const float* k2,

@@ -45,6 +45,7 @@ struct TapConvParams {
   int BN, ntiles_n, nchunks;
   int ncols, ngroups, ntchunks, total_tiles;
   int nslots, nbstages;
+  int MT;        // M=128 tiles per pipeline item (2: 32 positions x 8 columns share one window and every weight image)
   int tps;       // taps per streamed weight stage (one barrier round trip per `tps` taps)
   int resident;  // 1: every weight image of the launch stays in shared memory for the CTA's lifetime
   unsigned* err;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
   // fp32 mode: the dominant hi*hi products and the five small correction terms accumulate in
   // SEPARATE TMEM tiles (summed in the epilogue). The tensor core truncates its fp32 accumulator on
   // every MMA; keeping the small terms out of the big accumulator cuts those truncations 6x.
-  const uint32_t acc_stride = (kParts == 1 ? 1u : 2u) * static_cast<uint32_t>(p.BN);
+  const uint32_t acc_stride = (kParts == 1 ? 1u : 2u) * static_cast<uint32_t>(p.BN) * static_cast<uint32_t>(p.MT);
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * acc_stride) tmem_cols <<= 1;
 
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         i_colok = col < p.ncols;
         const int n = i_colok ? col / p.V : 0;
         const int v = i_colok ? col - n * p.V : 0;
-        i_tlo = tchunk * 16 * p.istride + p.minshift;
+        i_tlo = tchunk * 16 * p.MT * p.istride + p.minshift;
         i_colp = Xb + static_cast<size_t>(n) * p.Tin * pitch_t + static_cast<size_t>(v) * p.Cin;
       };
       if (i_tile < p.total_tiles) decode_tile();
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         const int tchunk = rest % p.ntchunks;
         const int group = rest / p.ntchunks;
         const int col = group * 8 + q;
-        const int t_lo = tchunk * 16 * p.istride + p.minshift;
+        const int t_lo = tchunk * 16 * p.MT * p.istride + p.minshift;
         for (int c = 0; c < p.nchunks; ++c) {
           // finish item (tile, c) FIRST and only then queue the copies of item +D: queueing needs the
           // slot the MMAs of the previous item are still reading, and waiting for it before the
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       const bool col_ok = col < p.ncols;
       const int n = col_ok ? col / p.V : 0;
       const int v = col_ok ? col % p.V : 0;
-      const int t_lo = tchunk * 16 * p.istride + p.minshift;
+      const int t_lo = tchunk * 16 * p.MT * p.istride + p.minshift;
       const T* colp = X + static_cast<size_t>(n) * p.Tin * pitch_t + static_cast<size_t>(v) * p.Cin;
       for (int c = 0; c < p.nchunks; ++c) {
         const int cb = c * 64 + pc * 8;
@@ -256,15 +257,18 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       const int tchunk = rest % p.ntchunks;
       const int group = rest / p.ntchunks;
       const int col = group * 8 + q;
-      const int j = tchunk * 16 + (r >> 3);
-      const bool row_ok = (col < p.ncols) && (j < p.Tj);
-      const int n = row_ok ? col / p.V : 0;
-      const int v = row_ok ? col % p.V : 0;
-      T* orow = O + (static_cast<size_t>(n) * p.Tout + (j * p.ostride + p.ooff)) * p.V * p.Cout +
-                static_cast<size_t>(v) * p.Cout;
+      const bool col_ok = col < p.ncols;
+      const int n = col_ok ? col / p.V : 0;
+      const int v = col_ok ? col % p.V : 0;
       mbar_wait(acc_full(as), aph, p.err, 2);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as) * acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int mt = 0; mt < p.MT; ++mt) {
+      const int j = (tchunk * p.MT + mt) * 16 + (r >> 3);
+      const bool row_ok = col_ok && (j < p.Tj);
+      T* orow = O + (static_cast<size_t>(n) * p.Tout + (row_ok ? j * p.ostride + p.ooff : 0)) * p.V * p.Cout +
+                static_cast<size_t>(v) * p.Cout;
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as) * acc_stride + static_cast<uint32_t>(mt) * (acc_stride / p.MT) +
+                             (static_cast<uint32_t>(quad * 32) << 16);
       for (int cg = half; cg < p.BN / 32; cg += kEpi / 4) {
         uint32_t acc[32];
         tmem_ld32(taddr + cg * 32, acc);
@@ -317,6 +321,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
             }
           }
         }
+      }
       }
       tc_fence_before();
       mbar_arrive(acc_empty(as));
@@ -378,6 +383,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
 #pragma unroll
         for (int m = 0; m < 9; ++m) tap_lo[m] = static_cast<uint32_t>(p.shift[m] - p.minshift) * 64u;  // atoms, 16-byte units
         const uint32_t img_lo = bstage_bytes >> 4;
+        const uint32_t mt_lo = 16u * static_cast<uint32_t>(p.istride) * 64u;  // second M tile: 16 positions later
         for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
           const int ntile = tile % p.ntiles_n;
           mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
@@ -392,10 +398,13 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
 #pragma unroll
               for (int m = 0; m < 9; ++m) {
                 if (m < p.ntaps) {
+                  for (uint32_t mt = 0; mt < static_cast<uint32_t>(p.MT); ++mt) {
 #pragma unroll
-                  for (uint32_t kk = 0; kk < 4; ++kk)
-                    umma_bf16_lh(d_tmem, a_lo0 + tap_lo[m] + kk * 2u, a_hi, b_lo0 + m * img_lo + kk * 2u, b_hi, idesc,
-                                 static_cast<uint32_t>(c) | static_cast<uint32_t>(m) | kk);
+                    for (uint32_t kk = 0; kk < 4; ++kk)
+                      umma_bf16_lh(d_tmem + mt * p.BN, a_lo0 + tap_lo[m] + mt * mt_lo + kk * 2u, a_hi,
+                                   b_lo0 + m * img_lo + kk * 2u, b_hi, idesc,
+                                   static_cast<uint32_t>(c) | static_cast<uint32_t>(m) | kk);
+                  }
                 }
               }
               umma_commit(win_empty(slot));
@@ -433,11 +442,16 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
               for (int mm = 0; mm < ntp; ++mm) {
                 const uint32_t a_lo = desc_lo(a_slot + static_cast<uint32_t>(p.shift[m0 + mm] - p.minshift) * 1024u, 16);
                 const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(mm) * (bstage_bytes >> 4);
+                if (kParts == 1) {
+                  for (uint32_t mt = 0; mt < static_cast<uint32_t>(p.MT); ++mt) {
+                    const uint32_t a_mt = a_lo + mt * a_sbo, d_mt = d_tmem + mt * p.BN;  // 16 positions = 16*a_sbo bytes = a_sbo 16-byte units
 #pragma unroll
-                for (uint32_t kk = 0; kk < 4; ++kk) {
-                  if (kParts == 1) {
-                    umma_bf16_lh(d_tmem, a_lo + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | static_cast<uint32_t>(mm) | kk);
-                  } else {
+                    for (uint32_t kk = 0; kk < 4; ++kk)
+                      umma_bf16_lh(d_mt, a_mt + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | static_cast<uint32_t>(mm) | kk);
+                  }
+                } else {
+#pragma unroll
+                  for (uint32_t kk = 0; kk < 4; ++kk) {
                     // (a0+a1+a2)(b0+b1+b2) ~ a0b0 + [a0b1 + a1b0 + a1b1 + a0b2 + a2b0] (rel. err ~2^-24)
                     const uint32_t pa[5] = {2, 0, 1, 1, 0};
                     const uint32_t pb[5] = {0, 2, 1, 0, 1};
@@ -631,13 +645,16 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
     }
   }
   p.minshift = mn;
-  p.win_atoms = 15 * istride + (mx - mn) + 1;
+  // two M tiles per item when the accumulators fit (2 stages x 2 tiles x BN columns) and the window stays small
+  const int bn_probe = pick_bn(Cout, dtype);
+  p.MT = (dtype == FMM_DT_BF16 && istride == 1 && bn_probe <= 128 && Tj > 16) ? 2 : 1;
+  p.win_atoms = (16 * p.MT - 1) * istride + (mx - mn) + 1;
   p.BN = pick_bn(Cout, dtype);
   p.ntiles_n = ((Cout + 31) / 32 * 32 + p.BN - 1) / p.BN;
   p.nchunks = (Cin + 63) / 64;
   p.ncols = N * V;
   p.ngroups = (p.ncols + 7) / 8;
-  p.ntchunks = (Tj + 15) / 16;
+  p.ntchunks = (Tj + 16 * p.MT - 1) / (16 * p.MT);
   p.total_tiles = p.ngroups * p.ntchunks * p.ntiles_n;
   p.err = err;
   const int nparts = dtype == FMM_DT_F32 ? 3 : 1;

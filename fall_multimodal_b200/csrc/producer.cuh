@@ -136,15 +136,33 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
   }
 }
 
-// issue the copies of atoms a0, a0+astep, ... of one chunk (zero fill outside [0,Tn) / invalid column)
+// issue the copies of atoms a0, a0+astep, ... of one chunk (zero fill outside [0,Tn) / invalid column).
+// The producer warps are instruction bound (one LDGSTS moves only 16 bytes per lane), so the common
+// case - the whole window inside the clip - runs without per-copy predicates or address multiplies.
 __device__ __forceinline__ void cpasync_issue_chunk(const __nv_bfloat16* __restrict__ col_base, size_t pitch_t,
                                                     bool col_ok, int Tn, int t_lo, int natoms, int a0, int astep,
                                                     uint32_t sdst) {
-  for (int a = a0; a < natoms; a += astep) {
-    const int ti = t_lo + a;
-    const bool ok = col_ok && ti >= 0 && ti < Tn;
-    const __nv_bfloat16* src = ok ? col_base + static_cast<size_t>(ti) * pitch_t : col_base;
-    cp_async16(sdst + static_cast<uint32_t>(a) * 1024u, src, ok ? 16u : 0u);
+  const int n_it = (natoms - a0 + astep - 1) / astep;
+  uint32_t dst = sdst + static_cast<uint32_t>(a0) * 1024u;
+  const uint32_t dstep = static_cast<uint32_t>(astep) * 1024u;
+  if (col_ok && t_lo >= 0 && t_lo + natoms <= Tn) {
+    const __nv_bfloat16* src = col_base + static_cast<size_t>(t_lo + a0) * pitch_t;
+    const size_t sstep = static_cast<size_t>(astep) * pitch_t;
+#pragma unroll 4
+    for (int i = 0; i < n_it; ++i) {
+      cp_async16(dst, src, 16u);
+      src += sstep;
+      dst += dstep;
+    }
+  } else {
+    int ti = t_lo + a0;
+    for (int i = 0; i < n_it; ++i) {
+      const bool ok = col_ok && ti >= 0 && ti < Tn;
+      const __nv_bfloat16* src = ok ? col_base + static_cast<size_t>(ti) * pitch_t : col_base;
+      cp_async16(dst, src, ok ? 16u : 0u);
+      ti += astep;
+      dst += dstep;
+    }
   }
 }
 

@@ -185,3 +185,22 @@ class BiLSTM(nn.Module):
             att = self.channelattention.attention
             out = out * att(out)                                                  # bilstm.py:16-19
             return self.fc(out)                                                   # bilstm.py:58
+
+
+class CNN_BiLSTM(nn.Module):
+    """Notebook sensor branch ``CNN_BiLSTM(hidden_size, num_layers, dropout_prob, num_classes, feature)``
+    (GSTCAN_HAR_conv_10kfold.ipynb#cell2:L85-100): CNN1D feature map (N,32,L//4) fed as a length-L//4
+    sequence of 32-d vectors to ``BiLSTM(32, 64, 1, 0.3, 11, 'mean')``. Like the reference, the constructor
+    arguments other than ``num_classes`` / ``feature`` are ignored in favour of those constants; submodule
+    names ``cnn`` / ``bilstm`` give the reference's state_dict keys. ``forward(x)`` takes ``(N, L, Cin)``."""
+
+    def __init__(self, hidden_size=64, num_layers=1, dropout_prob=0.3, num_classes=11, feature="mean",
+                 in_channels: int = 15, seq_len: int = 30):
+        super().__init__()
+        self.cnn = CNN1D(in_channels, seq_len)
+        self.bilstm = BiLSTM(input_size=32, hidden_size=64, num_layers=1, dropout_prob=0.3, num_classes=num_classes,
+                             feature=feature)
+
+    def forward(self, x):
+        feat = self.cnn.forward_channels_last(x)       # (N, L//4, 32): already the (batch, seq, feature) the LSTM wants
+        return self.bilstm(None, feat)

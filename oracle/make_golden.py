@@ -150,5 +150,50 @@ def main():
     print("fusion loss", res["loss"])
 
 
+def main_tragcn():
+    """TRAGCN family fixtures from the unmodified root-level reference files."""
+    import warnings
+    from oracle import tragcn_oracle as TO
+    torch.set_num_threads(4)
+    cases = [
+        ("targcn_v25_t12", dict(V=25, T=12, B=4, adj=None, fill_seed=5, batch_seed=11)),
+        ("targcn_v14_t30_adj", dict(V=14, T=30, B=3, adj="rand", fill_seed=6, batch_seed=12)),
+    ]
+    for name, c in cases:
+        adj = None
+        if c["adj"] == "rand":
+            g = torch.Generator().manual_seed(77)
+            a = (torch.rand(c["V"], c["V"], generator=g) < 0.3).float() * torch.rand(c["V"], c["V"], generator=g)
+            adj = ((a + a.t()) * 0.5).contiguous()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            M = ref_import.load_tragcn(c["T"])
+            mod = M.TARGCN(num_nodes=c["V"], adj=adj)
+        sd = mod.state_dict()
+        shapes = {k: tuple(v.shape) for k, v in sd.items()}
+        assert shapes == TO.targcn_param_shapes(V=c["V"], T=c["T"]), "oracle shape table drifted from the reference"
+        filled = TO.fill_targcn(shapes, c["fill_seed"])
+        assert torch.allclose(filled["encoder.trans_layer_T.PE.pe"], sd["encoder.trans_layer_T.PE.pe"].cpu())
+        mod.load_state_dict(filled)
+        x, tgt = TO.synthetic_clips(c["B"], c["T"], c["V"], seed=c["batch_seed"])
+        mod.train()
+        mod.zero_grad()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            logits = mod(x)
+        loss = torch.nn.CrossEntropyLoss()(logits, tgt)
+        loss.backward()
+        grads = {k: summarize(p.grad, k) for k, p in mod.named_parameters() if p.grad is not None}
+        torch.save({"config": {k: v for k, v in c.items() if k != "adj"}, "adj": adj, "shapes": shapes,
+                    "n_params": sum(p.numel() for p in mod.parameters()),
+                    "logits": logits.detach().clone(), "loss": float(loss), "grads": grads},
+                   os.path.join(OUT, name + ".pt"))
+        print(name, "loss", float(loss), "params", sum(p.numel() for p in mod.parameters()))
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["tragcn"]:
+        main_tragcn()
+    else:
+        main()
+        main_tragcn()

@@ -58,3 +58,21 @@ def load_notebook_sensor():
     ns: dict = {}
     exec("".join(nb["cells"][2]["source"]), ns)
     return ns
+
+
+def load_tragcn(seq_len: int):
+    """Root-level TRAGCN family loaded as a synthetic package; ``Transform`` /
+    ``PositionalEncoding`` hard-code 30 frames as a default argument (D5), re-pointed at ``seq_len``."""
+    if "TRAGCN" not in sys.modules:
+        pkg = types.ModuleType("TRAGCN")
+        pkg.__path__ = []
+        sys.modules["TRAGCN"] = pkg
+        for name in ("EmbGCN", "GRU", "TA", "TRAGCN"):
+            spec = importlib.util.spec_from_file_location(f"TRAGCN.{name}", os.path.join(REF, name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[f"TRAGCN.{name}"] = mod
+            spec.loader.exec_module(mod)
+    ta = sys.modules["TRAGCN.TA"]
+    ta.Transform.__init__.__defaults__ = (seq_len,)
+    ta.PositionalEncoding.__init__.__defaults__ = (seq_len,)
+    return sys.modules["TRAGCN.TRAGCN"]

@@ -278,6 +278,12 @@ def cnn1d_forward(sd, x, training=True, update=None):
     return x
 
 
+def cnn_bilstm_forward(sd, x, training=True, feature="mean", update=None):
+    """Notebook CNN_BiLSTM.forward (GSTCAN_HAR_conv_10kfold.ipynb#cell2:L85-100); x is (N, L, Cin)."""
+    feat = cnn1d_forward(_sub(sd, "cnn."), x.permute(0, 2, 1), training, _PrefixDict(update, "cnn."))
+    return bilstm_forward(_sub(sd, "bilstm."), feat.permute(0, 2, 1), training, feature, _PrefixDict(update, "bilstm."))
+
+
 def _sub(sd, prefix):
     return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
 

@@ -149,6 +149,34 @@ def test_bilstm_shapes_against_oracle(N, L, I, feature):
 
 
 @gpu
+def test_cnn_bilstm_matches_oracle():
+    """Notebook CNN_BiLSTM: CNN1D feature map -> BiLSTM(32); 67 195 parameters."""
+    from fall_multimodal_b200 import CNN_BiLSTM
+
+    dev = torch.device("cuda:0")
+    m = CNN_BiLSTM(64, 1, 0.3, 11, "mean")
+    assert sum(p.numel() for p in m.parameters()) == 67195
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = m.state_dict()
+    sd.update(O.fill_state_dict(shapes, 21))
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    _, sensor, target, _ = O.synthetic_batch(24, 4, 14, 11, sensor_len=30, sensor_ch=15, seed=9)
+    osd = {k: (v.detach().cpu().double().clone() if v.is_floating_point() else v.cpu().clone()) for k, v in m.state_dict().items()}
+    for k, v in osd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    oo = O.cnn_bilstm_forward(osd, sensor.double(), training=True)
+    O.soft_ce(oo, target.double()).backward()
+    out = m(sensor.to(dev))
+    torch.nn.CrossEntropyLoss()(out, target.to(dev)).backward()
+    assert (out.double().cpu() - oo).abs().max().item() / oo.abs().max().item() < 1e-4
+    ref = {k: {"full": v.grad} for k, v in osd.items() if v.is_floating_point() and v.grad is not None}
+    worst = check_grads({k: p.grad for k, p in m.named_parameters() if k in ref}, ref, 2e-4)
+    print("cnn_bilstm worst grad err", worst)
+
+
+@gpu
 def test_two_stream_bilstm_matches_reference_fixture():
     """The reference's own fusion class (combination.py:27-46) against its golden outputs."""
     from fall_multimodal_b200 import TwoStreamSTGCAN_BiLSTM

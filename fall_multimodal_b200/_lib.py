@@ -117,8 +117,29 @@ _SIGNATURES = {
     "fmm_conv1d_k5_bwd": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
     "fmm_wgrad": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                   C.POINTER(c_int), c_int, c_ll, c_ll, c_ll, c_ll, c_int, _P, _P],
+    "fmm_bgemm": [_P, _P],
+    "fmm_tg_catmix": [_P, c_ll, c_ll, _P, c_ll, c_ll, _P, c_ll, c_ll, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_tg_gate": [_P, _P, _P, _P, c_int, _P, c_ll, _P, c_ll, c_ll, _P, c_ll, c_ll, c_int, c_int, c_int, c_int, _P],
+    "fmm_tg_cell_bwd1": [_P, _P, c_ll, c_ll, _P, c_ll, _P, c_ll, c_ll, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "fmm_tg_mix_bwd": [_P, _P, _P, _P, _P, c_int, c_int, _P, c_ll, c_ll, c_int, _P, _P, c_ll, c_ll, _P, _P, _P, _P, _P,
+                       c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_tg_softmax_fwd": [_P, c_ll, c_int, c_int, c_int, _P],
+    "fmm_tg_softmax_bwd": [_P, _P, c_ll, c_int, c_int, c_int, _P],
+    "fmm_tg_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, c_ll, c_int, c_float, c_int, _P],
+    "fmm_tg_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P],
+    "fmm_tg_add_pe": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_tg_relu_mask": [_P, _P, c_ll, c_int, _P],
 }
 _RESTYPES = {"fmm_tapconv_packed_bytes": c_ll}
+
+
+class BgemmDesc(C.Structure):
+    """Mirror of ``fmm_bgemm_desc`` (include/fmm_b200.h)."""
+    _fields_ = ([(n, c_void_p) for n in ("A", "B", "C", "bias_m", "bias_n")] +
+                [(n, c_ll) for n in ("a_g1", "a_g2", "a_m", "a_k1", "a_k2", "a_k3", "b_g1", "b_g2", "b_n", "b_k1", "b_k2",
+                                     "b_k3", "c_g1", "c_g2", "c_m", "c_n")] +
+                [(n, c_int) for n in ("G1", "G2", "M", "N", "K1", "K2", "K3")] +
+                [("alpha", c_float), ("beta", c_int), ("act", c_int), ("splitk", c_int), ("dtype", c_int), ("c_dtype", c_int)])
 
 
 def int_array(vals):

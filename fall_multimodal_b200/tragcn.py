@@ -1,0 +1,645 @@
+"""TRAGCN family over the CUDA kernels of csrc/bgemm.cu + csrc/tragcn.cu.
+
+Reference: ``/root/reference/EmbGCN.py:59-89`` (EmbGCN), ``GRU.py:8-29`` (graph GRU cell),
+``TRAGCN.py:130-169`` (AVWDCRNN scan), ``TA.py:22-108`` (Transform / PositionalEncoding /
+transformer_layer), ``TRAGCN.py:177-224`` (TARGCN + head).  Same class names, constructor arguments,
+``forward(source[B,T,V,D])`` and state_dict keys, so reference checkpoints load.
+
+How the work is split:
+  * everything that depends on the batch runs in this library's kernels: the per-time-step concat +
+    adaptive-adjacency mix, the per-node weight products and Linear paths of both EmbGCN gates (one
+    strided batched GEMM per stage, bias folded in as a constant-1 input column), the GRU gate maths,
+    the time-as-channel (1,3) convolutions, QK^T / softmax / PV, LayerNorm, the feed-forward, the head,
+    and hand-written backward passes for all of them (BPTT over the scan; the weight gradients of the
+    scan are ONE batched GEMM over all (t, clip) pairs after the serial sweep);
+  * the batch-INDEPENDENT parameter algebra the reference recomputes in every one of its 2*T cell calls
+    (supports = softmax(relu(E E^T)) + I, the per-node weights E x weights_pool, the head's pooled
+    end_conv weights) is hoisted out of the time loop and evaluated once per step with a handful of torch
+    ops on (V,*)-sized tensors; autograd carries the kernel-produced gradients of those tensors back to
+    the pools and the node embeddings.
+There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _lib as L
+from .stgcan import _compute_dtype
+
+NREP = 16  # replicas of the dS accumulator
+
+
+# ------------------------------------------------------------------------------------------------
+# raw kernel faces
+# ------------------------------------------------------------------------------------------------
+def _addr(t: torch.Tensor, off: int = 0) -> int:
+    return t.data_ptr() + off * t.element_size()
+
+
+def bgemm(A, a_off, a_str, B, b_off, b_str, Cm, c_off, c_str, G, M, N, K, alpha=1.0, beta=0, act=0,
+          bias_m=None, bias_n=None, splitk=1):
+    """C[g1,g2][m][n] = act(alpha * sum_k A B + bias) (+C).  ``a_str`` = (g1,g2,m,k1,k2,k3) element strides,
+    ``b_str`` = (g1,g2,n,k1,k2,k3), ``c_str`` = (g1,g2,m,n); ``K`` = (K1,K2,K3). See csrc/bgemm.cu."""
+    L.require_device(A)
+    assert A.dtype == B.dtype, (A.dtype, B.dtype)
+    d = L.BgemmDesc()
+    d.A, d.B, d.C = _addr(A, a_off), _addr(B, b_off), _addr(Cm, c_off)
+    d.bias_m = bias_m.data_ptr() if bias_m is not None else None
+    d.bias_n = bias_n.data_ptr() if bias_n is not None else None
+    assert bias_m is None or bias_m.dtype == torch.float32
+    assert bias_n is None or bias_n.dtype == torch.float32
+    d.a_g1, d.a_g2, d.a_m, d.a_k1, d.a_k2, d.a_k3 = a_str
+    d.b_g1, d.b_g2, d.b_n, d.b_k1, d.b_k2, d.b_k3 = b_str
+    d.c_g1, d.c_g2, d.c_m, d.c_n = c_str
+    d.G1, d.G2 = G
+    d.M, d.N = M, N
+    d.K1, d.K2, d.K3 = K
+    d.alpha, d.beta, d.act, d.splitk = float(alpha), int(beta), int(act), int(splitk)
+    d.dtype, d.c_dtype = L.dt_of(A.dtype), L.dt_of(Cm.dtype)
+    L.check(L.load().fmm_bgemm(C.byref(d), L.stream()), "bgemm")
+
+
+def _splitk(M, N, G, K):
+    tiles = ((M + 63) // 64) * ((N + 63) // 64) * G
+    ktiles = (K + 31) // 32
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    return int(max(1, min(want, ktiles // 4 if ktiles >= 8 else 1, 65535)))
+
+
+def _dt(t):
+    return L.dt_of(t.dtype)
+
+
+def _sl(t):
+    """(pointer, clip stride, joint stride) of a (B,V,C) slice with unit channel stride (or Nones)."""
+    if t is None:
+        return None, 0, 0
+    assert t.stride(2) == 1
+    return t.data_ptr(), t.stride(0), t.stride(1)
+
+
+def catmix(x, h, r, S, xc0, xc1, Din, H, Cp):
+    B, V = x.shape[0], x.shape[1]
+    xp, xb, xv = _sl(x)
+    hp, hb, hv = _sl(h)
+    rp, rb, rv = _sl(r)
+    L.check(L.load().fmm_tg_catmix(xp, xb, xv, hp, hb, hv, rp, rb, rv, S.data_ptr(), xc0.data_ptr(), xc1.data_ptr(),
+                                   B, V, Din, H, Cp, _dt(x), L.stream()), "tg_catmix")
+
+
+def gate(pre, lin, out, lin_save, mode, z=None, zs=0, hprev=None, hout=None):
+    B, V, Cc = pre.shape
+    hp, hb, hv = _sl(hprev)
+    op, ob, ov = _sl(hout)
+    L.check(L.load().fmm_tg_gate(pre.data_ptr(), lin.data_ptr(), out.data_ptr(), lin_save.data_ptr(), mode,
+                                 z.data_ptr() if z is not None else None, zs, hp, hb, hv, op, ob, ov, B, V, Cc,
+                                 _dt(out), L.stream()), "tg_gate")
+
+
+def cell_bwd1(carry, dH, z, zs, hprev, hc, lu, dz, dpre, dlin):
+    B, V, H = carry.shape
+    dp, db, dv = _sl(dH)
+    hp, hb, hv = _sl(hprev)
+    L.check(L.load().fmm_tg_cell_bwd1(carry.data_ptr(), dp, db, dv, z.data_ptr(), zs, hp, hb, hv, hc.data_ptr(),
+                                      lu.data_ptr(), dz.data_ptr(), dpre.data_ptr(), dlin.data_ptr(), B, V, H, _dt(hc),
+                                      L.stream()), "tg_cell_bwd1")
+
+
+def mix_bwd(dxc0, dxc1, cat, S, dS, mode, dx, dx_accum, carry, hprev, zr, dz, lg, dpre, dlin, Din, H, Cp):
+    B, V = cat.shape[0], cat.shape[1]
+    xp, xb, xv = _sl(dx)
+    hp, hb, hv = _sl(hprev)
+    P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    L.check(L.load().fmm_tg_mix_bwd(dxc0.data_ptr(), dxc1.data_ptr(), cat.data_ptr(), S.data_ptr(), dS.data_ptr(),
+                                    dS.shape[0], mode, xp, xb, xv, int(dx_accum), carry.data_ptr(), hp, hb, hv, P(zr),
+                                    P(dz), P(lg), P(dpre), P(dlin), B, V, Din, H, Cp, _dt(cat), L.stream()), "tg_mix_bwd")
+
+
+# ------------------------------------------------------------------------------------------------
+# graph-GRU scan (GRU.py:17-26 inside TRAGCN.py:158-166)
+# ------------------------------------------------------------------------------------------------
+def _stage_fwd(xc_t, WW, PL, B, V, Cp, Co, g1_stride):
+    """PL[s][b][n][:] = XC[s][t][b][n][:] . WW[s][n]  for both s (graph path, Linear path) and all nodes."""
+    bgemm(xc_t, 0, (g1_stride, Cp, V * Cp, 1, 0, 0), WW, 0, (V * Cp * Co, Cp * Co, 1, Co, 0, 0),
+          PL, 0, (B * V * Co, Co, V * Co, 1), (2, V), B, Co, (Cp, 1, 1))
+
+
+def _stage_dgrad(dPL_t, WW, dXC, B, V, Cp, Co, g1_stride):
+    """dXC[s][b][n][:] = dPL[s][t][b][n][:] . WW[s][n]^T"""
+    bgemm(dPL_t, 0, (g1_stride, Co, V * Co, 1, 0, 0), WW, 0, (V * Cp * Co, Cp * Co, Co, 1, 0, 0),
+          dXC, 0, (B * V * Cp, Cp, V * Cp, 1), (2, V), B, Cp, (Co, 1, 1))
+
+
+class _GraphGRUScan(Function):
+    """One AVWDCRNN layer from the zero state: x (B,T,V,Din) -> all hidden states (B,T,V,H).
+
+    S (V,V) fp32 adaptive supports; WWg (2,V,Cp,2H) / WWu (2,V,Cp,H) fp32: [0] per-node graph weights,
+    [1] column-scaled Linear weights, row Din+H of each = bias (matched by the constant-1 input column)."""
+
+    @staticmethod
+    def forward(ctx, x, S, WWg, WWu):
+        with torch.autocast("cuda", enabled=False):
+            dt = x.dtype
+            B, T, V, Din = x.shape
+            H, Cp = WWu.shape[-1], WWu.shape[2]
+            dev = x.device
+            need = any(ctx.needs_input_grad)
+            S = S.contiguous().float()
+            Wg, Wu = WWg.to(dt).contiguous(), WWu.to(dt).contiguous()
+            Ts = T if need else 1
+            Hout = torch.empty(B, T, V, H, dtype=dt, device=dev)
+            XCg = torch.empty(2, Ts, B, V, Cp, dtype=dt, device=dev)
+            XCu = torch.empty(2, Ts, B, V, Cp, dtype=dt, device=dev)
+            ZR = torch.empty(Ts, B, V, 2 * H, dtype=dt, device=dev)
+            LG = torch.empty(Ts, B, V, 2 * H, dtype=dt, device=dev)
+            HC = torch.empty(Ts, B, V, H, dtype=dt, device=dev)
+            LU = torch.empty(Ts, B, V, H, dtype=dt, device=dev)
+            PLg = torch.empty(2, B, V, 2 * H, dtype=torch.float32, device=dev)
+            PLu = torch.empty(2, B, V, H, dtype=torch.float32, device=dev)
+            g1 = Ts * B * V * Cp
+            for t in range(T):
+                s = t if need else 0
+                hprev = Hout[:, t - 1] if t > 0 else None
+                xt = x[:, t]
+                catmix(xt, hprev, None, S, XCg[0, s], XCg[1, s], Din, H, Cp)
+                _stage_fwd(XCg[:, s], Wg, PLg, B, V, Cp, 2 * H, g1)
+                gate(PLg[0], PLg[1], ZR[s], LG[s], 0)
+                catmix(xt, hprev, ZR[s][..., H:], S, XCu[0, s], XCu[1, s], Din, H, Cp)
+                _stage_fwd(XCu[:, s], Wu, PLu, B, V, Cp, H, g1)
+                gate(PLu[0], PLu[1], HC[s], LU[s], 1, z=ZR[s], zs=2 * H, hprev=hprev, hout=Hout[:, t])
+            if need:
+                ctx.saved = (x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU)
+                ctx.need_dx = ctx.needs_input_grad[0]
+        return Hout
+
+    @staticmethod
+    def backward(ctx, dH):
+        x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU = ctx.saved
+        ctx.saved = None
+        with torch.autocast("cuda", enabled=False):
+            dt = x.dtype
+            B, T, V, Din = x.shape
+            H, Cp = Wu.shape[-1], Wu.shape[2]
+            dev = x.device
+            dH = dH.to(dt).contiguous()
+            carry = torch.zeros(B, V, H, dtype=torch.float32, device=dev)
+            DZ = torch.empty(B, V, H, dtype=torch.float32, device=dev)
+            dPLg = torch.empty(2, T, B, V, 2 * H, dtype=dt, device=dev)
+            dPLu = torch.empty(2, T, B, V, H, dtype=dt, device=dev)
+            dXC = torch.empty(2, B, V, Cp, dtype=torch.float32, device=dev)
+            dS = torch.zeros(NREP, V, V, dtype=torch.float32, device=dev)
+            dX = torch.empty(B, T, V, Din, dtype=dt, device=dev) if ctx.need_dx else None
+            for t in range(T - 1, -1, -1):
+                hprev = Hout[:, t - 1] if t > 0 else None
+                dxt = dX[:, t] if dX is not None else None
+                cell_bwd1(carry, dH[:, t], ZR[t], 2 * H, hprev, HC[t], LU[t], DZ, dPLu[0, t], dPLu[1, t])
+                _stage_dgrad(dPLu[:, t], Wu, dXC, B, V, Cp, H, T * B * V * H)
+                mix_bwd(dXC[0], dXC[1], XCu[1, t], S, dS, 1, dxt, False, carry, hprev, ZR[t], DZ, LG[t], dPLg[0, t],
+                        dPLg[1, t], Din, H, Cp)
+                _stage_dgrad(dPLg[:, t], Wg, dXC, B, V, Cp, 2 * H, T * B * V * 2 * H)
+                mix_bwd(dXC[0], dXC[1], XCg[1, t], S, dS, 0, dxt, True, carry, hprev, None, None, None, None, None,
+                        Din, H, Cp)
+            # weight gradients of both stages: one batched GEMM each over every (t, clip) pair
+            dWg = torch.empty(2, V, Cp, 2 * H, dtype=torch.float32, device=dev)
+            dWu = torch.empty(2, V, Cp, H, dtype=torch.float32, device=dev)
+            for XC, dPL, dW, Co in ((XCg, dPLg, dWg, 2 * H), (XCu, dPLu, dWu, H)):
+                bgemm(XC, 0, (T * B * V * Cp, Cp, 1, V * Cp, 0, 0), dPL, 0, (T * B * V * Co, Co, 1, V * Co, 0, 0),
+                      dW, 0, (V * Cp * Co, Cp * Co, Co, 1), (2, V), Cp, Co, (T * B, 1, 1))
+        return dX, dS.sum(0), dWg, dWu
+
+
+# ------------------------------------------------------------------------------------------------
+# time-axis transformer pieces (TA.py:40-69)
+# ------------------------------------------------------------------------------------------------
+def _rows(x):
+    return x.numel() // x.shape[-1]
+
+
+class _Linear(Function):
+    """y = x W^T + b over the last axis (optionally ReLU'd); W (Nout,Kin) / b fp32 parameters."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu, out_dtype):
+        with torch.autocast("cuda", enabled=False):
+            x = x.contiguous()
+            Wc = W.to(x.dtype).contiguous()
+            Kin, Nout, R = x.shape[-1], W.shape[0], _rows(x)
+            y = torch.empty(*x.shape[:-1], Nout, dtype=out_dtype or x.dtype, device=x.device)
+            bgemm(x, 0, (0, 0, Kin, 1, 0, 0), Wc, 0, (0, 0, Kin, 1, 0, 0), y, 0, (0, 0, Nout, 1), (1, 1), R, Nout,
+                  (Kin, 1, 1), act=1 if relu else 0, bias_n=b.float().contiguous() if b is not None else None)
+        ctx.saved = (x, Wc, y if relu else None)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wc, y = ctx.saved
+        ctx.saved = None
+        with torch.autocast("cuda", enabled=False):
+            Kin, Nout, R = x.shape[-1], Wc.shape[0], _rows(x)
+            dy = dy.to(x.dtype).contiguous()
+            if y is not None:
+                dy = dy.clone()
+                L.check(L.load().fmm_tg_relu_mask(dy.data_ptr(), y.data_ptr(), dy.numel(), _dt(dy), L.stream()), "tg_relu_mask")
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                bgemm(dy, 0, (0, 0, Nout, 1, 0, 0), Wc, 0, (0, 0, 1, Kin, 0, 0), dx, 0, (0, 0, Kin, 1), (1, 1), R, Kin,
+                      (Nout, 1, 1))
+            dW = torch.zeros(Nout, Kin, dtype=torch.float32, device=x.device)
+            bgemm(dy, 0, (0, 0, 1, Nout, 0, 0), x, 0, (0, 0, 1, Kin, 0, 0), dW, 0, (0, 0, Kin, 1), (1, 1), Nout, Kin,
+                  (R, 1, 1), splitk=_splitk(Nout, Kin, 1, R))
+            db = None
+            if ctx.has_bias:
+                db = torch.zeros(Nout, dtype=torch.float32, device=x.device)
+                one = torch.ones(8, dtype=x.dtype, device=x.device)
+                bgemm(one, 0, (0, 0, 0, 0, 0, 0), dy, 0, (0, 0, 1, Nout, 0, 0), db, 0, (0, 0, 0, 1), (1, 1), 1, Nout,
+                      (R, 1, 1), splitk=_splitk(1, Nout, 1, R))
+        return dx, dW, db, None, None
+
+
+class _TimeConv(Function):
+    """``nn.Conv2d(T, T, (1,3))`` applied to x (B,T,V,C) read as NCHW (TA.py:26-27,42-44): the channel axis is
+    TIME, the kernel slides over the feature axis. Returns q[b,v,t',f] as (B,V,T,C) with columns C-2.. zero."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        with torch.autocast("cuda", enabled=False):
+            x = x.contiguous()
+            B, T, V, Cc = x.shape
+            F = Cc - 2
+            Wc = W.to(x.dtype).contiguous()          # (T', T, 1, 3)
+            q = torch.zeros(B, V, T, Cc, dtype=x.dtype, device=x.device)
+            # k = (j, t): A[t'][(j,t)] = W[t',t,j]   B[(j,t)][f] = x[b,t,v,f+j]
+            bgemm(Wc, 0, (0, 0, 3 * T, 1, 3, 0), x, 0, (T * V * Cc, Cc, 1, 1, V * Cc, 0), q, 0, (V * T * Cc, T * Cc, Cc, 1),
+                  (B, V), T, F, (3, T, 1), bias_m=b.float().contiguous())
+        ctx.saved = (x, Wc)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        x, Wc = ctx.saved
+        ctx.saved = None
+        with torch.autocast("cuda", enabled=False):
+            B, T, V, Cc = x.shape
+            F = Cc - 2
+            dev = x.device
+            # zero the pad columns and give the buffer a zero front porch: the dgrad below reads dq[.., c-j]
+            pad = torch.zeros(B * V * T * Cc + 8, dtype=x.dtype, device=dev)
+            dqp = pad[8:].view(B, V, T, Cc)
+            dqp[..., :F].copy_(dq[..., :F])
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                # dx[b,t,v,c] = sum_{j,t'} W[t',t,j] dq[b,v,t',c-j]; out-of-range c-j lands on zero pad columns
+                bgemm(Wc, 0, (0, 0, 3, 1, 3 * T, 0), pad, 8, (V * T * Cc, T * Cc, 1, -1, Cc, 0), dx, 0,
+                      (T * V * Cc, Cc, V * Cc, 1), (B, V), T, Cc, (3, T, 1))
+            dW = torch.zeros(T, T, 1, 3, dtype=torch.float32, device=dev)
+            sk = _splitk(T, T, 1, B * V * F)
+            for j in range(3):
+                # dW[t',t,j] = sum_{b,v,f} dq[b,v,t',f] x[b,t,v,f+j]
+                bgemm(pad, 8, (0, 0, Cc, V * T * Cc, T * Cc, 1), x, j, (0, 0, V * Cc, T * V * Cc, Cc, 1), dW, j,
+                      (0, 0, 3 * T, 3), (1, 1), T, T, (B, V, F), splitk=sk)
+            db = torch.zeros(T, dtype=torch.float32, device=dev)
+            one = torch.ones(8, dtype=x.dtype, device=dev)
+            bgemm(pad, 8, (0, 0, Cc, V * T * Cc, T * Cc, 1), one, 0, (0, 0, 0, 0, 0, 0), db, 0, (0, 0, 1, 0), (1, 1), T, 1,
+                  (B, V, F), splitk=_splitk(T, 1, 1, B * V * F))
+        return dx, dW, db
+
+
+class _Attention(Function):
+    """softmax(q k^T / sqrt(C)) v over time per (clip, joint) (TA.py:55-62); q,k,v (B,V,T,C) -> (B,T,V,C)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v):
+        with torch.autocast("cuda", enabled=False):
+            B, V, T, Cc = q.shape
+            Tp = (T + 7) // 8 * 8
+            dt, dev = q.dtype, q.device
+            P = torch.empty(B, V, T, Tp, dtype=dt, device=dev)
+            sc = 1.0 / math.sqrt(Cc)
+            bgemm(q, 0, (V * T * Cc, T * Cc, Cc, 1, 0, 0), k, 0, (V * T * Cc, T * Cc, Cc, 1, 0, 0), P, 0,
+                  (V * T * Tp, T * Tp, Tp, 1), (B, V), T, T, (Cc, 1, 1), alpha=sc)
+            L.check(L.load().fmm_tg_softmax_fwd(P.data_ptr(), B * V * T, T, Tp, _dt(P), L.stream()), "tg_softmax_fwd")
+            out = torch.empty(B, T, V, Cc, dtype=dt, device=dev)
+            bgemm(P, 0, (V * T * Tp, T * Tp, Tp, 1, 0, 0), v, 0, (V * T * Cc, T * Cc, 1, Cc, 0, 0), out, 0,
+                  (T * V * Cc, Cc, V * Cc, 1), (B, V), T, Cc, (T, 1, 1))
+        ctx.saved = (q, k, v, P)
+        return out
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, P = ctx.saved
+        ctx.saved = None
+        with torch.autocast("cuda", enabled=False):
+            B, V, T, Cc = q.shape
+            Tp = P.shape[-1]
+            dt, dev = q.dtype, q.device
+            sc = 1.0 / math.sqrt(Cc)
+            do = do.to(dt).contiguous()                           # (B,T,V,C)
+            ga, gp = (V * T * Cc, T * Cc), (V * T * Tp, T * Tp)    # batch strides of (B,V,T,C) / (B,V,T,Tp)
+            go = (T * V * Cc, Cc)                                  # batch strides of (B,T,V,C) seen per (b,v)
+            dP = torch.empty(B, V, T, Tp, dtype=dt, device=dev)
+            bgemm(do, 0, (*go, V * Cc, 1, 0, 0), v, 0, (*ga, Cc, 1, 0, 0), dP, 0, (*gp, Tp, 1), (B, V), T, T, (Cc, 1, 1))
+            dv = torch.empty_like(v)
+            bgemm(P, 0, (*gp, 1, Tp, 0, 0), do, 0, (*go, 1, V * Cc, 0, 0), dv, 0, (*ga, Cc, 1), (B, V), T, Cc, (T, 1, 1))
+            L.check(L.load().fmm_tg_softmax_bwd(P.data_ptr(), dP.data_ptr(), B * V * T, T, Tp, _dt(P), L.stream()),
+                    "tg_softmax_bwd")
+            dq = torch.empty_like(q)
+            bgemm(dP, 0, (*gp, Tp, 1, 0, 0), k, 0, (*ga, 1, Cc, 0, 0), dq, 0, (*ga, Cc, 1), (B, V), T, Cc, (T, 1, 1), alpha=sc)
+            dk = torch.empty_like(k)
+            bgemm(dP, 0, (*gp, 1, Tp, 0, 0), q, 0, (*ga, 1, Cc, 0, 0), dk, 0, (*ga, Cc, 1), (B, V), T, Cc, (T, 1, 1), alpha=sc)
+        return dq, dk, dv
+
+
+class _ValueProj(Function):
+    """v = vff(x) (TA.py:45,50) written straight into (B,V,T,C) order; x (B,T,V,C)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        with torch.autocast("cuda", enabled=False):
+            x = x.contiguous()
+            B, T, V, Cc = x.shape
+            Wc = W.to(x.dtype).contiguous()
+            out = torch.empty(B, V, T, Cc, dtype=x.dtype, device=x.device)
+            bgemm(x, 0, (T * V * Cc, Cc, V * Cc, 1, 0, 0), Wc, 0, (0, 0, Cc, 1, 0, 0), out, 0, (V * T * Cc, T * Cc, Cc, 1),
+                  (B, V), T, Cc, (Cc, 1, 1), bias_n=b.float().contiguous())
+        ctx.saved = (x, Wc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dv):
+        x, Wc = ctx.saved
+        ctx.saved = None
+        with torch.autocast("cuda", enabled=False):
+            B, T, V, Cc = x.shape
+            dv = dv.to(x.dtype).contiguous()                      # (B,V,T,C)
+            dx = torch.empty_like(x)
+            bgemm(dv, 0, (V * T * Cc, T * Cc, Cc, 1, 0, 0), Wc, 0, (0, 0, 1, Cc, 0, 0), dx, 0, (T * V * Cc, Cc, V * Cc, 1),
+                  (B, V), T, Cc, (Cc, 1, 1))
+            R = B * V * T
+            dW = torch.zeros(Cc, Cc, dtype=torch.float32, device=x.device)
+            # rows of dv are (b,v,t), rows of x are (b,t,v): contract over the three levels explicitly
+            bgemm(dv, 0, (0, 0, 1, V * T * Cc, T * Cc, Cc), x, 0, (0, 0, 1, T * V * Cc, Cc, V * Cc), dW, 0, (0, 0, Cc, 1),
+                  (1, 1), Cc, Cc, (B, V, T), splitk=_splitk(Cc, Cc, 1, R))
+            db = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+            one = torch.ones(8, dtype=x.dtype, device=x.device)
+            bgemm(one, 0, (0, 0, 0, 0, 0, 0), dv, 0, (0, 0, 1, Cc, 0, 0), db, 0, (0, 0, 0, 1), (1, 1), 1, Cc, (R, 1, 1),
+                  splitk=_splitk(1, Cc, 1, R))
+        return dx, dW, db
+
+
+class _LayerNorm2(Function):
+    """LayerNorm over the last axis of (a + b) (TA.py:64-68); b may be None."""
+
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, eps):
+        with torch.autocast("cuda", enabled=False):
+            a = a.contiguous()
+            b = b.to(a.dtype).contiguous() if b is not None else None
+            Cc, R = a.shape[-1], _rows(a)
+            y = torch.empty_like(a)
+            mean = torch.empty(R, dtype=torch.float32, device=a.device)
+            rstd = torch.empty(R, dtype=torch.float32, device=a.device)
+            g, be = gamma.float().contiguous(), beta.float().contiguous()
+            L.check(L.load().fmm_tg_ln_fwd(a.data_ptr(), b.data_ptr() if b is not None else None, g.data_ptr(), be.data_ptr(),
+                                           y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), R, Cc, eps, _dt(a), L.stream()),
+                    "tg_ln_fwd")
+        ctx.saved = (a, b, g, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b, g, mean, rstd = ctx.saved
+        ctx.saved = None
+        with torch.autocast("cuda", enabled=False):
+            Cc, R = a.shape[-1], _rows(a)
+            dy = dy.to(a.dtype).contiguous()
+            dx = torch.empty_like(a)
+            dg = torch.zeros(Cc, dtype=torch.float32, device=a.device)
+            db = torch.zeros(Cc, dtype=torch.float32, device=a.device)
+            L.check(L.load().fmm_tg_ln_bwd(dy.data_ptr(), a.data_ptr(), b.data_ptr() if b is not None else None, g.data_ptr(),
+                                           mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), R,
+                                           Cc, _dt(a), L.stream()), "tg_ln_bwd")
+        return dx, (dx if b is not None else None), dg, db, None
+
+
+class _AddPE(Function):
+    @staticmethod
+    def forward(ctx, x, pe):
+        with torch.autocast("cuda", enabled=False):
+            x = x.contiguous()
+            B, T, V, Cc = x.shape
+            y = torch.empty_like(x)
+            L.check(L.load().fmm_tg_add_pe(x.data_ptr(), pe.float().contiguous().data_ptr(), y.data_ptr(), B, T, V, Cc, _dt(x),
+                                           L.stream()), "tg_add_pe")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, None
+
+
+class _Head(Function):
+    """end_conv + AdaptiveAvgPool2d(1) (TRAGCN.py:215-222) on the last 6 hidden frames: the pooling over the
+    horizon and over the joints commutes with the convolution, so feat = mean_v(x6) . W_eff + b_eff with
+    W_eff (C_out, 6, C) the horizon-mean of the conv weight (computed by the caller)."""
+
+    @staticmethod
+    def forward(ctx, x, Weff, beff):
+        with torch.autocast("cuda", enabled=False):
+            x = x.contiguous()
+            B, T, V, Cc = x.shape
+            Co = Weff.shape[0]
+            Wc = Weff.to(x.dtype).contiguous()                    # (Co, 6, C)
+            feat = torch.empty(B, Co, dtype=x.dtype, device=x.device)
+            bgemm(x, (T - 6) * V * Cc, (0, 0, T * V * Cc, V * Cc, Cc, 1), Wc, 0, (0, 0, 6 * Cc, Cc, 0, 1), feat, 0,
+                  (0, 0, Co, 1), (1, 1), B, Co, (6, V, Cc), alpha=1.0 / V, bias_n=None)
+        ctx.saved = (x, Wc)
+        return feat
+
+    @staticmethod
+    def backward(ctx, df):
+        x, Wc = ctx.saved
+        ctx.saved = None
+        with torch.autocast("cuda", enabled=False):
+            B, T, V, Cc = x.shape
+            Co = Wc.shape[0]
+            df = df.to(x.dtype).contiguous()
+            dx = torch.zeros_like(x)
+            # dx[b, T-6+s, v, k] = (1/V) sum_c df[b,c] W_eff[c,s,k]  (same for every joint): batch = (s, v)
+            bgemm(df, 0, (0, 0, Co, 1, 0, 0), Wc, 0, (Cc, 0, 1, 6 * Cc, 0, 0), dx, (T - 6) * V * Cc,
+                  (V * Cc, Cc, T * V * Cc, 1), (6, V), B, Cc, (Co, 1, 1), alpha=1.0 / V)
+            # dW_eff[c,s,k] = (1/V) sum_{b,v} df[b,c] x[b,T-6+s,v,k]: batch = s, contraction (b, v)
+            dW = torch.zeros(Co, 6, Cc, dtype=torch.float32, device=x.device)
+            bgemm(df, 0, (0, 0, 1, Co, 0, 0), x, (T - 6) * V * Cc, (V * Cc, 0, 1, T * V * Cc, Cc, 0), dW, 0,
+                  (Cc, 0, 6 * Cc, 1), (6, 1), Co, Cc, (B, V, 1), alpha=1.0 / V)
+        return dx, dW, None
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers with the reference's names
+# ------------------------------------------------------------------------------------------------
+def sym_norm_adj(adj: torch.Tensor) -> torch.Tensor:
+    """EmbGCN.py:13-26 followed by the constructor's softmax (:63-64, implicit dim=1 for a matrix)."""
+    W = adj.detach().double().cpu()
+    n = W.shape[0]
+    W = W + 0.5 * torch.eye(n, dtype=torch.float64)
+    d = torch.sqrt(1.0 / W.sum(1))
+    out = d[:, None] * W * d[None, :]
+    return torch.softmax(out.float(), dim=1)
+
+
+class EmbGCN(nn.Module):
+    def __init__(self, dim_in, dim_out, adj, cheb_k, embed_dim):
+        super().__init__()
+        self.cheb_k = cheb_k
+        self.register_buffer("_colscale", torch.softmax(sym_norm_adj(adj), dim=-1).sum(0), persistent=False)  # :77
+        self.linear = nn.Linear(dim_in, dim_out, bias=True)
+        # the reference leaves the pools uninitialised (torch.FloatTensor); small normal values here
+        self.weights_pool = nn.Parameter(torch.randn(embed_dim, dim_in, dim_out) * 0.02)
+        self.bias_pool = nn.Parameter(torch.randn(embed_dim, dim_out) * 0.02)
+
+    def stage_weights(self, E, Cp):
+        """(2, V, Cp, Cout) fp32: [0] per-node graph weights + bias row, [1] column-scaled Linear + bias row."""
+        V = E.shape[0]
+        Cin, Co = self.weights_pool.shape[1], self.weights_pool.shape[2]
+        Wn = torch.einsum("nd,dio->nio", E, self.weights_pool)                       # EmbGCN.py:80
+        bn = E @ self.bias_pool                                                       # :81
+        Wl = self._colscale[:, None, None] * self.linear.weight.t()[None]             # :77-78
+        bl = self.linear.bias[None].expand(V, Co)
+        z = E.new_zeros(V, Cp - Cin - 1, Co)
+        return torch.stack([torch.cat([Wn, bn[:, None], z], 1), torch.cat([Wl, bl[:, None], z], 1)])
+
+
+class GRU(nn.Module):
+    def __init__(self, node_num, dim_in, dim_out, adj, cheb_k, embed_dim):
+        super().__init__()
+        self.node_num, self.hidden_dim, self.dim_in = node_num, dim_out, dim_in
+        self.gate = EmbGCN(dim_in + dim_out, 2 * dim_out, adj, cheb_k, embed_dim)
+        self.update = EmbGCN(dim_in + dim_out, dim_out, adj, cheb_k, embed_dim)
+
+
+class Transform(nn.Module):
+    def __init__(self, outfea, d, seq_len=30):
+        super().__init__()
+        self.vff = nn.Linear(outfea, outfea)
+        self.conv1 = nn.Conv2d(seq_len, seq_len, (1, 3), bias=True)
+        self.conv2 = nn.Conv2d(seq_len, seq_len, (1, 3), bias=True)
+        self.ln = nn.LayerNorm(outfea)
+        self.lnff = nn.LayerNorm(outfea)
+        self.ff = nn.Sequential(nn.Linear(outfea, outfea), nn.ReLU(), nn.Linear(outfea, outfea))
+        self.d = d
+
+    def forward(self, x):
+        q = _TimeConv.apply(x, self.conv1.weight, self.conv1.bias)
+        k = _TimeConv.apply(x, self.conv2.weight, self.conv2.bias)
+        v = _ValueProj.apply(x, self.vff.weight, self.vff.bias)
+        att = _Attention.apply(q, k, v)
+        val = _LayerNorm2.apply(att, x, self.ln.weight, self.ln.bias, self.ln.eps)
+        h = _Linear.apply(val, self.ff[0].weight, self.ff[0].bias, True, None)
+        h = _Linear.apply(h, self.ff[2].weight, self.ff[2].bias, False, None)
+        return _LayerNorm2.apply(h, val, self.lnff.weight, self.lnff.bias, self.lnff.eps)
+
+
+class PositionalEncoding(nn.Module):
+    def __init__(self, outfea, max_len=30):
+        super().__init__()
+        pe = torch.zeros(max_len, outfea)
+        position = torch.arange(0, max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, outfea, 2) * -(math.log(10000.0) / outfea))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe.unsqueeze(0).unsqueeze(2))
+
+    def forward(self, x):
+        return _AddPE.apply(x, self.pe)
+
+
+class transformer_layer(nn.Module):
+    def __init__(self, dim_in, dim_out, num_layer, d=2, att_his=False, seq_len=30):
+        super().__init__()
+        self.trans_layers = nn.ModuleList(Transform(dim_out, d, seq_len) for _ in range(num_layer))
+        self.PE = PositionalEncoding(dim_out, seq_len)
+        self.num_layer = num_layer
+
+    def forward(self, x):
+        x = self.PE(x)
+        for layer in self.trans_layers:
+            x = layer(x)
+        return x
+
+
+class AVWDCRNN(nn.Module):
+    def __init__(self, node_num, dim_in, dim_out, cheb_k, embed_dim, adj, num_layers=1, seq_len=30):
+        super().__init__()
+        assert num_layers >= 1, "At least one GRU layer in the Encoder."
+        self.node_num, self.input_dim, self.num_layers = node_num, dim_in, num_layers
+        self.dcrnn_cells = nn.ModuleList([GRU(node_num, dim_in, dim_out, adj, cheb_k, embed_dim)])
+        for _ in range(1, num_layers):
+            self.dcrnn_cells.append(GRU(node_num, dim_out, dim_out, adj, cheb_k, embed_dim))
+        self.trans_layer_T = transformer_layer(dim_out, dim_out, 2, 2, seq_len=seq_len)
+
+    def forward(self, x, node_embeddings):
+        """x (B,T,V,Din) in the compute dtype -> (B,T,V,H); zero initial state (TRAGCN.py:212)."""
+        assert x.shape[2] == self.node_num and x.shape[3] == self.input_dim
+        E = node_embeddings.float()
+        with torch.autocast("cuda", enabled=False):
+            V = E.shape[0]
+            S = torch.softmax(torch.relu(E @ E.t()), dim=1) + torch.eye(V, device=E.device)      # EmbGCN.py:73-74
+            cur = x
+            for cell in self.dcrnn_cells:
+                Cp = (cell.dim_in + cell.hidden_dim + 1 + 7) // 8 * 8
+                cur = _GraphGRUScan.apply(cur.contiguous(), S, cell.gate.stage_weights(E, Cp), cell.update.stage_weights(E, Cp))
+        return self.trans_layer_T(cur)
+
+
+class TARGCN(nn.Module):
+    """``TARGCN(input_dim=3, num_classes=11, num_nodes=14, rnn_units=64, output_dim=64, horizon=30, num_layers=2,
+    embed_dim=64, cheb_k=2, adj=None)`` (TRAGCN.py:178). ``seq_len`` is the clip length the time-axis attention
+    is built for (the reference hard-codes 30 as a default argument of Transform / PositionalEncoding)."""
+
+    def __init__(self, input_dim=3, num_classes=11, num_nodes=14, rnn_units=64, output_dim=64, horizon=30, num_layers=2,
+                 embed_dim=64, cheb_k=2, adj=None, seq_len=30):
+        super().__init__()
+        if rnn_units % 32 or rnn_units > 256:
+            raise NotImplementedError("rnn_units must be a multiple of 32 up to 256")
+        if num_nodes > 32:
+            raise NotImplementedError("the cell kernels hold one clip's joints in shared memory (num_nodes <= 32)")
+        self.num_clsses, self.num_node, self.input_dim = num_classes, num_nodes, input_dim
+        self.hidden_dim, self.output_dim, self.horizon, self.num_layers = rnn_units, output_dim, horizon, num_layers
+        self.embed_dim, self.cheb_k, self.seq_len = embed_dim, cheb_k, seq_len
+        adj = adj if adj is not None else torch.ones(num_nodes, num_nodes)               # TRAGCN.py:191
+        adj = torch.as_tensor(adj, dtype=torch.float32)
+        assert adj.shape == (num_nodes, num_nodes)
+        self.node_embeddings = nn.Parameter(torch.randn(num_nodes, embed_dim))
+        self.encoder = AVWDCRNN(num_nodes, input_dim, rnn_units, cheb_k, embed_dim, adj, num_layers, seq_len)
+        self.end_conv = nn.Conv2d(6, horizon * output_dim, kernel_size=(1, rnn_units), bias=True)
+        self.fc = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(output_dim, num_classes))
+        self.compute_dtype = None
+
+    def features(self, source):
+        if not source.is_cuda:
+            raise RuntimeError("fall_multimodal_b200.TARGCN runs on CUDA (sm_100a) only; there is no CPU fallback")
+        B, T, V, D = source.shape
+        if T != self.seq_len:
+            raise ValueError(f"clip length {T} != seq_len {self.seq_len} the time-axis attention was built for")
+        dt = _compute_dtype(self)
+        out = self.encoder(source.to(dt).contiguous(), self.node_embeddings)
+        with torch.autocast("cuda", enabled=False):
+            W = self.end_conv.weight.float().view(self.horizon, self.output_dim, 6, self.hidden_dim).mean(0)
+            beff = self.end_conv.bias.float().view(self.horizon, self.output_dim).mean(0)
+        feat = _Head.apply(out, W, None)
+        return feat, beff, dt
+
+    def forward(self, source):
+        feat, beff, dt = self.features(source)
+        with torch.autocast("cuda", enabled=False):
+            f = feat.float() + beff
+            out = _Linear.apply(f.to(dt), self.fc[2].weight, self.fc[2].bias, False, torch.float32)
+        return out.to(dt) if dt == torch.bfloat16 else out

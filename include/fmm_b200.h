@@ -155,6 +155,66 @@ int fmm_lstm_bwd(const float* x, const float* w_ih, const float* w_hh, const flo
                  const float* cseq, const float* dout, float* dw_ih, float* dw_hh, float* db, float* dx, int N,
                  int T, int I, int H, int ndir, cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * TRAGCN family (EmbGCN.py:59-89, GRU.py:17-26, TRAGCN.py:150-224, TA.py:40-108).
+ *
+ * fmm_bgemm: strided batched GEMM  C[g1,g2][m][n] = act(alpha * sum_k A[g1,g2][m][k] B[g1,g2][k][n]
+ * + bias_m[m] + bias_n[n]) (+ C when beta).  All strides are in ELEMENTS, a stride of 0 broadcasts,
+ * the contraction index is k = (k1*K2 + k2)*K3 + k3 with one stride per level. It replaces torch.einsum /
+ * torch.matmul / nn.Linear / nn.Conv2d(T,T,(1,3)) at every call site of those reference files.
+ * dtype = operand type (FMM_DT_*), c_dtype = type of C; splitk > 1 accumulates partial sums into an
+ * fp32 C with atomics (zero it first; no bias/act/beta).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fmm_bgemm_desc {
+  const void* A;
+  const void* B;
+  void* C;
+  const float* bias_m;
+  const float* bias_n;
+  long long a_g1, a_g2, a_m, a_k1, a_k2, a_k3;
+  long long b_g1, b_g2, b_n, b_k1, b_k2, b_k3;
+  long long c_g1, c_g2, c_m, c_n;
+  int G1, G2, M, N, K1, K2, K3;
+  float alpha;
+  int beta;
+  int act; /* 0 none, 1 relu */
+  int splitk;
+  int dtype;
+  int c_dtype;
+} fmm_bgemm_desc;
+int fmm_bgemm(const fmm_bgemm_desc* desc, cudaStream_t stream);
+
+/* Graph-GRU cell pieces (one time step, all clips). Activations are [B][V][*] slices addressed by a clip
+ * stride (..b) and a joint stride (..v); XC buffers are [B][V][Cp] with Cp >= Din+H+1 (column Din+H is the
+ * constant 1 that carries the bias row of the per-node weights, the rest is zero padding).
+ *  tg_catmix : cat = [x_t | h (* r)] ; xc1 = cat ; xc0 = S . cat          (EmbGCN.py:77,83 ; GRU.py:20,23)
+ *  tg_gate   : out = sigmoid|tanh(pre + silu(lin)) ; mode 1 also h' = z*h + (1-z)*hc (GRU.py:21,24-25)
+ *  tg_cell_bwd1 / tg_mix_bwd : the matching backward steps (dS accumulates into nrep replicas [nrep][V][V]). */
+int fmm_tg_catmix(const void* x, long long xb, long long xv, const void* h, long long hb, long long hv, const void* r,
+                  long long rb, long long rv, const float* S, void* xc0, void* xc1, int B, int V, int Din, int H, int Cp,
+                  int dtype, cudaStream_t stream);
+int fmm_tg_gate(const float* pre, const float* lin, void* out, void* lin_save, int mode, const void* z, long long zs,
+                const void* hprev, long long hb, long long hv, void* hout, long long ob, long long ov, int B, int V, int C,
+                int dtype, cudaStream_t stream);
+int fmm_tg_cell_bwd1(float* carry, const void* dH, long long db, long long dv, const void* z, long long zs,
+                     const void* hprev, long long hb, long long hv, const void* hc, const void* lu, float* dz, void* dpre,
+                     void* dlin, int B, int V, int H, int dtype, cudaStream_t stream);
+int fmm_tg_mix_bwd(const float* dxc0, const float* dxc1, const void* cat, const float* S, float* dS, int nrep, int mode,
+                   void* dx, long long dxb, long long dxv, int dx_accum, float* carry, const void* hprev, long long hb,
+                   long long hv, const void* zr, const float* dz, const void* lg, void* dpre, void* dlin, int B, int V,
+                   int Din, int H, int Cp, int dtype, cudaStream_t stream);
+/* Time-axis attention pieces (TA.py:55-68): in-place row softmax over the first L of Lp entries (+ backward,
+ * written over dp), LayerNorm over C of (a + b) with saved mean/rstd (+ backward; dgamma/dbeta accumulate),
+ * positional encoding add, ReLU mask. */
+int fmm_tg_softmax_fwd(void* x, long long rows, int L, int Lp, int dtype, cudaStream_t stream);
+int fmm_tg_softmax_bwd(const void* p, void* dp, long long rows, int L, int Lp, int dtype, cudaStream_t stream);
+int fmm_tg_ln_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                  long long rows, int C, float eps, int dtype, cudaStream_t stream);
+int fmm_tg_ln_bwd(const void* dy, const void* a, const void* b, const float* gamma, const float* mean, const float* rstd,
+                  void* dx, float* dgamma, float* dbeta, long long rows, int C, int dtype, cudaStream_t stream);
+int fmm_tg_add_pe(const void* x, const float* pe, void* y, int B, int T, int V, int C, int dtype, cudaStream_t stream);
+int fmm_tg_relu_mask(void* dx, const void* y, long long total, int dtype, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,7 @@ _SIGNATURES = {
     "fmm_tg_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P],
     "fmm_tg_add_pe": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_tg_relu_mask": [_P, _P, c_ll, c_int, _P],
+    "fmm_tg_transpose": [_P, _P, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_int, c_int, c_int, _P],
 }
 _RESTYPES = {"fmm_tapconv_packed_bytes": c_ll}
 

@@ -317,6 +317,34 @@ __global__ void relu_mask_kernel(T* __restrict__ dx, const T* __restrict__ y, lo
     if (!(to_f32(y[i]) > 0.f)) dx[i] = from_f32<T>(0.f);
 }
 
+// batched 2-D transpose: in[g][r][c] (row stride in_rs, c contiguous) -> out[g][c][r] (row stride out_rs),
+// r in [0, Rp) with zeros for r >= R.  g = (g1, g2) with separate strides on both sides.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int R, int Cc, int Rp,
+                                                        long long in_g1, long long in_g2, long long in_rs,
+                                                        long long out_g1, long long out_g2, long long out_rs, int G2,
+                                                        int tiles_r, int tiles_c) {
+  __shared__ float tile[32][33];
+  int bid = blockIdx.x;
+  const int tr = bid % tiles_r;
+  bid /= tiles_r;
+  const int tc = bid % tiles_c;
+  const int g = bid / tiles_c;
+  const int g1 = g / G2, g2 = g % G2;
+  const T* src = in + g1 * in_g1 + g2 * in_g2;
+  T* dst = out + g1 * out_g1 + g2 * out_g2;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    int r = tr * 32 + i, c = tc * 32 + tx;
+    tile[i][tx] = (r < R && c < Cc) ? to_f32(src[r * in_rs + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int c = tc * 32 + i, r = tr * 32 + tx;
+    if (c < Cc && r < Rp) dst[c * out_rs + r] = from_f32<T>(tile[tx][i]);
+  }
+}
+
 static int ew_blocks(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   long long cap = (long long)num_sms() * 8;
@@ -447,6 +475,19 @@ int fmm_tg_relu_mask(void* dx, const void* y, long long total, int dtype, void* 
   FMM_CHECK_ARG(total > 0, "tg_relu_mask: empty");
   TG_DISPATCH(dtype, relu_mask_kernel<T><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((T*)dx, (const T*)y, total);)
   FMM_CHECK_LAUNCH("tg_relu_mask");
+  return FMM_OK;
+}
+
+int fmm_tg_transpose(const void* in, void* out, int R, int Cc, int Rp, long long in_g1, long long in_g2, long long in_rs,
+                     long long out_g1, long long out_g2, long long out_rs, int G1, int G2, int dtype, void* stream) {
+  TG_CHECK_DT(dtype, "tg_transpose");
+  FMM_CHECK_ARG(R > 0 && Cc > 0 && Rp >= R && G1 > 0 && G2 > 0, "tg_transpose: bad shape");
+  const int tiles_r = (Rp + 31) / 32, tiles_c = (Cc + 31) / 32;
+  long long blocks = (long long)tiles_r * tiles_c * G1 * G2;
+  FMM_CHECK_ARG(blocks < (1ll << 31), "tg_transpose: too many tiles");
+  TG_DISPATCH(dtype, transpose_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const T*)in, (T*)out, R, Cc, Rp, in_g1, in_g2, in_rs, out_g1, out_g2, out_rs, G2, tiles_r, tiles_c);)
+  FMM_CHECK_LAUNCH("tg_transpose");
   return FMM_OK;
 }
 

@@ -263,71 +263,102 @@ class _Linear(Function):
         return dx, dW, db, None, None
 
 
-class _TimeConv(Function):
-    """``nn.Conv2d(T, T, (1,3))`` applied to x (B,T,V,C) read as NCHW (TA.py:26-27,42-44): the channel axis is
-    TIME, the kernel slides over the feature axis. Returns q[b,v,t',f] as (B,V,T,C) with columns C-2.. zero."""
+def _transpose(src, dst, R, Cc, Rp, in_str, out_str, G):
+    L.check(L.load().fmm_tg_transpose(src.data_ptr(), dst.data_ptr(), R, Cc, Rp, in_str[0], in_str[1], in_str[2],
+                                      out_str[0], out_str[1], out_str[2], G[0], G[1], _dt(src), L.stream()), "tg_transpose")
+
+
+class _TimeToChannels(Function):
+    """x (B,T,V,C) -> xT (B,C,V,Tp): the time axis becomes the (64-padded, zero-filled) channel axis and the
+    feature axis becomes the position axis, which is how TA.py's Conv2d(T,T,(1,3)) reads its input."""
 
     @staticmethod
-    def forward(ctx, x, W, b):
+    def forward(ctx, x):
+        x = x.contiguous()
+        B, T, V, Cc = x.shape
+        Tp = (T + 63) // 64 * 64
+        xT = torch.empty(B, Cc, V, Tp, dtype=x.dtype, device=x.device)
+        _transpose(x, xT, T, Cc, Tp, (T * V * Cc, Cc, V * Cc), (Cc * V * Tp, Tp, V * Tp), (B, V))
+        ctx.T = T
+        return xT
+
+    @staticmethod
+    def backward(ctx, dxT):
+        dxT = dxT.contiguous()
+        B, Cc, V, Tp = dxT.shape
+        T = ctx.T
+        dx = torch.empty(B, T, V, Cc, dtype=dxT.dtype, device=dxT.device)
+        _transpose(dxT, dx, Cc, T, Cc, (Cc * V * Tp, Tp, V * Tp), (T * V * Cc, Cc, V * Cc), (B, V))
+        return dx
+
+
+class _TimeConv(Function):
+    """``nn.Conv2d(T, T, (1,3))`` of TA.py:26-27,42-44 on the tcgen05 tap-conv engines (csrc/tapconv.cu, wgrad.cu):
+    with time as the channel axis it is a 3-tap "valid" convolution along the feature axis.
+    xT (B,C,V,Tp) -> q (B,C-2,V,Tp) with q[b,f,v,t'] = bias[t'] + sum_{j,t} W[t',t,0,j] xT[b,f+j,v,t]."""
+
+    @staticmethod
+    def forward(ctx, xT, W, b, T):
+        from . import ops
         with torch.autocast("cuda", enabled=False):
-            x = x.contiguous()
-            B, T, V, Cc = x.shape
+            B, Cc, V, Tp = xT.shape
             F = Cc - 2
-            Wc = W.to(x.dtype).contiguous()          # (T', T, 1, 3)
-            q = torch.zeros(B, V, T, Cc, dtype=x.dtype, device=x.device)
-            # k = (j, t): A[t'][(j,t)] = W[t',t,j]   B[(j,t)][f] = x[b,t,v,f+j]
-            bgemm(Wc, 0, (0, 0, 3 * T, 1, 3, 0), x, 0, (T * V * Cc, Cc, 1, 1, V * Cc, 0), q, 0, (V * T * Cc, T * Cc, Cc, 1),
-                  (B, V), T, F, (3, T, 1), bias_m=b.float().contiguous())
-        ctx.saved = (x, Wc)
+            dt = xT.dtype
+            Wf = torch.zeros(Tp, Tp, 3, dtype=torch.float32, device=xT.device)   # channel counts padded like xT
+            Wf[:T, :T] = W.float().view(T, T, 3)
+            pw = ops.tapconv_pack(Wf, Tp, Tp, Tp, Tp, 0, 3 * Tp, 0, 3, 1, [0, 1, 2], dt)
+            bias = torch.zeros(Tp, dtype=torch.float32, device=xT.device)
+            bias[:T] = b.float()
+            q = torch.empty(B, F, V, Tp, dtype=dt, device=xT.device)
+            ops.tapconv(xT, pw, q, shifts=[0, 1, 2], tj=F, bias=bias)
+        ctx.saved = (xT, Wf)
+        ctx.T = T
         return q
 
     @staticmethod
     def backward(ctx, dq):
-        x, Wc = ctx.saved
+        from . import ops
+        xT, Wf = ctx.saved
         ctx.saved = None
+        T = ctx.T
         with torch.autocast("cuda", enabled=False):
-            B, T, V, Cc = x.shape
+            B, Cc, V, Tp = xT.shape
             F = Cc - 2
-            dev = x.device
-            # zero the pad columns and give the buffer a zero front porch: the dgrad below reads dq[.., c-j]
-            pad = torch.zeros(B * V * T * Cc + 8, dtype=x.dtype, device=dev)
-            dqp = pad[8:].view(B, V, T, Cc)
-            dqp[..., :F].copy_(dq[..., :F])
-            dx = None
+            dt, dev = xT.dtype, xT.device
+            dq = dq.to(dt).contiguous()
+            dxT = None
             if ctx.needs_input_grad[0]:
-                dx = torch.empty_like(x)
-                # dx[b,t,v,c] = sum_{j,t'} W[t',t,j] dq[b,v,t',c-j]; out-of-range c-j lands on zero pad columns
-                bgemm(Wc, 0, (0, 0, 3, 1, 3 * T, 0), pad, 8, (V * T * Cc, T * Cc, 1, -1, Cc, 0), dx, 0,
-                      (T * V * Cc, Cc, V * Cc, 1), (B, V), T, Cc, (3, T, 1))
-            dW = torch.zeros(T, T, 1, 3, dtype=torch.float32, device=dev)
-            sk = _splitk(T, T, 1, B * V * F)
-            for j in range(3):
-                # dW[t',t,j] = sum_{b,v,f} dq[b,v,t',f] x[b,t,v,f+j]
-                bgemm(pad, 8, (0, 0, Cc, V * T * Cc, T * Cc, 1), x, j, (0, 0, V * Cc, T * V * Cc, Cc, 1), dW, j,
-                      (0, 0, 3 * T, 3), (1, 1), T, T, (B, V, F), splitk=sk)
-            db = torch.zeros(T, dtype=torch.float32, device=dev)
-            one = torch.ones(8, dtype=x.dtype, device=dev)
-            bgemm(pad, 8, (0, 0, Cc, V * T * Cc, T * Cc, 1), one, 0, (0, 0, 0, 0, 0, 0), db, 0, (0, 0, 1, 0), (1, 1), T, 1,
-                  (B, V, F), splitk=_splitk(T, 1, 1, B * V * F))
-        return dx, dW, db
+                pwT = ops.tapconv_pack(Wf, Tp, Tp, Tp, Tp, 0, 3, 0, 3 * Tp, 1, [0, 1, 2], dt)
+                dxT = torch.empty_like(xT)
+                ops.tapconv(dq, pwT, dxT, shifts=[0, -1, -2], tj=Cc)
+            dWp = torch.zeros(Tp, Tp, 3, dtype=torch.float32, device=dev)      # [t'][t][j], padded
+            ops.wgrad(xT, dq, dWp, shifts=[0, 1, 2], s_m=1, s_c2=3, s_co=3 * Tp)
+            dW = dWp[:T, :T].reshape(T, T, 1, 3)
+            st = torch.zeros(2 * ops.NREP * Tp, dtype=torch.float64, device=dev)
+            ops.colstats(dq, st[:ops.NREP * Tp], st[ops.NREP * Tp:])
+            db = st[:ops.NREP * Tp].view(ops.NREP, Tp).sum(0)[:T].float()
+        return dxT, dW, db, None
 
 
 class _Attention(Function):
-    """softmax(q k^T / sqrt(C)) v over time per (clip, joint) (TA.py:55-62); q,k,v (B,V,T,C) -> (B,T,V,C)."""
+    """softmax(q k^T / sqrt(C)) v over time per (clip, joint) (TA.py:55-62).
+    q, k (B,F,V,Tp) as produced by _TimeConv (feature-major), v (B,V,T,C) -> (B,T,V,C)."""
 
     @staticmethod
     def forward(ctx, q, k, v):
         with torch.autocast("cuda", enabled=False):
-            B, V, T, Cc = q.shape
-            Tp = (T + 7) // 8 * 8
+            B, F, V, Tp = q.shape
+            T, Cc = v.shape[2], v.shape[3]
+            Pp = (T + 7) // 8 * 8
             dt, dev = q.dtype, q.device
-            P = torch.empty(B, V, T, Tp, dtype=dt, device=dev)
+            P = torch.empty(B, V, T, Pp, dtype=dt, device=dev)
             sc = 1.0 / math.sqrt(Cc)
-            bgemm(q, 0, (V * T * Cc, T * Cc, Cc, 1, 0, 0), k, 0, (V * T * Cc, T * Cc, Cc, 1, 0, 0), P, 0,
-                  (V * T * Tp, T * Tp, Tp, 1), (B, V), T, T, (Cc, 1, 1), alpha=sc)
-            L.check(L.load().fmm_tg_softmax_fwd(P.data_ptr(), B * V * T, T, Tp, _dt(P), L.stream()), "tg_softmax_fwd")
+            gq = (F * V * Tp, Tp)
+            bgemm(q, 0, (*gq, 1, V * Tp, 0, 0), k, 0, (*gq, 1, V * Tp, 0, 0), P, 0, (V * T * Pp, T * Pp, Pp, 1), (B, V), T, T,
+                  (F, 1, 1), alpha=sc)
+            L.check(L.load().fmm_tg_softmax_fwd(P.data_ptr(), B * V * T, T, Pp, _dt(P), L.stream()), "tg_softmax_fwd")
             out = torch.empty(B, T, V, Cc, dtype=dt, device=dev)
-            bgemm(P, 0, (V * T * Tp, T * Tp, Tp, 1, 0, 0), v, 0, (V * T * Cc, T * Cc, 1, Cc, 0, 0), out, 0,
+            bgemm(P, 0, (V * T * Pp, T * Pp, Pp, 1, 0, 0), v, 0, (V * T * Cc, T * Cc, 1, Cc, 0, 0), out, 0,
                   (T * V * Cc, Cc, V * Cc, 1), (B, V), T, Cc, (T, 1, 1))
         ctx.saved = (q, k, v, P)
         return out
@@ -337,23 +368,26 @@ class _Attention(Function):
         q, k, v, P = ctx.saved
         ctx.saved = None
         with torch.autocast("cuda", enabled=False):
-            B, V, T, Cc = q.shape
-            Tp = P.shape[-1]
+            B, F, V, Tp = q.shape
+            T, Cc = v.shape[2], v.shape[3]
+            Pp = P.shape[-1]
             dt, dev = q.dtype, q.device
             sc = 1.0 / math.sqrt(Cc)
             do = do.to(dt).contiguous()                           # (B,T,V,C)
-            ga, gp = (V * T * Cc, T * Cc), (V * T * Tp, T * Tp)    # batch strides of (B,V,T,C) / (B,V,T,Tp)
+            ga, gp = (V * T * Cc, T * Cc), (V * T * Pp, T * Pp)    # batch strides of (B,V,T,C) / (B,V,T,Pp)
             go = (T * V * Cc, Cc)                                  # batch strides of (B,T,V,C) seen per (b,v)
-            dP = torch.empty(B, V, T, Tp, dtype=dt, device=dev)
-            bgemm(do, 0, (*go, V * Cc, 1, 0, 0), v, 0, (*ga, Cc, 1, 0, 0), dP, 0, (*gp, Tp, 1), (B, V), T, T, (Cc, 1, 1))
+            gq = (F * V * Tp, Tp)                                  # batch strides of (B,F,V,Tp) seen per (b,v)
+            dP = torch.empty(B, V, T, Pp, dtype=dt, device=dev)
+            bgemm(do, 0, (*go, V * Cc, 1, 0, 0), v, 0, (*ga, Cc, 1, 0, 0), dP, 0, (*gp, Pp, 1), (B, V), T, T, (Cc, 1, 1))
             dv = torch.empty_like(v)
-            bgemm(P, 0, (*gp, 1, Tp, 0, 0), do, 0, (*go, 1, V * Cc, 0, 0), dv, 0, (*ga, Cc, 1), (B, V), T, Cc, (T, 1, 1))
-            L.check(L.load().fmm_tg_softmax_bwd(P.data_ptr(), dP.data_ptr(), B * V * T, T, Tp, _dt(P), L.stream()),
+            bgemm(P, 0, (*gp, 1, Pp, 0, 0), do, 0, (*go, 1, V * Cc, 0, 0), dv, 0, (*ga, Cc, 1), (B, V), T, Cc, (T, 1, 1))
+            L.check(L.load().fmm_tg_softmax_bwd(P.data_ptr(), dP.data_ptr(), B * V * T, T, Pp, _dt(P), L.stream()),
                     "tg_softmax_bwd")
-            dq = torch.empty_like(q)
-            bgemm(dP, 0, (*gp, Tp, 1, 0, 0), k, 0, (*ga, 1, Cc, 0, 0), dq, 0, (*ga, Cc, 1), (B, V), T, Cc, (T, 1, 1), alpha=sc)
-            dk = torch.empty_like(k)
-            bgemm(dP, 0, (*gp, 1, Tp, 0, 0), q, 0, (*ga, 1, Cc, 0, 0), dk, 0, (*ga, Cc, 1), (B, V), T, Cc, (T, 1, 1), alpha=sc)
+            # dq[b,f,v,t1] = sc * sum_t2 dS[t1,t2] k[b,f,v,t2];  dk[b,f,v,t2] = sc * sum_t1 dS[t1,t2] q[b,f,v,t1]
+            dq = torch.zeros_like(q)
+            bgemm(k, 0, (*gq, V * Tp, 1, 0, 0), dP, 0, (*gp, Pp, 1, 0, 0), dq, 0, (*gq, V * Tp, 1), (B, V), F, T, (T, 1, 1), alpha=sc)
+            dk = torch.zeros_like(k)
+            bgemm(q, 0, (*gq, V * Tp, 1, 0, 0), dP, 0, (*gp, 1, Pp, 0, 0), dk, 0, (*gq, V * Tp, 1), (B, V), F, T, (T, 1, 1), alpha=sc)
         return dq, dk, dv
 
 
@@ -537,8 +571,10 @@ class Transform(nn.Module):
         self.d = d
 
     def forward(self, x):
-        q = _TimeConv.apply(x, self.conv1.weight, self.conv1.bias)
-        k = _TimeConv.apply(x, self.conv2.weight, self.conv2.bias)
+        T = x.shape[1]
+        xT = _TimeToChannels.apply(x)
+        q = _TimeConv.apply(xT, self.conv1.weight, self.conv1.bias, T)
+        k = _TimeConv.apply(xT, self.conv2.weight, self.conv2.bias, T)
         v = _ValueProj.apply(x, self.vff.weight, self.vff.bias)
         att = _Attention.apply(q, k, v)
         val = _LayerNorm2.apply(att, x, self.ln.weight, self.ln.bias, self.ln.eps)

@@ -214,6 +214,10 @@ int fmm_tg_ln_bwd(const void* dy, const void* a, const void* b, const float* gam
                   void* dx, float* dgamma, float* dbeta, long long rows, int C, int dtype, cudaStream_t stream);
 int fmm_tg_add_pe(const void* x, const float* pe, void* y, int B, int T, int V, int C, int dtype, cudaStream_t stream);
 int fmm_tg_relu_mask(void* dx, const void* y, long long total, int dtype, cudaStream_t stream);
+/* batched 2-D transpose in[g1,g2][r][c] -> out[g1,g2][c][r], rows r in [R, Rp) written as zero (the time <-> feature
+ * swap that turns TA.py's time-as-channel (1,3) convolutions into tap convolutions for fmm_tapconv / fmm_wgrad) */
+int fmm_tg_transpose(const void* in, void* out, int R, int C, int Rp, long long in_g1, long long in_g2, long long in_rs,
+                     long long out_g1, long long out_g2, long long out_rs, int G1, int G2, int dtype, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -118,11 +118,8 @@ _SIGNATURES = {
     "fmm_wgrad": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                   C.POINTER(c_int), c_int, c_ll, c_ll, c_ll, c_ll, c_int, _P, _P],
     "fmm_bgemm": [_P, _P],
-    "fmm_tg_catmix": [_P, c_ll, c_ll, _P, c_ll, c_ll, _P, c_ll, c_ll, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
-    "fmm_tg_gate": [_P, _P, _P, _P, c_int, _P, c_ll, _P, c_ll, c_ll, _P, c_ll, c_ll, c_int, c_int, c_int, c_int, _P],
-    "fmm_tg_cell_bwd1": [_P, _P, c_ll, c_ll, _P, c_ll, _P, c_ll, c_ll, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
-    "fmm_tg_mix_bwd": [_P, _P, _P, _P, _P, c_int, c_int, _P, c_ll, c_ll, c_int, _P, _P, c_ll, c_ll, _P, _P, _P, _P, _P,
-                       c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_tg_cell_fwd": [_P, c_int, _P],
+    "fmm_tg_cell_bwd": [_P, c_int, _P],
     "fmm_tg_softmax_fwd": [_P, c_ll, c_int, c_int, c_int, _P],
     "fmm_tg_softmax_bwd": [_P, _P, c_ll, c_int, c_int, c_int, _P],
     "fmm_tg_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, c_ll, c_int, c_float, c_int, _P],
@@ -141,6 +138,23 @@ class BgemmDesc(C.Structure):
                                      "b_k3", "c_g1", "c_g2", "c_m", "c_n")] +
                 [(n, c_int) for n in ("G1", "G2", "M", "N", "K1", "K2", "K3")] +
                 [("alpha", c_float), ("beta", c_int), ("act", c_int), ("splitk", c_int), ("dtype", c_int), ("c_dtype", c_int)])
+
+
+def _struct(name, spec):
+    fields = []
+    for kind, names in spec:
+        fields += [(n, kind) for n in names.split()]
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+# mirrors of fmm_cell_fwd_args / fmm_cell_bwd_args (include/fmm_b200.h, csrc/gru_cell.cu)
+CellFwdArgs = _struct("CellFwdArgs", [
+    (c_void_p, "x"), (c_ll, "xb xv"), (c_void_p, "hprev"), (c_ll, "hb hv"), (c_void_p, "S pre lin zr lg hc lu hout"),
+    (c_ll, "ob ov"), (c_void_p, "xc0 xc1"), (c_int, "mode B V Din H Cp")])
+CellBwdArgs = _struct("CellBwdArgs", [
+    (c_void_p, "S carry dz dxc0 dxc1 dx"), (c_ll, "dxb dxv"), (c_void_p, "hprev"), (c_ll, "hb hv"),
+    (c_void_p, "zr lg dpre_g dlin_g dH"), (c_ll, "db dv"), (c_void_p, "z1 hprev1"), (c_ll, "hb1 hv1"),
+    (c_void_p, "hc1 lu1 dpre_u dlin_u"), (c_int, "mode dx_accum do_bwd1 B V Din H Cp")])
 
 
 def int_array(vals):

@@ -1,189 +1,15 @@
-// Memory-bound kernels of the TRAGCN family (reference: EmbGCN.py:59-89, GRU.py:17-26, TA.py:40-69):
-// the concat + adaptive-adjacency mix feeding the per-node products, the gate / candidate / state
-// update of the graph GRU and their backward counterparts, row softmax, LayerNorm(a+b), positional
-// encoding, ReLU masking. The matrix products in between run in bgemm.cu.
+// Memory-bound kernels of the time-axis transformer of the TRAGCN family (reference: TA.py:40-108):
+// row softmax, LayerNorm(a+b), positional encoding, ReLU masking, the time<->feature transpose.
+// The matrix products in between run in bgemm.cu / tapconv.cu / wgrad.cu; the graph-GRU glue is gru_cell.cu.
 #include "common.cuh"
 
 namespace fmm {
-
-constexpr int kMaxV = 32;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float silu_(float x) { return x * sigmoidf_(x); }
 __device__ __forceinline__ float dsilu_(float x) {
   float s = sigmoidf_(x);
   return s * (1.f + x * (1.f - s));
-}
-
-// ---------------------------------------------------------------------------------------------
-// catmix: cat = [x_t | h (*r) | 1 | 0-pad];  XC1 = cat;  XC0 = S . cat (the bias column stays 1)
-// one block per clip
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) catmix_kernel(const T* __restrict__ x, long long xb, long long xv,
-                                                     const T* __restrict__ h, long long hb, long long hv,
-                                                     const T* __restrict__ r, long long rb, long long rv,
-                                                     const float* __restrict__ S, T* __restrict__ xc0,
-                                                     T* __restrict__ xc1, int V, int Din, int H, int Cp) {
-  extern __shared__ float sm[];
-  float* cat = sm;             // [V][Cp]
-  float* Ss = sm + V * Cp;     // [V][V]
-  const int b = blockIdx.x, Cin = Din + H;
-  for (int i = threadIdx.x; i < V * V; i += blockDim.x) Ss[i] = S[i];
-  for (int i = threadIdx.x; i < V * Cp; i += blockDim.x) {
-    int m = i / Cp, c = i % Cp;
-    float v = 0.f;
-    if (c < Din) {
-      v = to_f32(x[b * xb + m * xv + c]);
-    } else if (c < Cin) {
-      if (h) {
-        v = to_f32(h[b * hb + m * hv + (c - Din)]);
-        if (r) v = to_f32(from_f32<T>(v * to_f32(r[b * rb + m * rv + (c - Din)])));  // r*state is a rounded tensor in the reference
-      }
-    } else if (c == Cin) {
-      v = 1.f;
-    }
-    cat[i] = v;
-  }
-  __syncthreads();
-  const long long ob = (long long)b * V * Cp;
-  for (int i = threadIdx.x; i < V * Cp; i += blockDim.x) {
-    int n = i / Cp, c = i % Cp;
-    float acc;
-    if (c < Cin) {
-      acc = 0.f;
-      for (int m = 0; m < V; ++m) acc += Ss[n * V + m] * cat[m * Cp + c];
-    } else {
-      acc = cat[i];
-    }
-    xc0[ob + i] = from_f32<T>(acc);
-    xc1[ob + i] = from_f32<T>(cat[i]);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// gate: out = act(pre + silu(lin)); mode 0: sigmoid -> zr.  mode 1: tanh -> hc, then h' = z*h + (1-z)*hc
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void gate_kernel(const float* __restrict__ pre, const float* __restrict__ lin, T* __restrict__ out,
-                            T* __restrict__ lin_save, int mode, const T* __restrict__ z, long long zs,
-                            const T* __restrict__ hprev, long long hb, long long hv, T* __restrict__ hout,
-                            long long ob, long long ov, int B, int V, int C) {
-  long long total = (long long)B * V * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    long long row = i / C;
-    float l = lin[i];
-    float a = pre[i] + silu_(l);
-    lin_save[i] = from_f32<T>(l);
-    if (mode == 0) {
-      out[i] = from_f32<T>(sigmoidf_(a));
-    } else {
-      int v = (int)(row % V);
-      long long b = row / V;
-      float hc = to_f32(from_f32<T>(tanhf(a)));
-      out[i] = from_f32<T>(hc);
-      float zz = to_f32(z[row * zs + c]);
-      float hp = hprev ? to_f32(hprev[b * hb + v * hv + c]) : 0.f;
-      hout[b * ob + v * ov + c] = from_f32<T>(zz * hp + (1.f - zz) * hc);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// backward, part 1 (state update + candidate): dh_tot = carry + dH_t
-//   dz = dh_tot*(h - hc); carry = dh_tot*z; dpre_u = dh_tot*(1-z)*(1-hc^2); dlin_u = dpre_u*silu'(lin_u)
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void cell_bwd1_kernel(float* __restrict__ carry, const T* __restrict__ dH, long long db, long long dv,
-                                 const T* __restrict__ z, long long zs, const T* __restrict__ hprev, long long hb,
-                                 long long hv, const T* __restrict__ hc, const T* __restrict__ lu,
-                                 float* __restrict__ dz, T* __restrict__ dpre, T* __restrict__ dlin, int B, int V, int H) {
-  long long total = (long long)B * V * H;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % H);
-    long long row = i / H;
-    int v = (int)(row % V);
-    long long b = row / V;
-    float d = carry[i] + (dH ? to_f32(dH[b * db + v * dv + c]) : 0.f);
-    float zz = to_f32(z[row * zs + c]);
-    float hp = hprev ? to_f32(hprev[b * hb + v * hv + c]) : 0.f;
-    float hcc = to_f32(hc[i]);
-    dz[i] = d * (hp - hcc);
-    carry[i] = d * zz;
-    float dp = d * (1.f - zz) * (1.f - hcc * hcc);
-    dpre[i] = from_f32<T>(dp);
-    dlin[i] = from_f32<T>(dp * dsilu_(to_f32(lu[i])));
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// backward, part 2: undo concat + mix.  dcat[m] = sum_n S[n][m]*dXC0[n] + dXC1[m];
-//   dS[n][m] += sum_{c<Cin} dXC0[n][c]*cat[m][c]
-//   mode 1 (candidate stage): dx += dcat[:Din]; drh = dcat[Din:]; dr = drh*h; carry += drh*r;
-//                             dpre_g = [dz*z(1-z) | dr*r(1-r)]; dlin_g = dpre_g*silu'(lin_g)
-//   mode 0 (gate stage):      dx += dcat[:Din]; carry += dcat[Din:]
-// one block per clip
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) mix_bwd_kernel(const float* __restrict__ dxc0, const float* __restrict__ dxc1,
-                                                      const T* __restrict__ cat, const float* __restrict__ S,
-                                                      float* __restrict__ dS, int nrep, int mode, T* __restrict__ dx,
-                                                      long long dxb, long long dxv, int dx_accum,
-                                                      float* __restrict__ carry, const T* __restrict__ hprev,
-                                                      long long hb, long long hv, const T* __restrict__ zr,
-                                                      const float* __restrict__ dz, const T* __restrict__ lg,
-                                                      T* __restrict__ dpre, T* __restrict__ dlin, int V, int Din,
-                                                      int H, int Cp) {
-  extern __shared__ float sm[];
-  float* d0 = sm;                 // [V][Cp]
-  float* ct = d0 + V * Cp;        // [V][Cp]
-  float* Ss = ct + V * Cp;        // [V][V]
-  const int b = blockIdx.x, Cin = Din + H;
-  const long long ob = (long long)b * V * Cp;
-  for (int i = threadIdx.x; i < V * V; i += blockDim.x) Ss[i] = S[i];
-  for (int i = threadIdx.x; i < V * Cp; i += blockDim.x) {
-    d0[i] = dxc0[ob + i];
-    ct[i] = to_f32(cat[ob + i]);
-  }
-  __syncthreads();
-  // dS partial: V*V dot products of length Cin
-  float* dSr = dS + (size_t)(b % nrep) * V * V;
-  for (int i = threadIdx.x; i < V * V; i += blockDim.x) {
-    int n = i / V, m = i % V;
-    float acc = 0.f;
-    for (int c = 0; c < Cin; ++c) acc += d0[n * Cp + c] * ct[m * Cp + c];
-    atomicAdd(&dSr[i], acc);
-  }
-  for (int i = threadIdx.x; i < V * Cin; i += blockDim.x) {
-    int m = i / Cin, c = i % Cin;
-    float acc = dxc1[ob + m * Cp + c];
-    for (int n = 0; n < V; ++n) acc += Ss[n * V + m] * d0[n * Cp + c];
-    if (c < Din) {
-      if (dx) {
-        T* p = dx + b * dxb + m * dxv + c;
-        *p = from_f32<T>(dx_accum ? to_f32(*p) + acc : acc);
-      }
-      continue;
-    }
-    int j = c - Din;
-    long long row = (long long)b * V + m;
-    long long hi = row * H + j;
-    if (mode == 0) {
-      carry[hi] += acc;
-    } else {
-      float hp = hprev ? to_f32(hprev[b * hb + m * hv + j]) : 0.f;
-      float zz = to_f32(zr[row * 2 * H + j]), rr = to_f32(zr[row * 2 * H + H + j]);
-      carry[hi] += acc * rr;
-      float dr = acc * hp;
-      float gz = dz[hi] * zz * (1.f - zz), gr = dr * rr * (1.f - rr);
-      long long o = row * 2 * H;
-      dpre[o + j] = from_f32<T>(gz);
-      dpre[o + H + j] = from_f32<T>(gr);
-      dlin[o + j] = from_f32<T>(gz * dsilu_(to_f32(lg[o + j])));
-      dlin[o + H + j] = from_f32<T>(gr * dsilu_(to_f32(lg[o + H + j])));
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -365,61 +191,6 @@ using namespace fmm;
 #define TG_CHECK_DT(dtype, name) FMM_CHECK_ARG((dtype) == FMM_DT_BF16 || (dtype) == FMM_DT_F32, name ": bad dtype %d", dtype)
 
 extern "C" {
-
-int fmm_tg_catmix(const void* x, long long xb, long long xv, const void* h, long long hb, long long hv, const void* r,
-                  long long rb, long long rv, const float* S, void* xc0, void* xc1, int B, int V, int Din, int H, int Cp,
-                  int dtype, void* stream) {
-  TG_CHECK_DT(dtype, "tg_catmix");
-  FMM_CHECK_ARG(B > 0 && V > 0 && V <= kMaxV && Din > 0 && H > 0 && Cp >= Din + H + 1, "tg_catmix: bad shape (B %d V %d Din %d H %d Cp %d)",
-                B, V, Din, H, Cp);
-  size_t smem = sizeof(float) * ((size_t)V * Cp + (size_t)V * V);
-  FMM_CHECK_ARG(smem <= 48 * 1024, "tg_catmix: V*Cp too large for shared memory");
-  TG_DISPATCH(dtype, catmix_kernel<T><<<B, 256, smem, (cudaStream_t)stream>>>(
-      (const T*)x, xb, xv, (const T*)h, hb, hv, (const T*)r, rb, rv, S, (T*)xc0, (T*)xc1, V, Din, H, Cp);)
-  FMM_CHECK_LAUNCH("tg_catmix");
-  return FMM_OK;
-}
-
-int fmm_tg_gate(const float* pre, const float* lin, void* out, void* lin_save, int mode, const void* z, long long zs,
-                const void* hprev, long long hb, long long hv, void* hout, long long ob, long long ov, int B, int V, int C,
-                int dtype, void* stream) {
-  TG_CHECK_DT(dtype, "tg_gate");
-  FMM_CHECK_ARG(B > 0 && V > 0 && C > 0 && (mode == 0 || (z && hout)), "tg_gate: bad arguments");
-  long long total = (long long)B * V * C;
-  TG_DISPATCH(dtype, gate_kernel<T><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      pre, lin, (T*)out, (T*)lin_save, mode, (const T*)z, zs, (const T*)hprev, hb, hv, (T*)hout, ob, ov, B, V, C);)
-  FMM_CHECK_LAUNCH("tg_gate");
-  return FMM_OK;
-}
-
-int fmm_tg_cell_bwd1(float* carry, const void* dH, long long db, long long dv, const void* z, long long zs,
-                     const void* hprev, long long hb, long long hv, const void* hc, const void* lu, float* dz, void* dpre,
-                     void* dlin, int B, int V, int H, int dtype, void* stream) {
-  TG_CHECK_DT(dtype, "tg_cell_bwd1");
-  long long total = (long long)B * V * H;
-  FMM_CHECK_ARG(total > 0, "tg_cell_bwd1: empty");
-  TG_DISPATCH(dtype, cell_bwd1_kernel<T><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      carry, (const T*)dH, db, dv, (const T*)z, zs, (const T*)hprev, hb, hv, (const T*)hc, (const T*)lu, dz, (T*)dpre,
-      (T*)dlin, B, V, H);)
-  FMM_CHECK_LAUNCH("tg_cell_bwd1");
-  return FMM_OK;
-}
-
-int fmm_tg_mix_bwd(const float* dxc0, const float* dxc1, const void* cat, const float* S, float* dS, int nrep, int mode,
-                   void* dx, long long dxb, long long dxv, int dx_accum, float* carry, const void* hprev, long long hb,
-                   long long hv, const void* zr, const float* dz, const void* lg, void* dpre, void* dlin, int B, int V,
-                   int Din, int H, int Cp, int dtype, void* stream) {
-  TG_CHECK_DT(dtype, "tg_mix_bwd");
-  FMM_CHECK_ARG(B > 0 && V > 0 && V <= kMaxV && nrep > 0 && Cp >= Din + H + 1, "tg_mix_bwd: bad shape");
-  FMM_CHECK_ARG(mode == 0 || (zr && dz && lg && dpre && dlin), "tg_mix_bwd: candidate stage needs the gate tensors");
-  size_t smem = sizeof(float) * (2 * (size_t)V * Cp + (size_t)V * V);
-  FMM_CHECK_ARG(smem <= 48 * 1024, "tg_mix_bwd: V*Cp too large for shared memory");
-  TG_DISPATCH(dtype, mix_bwd_kernel<T><<<B, 256, smem, (cudaStream_t)stream>>>(
-      dxc0, dxc1, (const T*)cat, S, dS, nrep, mode, (T*)dx, dxb, dxv, dx_accum, carry, (const T*)hprev, hb, hv,
-      (const T*)zr, dz, (const T*)lg, (T*)dpre, (T*)dlin, V, Din, H, Cp);)
-  FMM_CHECK_LAUNCH("tg_mix_bwd");
-  return FMM_OK;
-}
 
 int fmm_tg_softmax_fwd(void* x, long long rows, int L, int Lp, int dtype, void* stream) {
   TG_CHECK_DT(dtype, "tg_softmax_fwd");

@@ -31,9 +31,6 @@ from torch.autograd import Function
 from . import _lib as L
 from .stgcan import _compute_dtype
 
-NREP = 16  # replicas of the dS accumulator
-
-
 # ------------------------------------------------------------------------------------------------
 # raw kernel faces
 # ------------------------------------------------------------------------------------------------
@@ -83,41 +80,41 @@ def _sl(t):
     return t.data_ptr(), t.stride(0), t.stride(1)
 
 
-def catmix(x, h, r, S, xc0, xc1, Din, H, Cp):
-    B, V = x.shape[0], x.shape[1]
-    xp, xb, xv = _sl(x)
-    hp, hb, hv = _sl(h)
-    rp, rb, rv = _sl(r)
-    L.check(L.load().fmm_tg_catmix(xp, xb, xv, hp, hb, hv, rp, rb, rv, S.data_ptr(), xc0.data_ptr(), xc1.data_ptr(),
-                                   B, V, Din, H, Cp, _dt(x), L.stream()), "tg_catmix")
+def _P(t):
+    return t.data_ptr() if t is not None else None
 
 
-def gate(pre, lin, out, lin_save, mode, z=None, zs=0, hprev=None, hout=None):
-    B, V, Cc = pre.shape
-    hp, hb, hv = _sl(hprev)
-    op, ob, ov = _sl(hout)
-    L.check(L.load().fmm_tg_gate(pre.data_ptr(), lin.data_ptr(), out.data_ptr(), lin_save.data_ptr(), mode,
-                                 z.data_ptr() if z is not None else None, zs, hp, hb, hv, op, ob, ov, B, V, Cc,
-                                 _dt(out), L.stream()), "tg_gate")
+def cell_fwd(mode, dims, S, x=None, hprev=None, pre=None, lin=None, zr=None, lg=None, hc=None, lu=None, hout=None,
+             xc0=None, xc1=None):
+    """Fused cell glue, forward (csrc/gru_cell.cu); ``dims`` = (B, V, Din, H, Cp)."""
+    a = L.CellFwdArgs()
+    a.x, a.xb, a.xv = _sl(x)
+    a.hprev, a.hb, a.hv = _sl(hprev)
+    a.S, a.pre, a.lin, a.zr, a.lg, a.hc, a.lu = _P(S), _P(pre), _P(lin), _P(zr), _P(lg), _P(hc), _P(lu)
+    a.hout, a.ob, a.ov = _sl(hout)
+    a.xc0, a.xc1 = _P(xc0), _P(xc1)
+    a.mode = mode
+    a.B, a.V, a.Din, a.H, a.Cp = dims
+    ref = xc0 if xc0 is not None else hout
+    L.check(L.load().fmm_tg_cell_fwd(C.byref(a), _dt(ref), L.stream()), "tg_cell_fwd")
 
 
-def cell_bwd1(carry, dH, z, zs, hprev, hc, lu, dz, dpre, dlin):
-    B, V, H = carry.shape
-    dp, db, dv = _sl(dH)
-    hp, hb, hv = _sl(hprev)
-    L.check(L.load().fmm_tg_cell_bwd1(carry.data_ptr(), dp, db, dv, z.data_ptr(), zs, hp, hb, hv, hc.data_ptr(),
-                                      lu.data_ptr(), dz.data_ptr(), dpre.data_ptr(), dlin.data_ptr(), B, V, H, _dt(hc),
-                                      L.stream()), "tg_cell_bwd1")
-
-
-def mix_bwd(dxc0, dxc1, cat, S, dS, mode, dx, dx_accum, carry, hprev, zr, dz, lg, dpre, dlin, Din, H, Cp):
-    B, V = cat.shape[0], cat.shape[1]
-    xp, xb, xv = _sl(dx)
-    hp, hb, hv = _sl(hprev)
-    P = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
-    L.check(L.load().fmm_tg_mix_bwd(dxc0.data_ptr(), dxc1.data_ptr(), cat.data_ptr(), S.data_ptr(), dS.data_ptr(),
-                                    dS.shape[0], mode, xp, xb, xv, int(dx_accum), carry.data_ptr(), hp, hb, hv, P(zr),
-                                    P(dz), P(lg), P(dpre), P(dlin), B, V, Din, H, Cp, _dt(cat), L.stream()), "tg_mix_bwd")
+def cell_bwd(mode, dims, S, carry, dz, dt_ref, dxc0=None, dxc1=None, dx=None, dx_accum=False, hprev=None, zr=None, lg=None,
+             dpre_g=None, dlin_g=None, do_bwd1=False, dH=None, z1=None, hprev1=None, hc1=None, lu1=None, dpre_u=None,
+             dlin_u=None):
+    """Fused cell glue, backward (csrc/gru_cell.cu)."""
+    a = L.CellBwdArgs()
+    a.S, a.carry, a.dz, a.dxc0, a.dxc1 = _P(S), _P(carry), _P(dz), _P(dxc0), _P(dxc1)
+    a.dx, a.dxb, a.dxv = _sl(dx)
+    a.hprev, a.hb, a.hv = _sl(hprev)
+    a.zr, a.lg, a.dpre_g, a.dlin_g = _P(zr), _P(lg), _P(dpre_g), _P(dlin_g)
+    a.dH, a.db, a.dv = _sl(dH)
+    a.z1 = _P(z1)
+    a.hprev1, a.hb1, a.hv1 = _sl(hprev1)
+    a.hc1, a.lu1, a.dpre_u, a.dlin_u = _P(hc1), _P(lu1), _P(dpre_u), _P(dlin_u)
+    a.mode, a.dx_accum, a.do_bwd1 = mode, int(dx_accum), int(do_bwd1)
+    a.B, a.V, a.Din, a.H, a.Cp = dims
+    L.check(L.load().fmm_tg_cell_bwd(C.byref(a), L.dt_of(dt_ref), L.stream()), "tg_cell_bwd")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -129,10 +126,11 @@ def _stage_fwd(xc_t, WW, PL, B, V, Cp, Co, g1_stride):
           PL, 0, (B * V * Co, Co, V * Co, 1), (2, V), B, Co, (Cp, 1, 1))
 
 
-def _stage_dgrad(dPL_t, WW, dXC, B, V, Cp, Co, g1_stride):
-    """dXC[s][b][n][:] = dPL[s][t][b][n][:] . WW[s][n]^T"""
+def _stage_dgrad(dPL_t, WW, dXC0, dXC1, B, V, Cp, Co, g1_stride):
+    """dXC{s}[b][n][:] = dPL[s][t][b][n][:] . WW[s][n]^T; the two results land in separate (B,V,Cp) buffers."""
+    c_g1 = (dXC1.data_ptr() - dXC0.data_ptr()) // dXC0.element_size()
     bgemm(dPL_t, 0, (g1_stride, Co, V * Co, 1, 0, 0), WW, 0, (V * Cp * Co, Cp * Co, Co, 1, 0, 0),
-          dXC, 0, (B * V * Cp, Cp, V * Cp, 1), (2, V), B, Cp, (Co, 1, 1))
+          dXC0, 0, (c_g1, Cp, V * Cp, 1), (2, V), B, Cp, (Co, 1, 1))
 
 
 class _GraphGRUScan(Function):
@@ -162,16 +160,20 @@ class _GraphGRUScan(Function):
             PLg = torch.empty(2, B, V, 2 * H, dtype=torch.float32, device=dev)
             PLu = torch.empty(2, B, V, H, dtype=torch.float32, device=dev)
             g1 = Ts * B * V * Cp
+            dims = (B, V, Din, H, Cp)
+            cell_fwd(0, dims, S, x=x[:, 0], xc0=XCg[0, 0], xc1=XCg[1, 0])
             for t in range(T):
                 s = t if need else 0
                 hprev = Hout[:, t - 1] if t > 0 else None
-                xt = x[:, t]
-                catmix(xt, hprev, None, S, XCg[0, s], XCg[1, s], Din, H, Cp)
                 _stage_fwd(XCg[:, s], Wg, PLg, B, V, Cp, 2 * H, g1)
-                gate(PLg[0], PLg[1], ZR[s], LG[s], 0)
-                catmix(xt, hprev, ZR[s][..., H:], S, XCu[0, s], XCu[1, s], Din, H, Cp)
+                cell_fwd(1, dims, S, x=x[:, t], hprev=hprev, pre=PLg[0], lin=PLg[1], zr=ZR[s], lg=LG[s],
+                         xc0=XCu[0, s], xc1=XCu[1, s])
                 _stage_fwd(XCu[:, s], Wu, PLu, B, V, Cp, H, g1)
-                gate(PLu[0], PLu[1], HC[s], LU[s], 1, z=ZR[s], zs=2 * H, hprev=hprev, hout=Hout[:, t])
+                nxt = t + 1 < T
+                sn = (t + 1) if need else 0
+                cell_fwd(2, dims, S, x=x[:, t + 1] if nxt else None, hprev=hprev, pre=PLu[0], lin=PLu[1], zr=ZR[s],
+                         hc=HC[s], lu=LU[s], hout=Hout[:, t], xc0=XCg[0, sn] if nxt else None,
+                         xc1=XCg[1, sn] if nxt else None)
             if need:
                 ctx.saved = (x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU)
                 ctx.need_dx = ctx.needs_input_grad[0]
@@ -191,26 +193,48 @@ class _GraphGRUScan(Function):
             DZ = torch.empty(B, V, H, dtype=torch.float32, device=dev)
             dPLg = torch.empty(2, T, B, V, 2 * H, dtype=dt, device=dev)
             dPLu = torch.empty(2, T, B, V, H, dtype=dt, device=dev)
-            dXC = torch.empty(2, B, V, Cp, dtype=torch.float32, device=dev)
-            dS = torch.zeros(NREP, V, V, dtype=torch.float32, device=dev)
+            Cin = Din + H
+            # graph-path input gradients of every step are kept (slot t) for the dS GEMM below; slot T is the
+            # Linear-path scratch.  The bias rows are dropped from the dgrad weights: the constant-1 column has no gradient.
+            dXg = torch.empty(T + 1, B, V, Cp, dtype=dt, device=dev)
+            dXu = torch.empty(T + 1, B, V, Cp, dtype=dt, device=dev)
+            Wg_d, Wu_d = Wg.clone(), Wu.clone()
+            Wg_d[:, :, Cin:] = 0
+            Wu_d[:, :, Cin:] = 0
             dX = torch.empty(B, T, V, Din, dtype=dt, device=dev) if ctx.need_dx else None
+            dims = (B, V, Din, H, Cp)
+
+            def hp(t):
+                return Hout[:, t - 1] if t > 0 else None
+
+            t = T - 1
+            cell_bwd(0, dims, S, carry, DZ, dt, dH=dH[:, t], z1=ZR[t], hprev1=hp(t), hc1=HC[t], lu1=LU[t],
+                     dpre_u=dPLu[0, t], dlin_u=dPLu[1, t])
             for t in range(T - 1, -1, -1):
-                hprev = Hout[:, t - 1] if t > 0 else None
                 dxt = dX[:, t] if dX is not None else None
-                cell_bwd1(carry, dH[:, t], ZR[t], 2 * H, hprev, HC[t], LU[t], DZ, dPLu[0, t], dPLu[1, t])
-                _stage_dgrad(dPLu[:, t], Wu, dXC, B, V, Cp, H, T * B * V * H)
-                mix_bwd(dXC[0], dXC[1], XCu[1, t], S, dS, 1, dxt, False, carry, hprev, ZR[t], DZ, LG[t], dPLg[0, t],
-                        dPLg[1, t], Din, H, Cp)
-                _stage_dgrad(dPLg[:, t], Wg, dXC, B, V, Cp, 2 * H, T * B * V * 2 * H)
-                mix_bwd(dXC[0], dXC[1], XCg[1, t], S, dS, 0, dxt, True, carry, hprev, None, None, None, None, None,
-                        Din, H, Cp)
+                _stage_dgrad(dPLu[:, t], Wu_d, dXu[t], dXu[T], B, V, Cp, H, T * B * V * H)
+                cell_bwd(1, dims, S, carry, DZ, dt, dxc0=dXu[t], dxc1=dXu[T], dx=dxt, hprev=hp(t), zr=ZR[t], lg=LG[t],
+                         dpre_g=dPLg[0, t], dlin_g=dPLg[1, t])
+                _stage_dgrad(dPLg[:, t], Wg_d, dXg[t], dXg[T], B, V, Cp, 2 * H, T * B * V * 2 * H)
+                if t > 0:
+                    cell_bwd(2, dims, S, carry, DZ, dt, dxc0=dXg[t], dxc1=dXg[T], dx=dxt, dx_accum=True, do_bwd1=True,
+                             dH=dH[:, t - 1], z1=ZR[t - 1], hprev1=hp(t - 1), hc1=HC[t - 1], lu1=LU[t - 1],
+                             dpre_u=dPLu[0, t - 1], dlin_u=dPLu[1, t - 1])
+                else:
+                    cell_bwd(2, dims, S, carry, DZ, dt, dxc0=dXg[t], dxc1=dXg[T], dx=dxt, dx_accum=True)
+            # dS[n][m] = sum_{t,b,c} dXC0[t,b,n,c] cat[t,b,m,c] for both stages: split-K GEMMs over (t*b, c)
+            dS = torch.zeros(V, V, dtype=torch.float32, device=dev)
+            sk = _splitk(V, V, 1, T * B * Cp)
+            for dXs, XC in ((dXg, XCg), (dXu, XCu)):
+                bgemm(dXs, 0, (0, 0, Cp, V * Cp, 1, 0), XC[1], 0, (0, 0, Cp, V * Cp, 1, 0), dS, 0, (0, 0, V, 1), (1, 1), V, V,
+                      (T * B, Cp, 1), splitk=sk)
             # weight gradients of both stages: one batched GEMM each over every (t, clip) pair
             dWg = torch.empty(2, V, Cp, 2 * H, dtype=torch.float32, device=dev)
             dWu = torch.empty(2, V, Cp, H, dtype=torch.float32, device=dev)
             for XC, dPL, dW, Co in ((XCg, dPLg, dWg, 2 * H), (XCu, dPLu, dWu, H)):
                 bgemm(XC, 0, (T * B * V * Cp, Cp, 1, V * Cp, 0, 0), dPL, 0, (T * B * V * Co, Co, 1, V * Co, 0, 0),
                       dW, 0, (V * Cp * Co, Cp * Co, Co, 1), (2, V), Cp, Co, (T * B, 1, 1))
-        return dX, dS.sum(0), dWg, dWu
+        return dX, dS, dWg, dWu
 
 
 # ------------------------------------------------------------------------------------------------
@@ -539,7 +563,7 @@ class EmbGCN(nn.Module):
         self.weights_pool = nn.Parameter(torch.randn(embed_dim, dim_in, dim_out) * 0.02)
         self.bias_pool = nn.Parameter(torch.randn(embed_dim, dim_out) * 0.02)
 
-    def stage_weights(self, E, Cp):
+    def stage_weights(self, E, Cp, H):
         """(2, V, Cp, Cout) fp32: [0] per-node graph weights + bias row, [1] column-scaled Linear + bias row."""
         V = E.shape[0]
         Cin, Co = self.weights_pool.shape[1], self.weights_pool.shape[2]
@@ -548,7 +572,10 @@ class EmbGCN(nn.Module):
         Wl = self._colscale[:, None, None] * self.linear.weight.t()[None]             # :77-78
         bl = self.linear.bias[None].expand(V, Co)
         z = E.new_zeros(V, Cp - Cin - 1, Co)
-        return torch.stack([torch.cat([Wn, bn[:, None], z], 1), torch.cat([Wl, bl[:, None], z], 1)])
+        Dx = Cin - H
+        # rows follow the kernels' input layout [h | x | 1 | pad] (the reference concatenates (x, state), GRU.py:20)
+        return torch.stack([torch.cat([Wn[:, Dx:], Wn[:, :Dx], bn[:, None], z], 1),
+                            torch.cat([Wl[:, Dx:], Wl[:, :Dx], bl[:, None], z], 1)])
 
 
 class GRU(nn.Module):
@@ -631,7 +658,7 @@ class AVWDCRNN(nn.Module):
             cur = x
             for cell in self.dcrnn_cells:
                 Cp = (cell.dim_in + cell.hidden_dim + 1 + 7) // 8 * 8
-                cur = _GraphGRUScan.apply(cur.contiguous(), S, cell.gate.stage_weights(E, Cp), cell.update.stage_weights(E, Cp))
+                cur = _GraphGRUScan.apply(cur.contiguous(), S, cell.gate.stage_weights(E, Cp, cell.hidden_dim), cell.update.stage_weights(E, Cp, cell.hidden_dim))
         return self.trans_layer_T(cur)
 
 

@@ -184,25 +184,44 @@ typedef struct fmm_bgemm_desc {
 } fmm_bgemm_desc;
 int fmm_bgemm(const fmm_bgemm_desc* desc, cudaStream_t stream);
 
-/* Graph-GRU cell pieces (one time step, all clips). Activations are [B][V][*] slices addressed by a clip
- * stride (..b) and a joint stride (..v); XC buffers are [B][V][Cp] with Cp >= Din+H+1 (column Din+H is the
- * constant 1 that carries the bias row of the per-node weights, the rest is zero padding).
- *  tg_catmix : cat = [x_t | h (* r)] ; xc1 = cat ; xc0 = S . cat          (EmbGCN.py:77,83 ; GRU.py:20,23)
- *  tg_gate   : out = sigmoid|tanh(pre + silu(lin)) ; mode 1 also h' = z*h + (1-z)*hc (GRU.py:21,24-25)
- *  tg_cell_bwd1 / tg_mix_bwd : the matching backward steps (dS accumulates into nrep replicas [nrep][V][V]). */
-int fmm_tg_catmix(const void* x, long long xb, long long xv, const void* h, long long hb, long long hv, const void* r,
-                  long long rb, long long rv, const float* S, void* xc0, void* xc1, int B, int V, int Din, int H, int Cp,
-                  int dtype, cudaStream_t stream);
-int fmm_tg_gate(const float* pre, const float* lin, void* out, void* lin_save, int mode, const void* z, long long zs,
-                const void* hprev, long long hb, long long hv, void* hout, long long ob, long long ov, int B, int V, int C,
-                int dtype, cudaStream_t stream);
-int fmm_tg_cell_bwd1(float* carry, const void* dH, long long db, long long dv, const void* z, long long zs,
-                     const void* hprev, long long hb, long long hv, const void* hc, const void* lu, float* dz, void* dpre,
-                     void* dlin, int B, int V, int H, int dtype, cudaStream_t stream);
-int fmm_tg_mix_bwd(const float* dxc0, const float* dxc1, const void* cat, const float* S, float* dS, int nrep, int mode,
-                   void* dx, long long dxb, long long dxv, int dx_accum, float* carry, const void* hprev, long long hb,
-                   long long hv, const void* zr, const float* dz, const void* lg, void* dpre, void* dlin, int B, int V,
-                   int Din, int H, int Cp, int dtype, cudaStream_t stream);
+/* Graph-GRU cell glue (GRU.py:17-26 around EmbGCN.py:73-88; csrc/gru_cell.cu): one launch between consecutive
+ * per-node GEMMs, one block per clip, activations are [B][V][*] slices with a clip and a joint stride. The cell input
+ * is laid out [h (H) | x (Din) | 1 | 0-pad] (Cp wide, per-node weight rows permuted to match).
+ *  cell_fwd mode 0: cat=[h_{t-1}|x_t] -> xc0 = S.cat, xc1 = cat
+ *           mode 1: zr = sigmoid(pre + silu(lin)) -> zr, lg ; cat=[r*h_{t-1}|x_t] -> xc0, xc1
+ *           mode 2: hc = tanh(pre + silu(lin)), h_t = z*h_{t-1} + (1-z)*hc -> hc, lu, hout ; cat=[h_t|x] -> xc0, xc1 (if xc0)
+ *  cell_bwd mode 0: update/candidate backward of one step from carry + dH -> dz, carry, dpre_u, dlin_u
+ *           mode 1: candidate-stage mix backward -> dx, carry, dpre_g, dlin_g
+ *           mode 2: gate-stage mix backward -> dx (+=), carry, then mode 0 of the previous step when do_bwd1 */
+typedef struct fmm_cell_fwd_args {
+  const void* x; long long xb, xv;
+  const void* hprev; long long hb, hv;
+  const float* S;
+  const float* pre; const float* lin;
+  void* zr; void* lg;
+  void* hc; void* lu;
+  void* hout; long long ob, ov;
+  void* xc0; void* xc1;
+  int mode, B, V, Din, H, Cp;
+} fmm_cell_fwd_args;
+typedef struct fmm_cell_bwd_args {
+  const float* S;
+  float* carry; float* dz;
+  const void* dxc0; const void* dxc1;
+  void* dx; long long dxb, dxv;
+  const void* hprev; long long hb, hv;
+  const void* zr; const void* lg;
+  void* dpre_g; void* dlin_g;
+  const void* dH; long long db, dv;
+  const void* z1;
+  const void* hprev1; long long hb1, hv1;
+  const void* hc1; const void* lu1;
+  void* dpre_u; void* dlin_u;
+  int mode, dx_accum, do_bwd1, B, V, Din, H, Cp;
+} fmm_cell_bwd_args;
+int fmm_tg_cell_fwd(const fmm_cell_fwd_args* args, int dtype, cudaStream_t stream);
+int fmm_tg_cell_bwd(const fmm_cell_bwd_args* args, int dtype, cudaStream_t stream);
+
 /* Time-axis attention pieces (TA.py:55-68): in-place row softmax over the first L of Lp entries (+ backward,
  * written over dp), LayerNorm over C of (a + b) with saved mean/rstd (+ backward; dgamma/dbeta accumulate),
  * positional encoding add, ReLU mask. */

@@ -46,7 +46,7 @@ def timeit(fn, n):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n, (time.perf_counter() - t0) * 1e3 / n
 
-step(x, tgt)
+print("first losses", [round(step(x, tgt).item(), 4) for _ in range(4)])
 l0 = _lib.launch_count
 step(x, tgt)
 print("launches/step", _lib.launch_count - l0, "peak mem GB", torch.cuda.max_memory_allocated() / 2**30)

@@ -139,7 +139,7 @@ def test_targcn_hidden_states_and_input_grad_vs_oracle():
         cur = x.to(dev)
         for i, cell in enumerate(m.encoder.dcrnn_cells):
             Cp = (cell.dim_in + cell.hidden_dim + 1 + 7) // 8 * 8
-            cur = _GraphGRUScan.apply(cur.contiguous(), S, cell.gate.stage_weights(E, Cp), cell.update.stage_weights(E, Cp))
+            cur = _GraphGRUScan.apply(cur.contiguous(), S, cell.gate.stage_weights(E, Cp, cell.hidden_dim), cell.update.stage_weights(E, Cp, cell.hidden_dim))
             err = (cur.cpu().double() - col[f"scan{i}"]).abs().max().item() / col[f"scan{i}"].abs().max().item()
             assert err < 2e-5, (i, err)
         out = m.encoder.trans_layer_T(cur)

@@ -3,7 +3,8 @@ classifiers of musaru/Fall_Multimodal, behind the reference's PyTorch module API
 from .graph import Graph, register_layout  # noqa: F401
 from .stgcan import STGCAN, Channel_Attention, GraphConvolution, st_gcan  # noqa: F401
 from .sensor import CNN1D, BiLSTM, ChannelAttention, CNN_BiLSTM  # noqa: F401
+from .tragcn import TARGCN  # noqa: F401
 from .fusion import ThreeStreamSTGCAN, TwoStreamSTGCAN, TwoStreamSTGCAN_CNN1D, TwoStreamSTGCAN_BiLSTM  # noqa: F401
 
 __all__ = ["Graph", "register_layout", "STGCAN", "st_gcan", "GraphConvolution", "Channel_Attention", "CNN1D",
-           "TwoStreamSTGCAN", "TwoStreamSTGCAN_CNN1D", "TwoStreamSTGCAN_BiLSTM", "ThreeStreamSTGCAN", "BiLSTM", "ChannelAttention", "CNN_BiLSTM"]
+           "TwoStreamSTGCAN", "TwoStreamSTGCAN_CNN1D", "TwoStreamSTGCAN_BiLSTM", "ThreeStreamSTGCAN", "BiLSTM", "ChannelAttention", "CNN_BiLSTM", "TARGCN"]

@@ -32,15 +32,17 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int N, int iters, int
   const bool converged = (distinct_acc & 16) != 0;
   const bool leader = (threadIdx.x & 31) == 0;
   if ((distinct_acc & 32) && warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(N, 0, 0);
-    const uint32_t a_lo0 = desc_lo(base, 16), b_lo0 = desc_lo(base + 16384, 16), hi = desc_hi(1024);
+    const uint32_t idesc = make_idesc_bf16(N, a_mn, b_mn);
+    const uint32_t a_lo0 = a_mn ? desc_lo(base, 8192) : desc_lo(base, 16);
+    const uint32_t b_lo0 = b_mn ? desc_lo(base + 16384, 8192) : desc_lo(base + 16384, 16), hi = desc_hi(1024);
+    const uint32_t a_st = a_mn ? (2048u >> 4) : 2u, b_st = b_mn ? (2048u >> 4) : 2u;
     const long long t0 = clock64();
     for (int i = 0; i < iters; i += 4) {
       if (distinct_acc & 8) (void)mbar_try_wait(smem_u32(&bar2), 1);
       if (distinct_acc & 2) tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (uint32_t kk = 0; kk < 4; ++kk) umma_bf16_lh(tmem_base, a_lo0 + kk * 2u, hi, b_lo0 + kk * 2u, hi, idesc, (i | kk) ? 1u : 0u);
+        for (uint32_t kk = 0; kk < 4; ++kk) umma_bf16_lh(tmem_base, a_lo0 + kk * a_st, hi, b_lo0 + kk * b_st, hi, idesc, (i | kk) ? 1u : 0u);
         if (distinct_acc & 4) umma_commit(smem_u32(&bar3));
       }
       __syncwarp();

@@ -297,13 +297,15 @@ class TrunkEngine:
 
             # ---- temporal conv: wgrad + dgrad ----
             Wt = P[pre + "tcn.2.weight"]
-            dWt = arena.f32(Cout, Cout, 9, 1)
+            # accumulated as [tap][co][ci] (input channel contiguous: the 32 lanes of an atomic land in one line),
+            # handed to autograd as the (co, ci, tap, 1) view of that buffer
+            dWs = arena.f32(9, Cout, Cout)
             if b["H"] is not None:
-                wgrad_async(b["H"], dU, dWt, shifts=list(range(-4, 5)), istride=s, s_m=1, s_c2=9, s_co=Cout * 9)
+                wgrad_async(b["H"], dU, dWs, shifts=list(range(-4, 5)), istride=s, s_m=Cout * Cout, s_c2=1, s_co=Cout)
             else:
-                wgrad_async(G, dU, dWt, shifts=list(range(-4, 5)), istride=s, in_scale=b["a1"], in_shift=b["b1"],
-                            in_relu=True, s_m=1, s_c2=9, s_co=Cout * 9)
-            grads[pre + "tcn.2.weight"] = dWt
+                wgrad_async(G, dU, dWs, shifts=list(range(-4, 5)), istride=s, in_scale=b["a1"], in_shift=b["b1"],
+                            in_relu=True, s_m=Cout * Cout, s_c2=1, s_co=Cout)
+            grads[pre + "tcn.2.weight"] = dWs.permute(1, 2, 0).unsqueeze(-1)
             dH = torch.empty_like(G)
             if s == 1:
                 pw = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, 9, 0, Cout * 9, 1, list(range(9)), dt)

@@ -28,14 +28,14 @@ def err_word(device: torch.device) -> torch.Tensor:
 profile = None
 
 
-def _timed(kind, flops, fn):
+def _timed(kind, flops, nbytes, fn):
     if profile is None:
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     out = fn()
     e1.record()
-    profile.append((kind, flops, e0, e1))
+    profile.append((kind, flops, nbytes, e0, e1))
     return out
 
 
@@ -86,7 +86,9 @@ def tapconv(x: torch.Tensor, pw: PackedWeight, out: torch.Tensor, *, shifts, tj:
         L.check(st, "tapconv")
         return out
 
-    return _timed("tapconv", 2.0 * N * V * tj * Cin * Cout * len(shifts), run)
+    # multi-tap launches are tensor-pipe bound, the 1x1 channel mixes stream activations (HBM bound)
+    return _timed("tapconv_taps" if len(shifts) > 1 else "tapconv_1x1", 2.0 * N * V * tj * Cin * Cout * len(shifts),
+                  float(x.numel() + N * tj * V * Cout) * x.element_size(), run)
 
 
 def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, shifts, istride: int = 1,
@@ -112,7 +114,8 @@ def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, shifts, istrid
         L.check(st, "wgrad")
         return dw
 
-    return _timed("wgrad", 2.0 * N * V * Tj * Cin * Cout * len(shifts), run)
+    return _timed("wgrad_taps" if len(shifts) > 1 else "wgrad_1x1", 2.0 * N * V * Tj * Cin * Cout * len(shifts),
+                  float(x.numel() + dy.numel()) * x.element_size(), run)
 
 
 # ---------------------------------------------------------------------------------------------

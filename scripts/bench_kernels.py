@@ -46,7 +46,8 @@ def wg(name, T, Cin, Cout, ntaps, stride, prologue):
     sc = torch.rand(Cin, device=dev) + 0.5 if prologue else None
     sh = torch.randn(Cin, device=dev) if prologue else None
     sh_ = list(range(-(ntaps // 2), ntaps // 2 + 1))
-    f = lambda: ops.wgrad(x, dy, dw, shifts=sh_, istride=stride, in_scale=sc, in_shift=sh, in_relu=prologue, s_m=1, s_c2=ntaps, s_co=Cin * ntaps)
+    # dw is accumulated as [tap][co][ci] (ci contiguous), like engine.py does
+    f = lambda: ops.wgrad(x, dy, dw, shifts=sh_, istride=stride, in_scale=sc, in_shift=sh, in_relu=prologue, s_m=Cout * Cin, s_c2=1, s_co=Cin)
     best, med = timeit(f)
     fl = 2.0 * N * V * To * Cin * Cout * ntaps
     byt = (x.numel() + dy.numel()) * 2

@@ -11,3 +11,11 @@ for N in (64, 256):
         torch.cuda.synchronize()
         i, t = out.tolist()
         print(f"N={N:3d} {nm:28s}: issue {i/2000:6.1f} cyc/MMA, issue+drain {t/2000:6.1f} cyc/MMA  (floor {128*N/256:.0f})")
+
+print("operand majorness (lean issue path): a_mn / b_mn = 1 means MN-major (the weight-gradient engine's layout)")
+for N in (64, 128, 256):
+    for a_mn, b_mn in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        lib.fmm_debug_mma_probe(N, 2000, a_mn, b_mn, 32, 148, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        i, t = out.tolist()
+        print(f"N={N:3d} a_mn={a_mn} b_mn={b_mn}: issue {i/2000:6.1f} cyc/MMA, issue+drain {t/2000:6.1f} cyc/MMA  (floor {128*N/256:.0f})")

@@ -55,3 +55,6 @@ tap("P_b1", 64, 64, 192, 1, 1, False)
 wg("tcn_wgrad_b1", 64, 64, 64, 9, 1, True)
 wg("tcn_wgrad_b6", 16, 256, 256, 9, 1, True)
 wg("gcn_wgrad_b1", 64, 192, 64, 1, 1, False)
+wg("tcn_wgrad_b1 (plain cp.async)", 64, 64, 64, 9, 1, False)
+wg("tcn_wgrad_b4 (plain cp.async)", 32, 128, 128, 9, 1, False)
+wg("tcn_wgrad_b6 (plain cp.async)", 16, 256, 256, 9, 1, False)

@@ -190,6 +190,28 @@ def main_tragcn():
                    os.path.join(OUT, name + ".pt"))
         print(name, "loss", float(loss), "params", sum(p.numel() for p in mod.parameters()))
 
+    # the reference's own bf16 path (MF3/main.py:97 torch.amp.autocast) on CPU: the yardstick for the bf16 gate
+    c = dict(V=25, T=16, B=8, fill_seed=2, batch_seed=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        M = ref_import.load_tragcn(c["T"])
+        mod = M.TARGCN(num_nodes=c["V"], adj=None)
+    shapes = {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+    mod.load_state_dict(TO.fill_targcn(shapes, c["fill_seed"]))
+    x, tgt = TO.synthetic_clips(c["B"], c["T"], c["V"], seed=c["batch_seed"])
+    mod.train()
+    mod.zero_grad()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            logits = mod(x)
+            loss = torch.nn.CrossEntropyLoss()(logits.float(), tgt)
+    loss.backward()
+    grads = {k: summarize(p.grad, k) for k, p in mod.named_parameters() if p.grad is not None}
+    torch.save({"config": c, "shapes": shapes, "logits": logits.detach().float().clone(), "loss": float(loss.detach()),
+                "grads": grads}, os.path.join(OUT, "targcn_v25_t16_autocast.pt"))
+    print("targcn_v25_t16_autocast loss", float(loss.detach()))
+
 
 if __name__ == "__main__":
     if sys.argv[1:] == ["tragcn"]:

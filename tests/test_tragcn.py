@@ -148,29 +148,54 @@ def test_targcn_hidden_states_and_input_grad_vs_oracle():
         assert (m(x.to(dev)).cpu().double() - ref).abs().max().item() / ref.abs().max().item() < 5e-5
 
 
+def _summary_err(got, ref_summary, truth, floor):
+    """(error of ``got``, error of the fixture values) against the fp64 ``truth`` at the fixture's sample points."""
+    t = truth.detach().double().flatten().cpu()
+    g = got.detach().double().flatten().cpu()
+    if "full" in ref_summary:
+        r = ref_summary["full"].double().flatten()
+        idx = slice(None)
+    else:
+        idx = ref_summary["idx"]
+        r = ref_summary["vals"].double()
+    scale = max(t.abs().max().item(), floor)
+    return (g[idx] - t[idx]).abs().max().item() / scale, (r - t[idx]).abs().max().item() / scale
+
+
 @gpu
-def test_targcn_bf16_autocast_close_to_fp32():
+def test_targcn_bf16_no_worse_than_reference_autocast():
+    """bf16 gate: the reference's own autocast path (fixture from the unmodified modules, MF3/main.py:97) is far
+    from fp32 on this recurrent model (logits ~0.7 of the max off, gradients 0.14 median) — ours must be at least
+    as close to the fp64 truth, tensor by tensor (median) and in the worst case."""
+    import statistics
+    fx = load("targcn_v25_t16_autocast")
+    c = fx["config"]
     dev = _dev()
-    c = dict(V=25, T=16, B=8, fill_seed=2)
     m = _build(c, None, dev)
-    x, tgt = TO.synthetic_clips(c["B"], c["T"], c["V"], seed=5)
-    x, tgt = x.to(dev), tgt.to(dev)
-    ref = m(x)
-    torch.nn.CrossEntropyLoss()(ref, tgt).backward()
-    g32 = {k: p.grad.clone() for k, p in m.named_parameters()}
-    m.zero_grad()
+    x, tgt = TO.synthetic_clips(c["B"], c["T"], c["V"], seed=c["batch_seed"])
+    sd = {k: v.detach().cpu().double().requires_grad_(not k.endswith("PE.pe")) for k, v in m.state_dict().items()}
+    truth = TO.targcn_forward(sd, x.double())
+    torch.nn.CrossEntropyLoss()(truth, tgt.double()).backward()
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        out = m(x)
-        loss = torch.nn.CrossEntropyLoss()(out.float(), tgt)
+        out = m(x.to(dev))
+        loss = torch.nn.CrossEntropyLoss()(out.float(), tgt.to(dev))
     assert out.dtype == torch.bfloat16
     loss.backward()
-    assert (out.float() - ref).abs().max().item() / ref.abs().max().item() < 5e-2
-    bad = []
+    tmax = truth.abs().max().item()
+    e_ours = (out.double().cpu() - truth).abs().max().item() / tmax
+    e_ref = (fx["logits"].double() - truth).abs().max().item() / tmax
+    print(f"logits: ours {e_ours:.3e}, reference autocast {e_ref:.3e}")
+    assert e_ours <= max(1.1 * e_ref, 2e-2)
+    gs = max(v.grad.abs().max().item() for v in sd.values() if v.grad is not None)
+    ours, ref = [], []
     for k, p in m.named_parameters():
-        e = (p.grad - g32[k]).abs().max().item() / max(g32[k].abs().max().item(), 1e-3 * max(v.abs().max().item() for v in g32.values()))
-        if e > 0.15:
-            bad.append((k, e))
-    assert not bad, bad
+        a, b = _summary_err(p.grad, fx["grads"][k], sd[k].grad, 1e-3 * gs)
+        ours.append(a)
+        ref.append(b)
+    print(f"grads: median ours {statistics.median(ours):.3e} / ref {statistics.median(ref):.3e}; "
+          f"worst ours {max(ours):.3e} / ref {max(ref):.3e}")
+    assert statistics.median(ours) <= 1.1 * statistics.median(ref)
+    assert max(ours) <= 1.25 * max(ref)
 
 
 @gpu

@@ -53,7 +53,9 @@ def oracle_with_masks(m, fx, skel, target, dev):
     masks = []
     for i in range(7):
         b = m._engine.debug[i]["saved"]
-        mh = (b["a1"] * b["G"].float() + b["b1"]) > 0
+        # the kernels decide with fmaf(a1, G, b1) > 0 (one rounding): take the sign of the exact fp64 value, a
+        # separately rounded product can land on the other side of zero for a pre-activation within one ulp
+        mh = (b["a1"].double() * b["G"].double() + b["b1"].double()) > 0
         masks.append(mh.permute(0, 3, 1, 2))
         masks.append((b["Y"].float() > 0).permute(0, 3, 1, 2))
     out = O.stgcan_forward(sd, skel.double(), training=True, masks=masks)

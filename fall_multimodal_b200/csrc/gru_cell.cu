@@ -56,14 +56,29 @@ __device__ __forceinline__ float rnd(float v) { return to_f32(from_f32<T>(v)); }
 
 __device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) { load8(p, f); }
 
-// S.cat for 8 channels of joint n; cat in shared memory [V][Cp]
-__device__ __forceinline__ void mix8(const float* Ss, const float* cat, int V, int Cp, int n, int c0, float (&acc)[8]) {
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+// Shared-memory rows are stored "split": the 8 channels of group g live as two float4, the low half at
+// [g*4] and the high half at [Cp/2 + g*4], so that the float4 reads of consecutive lanes (consecutive
+// groups) are 16 bytes apart and bank-conflict free (8 contiguous floats per lane would be a 2-way conflict).
+__device__ __forceinline__ int split_idx(int Cp, int c) { return ((c & 4) ? (Cp >> 1) : 0) + ((c >> 3) << 2) + (c & 3); }
+__device__ __forceinline__ void sm_st8(float* row, int Cp, int c0, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(&row[(c0 >> 3) << 2]) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(&row[(Cp >> 1) + ((c0 >> 3) << 2)]) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void sm_ld8(const float* row, int Cp, int c0, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(&row[(c0 >> 3) << 2]);
+  const float4 b = *reinterpret_cast<const float4*>(&row[(Cp >> 1) + ((c0 >> 3) << 2)]);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// acc[0..7] += sum_m coef(m) * rows[m][c0..c0+7]; coef(m) = Ss[n*V+m] (forward, S.cat) or Ss[m*V+n] (backward, S^T.d)
+template <bool kTransposed>
+__device__ __forceinline__ void mix8(const float* Ss, const float* rows, int V, int Cp, int n, int c0, float (&acc)[8]) {
+  const int g4 = (c0 >> 3) << 2, hi = Cp >> 1;
   for (int m = 0; m < V; ++m) {
-    const float s = Ss[n * V + m];
-    const float4 a = *reinterpret_cast<const float4*>(&cat[m * Cp + c0]);
-    const float4 b = *reinterpret_cast<const float4*>(&cat[m * Cp + c0 + 4]);
+    const float s = kTransposed ? Ss[m * V + n] : Ss[n * V + m];
+    const float4 a = *reinterpret_cast<const float4*>(&rows[m * Cp + g4]);
+    const float4 b = *reinterpret_cast<const float4*>(&rows[m * Cp + hi + g4]);
     acc[0] += s * a.x; acc[1] += s * a.y; acc[2] += s * a.z; acc[3] += s * a.w;
     acc[4] += s * b.x; acc[5] += s * b.y; acc[6] += s * b.z; acc[7] += s * b.w;
   }
@@ -89,7 +104,7 @@ __global__ void __launch_bounds__(512) cell_fwd_kernel(const CellFwdArgs p) {
       else
 #pragma unroll
         for (int e = 0; e < 8; ++e) h[e] = 0.f;
-      store8(&cat[m * Cp + j], h);
+      sm_st8(&cat[m * Cp], Cp, j, h);
     }
   } else if (p.mode == 1) {
     T* zr = reinterpret_cast<T*>(p.zr);
@@ -114,7 +129,7 @@ __global__ void __launch_bounds__(512) cell_fwd_kernel(const CellFwdArgs p) {
           for (int e = 0; e < 8; ++e) h[e] = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) h[e] = rnd<T>(rnd<T>(g[e]) * h[e]);  // r*state is a rounded tensor in the reference
-        store8(&cat[m * Cp + j], h);
+        sm_st8(&cat[m * Cp], Cp, j, h);
       }
     }
   } else {
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(512) cell_fwd_kernel(const CellFwdArgs p) {
       store8(hc + row * H + j, c2);
       store8(lu + row * H + j, li);
       store8(hout + b * p.ob + m * p.ov + j, h);
-      if (want_cat) store8(&cat[m * Cp + j], h);
+      if (want_cat) sm_st8(&cat[m * Cp], Cp, j, h);
     }
   }
   if (!want_cat) return;
@@ -159,7 +174,7 @@ __global__ void __launch_bounds__(512) cell_fwd_kernel(const CellFwdArgs p) {
         else
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = (c8 == D8 && e == 0) ? 1.f : 0.f;
-        store8(&cat[m * Cp + H + c8 * 8], v);
+        sm_st8(&cat[m * Cp], Cp, H + c8 * 8, v);
       }
     } else {
       for (int i = threadIdx.x; i < V * W; i += blockDim.x) {
@@ -167,7 +182,7 @@ __global__ void __launch_bounds__(512) cell_fwd_kernel(const CellFwdArgs p) {
         float v = 0.f;
         if (c < Din) v = to_f32(x[b * p.xb + m * p.xv + c]);
         else if (c == Din) v = 1.f;
-        cat[m * Cp + H + c] = v;
+        cat[m * Cp + split_idx(Cp, H + c)] = v;
       }
     }
   }
@@ -178,9 +193,9 @@ __global__ void __launch_bounds__(512) cell_fwd_kernel(const CellFwdArgs p) {
   const long long ob = (long long)b * V * Cp;
   for (int it = threadIdx.x; it < V * Cp8; it += blockDim.x) {
     const int n = it / Cp8, c0 = (it % Cp8) * 8;
-    float acc[8], own[8];
-    mix8(Ss, cat, V, Cp, n, c0, acc);
-    ld8f(&cat[n * Cp + c0], own);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, own[8];
+    mix8<false>(Ss, cat, V, Cp, n, c0, acc);
+    sm_ld8(&cat[n * Cp], Cp, c0, own);
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       if (c0 + e >= Cin) acc[e] = own[e];  // bias column and pad are not mixed
@@ -243,7 +258,7 @@ __global__ void __launch_bounds__(512) cell_bwd_kernel(const CellBwdArgs p) {
   for (int it = threadIdx.x; it < V * Cp8; it += blockDim.x) {
     float v[8];
     load8(dxc0 + ob + it * 8, v);
-    store8(&d0[it * 8], v);
+    sm_st8(&d0[(it / Cp8) * Cp], Cp, (it % Cp8) * 8, v);
   }
   __syncthreads();
   for (int it = threadIdx.x; it < V * Cp8; it += blockDim.x) {
@@ -251,13 +266,7 @@ __global__ void __launch_bounds__(512) cell_bwd_kernel(const CellBwdArgs p) {
     if (c0 >= H + Din) continue;  // bias column / pad only
     float acc[8];
     load8(dxc1 + ob + m * Cp + c0, acc);
-    for (int n = 0; n < V; ++n) {
-      const float s = Ss[n * V + m];
-      const float4 a = *reinterpret_cast<const float4*>(&d0[n * Cp + c0]);
-      const float4 c = *reinterpret_cast<const float4*>(&d0[n * Cp + c0 + 4]);
-      acc[0] += s * a.x; acc[1] += s * a.y; acc[2] += s * a.z; acc[3] += s * a.w;
-      acc[4] += s * c.x; acc[5] += s * c.y; acc[6] += s * c.z; acc[7] += s * c.w;
-    }
+    mix8<true>(Ss, d0, V, Cp, m, c0, acc);
     if (c0 >= H) {  // x part
       if (p.dx) {
         T* dx = reinterpret_cast<T*>(p.dx) + b * p.dxb + m * p.dxv;

@@ -244,6 +244,22 @@ def _rows(x):
     return x.numel() // x.shape[-1]
 
 
+def _colsum(dy):
+    """Per-channel sum over all rows of a contiguous (.., C) tensor (bias gradients) -> fp32 (C,)."""
+    from . import ops
+    Cc = dy.shape[-1]
+    if dy.dim() == 4 and Cc % 8 == 0 and dy.shape[0] <= 65535:
+        st = torch.zeros(2 * ops.NREP * Cc, dtype=torch.float64, device=dy.device)
+        ops.colstats(dy, st[:ops.NREP * Cc], st[ops.NREP * Cc:])
+        return st[:ops.NREP * Cc].view(ops.NREP, Cc).sum(0).float()
+    R = _rows(dy)
+    db = torch.zeros(Cc, dtype=torch.float32, device=dy.device)
+    one = torch.ones(8, dtype=dy.dtype, device=dy.device)
+    bgemm(one, 0, (0, 0, 0, 0, 0, 0), dy, 0, (0, 0, 1, Cc, 0, 0), db, 0, (0, 0, 0, 1), (1, 1), 1, Cc, (R, 1, 1),
+          splitk=_splitk(1, Cc, 1, R))
+    return db
+
+
 class _Linear(Function):
     """y = x W^T + b over the last axis (optionally ReLU'd); W (Nout,Kin) / b fp32 parameters."""
 
@@ -278,12 +294,7 @@ class _Linear(Function):
             dW = torch.zeros(Nout, Kin, dtype=torch.float32, device=x.device)
             bgemm(dy, 0, (0, 0, 1, Nout, 0, 0), x, 0, (0, 0, 1, Kin, 0, 0), dW, 0, (0, 0, Kin, 1), (1, 1), Nout, Kin,
                   (R, 1, 1), splitk=_splitk(Nout, Kin, 1, R))
-            db = None
-            if ctx.has_bias:
-                db = torch.zeros(Nout, dtype=torch.float32, device=x.device)
-                one = torch.ones(8, dtype=x.dtype, device=x.device)
-                bgemm(one, 0, (0, 0, 0, 0, 0, 0), dy, 0, (0, 0, 1, Nout, 0, 0), db, 0, (0, 0, 0, 1), (1, 1), 1, Nout,
-                      (R, 1, 1), splitk=_splitk(1, Nout, 1, R))
+            db = _colsum(dy) if ctx.has_bias else None
         return dx, dW, db, None, None
 
 
@@ -445,10 +456,7 @@ class _ValueProj(Function):
             # rows of dv are (b,v,t), rows of x are (b,t,v): contract over the three levels explicitly
             bgemm(dv, 0, (0, 0, 1, V * T * Cc, T * Cc, Cc), x, 0, (0, 0, 1, T * V * Cc, Cc, V * Cc), dW, 0, (0, 0, Cc, 1),
                   (1, 1), Cc, Cc, (B, V, T), splitk=_splitk(Cc, Cc, 1, R))
-            db = torch.zeros(Cc, dtype=torch.float32, device=x.device)
-            one = torch.ones(8, dtype=x.dtype, device=x.device)
-            bgemm(one, 0, (0, 0, 0, 0, 0, 0), dv, 0, (0, 0, 1, Cc, 0, 0), db, 0, (0, 0, 0, 1), (1, 1), 1, Cc, (R, 1, 1),
-                  splitk=_splitk(1, Cc, 1, R))
+            db = _colsum(dv)
         return dx, dW, db
 
 

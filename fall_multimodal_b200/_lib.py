@@ -117,9 +117,6 @@ _SIGNATURES = {
     "fmm_conv1d_k5_bwd": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
     "fmm_wgrad": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                   C.POINTER(c_int), c_int, c_ll, c_ll, c_ll, c_ll, c_int, _P, _P],
-    "fmm_smallc_fwd": [_P, _P, _P, _P, c_int, c_ll, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, _P],
-    "fmm_smallc_dgrad": [_P, _P, _P, c_ll, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, _P],
-    "fmm_smallc_wgrad": [_P, _P, _P, c_ll, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, _P],
     "fmm_bgemm": [_P, _P],
     "fmm_tg_cell_fwd": [_P, c_int, _P],
     "fmm_tg_cell_bwd": [_P, c_int, _P],

@@ -126,13 +126,9 @@ class TrunkEngine:
             Wg = P[pre + "gcn.conv.weight"]
             Xa = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
             ops.agg_fwd(x, Xa, csr["fwd_rowptr"], csr["fwd_src"], coef_f, K)
+            pw_g = ops.tapconv_pack(Wg, Cout, K * Cin, Cout, Cin, 0, Cin, Cout * Cin, 1, 0, [0], dt)
             G = torch.empty(N, T, V, Cout, dtype=dt, device=dev)
-            if ops.smallc_ok(K * Cin, Cout):
-                # first block: 9 / 6 aggregated input channels, a streaming CUDA-core kernel (csrc/smallc.cu)
-                ops.smallc_fwd(Xa, Wg, G, Cin, Cin, Cout * Cin, 1, bias=bias_eff, bias_per_joint=True)
-            else:
-                pw_g = ops.tapconv_pack(Wg, Cout, K * Cin, Cout, Cin, 0, Cin, Cout * Cin, 1, 0, [0], dt)
-                ops.tapconv(Xa, pw_g, G, shifts=[0], tj=T, bias=bias_eff, bias_per_joint=True)
+            ops.tapconv(Xa, pw_g, G, shifts=[0], tj=T, bias=bias_eff, bias_per_joint=True)
 
             # BN1 statistics (stgcan.py:112), applied inside the temporal conv's prologue
             a1, b1, mean1, rstd1 = (torch.empty(Cout, dtype=torch.float32, device=dev) for _ in range(4))
@@ -336,19 +332,12 @@ class TrunkEngine:
             # ---- graph conv: wgrad, bias, dgrad through the weights, edge importance ----
             Wg = P[pre + "gcn.conv.weight"]
             dWg = arena.f32(K * Cout, Cin, 1, 1)
-            small = ops.smallc_ok(K * Cin, Cout)
-            if small:
-                ops.smallc_wgrad(Xa, dG, dWg, Cin, Cin, Cout * Cin, 1)
-            else:
-                wgrad_async(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
+            wgrad_async(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
             grads[pre + "gcn.conv.weight"] = dWg
             grads[pre + "gcn.conv.bias"] = (b["colsum"] @ Tbl).flatten()
+            pw_gT = ops.tapconv_pack(Wg, K * Cin, Cout, Cin, Cout, Cout * Cin, 1, 0, Cin, 0, [0], dt)
             Pm = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
-            if small:
-                ops.smallc_dgrad(dG, Wg, Pm, Cin, Cin, Cout * Cin, 1)
-            else:
-                pw_gT = ops.tapconv_pack(Wg, K * Cin, Cout, Cin, Cout, Cout * Cin, 1, 0, Cin, 0, [0], dt)
-                ops.tapconv(dG, pw_gT, Pm, shifts=[0], tj=T)
+            ops.tapconv(dG, pw_gT, Pm, shifts=[0], tj=T)
             dcoef = arena.f32(self.E)
             fused_dcoef = Cin % 8 == 0
             if not fused_dcoef:

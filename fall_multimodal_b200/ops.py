@@ -91,42 +91,6 @@ def tapconv(x: torch.Tensor, pw: PackedWeight, out: torch.Tensor, *, shifts, tj:
                   float(x.numel() + N * tj * V * Cout) * x.element_size(), run)
 
 
-def smallc_ok(ck: int, cw: int) -> bool:
-    """Shapes served by the narrow-side CUDA-core kernels (csrc/smallc.cu)."""
-    c8 = cw // 8
-    return ck <= 16 and cw % 8 == 0 and 1 <= c8 <= 32 and (c8 & (c8 - 1)) == 0
-
-
-def smallc_fwd(x, w, out, k2, s_co, s_k1, s_k2, bias=None, bias_per_joint=False):
-    """out[n,t,v,co] = bias[v][co] + sum_k x[n,t,v,k] * w[co*s_co + (k//k2)*s_k1 + (k%k2)*s_k2]  (narrow x)."""
-    N, Tn, V, Ck = _shape4(x)
-    Cw = out.shape[-1]
-    assert x.is_contiguous() and out.is_contiguous() and w.dtype == torch.float32 and x.dtype == out.dtype
-    L.check(L.load().fmm_smallc_fwd(L.ptr(x), L.ptr(out), L.ptr(w), L.ptr(bias), int(bias_per_joint), N * Tn * V, V, Ck, Cw,
-                                    k2, s_co, s_k1, s_k2, L.dt_of(x.dtype), L.stream()), "smallc_fwd")
-    return out
-
-
-def smallc_dgrad(dy, w, pout, k2, s_co, s_k1, s_k2):
-    """pout[n,t,v,k] = sum_co dy[n,t,v,co] * w[co, k]  (narrow output)."""
-    N, Tn, V, Cw = _shape4(dy)
-    Ck = pout.shape[-1]
-    assert dy.is_contiguous() and pout.is_contiguous() and w.dtype == torch.float32 and dy.dtype == pout.dtype
-    L.check(L.load().fmm_smallc_dgrad(L.ptr(dy), L.ptr(pout), L.ptr(w), N * Tn * V, Ck, Cw, k2, s_co, s_k1, s_k2,
-                                      L.dt_of(dy.dtype), L.stream()), "smallc_dgrad")
-    return pout
-
-
-def smallc_wgrad(x, dy, dw, k2, s_co, s_k1, s_k2):
-    """dw[co, k] += sum_rows dy[.., co] * x[.., k]  (fp32 atomics into a zeroed buffer addressed like the weight)."""
-    N, Tn, V, Ck = _shape4(x)
-    Cw = dy.shape[-1]
-    assert x.is_contiguous() and dy.is_contiguous() and dw.dtype == torch.float32 and x.dtype == dy.dtype
-    L.check(L.load().fmm_smallc_wgrad(L.ptr(x), L.ptr(dy), L.ptr(dw), N * Tn * V, Ck, Cw, k2, s_co, s_k1, s_k2,
-                                      L.dt_of(x.dtype), L.stream()), "smallc_wgrad")
-    return dw
-
-
 def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, shifts, istride: int = 1,
           in_scale=None, in_shift=None, in_relu: bool = False, c2: int | None = None,
           s_m: int, s_c1: int = 0, s_c2: int, s_co: int) -> torch.Tensor:

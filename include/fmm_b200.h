@@ -156,21 +156,6 @@ int fmm_lstm_bwd(const float* x, const float* w_ih, const float* w_hh, const flo
                  int T, int I, int H, int ndir, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * 1x1 channel mixes with a narrow side of <= 16 channels (first GSTCAN block: K*in_channels = 9 / 6 aggregated
- * input channels, stgcan.py:50-56), CUDA-core kernels that stream the wide tensor once. rows = N*T*V; the weight
- * element (co, k) lives at w[co*s_co + (k/K2)*s_k1 + (k%K2)*s_k2] (the k-major graph-conv weight, no repacking).
- *  smallc_fwd  : out[r][co] = bias[v][co] + sum_k x[r][k] W[co][k]       x [rows][Ck], out [rows][Cw]
- *  smallc_dgrad: p[r][k]    = sum_co dy[r][co] W[co][k]
- *  smallc_wgrad: dw[co][k] += sum_r dy[r][co] x[r][k]                    (fp32 atomics, zero dw first)
- * ------------------------------------------------------------------------------------------- */
-int fmm_smallc_fwd(const void* x, void* out, const float* w, const float* bias, int bias_per_joint, long long rows, int V,
-                   int Ck, int Cw, int K2, long long s_co, long long s_k1, long long s_k2, int dtype, cudaStream_t stream);
-int fmm_smallc_dgrad(const void* dy, void* p, const float* w, long long rows, int Ck, int Cw, int K2, long long s_co,
-                     long long s_k1, long long s_k2, int dtype, cudaStream_t stream);
-int fmm_smallc_wgrad(const void* x, const void* dy, float* dw, long long rows, int Ck, int Cw, int K2, long long s_co,
-                     long long s_k1, long long s_k2, int dtype, cudaStream_t stream);
-
-/* ---------------------------------------------------------------------------------------------
  * TRAGCN family (EmbGCN.py:59-89, GRU.py:17-26, TRAGCN.py:150-224, TA.py:40-108).
  *
  * fmm_bgemm: strided batched GEMM  C[g1,g2][m][n] = act(alpha * sum_k A[g1,g2][m][k] B[g1,g2][k][n]

@@ -57,6 +57,8 @@ tap("tcn_fwd_b1", 64, 64, 64, 9, 1, True)
 tap("tcn_fwd_b3", 64, 128, 128, 9, 2, True)   # (approx: block 3 has Cin=Cout=128 for the tcn)
 tap("tcn_fwd_b4", 32, 128, 128, 9, 1, True)
 tap("tcn_fwd_b6", 16, 256, 256, 9, 1, True)
+tap("tcn_plain_b6", 16, 256, 256, 9, 1, False)     # what the engine runs: relu(bn1(G)) is materialised, plain cp.async window
+tap("tcn_plain_b4", 32, 128, 128, 9, 1, False)
 tap("tcn_dgrad_b1", 64, 64, 64, 9, 1, False)
 tap("gcn_fwd_b1", 64, 192, 64, 1, 1, False)
 tap("gcn_fwd_b4", 32, 384, 128, 1, 1, False)
@@ -68,6 +70,8 @@ wg("tcn_wgrad_b1", 64, 64, 64, 9, 1, True)
 wg("tcn_wgrad_b4", 32, 128, 128, 9, 1, True)
 wg("tcn_wgrad_b5", 32, 256, 256, 9, 2, True)
 wg("tcn_wgrad_b6", 16, 256, 256, 9, 1, True)
+wg("tcn_wgrad_plain_b6", 16, 256, 256, 9, 1, False)
+wg("tcn_wgrad_plain_b4", 32, 128, 128, 9, 1, False)
 wg("gcn_wgrad_b1", 64, 192, 64, 1, 1, False)
 wg("gcn_wgrad_b6", 16, 768, 256, 1, 1, False)
 wg("res_wgrad_b3", 64, 64, 128, 1, 2, False)

@@ -47,7 +47,8 @@ struct TapConvParams {
   int nslots, nbstages;
   int MT;        // M=128 tiles per pipeline item (2: 32 positions x 8 columns share one window and every weight image)
   int tps;       // taps per streamed weight stage (one barrier round trip per `tps` taps)
-  int resident;  // 1: every weight image of the launch stays in shared memory for the CTA's lifetime
+  int resident;  // 1: the weight images stay in shared memory for the CTA's lifetime
+  int res_local; // resident && 1: only the images of the CTA's own N tile (gridDim.x is a multiple of ntiles_n)
   unsigned* err;
 };
 
@@ -339,9 +340,10 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       if (p.resident) {
         // all images once: one transaction barrier, one bulk copy per image
         if (first_tile < p.total_tiles) {
+          const size_t base = p.res_local ? static_cast<size_t>(first_tile % p.ntiles_n) * p.nbstages * bstage_bytes : 0;
           mbar_arrive_expect_tx(b_full(0), static_cast<uint32_t>(p.nbstages) * bstage_bytes);
           for (int i = 0; i < p.nbstages; ++i)
-            bulk_g2s(bst0 + i * bstage_bytes, W + static_cast<size_t>(i) * bstage_bytes, bstage_bytes, b_full(0));
+            bulk_g2s(bst0 + i * bstage_bytes, W + base + static_cast<size_t>(i) * bstage_bytes, bstage_bytes, b_full(0));
         }
       } else
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         const uint32_t img_lo = bstage_bytes >> 4;
         const uint32_t mt_lo = 16u * static_cast<uint32_t>(p.istride) * 64u;  // second M tile: 16 positions later
         for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
-          const int ntile = tile % p.ntiles_n;
+          const int ntile = p.res_local ? 0 : tile % p.ntiles_n;  // index into the resident images
           mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * acc_stride;
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         }
       } else
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
-        const int ntile = tile % p.ntiles_n;
+        const int ntile = p.res_local ? 0 : tile % p.ntiles_n;  // only used to index resident images
         mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * acc_stride;
@@ -665,10 +667,21 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   // round trips at all); otherwise stream them through as deep a ring as fits beside 4 slots.
   const int nimg = p.ntiles_n * p.nchunks * ntaps;
   int nb, ns;
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   p.resident = (nimg <= 96 && nimg * bstage_bytes + 3 * slot_bytes <= budget) ? 1 : 0;
+  p.res_local = 0;
+  // several N tiles whose images do not all fit: a CTA whose tiles all share one N tile (tile index = rows * ntiles_n
+  // + ntile, stride gridDim.x) keeps just that tile's images
+  const int nimg_tile = p.nchunks * ntaps;
+  if (!p.resident && p.ntiles_n > 1 && grid >= p.ntiles_n && nimg_tile <= 96 &&
+      nimg_tile * bstage_bytes + 3 * slot_bytes <= budget) {
+    p.resident = 1;
+    p.res_local = 1;
+    grid -= grid % p.ntiles_n;
+  }
   p.tps = 1;
   if (p.resident) {
-    nb = nimg;
+    nb = p.res_local ? nimg_tile : nimg;
     ns = static_cast<int>((budget - nb * bstage_bytes) / slot_bytes);
     if (ns > 8) ns = 8;  // more window slots = more cp.async bytes in flight (the 1x1 GEMMs are streaming kernels)
   } else {
@@ -689,7 +702,6 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   p.nslots = ns;
   p.nbstages = nb;
   const size_t smem = nb * bstage_bytes * p.tps + ns * slot_bytes + 1024 + 2048;
-  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   const bool wide = p.BN >= 128;
 #define FMM_LAUNCH_TAPCONV(TT, EPI)                                                                              \
   do {                                                                                                           \

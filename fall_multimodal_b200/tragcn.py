@@ -34,6 +34,19 @@ from .stgcan import _compute_dtype
 # ------------------------------------------------------------------------------------------------
 # raw kernel faces
 # ------------------------------------------------------------------------------------------------
+profile = None  # bench hook: while a list, every bgemm / cell kernel launch appends (kind, flops, bytes, event0, event1)
+
+
+def _timed(kind, flops, nbytes, fn):
+    if profile is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    profile.append((kind, flops, nbytes, e0, e1))
+
+
 def _addr(t: torch.Tensor, off: int = 0) -> int:
     return t.data_ptr() + off * t.element_size()
 
@@ -58,7 +71,10 @@ def bgemm(A, a_off, a_str, B, b_off, b_str, Cm, c_off, c_str, G, M, N, K, alpha=
     d.K1, d.K2, d.K3 = K
     d.alpha, d.beta, d.act, d.splitk = float(alpha), int(beta), int(act), int(splitk)
     d.dtype, d.c_dtype = L.dt_of(A.dtype), L.dt_of(Cm.dtype)
-    L.check(L.load().fmm_bgemm(C.byref(d), L.stream()), "bgemm")
+    Kt = K[0] * K[1] * K[2]
+    Gt = G[0] * G[1]
+    _timed("bgemm", 2.0 * Gt * M * N * Kt, float(Gt) * (M * Kt * A.element_size() + Kt * N * B.element_size() + M * N * Cm.element_size()),
+           lambda: L.check(L.load().fmm_bgemm(C.byref(d), L.stream()), "bgemm"))
 
 
 def _splitk(M, N, G, K):
@@ -96,7 +112,11 @@ def cell_fwd(mode, dims, S, x=None, hprev=None, pre=None, lin=None, zr=None, lg=
     a.mode = mode
     a.B, a.V, a.Din, a.H, a.Cp = dims
     ref = xc0 if xc0 is not None else hout
-    L.check(L.load().fmm_tg_cell_fwd(C.byref(a), _dt(ref), L.stream()), "tg_cell_fwd")
+    Bc, Vc, Din, H, Cp = dims
+    es = ref.element_size()
+    co = {0: 0, 1: 2 * H, 2: H}[mode]
+    nb = Bc * Vc * (2 * co * 4 + 2 * co * es + H * es + (H * es if mode == 2 else 0) + (Din * es + 2 * Cp * es if xc0 is not None else 0))
+    _timed("gru_cell", 0.0, float(nb), lambda: L.check(L.load().fmm_tg_cell_fwd(C.byref(a), _dt(ref), L.stream()), "tg_cell_fwd"))
 
 
 def cell_bwd(mode, dims, S, carry, dz, dt_ref, dxc0=None, dxc1=None, dx=None, dx_accum=False, hprev=None, zr=None, lg=None,
@@ -114,7 +134,10 @@ def cell_bwd(mode, dims, S, carry, dz, dt_ref, dxc0=None, dxc1=None, dx=None, dx
     a.hc1, a.lu1, a.dpre_u, a.dlin_u = _P(hc1), _P(lu1), _P(dpre_u), _P(dlin_u)
     a.mode, a.dx_accum, a.do_bwd1 = mode, int(dx_accum), int(do_bwd1)
     a.B, a.V, a.Din, a.H, a.Cp = dims
-    L.check(L.load().fmm_tg_cell_bwd(C.byref(a), L.dt_of(dt_ref), L.stream()), "tg_cell_bwd")
+    Bc, Vc, Din, H, Cp = dims
+    es = 2 if dt_ref == torch.bfloat16 else 4
+    nb = Bc * Vc * ((2 * Cp * es if mode else 0) + 2 * H * 4 + (6 * H * es if (mode == 0 or do_bwd1) else 0) + (8 * H * es if mode == 1 else 0))
+    _timed("gru_cell", 0.0, float(nb), lambda: L.check(L.load().fmm_tg_cell_bwd(C.byref(a), L.dt_of(dt_ref), L.stream()), "tg_cell_bwd"))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -117,6 +117,8 @@ _SIGNATURES = {
     "fmm_conv1d_k5_bwd": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
     "fmm_wgrad": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                   C.POINTER(c_int), c_int, c_ll, c_ll, c_ll, c_ll, c_int, _P, _P],
+    "fmm_prep_frames": [_P, _P, _P, _P, _P, c_int, c_int, c_int, C.c_uint, c_int, c_int, _P],
+    "fmm_prep_windows": [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_bgemm": [_P, _P],
     "fmm_tg_cell_fwd": [_P, c_int, _P],
     "fmm_tg_cell_bwd": [_P, c_int, _P],

@@ -238,6 +238,19 @@ int fmm_tg_relu_mask(void* dx, const void* y, long long total, int dtype, cudaSt
 int fmm_tg_transpose(const void* in, void* out, int R, int C, int Rp, long long in_g1, long long in_g2, long long in_rs,
                      long long out_g1, long long out_g2, long long out_rs, int G1, int G2, int dtype, cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * On-device input preparation (3_stream/har_create4_sensor.py:36-47,113-132; Multimodal_Fall3/dataset.py:28-41;
+ * Fall_2_Spatial_Temporal_SR/dataset.py:27; Model/combination.py:39): a resident recording is normalised once
+ * (prep_frames: xys [L][J][3] fp64 (x, y, score) -> frames [L][J+1][3] fp32 with the centre joint, per-frame
+ * score scr [L], score-weighted targets lbw [L][C]; main_mask = joints whose score is weighted x1.5) and
+ * T-frame windows are gathered at arbitrary start frames into skeleton [N][3][T][V], motion [N][2][T-1][V]
+ * (optional), sensor [N][T][S] (optional) and window-mean labels [N][C] (optional).
+ * ------------------------------------------------------------------------------------------- */
+int fmm_prep_frames(const double* xys, const double* labels, float* frames, float* scr, float* lbw, int L, int J, int C,
+                    unsigned main_mask, int center_main, int nan_to_num, cudaStream_t stream);
+int fmm_prep_windows(const float* frames, const float* lbw, const float* sensors, const int* starts, float* skel, float* mot,
+                     float* sensor_out, float* label_out, int N, int T, int V, int C, int S, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,12 @@ _SIGNATURES = {
     "fmm_conv1d_k5_bwd": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
     "fmm_wgrad": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                   C.POINTER(c_int), c_int, c_ll, c_ll, c_ll, c_ll, c_int, _P, _P],
+    "fmm_dwconv_fwd": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_dwconv_bwd_data": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_dwconv_bwd_weight": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_affine_act": [_P, _P, _P, _P, _P, c_ll, c_int, c_int, c_int, _P],
+    "fmm_bn_act_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, c_int, _P],
+    "fmm_bn_act_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, C.c_double, c_int, _P, _P, c_ll, c_int, c_int, c_int, _P],
     "fmm_prep_frames": [_P, _P, _P, _P, _P, c_int, c_int, c_int, C.c_uint, c_int, c_int, _P],
     "fmm_prep_windows": [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_bgemm": [_P, _P],

@@ -239,6 +239,28 @@ int fmm_tg_transpose(const void* in, void* out, int R, int C, int Rp, long long 
                      long long out_g1, long long out_g2, long long out_rs, int G1, int G2, int dtype, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * musa `Model` (Multimodal_Fall3/model/musa_model.py), channels-last [N][T][V][C], C % 8 == 0.
+ *  dwconv_*          depthwise (k x 1) temporal conv, groups = C (:165-168, :426, :446): w [C][k] fp32, bias [C]
+ *  affine_act        y = act(a[c]*x + b[c] (+ res)), act 0 none / 1 relu / 2 tanh / 3 leaky-relu(0.01): a folded
+ *                    BatchNorm2d + residual add + activation (:144-146, :195-199, :430-436)
+ *  bn_act_bwd_reduce S1[c] += sum dz, S2[c] += sum dz*xhat with dz = dy*act'(y), xhat = (x-mean)*rstd (fp64, zero first)
+ *  bn_act_bwd_apply  dx = a*(dz - S1/cnt - xhat*S2/cnt) (training) | a*dz (eval); dres = dz (optional)
+ * ------------------------------------------------------------------------------------------- */
+int fmm_dwconv_fwd(const void* x, const float* w, const float* b, void* out, int N, int Tin, int Tout, int V, int C, int k,
+                   int stride, int pad, int dtype, cudaStream_t stream);
+int fmm_dwconv_bwd_data(const void* dy, const float* w, void* dx, int N, int Tin, int Tout, int V, int C, int k, int stride,
+                        int pad, int dtype, cudaStream_t stream);
+int fmm_dwconv_bwd_weight(const void* x, const void* dy, float* dw, float* db, int N, int Tin, int Tout, int V, int C, int k,
+                          int stride, int pad, int dtype, cudaStream_t stream);
+int fmm_affine_act(const void* x, const float* a, const float* b, const void* res, void* y, long long rows, int C, int act,
+                   int dtype, cudaStream_t stream);
+int fmm_bn_act_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* rstd, double* S1,
+                          double* S2, long long rows, int C, int act, int dtype, cudaStream_t stream);
+int fmm_bn_act_bwd_apply(const void* dy, const void* y, const void* x, const float* a, const float* mean, const float* rstd,
+                         const double* S1, const double* S2, double inv_count, int training, void* dx, void* dres,
+                         long long rows, int C, int act, int dtype, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * On-device input preparation (3_stream/har_create4_sensor.py:36-47,113-132; Multimodal_Fall3/dataset.py:28-41;
  * Fall_2_Spatial_Temporal_SR/dataset.py:27; Model/combination.py:39): a resident recording is normalised once
  * (prep_frames: xys [L][J][3] fp64 (x, y, score) -> frames [L][J+1][3] fp32 with the centre joint, per-frame

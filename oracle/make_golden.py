@@ -213,9 +213,55 @@ def main_tragcn():
     print("targcn_v25_t16_autocast loss", float(loss.detach()))
 
 
+def main_musa():
+    """musa Model of Multimodal_Fall3/main.py:307-320: train step with DropBlock / Dropout switched off
+    (keep_prob = 1, p = 0: the random masks are the only thing that cannot be pinned) + eval logits."""
+    import warnings
+    from oracle import musa_oracle as MO
+    torch.set_num_threads(4)
+    mm = ref_import.load_musa()
+    c = dict(N=8, T=30, V=14, fill_seed=3, batch_seed=13)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = mm.Model(num_class=11, num_point=14, max_frame=300, graph=mm.adjGraph(layout="coco_cut", strategy="uniform"),
+                       bias=True, edge=True, block_size=41, embed_dim=64, n_stage=1, act_type="tanh")
+    sd = mod.state_dict()
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    sd.update(MO.fill_musa(shapes, c["fill_seed"]))
+    mod.load_state_dict(sd)
+    for m in mod.modules():
+        if hasattr(m, "keep_prob"):
+            m.keep_prob = 1
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    skel, _, target, _ = O.synthetic_batch(c["N"], c["T"], c["V"], 11, seed=c["batch_seed"])
+    # fp32 run of the reference (what a user sees) and an fp64 run of the same module (the truth both fp32 implementations
+    # are measured against: the first-layer gradients of this net are cancellation-heavy, the reference's own fp32 run is
+    # ~1e-3 away from it)
+    res32 = run_train_step(mod, lambda: mod(skel), target)
+    mod.load_state_dict(sd)
+    mod64 = mod.double()
+    skel64, target64 = skel.double(), target.double()
+    res = run_train_step(mod64, lambda: mod64(skel64), target64)
+    g32 = {k: v for k, v in res32["grads"].items()}
+    ref32_err = {}
+    for k, summ in res["grads"].items():
+        a, b = summ, g32[k]
+        if "full" in a:
+            ref32_err[k] = float((a["full"].double() - b["full"].double()).abs().max())
+        else:
+            ref32_err[k] = float((a["vals"].double() - b["vals"].double()).abs().max())
+    torch.save({"config": c, "shapes": shapes, "A": sd["stream_pos.0.A"].clone(), "n_params": sum(p.numel() for p in mod.parameters()),
+                "ref32_logits": res32["logits"], "ref32_grad_abs_err": ref32_err, **res}, os.path.join(OUT, "musa_coco_uniform.pt"))
+    print("musa loss", res["loss"])
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["tragcn"]:
         main_tragcn()
+    elif sys.argv[1:] == ["musa"]:
+        main_musa()
     else:
         main()
         main_tragcn()
+        main_musa()

@@ -76,3 +76,11 @@ def load_tragcn(seq_len: int):
     ta.Transform.__init__.__defaults__ = (seq_len,)
     ta.PositionalEncoding.__init__.__defaults__ = (seq_len,)
     return sys.modules["TRAGCN.TRAGCN"]
+
+
+def load_musa():
+    """Multimodal_Fall3/model/musa_model.py (imports cleanly: torch + numpy only)."""
+    spec = importlib.util.spec_from_file_location("musa_model", os.path.join(REF, "Multimodal_Fall3", "model", "musa_model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -328,7 +328,11 @@ class embed(nn.Module):
 
     def forward(self, x):
         c = self.cnn[0].cnn
-        return _Linear.apply(x, c.weight.view(c.out_channels, c.in_channels), c.bias, True, None)
+        W = c.weight.view(c.out_channels, c.in_channels)
+        pad = (-c.in_channels) % 8
+        if pad:   # 3 / 2 input channels: zero-pad to 8 so the GEMM fetches 16-byte vectors (the pad columns meet zero weights)
+            x, W = F.pad(x, (0, pad)), F.pad(W, (0, pad))
+        return _Linear.apply(x, W, c.bias, True, None)
 
 
 class Classification_Module(nn.Module):

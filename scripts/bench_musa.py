@@ -47,3 +47,12 @@ g.replay()
 graph = timeit(g.replay, 50)
 print(json.dumps({"workload": "musa Model B=256 T=30 V=14 bf16 train step (keep_prob 0.9)", "launches_per_step": launches,
                   "eager_ms": eager, "graph_ms": graph, "clips_per_s_graph": B / graph * 1e3, "loss": g.output.item()}))
+if len(sys.argv) > 1 and sys.argv[1] == "prof":
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as p:
+        step(skel, target); torch.cuda.synchronize()
+    rows = sorted(p.key_averages(), key=lambda r: -r.device_time_total)[:22]
+    tot = sum(r.device_time_total for r in p.key_averages())
+    print(f"kernel time total {tot / 1e3:.2f} ms over {sum(r.count for r in p.key_averages())} launches")
+    for r in rows:
+        print(f"  {r.key[:80]:80s} n={r.count:4d} {r.device_time_total / 1e3:7.2f} ms  avg {r.device_time_total / r.count:7.1f} us")

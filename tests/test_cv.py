@@ -1,0 +1,48 @@
+"""CPU: the k-fold scheduler (folds as independent per-device jobs) and the device-side macro metrics."""
+import csv
+
+import numpy as np
+import torch
+
+from fall_multimodal_b200.cv import assign_folds, macro_precision_recall_f1, run_cv
+
+
+def test_assign_folds_round_robin():
+    a = assign_folds(10, 8)
+    assert a[0] == [0, 8] and a[1] == [1, 9] and a[7] == [7]
+    assert sorted(f for w in a for f in w) == list(range(10))
+    assert assign_folds(3, 8)[:3] == [[0], [1], [2]]
+
+
+def test_macro_metrics_match_sklearn():
+    from sklearn.metrics import precision_recall_fscore_support
+    rng = np.random.default_rng(0)
+    for C in (2, 6, 11):
+        y = rng.integers(0, C, 500)
+        p = np.where(rng.random(500) < 0.7, y, rng.integers(0, C, 500))
+        p[p == C - 1] = 0                                    # a class that is never predicted (0/0 precision -> 0)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = precision_recall_fscore_support(y, p, average="macro")
+        got = macro_precision_recall_f1(torch.from_numpy(p), torch.from_numpy(y))
+        assert abs(got["precision"] - want[0]) < 1e-12 and abs(got["recall"] - want[1]) < 1e-12 and abs(got["f1"] - want[2]) < 1e-12
+        assert abs(got["accuracy"] - (y == p).mean()) < 1e-12
+
+
+def _fake_fold(fold, device):
+    # deterministic per-fold "metrics"; proves every fold ran exactly once on some worker
+    torch.manual_seed(fold)
+    y = torch.randint(0, 4, (200,), device=device)
+    p = torch.where(torch.rand(200, device=device) < 0.5 + 0.04 * fold, y, torch.randint(0, 4, (200,), device=device))
+    return macro_precision_recall_f1(p, y, 4)
+
+
+def test_run_cv_two_cpu_workers(tmp_path):
+    out = tmp_path / "precision_recall_f1.csv"
+    rows = run_cv(_fake_fold, 5, devices=["cpu", "cpu"], out_csv=str(out))
+    assert len(rows) == 5
+    for f, r in enumerate(rows):
+        assert r == {k: float(v) for k, v in _fake_fold(f, torch.device("cpu")).items()}
+    table = list(csv.reader(open(out)))
+    assert table[0] == ["", "precision", "recall", "f1", "accuracy"] and len(table) == 6 and table[3][0] == "2"

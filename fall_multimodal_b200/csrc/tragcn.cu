@@ -46,6 +46,198 @@ __global__ void softmax_bwd_kernel(const T* __restrict__ pr, T* __restrict__ dp,
   for (int i = lane; i < Lp; i += 32) d[i] = from_f32<T>(i < L ? to_f32(p[i]) * (to_f32(d[i]) - s) : 0.f);
 }
 
+// ---- vectorised fast paths: every global access is a 16-byte (bf16) / 32-byte (fp32) vector, each row is read once ----
+// softmax: one warp per row, up to 2 vectors (16 values) per lane held in registers (Lp <= 512, Lp % 8 == 0)
+template <typename T>
+__global__ void softmax_fwd_vec_kernel(T* __restrict__ x, long long rows, int L, int Lp) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nv = Lp >> 3;
+  T* p = x + row * Lp;
+  float v[2][8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int vi = lane + 32 * k;
+    if (vi < nv) load8(p + vi * 8, v[k]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (vi >= nv || vi * 8 + e >= L) v[k][e] = -INFINITY;
+      mx = fmaxf(mx, v[k][e]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[k][e] = __expf(v[k][e] - mx);   // exp(-inf) = 0 for the masked tail
+      s += v[k][e];
+    }
+  const float inv = 1.f / warp_sum(s);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int vi = lane + 32 * k;
+    if (vi < nv) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[k][e] *= inv;
+      store8(p + vi * 8, v[k]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void softmax_bwd_vec_kernel(const T* __restrict__ pr, T* __restrict__ dp, long long rows, int L, int Lp) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nv = Lp >> 3;
+  const T* p = pr + row * Lp;
+  T* d = dp + row * Lp;
+  float pv[2][8], dv[2][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int vi = lane + 32 * k;
+    if (vi < nv) {
+      load8(p + vi * 8, pv[k]);
+      load8(d + vi * 8, dv[k]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (vi >= nv || vi * 8 + e >= L) pv[k][e] = dv[k][e] = 0.f;
+      s = fmaf(pv[k][e], dv[k][e], s);
+    }
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int vi = lane + 32 * k;
+    if (vi < nv) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dv[k][e] = pv[k][e] * (dv[k][e] - s);
+      store8(d + vi * 8, dv[k]);
+    }
+  }
+}
+
+// LayerNorm, C = 8 * LPR with LPR (lanes per row) a power of two <= 32: 32/LPR rows per warp, reductions over LPR lanes
+template <typename T>
+__global__ void ln_fwd_vec_kernel(const T* __restrict__ a, const T* __restrict__ b2, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean,
+                                  float* __restrict__ rstd, long long rows, int C, float eps) {
+  const int lpr = C >> 3, rpw = 32 / lpr;
+  const int lane = threadIdx.x & 31, sub = lane % lpr;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw + lane / lpr;
+  const bool ok = row < rows;
+  float v[8], g[8], be[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (ok) {
+    load8(a + row * C + sub * 8, v);
+    if (b2) {
+      float w[8];
+      load8(b2 + row * C + sub * 8, w);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = to_f32(from_f32<T>(v[e] + w[e]));  // the sum is a rounded tensor in the reference
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s += v[e];
+  for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q += (v[e] - mu) * (v[e] - mu);
+  for (int o = lpr >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rs = rsqrtf(q / C + eps);
+  if (!ok) return;
+  if (sub == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+  load8(gamma + sub * 8, g);
+  load8(beta + sub * 8, be);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = (v[e] - mu) * rs * g[e] + be[e];
+  store8(y + row * C + sub * 8, v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ a,
+                                                         const T* __restrict__ b2, const float* __restrict__ gamma,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         T* __restrict__ dx, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta, long long rows, int C, int iters) {
+  __shared__ float sg[256][9], sb[256][9];
+  const int lpr = C >> 3, rpw = 32 / lpr;
+  const int lane = threadIdx.x & 31, sub = lane % lpr;
+  float g[8], ag[8], ab[8];
+  load8(gamma + sub * 8, g);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ag[e] = ab[e] = 0.f;
+  const long long rows_per_block = (long long)(blockDim.x >> 5) * rpw * iters;
+  for (int it = 0; it < iters; ++it) {
+    const long long row = (long long)blockIdx.x * rows_per_block + ((long long)it * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw + lane / lpr;
+    const bool ok = row < rows;
+    float v[8], d[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = d[e] = 0.f;
+    float mu = 0.f, rs = 0.f;
+    if (ok) {
+      load8(a + row * C + sub * 8, v);
+      if (b2) {
+        float w[8];
+        load8(b2 + row * C + sub * 8, w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = to_f32(from_f32<T>(v[e] + w[e]));
+      }
+      load8(dy + row * C + sub * 8, d);
+      mu = mean[row];
+      rs = rstd[row];
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = (v[e] - mu) * rs;            // xhat
+      ag[e] = fmaf(d[e], v[e], ag[e]);
+      ab[e] += d[e];
+      d[e] *= g[e];
+      s1 += d[e];
+      s2 = fmaf(d[e], v[e], s2);
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 /= C;
+    s2 /= C;
+    if (ok) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = rs * (d[e] - s1 - v[e] * s2);
+      store8(dx + row * C + sub * 8, d);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sg[threadIdx.x][e] = ag[e];
+    sb[threadIdx.x][e] = ab[e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int s8 = c >> 3, e = c & 7;
+    float gs = 0.f, bs = 0.f;
+    for (int t = s8; t < (int)blockDim.x; t += lpr) {   // all threads whose channel group is s8
+      gs += sg[t][e];
+      bs += sb[t][e];
+    }
+    atomicAdd(&dgamma[c], gs);
+    atomicAdd(&dbeta[c], bs);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over C (<= 256, multiple of 32) of (a + b); one warp per row
 // ---------------------------------------------------------------------------------------------
@@ -195,7 +387,12 @@ extern "C" {
 int fmm_tg_softmax_fwd(void* x, long long rows, int L, int Lp, int dtype, void* stream) {
   TG_CHECK_DT(dtype, "tg_softmax_fwd");
   FMM_CHECK_ARG(rows > 0 && L > 0 && Lp >= L, "tg_softmax_fwd: bad shape");
-  TG_DISPATCH(dtype, softmax_fwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((T*)x, rows, L, Lp);)
+  const bool vec = (Lp % 8) == 0 && Lp <= 512 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (vec) {
+    TG_DISPATCH(dtype, softmax_fwd_vec_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((T*)x, rows, L, Lp);)
+  } else {
+    TG_DISPATCH(dtype, softmax_fwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((T*)x, rows, L, Lp);)
+  }
   FMM_CHECK_LAUNCH("tg_softmax_fwd");
   return FMM_OK;
 }
@@ -203,7 +400,12 @@ int fmm_tg_softmax_fwd(void* x, long long rows, int L, int Lp, int dtype, void* 
 int fmm_tg_softmax_bwd(const void* p, void* dp, long long rows, int L, int Lp, int dtype, void* stream) {
   TG_CHECK_DT(dtype, "tg_softmax_bwd");
   FMM_CHECK_ARG(rows > 0 && L > 0 && Lp >= L, "tg_softmax_bwd: bad shape");
-  TG_DISPATCH(dtype, softmax_bwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const T*)p, (T*)dp, rows, L, Lp);)
+  const bool vec = (Lp % 8) == 0 && Lp <= 512 && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(dp)) & 15) == 0;
+  if (vec) {
+    TG_DISPATCH(dtype, softmax_bwd_vec_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const T*)p, (T*)dp, rows, L, Lp);)
+  } else {
+    TG_DISPATCH(dtype, softmax_bwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const T*)p, (T*)dp, rows, L, Lp);)
+  }
   FMM_CHECK_LAUNCH("tg_softmax_bwd");
   return FMM_OK;
 }
@@ -212,8 +414,17 @@ int fmm_tg_ln_fwd(const void* a, const void* b, const float* gamma, const float*
                   long long rows, int C, float eps, int dtype, void* stream) {
   TG_CHECK_DT(dtype, "tg_ln_fwd");
   FMM_CHECK_ARG(rows > 0 && C >= 32 && C <= 256 && (C % 32) == 0, "tg_ln_fwd: C must be a multiple of 32 up to 256, got %d", C);
-  TG_DISPATCH(dtype, ln_fwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      (const T*)a, (const T*)b, gamma, beta, (T*)y, mean, rstd, rows, C, eps);)
+  const int lpr = C / 8;
+  const bool vec = (C % 8) == 0 && lpr <= 32 && (lpr & (lpr - 1)) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (vec) {
+    const long long rpb = 8ll * (32 / lpr);
+    TG_DISPATCH(dtype, ln_fwd_vec_kernel<T><<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)a, (const T*)b, gamma, beta, (T*)y, mean, rstd, rows, C, eps);)
+  } else {
+    TG_DISPATCH(dtype, ln_fwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)a, (const T*)b, gamma, beta, (T*)y, mean, rstd, rows, C, eps);)
+  }
   FMM_CHECK_LAUNCH("tg_ln_fwd");
   return FMM_OK;
 }
@@ -222,12 +433,26 @@ int fmm_tg_ln_bwd(const void* dy, const void* a, const void* b, const float* gam
                   void* dx, float* dgamma, float* dbeta, long long rows, int C, int dtype, void* stream) {
   TG_CHECK_DT(dtype, "tg_ln_bwd");
   FMM_CHECK_ARG(rows > 0 && C >= 32 && C <= 256 && (C % 32) == 0, "tg_ln_bwd: C must be a multiple of 32 up to 256, got %d", C);
-  long long warps = (long long)num_sms() * 8 * 4;
-  int rpw = (int)((rows + warps - 1) / warps);
-  if (rpw < 1) rpw = 1;
-  long long blocks = (rows + 8ll * rpw - 1) / (8ll * rpw);
-  TG_DISPATCH(dtype, ln_bwd_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      (const T*)dy, (const T*)a, (const T*)b, gamma, mean, rstd, (T*)dx, dgamma, dbeta, rows, C, rpw);)
+  const int lpr = C / 8;
+  const bool vec = (C % 8) == 0 && lpr <= 32 && (lpr & (lpr - 1)) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(dy) |
+                     reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  if (vec) {
+    const long long rows_per_pass = 8ll * (32 / lpr);                       // rows a 256-thread block covers per iteration
+    long long blocks = (long long)num_sms() * 16;
+    int iters = (int)((rows + blocks * rows_per_pass - 1) / (blocks * rows_per_pass));
+    if (iters < 1) iters = 1;
+    blocks = (rows + rows_per_pass * iters - 1) / (rows_per_pass * iters);
+    TG_DISPATCH(dtype, ln_bwd_vec_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dy, (const T*)a, (const T*)b, gamma, mean, rstd, (T*)dx, dgamma, dbeta, rows, C, iters);)
+  } else {
+    long long warps = (long long)num_sms() * 8 * 4;
+    int rpw = (int)((rows + warps - 1) / warps);
+    if (rpw < 1) rpw = 1;
+    long long blocks = (rows + 8ll * rpw - 1) / (8ll * rpw);
+    TG_DISPATCH(dtype, ln_bwd_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dy, (const T*)a, (const T*)b, gamma, mean, rstd, (T*)dx, dgamma, dbeta, rows, C, rpw);)
+  }
   FMM_CHECK_LAUNCH("tg_ln_bwd");
   return FMM_OK;
 }

@@ -21,7 +21,7 @@ struct CellFwdArgs {
   const void* x;      long long xb, xv;   // x slice (B,V,Din) feeding the cat being built (null: no cat)
   const void* hprev;  long long hb, hv;   // h_{t-1} (null at t = 0)
   const float* S;                         // (V,V) supports
-  const float* pre;   const float* lin;   // (B,V,Co) fp32 GEMM outputs of the stage being finished
+  const void* pre;    const void* lin;    // (B,V,Co) GEMM outputs of the stage being finished, in the activation dtype
   void* zr;  void* lg;                    // (B,V,2H): mode 1 writes, mode 2 reads zr
   void* hc;  void* lu;                    // (B,V,H): mode 2 writes
   void* hout; long long ob, ov;           // H_t slice (mode 2)
@@ -85,7 +85,7 @@ __device__ __forceinline__ void mix8(const float* Ss, const float* rows, int V, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512) cell_fwd_kernel(const CellFwdArgs p) {
+__global__ void __launch_bounds__(256, 4) cell_fwd_kernel(const CellFwdArgs p) {
   extern __shared__ __align__(16) float sm[];
   float* cat = sm;                  // [V][Cp]
   float* Ss = sm + p.V * p.Cp;      // [V][V]
@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(512) cell_fwd_kernel(const CellFwdArgs p) {
       const int m = it / C8, c = (it % C8) * 8;
       const long long o = ((long long)b * V + m) * 2 * H + c;
       float pr[8], li[8], g[8];
-      ld8f(p.pre + o, pr);
-      ld8f(p.lin + o, li);
+      load8(reinterpret_cast<const T*>(p.pre) + o, pr);
+      load8(reinterpret_cast<const T*>(p.lin) + o, li);
 #pragma unroll
       for (int e = 0; e < 8; ++e) g[e] = sigm(pr[e] + li[e] * sigm(li[e]));
       store8(zr + o, g);
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(512) cell_fwd_kernel(const CellFwdArgs p) {
       const int m = it / H8, j = (it % H8) * 8;
       const long long row = (long long)b * V + m;
       float pr[8], li[8], z[8], h[8], c2[8];
-      ld8f(p.pre + row * H + j, pr);
-      ld8f(p.lin + row * H + j, li);
+      load8(reinterpret_cast<const T*>(p.pre) + row * H + j, pr);
+      load8(reinterpret_cast<const T*>(p.lin) + row * H + j, li);
       load8(zr + row * 2 * H + j, z);
       if (hprev) load8(hprev + b * p.hb + m * p.hv + j, h);
       else
@@ -236,7 +236,7 @@ __device__ __forceinline__ void bwd1_vec(const CellBwdArgs& p, int b, int m, int
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512) cell_bwd_kernel(const CellBwdArgs p) {
+__global__ void __launch_bounds__(256, 4) cell_bwd_kernel(const CellBwdArgs p) {
   extern __shared__ __align__(16) float sm[];
   float* d0 = sm;                 // [V][Cp]
   float* Ss = sm + p.V * p.Cp;    // [V][V]
@@ -353,8 +353,8 @@ int fmm_tg_cell_fwd(const CellFwdArgs* a, int dtype, void* stream) {
   FMM_CHECK_ARG(a->mode != 2 || (a->hc && a->lu && a->hout), "tg_cell_fwd: missing state outputs");
   FMM_CHECK_ARG(!a->xc0 || (a->xc1 && a->x && a->S), "tg_cell_fwd: missing cat operands");
   size_t smem = sizeof(float) * ((size_t)a->V * a->Cp + (size_t)a->V * a->V);
-  if (dtype == FMM_DT_BF16) cell_fwd_kernel<__nv_bfloat16><<<a->B, 512, smem, (cudaStream_t)stream>>>(*a);
-  else cell_fwd_kernel<float><<<a->B, 512, smem, (cudaStream_t)stream>>>(*a);
+  if (dtype == FMM_DT_BF16) cell_fwd_kernel<__nv_bfloat16><<<a->B, 256, smem, (cudaStream_t)stream>>>(*a);
+  else cell_fwd_kernel<float><<<a->B, 256, smem, (cudaStream_t)stream>>>(*a);
   FMM_CHECK_LAUNCH("tg_cell_fwd");
   return FMM_OK;
 }
@@ -369,8 +369,8 @@ int fmm_tg_cell_bwd(const CellBwdArgs* a, int dtype, void* stream) {
   FMM_CHECK_ARG(!(a->mode == 0 || (a->mode == 2 && a->do_bwd1)) || (a->z1 && a->hc1 && a->lu1 && a->dpre_u && a->dlin_u),
                 "tg_cell_bwd: missing update-stage tensors");
   size_t smem = sizeof(float) * ((size_t)a->V * a->Cp + (size_t)a->V * a->V);
-  if (dtype == FMM_DT_BF16) cell_bwd_kernel<__nv_bfloat16><<<a->B, 512, smem, (cudaStream_t)stream>>>(*a);
-  else cell_bwd_kernel<float><<<a->B, 512, smem, (cudaStream_t)stream>>>(*a);
+  if (dtype == FMM_DT_BF16) cell_bwd_kernel<__nv_bfloat16><<<a->B, 256, smem, (cudaStream_t)stream>>>(*a);
+  else cell_bwd_kernel<float><<<a->B, 256, smem, (cudaStream_t)stream>>>(*a);
   FMM_CHECK_LAUNCH("tg_cell_bwd");
   return FMM_OK;
 }

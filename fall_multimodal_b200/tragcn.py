@@ -115,7 +115,7 @@ def cell_fwd(mode, dims, S, x=None, hprev=None, pre=None, lin=None, zr=None, lg=
     Bc, Vc, Din, H, Cp = dims
     es = ref.element_size()
     co = {0: 0, 1: 2 * H, 2: H}[mode]
-    nb = Bc * Vc * (2 * co * 4 + 2 * co * es + H * es + (H * es if mode == 2 else 0) + (Din * es + 2 * Cp * es if xc0 is not None else 0))
+    nb = Bc * Vc * (2 * co * es + 2 * co * es + H * es + (H * es if mode == 2 else 0) + (Din * es + 2 * Cp * es if xc0 is not None else 0))
     _timed("gru_cell", 0.0, float(nb), lambda: L.check(L.load().fmm_tg_cell_fwd(C.byref(a), _dt(ref), L.stream()), "tg_cell_fwd"))
 
 
@@ -180,8 +180,8 @@ class _GraphGRUScan(Function):
             LG = torch.empty(Ts, B, V, 2 * H, dtype=dt, device=dev)
             HC = torch.empty(Ts, B, V, H, dtype=dt, device=dev)
             LU = torch.empty(Ts, B, V, H, dtype=dt, device=dev)
-            PLg = torch.empty(2, B, V, 2 * H, dtype=torch.float32, device=dev)
-            PLu = torch.empty(2, B, V, H, dtype=torch.float32, device=dev)
+            PLg = torch.empty(2, B, V, 2 * H, dtype=dt, device=dev)      # stage GEMM outputs (rounded tensors in the reference too)
+            PLu = torch.empty(2, B, V, H, dtype=dt, device=dev)
             g1 = Ts * B * V * Cp
             dims = (B, V, Din, H, Cp)
             cell_fwd(0, dims, S, x=x[:, 0], xc0=XCg[0, 0], xc1=XCg[1, 0])

@@ -197,7 +197,7 @@ typedef struct fmm_cell_fwd_args {
   const void* x; long long xb, xv;
   const void* hprev; long long hb, hv;
   const float* S;
-  const float* pre; const float* lin;
+  const void* pre; const void* lin;   /* stage GEMM outputs, activation dtype */
   void* zr; void* lg;
   void* hc; void* lu;
   void* hout; long long ob, ov;

@@ -359,7 +359,7 @@ __device__ __forceinline__ void pipe_load(__nv_bfloat16* S, const Operand& op, i
 }
 
 template <int AM, int BMo>
-__global__ void __launch_bounds__(pThreads) bgemm_pipe_kernel(const BgemmDesc p, int vec_epi) {
+__global__ void __launch_bounds__(pThreads, 3) bgemm_pipe_kernel(const BgemmDesc p, int vec_epi) {
   __shared__ __align__(128) __nv_bfloat16 smem[pStages * (pAStage + pBStage)];
   __nv_bfloat16(*As)[pAStage] = reinterpret_cast<__nv_bfloat16(*)[pAStage]>(smem);
   __nv_bfloat16(*Bs)[pBStage] = reinterpret_cast<__nv_bfloat16(*)[pBStage]>(smem + pStages * pAStage);

@@ -462,7 +462,7 @@ def run_targcn(args):
     # per-launch timing of the GEMM / cell kernels on one eager step behind a parked queue, and the launch count
     tragcn.profile = []
     l0 = _lib.launch_count
-    torch.cuda._sleep(int(0.25 * 1.9e9))
+    torch.cuda._sleep(int(0.6 * 1.9e9))       # an eager step is ~0.2 s of host launches: park the GPU until it is queued
     step(x, tgt)
     torch.cuda.synchronize()
     launches = (_lib.launch_count - l0) * args.steps

@@ -48,6 +48,8 @@ struct TapConvParams {
   int MT;        // M=128 tiles per pipeline item (2: 32 positions x 8 columns share one window and every weight image)
   int tps;       // taps per streamed weight stage (one barrier round trip per `tps` taps)
   int resident;  // 1: the weight images stay in shared memory for the CTA's lifetime
+  int bias_smem; // > 0: this many floats of `bias` are staged in shared memory once per CTA (the epilogue's bias loads sit on
+                 // the tile's critical path: a per-joint table read from global memory cost +50 % on the 1x1 graph convs)
   int res_local; // resident && 1: only the images of the CTA's own N tile (gridDim.x is a multiple of ntiles_n)
   unsigned* err;
 };
@@ -108,6 +110,15 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
+  const uint32_t bias_s0 = bars0 + 2048u;  // behind the barrier block
+  // staged as [Cout/4][rows][4]: the 8 joints of a tile read 8 neighbouring float4 (one conflict-free wavefront per load;
+  // the row-major table costs 8 wavefronts per load, in shared memory as in L1)
+  const int bias_rows = p.bias_vstride ? p.V : 1;
+  for (int i = threadIdx.x; i < p.bias_smem; i += blockDim.x) {
+    const int v = i / p.Cout, c = i % p.Cout;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s0 + 4u * (((c >> 2) * bias_rows + v) * 4 + (c & 3))), "f"(p.bias[i]) : "memory");
+  }
+  const float* __restrict__ bias_tab = reinterpret_cast<const float*>(smem_raw + (bias_s0 - smem_u32(smem_raw)));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -285,10 +296,14 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         if (row_ok && vec_ok && co0 + 32 <= p.Cout) {
           // fast path: whole 32-column group in range
           if (p.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(v) * p.bias_vstride + co0);
+            const int vrow = p.bias_vstride ? v : 0;
+            const float4* bp = p.bias_smem > 0
+                                   ? reinterpret_cast<const float4*>(bias_tab) + (co0 >> 2) * bias_rows + vrow
+                                   : reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(v) * p.bias_vstride + co0);
+            const int bstep = p.bias_smem > 0 ? bias_rows : 1;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              const float4 b = bp[g];
+              const float4 b = bp[g * bstep];
               acc[4 * g + 0] = __float_as_uint(__uint_as_float(acc[4 * g + 0]) + b.x);
               acc[4 * g + 1] = __float_as_uint(__uint_as_float(acc[4 * g + 1]) + b.y);
               acc[4 * g + 2] = __float_as_uint(__uint_as_float(acc[4 * g + 2]) + b.z);
@@ -309,7 +324,10 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int co = co0 + g * 8 + i;
-              float b = (p.bias && co < p.Cout) ? p.bias[v * p.bias_vstride + co] : 0.f;
+              float b = 0.f;
+              if (p.bias && co < p.Cout)
+                b = p.bias_smem > 0 ? bias_tab[((co >> 2) * bias_rows + (p.bias_vstride ? v : 0)) * 4 + (co & 3)]
+                                    : p.bias[v * p.bias_vstride + co];
               f[i] = __uint_as_float(acc[g * 8 + i]) + b;
             }
             const int co = co0 + g * 8;
@@ -662,7 +680,11 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   const int nparts = dtype == FMM_DT_F32 ? 3 : 1;
   const size_t slot_bytes = static_cast<size_t>(nparts) * p.win_atoms * 1024;
   const size_t bstage_bytes = static_cast<size_t>(nparts) * p.BN * 128;
-  const size_t budget = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers*/;
+  // the bias table ([V][Cout] for the per-joint bias of the graph conv, else [Cout]) rides along in shared memory when small
+  const size_t bias_floats = bias ? static_cast<size_t>(bias_per_joint ? V : 1) * Cout : 0;
+  p.bias_smem = (bias_floats > 0 && bias_floats * 4 <= 36 * 1024 && (Cout % 4) == 0) ? static_cast<int>(bias_floats) : 0;
+  const size_t bias_bytes = (static_cast<size_t>(p.bias_smem) * 4 + 15) / 16 * 16;
+  const size_t budget = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers*/ - bias_bytes;
   // Weights: keep every image resident when they fit next to >= 3 window slots (no per-tap barrier
   // round trips at all); otherwise stream them through as deep a ring as fits beside 4 slots.
   const int nimg = p.ntiles_n * p.nchunks * ntaps;
@@ -701,7 +723,7 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
                 "tapconv: tile does not fit shared memory (win_atoms=%d BN=%d parts=%d)", p.win_atoms, p.BN, nparts);
   p.nslots = ns;
   p.nbstages = nb;
-  const size_t smem = nb * bstage_bytes * p.tps + ns * slot_bytes + 1024 + 2048;
+  const size_t smem = nb * bstage_bytes * p.tps + ns * slot_bytes + 1024 + 2048 + bias_bytes;
   const bool wide = p.BN >= 128;
 #define FMM_LAUNCH_TAPCONV(TT, EPI)                                                                              \
   do {                                                                                                           \

@@ -21,7 +21,7 @@ def timeit(fn):
         ts.append(e0.elapsed_time(e1) * 1e3)
     return min(ts), sorted(ts)[len(ts) // 2]
 
-def tap(name, T, Cin, Cout, ntaps, stride, prologue):
+def tap(name, T, Cin, Cout, ntaps, stride, prologue, vbias=False):
     if only and only not in name: return
     x = torch.randn(N, T, V, Cin, device=dev).to(dt)
     W = torch.randn(Cout, Cin, ntaps, device=dev) * 0.05
@@ -31,7 +31,9 @@ def tap(name, T, Cin, Cout, ntaps, stride, prologue):
     sc = torch.rand(Cin, device=dev) + 0.5 if prologue else None
     sh = torch.randn(Cin, device=dev) if prologue else None
     sh_ = list(range(-(ntaps // 2), ntaps // 2 + 1))
-    f = lambda: ops.tapconv(x, pw, out, shifts=sh_, tj=To, istride=stride, in_scale=sc, in_shift=sh, in_relu=prologue)
+    bias = (torch.randn(V, Cout, device=dev) if vbias else torch.randn(Cout, device=dev)) if vbias is not None else None
+    f = lambda: ops.tapconv(x, pw, out, shifts=sh_, tj=To, istride=stride, in_scale=sc, in_shift=sh, in_relu=prologue,
+                            bias=bias, bias_per_joint=bool(vbias))
     best, med = timeit(f)
     fl = 2.0 * N * V * To * Cin * Cout * ntaps
     byt = (x.numel() + out.numel()) * 2
@@ -61,7 +63,10 @@ tap("tcn_plain_b6", 16, 256, 256, 9, 1, False)     # what the engine runs: relu(
 tap("tcn_plain_b4", 32, 128, 128, 9, 1, False)
 tap("tcn_dgrad_b1", 64, 64, 64, 9, 1, False)
 tap("gcn_fwd_b1", 64, 192, 64, 1, 1, False)
+tap("gcn_fwd_b1_jointbias", 64, 192, 64, 1, 1, False, vbias=True)   # the engine's graph conv: per-joint bias
+tap("gcn_fwd_b1_nobias", 64, 192, 64, 1, 1, False, vbias=None)
 tap("gcn_fwd_b4", 32, 384, 128, 1, 1, False)
+tap("gcn_fwd_b4_jointbias", 32, 384, 128, 1, 1, False, vbias=True)
 tap("gcn_fwd_b6", 16, 768, 256, 1, 1, False)
 tap("P_b1", 64, 64, 192, 1, 1, False)
 tap("P_b6", 16, 256, 768, 1, 1, False)

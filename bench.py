@@ -85,7 +85,9 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference algorithm on the host cores
 # --------------------------------------------------------------------------------------------
-def cpu_step_factory(n, threads):
+def cpu_step_factory(n, threads, device="cpu", autocast=False):
+    """The oracle port of the reference modules as a train step; ``device='cuda'`` + ``autocast`` gives the stock
+    PyTorch/cuDNN eager path of the same model on the GPU (the de-facto incumbent)."""
     from oracle import stgcn_oracle as O
 
     torch.set_num_threads(threads)
@@ -102,18 +104,20 @@ def cpu_step_factory(n, threads):
     sd = O.fill_state_dict(shapes, 0)
     sd["stgcan_1.A"] = A
     sd["stgcan_2.A"] = A.clone()
+    sd = {k: v.to(device) for k, v in sd.items()}
     params = [v.requires_grad_(True) for k, v in sd.items()
               if v.is_floating_point() and "running_" not in k and not k.endswith(".A")]
     opt = torch.optim.RMSprop(params, lr=1e-3)
-    skel, sensor, target = synthetic(n, 42)
+    skel, sensor, target = synthetic(n, 42, device)
 
     def step():
         opt.zero_grad(set_to_none=True)
-        out = O.two_stream_cnn_forward(sd, skel, sensor, training=True)
-        loss = O.soft_ce(out, target)
+        with torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=autocast):
+            out = O.two_stream_cnn_forward(sd, skel, sensor, training=True)
+        loss = O.soft_ce(out.float(), target)
         loss.backward()
         opt.step()
-        return float(loss.detach())
+        return loss.detach()
 
     return step
 
@@ -329,6 +333,23 @@ def run_ours(args):
             v, dt = time_cpu(args.cpu_clips, 2, 1, threads)
             cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
                    "sample": f"2 steps of {args.cpu_clips} clips after 1 warm-up ({dt:.1f} s/step), same model/shape"}
+        eager_gpu = None
+        if world == 1 and args.torch_eager_gpu:
+            # the same model through stock PyTorch/cuDNN on this GPU (oracle modules, bf16 autocast, eager): informational
+            torch.backends.cudnn.benchmark = True
+            est = cpu_step_factory(B, os.cpu_count() or 1, device=str(dev), autocast=True)
+            for _ in range(3):
+                est()
+            torch.cuda.synchronize()
+            ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ee0.record()
+            for _ in range(5):
+                est()
+            ee1.record()
+            torch.cuda.synchronize()
+            ems = ee0.elapsed_time(ee1) / 5
+            eager_gpu = {"value": B / ems * 1e3, "unit": "clips/s", "ms_per_step": ems,
+                         "what": "oracle port of the reference modules, torch eager + cuDNN, bf16 autocast, same GPU, same batch"}
         line = {"metric": "train clips/sec fwd+bwd (GSTCAN, Bx3xT64xV33)", "value": value, "unit": "clips/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -338,6 +359,8 @@ def run_ours(args):
                 "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+        if eager_gpu is not None:
+            line["torch_eager_gpu"] = eager_gpu
         print(json.dumps(line), flush=True)
     if world > 1:
         # Captured NCCL collectives keep the communicator busy at teardown: destroy_process_group() was
@@ -559,6 +582,8 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="1: run the independent branches (two trunks, sensor) on side streams")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the whole train step as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-eager-gpu", action="store_true",
+                    help="also time the stock PyTorch/cuDNN eager path of the same model on the GPU (adds a torch_eager_gpu key)")
     ap.add_argument("--workload", default="gstcan", choices=["gstcan", "targcn"],
                     help="gstcan: BASELINE configs[1] (the headline, default); targcn: configs[3] (TARGCN T=300 V=25, 512 clips)")
     args = ap.parse_args()

@@ -381,27 +381,36 @@ TG_WORKLOAD = ("TARGCN(num_nodes=25, adj=None) graph-GRU encoder (2 layers x 300
 TG_METRIC = "train clips/sec fwd+bwd (TARGCN, BxT300xV25x3)"
 
 
-def targcn_cpu(n, steps, warmup, threads):
-    """The oracle port of TRAGCN.py / GRU.py / EmbGCN.py / TA.py on the host cores (bounded sample of n clips)."""
+def targcn_cpu(n, steps, warmup, threads, device="cpu", autocast=False):
+    """The oracle port of TRAGCN.py / GRU.py / EmbGCN.py / TA.py (bounded sample of n clips) on the host cores, or with
+    ``device='cuda'`` the stock PyTorch eager path on the GPU. Note: the port already hoists the loop-invariant EmbGCN algebra
+    the literal reference recomputes in each of its 2*T cell calls, i.e. it is faster than the reference as written."""
     from oracle import tragcn_oracle as TO
 
     torch.set_num_threads(threads)
-    sd = {k: v.clone().requires_grad_(not k.endswith("PE.pe")) for k, v in
+    sd = {k: v.to(device).requires_grad_(not k.endswith("PE.pe")) for k, v in
           TO.fill_targcn(TO.targcn_param_shapes(V=TG_V, T=TG_T), 1).items()}
     opt = torch.optim.RMSprop([v for v in sd.values() if v.requires_grad], lr=1e-4)
-    x, tgt = TO.synthetic_clips(n, TG_T, TG_V, seed=42)
+    x, tgt = (t.to(device) for t in TO.synthetic_clips(n, TG_T, TG_V, seed=42))
+    cuda = torch.device(device).type == "cuda"
 
     def step():
         opt.zero_grad(set_to_none=True)
-        loss = torch.nn.CrossEntropyLoss()(TO.targcn_forward(sd, x), tgt)
+        with torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=autocast):
+            out = TO.targcn_forward(sd, x)
+        loss = torch.nn.CrossEntropyLoss()(out.float(), tgt)
         loss.backward()
         opt.step()
 
     for _ in range(warmup):
         step()
+    if cuda:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
+    if cuda:
+        torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
     return n / dt, dt
 
@@ -551,6 +560,12 @@ def run_targcn(args):
             v, dt = targcn_cpu(2, 1, 1, threads)
             cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
                    "sample": f"1 step of 2 clips after 1 warm-up ({dt:.1f} s/step), same model/shape"}
+        eager_gpu = None
+        if world == 1 and args.torch_eager_gpu:
+            nb = min(B, 128)        # stock eager keeps every intermediate of the 600 cell calls alive: bounded batch
+            v, dt = targcn_cpu(nb, 2, 1, os.cpu_count() or 1, device=str(dev), autocast=True)
+            eager_gpu = {"value": v, "unit": "clips/s", "ms_per_step": dt * 1e3, "clips_per_step": nb,
+                         "what": "oracle port (loop invariants already hoisted), torch eager, bf16 autocast, same GPU"}
         line = {"metric": TG_METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -562,6 +577,8 @@ def run_targcn(args):
                         "h2d_bytes_per_step": (x_h.numel() + t_h.numel()) * 4, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+        if eager_gpu is not None:
+            line["torch_eager_gpu"] = eager_gpu
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.cuda.synchronize()

@@ -45,8 +45,8 @@ def positional_encoding(T: int, C: int) -> torch.Tensor:
 def emb_gcn_invariants(sd, prefix, E, sym):
     """Everything in EmbGCN.forward that does not depend on x (EmbGCN.py:73-83)."""
     V = E.shape[0]
-    supports = F.softmax(F.relu(E @ E.t()), dim=1) + torch.eye(V, dtype=E.dtype)      # :73-74
-    colscale = torch.softmax(sym.to(E.dtype), dim=-1).sum(0)                            # :77 "nm,bmc->bmc" sums n
+    supports = F.softmax(F.relu(E @ E.t()), dim=1) + torch.eye(V, dtype=E.dtype, device=E.device)      # :73-74
+    colscale = torch.softmax(sym.to(E.device, E.dtype), dim=-1).sum(0)                            # :77 "nm,bmc->bmc" sums n
     weights = torch.einsum("nd,dio->nio", E, sd[prefix + "weights_pool"])              # :80
     bias = E @ sd[prefix + "bias_pool"]                                                 # :81
     return supports, colscale, weights, bias
@@ -91,7 +91,7 @@ def encoder(sd, x, sym, num_layers=2, H=64, trans_layers=2, collect=None):
         p = f"encoder.dcrnn_cells.{i}."
         inv_g = emb_gcn_invariants(sd, p + "gate.", E, sym)
         inv_u = emb_gcn_invariants(sd, p + "update.", E, sym)
-        state = torch.zeros(B, V, H, dtype=x.dtype)
+        state = torch.zeros(B, V, H, dtype=x.dtype, device=x.device)
         states = []
         for t in range(T):
             state = gru_cell(cur[:, t], state, inv_g, inv_u, sd, p, H)
@@ -99,7 +99,7 @@ def encoder(sd, x, sym, num_layers=2, H=64, trans_layers=2, collect=None):
         cur = torch.stack(states, dim=1)
         if collect is not None:
             collect[f"scan{i}"] = cur
-    cur = cur + positional_encoding(T, H).to(cur.dtype)                                   # TA.py:98
+    cur = cur + positional_encoding(T, H).to(cur.device, cur.dtype)                                   # TA.py:98
     for l in range(trans_layers):
         cur = transform(cur, sd, f"encoder.trans_layer_T.trans_layers.{l}.")
         if collect is not None:

@@ -71,3 +71,39 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().lower().replace("# oracle", ""), f
+
+
+def test_descriptor_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors of the POD descriptors (bgemm, cell_fwd, cell_bwd) have the C header's size and field offsets."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from fall_multimodal_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    cuda_inc = "/usr/local/cuda/include"
+    if gcc is None or not os.path.isdir(cuda_inc):
+        pytest.skip("needs gcc and the CUDA headers")
+    checks = {"fmm_bgemm_desc": (_lib.BgemmDesc, ["A", "bias_n", "a_g1", "b_k3", "c_n", "G1", "K3", "alpha", "beta", "c_dtype"]),
+              "fmm_cell_fwd_args": (_lib.CellFwdArgs, ["x", "hv", "S", "lu", "hout", "ov", "xc1", "mode", "Cp"]),
+              "fmm_cell_bwd_args": (_lib.CellBwdArgs, ["S", "dz", "dx", "dxv", "lg", "dH", "z1", "hv1", "dlin_u", "mode", "Cp"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fmm_b200.h"', "int main(void) {"]
+    for cname, (_, fields) in checks.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname} {f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi_probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_probe"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([gcc, "-I", os.path.join(root, "include"), "-I", cuda_inc, str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    for line in filter(None, out):
+        cname, what, val = line.split()
+        struct = checks[cname][0]
+        if what == "size":
+            assert ctypes.sizeof(struct) == int(val), (cname, ctypes.sizeof(struct), val)
+        else:
+            assert getattr(struct, what).offset == int(val), (cname, what)

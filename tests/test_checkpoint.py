@@ -50,3 +50,15 @@ def test_reference_checkpoint_dict_round_trip():
     save_checkpoint(buf, m)                                                  # best_model.pt layout (:323-326)
     buf.seek(0)
     assert set(torch.load(buf, weights_only=False).keys()) == {"model_weight"}
+
+
+def test_remap_is_idempotent_and_keeps_unknown_keys():
+    from fall_multimodal_b200 import STGCAN
+    from fall_multimodal_b200.checkpoint import remap_reference_state_dict
+    m = STGCAN(3, {"layout": "coco_cut", "strategy": "spatial"}, 11)
+    sd = m.state_dict()
+    once = remap_reference_state_dict({"module." + k.replace("st_gcan_networks", "st_gcn_networks"): v for k, v in sd.items()}, m)
+    assert set(once) == set(sd)
+    assert set(remap_reference_state_dict(once, m)) == set(sd)                       # already-native keys pass through
+    odd = remap_reference_state_dict({"something.else": torch.zeros(1)}, m)
+    assert list(odd) == ["something.else"]                                            # left for load_state_dict(strict) to report

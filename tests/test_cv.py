@@ -46,3 +46,29 @@ def test_run_cv_two_cpu_workers(tmp_path):
         assert r == {k: float(v) for k, v in _fake_fold(f, torch.device("cpu")).items()}
     table = list(csv.reader(open(out)))
     assert table[0] == ["", "precision", "recall", "f1", "accuracy"] and len(table) == 6 and table[3][0] == "2"
+
+
+def test_assign_folds_properties():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 16))
+    def prop(n_folds, n_workers):
+        a = assign_folds(n_folds, n_workers)
+        assert len(a) == n_workers
+        assert sorted(f for w in a for f in w) == list(range(n_folds))               # every fold exactly once
+        sizes = [len(w) for w in a]
+        assert max(sizes) - min(sizes) <= 1                                           # balanced to within one fold
+
+    prop()
+
+
+def test_train_step_and_run_cv_refuse_to_run_without_cuda():
+    import pytest
+    from fall_multimodal_b200.train import TrainStep
+    lin = torch.nn.Linear(4, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        TrainStep(lin, torch.optim.SGD(lin.parameters(), lr=0.1), torch.nn.CrossEntropyLoss(), (torch.zeros(3, 4),), torch.zeros(3, 2))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA devices"):
+            run_cv(_fake_fold, 2)

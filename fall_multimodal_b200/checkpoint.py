@@ -43,13 +43,30 @@ def remap_reference_state_dict(sd: dict, model: torch.nn.Module) -> dict:
     return out
 
 
-def load_reference_checkpoint(model: torch.nn.Module, path_or_obj, strict: bool = True, map_location="cpu") -> dict:
+def load_reference_checkpoint(model: torch.nn.Module, path_or_obj, strict: bool = True, map_location="cpu",
+                              allow_pickle: bool = False) -> dict:
     """Load ``best_model.pt`` / ``checkpoint.pt`` / a bare notebook state_dict into ``model``.
+
+    ``path_or_obj``: a path (``str`` / ``bytes`` / ``os.PathLike``), an open file, or an already loaded object. Files are read
+    with ``weights_only=True`` (tensors and plain containers only); a checkpoint that needs arbitrary pickled classes (e.g. a
+    pickled lr-scheduler object) is refused unless ``allow_pickle=True`` - unpickling runs code from the file.
 
     Returns the rest of the checkpoint (``epoch``, ``optimizer``, ``best_acc`` ... when present) so a resume can
     restore the optimizer exactly as ``F2/main.py:294-303`` does."""
-    obj = torch.load(path_or_obj, map_location=map_location, weights_only=False) if isinstance(path_or_obj, (str, bytes)) or \
-        hasattr(path_or_obj, "read") else path_or_obj
+    import os
+    import pickle
+
+    if isinstance(path_or_obj, (str, bytes, os.PathLike)) or hasattr(path_or_obj, "read"):
+        try:
+            obj = torch.load(path_or_obj, map_location=map_location, weights_only=True)
+        except pickle.UnpicklingError as e:
+            if not allow_pickle:
+                raise RuntimeError(f"checkpoint needs full unpickling ({e}); pass allow_pickle=True if you trust the file") from e
+            if hasattr(path_or_obj, "seek"):
+                path_or_obj.seek(0)
+            obj = torch.load(path_or_obj, map_location=map_location, weights_only=False)
+    else:
+        obj = path_or_obj
     sd = obj["model_weight"] if isinstance(obj, dict) and "model_weight" in obj else obj
     model.load_state_dict(remap_reference_state_dict(sd, model), strict=strict)
     return {k: v for k, v in obj.items() if k != "model_weight"} if isinstance(obj, dict) and "model_weight" in obj else {}

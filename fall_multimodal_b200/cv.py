@@ -40,16 +40,23 @@ def macro_precision_recall_f1(prediction: torch.Tensor, labels: torch.Tensor, nu
 
 
 def _worker(rank: int, devices: Sequence[str], folds: list[list[int]], fold_fn: Callable, queue):
-    dev = torch.device(devices[rank])
-    if dev.type == "cuda":
-        torch.cuda.set_device(dev)
-    for fold in folds[rank]:
-        res = fold_fn(fold, dev)
-        queue.put((fold, {k: float(v) for k, v in res.items()}))
-    queue.put((None, rank))
+    try:
+        dev = torch.device(devices[rank])
+        if dev.type == "cuda":
+            torch.cuda.set_device(dev)
+        for fold in folds[rank]:
+            res = fold_fn(fold, dev)
+            queue.put(("fold", fold, {k: float(v) for k, v in res.items()}))
+        queue.put(("done", rank, None))
+    except BaseException:       # report instead of dying silently: the parent would otherwise wait for the sentinel forever
+        import traceback
+
+        queue.put(("error", rank, traceback.format_exc()))
+        raise
 
 
-def run_cv(fold_fn: Callable, n_folds: int, devices: Sequence[str] | None = None, out_csv: str | None = None):
+def run_cv(fold_fn: Callable, n_folds: int, devices: Sequence[str] | None = None, out_csv: str | None = None,
+           poll_s: float = 5.0):
     """Run ``fold_fn(fold_index, device) -> {"precision","recall","f1","accuracy"}`` for every fold, folds dealt round-robin
     to one process per device. Returns the per-fold dicts in fold order and (optionally) writes the reference's CSV."""
     if devices is None:
@@ -63,13 +70,31 @@ def run_cv(fold_fn: Callable, n_folds: int, devices: Sequence[str] | None = None
     procs = [ctx.Process(target=_worker, args=(r, devices, folds, fold_fn, queue)) for r in range(len(devices))]
     for p in procs:
         p.start()
-    results, done = {}, 0
-    while done < len(procs):
-        fold, payload = queue.get()
-        if fold is None:
+    import queue as _queue
+
+    results, done, failure = {}, 0, None
+    while done < len(procs) and failure is None:
+        try:
+            kind, a, b = queue.get(timeout=poll_s)
+        except _queue.Empty:
+            # no message: a worker that died without reporting (OOM kill, CUDA abort, segfault) never sends its sentinel
+            dead = [r for r, p in enumerate(procs) if not p.is_alive() and p.exitcode not in (0, None)]
+            if dead:
+                failure = f"cross-validation worker {dead[0]} exited with code {procs[dead[0]].exitcode} without a result"
+            continue
+        if kind == "done":
             done += 1
+        elif kind == "error":
+            failure = f"cross-validation worker {a} failed:\n{b}"
         else:
-            results[fold] = payload
+            results[a] = b
+    if failure is not None:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+        for p in procs:
+            p.join()
+        raise RuntimeError(failure)
     for p in procs:
         p.join()
         if p.exitcode != 0:

@@ -34,6 +34,7 @@ class GradBuckets:
         self._comm_stream = None
         self._comm_used = False  # anything queued on the comm stream since the last wait()
         self._handles = []
+        self._hook_handles = []
         for params in groups:
             params = [p for p in params if p.requires_grad]
             if not params:
@@ -50,7 +51,7 @@ class GradBuckets:
             idx = len(self.buckets)
             self.buckets.append(b)
             for p in params:
-                p.register_post_accumulate_grad_hook(self._make_hook(idx))
+                self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(idx)))
         dev = self.buckets[0]["params"][0].device if self.buckets else torch.device("cpu")
         if dev.type == "cuda" and self.world > 1:
             self._comm_stream = torch.cuda.Stream(device=dev)
@@ -87,6 +88,12 @@ class GradBuckets:
             dist.all_reduce(flat, op=op, group=self.pg)
             if self.average:
                 flat.div_(self.world)
+
+    def close(self):
+        """Remove the post-accumulate hooks (a second GradBuckets on the same parameters would otherwise double count)."""
+        for h in self._hook_handles:
+            h.remove()
+        self._hook_handles.clear()
 
     def zero_grad(self):
         """Call instead of ``model.zero_grad()``: gradients become None (no zero-fill, no accumulate kernels)."""

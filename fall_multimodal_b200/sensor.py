@@ -137,7 +137,9 @@ class _LSTMFn(torch.autograd.Function):
             dx = torch.zeros_like(x) if ctx.need_dx else None
             ops.lstm_bwd(x, wi, wh, out, gates, cseq, dout.float().contiguous(), dwi, dwh, db, dx)
         ctx.saved = None
-        return dx, dwi[0], dwh[0], db[0], db[0], dwi[1], dwh[1], db[1], db[1]
+        # b_ih and b_hh receive the same values but must not share storage: autograd adopts the returned tensors as
+        # .grad, and an in-place op on aliased gradients (clip_grad_norm_, a second backward) would hit the memory twice
+        return dx, dwi[0], dwh[0], db[0], db[0].clone(), dwi[1], dwh[1], db[1], db[1].clone()
 
 
 class ChannelAttention(nn.Module):

@@ -158,7 +158,12 @@ def main_tragcn():
     cases = [
         ("targcn_v25_t12", dict(V=25, T=12, B=4, adj=None, fill_seed=5, batch_seed=11)),
         ("targcn_v14_t30_adj", dict(V=14, T=30, B=3, adj="rand", fill_seed=6, batch_seed=12)),
+        # BASELINE config 4's own clip shape (T=300, V=25; SURVEY D5: seq_len re-pointed), a bounded batch
+        ("targcn_v25_t300", dict(V=25, T=300, B=4, adj=None, fill_seed=7, batch_seed=13)),
     ]
+    only = os.environ.get("FMM_GOLDEN_ONLY")
+    if only:
+        cases = [c for c in cases if c[0] in only.split(",")]
     for name, c in cases:
         adj = None
         if c["adj"] == "rand":
@@ -190,6 +195,8 @@ def main_tragcn():
                    os.path.join(OUT, name + ".pt"))
         print(name, "loss", float(loss), "params", sum(p.numel() for p in mod.parameters()))
 
+    if only:
+        return
     # the reference's own bf16 path (MF3/main.py:97 torch.amp.autocast) on CPU: the yardstick for the bf16 gate
     c = dict(V=25, T=16, B=8, fill_seed=2, batch_seed=5)
     with warnings.catch_warnings():

@@ -1,8 +1,10 @@
-"""ORACLE tooling — imports the UNMODIFIED reference modules from /root/reference.
+"""ORACLE tooling — imports the UNMODIFIED reference modules.
 
-Only usable in the build container (the reference tree does not travel to the GPU box); used by
-``oracle/make_golden.py`` to generate the committed fixtures and by the optional local
-cross-check in ``tests/test_oracle.py``. Import recipe: SURVEY.md section 8(c).
+Root: ``$FMM_REFERENCE_ROOT``, else ``/root/reference`` (the build container), else ``oracle/_ref`` — the byte-for-byte staged
+copy ``oracle/build_ref.py`` makes of the hot-path files (git-ignored; it travels to the GPU box with the snapshot so the
+reference arm of ``bench.py`` runs the reference's own code there). Used by ``oracle/make_golden.py`` to generate the
+committed fixtures, by the cross-checks in ``tests/test_oracle.py`` and by ``bench.py --impl reference`` / its
+``cpu_baseline`` leg. Import recipe: SURVEY.md section 8(c).
 """
 from __future__ import annotations
 
@@ -13,7 +15,9 @@ import os
 import sys
 import types
 
-REF = os.environ.get("FMM_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REF = os.environ.get("FMM_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/Fall_2_Spatial_Temporal_SR")
+                                                else _STAGED)
 F2 = os.path.join(REF, "Fall_2_Spatial_Temporal_SR")
 
 

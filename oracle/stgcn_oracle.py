@@ -340,60 +340,7 @@ class _PrefixDict:
 # ------------------------------------------------------------------------------------------------
 # Deterministic parameter fill + synthetic inputs + the train step (F2/main.py:104-132)
 # ------------------------------------------------------------------------------------------------
-def fill_state_dict(shapes, seed=0):
-    """Order-independent deterministic fill: every key gets its own generator seeded by its name.
-
-    Conv/linear weights ~ N(0, 1/fan_in); biases small; BN weight in [0.5,1.5]; running stats
-    plausible; edge_importance around 1; ``A`` is NOT filled here (build_adjacency provides it).
-    """
-    import zlib
-    sd = {}
-    for k, shp in shapes.items():
-        g = torch.Generator().manual_seed((zlib.crc32(k.encode()) + seed) % (2 ** 31))
-        if k == "A" or k.endswith(".A"):
-            continue
-        if k.endswith("num_batches_tracked"):
-            sd[k] = torch.zeros((), dtype=torch.long)
-        elif k.endswith("running_mean"):
-            sd[k] = torch.randn(shp, generator=g) * 0.1
-        elif k.endswith("running_var"):
-            sd[k] = torch.rand(shp, generator=g) + 0.5
-        elif "edge_importance" in k:
-            sd[k] = 1.0 + 0.2 * torch.randn(shp, generator=g)
-        elif k.endswith("bias"):
-            sd[k] = torch.randn(shp, generator=g) * 0.1
-        elif len(shp) == 1:  # BN / norm weight
-            sd[k] = torch.rand(shp, generator=g) + 0.5
-        else:
-            fan_in = int(np.prod(shp[1:]))
-            sd[k] = torch.randn(shp, generator=g) / math.sqrt(fan_in)
-    return sd
-
-
-def synthetic_batch(N, T, V, num_class=11, sensor_len=30, sensor_ch=15, seed=42, per_clip=True):
-    """xy in [-1,1], score ~ U(0,1), sensor ~ N(0,1), label-smoothed soft targets.
-
-    ``per_clip`` gives every clip its own pose scale/offset and sensor gain (different subjects at
-    different positions). Without it all clips have near-identical pooled statistics and the
-    squeeze-excite BatchNorm over N (stgcan.py:66) becomes ill-conditioned: its output is then
-    dominated by fp32 rounding and no two correct fp32 implementations agree to 1e-4.
-    """
-    g = torch.Generator().manual_seed(seed)
-    skel = torch.empty(N, 3, T, V)
-    skel[:, :2] = torch.rand(N, 2, T, V, generator=g) * 2 - 1
-    skel[:, 2] = torch.rand(N, T, V, generator=g)
-    sensor = torch.randn(N, sensor_len, sensor_ch, generator=g)
-    if per_clip:
-        scale = 0.3 + 0.7 * torch.rand(N, 1, 1, 1, generator=g)
-        off = torch.rand(N, 2, 1, 1, generator=g) - 0.5
-        skel[:, :2] = (skel[:, :2] * scale * 0.5 + off).clamp(-1, 1)
-        skel[:, 2:] = skel[:, 2:] * (0.5 + 0.5 * torch.rand(N, 1, 1, 1, generator=g))
-        sensor = sensor * (0.5 + torch.rand(N, 1, 1, generator=g)) + 0.3 * torch.randn(N, 1, sensor_ch, generator=g)
-    labels = torch.randint(0, num_class, (N,), generator=g)
-    eps = 0.1
-    target = torch.full((N, num_class), eps / (num_class - 1))
-    target[torch.arange(N), labels] = 1 - eps
-    return skel, sensor, target, labels
+from synth import fill_state_dict, synthetic_batch  # noqa: E402,F401  (generators live in /synth.py)
 
 
 def soft_ce(logits, target):

@@ -32,14 +32,7 @@ def sym_norm_adj(adj: torch.Tensor) -> torch.Tensor:
     return F.softmax(torch.from_numpy(out).to(torch.float32), dim=1)
 
 
-def positional_encoding(T: int, C: int) -> torch.Tensor:
-    """TA.py:73-83 -> (1, T, 1, C)."""
-    pe = torch.zeros(T, C)
-    position = torch.arange(0, T).unsqueeze(1)
-    div_term = torch.exp(torch.arange(0, C, 2) * -(math.log(10000.0) / C))
-    pe[:, 0::2] = torch.sin(position * div_term)
-    pe[:, 1::2] = torch.cos(position * div_term)
-    return pe.unsqueeze(0).unsqueeze(2)
+from synth import fill_targcn, positional_encoding, synthetic_clips  # noqa: E402,F401  (generators live in /synth.py)
 
 
 def emb_gcn_invariants(sd, prefix, E, sym):
@@ -144,38 +137,3 @@ def targcn_param_shapes(V=25, T=30, D=3, H=64, E=64, horizon=30, output_dim=64, 
     return sh
 
 
-def fill_targcn(shapes, seed=0):
-    """Deterministic, order-independent fill (per-key generators) scaled so the recurrence is lively:
-    pools ~ N(0, 0.02^2... scaled by fan-in), embeddings ~ N(0,1) like the reference constructor."""
-    import zlib
-    sd = {}
-    for k, shp in shapes.items():
-        g = torch.Generator().manual_seed((zlib.crc32(k.encode()) + seed) % (2 ** 31))
-        if k.endswith("PE.pe"):
-            sd[k] = positional_encoding(shp[1], shp[3])
-        elif k == "node_embeddings":
-            sd[k] = torch.randn(shp, generator=g) * 0.5
-        elif k.endswith("weights_pool"):
-            sd[k] = torch.randn(shp, generator=g) / math.sqrt(shp[0] * shp[1]) * 2.0
-        elif k.endswith("bias_pool"):
-            sd[k] = torch.randn(shp, generator=g) * 0.02
-        elif k.endswith("bias"):
-            sd[k] = torch.randn(shp, generator=g) * 0.1
-        elif len(shp) == 1:
-            sd[k] = torch.rand(shp, generator=g) + 0.5
-        else:
-            sd[k] = torch.randn(shp, generator=g) / math.sqrt(int(np.prod(shp[1:])))
-    return sd
-
-
-def synthetic_clips(B, T, V, D=3, num_class=11, seed=42):
-    """(B,T,V,D) poses in [-1,1] with a per-clip modulation + soft targets."""
-    g = torch.Generator().manual_seed(seed)
-    x = torch.rand(B, T, V, D, generator=g) * 2 - 1
-    x[..., 2] = torch.rand(B, T, V, generator=g)
-    x = x * (0.5 + torch.rand(B, 1, 1, 1, generator=g)) + 0.3 * torch.randn(B, 1, 1, D, generator=g)
-    lab = torch.randint(0, num_class, (B,), generator=g)
-    tgt = torch.full((B, num_class), 0.1 / (num_class - 1))
-    tgt[torch.arange(B), lab] = 0.9
-    tgt = tgt * (0.5 + 0.5 * torch.rand(B, 1, generator=g))
-    return x, tgt

@@ -72,3 +72,28 @@ def test_train_step_and_run_cv_refuse_to_run_without_cuda():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="CUDA devices"):
             run_cv(_fake_fold, 2)
+
+
+def _failing_fold(fold, device):
+    if fold == 1:
+        raise ValueError("fold 1 blew up")
+    return {"precision": 1.0, "recall": 1.0, "f1": 1.0, "accuracy": 1.0}
+
+
+def _dying_fold(fold, device):
+    import os
+    if fold == 0:
+        os._exit(7)                 # dies without a traceback or a sentinel (what an OOM kill looks like)
+    return {"precision": 1.0, "recall": 1.0, "f1": 1.0, "accuracy": 1.0}
+
+
+def test_run_cv_reports_worker_exception_instead_of_hanging():
+    import pytest
+    with pytest.raises(RuntimeError, match="fold 1 blew up"):
+        run_cv(_failing_fold, 4, devices=["cpu", "cpu"], poll_s=0.2)
+
+
+def test_run_cv_detects_dead_worker():
+    import pytest
+    with pytest.raises(RuntimeError, match="exited with code 7"):
+        run_cv(_dying_fold, 2, devices=["cpu", "cpu"], poll_s=0.2)

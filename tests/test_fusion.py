@@ -221,9 +221,22 @@ def test_three_stream_matches_oracle():
     skel, _, target, _ = O.synthetic_batch(N, T, V, 11, seed=23)
     skel, target = skel.to(dev), target.to(dev)
     osd = {k: (v.detach().double().clone() if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    for k, v in osd.items():
+        if v.is_floating_point() and "running_" not in k and not k.endswith(".A"):
+            v.requires_grad_(True)
     oout = O.three_stream_forward(osd, skel.double(), m.parents, training=True)
+    O.soft_ce(oout, target.double()).backward()
     out = m(skel, None)
     torch.nn.CrossEntropyLoss()(out, target).backward()
     err = (out.double() - oout).abs().max().item() / oout.abs().max().item()
     assert err < 1e-4, err
-    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    assert torch.equal(out.argmax(-1), oout.argmax(-1))
+    gs = max(v.grad.abs().max().item() for v in osd.values() if v.is_floating_point() and v.grad is not None)
+    worst = 0.0
+    for k, p in m.named_parameters():
+        r = osd[k].grad
+        assert p.grad is not None and r is not None, k
+        scale = max(r.abs().max().item(), (1.0 if k.endswith(ZERO_GRAD_SUFFIXES) else 1e-3) * gs)
+        worst = max(worst, (p.grad.double() - r).abs().max().item() / scale)
+    print(f"three-stream fp32: logits {err:.2e}, worst gradient err {worst:.2e} (all three trunks + fc, natural ReLU decisions)")
+    assert worst < 5e-2      # a single flipped ReLU decision moves a gradient by a whole element at N=6; see test_stgcan.py

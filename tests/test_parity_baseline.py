@@ -1,0 +1,284 @@
+"""GPU parity AT THE SHAPES BASELINE.json QUOTES: the configurations bench.py times are the ones pinned here.
+
+  * config 2 — TwoStreamSTGCAN_CNN1D, T=64, V=33 (mediapipe33, spatial K=3), sensor 30x15: fp32 and bf16 at N=64 against the
+    fp64 oracle (logits, loss, every gradient), bf16 also at the bench batch N=256;
+  * config 4 — TARGCN at T=300, V=25 against a fixture generated from the UNMODIFIED reference (oracle/make_golden.py);
+  * config 5 — BiLSTM inference on 8192 windows of 128 x 6 against the oracle;
+  * data parallel — two NCCL ranks of the real fusion model: all-reduced gradients == mean of the single-GPU shard gradients
+    (skipped with fewer than two GPUs).
+
+Tolerances (north_star): fp32 1e-4 relative to the tensor's max magnitude; bf16 2e-2 on the logits; labels identical wherever
+the exact top-2 margin exceeds the logit tolerance (mismatches are counted and printed with their margins). bf16 gradients are
+reported in three metrics per tensor — max-abs / max (the flip-sensitive one), relative L2 and cosine — next to the same
+metrics of torch's own bf16 autocast path on the same inputs, all against the fp64 truth.
+"""
+import os
+import socket
+import statistics
+
+import pytest
+import torch
+
+from oracle import stgcn_oracle as O
+from oracle import tragcn_oracle as TO
+from tests.golden_util import ZERO_GRAD_SUFFIXES, check_summary, load
+
+gpu = pytest.mark.gpu
+T, V, L, CS, NC = 64, 33, 30, 15, 11
+
+
+def _fusion(dev, seed=0):
+    import fall_multimodal_b200 as fmm
+
+    m = fmm.TwoStreamSTGCAN_CNN1D(3, {"layout": "mediapipe33", "strategy": "spatial"}, NC, CS, L)
+    sd = m.state_dict()
+    sd.update(O.fill_state_dict({k: tuple(v.shape) for k, v in sd.items()}, seed))
+    m.load_state_dict(sd)
+    return m.to(dev).train()
+
+
+def _oracle_grads(m, skel, sensor, target, dtype, autocast=False):
+    """Oracle restatement of the same model on the GPU (fp64 = truth; fp32 + autocast = torch's own bf16 path)."""
+    sd = {k: (v.detach().to(dtype).clone() if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k and not k.endswith(".A") and not k.startswith("cnn.fc"):
+            v.requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        out = O.two_stream_cnn_forward(sd, skel.to(dtype), sensor.to(dtype), training=True)
+        loss = O.soft_ce(out, target.to(dtype))
+    loss.backward()
+    return out.detach(), float(loss), {k: v.grad for k, v in sd.items() if v.is_floating_point() and v.grad is not None}
+
+
+def _metrics(g, r, floor):
+    g, r = g.double().flatten(), r.double().flatten()
+    maxrel = (g - r).abs().max().item() / max(r.abs().max().item(), floor)
+    rl2 = (g - r).norm().item() / max(r.norm().item(), floor * r.numel() ** 0.5)
+    cos = torch.dot(g, r).item() / max(g.norm().item() * r.norm().item(), 1e-300)
+    return maxrel, rl2, cos
+
+
+def _label_report(out, truth, tol):
+    top2 = truth.topk(2, dim=-1).values
+    margin = (top2[:, 0] - top2[:, 1]) / truth.abs().max()
+    mism = (out.argmax(-1) != truth.argmax(-1)).nonzero().flatten().tolist()
+    rows = [(i, float(margin[i])) for i in mism]
+    undecided = [i for i, mg in rows if mg <= 2 * tol]
+    decided_bad = [i for i, mg in rows if mg > 2 * tol]
+    return rows, undecided, decided_bad
+
+
+@gpu
+@pytest.mark.timeout(1200)
+def test_config2_fp32_n64_matches_fp64_oracle():
+    dev = torch.device("cuda:0")
+    m = _fusion(dev)
+    m.compute_dtype = torch.float32
+    skel, sensor, target, _ = O.synthetic_batch(64, T, V, NC, sensor_len=L, sensor_ch=CS, seed=42)
+    skel, sensor, target = skel.to(dev), sensor.to(dev), target.to(dev)
+    truth, tloss, tg = _oracle_grads(m, skel, sensor, target, torch.float64)
+    out = m(skel, sensor)
+    loss = torch.nn.CrossEntropyLoss()(out, target)
+    loss.backward()
+    torch.cuda.synchronize()
+    err = (out.double() - truth).abs().max().item() / truth.abs().max().item()
+    assert err < 1e-4, f"fp32 logits err {err:.3e}"
+    assert abs(loss.item() - tloss) < 1e-4 * max(1.0, abs(tloss))
+    rows, undecided, bad = _label_report(out.double(), truth, 1e-4)
+    print(f"config2 fp32 N=64: logits {err:.2e}; label mismatches {rows}")
+    assert not rows, f"fp32 labels differ: {rows}"
+    gs = max(g.abs().max().item() for g in tg.values())
+    worst, worst_k = 0.0, None
+    for k, p in m.named_parameters():
+        if k.startswith("cnn.fc"):
+            continue
+        floor = (1.0 if k.endswith(ZERO_GRAD_SUFFIXES) else 1e-3) * gs
+        e = _metrics(p.grad, tg[k], floor)[0]
+        if e > worst:
+            worst, worst_k = e, k
+    print(f"config2 fp32 N=64: worst gradient err {worst:.2e} ({worst_k}) vs fp64 oracle, natural ReLU decisions")
+    assert worst < 1e-4, f"{worst_k}: {worst:.3e}"
+
+
+def _bf16_case(N):
+    dev = torch.device("cuda:0")
+    m = _fusion(dev)
+    skel, sensor, target, _ = O.synthetic_batch(N, T, V, NC, sensor_len=L, sensor_ch=CS, seed=42)
+    skel, sensor, target = skel.to(dev), sensor.to(dev), target.to(dev)
+    truth, tloss, tg = _oracle_grads(m, skel, sensor, target, torch.float64)
+    _, _, ag = _oracle_grads(m, skel, sensor, target, torch.float32, autocast=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(skel, sensor)
+        assert out.dtype == torch.bfloat16
+        loss = torch.nn.CrossEntropyLoss()(out.float(), target)
+    loss.backward()
+    torch.cuda.synchronize()
+    err = (out.double() - truth).abs().max().item() / truth.abs().max().item()
+    rows, undecided, bad = _label_report(out.double(), truth, 2e-2)
+    print(f"config2 bf16 N={N}: logits err {err:.2e}, loss {loss.item():.5f} vs {tloss:.5f}; label mismatches (row, margin/max): {rows}")
+    assert err < 2e-2, f"bf16 logits err {err:.3e}"
+    assert abs(loss.item() - tloss) < 2e-2 * max(1.0, abs(tloss))
+    assert not bad, f"labels differ where the exact margin exceeds the tolerance: {bad}"
+    assert len(rows) <= max(1, N // 32), f"too many label mismatches: {rows}"
+    gs = max(g.abs().max().item() for g in tg.values())
+    mine, auto = {}, {}
+    for k, p in m.named_parameters():
+        if k.startswith("cnn.fc") or k.endswith(ZERO_GRAD_SUFFIXES):
+            continue
+        floor = 2e-2 * gs
+        mine[k] = _metrics(p.grad, tg[k], floor)
+        auto[k] = _metrics(ag[k], tg[k], floor)
+    med = lambda d, i: statistics.median(v[i] for v in d.values())
+    worst = lambda d, i: max(v[i] for v in d.values())
+    print(f"config2 bf16 N={N} gradients vs fp64 truth (ours | torch autocast): "
+          f"max-abs/max median {med(mine, 0):.2e} | {med(auto, 0):.2e}, worst {worst(mine, 0):.2e} | {worst(auto, 0):.2e}; "
+          f"rel-L2 median {med(mine, 1):.2e} | {med(auto, 1):.2e}, worst {worst(mine, 1):.2e} | {worst(auto, 1):.2e}; "
+          f"cosine min {min(v[2] for v in mine.values()):.5f} | {min(v[2] for v in auto.values()):.5f}")
+    # gates: no worse than the reference's own bf16 path in every metric, plus absolute floors on direction and size
+    assert med(mine, 0) <= 1.1 * med(auto, 0) and worst(mine, 0) <= 1.25 * worst(auto, 0)
+    assert med(mine, 1) <= 1.1 * med(auto, 1) and worst(mine, 1) <= 1.25 * worst(auto, 1)
+    assert min(v[2] for v in mine.values()) >= min(0.98, min(v[2] for v in auto.values()) - 5e-3)
+
+
+@gpu
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("N", [64, 256])
+def test_config2_bf16_bench_shape(N):
+    _bf16_case(N)
+
+
+@gpu
+@pytest.mark.timeout(1200)
+def test_targcn_t300_v25_matches_reference_fixture():
+    """BASELINE config 4's clip shape against the unmodified reference (SURVEY D5 seq_len patch), fp32."""
+    from fall_multimodal_b200.tragcn import TARGCN
+
+    fx = load("targcn_v25_t300")
+    c = fx["config"]
+    dev = torch.device("cuda:0")
+    m = TARGCN(num_nodes=c["V"], adj=None, seq_len=c["T"])
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert shapes == fx["shapes"]
+    m.load_state_dict(TO.fill_targcn(shapes, c["fill_seed"]))
+    m = m.to(dev).train()
+    assert sum(p.numel() for p in m.parameters()) == fx["n_params"]
+    x, tgt = TO.synthetic_clips(c["B"], c["T"], c["V"], seed=c["batch_seed"])
+    logits = m(x.to(dev))
+    loss = torch.nn.CrossEntropyLoss()(logits, tgt.to(dev))
+    loss.backward()
+    ref = fx["logits"]
+    err = (logits.cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-4, err
+    assert abs(loss.item() - fx["loss"]) < 1e-4 * max(1.0, abs(fx["loss"]))
+    assert (logits.argmax(1).cpu() == ref.argmax(1)).all()
+    gs = max(v["amax"] if "amax" in v else float(v["full"].abs().max()) for v in fx["grads"].values())
+    worst = 0.0
+    for k, p in m.named_parameters():
+        worst = max(worst, check_summary(k, p.grad, fx["grads"][k], 1e-4, atol_scale=1e-3 * gs))
+    print(f"targcn T=300 V=25 B={c['B']}: logits {err:.2e}, worst gradient err {worst:.2e} vs the reference fixture")
+
+
+@gpu
+@pytest.mark.timeout(600)
+def test_bilstm_inference_8192x128x6_matches_oracle():
+    """BASELINE config 5: sensor-only BiLSTM inference on HAR-shaped windows, the whole 8192-window batch."""
+    from fall_multimodal_b200 import BiLSTM
+
+    dev = torch.device("cuda:0")
+    m = BiLSTM(6, 64, 1, 0.3, NC, "mean")
+    sd = m.state_dict()
+    sd.update(O.fill_state_dict({k: tuple(v.shape) for k, v in sd.items()}, 12))
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(8192, 128, 6, generator=g) * (0.5 + torch.rand(8192, 1, 1, generator=g))).to(dev)
+    with torch.no_grad():
+        out = m(None, x)
+        osd = {k: (v.detach().double() if v.is_floating_point() else v) for k, v in m.state_dict().items()}
+        ref = O.bilstm_forward(osd, x.double(), training=False, feature="mean")
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    mism = int((out.argmax(-1) != ref.argmax(-1)).sum())
+    print(f"BiLSTM 8192x128x6 inference: logits err {err:.2e}, label mismatches {mism}")
+    assert err < 1e-4 and mism == 0
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# two NCCL ranks of the real model
+# --------------------------------------------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from fall_multimodal_b200.parallel import GradBuckets
+
+    Tn, n_per = 16, 8
+    m = _fusion(dev, seed=3)
+    m.compute_dtype = torch.float32
+    buckets = GradBuckets([list(m.fc.parameters()) + list(m.cnn.parameters()), list(m.stgcan_2.parameters()),
+                           list(m.stgcan_1.parameters())])
+    skel, sensor, target, _ = O.synthetic_batch(world * n_per, Tn, V, NC, sensor_len=L, sensor_ch=CS, seed=77)
+    sl = slice(rank * n_per, (rank + 1) * n_per)
+    loss_fn = torch.nn.CrossEntropyLoss()
+
+    def shard_grads(model, s):
+        for p in model.parameters():
+            p.grad = None
+        loss_fn(model(skel[s].to(dev), sensor[s].to(dev)), target[s].to(dev)).backward()
+        return {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    for _ in range(2):                      # second pass: zero_grad re-arms the hooks
+        buckets.zero_grad()
+        loss_fn(m(skel[sl].to(dev), sensor[sl].to(dev)), target[sl].to(dev)).backward()
+        buckets.wait()
+    torch.cuda.synchronize()
+    got = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    buckets.close()
+    ok, worst = True, 0.0
+    if rank == 0:
+        # the same weights, each shard on this single GPU, no process group involved in the backward
+        state = {k: v.clone() for k, v in m.state_dict().items()}
+        per = []
+        for r in range(world):
+            m.load_state_dict(state)        # running stats back to the pre-step values
+            per.append(shard_grads(m, slice(r * n_per, (r + 1) * n_per)))
+        gs = max(g.abs().max().item() for g in per[0].values())
+        for k in got:
+            want = sum(p[k] for p in per) / world
+            e = (got[k] - want).abs().max().item() / max(want.abs().max().item(), 1e-3 * gs)
+            worst = max(worst, e)
+        ok = worst < 1e-5
+    q.put((rank, ok, worst))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@gpu
+@pytest.mark.timeout(900)
+def test_data_parallel_nccl_two_ranks_matches_shard_mean():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    print("DP (2 NCCL ranks) gradient err vs mean of shard gradients:", res)
+    assert all(ok for _, ok, _ in res), res

@@ -34,7 +34,8 @@ def build_from_fixture(fx, dev, compute_dtype):
     return m, skel, target.to(dev)
 
 
-FLIP_TOL = 5e-2  # fixture gradients: sanity bound that tolerates single-element ReLU decision flips
+FLIP_TOL = 5e-2  # fixture gradients when a ReLU decision flipped (one flip moves a gradient by a whole element at these
+#                   tiny batch sizes); with zero flips the fixture is held to the north-star 1e-4 like everything else
 
 
 def oracle_with_masks(m, fx, skel, target, dev):
@@ -111,10 +112,10 @@ def test_stgcan_fp32_matches_reference_fixture(name):
     if fx["config"]["num_class"]:
         assert torch.equal(out.argmax(-1), ref.argmax(-1))
     grads = {k: p.grad for k, p in m.named_parameters()}
-    # (1) against the reference's own gradients (fixture): flips of single ReLU decisions allowed
-    worst_fx = check_grads(grads, fx["grads"], FLIP_TOL)
     # (2) strict: against the fp64 oracle evaluated with the SAME ReLU decisions
     ograds, oout, flips, worst_pre = oracle_with_masks(m, fx, skel, target, dev)
+    # (1) against the reference's own gradients (fixture): 1e-4 unless a ReLU decision differs from exact arithmetic
+    worst_fx = check_grads(grads, fx["grads"], FP32_TOL if flips == 0 else FLIP_TOL)
     assert (out.double() - oout).abs().max().item() / oout.abs().max().item() < FP32_TOL
     assert worst_pre < 1e-4, f"a ReLU decision differs at |x|/max = {worst_pre:.2e}: not a rounding-level flip"
     gs = max(g.abs().max().item() for g in ograds.values())

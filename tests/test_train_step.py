@@ -55,3 +55,79 @@ def test_train_step_matches_eager_loop(use_graph):
     assert abs(top1 - hits / 24) <= 1 / 24 + 1e-9
     # (parameters are not compared one by one: RMSprop's first steps move zero-gradient parameters, e.g. conv biases in
     # front of a train-mode BatchNorm, by +-lr/sqrt(1-alpha) with the sign of rounding noise)
+
+
+@gpu
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_matches_oracle_loop(use_graph):
+    """TrainStep against the ORACLE's train loop (the restated reference model + torch RMSprop, fp64 on the same device),
+    three consecutive steps in fp32 compute: every step's loss, the running top-1 count, and - because constructing a
+    TrainStep must not perturb the trajectory - the model / optimizer state right after construction."""
+    import fall_multimodal_b200 as fmm
+    from fall_multimodal_b200.train import TrainStep
+
+    dev = torch.device("cuda:0")
+    m = fmm.TwoStreamSTGCAN_CNN1D(3, {"layout": "coco_cut", "strategy": "spatial"}, 11, 15, 30)
+    sd = m.state_dict()
+    sd.update(O.fill_state_dict({k: tuple(v.shape) for k, v in sd.items()}, 31))
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    batches = [O.synthetic_batch(8, 16, 14, 11, sensor_len=30, sensor_ch=15, seed=s)[:3] for s in (4, 5, 6)]
+    # --- oracle loop (F2/main.py:104-132 restated): fp64, same RMSprop hyper-parameters ---
+    osd = {k: (v.detach().double().clone() if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    oparams = [v.requires_grad_(True) for k, v in osd.items()
+               if v.is_floating_point() and "running_" not in k and not k.endswith(".A") and not k.startswith("cnn.fc")]
+    oopt = torch.optim.RMSprop(oparams, lr=1e-4)
+    ref_losses, ref_hits = [], 0
+    for skel, sensor, tgt in batches:
+        oopt.zero_grad(set_to_none=True)
+        out = O.two_stream_cnn_forward(osd, skel.to(dev).double(), sensor.to(dev).double(), training=True)
+        loss = O.soft_ce(out, tgt.to(dev).double())
+        loss.backward()
+        oopt.step()
+        ref_losses.append(loss.item())
+        ref_hits += int((out.argmax(-1) == tgt.to(dev).argmax(-1)).sum())
+    # --- TrainStep ---
+    opt = torch.optim.RMSprop(m.parameters(), lr=1e-4, capturable=True)
+    before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ts = TrainStep(m, opt, torch.nn.CrossEntropyLoss(), tuple(t.to(dev) for t in batches[0][:2]), batches[0][2].to(dev),
+                   autocast_dtype=None, use_graph=use_graph, warmup=2)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), f"constructing TrainStep changed {k}"
+    for st in opt.state.values():
+        for k, v in st.items():
+            if torch.is_tensor(v):
+                assert float(v.abs().max()) == 0.0, f"optimizer state {k} not rolled back"
+    losses = [ts.run((skel.pin_memory(), sensor.pin_memory()), tgt.pin_memory()).item() for skel, sensor, tgt in batches]
+    mean_loss, top1 = ts.stats()
+    print("train-step losses", losses, "oracle", ref_losses)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (losses, ref_losses)
+    assert abs(mean_loss - sum(ref_losses) / 3) < 2e-4 * max(1.0, abs(sum(ref_losses) / 3))
+    assert abs(top1 - ref_hits / 24) <= 1 / 24 + 1e-9
+    ts.close()
+
+
+@gpu
+def test_train_step_follows_lr_changes_under_graph():
+    """A scheduler that ASSIGNS param_group['lr'] (timm / the reference's optimizer.py) and one that fills the tensor must both
+    reach the captured optimizer step: replay with lr=0 leaves the weights untouched, a later non-zero lr moves them."""
+    import fall_multimodal_b200 as fmm
+    from fall_multimodal_b200.train import TrainStep
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    m = fmm.TwoStreamSTGCAN_CNN1D(3, {"layout": "coco_cut", "strategy": "spatial"}, 11, 15, 30).to(dev).train()
+    skel, sensor, tgt = (t.to(dev) for t in O.synthetic_batch(8, 16, 14, 11, sensor_len=30, sensor_ch=15, seed=9)[:3])
+    opt = torch.optim.RMSprop(m.parameters(), lr=1e-3, capturable=True)
+    with pytest.raises(ValueError):
+        TrainStep(m, torch.optim.RMSprop(m.parameters(), lr=1e-3), torch.nn.CrossEntropyLoss(), (skel, sensor), tgt)
+    ts = TrainStep(m, opt, torch.nn.CrossEntropyLoss(), (skel, sensor), tgt, use_graph=True, warmup=1)
+    w0 = m.fc.weight.detach().clone()
+    opt.param_groups[0]["lr"] = 0.0                 # assignment, as timm-style schedulers do
+    ts.run((skel, sensor), tgt)
+    assert torch.equal(m.fc.weight, w0), "lr=0 still moved the weights: the captured step ignores lr updates"
+    ts.set_lr(1e-3)
+    ts.run((skel, sensor), tgt)
+    assert not torch.equal(m.fc.weight, w0)
+    ts.close()

@@ -93,6 +93,9 @@ _SIGNATURES = {
                          C.POINTER(c_int), c_int, _P],
     "fmm_tapconv": [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                     c_int, c_int, c_int, c_int, C.POINTER(c_int), c_int, _P, _P],
+    "fmm_gcn_packed_bytes": [c_int, c_int, c_int],
+    "fmm_gcn_pack": [_P, _P, c_int, c_int, c_int, _P],
+    "fmm_gcn_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "fmm_agg_fwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_dcoef": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
@@ -136,7 +139,7 @@ _SIGNATURES = {
     "fmm_tg_relu_mask": [_P, _P, c_ll, c_int, _P],
     "fmm_tg_transpose": [_P, _P, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_int, c_int, c_int, _P],
 }
-_RESTYPES = {"fmm_tapconv_packed_bytes": c_ll}
+_RESTYPES = {"fmm_tapconv_packed_bytes": c_ll, "fmm_gcn_packed_bytes": c_ll}
 
 
 class BgemmDesc(C.Structure):

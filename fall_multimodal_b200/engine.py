@@ -67,6 +67,8 @@ class TrunkEngine:
         # they overlap the dgrad -> BatchNorm-backward -> aggregation chain of the same and later blocks.
         self.materialize_h = True  # bf16: write relu(bn1(G)) once instead of transforming it in two GEMM prologues
         self.overlap_wgrad = False  # measured: no gain, two persistent GEMM CTAs cannot share an SM
+        self.fused_gcn = True        # bf16, C % 64 == 0: csrc/gcn.cu instead of agg_fwd + 1x1 tapconv + colstats
+        self.fused_gcn_wgrad = False  # weight gradient re-derives the aggregated operand (no saved Xa)
         self._wstreams = {}
 
     def csr(self, device):
@@ -124,17 +126,25 @@ class TrunkEngine:
             bg = P[pre + "gcn.conv.bias"].view(K, Cout)
             bias_eff = (colsum.t() @ bg).contiguous()              # (V, Cout)
             Wg = P[pre + "gcn.conv.weight"]
-            Xa = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
-            ops.agg_fwd(x, Xa, csr["fwd_rowptr"], csr["fwd_src"], coef_f, K)
-            pw_g = ops.tapconv_pack(Wg, Cout, K * Cin, Cout, Cin, 0, Cin, Cout * Cin, 1, 0, [0], dt)
             G = torch.empty(N, T, V, Cout, dtype=dt, device=dev)
-            ops.tapconv(Xa, pw_g, G, shifts=[0], tj=T, bias=bias_eff, bias_per_joint=True)
-
-            # BN1 statistics (stgcan.py:112), applied inside the temporal conv's prologue
             a1, b1, mean1, rstd1 = (torch.empty(Cout, dtype=torch.float32, device=dev) for _ in range(4))
             st = arena.f64(2 * NR * Cout)
-            if training:
-                ops.colstats(G, st[:NR * Cout], st[NR * Cout:])
+            fused = self.fused_gcn and ops.gcn_supported(dt, Cin, Cout, V)
+            if fused:
+                # north-star graph conv: adjacency aggregation in the tcgen05 GEMM prologue, BN1 statistics in its epilogue
+                # (csrc/gcn.cu); the K-times wider aggregated tensor only reaches HBM while the old wgrad still wants it
+                Xa = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev) if (need_grad and not self.fused_gcn_wgrad) else None
+                ops.gcn_fwd(x, ops.gcn_pack(Wg.view(K * Cout, Cin), K, Cin, Cout), G, csr["fwd_rowptr"], csr["fwd_src"], coef_f, K,
+                            bias=bias_eff, ch_sum=st[:NR * Cout] if training else None,
+                            ch_sq=st[NR * Cout:] if training else None, xa=Xa)
+            else:
+                Xa = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
+                ops.agg_fwd(x, Xa, csr["fwd_rowptr"], csr["fwd_src"], coef_f, K)
+                pw_g = ops.tapconv_pack(Wg, Cout, K * Cin, Cout, Cin, 0, Cin, Cout * Cin, 1, 0, [0], dt)
+                ops.tapconv(Xa, pw_g, G, shifts=[0], tj=T, bias=bias_eff, bias_per_joint=True)
+                # BN1 statistics (stgcan.py:112), applied inside the temporal conv's prologue
+                if training:
+                    ops.colstats(G, st[:NR * Cout], st[NR * Cout:])
             ops.bn_finalize(st[:NR * Cout], st[NR * Cout:], N * T * V, P[pre + "tcn.0.weight"], P[pre + "tcn.0.bias"],
                             P[pre + "tcn.0.running_mean"], P[pre + "tcn.0.running_var"], training, a1, b1, mean1, rstd1)
 

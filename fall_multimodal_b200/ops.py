@@ -119,6 +119,41 @@ def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, shifts, istrid
 
 
 # ---------------------------------------------------------------------------------------------
+# fused spatial graph convolution (csrc/gcn.cu): aggregation in the GEMM prologue, BN statistics in the epilogue
+# ---------------------------------------------------------------------------------------------
+def gcn_supported(x_dtype, cin: int, cout: int, V: int) -> bool:
+    return x_dtype == torch.bfloat16 and cin % 64 == 0 and cout % 64 == 0 and cout <= 256 and cin <= 512 and V <= 33
+
+
+def gcn_pack(w: torch.Tensor, K: int, cin: int, cout: int) -> torch.Tensor:
+    """W fp32 (K*Cout, Cin[,1,1]) -> tensor-core operand images for `gcn_fwd`."""
+    L.require_device(w)
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.numel() == K * cout * cin
+    lib = L.load()
+    out = torch.empty(lib.fmm_gcn_packed_bytes(K, cin, cout), dtype=torch.uint8, device=w.device)
+    L.check(lib.fmm_gcn_pack(L.ptr(w), L.ptr(out), K, cin, cout, L.stream()), "gcn_pack")
+    return out
+
+
+def gcn_fwd(x, wpk, g, rowptr, src, coef, K, bias=None, ch_sum=None, ch_sq=None, xa=None):
+    """g = bias[v] + aggregate(x, edges) @ W^T over the flat rows of channels-last bf16 ``x`` (N,T,V,Cin) -> ``g`` (N,T,V,Cout)."""
+    L.require_device(x)
+    N, Tn, V, Cin = x.shape
+    Cout = g.shape[-1]
+    assert x.is_contiguous() and g.is_contiguous() and x.dtype == g.dtype == torch.bfloat16 and g.shape[:3] == x.shape[:3]
+    assert xa is None or (xa.is_contiguous() and xa.shape == (N, Tn, V, K * Cin) and xa.dtype == x.dtype)
+    rows = N * Tn * V
+
+    def run():
+        L.check(L.load().fmm_gcn_fwd(L.ptr(x), L.ptr(g), L.ptr(xa), L.ptr(wpk), L.ptr(bias), L.ptr(rowptr), L.ptr(src),
+                                     L.ptr(coef), L.ptr(ch_sum), L.ptr(ch_sq), _nrep(ch_sum, Cout), rows, V, K, Cin, Cout,
+                                     src.numel(), L.ptr(err_word(x.device)), L.stream()), "gcn_fwd")
+        return g
+
+    return _timed("gcn_fwd", 2.0 * rows * K * Cin * Cout, float(x.numel() + g.numel()) * 2, run)
+
+
+# ---------------------------------------------------------------------------------------------
 # memory-bound kernels (csrc/elementwise.cu) and per-channel/per-clip kernels (csrc/tiny.cu)
 # ---------------------------------------------------------------------------------------------
 def _shape4(x):

@@ -66,6 +66,20 @@ int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, c
               long long s_m, long long s_c1, long long s_c2, long long s_co, int dtype, unsigned* err,
               cudaStream_t stream);
 
+/* Fused spatial graph convolution (stgcan.py:50-56 + the A*edge_importance product of :222), bf16 activations:
+ *   g[r][co] = bias[v(r)][co] + sum_k sum_ci (sum_{e in in(k,v(r))} coef[e] * x[frame(r)*V + src[e]][ci]) * W[k*Cout+co][ci]
+ * over the flat rows r = (n,t,v) of channels-last x[rows][Cin] -> g[rows][Cout]. The adjacency aggregation runs in the GEMM
+ * prologue (shared memory), the K-times wider intermediate never reaches HBM; x is fetched and g written with tensor-map
+ * TMA. ch_sum / ch_sq (nullable, fp64 [nrep][Cout], accumulated into) receive the per-channel sum / sum of squares of the
+ * stored g: the BatchNorm2d batch statistics of stgcan.py:112. `xa` (nullable) additionally receives the aggregated operand
+ * [rows][K*Cin] (dev / cross-check output). CSR arrays as fmm_agg_fwd. Cin, Cout multiples of 64, Cout <= 256, V <= 33.
+ * `wpk` from fmm_gcn_pack(W fp32 [K*Cout][Cin]). */
+long long fmm_gcn_packed_bytes(int K, int Cin, int Cout);
+int fmm_gcn_pack(const float* w, void* out, int K, int Cin, int Cout, cudaStream_t stream);
+int fmm_gcn_fwd(const void* x, void* g, void* xa, const void* wpk, const float* bias, const int* rowptr, const int* src,
+                const float* coef, double* ch_sum, double* ch_sq, int nrep, long long rows, int V, int K, int Cin, int Cout,
+                int E, unsigned* err, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * memory-bound kernels (one pass over an activation each)
  * ------------------------------------------------------------------------------------------- */

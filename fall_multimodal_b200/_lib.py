@@ -95,7 +95,8 @@ _SIGNATURES = {
                     c_int, c_int, c_int, c_int, C.POINTER(c_int), c_int, _P, _P],
     "fmm_gcn_packed_bytes": [c_int, c_int, c_int],
     "fmm_gcn_pack": [_P, _P, c_int, c_int, c_int, _P],
-    "fmm_gcn_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "fmm_gcn_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(c_int), _P, _P, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "fmm_gcn_wgrad": [_P, _P, _P, _P, _P, _P, C.POINTER(c_int), c_ll, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "fmm_agg_fwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_dcoef": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],

@@ -74,72 +74,197 @@ constexpr int kGcnRawBoxes = 3;                      // 192 rows >= 128 + 2*(V-1
 constexpr int kGcnRawRows = kGcnRawBox * kGcnRawBoxes;
 constexpr uint32_t kGcnRawBytes = kGcnRawRows * 128u;
 constexpr uint32_t kGcnChunkBytes = kGcnTileRows * 128u;   // one [128 rows][64 ch] bf16 operand image
-constexpr int kGcnProducers = 256;
+constexpr int kGcnProducerWarps = 16;   // 2 warps per scheduler left the aggregation latency bound (ncu: 18 % issue per warp)
+constexpr int kGcnProducers = kGcnProducerWarps * 32;
+constexpr int kGcnRowStride = kGcnProducers / 8;   // a producer thread owns rows (tid>>3) + kGcnRowStride*i, piece tid&7
 constexpr int kGcnMaxV = 33;
 
+constexpr int kGcnMaxDeg = 16;  // sum over partitions of the maximum in-degree (mediapipe33 / spatial: 1 + 4 + 1)
+
 struct GcnEdges {
-  // shared-memory adjacency: ptr[(w*K + k)] = (first, last) into tab[]; tab[e] = (src*128 bytes, coef bits)
-  uint32_t ptr;
+  // shared-memory adjacency, dense and zero padded: partition k owns slots [off[k], off[k] + deg[k]) of every joint;
+  // tab[w*DT + slot] = (src*128 bytes, coef bits); padding slots are (w*128, 0.0f). Uniform trip counts keep the producer
+  // warps convergent and let every load of a chunk be issued before the first FMA needs one.
   uint32_t tab;
+  int DT;
+  const int* off;  // [K] first slot of partition k   (both point into the kernel's __grid_constant__ parameters)
+  const int* deg;  // [K] slots of partition k = its maximum in-degree
 };
 
-// Stage the CSR adjacency (rowptr over k*V+w, src, coef: csrc/elementwise.cu agg_fwd layout) in shared memory, per joint.
+// Stage the CSR adjacency (rowptr over k*V+w, src, coef: csrc/elementwise.cu agg_fwd layout) in shared memory.
+// `kdeg[k]` = maximum in-degree of partition k (host knowledge of the static graph); a joint with more edges traps.
 __device__ __forceinline__ void gcn_stage_edges(const GcnEdges& ed, const int* __restrict__ rowptr, const int* __restrict__ src,
-                                                const float* __restrict__ coef, int V, int K, int E) {
+                                                const float* __restrict__ coef, int V, int K, unsigned* err) {
   for (int i = threadIdx.x; i < V * K; i += blockDim.x) {
     const int k = i / V, w = i - k * V;
-    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(ed.ptr + 8u * (w * K + k)), "r"(rowptr[i]), "r"(rowptr[i + 1]) : "memory");
+    const int e0 = rowptr[i], e1 = rowptr[i + 1];
+    if (e1 - e0 > ed.deg[k]) {
+      if (err) atomicCAS(err, 0u, 0x80000000u | (31u << 16) | static_cast<unsigned>(i));
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+    for (int j = 0; j < ed.deg[k]; ++j) {
+      const bool real = e0 + j < e1;
+      const int so = (real ? src[e0 + j] : w) * 128;
+      const float cf = real ? coef[e0 + j] : 0.f;
+      asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(ed.tab + 8u * static_cast<uint32_t>(w * ed.DT + ed.off[k] + j)), "r"(so),
+                   "r"(__float_as_uint(cf)) : "memory");
+    }
   }
-  for (int e = threadIdx.x; e < E; e += blockDim.x)
-    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(ed.tab + 8u * e), "r"(src[e] * 128), "r"(__float_as_uint(coef[e])) : "memory");
 }
 
 // One producer thread's share of an aggregated operand image: rows (tid>>3) + 32*i, 16-byte piece tid&7.
-//   raw    : shared address of the raw slab (row j at j*128, pieces unswizzled)
-//   fb[i]  : byte offset of row i's frame inside the slab (negative never happens); valid[i]: row exists
+//   raw    : shared address of the raw slab (row j at j*128, pieces unswizzled); rows past the end of x are zero (TMA fill)
+//   tb[i]  : shared address of row i's edge slots (partition 0), rb[i]: address of this thread's piece in row i's frame
 //   dst    : shared address of the [128][64] SWIZZLE_128B image
 struct GcnRows {
-  int w[4];
-  int fb[4];
-  bool valid[4];
+  uint32_t tb[4];
+  uint32_t rb[4];
 };
-__device__ __forceinline__ void gcn_produce_chunk(const GcnEdges& ed, const GcnRows& rw, uint32_t raw, uint32_t dst, int k, int K) {
+template <int D, int NR>
+__device__ __forceinline__ void gcn_produce_rows(const GcnRows& rw, uint32_t raw, uint32_t dst, uint32_t slot_off) {
+  // (the shared-memory loads are volatile asm: they issue in program order, so the order below IS the schedule -
+  //  all edge slots first, then the raw pieces of a whole row group, and only then the arithmetic)
+  constexpr int RG = NR >= 2 ? 2 : 1;  // rows whose raw pieces are in flight together (16*RG*D bytes of registers)
   const uint32_t p = threadIdx.x & 7u;
   const uint32_t rl = threadIdx.x >> 3;
+  uint2 en[NR][D];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float acc[8];
+  for (int i = 0; i < NR; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (rw.valid[i]) {
-      const uint2 pe = lds64(ed.ptr + 8u * static_cast<uint32_t>(rw.w[i] * K + k));
-      const uint32_t base = raw + static_cast<uint32_t>(rw.fb[i]) + p * 16u;
-      for (uint32_t e = pe.x; e < pe.y; ++e) {
-        const uint2 en = lds64(ed.tab + 8u * e);
-        const uint4 u = lds128(base + en.x);
-        const float cf = __uint_as_float(en.y);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    for (int j = 0; j < D; ++j) en[i][j] = lds64(rw.tb[i] + slot_off + 8u * j);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 t = __bfloat1622float2(h[j]);
-          acc[2 * j] = fmaf(cf, t.x, acc[2 * j]);
-          acc[2 * j + 1] = fmaf(cf, t.y, acc[2 * j + 1]);
+  for (int i0 = 0; i0 < NR; i0 += RG) {
+    uint4 u[RG][D];
+#pragma unroll
+    for (int i = 0; i < RG; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) u[i][j] = lds128(raw + rw.rb[i0 + i] + en[i0 + i][j].x);
+#pragma unroll
+    for (int i = 0; i < RG; ++i) {
+      float acc[8];
+#pragma unroll
+      for (int l = 0; l < 8; ++l) acc[l] = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const float cf = __uint_as_float(en[i0 + i][j].y);
+        const uint32_t uw[4] = {u[i][j].x, u[i][j].y, u[i][j].z, u[i][j].w};
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          // bf16 -> fp32 is a 16-bit shift: one instruction per element (low half: shift, high half: mask)
+          acc[2 * l] = fmaf(cf, __uint_as_float(uw[l] << 16), acc[2 * l]);
+          acc[2 * l + 1] = fmaf(cf, __uint_as_float(uw[l] & 0xffff0000u), acc[2 * l + 1]);
         }
       }
+      const uint32_t row = rl + static_cast<uint32_t>(kGcnRowStride) * (i0 + i);
+      sts128g(dst + row * 128u + ((p ^ (row & 7u)) << 4), pack8_bf16(acc));
     }
-    const uint32_t row = rl + 32u * i;
-    sts128g(dst + row * 128u + ((p ^ (row & 7u)) << 4), pack8_bf16(acc));
   }
 }
-__device__ __forceinline__ void gcn_rows_of_tile(GcnRows& rw, long long r0, int raw_start, long long R, int V) {
-  const int rl = threadIdx.x >> 3;
+template <int NR>
+__device__ __forceinline__ void gcn_produce_chunk(const GcnEdges& ed, const GcnRows& rw, uint32_t raw, uint32_t dst, int k) {
+  const uint32_t so = 8u * static_cast<uint32_t>(ed.off[k]);
+  switch (ed.deg[k]) {
+    case 1: gcn_produce_rows<1, NR>(rw, raw, dst, so); break;
+    case 2: gcn_produce_rows<2, NR>(rw, raw, dst, so); break;
+    case 3: gcn_produce_rows<3, NR>(rw, raw, dst, so); break;
+    case 4: gcn_produce_rows<4, NR>(rw, raw, dst, so); break;
+    case 5: gcn_produce_rows<5, NR>(rw, raw, dst, so); break;
+    case 6: gcn_produce_rows<6, NR>(rw, raw, dst, so); break;
+    case 7: gcn_produce_rows<7, NR>(rw, raw, dst, so); break;
+    default: gcn_produce_rows<8, NR>(rw, raw, dst, so); break;
+  }
+}
+// All three operand images of one slab in ONE straight-line pass (K = 3 partitions with maximum in-degrees D0, D1, D2):
+// no per-chunk dispatch, one barrier round trip per slab instead of three, and the arithmetic of a padding slot is skipped
+// when none of the four joints a warp instruction covers has an edge there (a vote + branch instead of 16 FMA / unpack ops;
+// mediapipe33 / spatial: 4.0 of the 6 slots survive on average).
+__device__ __forceinline__ void gcn_fma8(float (&acc)[8], float cf, const uint4& u) {
+  const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long r = r0 + rl + 32 * i;
-    rw.valid[i] = r < R;
-    const int f = static_cast<int>((rw.valid[i] ? r : r0) / V);
-    rw.w[i] = static_cast<int>((rw.valid[i] ? r : r0) - static_cast<long long>(f) * V);
-    rw.fb[i] = (f * V - raw_start) * 128;
+  for (int l = 0; l < 4; ++l) {
+    // bf16 -> fp32 is a 16-bit shift: one instruction per element (low half: shift, high half: mask)
+    acc[2 * l] = fmaf(cf, __uint_as_float(uw[l] << 16), acc[2 * l]);
+    acc[2 * l + 1] = fmaf(cf, __uint_as_float(uw[l] & 0xffff0000u), acc[2 * l + 1]);
+  }
+}
+template <int NR, int DN, int J0, int DT>
+__device__ __forceinline__ void gcn_produce_part(const GcnRows& rw, uint32_t raw, uint32_t dst) {
+  // one partition (slots J0 .. J0+DN-1 of every joint) -> one operand image; all loads of the thread's rows first
+  const uint32_t p = threadIdx.x & 7u;
+  const uint32_t rl = threadIdx.x >> 3;
+  uint2 en[NR][DN];
+  uint4 u[NR][DN];
+#pragma unroll
+  for (int i = 0; i < NR; ++i)
+#pragma unroll
+    for (int j = 0; j < DN; ++j) en[i][j] = lds64(rw.tb[i] + 8u * (J0 + j));
+#pragma unroll
+  for (int i = 0; i < NR; ++i)
+#pragma unroll
+    for (int j = 0; j < DN; ++j) u[i][j] = lds128(raw + rw.rb[i] + en[i][j].x);
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const uint32_t row = rl + static_cast<uint32_t>(kGcnRowStride) * i;
+    const uint32_t d = dst + row * 128u + ((p ^ (row & 7u)) << 4);
+    // slot 0 of a partition holds a real edge for most joints: a plain product starts the sum; a partition in which
+    // none of the warp's four joints has any edge (the sparse "further" partition) just stores zeros
+    if (!__any_sync(0xffffffffu, en[i][0].y != 0u)) {
+      sts128g(d, make_uint4(0, 0, 0, 0));
+      continue;
+    }
+    float acc[8];
+    {
+      const float cf = __uint_as_float(en[i][0].y);
+      const uint32_t uw[4] = {u[i][0].x, u[i][0].y, u[i][0].z, u[i][0].w};
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        acc[2 * l] = cf * __uint_as_float(uw[l] << 16);
+        acc[2 * l + 1] = cf * __uint_as_float(uw[l] & 0xffff0000u);
+      }
+    }
+#pragma unroll
+    for (int j = 1; j < DN; ++j)
+      if (__any_sync(0xffffffffu, en[i][j].y != 0u)) gcn_fma8(acc, __uint_as_float(en[i][j].y), u[i][j]);
+    sts128g(d, pack8_bf16(acc));
+  }
+}
+// The three operand images of one slab, partition by partition: `acquire(k)` returns the shared address of image k (after
+// whatever wait makes it writable), `publish(k)` hands it on. Chunk granularity lets the tensor core start on image 0
+// while image 1 is being aggregated even when only three or four operand slots fit in shared memory.
+template <int NR, int D0, int D1, int D2, typename Acq, typename Pub>
+__device__ __forceinline__ void gcn_produce_slab3(const GcnRows& rw, uint32_t raw, Acq acquire, Pub publish) {
+  constexpr int DT = D0 + D1 + D2;
+  gcn_produce_part<NR, D0, 0, DT>(rw, raw, acquire(0));
+  publish(0);
+  gcn_produce_part<NR, D1, D0, DT>(rw, raw, acquire(1));
+  publish(1);
+  gcn_produce_part<NR, D2, D0 + D1, DT>(rw, raw, acquire(2));
+  publish(2);
+}
+// degree signature of the specialised slab producers: K == 3 and (D0, D1, D2) one of the spatial-partition layouts
+__device__ __forceinline__ int gcn_signature(const int* kdeg, int K) {
+  if (K != 3 || kdeg[0] != 1 || kdeg[2] != 1) return 0;
+  return (kdeg[1] >= 3 && kdeg[1] <= 5) ? kdeg[1] : 0;
+}
+template <int NR, typename Acq, typename Pub>
+__device__ __forceinline__ void gcn_produce_slab3_sig(int sig, const GcnRows& rw, uint32_t raw, Acq acquire, Pub publish) {
+  if (sig == 4) gcn_produce_slab3<NR, 1, 4, 1>(rw, raw, acquire, publish);
+  else if (sig == 3) gcn_produce_slab3<NR, 1, 3, 1>(rw, raw, acquire, publish);
+  else gcn_produce_slab3<NR, 1, 5, 1>(rw, raw, acquire, publish);
+}
+
+template <int NR>
+__device__ __forceinline__ void gcn_rows_of_tile(GcnRows& rw, const GcnEdges& ed, long long r0, int raw_start, int V) {
+  const int rl = threadIdx.x >> 3;
+  const uint32_t p = threadIdx.x & 7u;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const long long r = r0 + rl + kGcnRowStride * i;
+    const int f = static_cast<int>(r / V);
+    const int w = static_cast<int>(r - static_cast<long long>(f) * V);
+    rw.tb[i] = ed.tab + 8u * static_cast<uint32_t>(w * ed.DT);
+    rw.rb[i] = static_cast<uint32_t>(f * V - raw_start) * 128u + p * 16u;
   }
 }
 
@@ -160,10 +285,13 @@ struct GcnFwdParams {
   int BN, NCC, ntiles;
   int n_raw, n_a, n_b, resident;
   int write_xa;
+  int kdeg[8], koff[8], DT;
   unsigned* err;
 };
 
-constexpr int kGcnFwdThreads = 480;  // 8 producer, 4 epilogue, raw loader, weight loader, MMA warps
+constexpr int kGcnEpiWarps = 8;
+constexpr int kGcnFwdThreads = (kGcnProducerWarps + kGcnEpiWarps + 3) * 32;  // producer, epilogue, raw loader, weight loader, MMA warps
+constexpr int kGcnFwdRows = kGcnTileRows / kGcnRowStride;      // rows per producer thread
 
 __global__ void __launch_bounds__(kGcnFwdThreads, 1)
 gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ CUtensorMap tm_x,
@@ -174,15 +302,15 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
   const uint32_t raw0 = base;
   const uint32_t a0 = raw0 + p.n_raw * kGcnRawBytes;
   const uint32_t b0 = a0 + p.n_a * kGcnChunkBytes;
-  const uint32_t stg0 = b0 + p.n_b * b_bytes;                     // 4 x 4096: per-epilogue-warp staging tile [32][64] bf16
-  const uint32_t bias0 = stg0 + 4u * 4096u;                        // [Cout/4][V][4] fp32
+  const uint32_t stg0 = b0 + p.n_b * b_bytes;                     // one staging tile [32][64] bf16 per epilogue warp
+  const uint32_t bias0 = stg0 + static_cast<uint32_t>(kGcnEpiWarps) * 4096u;                        // [Cout/4][V][4] fp32
   const uint32_t bias_bytes = (p.bias ? static_cast<uint32_t>(p.V * p.Cout) * 4u : 0u);
-  const uint32_t stat0 = bias0 + ((bias_bytes + 15u) & ~15u);      // [4 warps][BN][2] fp32
-  const uint32_t stat_bytes = 4u * static_cast<uint32_t>(p.BN) * 8u;
   GcnEdges ed;
-  ed.ptr = stat0 + stat_bytes;
-  ed.tab = ed.ptr + 8u * static_cast<uint32_t>(p.V * p.K);
-  const uint32_t bars0 = (ed.tab + 8u * static_cast<uint32_t>(p.E) + 15u) & ~15u;
+  ed.tab = bias0 + ((bias_bytes + 15u) & ~15u);
+  ed.DT = p.DT;
+  ed.off = p.koff;
+  ed.deg = p.kdeg;
+  const uint32_t bars0 = (ed.tab + 8u * static_cast<uint32_t>(p.V * ed.DT) + 15u) & ~15u;
   auto raw_full = [&](int s) { return bars0 + 8u * s; };
   auto raw_empty = [&](int s) { return bars0 + 8u * (p.n_raw + s); };
   auto a_full = [&](int s) { return bars0 + 8u * (2 * p.n_raw + s); };
@@ -213,27 +341,25 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), 128);
+      mbar_init(acc_empty(s), 128);   // the four quadrant warps of the stage's epilogue group
     }
     mbar_fence_init();
   }
-  if (warp == 14) {
+  if (warp == kGcnProducerWarps + kGcnEpiWarps + 2) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
-  if (warp == 12 && lane == 0) {
+  if (warp == kGcnProducerWarps + kGcnEpiWarps && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_g);
     if (p.write_xa) tma_prefetch_desc(&tm_xa);
   }
-  gcn_stage_edges(ed, p.rowptr, p.src, p.coef, p.V, p.K, p.E);
+  gcn_stage_edges(ed, p.rowptr, p.src, p.coef, p.V, p.K, p.err);
   // bias table [Cout/4][V][4]: the 32 rows of an epilogue warp are consecutive joints -> consecutive float4
   for (int i = threadIdx.x; i < (p.bias ? p.V * p.Cout : 0); i += blockDim.x) {
     const int v = i / p.Cout, c = i - v * p.Cout;
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias0 + 4u * (((c >> 2) * p.V + v) * 4 + (c & 3))), "f"(p.bias[i]) : "memory");
   }
-  for (int i = threadIdx.x; i < 4 * p.BN * 2; i += blockDim.x)
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(stat0 + 4u * i), "f"(0.f) : "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -243,26 +369,44 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
   const int nchunk = p.NCC * p.K;  // operand chunks (MMA k-blocks of 64) per tile
 
-  if (warp < 8) {
+  if (warp < kGcnProducerWarps) {
     // ------------------------------ aggregation producers ------------------------------
     int rs = 0, as = 0;
     uint32_t rph = 0, aph = 0;
+    const int sig = gcn_signature(p.kdeg, p.K);
+    auto next_slot = [&]() {
+      if (++as == p.n_a) {
+        as = 0;
+        aph ^= 1u;
+      }
+    };
     for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
       const long long r0 = static_cast<long long>(tile) * kGcnTileRows;
       const int raw_start = static_cast<int>(r0 / p.V) * p.V;
       GcnRows rw;
-      gcn_rows_of_tile(rw, r0, raw_start, p.R, p.V);
+      gcn_rows_of_tile<kGcnFwdRows>(rw, ed, r0, raw_start, p.V);
       for (int cc = 0; cc < p.NCC; ++cc) {
-        mbar_wait(raw_full(rs), rph, p.err, 1);
+        mbar_wait_relaxed(raw_full(rs), rph, p.err, 1, 20);
         const uint32_t raw = raw0 + rs * kGcnRawBytes;
-        for (int k = 0; k < p.K; ++k) {
-          mbar_wait(a_empty(as), aph ^ 1u, p.err, 2);
-          gcn_produce_chunk(ed, rw, raw, a0 + as * kGcnChunkBytes, k, p.K);
-          fence_proxy_async_smem();
-          mbar_arrive(a_full(as));
-          if (++as == p.n_a) {
-            as = 0;
-            aph ^= 1u;
+        if (sig) {
+          gcn_produce_slab3_sig<kGcnFwdRows>(
+              sig, rw, raw,
+              [&](int) {
+                mbar_wait_relaxed(a_empty(as), aph ^ 1u, p.err, 2, 20);
+                return a0 + as * kGcnChunkBytes;
+              },
+              [&](int) {
+                fence_proxy_async_smem();
+                mbar_arrive(a_full(as));
+                next_slot();
+              });
+        } else {
+          for (int k = 0; k < p.K; ++k) {
+            mbar_wait_relaxed(a_empty(as), aph ^ 1u, p.err, 2, 20);
+            gcn_produce_chunk<kGcnFwdRows>(ed, rw, raw, a0 + as * kGcnChunkBytes, k);
+            fence_proxy_async_smem();
+            mbar_arrive(a_full(as));
+            next_slot();
           }
         }
         mbar_arrive(raw_empty(rs));
@@ -272,105 +416,116 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
         }
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < kGcnProducerWarps + kGcnEpiWarps) {
     // ---------------------------------- epilogue ----------------------------------
-    const int quad = warp & 3;
-    const uint32_t stg = stg0 + static_cast<uint32_t>(quad) * 4096u;
-    const uint32_t my_stat = stat0 + static_cast<uint32_t>(quad) * static_cast<uint32_t>(p.BN) * 8u;
+    // Eight warps: group g = (warp - first) / 4 owns TMEM accumulator stage g (every second tile of this CTA), quadrant
+    // q = warp % 4 its 32 TMEM lanes. With four warps the epilogue was the kernel's critical path (ncu: the aggregation
+    // warps idle on a_empty while the epilogue warps never wait).
+    const int ew = warp - kGcnProducerWarps;
+    const int quad = ew & 3, grp = ew >> 2;
+    const uint32_t stg = stg0 + static_cast<uint32_t>(ew) * 4096u;
     const bool stats = p.ch_sum != nullptr;
-    int acs = 0;
+    const int npass = p.BN / 64;
+    float st[4][4];   // per 64-column pass: (sum, sumsq) of channels 2*lane and 2*lane+1 over this warp's rows
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) st[a][b] = 0.f;
     uint32_t acph = 0;
-    for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
+    int it = 0;
+    for (int tile = first_tile; tile < p.ntiles; tile += tile_step, ++it) {
+      if ((it & 1) != grp) continue;
       const long long r0 = static_cast<long long>(tile) * kGcnTileRows;
       const long long r = r0 + quad * 32 + lane;
       const bool row_ok = r < p.R;
       const int w = static_cast<int>((row_ok ? r : 0) % p.V);
-      mbar_wait(acc_full(acs), acph, p.err, 3);
+      mbar_wait_relaxed(acc_full(grp), acph, p.err, 3, 20);
+      acph ^= 1u;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acs) * static_cast<uint32_t>(p.BN) + (static_cast<uint32_t>(quad * 32) << 16);
-      for (int c64 = 0; c64 < p.BN / 64; ++c64) {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(taddr + c64 * 64, v0);
-        tmem_ld32(taddr + c64 * 64 + 32, v1);
-        tmem_ld_wait();
-        if (c64 == p.BN / 64 - 1) {
-          // the accumulator is in registers: hand the TMEM stage back before the stores
-          tc_fence_before();
-          mbar_arrive(acc_empty(acs));
-        }
-        // the previous TMA store of this warp must have read the staging tile before it is overwritten
-        if (lane == 0) tma_wait_read<0>();
-        __syncwarp();
-        const uint32_t srow = stg + static_cast<uint32_t>(lane) * 128u;
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(grp) * static_cast<uint32_t>(p.BN) + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float f[8];
-          const uint32_t* vv = g < 4 ? v0 : v1;
+      for (int c64 = 0; c64 < 4; ++c64) {
+        if (c64 < npass) {
+          // the TMA store of the previous pass must have read the staging tile before it is overwritten
+          if (lane == 0) tma_wait_read<0>();
+          __syncwarp();
+          const uint32_t srow = stg + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(vv[(g & 3) * 8 + i]);
-          if (p.bias) {
-            const int co = c64 * 64 + g * 8;
-            const uint4 ba = lds128(bias0 + 16u * static_cast<uint32_t>((co >> 2) * p.V + w));
-            const uint4 bb = lds128(bias0 + 16u * static_cast<uint32_t>(((co >> 2) + 1) * p.V + w));
-            f[0] += __uint_as_float(ba.x); f[1] += __uint_as_float(ba.y); f[2] += __uint_as_float(ba.z); f[3] += __uint_as_float(ba.w);
-            f[4] += __uint_as_float(bb.x); f[5] += __uint_as_float(bb.y); f[6] += __uint_as_float(bb.z); f[7] += __uint_as_float(bb.w);
+          for (int h = 0; h < 2; ++h) {
+            uint32_t vv[32];
+            tmem_ld32(taddr + c64 * 64 + h * 32, vv);
+            tmem_ld_wait();
+            if (h == 1 && c64 == npass - 1) {
+              // the accumulator is in registers: hand the TMEM stage back before the stores
+              tc_fence_before();
+              mbar_arrive(acc_empty(grp));
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(vv[g * 8 + i]);
+              if (p.bias) {
+                const int co = c64 * 64 + h * 32 + g * 8;
+                const uint4 ba = lds128(bias0 + 16u * static_cast<uint32_t>((co >> 2) * p.V + w));
+                const uint4 bb = lds128(bias0 + 16u * static_cast<uint32_t>(((co >> 2) + 1) * p.V + w));
+                f[0] += __uint_as_float(ba.x); f[1] += __uint_as_float(ba.y); f[2] += __uint_as_float(ba.z); f[3] += __uint_as_float(ba.w);
+                f[4] += __uint_as_float(bb.x); f[5] += __uint_as_float(bb.y); f[6] += __uint_as_float(bb.z); f[7] += __uint_as_float(bb.w);
+              }
+              if (!row_ok) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = 0.f;
+              }
+              sts128g(srow + ((static_cast<uint32_t>(h * 4 + g) ^ (static_cast<uint32_t>(lane) & 7u)) << 4), pack8_bf16(f));
+            }
           }
-          if (!row_ok) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = 0.f;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_g, c64 * 64, static_cast<int>(r0) + quad * 32, stg);
+            tma_commit();
           }
-          sts128g(srow + ((static_cast<uint32_t>(g) ^ (static_cast<uint32_t>(lane) & 7u)) << 4), pack8_bf16(f));
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tm_g, c64 * 64, static_cast<int>(r0) + quad * 32, stg);
-          tma_commit();
-        }
-        if (stats) {
-          // column sums of the bf16 values just staged: lane l owns channels 2l, 2l+1 (one 32-bit word per row)
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          const uint32_t piece = static_cast<uint32_t>(lane) >> 2, word = (static_cast<uint32_t>(lane) & 3u) * 4u;
+          if (stats) {
+            // column sums of the bf16 values just staged: lane l owns channels 2l, 2l+1 (one 32-bit word per row)
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const uint32_t piece = static_cast<uint32_t>(lane) >> 2, word = (static_cast<uint32_t>(lane) & 3u) * 4u;
 #pragma unroll 8
-          for (uint32_t rr = 0; rr < 32; ++rr) {
-            const uint32_t u = lds32(stg + rr * 128u + ((piece ^ (rr & 7u)) << 4) + word);
-            const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
-            s0 += t.x; s1 += t.y;
-            q0 = fmaf(t.x, t.x, q0); q1 = fmaf(t.y, t.y, q1);
+            for (uint32_t rr = 0; rr < 32; ++rr) {
+              const uint32_t u = lds32(stg + rr * 128u + ((piece ^ (rr & 7u)) << 4) + word);
+              const float lo = __uint_as_float(u << 16), hi = __uint_as_float(u & 0xffff0000u);
+              s0 += lo; s1 += hi;
+              q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+            }
+            st[c64][0] += s0; st[c64][1] += q0; st[c64][2] += s1; st[c64][3] += q1;
           }
-          const uint32_t sa = my_stat + 8u * static_cast<uint32_t>(c64 * 64 + 2 * lane);
-          uint4 old = lds128(sa);
-          old.x = __float_as_uint(__uint_as_float(old.x) + s0);
-          old.y = __float_as_uint(__uint_as_float(old.y) + q0);
-          old.z = __float_as_uint(__uint_as_float(old.z) + s1);
-          old.w = __float_as_uint(__uint_as_float(old.w) + q1);
-          sts128g(sa, old);
         }
-      }
-      if (++acs == 2) {
-        acs = 0;
-        acph ^= 1u;
       }
     }
     if (lane == 0) tma_wait_read<0>();
     __syncwarp();
     if (stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = threadIdx.x - 256;  // 0..127
-      const int rep = blockIdx.x % p.nrep;
-      for (int c = t; c < p.BN && c < p.Cout; c += 128) {
-        float s = 0.f, q = 0.f;
+      // per-warp partial sums -> this warp's (now idle) staging tile as [BN][2] fp32 -> one fp64 atomic per channel and CTA
 #pragma unroll
-        for (int wq = 0; wq < 4; ++wq) {
-          const uint2 u = lds64(stat0 + static_cast<uint32_t>(wq) * static_cast<uint32_t>(p.BN) * 8u + 8u * c);
-          s += __uint_as_float(u.x);
-          q += __uint_as_float(u.y);
+      for (int c64 = 0; c64 < 4; ++c64)
+        if (c64 < npass)
+          sts128g(stg + 8u * static_cast<uint32_t>(c64 * 64 + 2 * lane),
+                  make_uint4(__float_as_uint(st[c64][0]), __float_as_uint(st[c64][1]), __float_as_uint(st[c64][2]), __float_as_uint(st[c64][3])));
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int t = threadIdx.x - kGcnProducers;  // 0..255
+      const int rep = blockIdx.x % p.nrep;
+      for (int c = t; c < p.BN && c < p.Cout; c += kGcnEpiWarps * 32) {
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < kGcnEpiWarps; ++wq) {
+          const uint2 u = lds64(stg0 + static_cast<uint32_t>(wq) * 4096u + 8u * c);
+          sum += __uint_as_float(u.x);
+          sq += __uint_as_float(u.y);
         }
-        atomicAdd(p.ch_sum + static_cast<size_t>(rep) * p.Cout + c, static_cast<double>(s));
-        atomicAdd(p.ch_sq + static_cast<size_t>(rep) * p.Cout + c, static_cast<double>(q));
+        atomicAdd(p.ch_sum + static_cast<size_t>(rep) * p.Cout + c, static_cast<double>(sum));
+        atomicAdd(p.ch_sq + static_cast<size_t>(rep) * p.Cout + c, static_cast<double>(sq));
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == kGcnProducerWarps + kGcnEpiWarps) {
     // ------------------------------ raw-slab loader (TMA) ------------------------------
     if (lane == 0) {
       int rs = 0;
@@ -379,7 +534,7 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
         const long long r0 = static_cast<long long>(tile) * kGcnTileRows;
         const int raw_start = static_cast<int>(r0 / p.V) * p.V;
         for (int cc = 0; cc < p.NCC; ++cc) {
-          mbar_wait(raw_empty(rs), rph ^ 1u, p.err, 4);
+          mbar_wait_relaxed(raw_empty(rs), rph ^ 1u, p.err, 4, 40);
           mbar_arrive_expect_tx(raw_full(rs), kGcnRawBytes);
 #pragma unroll
           for (int b = 0; b < kGcnRawBoxes; ++b)
@@ -392,7 +547,7 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
       }
     }
     __syncwarp();
-  } else if (warp == 13) {
+  } else if (warp == kGcnProducerWarps + kGcnEpiWarps + 1) {
     // -------------------------------- weight loader --------------------------------
     if (lane == 0 && first_tile < p.ntiles) {
       const uint8_t* W = reinterpret_cast<const uint8_t*>(p.wpk);
@@ -404,7 +559,7 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
         uint32_t bph = 0;
         for (int tile = first_tile; tile < p.ntiles; tile += tile_step)
           for (int i = 0; i < nchunk; ++i) {
-            mbar_wait(b_empty(bs), bph ^ 1u, p.err, 5);
+            mbar_wait_relaxed(b_empty(bs), bph ^ 1u, p.err, 5, 40);
             mbar_arrive_expect_tx(b_full(bs), b_bytes);
             bulk_g2s(b0 + bs * b_bytes, W + static_cast<size_t>(i) * b_bytes, b_bytes, b_full(bs));
             if (++bs == p.n_b) {
@@ -419,7 +574,7 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
     // ---------------------------------- MMA issuer ----------------------------------
     const uint32_t idesc = make_idesc_bf16(p.BN, 0, 0);
     const uint32_t hi = desc_hi(1024);
-    int as = 0, bs = 0, acs = 0, prev_as = -1;
+    int as = 0, bs = 0, acs = 0;
     uint32_t aph = 0, bph = 0, acph = 0;
     if (p.resident && first_tile < p.ntiles) mbar_wait(b_full(0), 0, p.err, 6);
     for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
@@ -441,18 +596,16 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
           if (!p.resident) umma_commit(b_empty(bs));
           if (i == nchunk - 1) umma_commit(acc_full(acs));
           if (p.write_xa) {
-            // training-mode side output (dev / fallback path): the aggregated operand image as rows of Xa[R][K*Cin]
+            // side output (dev / cross-check path): the aggregated operand image as rows of Xa[R][K*Cin]. The slot is
+            // released by a second arrival once the store has read it (a_empty counts 2 in this mode).
             const int cc = i / p.K, k = i - cc * p.K;
             tma_store_2d(&tm_xa, k * p.Cin + cc * 64, r0, a0 + as * kGcnChunkBytes);
             tma_commit();
-            if (prev_as >= 0) {
-              tma_wait_read<1>();
-              mbar_arrive(a_empty(prev_as));
-            }
+            tma_wait_read<0>();
+            mbar_arrive(a_empty(as));
           }
         }
         __syncwarp();
-        prev_as = as;
         if (++as == p.n_a) {
           as = 0;
           aph ^= 1u;
@@ -467,18 +620,229 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
         acph ^= 1u;
       }
     }
-    if (p.write_xa && prev_as >= 0) {
-      if (elect_one()) {
-        tma_wait_read<0>();
-        mbar_arrive(a_empty(prev_as));
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kGcnProducerWarps + kGcnEpiWarps + 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient:  dW[(k*Cout + co)][ci] += sum_r dG[r][co] * A_k[r][ci]     (A_k = aggregated input, re-derived here)
+//
+// Mirror image of the forward GEMM (contraction over the rows), same operand images: the aggregated chunk [TR rows][64 ch]
+// is the MN-major A' operand (M' = channels), the dG tile [TR rows][Cout] the MN-major B' operand, K' = TR rows per tile.
+// Work split: an item is one 64-channel slab cc of the input with its K aggregated chunks (M' = 64*K, as ceil(K/2) M=128
+// blocks; an odd K pads the last block with a zero image); the CTAs of an item slice the row tiles, keep their
+// [64*K x Cout] fp32 accumulators in TMEM for the whole slice and add them to dW with atomics at the end. Every chunk is
+// aggregated by exactly one item (no duplicated prologue work); dG is re-read once per slab (L2).
+// ------------------------------------------------------------------------------------------
+struct GcnWgradParams {
+  float* dw;
+  const int* rowptr;
+  const int* src;
+  const float* coef;
+  long long R;
+  int V, K, Cin, Cout;
+  int NCC, MB, slices, ntiles;
+  int n_raw, n_st;
+  int kdeg[8], koff[8], DT;
+  unsigned* err;
+};
+
+constexpr int kGcnWgThreads = (kGcnProducerWarps + 2) * 32;  // producer warps (0-3 also run the epilogue), loader, MMA
+
+template <int TR>
+__global__ void __launch_bounds__(kGcnWgThreads, 1)
+gcn_wgrad_kernel(const __grid_constant__ GcnWgradParams p, const __grid_constant__ CUtensorMap tm_x,
+                 const __grid_constant__ CUtensorMap tm_dg) {
+  constexpr int NR = TR / kGcnRowStride;
+  constexpr uint32_t kChunk = TR * 128u;                         // one [TR][64] image
+  constexpr int kRawBoxes = (TR + 64 + kGcnRawBox - 1) / kGcnRawBox;   // TR + 2*(V-1) <= TR + 64 rows
+  constexpr uint32_t kRaw = kRawBoxes * kGcnRawBox * 128u;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nb = p.Cout / 64;                                    // 64-column images of the dG tile
+  const uint32_t a_bytes = static_cast<uint32_t>(p.K) * kChunk, b_bytes = static_cast<uint32_t>(nb) * kChunk;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t st0 = base;
+  const uint32_t zero0 = st0 + p.n_st * stage_bytes;             // zero image (odd K), above every stage: LBO stays positive
+  const uint32_t raw0 = zero0 + ((p.K & 1) ? kChunk : 0u);
+  GcnEdges ed;
+  ed.tab = raw0 + p.n_raw * kRaw;
+  ed.DT = p.DT;
+  ed.off = p.koff;
+  ed.deg = p.kdeg;
+  const uint32_t bars0 = (ed.tab + 8u * static_cast<uint32_t>(p.V * p.DT) + 15u) & ~15u;
+  auto raw_full = [&](int s) { return bars0 + 8u * s; };
+  auto raw_empty = [&](int s) { return bars0 + 8u * (p.n_raw + s); };
+  auto a_full = [&](int s) { return bars0 + 8u * (2 * p.n_raw + s); };
+  auto b_full = [&](int s) { return bars0 + 8u * (2 * p.n_raw + p.n_st + s); };
+  auto st_empty = [&](int s) { return bars0 + 8u * (2 * p.n_raw + 2 * p.n_st + s); };
+  const uint32_t acc_full = bars0 + 8u * (2 * p.n_raw + 3 * p.n_st);
+  const uint32_t tmem_slot = acc_full + 8u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(p.MB * p.Cout)) tmem_cols <<= 1;
+
+  const int cc = blockIdx.x % p.NCC;       // the input slab of this item
+  const int slice = blockIdx.x / p.NCC;
+  const int my_tiles = slice < p.ntiles ? (p.ntiles - slice + p.slices - 1) / p.slices : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_raw; ++s) {
+      mbar_init(raw_full(s), 1);
+      mbar_init(raw_empty(s), kGcnProducers);
+    }
+    for (int s = 0; s < p.n_st; ++s) {
+      mbar_init(a_full(s), kGcnProducers);
+      mbar_init(b_full(s), 1);
+      mbar_init(st_empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == kGcnProducerWarps + 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp == kGcnProducerWarps && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_dg);
+  }
+  gcn_stage_edges(ed, p.rowptr, p.src, p.coef, p.V, p.K, p.err);
+  if (p.K & 1) {
+    for (uint32_t o = threadIdx.x * 16u; o < kChunk; o += blockDim.x * 16u) sts128g(zero0 + o, make_uint4(0, 0, 0, 0));
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (my_tiles > 0) {
+    if (warp < kGcnProducerWarps) {
+      // ------------------------------ aggregation producers ------------------------------
+      int rs = 0, st = 0;
+      uint32_t rph = 0, sph = 0;
+      const int sig = gcn_signature(p.kdeg, p.K);
+      for (int tile = slice; tile < p.ntiles; tile += p.slices) {
+        const long long r0 = static_cast<long long>(tile) * TR;
+        const int raw_start = static_cast<int>(r0 / p.V) * p.V;
+        GcnRows rw;
+        gcn_rows_of_tile<NR>(rw, ed, r0, raw_start, p.V);
+        mbar_wait_relaxed(st_empty(st), sph ^ 1u, p.err, 11, 20);
+        const uint32_t a_base = st0 + st * stage_bytes;
+        mbar_wait_relaxed(raw_full(rs), rph, p.err, 12, 20);
+        const uint32_t raw = raw0 + rs * kRaw;
+        if (sig) {
+          gcn_produce_slab3_sig<NR>(sig, rw, raw, [&](int k) { return a_base + static_cast<uint32_t>(k) * kChunk; }, [](int) {});
+        } else {
+          for (int k = 0; k < p.K; ++k) gcn_produce_chunk<NR>(ed, rw, raw, a_base + static_cast<uint32_t>(k) * kChunk, k);
+        }
+        mbar_arrive(raw_empty(rs));
+        if (++rs == p.n_raw) {
+          rs = 0;
+          rph ^= 1u;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(a_full(st));
+        if (++st == p.n_st) {
+          st = 0;
+          sph ^= 1u;
+        }
+      }
+    }
+    if (warp < 4) {
+      // ------------------------------ epilogue (same warps, after their last tile) ------------------------------
+      mbar_wait_relaxed(acc_full, 0, p.err, 13);
+      tc_fence_after();
+      const int row = warp * 32 + lane;                 // 0..127 inside an M block: two 64-channel chunks
+      for (int mb = 0; mb < p.MB; ++mb) {
+        const int k = 2 * mb + (row >> 6);
+        const bool row_ok = k < p.K;
+        float* dst = p.dw + (static_cast<size_t>(row_ok ? k : 0) * p.Cout) * p.Cin + cc * 64 + (row & 63);
+        for (int cg = 0; cg < p.Cout / 32; ++cg) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + static_cast<uint32_t>(mb * p.Cout + cg * 32) + (static_cast<uint32_t>(warp * 32) << 16), acc);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + static_cast<size_t>(cg * 32 + i) * p.Cin, __uint_as_float(acc[i]));
+          }
+        }
+      }
+    } else if (warp == kGcnProducerWarps) {
+      // ------------------------------ loader: raw slabs + dG tiles (TMA) ------------------------------
+      if (lane == 0) {
+        int rs = 0, st = 0;
+        uint32_t rph = 0, sph = 0;
+        for (int tile = slice; tile < p.ntiles; tile += p.slices) {
+          const long long r0 = static_cast<long long>(tile) * TR;
+          const int raw_start = static_cast<int>(r0 / p.V) * p.V;
+          mbar_wait_relaxed(raw_empty(rs), rph ^ 1u, p.err, 14, 40);
+          mbar_arrive_expect_tx(raw_full(rs), kRaw);
+#pragma unroll
+          for (int b = 0; b < kRawBoxes; ++b)
+            tma_load_2d(raw0 + rs * kRaw + b * (kGcnRawBox * 128u), &tm_x, cc * 64, raw_start + b * kGcnRawBox, raw_full(rs));
+          if (++rs == p.n_raw) {
+            rs = 0;
+            rph ^= 1u;
+          }
+          mbar_wait_relaxed(st_empty(st), sph ^ 1u, p.err, 15, 40);
+          mbar_arrive_expect_tx(b_full(st), b_bytes);
+          for (int h = 0; h < nb; ++h)
+            tma_load_2d(st0 + st * stage_bytes + a_bytes + h * kChunk, &tm_dg, h * 64, static_cast<int>(r0), b_full(st));
+          if (++st == p.n_st) {
+            st = 0;
+            sph ^= 1u;
+          }
+        }
       }
       __syncwarp();
+    } else if (warp == kGcnProducerWarps + 1) {
+      // ---------------------------------- MMA issuer ----------------------------------
+      const uint32_t idesc = make_idesc_bf16(p.Cout, 1, 1);
+      const uint32_t hi = desc_hi(1024);               // both operands: 8-row (K') groups 1024 bytes apart
+      int st = 0;
+      uint32_t sph = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(a_full(st), sph, p.err, 16);
+        mbar_wait(b_full(st), sph, p.err, 17);
+        tc_fence_after();
+        const uint32_t a_base = st0 + st * stage_bytes;
+        const uint32_t b_lo0 = desc_lo(a_base + a_bytes, kChunk);  // LBO: next 64-column image of dG
+        if (elect_one()) {
+          for (int mb = 0; mb < p.MB; ++mb) {
+            // M block = chunks (2mb, 2mb+1); LBO = distance to the second 64-channel atom (the zero image for an odd tail)
+            const uint32_t a_first = a_base + static_cast<uint32_t>(2 * mb) * kChunk;
+            const uint32_t a_lo0 = desc_lo(a_first, (2 * mb + 1 < p.K) ? kChunk : zero0 - a_first);
+            const uint32_t d = tmem_base + static_cast<uint32_t>(mb * p.Cout);
+#pragma unroll
+            for (uint32_t kk = 0; kk < TR / 16; ++kk)   // K' = 16 rows = two 8-row groups = 2048 bytes
+              umma_bf16_lh(d, a_lo0 + kk * 128u, hi, b_lo0 + kk * 128u, hi, idesc, static_cast<uint32_t>(it) | kk);
+          }
+          umma_commit(st_empty(st));
+          if (it == my_tiles - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+        if (++st == p.n_st) {
+          st = 0;
+          sph ^= 1u;
+        }
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 14) {
+  if (warp == kGcnProducerWarps + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -565,14 +929,23 @@ int fmm_gcn_pack(const float* w, void* out, int K, int Cin, int Cout, cudaStream
 }
 
 int fmm_gcn_fwd(const void* x, void* g, void* xa, const void* wpk, const float* bias, const int* rowptr, const int* src,
-                const float* coef, double* ch_sum, double* ch_sq, int nrep, long long rows, int V, int K, int Cin, int Cout,
-                int E, unsigned* err, cudaStream_t stream) {
+                const float* coef, const int* kdeg, double* ch_sum, double* ch_sq, int nrep, long long rows, int V, int K,
+                int Cin, int Cout, int E, unsigned* err, cudaStream_t stream) {
   FMM_CHECK_ARG(x && g && wpk && rowptr && src && coef, "gcn_fwd: null pointer");
   FMM_CHECK_ARG(rows > 0 && rows < (1ll << 31) && V > 0 && V <= kGcnMaxV && K > 0 && K <= 8, "gcn_fwd: bad shape (rows=%lld V=%d K=%d)", rows, V, K);
   FMM_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cout <= 256 && Cin <= 512, "gcn_fwd: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
   FMM_CHECK_ARG((ch_sum == nullptr) == (ch_sq == nullptr) && (ch_sum == nullptr || nrep > 0), "gcn_fwd: statistics buffers");
-  FMM_CHECK_ARG(E > 0 && E <= 4096, "gcn_fwd: edge count %d", E);
+  FMM_CHECK_ARG(E > 0 && E <= 4096 && kdeg, "gcn_fwd: edge count %d", E);
   GcnFwdParams p;
+  int DT = 0;
+  for (int k = 0; k < 8; ++k) {
+    p.koff[k] = DT;
+    p.kdeg[k] = k < K ? kdeg[k] : 0;
+    FMM_CHECK_ARG(p.kdeg[k] >= 0 && p.kdeg[k] <= 8 && (k >= K || p.kdeg[k] >= 1), "gcn_fwd: partition %d has max in-degree %d (1..8 supported)", k, p.kdeg[k]);
+    DT += p.kdeg[k];
+  }
+  FMM_CHECK_ARG(DT <= kGcnMaxDeg, "gcn_fwd: total padded degree %d > %d", DT, kGcnMaxDeg);
+  p.DT = DT;
   p.bias = bias;
   p.wpk = wpk;
   p.rowptr = rowptr;
@@ -593,8 +966,8 @@ int fmm_gcn_fwd(const void* x, void* g, void* xa, const void* wpk, const float* 
   p.write_xa = xa != nullptr;
   p.err = err;
   const size_t b_bytes = static_cast<size_t>(p.BN) * 128;
-  const size_t fixed = 4 * 4096 + ((static_cast<size_t>(bias ? V * Cout : 0) * 4 + 15) & ~15ull) + 4 * static_cast<size_t>(p.BN) * 8 +
-                       8 * static_cast<size_t>(V * K) + 8 * static_cast<size_t>(E) + 16 + 512 /*barriers*/ + 1024 /*align*/;
+  const size_t fixed = ((static_cast<size_t>(bias ? V * Cout : 0) * 4 + 15) & ~15ull) + kGcnEpiWarps * 4096 +
+                       8 * static_cast<size_t>(V * DT) + 16 + 512 /*barriers*/ + 1024 /*align*/;
   const size_t budget = 227 * 1024;
   const int nchunk = p.NCC * K;
   p.n_raw = 2;
@@ -638,6 +1011,85 @@ int fmm_gcn_fwd(const void* x, void* g, void* xa, const void* wpk, const float* 
   const int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
   gcn_fwd_kernel<<<grid, kGcnFwdThreads, used, stream>>>(p, tm_x, tm_g, tm_xa);
   FMM_CHECK_LAUNCH("gcn_fwd");
+  return FMM_OK;
+}
+
+int fmm_gcn_wgrad(const void* x, const void* dg, float* dw, const int* rowptr, const int* src, const float* coef,
+                  const int* kdeg, long long rows, int V, int K, int Cin, int Cout, int E, unsigned* err, cudaStream_t stream) {
+  FMM_CHECK_ARG(x && dg && dw && rowptr && src && coef && kdeg, "gcn_wgrad: null pointer");
+  FMM_CHECK_ARG(rows > 0 && rows < (1ll << 31) && V > 0 && V <= kGcnMaxV && K > 0 && K <= 8, "gcn_wgrad: bad shape (rows=%lld V=%d K=%d)", rows, V, K);
+  FMM_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cout <= 256 && Cin <= 512, "gcn_wgrad: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
+  FMM_CHECK_ARG(E > 0 && E <= 4096, "gcn_wgrad: edge count %d", E);
+  GcnWgradParams p;
+  int DT = 0;
+  for (int k = 0; k < 8; ++k) {
+    p.koff[k] = DT;
+    p.kdeg[k] = k < K ? kdeg[k] : 0;
+    FMM_CHECK_ARG(p.kdeg[k] >= 0 && p.kdeg[k] <= 8 && (k >= K || p.kdeg[k] >= 1), "gcn_wgrad: partition %d has max in-degree %d (1..8 supported)", k, p.kdeg[k]);
+    DT += p.kdeg[k];
+  }
+  FMM_CHECK_ARG(DT <= kGcnMaxDeg, "gcn_wgrad: total padded degree %d > %d", DT, kGcnMaxDeg);
+  p.DT = DT;
+  p.dw = dw;
+  p.rowptr = rowptr;
+  p.src = src;
+  p.coef = coef;
+  p.R = rows;
+  p.V = V;
+  p.K = K;
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.NCC = Cin / 64;
+  p.MB = (K + 1) / 2;
+  p.err = err;
+  FMM_CHECK_ARG(p.MB * Cout <= 512, "gcn_wgrad: %d partitions x %d output channels exceed the 512 TMEM columns", K, Cout);
+  // 128-row tiles when two stages of (K operand chunks + the dG tile) fit next to two raw slabs, else 64-row tiles
+  const size_t fixed = 8 * static_cast<size_t>(V * DT) + 16 + 256 + 1024;
+  const size_t budget = 227 * 1024;
+  int TR = 128;
+  size_t chunk = 0, stage = 0, raw = 0, used = 0;
+  for (;; TR = 64) {
+    chunk = static_cast<size_t>(TR) * 128;
+    stage = (K + Cout / 64) * chunk;
+    raw = static_cast<size_t>((TR + 64 + kGcnRawBox - 1) / kGcnRawBox) * kGcnRawBox * 128;
+    used = fixed + 2 * stage + 2 * raw + ((K & 1) ? chunk : 0);
+    if (used <= budget || TR == 64) break;
+  }
+  FMM_CHECK_ARG(used <= budget, "gcn_wgrad: stages do not fit shared memory (%zu bytes)", used);
+  p.n_st = 2;
+  p.n_raw = 2;
+  while (p.n_st < 4 && used + stage <= budget) {
+    ++p.n_st;
+    used += stage;
+  }
+  while (p.n_raw < 4 && used + raw <= budget) {
+    ++p.n_raw;
+    used += raw;
+  }
+  p.ntiles = static_cast<int>((rows + TR - 1) / TR);
+  int slices = num_sms() / p.NCC;
+  if (slices < 1) slices = 1;
+  if (slices > p.ntiles) slices = p.ntiles;
+  p.slices = slices;
+  CUtensorMap tm_x, tm_dg;
+  int st = make_tmap_2d(&tm_x, x, rows, Cin, kGcnRawBox, 64, false);
+  if (st != FMM_OK) return st;
+  st = make_tmap_2d(&tm_dg, dg, rows, Cout, TR, 64, true);
+  if (st != FMM_OK) return st;
+  const int grid = p.NCC * p.slices;
+  cudaError_t e;
+  if (TR == 128) {
+    e = cudaFuncSetAttribute(gcn_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(used));
+    if (e == cudaSuccess) gcn_wgrad_kernel<128><<<grid, kGcnWgThreads, used, stream>>>(p, tm_x, tm_dg);
+  } else {
+    e = cudaFuncSetAttribute(gcn_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(used));
+    if (e == cudaSuccess) gcn_wgrad_kernel<64><<<grid, kGcnWgThreads, used, stream>>>(p, tm_x, tm_dg);
+  }
+  if (e != cudaSuccess) {
+    set_last_error("gcn_wgrad: smem attribute (%zu bytes): %s", used, cudaGetErrorString(e));
+    return FMM_ERR_SMEM;
+  }
+  FMM_CHECK_LAUNCH("gcn_wgrad");
   return FMM_OK;
 }
 

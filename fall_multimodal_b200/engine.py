@@ -61,6 +61,7 @@ class TrunkEngine:
         self.blocks = [(in_channels if cin is None else cin, cout, s, res) for cin, cout, s, res in BLOCK_PLAN]
         self._csr_np = adjacency_csr(A.detach().cpu().double().numpy())
         self.E = len(self._csr_np["fwd_src"])
+        self.kdeg = ops.partition_degrees([int(v) for v in self._csr_np["fwd_rowptr"]], self.K, self.V)
         self._dev = {}
         self.debug = None  # dev aid: set to a dict to capture backward intermediates per block
         # Weight gradients are only needed when backward returns: they are queued on a side stream so
@@ -68,7 +69,7 @@ class TrunkEngine:
         self.materialize_h = True  # bf16: write relu(bn1(G)) once instead of transforming it in two GEMM prologues
         self.overlap_wgrad = False  # measured: no gain, two persistent GEMM CTAs cannot share an SM
         self.fused_gcn = True        # bf16, C % 64 == 0: csrc/gcn.cu instead of agg_fwd + 1x1 tapconv + colstats
-        self.fused_gcn_wgrad = False  # weight gradient re-derives the aggregated operand (no saved Xa)
+        self.fused_gcn_wgrad = True   # weight gradient re-derives the aggregated operand (no saved Xa)
         self._wstreams = {}
 
     def csr(self, device):
@@ -135,7 +136,7 @@ class TrunkEngine:
                 # (csrc/gcn.cu); the K-times wider aggregated tensor only reaches HBM while the old wgrad still wants it
                 Xa = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev) if (need_grad and not self.fused_gcn_wgrad) else None
                 ops.gcn_fwd(x, ops.gcn_pack(Wg.view(K * Cout, Cin), K, Cin, Cout), G, csr["fwd_rowptr"], csr["fwd_src"], coef_f, K,
-                            bias=bias_eff, ch_sum=st[:NR * Cout] if training else None,
+                            self.kdeg, bias=bias_eff, ch_sum=st[:NR * Cout] if training else None,
                             ch_sq=st[NR * Cout:] if training else None, xa=Xa)
             else:
                 Xa = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
@@ -342,7 +343,10 @@ class TrunkEngine:
             # ---- graph conv: wgrad, bias, dgrad through the weights, edge importance ----
             Wg = P[pre + "gcn.conv.weight"]
             dWg = arena.f32(K * Cout, Cin, 1, 1)
-            wgrad_async(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
+            if Xa is None:   # fused graph conv: the aggregated operand is re-derived in the wgrad prologue (csrc/gcn.cu)
+                ops.gcn_wgrad(x, dG, dWg, csr["fwd_rowptr"], csr["fwd_src"], b["coef_f"], K, self.kdeg)
+            else:
+                wgrad_async(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
             grads[pre + "gcn.conv.weight"] = dWg
             grads[pre + "gcn.conv.bias"] = (b["colsum"] @ Tbl).flatten()
             pw_gT = ops.tapconv_pack(Wg, K * Cin, Cout, Cin, Cout, Cout * Cin, 1, 0, Cin, 0, [0], dt)

@@ -135,7 +135,13 @@ def gcn_pack(w: torch.Tensor, K: int, cin: int, cout: int) -> torch.Tensor:
     return out
 
 
-def gcn_fwd(x, wpk, g, rowptr, src, coef, K, bias=None, ch_sum=None, ch_sq=None, xa=None):
+def partition_degrees(rowptr, K: int, V: int):
+    """Maximum in-degree of each adjacency partition from the CSR row pointer (host list; the graph is static)."""
+    rp = rowptr.detach().cpu().view(-1).tolist() if torch.is_tensor(rowptr) else list(rowptr)
+    return [max(1, max(rp[k * V + w + 1] - rp[k * V + w] for w in range(V))) for k in range(K)]
+
+
+def gcn_fwd(x, wpk, g, rowptr, src, coef, K, kdeg, bias=None, ch_sum=None, ch_sq=None, xa=None):
     """g = bias[v] + aggregate(x, edges) @ W^T over the flat rows of channels-last bf16 ``x`` (N,T,V,Cin) -> ``g`` (N,T,V,Cout)."""
     L.require_device(x)
     N, Tn, V, Cin = x.shape
@@ -146,11 +152,29 @@ def gcn_fwd(x, wpk, g, rowptr, src, coef, K, bias=None, ch_sum=None, ch_sq=None,
 
     def run():
         L.check(L.load().fmm_gcn_fwd(L.ptr(x), L.ptr(g), L.ptr(xa), L.ptr(wpk), L.ptr(bias), L.ptr(rowptr), L.ptr(src),
-                                     L.ptr(coef), L.ptr(ch_sum), L.ptr(ch_sq), _nrep(ch_sum, Cout), rows, V, K, Cin, Cout,
+                                     L.ptr(coef), L.int_array(list(kdeg)), L.ptr(ch_sum), L.ptr(ch_sq), _nrep(ch_sum, Cout), rows, V, K, Cin, Cout,
                                      src.numel(), L.ptr(err_word(x.device)), L.stream()), "gcn_fwd")
         return g
 
     return _timed("gcn_fwd", 2.0 * rows * K * Cin * Cout, float(x.numel() + g.numel()) * 2, run)
+
+
+def gcn_wgrad(x, dg, dw, rowptr, src, coef, K, kdeg):
+    """dw (K*Cout, Cin) fp32 += aggregate(x)^T dg  (zero dw first); the aggregated operand is re-derived, not read."""
+    L.require_device(x)
+    N, Tn, V, Cin = x.shape
+    Cout = dg.shape[-1]
+    assert x.is_contiguous() and dg.is_contiguous() and x.dtype == dg.dtype == torch.bfloat16 and dg.shape[:3] == x.shape[:3]
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == K * Cout * Cin
+    rows = N * Tn * V
+
+    def run():
+        L.check(L.load().fmm_gcn_wgrad(L.ptr(x), L.ptr(dg), L.ptr(dw), L.ptr(rowptr), L.ptr(src), L.ptr(coef),
+                                       L.int_array(list(kdeg)), rows, V, K, Cin, Cout, src.numel(), L.ptr(err_word(x.device)),
+                                       L.stream()), "gcn_wgrad")
+        return dw
+
+    return _timed("gcn_wgrad", 2.0 * rows * K * Cin * Cout, float(x.numel() + dg.numel()) * 2, run)
 
 
 # ---------------------------------------------------------------------------------------------

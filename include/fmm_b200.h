@@ -72,13 +72,20 @@ int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, c
  * prologue (shared memory), the K-times wider intermediate never reaches HBM; x is fetched and g written with tensor-map
  * TMA. ch_sum / ch_sq (nullable, fp64 [nrep][Cout], accumulated into) receive the per-channel sum / sum of squares of the
  * stored g: the BatchNorm2d batch statistics of stgcan.py:112. `xa` (nullable) additionally receives the aggregated operand
- * [rows][K*Cin] (dev / cross-check output). CSR arrays as fmm_agg_fwd. Cin, Cout multiples of 64, Cout <= 256, V <= 33.
+ * [rows][K*Cin] (dev / cross-check output). CSR arrays (device) as fmm_agg_fwd; kdeg = HOST array of K ints, the maximum
+ * in-degree of each partition of the (static) graph. Cin, Cout multiples of 64, Cout <= 256, V <= 33.
  * `wpk` from fmm_gcn_pack(W fp32 [K*Cout][Cin]). */
 long long fmm_gcn_packed_bytes(int K, int Cin, int Cout);
 int fmm_gcn_pack(const float* w, void* out, int K, int Cin, int Cout, cudaStream_t stream);
 int fmm_gcn_fwd(const void* x, void* g, void* xa, const void* wpk, const float* bias, const int* rowptr, const int* src,
-                const float* coef, double* ch_sum, double* ch_sq, int nrep, long long rows, int V, int K, int Cin, int Cout,
-                int E, unsigned* err, cudaStream_t stream);
+                const float* coef, const int* kdeg, double* ch_sum, double* ch_sq, int nrep, long long rows, int V, int K,
+                int Cin, int Cout, int E, unsigned* err, cudaStream_t stream);
+
+/* Weight gradient of the fused graph convolution: dw[(k*Cout + co)*Cin + ci] += sum_r dg[r][co] * A_k[r][ci], where A_k is the
+ * aggregated input of fmm_gcn_fwd, re-derived in the prologue (nothing saved by the forward pass). fp32 atomics: zero dw
+ * first. Replaces autograd's weight gradient of the 1x1 conv of stgcan.py:42-51 through the einsum of :54. */
+int fmm_gcn_wgrad(const void* x, const void* dg, float* dw, const int* rowptr, const int* src, const float* coef,
+                  const int* kdeg, long long rows, int V, int K, int Cin, int Cout, int E, unsigned* err, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * memory-bound kernels (one pass over an activation each)

@@ -16,12 +16,12 @@ CASES = [  # layout, N, T, Cin, Cout
 ]
 
 
-def _setup(layout, N, T, Cin, Cout, dev, seed=0):
+def _setup(layout, N, T, Cin, Cout, dev, seed=0, strategy="spatial"):
     from fall_multimodal_b200.graph import Graph, adjacency_csr
 
     g = torch.Generator().manual_seed(seed)
     try:
-        A = torch.tensor(Graph(layout, "spatial").A, dtype=torch.float32)
+        A = torch.tensor(Graph(layout, strategy).A, dtype=torch.float32)
     except Exception:
         pytest.skip(f"layout {layout} not registered")
     K, V, _ = A.shape
@@ -33,7 +33,8 @@ def _setup(layout, N, T, Cin, Cout, dev, seed=0):
     x = torch.randn(N, T, V, Cin, generator=g).to(dev, torch.bfloat16)
     W = (torch.randn(K * Cout, Cin, generator=g) / Cin ** 0.5).to(dev)
     bias = (0.1 * torch.randn(V, Cout, generator=g)).to(dev)
-    return A, Ahat.to(dev), K, V, rowptr, src, coef, x, W, bias
+    kdeg = [int(v) for v in (A != 0).sum(1).max(1).values.clamp_min(1)]
+    return A, Ahat.to(dev), K, V, rowptr, src, coef, x, W, bias, kdeg
 
 
 @gpu
@@ -42,13 +43,13 @@ def test_gcn_fwd_matches_torch(layout, N, T, Cin, Cout):
     from fall_multimodal_b200 import ops
 
     dev = torch.device("cuda:0")
-    A, Ahat, K, V, rowptr, src, coef, x, W, bias = _setup(layout, N, T, Cin, Cout, dev)
+    A, Ahat, K, V, rowptr, src, coef, x, W, bias, kdeg = _setup(layout, N, T, Cin, Cout, dev)
     wpk = ops.gcn_pack(W, K, Cin, Cout)
     G = torch.full((N, T, V, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
     Xa = torch.full((N, T, V, K * Cin), float("nan"), dtype=torch.bfloat16, device=dev)
     s1 = torch.zeros(ops.NREP * Cout, dtype=torch.float64, device=dev)
     s2 = torch.zeros(ops.NREP * Cout, dtype=torch.float64, device=dev)
-    ops.gcn_fwd(x, wpk, G, rowptr, src, coef, K, bias=bias, ch_sum=s1, ch_sq=s2, xa=Xa)
+    ops.gcn_fwd(x, wpk, G, rowptr, src, coef, K, kdeg, bias=bias, ch_sum=s1, ch_sq=s2, xa=Xa)
     torch.cuda.synchronize()
     assert int(ops.err_word(dev).item()) == 0
     # reference: aggregate in fp32, round to bf16 (what the tensor core sees), mix channels with bf16 weights, fp32 accumulate
@@ -78,10 +79,10 @@ def test_gcn_fwd_without_optional_outputs_and_bench_shape():
 
     dev = torch.device("cuda:0")
     N, T, Cin, Cout = 256, 64, 64, 64
-    A, Ahat, K, V, rowptr, src, coef, x, W, bias = _setup("mediapipe33", N, T, Cin, Cout, dev, seed=3)
+    A, Ahat, K, V, rowptr, src, coef, x, W, bias, kdeg = _setup("mediapipe33", N, T, Cin, Cout, dev, seed=3)
     wpk = ops.gcn_pack(W, K, Cin, Cout)
     G = torch.empty(N, T, V, Cout, dtype=torch.bfloat16, device=dev)
-    ops.gcn_fwd(x, wpk, G, rowptr, src, coef, K)
+    ops.gcn_fwd(x, wpk, G, rowptr, src, coef, K, kdeg)
     torch.cuda.synchronize()
     assert int(ops.err_word(dev).item()) == 0
     for n in (0, 77, 255):
@@ -89,3 +90,48 @@ def test_gcn_fwd_without_optional_outputs_and_bench_shape():
         g_ref = torch.einsum("twkc,koc->two", xa_ref, W.view(K, Cout, Cin).to(torch.bfloat16).float())
         err = (G[n].float() - g_ref).abs().max().item() / g_ref.abs().max().item()
         assert err < 6e-3, (n, err)
+
+
+@gpu
+@pytest.mark.parametrize("layout,N,T,Cin,Cout", CASES)
+def test_gcn_wgrad_matches_torch(layout, N, T, Cin, Cout):
+    """dW = aggregate(x)^T dG with the aggregated operand re-derived in the prologue, against fp64 torch on the bf16 inputs."""
+    from fall_multimodal_b200 import ops
+
+    dev = torch.device("cuda:0")
+    A, Ahat, K, V, rowptr, src, coef, x, W, bias, kdeg = _setup(layout, N, T, Cin, Cout, dev, seed=5)
+    g = torch.Generator().manual_seed(9)
+    dG = torch.randn(N, T, V, Cout, generator=g).to(dev, torch.bfloat16)
+    dW = torch.zeros(K * Cout, Cin, device=dev)
+    ops.gcn_wgrad(x, dG, dW, rowptr, src, coef, K, kdeg)
+    ops.gcn_wgrad(x, dG, dW, rowptr, src, coef, K, kdeg)      # accumulates
+    torch.cuda.synchronize()
+    assert int(ops.err_word(dev).item()) == 0
+    xa = torch.einsum("ntvc,kvw->ntwkc", x.float(), Ahat).to(torch.bfloat16).double()     # what the tensor core sees
+    ref = 2 * torch.einsum("ntwkc,ntwo->koc", xa, dG.double()).reshape(K * Cout, Cin)
+    err = (dW.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-3, f"wgrad err {err:.2e}"
+
+
+@gpu
+@pytest.mark.parametrize("strategy,layout", [("uniform", "coco_cut"), ("distance", "mediapipe33"), ("uniform", "mediapipe33")])
+def test_gcn_generic_partitions(strategy, layout):
+    """K = 1 / 2 partitions (uniform / distance strategies, graph.py:76-97 of the reference): the generic producer path."""
+    from fall_multimodal_b200 import ops
+
+    dev = torch.device("cuda:0")
+    N, T, Cin, Cout = 3, 11, 128, 64
+    A, Ahat, K, V, rowptr, src, coef, x, W, bias, kdeg = _setup(layout, N, T, Cin, Cout, dev, seed=7, strategy=strategy)
+    if max(kdeg) > 8:
+        pytest.skip("in-degree above the kernel's unroll limit")
+    G = torch.empty(N, T, V, Cout, dtype=torch.bfloat16, device=dev)
+    ops.gcn_fwd(x, ops.gcn_pack(W, K, Cin, Cout), G, rowptr, src, coef, K, kdeg, bias=bias)
+    xa = torch.einsum("ntvc,kvw->ntwkc", x.float(), Ahat).to(torch.bfloat16).float()
+    g_ref = torch.einsum("ntwkc,koc->ntwo", xa, W.view(K, Cout, Cin).to(torch.bfloat16).float()) + bias[None, None]
+    assert (G.float() - g_ref).abs().max().item() / g_ref.abs().max().item() < 6e-3
+    dG = torch.randn(N, T, V, Cout, generator=torch.Generator().manual_seed(1)).to(dev, torch.bfloat16)
+    dW = torch.zeros(K * Cout, Cin, device=dev)
+    ops.gcn_wgrad(x, dG, dW, rowptr, src, coef, K, kdeg)
+    ref = torch.einsum("ntwkc,ntwo->koc", xa.double(), dG.double()).reshape(K * Cout, Cin)
+    assert (dW.double() - ref).abs().max().item() / ref.abs().max().item() < 2e-3
+    assert int(ops.err_word(dev).item()) == 0

@@ -11,7 +11,11 @@ CrossEntropy(soft targets) -> backward -> RMSprop(lr 1e-3).step(), as F2/main.py
     python bench.py --impl reference ...                     the reference algorithm on the host CPU
 
 Prints ONE JSON line (rank 0). `value` = whole-job clips/s with inputs resident in HBM; `e2e` =
-the same step fed from pinned host memory with the loss read back every step.
+the same step fed from pinned host memory with the loss read back every step. The same line carries, as sub-objects,
+the other BASELINE configurations so that the driver records them too: `config3` (3-stream joint/bone/motion model,
+GLOBAL batch 1024 sharded over the ranks = strong scaling), and at N=1 `targcn` (config 4), `sensor` (config 5),
+`torch_eager_gpu` (the same model through stock PyTorch/cuDNN on this GPU, the de-facto incumbent) and `cpu_baseline`
+(the UNMODIFIED reference modules from the staged tree oracle/_ref on the host cores; the oracle port when absent).
 """
 from __future__ import annotations
 
@@ -85,9 +89,46 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference algorithm on the host cores
 # --------------------------------------------------------------------------------------------
+def reference_available():
+    try:
+        from oracle import build_ref, ref_import
+        return ref_import.available() and (os.path.isdir("/root/reference") or build_ref.verify())
+    except Exception:
+        return False
+
+
+def ref_step_factory(n, threads, device="cpu", autocast=False, config1=False):
+    """Train step of the UNMODIFIED reference modules (oracle/ref_models.py assembles the reference's own classes; the tree
+    is /root/reference here and its staged byte-for-byte copy oracle/_ref on the GPU box). ``config1``: BASELINE configs[0],
+    single STGCAN(3, 33-node spatial, 11 classes), fp32."""
+    from oracle import ref_models as R
+
+    torch.set_num_threads(threads)
+    if config1:
+        stg = R.gstcan_modules(LAYOUT)[0]
+        model = R.load_filled(stg.STGCAN(3, {"layout": LAYOUT, "strategy": "spatial"}, NUM_CLASS), 0)
+    else:
+        model = R.load_filled(R.RefTwoStreamCNN1D(LAYOUT, NUM_CLASS, SENSOR_C, SENSOR_L), 0)
+    model = model.to(device).train()
+    opt = torch.optim.RMSprop(model.parameters(), lr=1e-3)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    skel, sensor, target = synthetic(n, 42, device)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=autocast):
+            out = model(skel, sensor)
+        loss = loss_fn(out.float(), target)          # F2/main.py:113 (probability targets)
+        loss.backward()
+        opt.step()
+        return loss.detach()
+
+    return step
+
+
 def cpu_step_factory(n, threads, device="cpu", autocast=False):
-    """The oracle port of the reference modules as a train step; ``device='cuda'`` + ``autocast`` gives the stock
-    PyTorch/cuDNN eager path of the same model on the GPU (the de-facto incumbent)."""
+    """The oracle PORT of the reference modules as a train step (fallback when the reference tree is not staged);
+    ``device='cuda'`` + ``autocast`` gives the stock PyTorch/cuDNN eager path of the same model on the GPU."""
     from oracle import stgcn_oracle as O
 
     torch.set_num_threads(threads)
@@ -122,15 +163,19 @@ def cpu_step_factory(n, threads, device="cpu", autocast=False):
     return step
 
 
-def time_cpu(n, steps, warmup, threads):
-    step = cpu_step_factory(n, threads)
+def time_cpu(n, steps, warmup, threads, config1=False):
+    """(clips/s, s/step, kind): best single step of `steps` after `warmup`, reference modules when staged else the port."""
+    kind = "reference" if reference_available() else "port"
+    step = ref_step_factory(n, threads, config1=config1) if kind == "reference" else cpu_step_factory(n, threads)
     for _ in range(warmup):
         step()
-    t0 = time.perf_counter()
+    best, tot = float("inf"), 0.0
     for _ in range(steps):
+        t0 = time.perf_counter()
         step()
-    dt = (time.perf_counter() - t0) / steps
-    return n / dt, dt
+        d = time.perf_counter() - t0
+        best, tot = min(best, d), tot + d
+    return n / (tot / steps), tot / steps, kind, n / best
 
 
 def run_reference(args):
@@ -139,17 +184,170 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     n = args.cpu_clips
-    value, dt = time_cpu(n, args.steps, args.warmup, threads)
+    value, dt, kind, best = time_cpu(n, args.steps, args.warmup, threads)
+    what = ("the UNMODIFIED reference modules (Fall_2_Spatial_Temporal_SR/Model/stgcan.py STGCAN x2 + notebook CNN1D + Linear; staged "
+            "tree oracle/_ref) on the host CPU, fp32") if kind == "reference" else \
+        "oracle port of the reference PyTorch modules on the host CPU (reference tree not staged)"
+    # BASELINE.md section 2's own CPU case next to it: configs[0], single STGCAN, N=16, fp32, best of 3
+    c1 = None
+    if kind == "reference":
+        v1, dt1, _, best1 = time_cpu(16, 3, 1, threads, config1=True)
+        c1 = {"workload": "BASELINE configs[0]: STGCAN(3, 33-node spatial, 11 classes) fp32, N=16, T=64", "value": best1,
+              "mean": v1, "unit": "clips/s", "s_per_step": dt1, "sample": "best of 3 steps after 1 warm-up"}
     line = {"metric": "train clips/sec fwd+bwd (GSTCAN, Bx3xT64xV33)", "value": value, "unit": "clips/s",
             "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clips_per_step": n, "T": T, "V": V, "impl": "oracle port of the "
-                       "reference PyTorch modules on the host CPU (the reference tree does not travel to the box)"},
-            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} steps of {n} clips after {args.warmup} warm-up"},
+            "config": {"workload": WORKLOAD, "clips_per_step": n, "T": T, "V": V, "impl": what},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": kind, "best_step": best,
+                             "sample": f"{args.steps} steps of {n} clips after {args.warmup} warm-up", "config1": c1},
             "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# sub-benchmarks carried in the default line
+# --------------------------------------------------------------------------------------------
+GLOBAL_BATCH_3 = 1024
+
+
+def bench_config3(args, dev, world, rank, barrier):
+    """BASELINE configs[2]: 3-stream joint/bone/motion GSTCAN, GLOBAL batch 1024 sharded over the ranks (strong scaling),
+    bf16, NCCL gradient all-reduce bucketed behind backward, whole step as a CUDA graph. Every rank runs this."""
+    import torch.distributed as dist
+
+    import fall_multimodal_b200 as fmm
+    from fall_multimodal_b200.graphs import GraphedStep
+    from fall_multimodal_b200.parallel import GradBuckets
+
+    B = GLOBAL_BATCH_3 // world
+    torch.manual_seed(7)
+    model = fmm.ThreeStreamSTGCAN(3, {"layout": LAYOUT, "strategy": "spatial"}, NUM_CLASS).to(dev).train()
+    if args.sync_bn and world > 1:
+        model.set_sync_bn(True)
+    if world > 1:
+        for p in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(p.data, 0)
+    opt = torch.optim.RMSprop(model.parameters(), lr=1e-3, capturable=True)
+    buckets = GradBuckets([list(model.fc.parameters()) + list(model.stgcan_3.parameters()), list(model.stgcan_2.parameters()),
+                           list(model.stgcan_1.parameters())])
+    loss_fn = torch.nn.CrossEntropyLoss()
+    skel_h, _, target_h = synthetic(B, 1000 + rank)
+    skel, target = skel_h.to(dev), target_h.to(dev)
+
+    def step():
+        buckets.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(skel, None)
+        loss = loss_fn(out.float(), target)
+        loss.backward()
+        buckets.wait()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step()
+    graphed = GraphedStep(step, (), warmup=1)
+    for _ in range(2):
+        graphed.replay()
+    steps = max(4, args.steps // 2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graphed.replay()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    loss = float(graphed.output)
+    buckets.close()
+    graphed = None
+    torch.cuda.empty_cache()
+    return {"workload": "3-stream GSTCAN (joints 3x64x33 + motion 2x63x33 + bones 3x64x33) + Linear(768, 11), train step "
+                        "fwd+bwd+RMSprop, bf16", "metric": "train clips/sec fwd+bwd (3-stream GSTCAN)", "value": GLOBAL_BATCH_3 * steps / (ms / 1e3),
+            "unit": "clips/s", "global_batch": GLOBAL_BATCH_3, "clips_per_gpu": B, "n_gpus": world, "scaling": "strong", "steps": steps,
+            "ms_per_step": ms / steps, "bn": "synchronised over the ranks" if (args.sync_bn and world > 1) else "per-shard statistics",
+            "gradient_bytes_per_step": sum(p.numel() for p in model.parameters()) * 4, "loss": loss,
+            "note": "efficiency vs N=1 = value(N) / (N * value(1)) over the driver's N = 1, 2, 4, 8 runs of this same line"}
+
+
+def bench_sensor(dev):
+    """BASELINE configs[4]: sensor-only BiLSTM(6, 64) inference on 8192 windows of 128 x 6 (HAR-shaped), fp32 recurrence."""
+    import fall_multimodal_b200 as fmm
+
+    B, Tn, I = 8192, 128, 6
+    torch.manual_seed(42)
+    m = fmm.BiLSTM(I, 64, 1, 0.3, NUM_CLASS, "mean").to(dev).eval()
+    host = torch.randn(B, Tn, I).pin_memory()
+    x = host.to(dev)
+
+    def timeit(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    with torch.no_grad():
+        ms = timeit(lambda: m(None, x), 10)
+        ms_e2e = timeit(lambda: m(None, host.to(dev, non_blocking=True)).argmax(1).cpu(), 5)
+    fl = 2.0 * Tn * 2 * 4 * 64 * (I + 64) * B
+    return {"workload": "BiLSTM(6,64,'mean') inference, 8192 windows of 128 x 6", "metric": "windows/s", "value": B / ms * 1e3,
+            "unit": "windows/s", "ms": ms, "us_per_time_step": ms * 1e3 / Tn, "tflops": fl / ms / 1e9,
+            "e2e": {"value": B / ms_e2e * 1e3, "unit": "windows/s", "h2d_bytes_per_step": B * Tn * I * 4, "d2h_bytes_per_step": B * 8}}
+
+
+def bench_targcn_sub(args, dev):
+    """BASELINE configs[3] as a sub-object of the default line (the standalone line: --workload targcn)."""
+    import fall_multimodal_b200 as fmm
+    from fall_multimodal_b200 import _lib
+    from fall_multimodal_b200.graphs import GraphedStep
+    import synth
+
+    B = 512
+    model = fmm.TARGCN(num_nodes=TG_V, adj=None, seq_len=TG_T)
+    model.load_state_dict(synth.fill_targcn({k: tuple(v.shape) for k, v in model.state_dict().items()}, 1))
+    model = model.to(dev).train()
+    opt = torch.optim.RMSprop(model.parameters(), lr=1e-4, capturable=True)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    x, tgt = (t.to(dev) for t in synth.synthetic_clips(B, TG_T, TG_V, seed=42))
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(x)
+        loss = loss_fn(out.float(), tgt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    l0 = _lib.launch_count
+    step()
+    launches = _lib.launch_count - l0
+    graphed = GraphedStep(step, (), warmup=1)
+    graphed.replay()
+    torch.cuda.synchronize()
+    steps = 4
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graphed.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    graphed = None
+    torch.cuda.empty_cache()
+    return {"workload": TG_WORKLOAD, "metric": TG_METRIC, "value": B / ms * 1e3, "unit": "clips/s", "clips_per_gpu": B,
+            "ms_per_step": ms, "launches_per_step": launches, "steps": steps, "dtype": "bf16"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -202,19 +400,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    step_ms = []
+
+    def timed(fn, steps, per_step=None):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            evs[i + 1].record()          # an event record does not synchronise: the K steps stay back to back
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([evs[0].elapsed_time(evs[-1])], device=dev)
+        if per_step is not None:
+            per_step[:] = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    graphed = None
     for _ in range(args.warmup):
         step(skel, sensor, target)
     if args.graph:
@@ -255,11 +458,11 @@ def run_ours(args):
         prof, ops.profile = ops.profile, None
         prof_steps = 2
         model.concurrent_streams = bool(args.streams)
-        ms = timed(lambda: step(skel, sensor, target), args.steps)
+        ms = timed(lambda: step(skel, sensor, target), args.steps, step_ms)
     else:
         ops.profile = []
         launches0 = _lib.launch_count
-        ms = timed(lambda: step(skel, sensor, target), args.steps)
+        ms = timed(lambda: step(skel, sensor, target), args.steps, step_ms)
         launches = _lib.launch_count - launches0
         prof, ops.profile = ops.profile, None
         prof_steps = args.steps
@@ -279,6 +482,12 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     h2d = skel_h.numel() * 4 + sensor_h.numel() * 4 + target_h.numel() * 4
+
+    config3 = None
+    if not args.no_config3:
+        graphed = eager_step = None   # drop the captured step (its memory pool) before the next model is built
+        torch.cuda.empty_cache()
+        config3 = bench_config3(args, dev, world, rank, barrier)
 
     if rank == 0:
         peaks = {}
@@ -311,9 +520,13 @@ def run_ours(args):
             kind = max(tot, key=lambda k: tot[k][1])
             fl, sec, cnt, nb = tot[kind]
             traffic = None
-            try:  # DRAM bytes per launch of the same kernel from the committed ncu capture of one step
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")))[kind.split("_")[0]][
-                    "avg_dram_bytes_per_launch"]
+            try:  # DRAM bytes per launch, PER LAUNCH CLASS, from the committed ncu capture of one step of this command
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic_by_class.json")))
+                for k in by:
+                    if k in tr:
+                        by[k]["traffic"] = tr[k]["avg_dram_bytes_per_launch"]
+                        by[k]["traffic_over_algorithmic"] = tr[k]["avg_dram_bytes_per_launch"] / (tot[k][3] / tot[k][2])
+                traffic = by[kind].get("traffic")
             except (OSError, KeyError, ValueError):
                 pass
             roof = {"bound": by[kind]["bound"],
@@ -321,7 +534,7 @@ def run_ours(args):
                               f" ({cnt // prof_steps} per step)",
                     "achieved": by[kind]["achieved"], "peak": peak_tf if by[kind]["bound"] == "tensor" else peak_bw,
                     "unit": by[kind]["unit"], "frac": by[kind]["frac"], "traffic": traffic,
-                    "traffic_unit": "DRAM bytes per launch, all launches of this kernel (ncu, profiles/r01_gemm_dram_traffic.json)",
+                    "traffic_unit": "DRAM bytes per launch of this launch class (ncu dram__bytes_read+write, profiles/r02_dram_traffic_by_class.json)",
                     "flops_per_launch": fl / cnt, "algorithmic_bytes_per_launch": nb / cnt,
                     "peak_source": peak_src + (" / hbm_gbs" if peaks else ""), "share_of_step": by[kind]["share_of_step"],
                     "timed_on": ("eager steps (branches serialised) next to the graph-replayed timed region; share_of_step = "
@@ -330,14 +543,17 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, dt = time_cpu(args.cpu_clips, 2, 1, threads)
-            cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
-                   "sample": f"2 steps of {args.cpu_clips} clips after 1 warm-up ({dt:.1f} s/step), same model/shape"}
+            v, dt, ckind, best = time_cpu(args.cpu_clips, 3, 1, threads)
+            cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": ckind, "best_step": best,
+                   "sample": f"3 steps of {args.cpu_clips} clips after 1 warm-up ({dt:.1f} s/step), same model/shape: " +
+                             ("the unmodified reference modules (staged tree oracle/_ref)" if ckind == "reference" else "oracle port")}
         eager_gpu = None
-        if world == 1 and args.torch_eager_gpu:
-            # the same model through stock PyTorch/cuDNN on this GPU (oracle modules, bf16 autocast, eager): informational
+        if world == 1 and not args.no_torch_eager:
+            # the same model through stock PyTorch/cuDNN on this GPU (the reference's own modules when staged, bf16 autocast,
+            # eager - exactly what MF3/main.py:97 runs): the incumbent SURVEY 2.1 says to beat
             torch.backends.cudnn.benchmark = True
-            est = cpu_step_factory(B, os.cpu_count() or 1, device=str(dev), autocast=True)
+            ref_ok = reference_available()
+            est = (ref_step_factory if ref_ok else cpu_step_factory)(B, os.cpu_count() or 1, device=str(dev), autocast=True)
             for _ in range(3):
                 est()
             torch.cuda.synchronize()
@@ -348,8 +564,15 @@ def run_ours(args):
             ee1.record()
             torch.cuda.synchronize()
             ems = ee0.elapsed_time(ee1) / 5
-            eager_gpu = {"value": B / ems * 1e3, "unit": "clips/s", "ms_per_step": ems,
-                         "what": "oracle port of the reference modules, torch eager + cuDNN, bf16 autocast, same GPU, same batch"}
+            eager_gpu = {"value": B / ems * 1e3, "unit": "clips/s", "ms_per_step": ems, "speedup": value / (B / ems * 1e3),
+                         "what": ("the unmodified reference modules" if ref_ok else "oracle port of the reference modules") +
+                                 ", torch eager + cuDNN, bf16 autocast, same GPU, same batch, 5 steps after 3 warm-up"}
+            del est
+            torch.cuda.empty_cache()
+        targ = sens = None
+        if world == 1 and not args.no_extra:
+            sens = bench_sensor(dev)
+            targ = bench_targcn_sub(args, dev)
         line = {"metric": "train clips/sec fwd+bwd (GSTCAN, Bx3xT64xV33)", "value": value, "unit": "clips/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -359,8 +582,18 @@ def run_ours(args):
                 "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+        if step_ms:
+            sm = sorted(step_ms)
+            line["step_ms"] = {"min": sm[0], "median": sm[len(sm) // 2], "max": sm[-1],
+                               "note": "per-step CUDA-event intervals inside the timed region (rank 0)"}
         if eager_gpu is not None:
             line["torch_eager_gpu"] = eager_gpu
+        if config3 is not None:
+            line["config3"] = config3
+        if targ is not None:
+            line["targcn"] = targ
+        if sens is not None:
+            line["sensor"] = sens
         print(json.dumps(line), flush=True)
     if world > 1:
         # Captured NCCL collectives keep the communicator busy at teardown: destroy_process_group() was
@@ -381,26 +614,45 @@ TG_WORKLOAD = ("TARGCN(num_nodes=25, adj=None) graph-GRU encoder (2 layers x 300
 TG_METRIC = "train clips/sec fwd+bwd (TARGCN, BxT300xV25x3)"
 
 
-def targcn_cpu(n, steps, warmup, threads, device="cpu", autocast=False):
+def targcn_cpu(n, steps, warmup, threads, device="cpu", autocast=False, use_reference=False):
     """The oracle port of TRAGCN.py / GRU.py / EmbGCN.py / TA.py (bounded sample of n clips) on the host cores, or with
     ``device='cuda'`` the stock PyTorch eager path on the GPU. Note: the port already hoists the loop-invariant EmbGCN algebra
     the literal reference recomputes in each of its 2*T cell calls, i.e. it is faster than the reference as written."""
     from oracle import tragcn_oracle as TO
 
     torch.set_num_threads(threads)
-    sd = {k: v.to(device).requires_grad_(not k.endswith("PE.pe")) for k, v in
-          TO.fill_targcn(TO.targcn_param_shapes(V=TG_V, T=TG_T), 1).items()}
-    opt = torch.optim.RMSprop([v for v in sd.values() if v.requires_grad], lr=1e-4)
     x, tgt = (t.to(device) for t in TO.synthetic_clips(n, TG_T, TG_V, seed=42))
     cuda = torch.device(device).type == "cuda"
+    if use_reference:
+        # the unmodified TRAGCN.py / GRU.py / EmbGCN.py / TA.py (staged tree), seq_len re-pointed at T (SURVEY D5), pools seeded
+        import warnings
+        from oracle import ref_models as R
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model = R.targcn(TG_V, TG_T).to(device).train()
+        opt = torch.optim.RMSprop(model.parameters(), lr=1e-4)
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        with torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=autocast):
-            out = TO.targcn_forward(sd, x)
-        loss = torch.nn.CrossEntropyLoss()(out.float(), tgt)
-        loss.backward()
-        opt.step()
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                with torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=autocast):
+                    out = model(x)
+            loss = torch.nn.CrossEntropyLoss()(out.float(), tgt)
+            loss.backward()
+            opt.step()
+    else:
+        sd = {k: v.to(device).requires_grad_(not k.endswith("PE.pe")) for k, v in
+              TO.fill_targcn(TO.targcn_param_shapes(V=TG_V, T=TG_T), 1).items()}
+        opt = torch.optim.RMSprop([v for v in sd.values() if v.requires_grad], lr=1e-4)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=autocast):
+                out = TO.targcn_forward(sd, x)
+            loss = torch.nn.CrossEntropyLoss()(out.float(), tgt)
+            loss.backward()
+            opt.step()
 
     for _ in range(warmup):
         step()
@@ -420,13 +672,15 @@ def run_reference_targcn(args):
         return
     threads = os.cpu_count() or 1
     n = max(1, min(args.cpu_clips, 4))
-    value, dt = targcn_cpu(n, args.steps, args.warmup, threads)
+    ref_ok = reference_available()
+    value, dt = targcn_cpu(n, args.steps, args.warmup, threads, use_reference=ref_ok)
     line = {"metric": TG_METRIC, "value": value, "unit": "clips/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": TG_WORKLOAD, "clips_per_step": n, "T": TG_T, "V": TG_V,
-                       "impl": "oracle port of the reference PyTorch modules on the host CPU"},
-            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port",
+                       "impl": ("the UNMODIFIED reference TRAGCN.py/GRU.py/EmbGCN.py/TA.py (staged tree oracle/_ref)" if ref_ok else
+                                "oracle port of the reference PyTorch modules") + " on the host CPU"},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "reference" if ref_ok else "port",
                              "sample": f"{args.steps} steps of {n} clips after {args.warmup} warm-up"},
             "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -439,7 +693,7 @@ def run_targcn(args):
     from fall_multimodal_b200 import _lib, tragcn
     from fall_multimodal_b200.graphs import GraphedStep
     from fall_multimodal_b200.parallel import GradBuckets
-    from oracle import tragcn_oracle as TO  # synthetic clips + deterministic weights only
+    import synth as TO  # synthetic clips + deterministic weights (neutral generators, not the oracle)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -599,8 +853,11 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="1: run the independent branches (two trunks, sensor) on side streams")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the whole train step as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--torch-eager-gpu", action="store_true",
-                    help="also time the stock PyTorch/cuDNN eager path of the same model on the GPU (adds a torch_eager_gpu key)")
+    ap.add_argument("--no-torch-eager", action="store_true", help="skip the stock PyTorch/cuDNN eager leg on the same GPU (N=1)")
+    ap.add_argument("--torch-eager-gpu", action="store_true", help="(kept for compatibility: the eager leg is on by default)")
+    ap.add_argument("--no-config3", action="store_true", help="skip the 3-stream / global-batch-1024 strong-scaling sub-benchmark")
+    ap.add_argument("--no-extra", action="store_true", help="skip the TARGCN (config 4) and sensor (config 5) sub-benchmarks (N=1)")
+    ap.add_argument("--sync-bn", type=int, default=0, help="config3: 1 = BatchNorm statistics all-reduced over the ranks")
     ap.add_argument("--workload", default="gstcan", choices=["gstcan", "targcn"],
                     help="gstcan: BASELINE configs[1] (the headline, default); targcn: configs[3] (TARGCN T=300 V=25, 512 clips)")
     args = ap.parse_args()

@@ -15,6 +15,8 @@
 // Work split: item = (ci tile, tap group, co tile) keeps TG accumulators [128 x BN] resident in
 // TMEM; the row dimension is sliced across CTAs and the partial results are added to global
 // memory with fp32 atomics (dW must be zeroed by the caller).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "producer.cuh"
 #include "ptx.cuh"
@@ -374,7 +376,10 @@ int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, c
   if (nparts == 1) {
     p.JT = 16;
     p.MCH = Cin > 64 ? 2 : 1;
-    p.BN = ntaps > 1 ? 64 : (cout64 < 256 ? cout64 : 256);
+    // multi-tap: the accumulators of a tap group share TMEM (TG * BN <= 512). N = 64 MMAs run at ~57 cycles (shared-memory
+    // bound, floor 32); N = 128 runs at its 64-cycle floor, so wide layers take 128-column tiles (4 taps per group)
+    static const int kWgTapBn = getenv("FMM_WG_TAP_BN") ? atoi(getenv("FMM_WG_TAP_BN")) : 128;
+    p.BN = ntaps > 1 ? (cout64 >= 128 && p.MCH == 2 ? kWgTapBn : 64) : (cout64 < 256 ? cout64 : 256);
   } else {
     p.JT = 8;
     p.MCH = 1;

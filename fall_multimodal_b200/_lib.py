@@ -97,6 +97,9 @@ _SIGNATURES = {
     "fmm_gcn_pack": [_P, _P, c_int, c_int, c_int, _P],
     "fmm_gcn_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(c_int), _P, _P, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "fmm_gcn_wgrad": [_P, _P, _P, _P, _P, _P, C.POINTER(c_int), c_ll, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "fmm_gcn_packed_bwd_bytes": [c_int, c_int, c_int],
+    "fmm_gcn_pack_bwd": [_P, _P, c_int, c_int, c_int, _P],
+    "fmm_gcn_bwd": [_P] * 11 + [c_int, c_ll, c_int, c_int, c_int, c_int, _P, _P],
     "fmm_agg_fwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_dcoef": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
@@ -140,7 +143,7 @@ _SIGNATURES = {
     "fmm_tg_relu_mask": [_P, _P, c_ll, c_int, _P],
     "fmm_tg_transpose": [_P, _P, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_int, c_int, c_int, _P],
 }
-_RESTYPES = {"fmm_tapconv_packed_bytes": c_ll, "fmm_gcn_packed_bytes": c_ll}
+_RESTYPES = {"fmm_tapconv_packed_bytes": c_ll, "fmm_gcn_packed_bytes": c_ll, "fmm_gcn_packed_bwd_bytes": c_ll}
 
 
 class BgemmDesc(C.Structure):

@@ -848,6 +848,372 @@ gcn_wgrad_kernel(const __grid_constant__ GcnWgradParams p, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// backward data:  dx[(f,v)][ci] = addend + sum_{e in out(v)} coef[e] * P[(f, dst e)][kk e][ci],   P = dG . W_k^T
+//                 dcoef[eid e] += sum_{f,ci} x[(f,v)][ci] * P[(f, dst e)][kk e][ci]       (gradient of A*edge_importance)
+//
+// The GEMM comes first here (P is what the edge-importance gradient needs), the TRANSPOSED adjacency aggregation runs in
+// the epilogue: a tile is floor(128/V) whole frames; per 64-channel slab cc of the input the tensor core produces
+// P[128 rows][K*64] (one N = K*64 MMA per 16 output channels) into TMEM, four converter warps move it to shared memory as
+// bf16, and sixteen aggregation warps gather it along the out-edges of every joint into dx (adding the residual-path
+// gradient) while dotting the same pieces with x for dcoef. P never reaches HBM (the round-1 path wrote and re-read a
+// K-times wider tensor and ran a separate aggregation kernel).
+// ------------------------------------------------------------------------------------------
+struct GcnBwdParams {
+  const void* x;        // [R][Cin] bf16 (for dcoef; nullable with dcoef)
+  const void* addend;   // [R][Cin] bf16 or null
+  void* dx;             // [R][Cin] bf16
+  const void* wpk;      // images [(cc*nck + kc)][K*64 rows = (k, ci)][64 = co - kc*64] bf16 SWIZZLE_128B (fmm_gcn_pack_bwd)
+  const int* rowptr;    // bwd CSR over v: out-edges
+  const int* dst;
+  const int* kk;
+  const float* coef;
+  const int* eid;
+  float* dcoef;         // [E] fp32, accumulated into (nullable)
+  long long R;
+  int V, K, Cin, Cout, D;   // D = maximum total out-degree of a joint (slots per joint)
+  int NCC, nck, FPT, ntiles;
+  int n_g, n_w, resident;
+  unsigned* err;
+};
+
+constexpr int kGcnBwdAggWarps = 16;
+constexpr int kGcnBwdThreads = (kGcnBwdAggWarps + 4 + 3) * 32;   // aggregation, converter, dG loader, weight loader, MMA
+constexpr int kGcnBwdMaxD = 8;
+
+template <int D>
+__device__ __forceinline__ void gcn_bwd_rows(const GcnBwdParams& p, uint32_t tab, uint32_t pst, uint32_t PR, int cc, long long r0,
+                                             int tile_rows, float (&dc)[2][kGcnBwdMaxD]) {
+  // thread = (16-byte piece of the 64-channel slab, row lane); rows rl and rl + 64 of the tile
+  const uint32_t pc = threadIdx.x & 7u;
+  const int rl = threadIdx.x >> 3;
+  const __nv_bfloat16* __restrict__ X = reinterpret_cast<const __nv_bfloat16*>(p.x);
+  const __nv_bfloat16* __restrict__ AD = reinterpret_cast<const __nv_bfloat16*>(p.addend);
+  __nv_bfloat16* __restrict__ DX = reinterpret_cast<__nv_bfloat16*>(p.dx);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = rl + 64 * i;
+    const long long r = r0 + row;
+    if (row >= tile_rows || r >= p.R) continue;   // warp-uniform up to the 4 rows of a warp: the vote below uses the active mask
+    const int f = row / p.V, v = row - f * p.V;
+    const size_t goff = static_cast<size_t>(r) * p.Cin + cc * 64 + pc * 8;
+    uint4 xa = make_uint4(0, 0, 0, 0), ad = make_uint4(0, 0, 0, 0);
+    if (p.dcoef) xa = *reinterpret_cast<const uint4*>(X + goff);
+    if (AD) ad = *reinterpret_cast<const uint4*>(AD + goff);
+    uint2 en[D];
+    uint4 u[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) en[j] = lds64(tab + 8u * static_cast<uint32_t>(v * D + j));
+    const uint32_t fb = pst + static_cast<uint32_t>(f * p.V) * PR + pc * 16u;
+#pragma unroll
+    for (int j = 0; j < D; ++j) u[j] = lds128(fb + en[j].x);
+    float acc[8], xf[8];
+    {
+      const uint32_t aw[4] = {ad.x, ad.y, ad.z, ad.w}, xw[4] = {xa.x, xa.y, xa.z, xa.w};
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        acc[2 * l] = __uint_as_float(aw[l] << 16);
+        acc[2 * l + 1] = __uint_as_float(aw[l] & 0xffff0000u);
+        xf[2 * l] = __uint_as_float(xw[l] << 16);
+        xf[2 * l + 1] = __uint_as_float(xw[l] & 0xffff0000u);
+      }
+    }
+    const unsigned am = __activemask();
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      if (!__any_sync(am, en[j].y != 0u)) continue;
+      const float cf = __uint_as_float(en[j].y);
+      const uint32_t uw[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+      float d = 0.f;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const float lo = __uint_as_float(uw[l] << 16), hi = __uint_as_float(uw[l] & 0xffff0000u);
+        acc[2 * l] = fmaf(cf, lo, acc[2 * l]);
+        acc[2 * l + 1] = fmaf(cf, hi, acc[2 * l + 1]);
+        d = fmaf(xf[2 * l], lo, d);
+        d = fmaf(xf[2 * l + 1], hi, d);
+      }
+      dc[i][j] += d;
+    }
+    *reinterpret_cast<uint4*>(DX + goff) = pack8_bf16(acc);
+  }
+}
+
+__global__ void __launch_bounds__(kGcnBwdThreads, 1)
+gcn_bwd_kernel(const __grid_constant__ GcnBwdParams p, const __grid_constant__ CUtensorMap tm_dg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t g_bytes = static_cast<uint32_t>(p.nck) * kGcnChunkBytes;            // dG tile: nck images [128][64]
+  const uint32_t w_bytes = static_cast<uint32_t>(p.K) * 64u * 128u;                  // one weight image [K*64][64]
+  const uint32_t PR = static_cast<uint32_t>(p.K) * 128u + 16u;                       // P staging row pitch (bank-conflict pad)
+  const uint32_t pst_bytes = (128u * PR + 1023u) & ~1023u;
+  const uint32_t g0 = base;
+  const uint32_t w0 = g0 + p.n_g * g_bytes;
+  const uint32_t pst0 = w0 + p.n_w * w_bytes;
+  const uint32_t tab = pst0 + 2u * pst_bytes;                                        // [V][D] (dst offset, coef)
+  const uint32_t eidt = tab + 8u * static_cast<uint32_t>(p.V * p.D);                 // [V][D] forward edge id or -1
+  const uint32_t bars0 = (eidt + 4u * static_cast<uint32_t>(p.V * p.D) + 15u) & ~15u;
+  auto g_full = [&](int s) { return bars0 + 8u * s; };
+  auto g_empty = [&](int s) { return bars0 + 8u * (p.n_g + s); };
+  auto w_full = [&](int s) { return bars0 + 8u * (2 * p.n_g + s); };
+  auto w_empty = [&](int s) { return bars0 + 8u * (2 * p.n_g + p.n_w + s); };
+  auto acc_full = [&](int s) { return bars0 + 8u * (2 * p.n_g + 2 * p.n_w + s); };
+  auto acc_empty = [&](int s) { return bars0 + 8u * (2 * p.n_g + 2 * p.n_w + 2 + s); };
+  auto pst_full = [&](int s) { return bars0 + 8u * (2 * p.n_g + 2 * p.n_w + 4 + s); };
+  auto pst_empty = [&](int s) { return bars0 + 8u * (2 * p.n_g + 2 * p.n_w + 6 + s); };
+  const uint32_t tmem_slot = bars0 + 8u * (2 * p.n_g + 2 * p.n_w + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int NP = p.K * 64;   // MMA N = columns of P per slab
+  constexpr int kLoaderG = kGcnBwdAggWarps + 4, kLoaderW = kGcnBwdAggWarps + 5, kMma = kGcnBwdAggWarps + 6;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_g; ++s) {
+      mbar_init(g_full(s), 1);
+      mbar_init(g_empty(s), 1);
+    }
+    for (int s = 0; s < p.n_w; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 128);
+      mbar_init(pst_full(s), 128);
+      mbar_init(pst_empty(s), kGcnBwdAggWarps * 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kMma) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (warp == kLoaderG && lane == 0) tma_prefetch_desc(&tm_dg);
+  // out-edge table, dense and zero padded to D slots per joint: (dst*PR + kk*128 bytes, coef); padding = (v*PR, 0)
+  for (int i = threadIdx.x; i < p.V * p.D; i += blockDim.x) {
+    const int v = i / p.D, j = i - v * p.D;
+    const int e0 = p.rowptr[v], e1 = p.rowptr[v + 1];
+    if (j == 0 && e1 - e0 > p.D) {
+      if (p.err) atomicCAS(p.err, 0u, 0x80000000u | (30u << 16) | static_cast<unsigned>(v));
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+    const bool real = e0 + j < e1;
+    const uint32_t off = real ? static_cast<uint32_t>(p.dst[e0 + j]) * PR + static_cast<uint32_t>(p.kk[e0 + j]) * 128u : static_cast<uint32_t>(v) * PR;
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(tab + 8u * i), "r"(off), "r"(real ? __float_as_uint(p.coef[e0 + j]) : 0u) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(eidt + 4u * i), "r"(real ? p.eid[e0 + j] : -1) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  const int tile_rows = p.FPT * p.V;
+  const int nimg = p.NCC * p.nck;
+
+  if (warp < kGcnBwdAggWarps) {
+    // ------------------------------ transposed aggregation -> dx, dcoef ------------------------------
+    float dc[2][kGcnBwdMaxD];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < kGcnBwdMaxD; ++j) dc[i][j] = 0.f;
+    int ps = 0;
+    uint32_t pph = 0;
+    for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
+      const long long r0 = static_cast<long long>(tile) * tile_rows;
+      for (int cc = 0; cc < p.NCC; ++cc) {
+        mbar_wait_relaxed(pst_full(ps), pph, p.err, 21, 20);
+        const uint32_t pst = pst0 + ps * pst_bytes;
+        switch (p.D) {
+          case 1: case 2: case 3: case 4: gcn_bwd_rows<4>(p, tab, pst, PR, cc, r0, tile_rows, dc); break;
+          case 5: gcn_bwd_rows<5>(p, tab, pst, PR, cc, r0, tile_rows, dc); break;
+          case 6: gcn_bwd_rows<6>(p, tab, pst, PR, cc, r0, tile_rows, dc); break;
+          case 7: gcn_bwd_rows<7>(p, tab, pst, PR, cc, r0, tile_rows, dc); break;
+          default: gcn_bwd_rows<8>(p, tab, pst, PR, cc, r0, tile_rows, dc); break;
+        }
+        mbar_arrive(pst_empty(ps));
+        if (++ps == 2) {
+          ps = 0;
+          pph ^= 1u;
+        }
+      }
+    }
+    if (p.dcoef) {
+      // reduce over the eight 16-byte pieces of a row (consecutive lanes), one atomic per (row lane, slot)
+      const int rl = threadIdx.x >> 3;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int row = rl + 64 * i;
+        const int v = row % p.V;
+#pragma unroll
+        for (int j = 0; j < kGcnBwdMaxD; ++j) {
+          float d = dc[i][j];
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if ((threadIdx.x & 7) == 0 && row < tile_rows && j < (p.D < 4 ? 4 : p.D) && j < p.D) {
+            const int e = static_cast<int>(lds32(eidt + 4u * static_cast<uint32_t>(v * p.D + j)));
+            if (e >= 0) atomicAdd(p.dcoef + e, d);
+          }
+        }
+      }
+    }
+  } else if (warp < kGcnBwdAggWarps + 4) {
+    // ------------------------------ converters: TMEM -> bf16 staging ------------------------------
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acs = 0, ps = 0;
+    uint32_t acph = 0, pph = 0;
+    for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
+      for (int cc = 0; cc < p.NCC; ++cc) {
+        mbar_wait_relaxed(acc_full(acs), acph, p.err, 22, 20);
+        tc_fence_after();
+        mbar_wait_relaxed(pst_empty(ps), pph ^ 1u, p.err, 23, 20);
+        const uint32_t taddr = tmem_base + static_cast<uint32_t>(acs) * 256u + (static_cast<uint32_t>(quad * 32) << 16);
+        const uint32_t drow = pst0 + ps * pst_bytes + static_cast<uint32_t>(row) * PR;
+        for (int cg = 0; cg < NP / 32; ++cg) {
+          uint32_t vv[32];
+          tmem_ld32(taddr + cg * 32, vv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(vv[g * 8 + i]);
+            sts128g(drow + static_cast<uint32_t>(cg * 64 + g * 16), pack8_bf16(f));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty(acs));
+        mbar_arrive(pst_full(ps));
+        if (++acs == 2) {
+          acs = 0;
+          acph ^= 1u;
+        }
+        if (++ps == 2) {
+          ps = 0;
+          pph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == kLoaderG) {
+    // ------------------------------ dG tile loader (TMA) ------------------------------
+    if (lane == 0) {
+      int gs = 0;
+      uint32_t gph = 0;
+      for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
+        const int r0 = tile * tile_rows;
+        mbar_wait_relaxed(g_empty(gs), gph ^ 1u, p.err, 24, 40);
+        mbar_arrive_expect_tx(g_full(gs), g_bytes);
+        for (int kc = 0; kc < p.nck; ++kc) tma_load_2d(g0 + gs * g_bytes + kc * kGcnChunkBytes, &tm_dg, kc * 64, r0, g_full(gs));
+        if (++gs == p.n_g) {
+          gs = 0;
+          gph ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kLoaderW) {
+    // -------------------------------- weight loader --------------------------------
+    if (lane == 0 && first_tile < p.ntiles) {
+      const uint8_t* W = reinterpret_cast<const uint8_t*>(p.wpk);
+      if (p.resident) {
+        mbar_arrive_expect_tx(w_full(0), static_cast<uint32_t>(nimg) * w_bytes);
+        for (int i = 0; i < nimg; ++i) bulk_g2s(w0 + i * w_bytes, W + static_cast<size_t>(i) * w_bytes, w_bytes, w_full(0));
+      } else {
+        int ws = 0;
+        uint32_t wph = 0;
+        for (int tile = first_tile; tile < p.ntiles; tile += tile_step)
+          for (int i = 0; i < nimg; ++i) {
+            mbar_wait_relaxed(w_empty(ws), wph ^ 1u, p.err, 25, 40);
+            mbar_arrive_expect_tx(w_full(ws), w_bytes);
+            bulk_g2s(w0 + ws * w_bytes, W + static_cast<size_t>(i) * w_bytes, w_bytes, w_full(ws));
+            if (++ws == p.n_w) {
+              ws = 0;
+              wph ^= 1u;
+            }
+          }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------- MMA issuer ----------------------------------
+    const uint32_t idesc = make_idesc_bf16(NP, 0, 0);
+    const uint32_t hi = desc_hi(1024);
+    int gs = 0, ws = 0, acs = 0;
+    uint32_t gph = 0, wph = 0, acph = 0;
+    if (p.resident && first_tile < p.ntiles) mbar_wait(w_full(0), 0, p.err, 26);
+    for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
+      mbar_wait(g_full(gs), gph, p.err, 27);
+      for (int cc = 0; cc < p.NCC; ++cc) {
+        mbar_wait(acc_empty(acs), acph ^ 1u, p.err, 28);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acs) * 256u;
+        for (int kc = 0; kc < p.nck; ++kc) {
+          const int img = cc * p.nck + kc;
+          if (!p.resident) mbar_wait(w_full(ws), wph, p.err, 29);
+          tc_fence_after();
+          const uint32_t a_lo = desc_lo(g0 + gs * g_bytes + kc * kGcnChunkBytes, 16);
+          const uint32_t b_lo = desc_lo(p.resident ? w0 + img * w_bytes : w0 + ws * w_bytes, 16);
+          if (elect_one()) {
+#pragma unroll
+            for (uint32_t kk = 0; kk < 4; ++kk)
+              umma_bf16_lh(d_tmem, a_lo + kk * 2u, hi, b_lo + kk * 2u, hi, idesc, static_cast<uint32_t>(kc) | kk);
+            if (!p.resident) umma_commit(w_empty(ws));
+            if (kc == p.nck - 1) {
+              umma_commit(acc_full(acs));
+              if (cc == p.NCC - 1) umma_commit(g_empty(gs));
+            }
+          }
+          __syncwarp();
+          if (!p.resident && ++ws == p.n_w) {
+            ws = 0;
+            wph ^= 1u;
+          }
+        }
+        if (++acs == 2) {
+          acs = 0;
+          acph ^= 1u;
+        }
+      }
+      if (++gs == p.n_g) {
+        gs = 0;
+        gph ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMma) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// weights W[(k*Cout + co)][ci] fp32 -> images [(cc*nck + kc)][rows n = k*64 + (ci - cc*64)][64 = co - kc*64] bf16 SWIZZLE_128B
+__global__ void gcn_pack_bwd_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int K, int Cin, int Cout) {
+  const int NCC = Cin / 64, nck = Cout / 64, NP = K * 64;
+  const int total = NCC * nck * NP * 8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int pc = idx & 7;
+    int r = idx >> 3;
+    const int n = r % NP;
+    r /= NP;
+    const int kc = r % nck;
+    const int cc = r / nck;
+    const int k = n >> 6, ci = cc * 64 + (n & 63);
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = w[(static_cast<size_t>(k) * Cout + kc * 64 + pc * 8 + i) * Cin + ci];
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(cc * nck + kc) * NP * 128 + sw128_off(n, pc)) = pack8_bf16(f);
+  }
+}
+
 // weights W[(k*Cout + co)][ci] fp32 -> images [(cc*K + k)][BN rows = co][64 = ci - cc*64] bf16 SWIZZLE_128B (zero padded)
 __global__ void gcn_pack_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int K, int Cin, int Cout, int BN, int NCC) {
   const int total = NCC * K * BN * 8;
@@ -1090,6 +1456,82 @@ int fmm_gcn_wgrad(const void* x, const void* dg, float* dw, const int* rowptr, c
     return FMM_ERR_SMEM;
   }
   FMM_CHECK_LAUNCH("gcn_wgrad");
+  return FMM_OK;
+}
+
+long long fmm_gcn_packed_bwd_bytes(int K, int Cin, int Cout) { return static_cast<long long>(Cin / 64) * (Cout / 64) * K * 64 * 128; }
+
+int fmm_gcn_pack_bwd(const float* w, void* out, int K, int Cin, int Cout, cudaStream_t stream) {
+  FMM_CHECK_ARG(w && out && K > 0 && Cin % 64 == 0 && Cout % 64 == 0, "gcn_pack_bwd: bad arguments");
+  const int total = (Cin / 64) * (Cout / 64) * K * 64 * 8;
+  gcn_pack_bwd_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, reinterpret_cast<uint8_t*>(out), K, Cin, Cout);
+  FMM_CHECK_LAUNCH("gcn_pack_bwd");
+  return FMM_OK;
+}
+
+int fmm_gcn_bwd(const void* dg, const void* x, const void* addend, void* dx, const void* wpk, const int* rowptr, const int* dst,
+                const int* kk, const float* coef, const int* eid, float* dcoef, int max_out_degree, long long rows, int V, int K,
+                int Cin, int Cout, unsigned* err, cudaStream_t stream) {
+  FMM_CHECK_ARG(dg && dx && wpk && rowptr && dst && kk && coef, "gcn_bwd: null pointer");
+  FMM_CHECK_ARG((dcoef == nullptr) || (x && eid), "gcn_bwd: dcoef needs x and eid");
+  FMM_CHECK_ARG(rows > 0 && rows < (1ll << 31) && V > 0 && V <= kGcnMaxV && K > 0 && K <= 3 && rows % V == 0, "gcn_bwd: bad shape (rows=%lld V=%d K=%d)", rows, V, K);
+  FMM_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cout <= 256 && Cin <= 512, "gcn_bwd: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
+  FMM_CHECK_ARG(max_out_degree >= 1 && max_out_degree <= kGcnBwdMaxD, "gcn_bwd: maximum out-degree %d (1..%d supported)", max_out_degree, kGcnBwdMaxD);
+  GcnBwdParams p;
+  p.x = x;
+  p.addend = addend;
+  p.dx = dx;
+  p.wpk = wpk;
+  p.rowptr = rowptr;
+  p.dst = dst;
+  p.kk = kk;
+  p.coef = coef;
+  p.eid = eid;
+  p.dcoef = dcoef;
+  p.R = rows;
+  p.V = V;
+  p.K = K;
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.D = max_out_degree < 4 ? 4 : max_out_degree;
+  p.NCC = Cin / 64;
+  p.nck = Cout / 64;
+  p.FPT = kGcnTileRows / V;
+  const long long frames = rows / V;
+  p.ntiles = static_cast<int>((frames + p.FPT - 1) / p.FPT);
+  p.err = err;
+  const size_t g_bytes = static_cast<size_t>(p.nck) * kGcnChunkBytes, w_bytes = static_cast<size_t>(K) * 64 * 128;
+  const size_t pst_bytes = (128 * (static_cast<size_t>(K) * 128 + 16) + 1023) & ~1023ull;
+  const size_t fixed = 2 * pst_bytes + 12 * static_cast<size_t>(V * p.D) + 16 + 512 + 1024;
+  const size_t budget = 227 * 1024;
+  const int nimg = p.NCC * p.nck;
+  p.n_g = 1;
+  size_t used = fixed + g_bytes;
+  FMM_CHECK_ARG(used + w_bytes <= budget, "gcn_bwd: tile does not fit shared memory");
+  if (used + nimg * w_bytes <= budget) {
+    p.resident = 1;
+    p.n_w = nimg;
+  } else {
+    p.resident = 0;
+    p.n_w = static_cast<int>((budget - used) / w_bytes);
+    if (p.n_w > 4) p.n_w = 4;
+  }
+  used += p.n_w * w_bytes;
+  if (used + g_bytes <= budget) {
+    p.n_g = 2;
+    used += g_bytes;
+  }
+  CUtensorMap tm_dg;
+  int st = make_tmap_2d(&tm_dg, dg, rows, Cout, kGcnTileRows, 64, true);
+  if (st != FMM_OK) return st;
+  cudaError_t e = cudaFuncSetAttribute(gcn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(used));
+  if (e != cudaSuccess) {
+    set_last_error("gcn_bwd: smem attribute (%zu bytes): %s", used, cudaGetErrorString(e));
+    return FMM_ERR_SMEM;
+  }
+  const int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
+  gcn_bwd_kernel<<<grid, kGcnBwdThreads, used, stream>>>(p, tm_dg);
+  FMM_CHECK_LAUNCH("gcn_bwd");
   return FMM_OK;
 }
 

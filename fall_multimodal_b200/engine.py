@@ -70,6 +70,9 @@ class TrunkEngine:
         self.overlap_wgrad = False  # measured: no gain, two persistent GEMM CTAs cannot share an SM
         self.fused_gcn = True        # bf16, C % 64 == 0: csrc/gcn.cu instead of agg_fwd + 1x1 tapconv + colstats
         self.fused_gcn_wgrad = True   # weight gradient re-derives the aggregated operand (no saved Xa)
+        self.fused_gcn_bwd = True     # dx / d(edge importance): GEMM + transposed aggregation in one kernel (no P tensor)
+        rp = self._csr_np["bwd_rowptr"]
+        self.max_out_deg = int(max(int(rp[i + 1]) - int(rp[i]) for i in range(self.V)))
         self._wstreams = {}
 
     def csr(self, device):
@@ -349,10 +352,13 @@ class TrunkEngine:
                 wgrad_async(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
             grads[pre + "gcn.conv.weight"] = dWg
             grads[pre + "gcn.conv.bias"] = (b["colsum"] @ Tbl).flatten()
-            pw_gT = ops.tapconv_pack(Wg, K * Cin, Cout, Cin, Cout, Cout * Cin, 1, 0, Cin, 0, [0], dt)
-            Pm = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
-            ops.tapconv(dG, pw_gT, Pm, shifts=[0], tj=T)
+            fused_bwd = self.fused_gcn_bwd and ops.gcn_bwd_supported(dt, Cin, Cout, V, K, self.max_out_deg)
             dcoef = arena.f32(self.E)
+            Pm = None
+            if not fused_bwd:
+                pw_gT = ops.tapconv_pack(Wg, K * Cin, Cout, Cin, Cout, Cout * Cin, 1, 0, Cin, 0, [0], dt)
+                Pm = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
+                ops.tapconv(dG, pw_gT, Pm, shifts=[0], tj=T)
             fused_dcoef = Cin % 8 == 0
             if not fused_dcoef:
                 ops.agg_dcoef(x, Pm, dcoef, csr["fwd_src"], csr["dst"], csr["kk"], K)
@@ -374,7 +380,11 @@ class TrunkEngine:
 
             dx = torch.empty_like(x)
             coef_b = b["coef_f"][csr["bwd_perm"]].contiguous()
-            if fused_dcoef:
+            if fused_bwd:
+                # P = dG.W^T stays on chip: GEMM + transposed aggregation + edge-coefficient gradient in one kernel (csrc/gcn.cu)
+                ops.gcn_bwd(dG, ops.gcn_pack_bwd(Wg.view(K * Cout, Cin), K, Cin, Cout), dx, csr["bwd_rowptr"], csr["dst_b"],
+                            csr["kk_b"], coef_b, K, self.max_out_deg, addend=addend, x=x, eid=csr["eid_b"], dcoef=dcoef)
+            elif fused_dcoef:
                 ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K, x=x,
                             eid=csr["eid_b"], dcoef=dcoef)
             else:

@@ -177,6 +177,40 @@ def gcn_wgrad(x, dg, dw, rowptr, src, coef, K, kdeg):
     return _timed("gcn_wgrad", 2.0 * rows * K * Cin * Cout, float(x.numel() + dg.numel()) * 2, run)
 
 
+def gcn_pack_bwd(w: torch.Tensor, K: int, cin: int, cout: int) -> torch.Tensor:
+    """W fp32 (K*Cout, Cin) -> operand images of `gcn_bwd` (P = dG . W_k^T for all K partitions of a 64-channel slab at once)."""
+    L.require_device(w)
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.numel() == K * cout * cin
+    lib = L.load()
+    out = torch.empty(lib.fmm_gcn_packed_bwd_bytes(K, cin, cout), dtype=torch.uint8, device=w.device)
+    L.check(lib.fmm_gcn_pack_bwd(L.ptr(w), L.ptr(out), K, cin, cout, L.stream()), "gcn_pack_bwd")
+    return out
+
+
+def gcn_bwd_supported(dtype, cin: int, cout: int, V: int, K: int, max_out_degree: int) -> bool:
+    return gcn_supported(dtype, cin, cout, V) and K <= 3 and max_out_degree <= 8
+
+
+def gcn_bwd(dg, wpk, dx, rowptr, dst, kk, coef, K, max_out_degree, addend=None, x=None, eid=None, dcoef=None):
+    """dx = addend + A^T-aggregate(dG . W^T) with the GEMM result kept on chip; with x/eid/dcoef also the edge-coefficient gradient."""
+    L.require_device(dg)
+    N, Tn, V, Cout = dg.shape
+    Cin = dx.shape[-1]
+    assert dg.is_contiguous() and dx.is_contiguous() and dg.dtype == dx.dtype == torch.bfloat16 and dx.shape[:3] == dg.shape[:3]
+    assert addend is None or (addend.shape == dx.shape and addend.is_contiguous() and addend.dtype == dx.dtype)
+    assert x is None or (x.shape == dx.shape and x.is_contiguous() and x.dtype == dx.dtype)
+    rows = N * Tn * V
+
+    def run():
+        L.check(L.load().fmm_gcn_bwd(L.ptr(dg), L.ptr(x), L.ptr(addend), L.ptr(dx), L.ptr(wpk), L.ptr(rowptr), L.ptr(dst), L.ptr(kk),
+                                     L.ptr(coef), L.ptr(eid), L.ptr(dcoef), int(max_out_degree), rows, V, K, Cin, Cout,
+                                     L.ptr(err_word(dg.device)), L.stream()), "gcn_bwd")
+        return dx
+
+    nb = dg.numel() + dx.numel() + (x.numel() if x is not None else 0) + (addend.numel() if addend is not None else 0)
+    return _timed("gcn_bwd", 2.0 * rows * K * Cin * Cout, float(nb) * 2, run)
+
+
 # ---------------------------------------------------------------------------------------------
 # memory-bound kernels (csrc/elementwise.cu) and per-channel/per-clip kernels (csrc/tiny.cu)
 # ---------------------------------------------------------------------------------------------

@@ -87,6 +87,18 @@ int fmm_gcn_fwd(const void* x, void* g, void* xa, const void* wpk, const float* 
 int fmm_gcn_wgrad(const void* x, const void* dg, float* dw, const int* rowptr, const int* src, const float* coef,
                   const int* kdeg, long long rows, int V, int K, int Cin, int Cout, int E, unsigned* err, cudaStream_t stream);
 
+/* Backward data of the fused graph convolution, bf16:
+ *   dx[(f,v)][ci] = addend[(f,v)][ci] + sum_{e in out(v)} coef[e] * P[(f, dst e)][kk e][ci],   P = dg . W_k^T  (never in HBM)
+ *   dcoef[eid[e]] += sum_{f,ci} x[(f,v)][ci] * P[(f, dst e)][kk e][ci]     (gradient of A*edge_importance, stgcan.py:222)
+ * GEMM on tcgen05 (N = K*64 per 64-channel slab), transposed adjacency aggregation in the epilogue. CSR over v (out-edges):
+ * rowptr[V+1], dst / kk / coef / eid [E] (device); max_out_degree = largest number of out-edges of a joint (host knowledge
+ * of the static graph, <= 8). addend, x/eid/dcoef nullable. `wpk` from fmm_gcn_pack_bwd. K <= 3, rows % V == 0. */
+long long fmm_gcn_packed_bwd_bytes(int K, int Cin, int Cout);
+int fmm_gcn_pack_bwd(const float* w, void* out, int K, int Cin, int Cout, cudaStream_t stream);
+int fmm_gcn_bwd(const void* dg, const void* x, const void* addend, void* dx, const void* wpk, const int* rowptr, const int* dst,
+                const int* kk, const float* coef, const int* eid, float* dcoef, int max_out_degree, long long rows, int V, int K,
+                int Cin, int Cout, unsigned* err, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * memory-bound kernels (one pass over an activation each)
  * ------------------------------------------------------------------------------------------- */

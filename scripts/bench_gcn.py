@@ -63,6 +63,19 @@ for blk, T, Cin, Cout in [(1, 64, 64, 64), (3, 64, 64, 128), (4, 32, 128, 128), 
     print(f"block {blk}: T={T:2d} {Cin:3d}->{Cout:3d}  fused {t_f:6.1f} us ({byt / t_f / 1e3:5.0f} GB/s = {byt / t_f / 1e3 / PEAK:.2f} of copy peak, "
           f"{fl / t_f / 1e6:5.0f} TF/s) | no stats {t_nostat:6.1f} | +xa {t_xa:6.1f} | round-1 path agg {t_agg:6.1f} + gemm {t_mm:6.1f} + "
           f"colstats {t_cs:5.1f} = {t_agg + t_mm + t_cs:6.1f} us")
+    if hasattr(ops, "gcn_bwd"):
+        dGb = torch.randn(N, T, V, Cout, device=dev).to(torch.bfloat16)
+        dxb = torch.empty(N, T, V, Cin, device=dev, dtype=torch.bfloat16)
+        add = torch.randn(N, T, V, Cin, device=dev).to(torch.bfloat16)
+        dco = torch.zeros(src.numel(), device=dev)
+        wpb = ops.gcn_pack_bwd(W, K, Cin, Cout)
+        maxdeg = int((rowptr_b[1:] - rowptr_b[:-1]).max())
+        t_b = timeit(lambda: ops.gcn_bwd(dGb, wpb, dxb, rowptr_b, dst_b, kk_b, coef_b, K, maxdeg, addend=add, x=x, eid=eid_b, dcoef=dco))
+        pwT = ops.tapconv_pack(W.view(K * Cout, Cin, 1, 1), K * Cin, Cout, Cin, Cout, Cout * Cin, 1, 0, Cin, 0, [0], torch.bfloat16)
+        t_p = timeit(lambda: ops.tapconv(dGb, pwT, Xa, shifts=[0], tj=T))
+        t_ab = timeit(lambda: ops.agg_bwd(Xa, add, dxb, rowptr_b, dst_b, kk_b, coef_b, K, x=x, eid=eid_b, dcoef=dco))
+        nbb = (dGb.numel() + 3 * dxb.numel()) * 2
+        print(f"         bwd-data fused {t_b:6.1f} us ({nbb / t_b / 1e3:5.0f} GB/s of dG+x+addend+dx) | round-1 path P gemm {t_p:6.1f} + agg_bwd {t_ab:6.1f} = {t_p + t_ab:6.1f} us")
     if hasattr(ops, "gcn_wgrad"):
         dG = torch.randn(N, T, V, Cout, device=dev).to(torch.bfloat16)
         dW = torch.zeros(K * Cout, Cin, device=dev)

@@ -135,3 +135,41 @@ def test_gcn_generic_partitions(strategy, layout):
     ref = torch.einsum("ntwkc,ntwo->koc", xa.double(), dG.double()).reshape(K * Cout, Cin)
     assert (dW.double() - ref).abs().max().item() / ref.abs().max().item() < 2e-3
     assert int(ops.err_word(dev).item()) == 0
+
+
+@gpu
+@pytest.mark.parametrize("layout,N,T,Cin,Cout", CASES)
+@pytest.mark.parametrize("with_addend", [False, True])
+def test_gcn_bwd_matches_torch(layout, N, T, Cin, Cout, with_addend):
+    """dx and d(edge coefficients) of the graph conv with P = dG.W^T kept on chip, against fp64 torch on the bf16 inputs."""
+    from fall_multimodal_b200 import ops
+    from fall_multimodal_b200.graph import adjacency_csr
+
+    dev = torch.device("cuda:0")
+    A, Ahat, K, V, rowptr, src, coef, x, W, bias, kdeg = _setup(layout, N, T, Cin, Cout, dev, seed=11)
+    csr = adjacency_csr(A.double().numpy())
+    t = lambda a, dt=torch.int32: torch.as_tensor(a).to(device=dev, dtype=dt)
+    perm = torch.as_tensor(csr["bwd_perm"]).long().to(dev)
+    rowptr_b, dst_b, kk_b, eid_b = t(csr["bwd_rowptr"]), t(csr["dst"])[perm].contiguous(), t(csr["kk"])[perm].contiguous(), perm.int().contiguous()
+    coef_b = coef[perm].contiguous()
+    maxdeg = int((torch.as_tensor(csr["bwd_rowptr"])[1:] - torch.as_tensor(csr["bwd_rowptr"])[:-1]).max())
+    g = torch.Generator().manual_seed(13)
+    dG = torch.randn(N, T, V, Cout, generator=g).to(dev, torch.bfloat16)
+    addend = torch.randn(N, T, V, Cin, generator=g).to(dev, torch.bfloat16) if with_addend else None
+    dx = torch.full((N, T, V, Cin), float("nan"), dtype=torch.bfloat16, device=dev)
+    dcoef = torch.zeros(src.numel(), dtype=torch.float32, device=dev)
+    ops.gcn_bwd(dG, ops.gcn_pack_bwd(W, K, Cin, Cout), dx, rowptr_b, dst_b, kk_b, coef_b, K, maxdeg, addend=addend, x=x, eid=eid_b,
+                dcoef=dcoef)
+    torch.cuda.synchronize()
+    assert int(ops.err_word(dev).item()) == 0
+    # reference: P rounded to bf16 (what the staging tile holds), then exact arithmetic
+    Wk = W.view(K, Cout, Cin).to(torch.bfloat16).double()
+    P = torch.einsum("ntwo,koc->ntwkc", dG.double(), Wk).to(torch.bfloat16).double()
+    dx_ref = torch.einsum("ntwkc,kvw->ntvc", P, Ahat.double()) + (addend.double() if with_addend else 0)
+    assert torch.isfinite(dx.float()).all()
+    e_dx = (dx.double() - dx_ref).abs().max().item() / dx_ref.abs().max().item()
+    assert e_dx < 6e-3, f"dx err {e_dx:.2e}"
+    dA_ref = torch.einsum("ntvc,ntwkc->kvw", x.double(), P)              # d loss / d (A*importance)[k,v,w]
+    dcoef_ref = dA_ref.flatten()[torch.as_tensor(csr["dense_idx"]).long().to(dev)]
+    e_dc = (dcoef.double() - dcoef_ref).abs().max().item() / dcoef_ref.abs().max().item()
+    assert e_dc < 2e-3, f"dcoef err {e_dc:.2e}"

@@ -54,7 +54,7 @@ def load() -> C.CDLL:
 
 
 # number of kernels each C entry point launches (default 1); used for the launch counter
-_KERNELS_PER_CALL = {"se_fwd": 3, "se_bwd": 5, "conv1d_k5_bwd": 2}
+_KERNELS_PER_CALL = {"se_fwd": 3, "se_bwd": 5, "conv1d_k5_bwd": 2, "head_ce_bwd": 2}
 launch_count = 0
 
 
@@ -100,6 +100,14 @@ _SIGNATURES = {
     "fmm_gcn_packed_bwd_bytes": [c_int, c_int, c_int],
     "fmm_gcn_pack_bwd": [_P, _P, c_int, c_int, c_int, _P],
     "fmm_gcn_bwd": [_P] * 11 + [c_int, c_ll, c_int, c_int, c_int, c_int, _P, _P],
+    "fmm_databn_stats": [_P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "fmm_databn_apply": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_databn_bwd": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_head_ce_fwd": [_P, _P],
+    "fmm_head_ce_bwd": [_P, _P],
+    "fmm_opt_chunk": [],
+    "fmm_rmsprop_step": [_P, _P, _P, c_int, _P, c_float, c_float, c_float, _P, c_float, _P, _P],
+    "fmm_grad_norm_sq": [_P, _P, _P, c_int, _P, _P],
     "fmm_agg_fwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_dcoef": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
@@ -170,6 +178,12 @@ CellBwdArgs = _struct("CellBwdArgs", [
     (c_void_p, "S carry dz dxc0 dxc1 dx"), (c_ll, "dxb dxv"), (c_void_p, "hprev"), (c_ll, "hb hv"),
     (c_void_p, "zr lg dpre_g dlin_g dH"), (c_ll, "db dv"), (c_void_p, "z1 hprev1"), (c_ll, "hb1 hv1"),
     (c_void_p, "hc1 lu1 dpre_u dlin_u"), (c_int, "mode dx_accum do_bwd1 B V Din H Cp")])
+
+
+# mirror of fmm_head_args (include/fmm_b200.h, csrc/head.cu)
+HeadArgs = _struct("HeadArgs", [
+    (c_void_p * 4, "feat dfeat"), (c_int * 4, "width"), (c_int, "nseg"), (c_void_p, "W bias target out prob prob2 loss gloss dz dW dbias"),
+    (c_int, "N C F pre_softmax"), (c_float, "smoothing")])
 
 
 def int_array(vals):

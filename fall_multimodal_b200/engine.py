@@ -99,26 +99,21 @@ class TrunkEngine:
         csr = self.csr(dev)
         A = P["A"]
         NR = ops.NREP
-        arena = _Arena(dev, 7 * 6 * NR * 256 + 4096, 8 * N * 256 + 4096)
+        arena = _Arena(dev, 7 * 6 * NR * 256 + 4096 + 2 * V * C, 8 * N * 256 + 4096)
         sv = {"blocks": [], "N": N, "dt": dt, "training": training}
 
-        # ---- data_bn (stgcan.py:213-218): per-(v,c) BatchNorm1d over (N,T); tiny, torch ----
-        g0 = P["data_bn.weight"].view(V, C)
-        be0 = P["data_bn.bias"].view(V, C)
-        xp = skel.float().permute(0, 2, 3, 1)  # (N,T,V,C) view
+        # ---- data_bn (stgcan.py:213-218): per-(v,c) BatchNorm1d over (N,T), csrc/databn.cu; the normalised clip is written
+        # once, already channels-last in the compute dtype ----
+        xin = skel.float().contiguous()
+        VC = V * C
+        st0 = arena.f64(2 * VC)
+        a0, b0, mean0, rstd0 = (torch.empty(VC, dtype=torch.float32, device=dev) for _ in range(4))
         if training:
-            var, mean = torch.var_mean(xp, dim=(0, 1), unbiased=False)
-            cnt = N * T
-            with torch.no_grad():
-                P["data_bn.running_mean"].mul_(1 - MOMENTUM).add_(mean.flatten(), alpha=MOMENTUM)
-                P["data_bn.running_var"].mul_(1 - MOMENTUM).add_(var.flatten() * (cnt / max(cnt - 1, 1)), alpha=MOMENTUM)
-        else:
-            mean = P["data_bn.running_mean"].view(V, C)
-            var = P["data_bn.running_var"].view(V, C)
-        rstd0 = (var + EPS).rsqrt()
-        a0 = g0 * rstd0
-        x = (xp * a0 + (be0 - mean * a0)).to(dt).contiguous()
-        sv["data_bn"] = (xp, mean, rstd0)
+            ops.databn_stats(xin, st0[:VC], st0[VC:])
+        ops.bn_finalize(st0[:VC], st0[VC:], N * T, P["data_bn.weight"], P["data_bn.bias"], P["data_bn.running_mean"],
+                        P["data_bn.running_var"], training, a0, b0, mean0, rstd0)
+        x = ops.databn_apply(xin, a0, b0, torch.empty(N, T, V, C, dtype=dt, device=dev))
+        sv["data_bn"] = (xin, mean0, rstd0)
 
         for i, (Cin, Cout, s, reskind) in enumerate(self.blocks):
             pre = f"{self.block_key}.{i}."
@@ -239,7 +234,7 @@ class TrunkEngine:
         NR = ops.NREP
         wsize = sum(9 * co * co + K * co * ci + (co * ci if r == "conv" else 0) + 4 * K * V * V
                     for ci, co, _, r in self.blocks)
-        arena = _Arena(dev, 7 * 4 * NR * 256 + 4096,
+        arena = _Arena(dev, 7 * 4 * NR * 256 + 4096 + 2 * V * self.in_channels,
                        40 * N * 256 + 7 * NR * V * 256 + 7 * 2 * 256 * 64 + 65536 + wsize + 64 * len(self.blocks))
         f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
         z32 = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)
@@ -402,9 +397,10 @@ class TrunkEngine:
             cur.wait_stream(ws)
             keep.clear()
         # ---- data_bn backward (input itself needs no gradient) ----
-        xp, mean0, rstd0 = sv["data_bn"]
-        dxf = dY.float()
-        xhat = (xp - mean0) * rstd0
-        grads["data_bn.weight"] = (dxf * xhat).sum((0, 1)).flatten()
-        grads["data_bn.bias"] = dxf.sum((0, 1)).flatten()
+        xin, mean0, rstd0 = sv["data_bn"]
+        VC = V * self.in_channels
+        dgb = arena.f64(2 * VC)
+        ops.databn_bwd(dY, xin, mean0, rstd0, dgb[:VC], dgb[VC:])
+        grads["data_bn.weight"] = dgb[:VC].float()
+        grads["data_bn.bias"] = dgb[VC:].float()
         return grads

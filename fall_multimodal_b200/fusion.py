@@ -39,13 +39,14 @@ class TwoStreamSTGCAN(nn.Module):
         self.stgcan_2 = STGCAN(2, graph_args, num_class=None)
         self.fc = nn.Linear(256 * 2, num_class)
         self.compute_dtype = None
+        self.pre_softmax = False         # True: return softmax(logits) like the notebook models
         self.concurrent_streams = False  # opt-in: run the independent branches on side streams
         self._streams = _Streams()
 
     def _branches(self, skel, sensor):
         return []
 
-    def forward(self, skel, sensor=None):
+    def _features(self, skel, sensor=None):
         dt = _compute_dtype(self)
         self.stgcan_1.compute_dtype = self.stgcan_2.compute_dtype = dt
         mot = skel[:, :2, 1:] - skel[:, :2, :-1]          # combination.py:13,39
@@ -66,10 +67,26 @@ class TwoStreamSTGCAN(nn.Module):
                 o.record_stream(cur)
         else:
             outs = [job() for job in jobs]
+        return outs, dt
+
+    def forward(self, skel, sensor=None):
+        outs, dt = self._features(skel, sensor)
         x = torch.cat([o.float() for o in outs], dim=-1)
         with torch.autocast("cuda", enabled=False):
             out = torch.addmm(self.fc.bias, x, self.fc.weight.t())
+        if self.pre_softmax:                                   # notebook models: F.softmax(out, dim=-1)
+            out = torch.softmax(out, dim=-1)
         return out.to(dt) if dt == torch.bfloat16 else out
+
+    def forward_loss(self, skel, sensor, target, label_smoothing: float = 0.0):
+        """``(pred, loss)`` of ``CrossEntropyLoss(label_smoothing)(self(skel, sensor), target)`` with the late-fusion Linear and
+        the loss in one fused kernel pair (csrc/head.cu; combination.py:44-46 + F2/main.py:113)."""
+        from .head import linear_cross_entropy
+
+        outs, dt = self._features(skel, sensor)
+        pred, loss = linear_cross_entropy([o.float() for o in outs], self.fc.weight, self.fc.bias, target,
+                                          pre_softmax=self.pre_softmax, label_smoothing=label_smoothing)
+        return (pred.to(dt) if dt == torch.bfloat16 else pred), loss
 
 
 class TwoStreamSTGCAN_CNN1D(TwoStreamSTGCAN):

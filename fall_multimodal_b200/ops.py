@@ -119,6 +119,29 @@ def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, shifts, istrid
 
 
 # ---------------------------------------------------------------------------------------------
+# data_bn (csrc/databn.cu): clip (N,C,T,V) fp32 -> normalised channels-last activation (N,T,V,C)
+# ---------------------------------------------------------------------------------------------
+def databn_stats(x, s, q):
+    N, C, Tn, V = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and s.dtype == q.dtype == torch.float64
+    L.check(L.load().fmm_databn_stats(L.ptr(x), L.ptr(s), L.ptr(q), N, C, Tn, V, L.stream()), "databn_stats")
+
+
+def databn_apply(x, a, b, y):
+    N, C, Tn, V = x.shape
+    assert y.shape == (N, Tn, V, C) and y.is_contiguous() and x.is_contiguous()
+    L.check(L.load().fmm_databn_apply(L.ptr(x), L.ptr(a), L.ptr(b), L.ptr(y), N, C, Tn, V, L.dt_of(y.dtype), L.stream()), "databn_apply")
+    return y
+
+
+def databn_bwd(dy, x, mean, rstd, dgamma, dbeta):
+    N, C, Tn, V = x.shape
+    assert dy.shape == (N, Tn, V, C) and dy.is_contiguous() and dgamma.dtype == dbeta.dtype == torch.float64
+    L.check(L.load().fmm_databn_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(dgamma), L.ptr(dbeta), N, C, Tn, V,
+                                    L.dt_of(dy.dtype), L.stream()), "databn_bwd")
+
+
+# ---------------------------------------------------------------------------------------------
 # fused spatial graph convolution (csrc/gcn.cu): aggregation in the GEMM prologue, BN statistics in the epilogue
 # ---------------------------------------------------------------------------------------------
 def gcn_supported(x_dtype, cin: int, cout: int, V: int) -> bool:

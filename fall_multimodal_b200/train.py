@@ -37,13 +37,18 @@ class TrainStep:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, loss_fn, example_inputs: Sequence,
                  example_target: torch.Tensor, autocast_dtype: torch.dtype | None = torch.bfloat16,
                  bucket_groups: Sequence | None = None, use_graph: bool = True, warmup: int = 2,
-                 max_norm: float | None = None):
+                 max_norm: float | None = None, fused_loss: bool = False, label_smoothing: float = 0.0):
         dev = example_target.device
         if dev.type != "cuda":
             raise RuntimeError("TrainStep needs CUDA tensors (the product path has no CPU fallback)")
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
         self.autocast_dtype = autocast_dtype
         self.max_norm = max_norm           # MF3/main.py:108 clip_grad_norm_(model.parameters(), max_norm) before the step
+        # fused_loss: late-fusion Linear + CrossEntropy(label_smoothing) in one kernel pair (model.forward_loss, csrc/head.cu)
+        # instead of model(...) followed by loss_fn
+        self.fused_loss, self.label_smoothing = bool(fused_loss), float(label_smoothing)
+        if self.fused_loss and not hasattr(model, "forward_loss"):
+            raise ValueError("fused_loss=True needs a model with forward_loss(skel, sensor, target) (the fusion models)")
         if use_graph:
             for g in optimizer.param_groups:
                 if not g.get("capturable", False) and not getattr(optimizer, "graph_safe", False):
@@ -109,11 +114,15 @@ class TrainStep:
     def _step(self):
         self.buckets.zero_grad()
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
-            pred = self.model(*self.inputs)
-        loss = self.loss_fn(pred.float(), self.target)
+            if self.fused_loss:
+                pred, loss = self.model.forward_loss(*self.inputs, self.target, label_smoothing=self.label_smoothing)
+            else:
+                pred = self.model(*self.inputs)
+        if not self.fused_loss:
+            loss = self.loss_fn(pred.float(), self.target)
         loss.backward()
         self.buckets.wait()
-        if self.max_norm is not None:
+        if self.max_norm is not None and getattr(self.optimizer, "max_norm", None) is None:   # FusedRMSprop clips inside its step
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.max_norm, foreach=True)
         self.optimizer.step()
         with torch.no_grad():

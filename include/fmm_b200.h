@@ -99,6 +99,55 @@ int fmm_gcn_bwd(const void* dg, const void* x, const void* addend, void* dx, con
                 const int* kk, const float* coef, const int* eid, float* dcoef, int max_out_degree, long long rows, int V, int K,
                 int Cin, int Cout, unsigned* err, cudaStream_t stream);
 
+/* data_bn (stgcan.py:212-218): BatchNorm1d(V*C) over (N,T) of the clip x (N,C,T,V) fp32, channel index v*C + c, written
+ * once in the channels-last (N,T,V,C) activation layout. stats -> fmm_bn_finalize(count = N*T, C = V*C) -> apply; bwd gives
+ * the affine parameter gradients (fp64 accumulators, zeroed by the caller; the clip itself needs no gradient). */
+int fmm_databn_stats(const float* x, double* sum, double* sq, int N, int C, int T, int V, cudaStream_t stream);
+int fmm_databn_apply(const float* x, const float* a, const float* b, void* y, int N, int C, int T, int V, int dtype,
+                     cudaStream_t stream);
+int fmm_databn_bwd(const void* dy, const float* x, const float* mean, const float* rstd, double* dgamma, double* dbeta, int N,
+                   int C, int T, int V, int dtype, cudaStream_t stream);
+
+/* Fused late-fusion head + cross-entropy (combination.py:37-46: cat -> Linear; F2/main.py:113,280: CrossEntropyLoss with
+ * label smoothing on PROBABILITY targets, mean over the batch; pre_softmax: the notebooks' softmax-before-the-loss).
+ * Up to 4 feature segments (no concat copy), at most 32 classes, everything fp32. fwd: out = logits (or softmax(logits)),
+ * prob / prob2 saved, loss accumulated into a zeroed scalar. bwd: dfeat[s] (nullable per segment), dW [C][F], dbias [C],
+ * dz = [N][C] workspace, gloss = device scalar d L / d loss. */
+typedef struct fmm_head_args {
+  const float* feat[4];
+  float* dfeat[4];
+  int width[4];
+  int nseg;
+  const float* W;
+  const float* bias;
+  const float* target;
+  float* out;
+  float* prob;
+  float* prob2;
+  float* loss;
+  const float* gloss;
+  float* dz;
+  float* dW;
+  float* dbias;
+  int N, C, F;
+  int pre_softmax;
+  float smoothing;
+} fmm_head_args;
+int fmm_head_ce_fwd(const fmm_head_args* a, cudaStream_t stream);
+int fmm_head_ce_bwd(const fmm_head_args* a, cudaStream_t stream);
+
+/* Multi-tensor RMSprop (F2/optimizer.py:20-21; MF3/main.py:103-113 for unscale + clip_grad_norm_): ONE launch for all
+ * parameter tensors. `tensors`: device array of {float* param; const float* grad; float* square_avg; long long numel};
+ * chunk tables: fmm_opt_chunk() elements per chunk. lr / norm_sq / inv_scale are DEVICE scalars (graph-replay safe);
+ * norm_sq (nullable) = sum of squared gradients from fmm_grad_norm_sq (zero it first): enables clipping to max_norm (> 0)
+ * and skips the step when it is not finite. */
+int fmm_opt_chunk(void);
+int fmm_rmsprop_step(const void* tensors, const int* chunk_tensor, const long long* chunk_off, int nchunks, const float* lr,
+                     float alpha, float eps, float weight_decay, const float* norm_sq, float max_norm, const float* inv_scale,
+                     cudaStream_t stream);
+int fmm_grad_norm_sq(const void* tensors, const int* chunk_tensor, const long long* chunk_off, int nchunks, float* norm_sq,
+                     cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * memory-bound kernels (one pass over an activation each)
  * ------------------------------------------------------------------------------------------- */

@@ -377,7 +377,13 @@ def run_ours(args):
     if world > 1:  # identical replicas
         for p in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(p.data, 0)
-    opt = torch.optim.RMSprop(model.parameters(), lr=1e-3, capturable=bool(args.graph))
+    # the product step: fused late-fusion head + cross-entropy (model.forward_loss) and the multi-tensor RMSprop of this package;
+    # --stock-step 1 runs torch's CrossEntropyLoss + torch.optim.RMSprop(capturable) around the same model instead
+    from fall_multimodal_b200.optim import FusedRMSprop
+    if args.stock_step:
+        opt = torch.optim.RMSprop(model.parameters(), lr=1e-3, capturable=bool(args.graph))
+    else:
+        opt = FusedRMSprop(model.parameters(), lr=1e-3)
     buckets = GradBuckets([list(model.fc.parameters()) + list(model.cnn.parameters()),
                            list(model.stgcan_2.parameters()), list(model.stgcan_1.parameters())])
     loss_fn = torch.nn.CrossEntropyLoss()
@@ -388,8 +394,12 @@ def run_ours(args):
     def step(sk, se, tg):
         buckets.zero_grad()
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = model(sk, se)
-        loss = loss_fn(out.float(), tg)
+            if args.stock_step:
+                out = model(sk, se)
+            else:
+                out, loss = model.forward_loss(sk, se, tg)
+        if args.stock_step:
+            loss = loss_fn(out.float(), tg)
         loss.backward()
         buckets.wait()
         opt.step()
@@ -578,7 +588,9 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "clips_per_gpu": B, "global_batch": world * B, "T": T, "V": V,
                            "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) >> 126 MB L2",
-                           "bn": "per-shard statistics", "streams": bool(args.streams), "cuda_graph": bool(args.graph)},
+                           "bn": "per-shard statistics", "streams": bool(args.streams), "cuda_graph": bool(args.graph),
+                           "step": "torch CrossEntropyLoss + torch.optim.RMSprop" if args.stock_step else
+                                   "fused head + cross-entropy kernel, multi-tensor RMSprop kernel"},
                 "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
@@ -853,6 +865,7 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="1: run the independent branches (two trunks, sensor) on side streams")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the whole train step as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stock-step", type=int, default=0, help="1: torch CrossEntropyLoss + torch.optim.RMSprop instead of the fused head/loss and optimizer kernels")
     ap.add_argument("--no-torch-eager", action="store_true", help="skip the stock PyTorch/cuDNN eager leg on the same GPU (N=1)")
     ap.add_argument("--torch-eager-gpu", action="store_true", help="(kept for compatibility: the eager leg is on by default)")
     ap.add_argument("--no-config3", action="store_true", help="skip the 3-stream / global-batch-1024 strong-scaling sub-benchmark")

@@ -108,6 +108,8 @@ _SIGNATURES = {
     "fmm_opt_chunk": [],
     "fmm_rmsprop_step": [_P, _P, _P, c_int, _P, c_float, c_float, c_float, _P, c_float, _P, _P],
     "fmm_grad_norm_sq": [_P, _P, _P, c_int, _P, _P],
+    "fmm_gcn_prep_fwd": [_P] * 9 + [c_int, c_int, c_int, c_int, _P],
+    "fmm_gcn_prep_bwd": [_P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_fwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_agg_dcoef": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],

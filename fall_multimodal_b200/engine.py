@@ -118,12 +118,10 @@ class TrunkEngine:
         for i, (Cin, Cout, s, reskind) in enumerate(self.blocks):
             pre = f"{self.block_key}.{i}."
             b = {"T": T}
-            imp = P[f"edge_importance.{i}"]
-            Ahat = A * imp
-            coef_f = Ahat.flatten()[csr["dense_idx"]].contiguous()
-            colsum = Ahat.sum(1)                                   # (K, V): sum over source joints
-            bg = P[pre + "gcn.conv.bias"].view(K, Cout)
-            bias_eff = (colsum.t() @ bg).contiguous()              # (V, Cout)
+            # A*importance as edge coefficients (forward and out-edge order), its column sums and the conv bias folded through
+            # the aggregation: one launch (csrc/gcnprep.cu)
+            coef_f, coef_b, colsum, bias_eff = ops.gcn_prep_fwd(A, P[f"edge_importance.{i}"], P[pre + "gcn.conv.bias"],
+                                                                csr["dense_idx"], csr["bwd_perm"], Cout)
             Wg = P[pre + "gcn.conv.weight"]
             G = torch.empty(N, T, V, Cout, dtype=dt, device=dev)
             a1, b1, mean1, rstd1 = (torch.empty(Cout, dtype=torch.float32, device=dev) for _ in range(4))
@@ -208,7 +206,7 @@ class TrunkEngine:
             if need_grad:
                 b.update(x=x, Xa=Xa, G=G, H=Hm, U=U, R=R, Y=Y, a1=a1, b1=b1, mean1=mean1, rstd1=rstd1, a2=a2, b2=b2,
                          mean2=mean2, rstd2=rstd2, pool=pool, p=p_, h=h_, s=s_, ah=ah, bh=bh, hmean=hmean,
-                         hrstd=hrstd, ar=ar, meanr=meanr, rstdr=rstdr, coef_f=coef_f, colsum=colsum, To=To)
+                         hrstd=hrstd, ar=ar, meanr=meanr, rstdr=rstdr, coef_f=coef_f, coef_b=coef_b, colsum=colsum, To=To)
                 sv["blocks"].append(b)
             x, T = Y, To
 
@@ -336,7 +334,6 @@ class TrunkEngine:
             dG = torch.empty_like(G)
             TblR = arena.f32(NR, V, Cout)
             ops.bn1_bwd_apply(dH, G, b["a1"], b["b1"], c1, c2, c3, dG, TblR)
-            Tbl = TblR.sum(0)
 
             # ---- graph conv: wgrad, bias, dgrad through the weights, edge importance ----
             Wg = P[pre + "gcn.conv.weight"]
@@ -346,7 +343,6 @@ class TrunkEngine:
             else:
                 wgrad_async(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
             grads[pre + "gcn.conv.weight"] = dWg
-            grads[pre + "gcn.conv.bias"] = (b["colsum"] @ Tbl).flatten()
             fused_bwd = self.fused_gcn_bwd and ops.gcn_bwd_supported(dt, Cin, Cout, V, K, self.max_out_deg)
             dcoef = arena.f32(self.E)
             Pm = None
@@ -374,7 +370,7 @@ class TrunkEngine:
                 ops.tapconv(dR, pw_rT, addend, shifts=[0], tj=To, ostride=s, ooff=0)
 
             dx = torch.empty_like(x)
-            coef_b = b["coef_f"][csr["bwd_perm"]].contiguous()
+            coef_b = b["coef_b"]
             if fused_bwd:
                 # P = dG.W^T stays on chip: GEMM + transposed aggregation + edge-coefficient gradient in one kernel (csrc/gcn.cu)
                 ops.gcn_bwd(dG, ops.gcn_pack_bwd(Wg.view(K * Cout, Cin), K, Cin, Cout), dx, csr["bwd_rowptr"], csr["dst_b"],
@@ -384,10 +380,11 @@ class TrunkEngine:
                             eid=csr["eid_b"], dcoef=dcoef)
             else:
                 ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K)
-            bg = P[pre + "gcn.conv.bias"].view(K, Cout)
-            dA = arena.f32(K * V * V)
-            dA[csr["dense_idx"]] = dcoef
-            grads[f"edge_importance.{i}"] = A * (dA.view(K, V, V) + (bg @ Tbl.t())[:, None, :])
+            # d(conv bias) and d(edge importance) from the per-joint sums of dG and the per-edge sums: one launch
+            dbg, dimp = arena.f32(K * Cout), arena.f32(K, V, V)
+            ops.gcn_prep_bwd(A, P[pre + "gcn.conv.bias"], b["colsum"], TblR, dcoef, csr["dense_idx"], dbg, dimp)
+            grads[pre + "gcn.conv.bias"] = dbg
+            grads[f"edge_importance.{i}"] = dimp
             if self.debug is not None:
                 self.debug[i] = dict(dY=dY, dU=dU, dH=dH, dG=dG, P=Pm, dx=dx, S1=S1, S2=S2, dp=dp, dR=dR, c1=c1, c2=c2,
                                      c3=c3, T1=T1, T2=T2, saved=b)

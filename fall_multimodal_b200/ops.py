@@ -119,6 +119,28 @@ def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, shifts, istrid
 
 
 # ---------------------------------------------------------------------------------------------
+# parameter-side algebra of the graph conv (csrc/gcnprep.cu)
+# ---------------------------------------------------------------------------------------------
+def gcn_prep_fwd(A, imp, bg, dense_idx, bwd_perm, Cout):
+    """-> (coef_f [E], coef_b [E], colsum [K,V], bias_eff [V,Cout]) of A*imp; one launch."""
+    K, V, _ = A.shape
+    E = dense_idx.numel()
+    dev = A.device
+    coef_f, coef_b = torch.empty(E, device=dev), torch.empty(E, device=dev)
+    colsum, bias_eff = torch.empty(K, V, device=dev), torch.empty(V, Cout, device=dev)
+    L.check(L.load().fmm_gcn_prep_fwd(L.ptr(A), L.ptr(imp), L.ptr(bg), L.ptr(dense_idx), L.ptr(bwd_perm), L.ptr(coef_f), L.ptr(coef_b),
+                                      L.ptr(colsum), L.ptr(bias_eff), K, V, Cout, E, L.stream()), "gcn_prep_fwd")
+    return coef_f, coef_b, colsum, bias_eff
+
+
+def gcn_prep_bwd(A, bg, colsum, TblR, dcoef, dense_idx, dbg, dimp):
+    K, V, _ = A.shape
+    Cout = bg.numel() // K
+    L.check(L.load().fmm_gcn_prep_bwd(L.ptr(A), L.ptr(bg), L.ptr(colsum), L.ptr(TblR), TblR.numel() // (V * Cout), L.ptr(dcoef),
+                                      L.ptr(dense_idx), L.ptr(dbg), L.ptr(dimp), K, V, Cout, dense_idx.numel(), L.stream()), "gcn_prep_bwd")
+
+
+# ---------------------------------------------------------------------------------------------
 # data_bn (csrc/databn.cu): clip (N,C,T,V) fp32 -> normalised channels-last activation (N,T,V,C)
 # ---------------------------------------------------------------------------------------------
 def databn_stats(x, s, q):

@@ -148,6 +148,15 @@ int fmm_rmsprop_step(const void* tensors, const int* chunk_tensor, const long lo
 int fmm_grad_norm_sq(const void* tensors, const int* chunk_tensor, const long long* chunk_off, int nchunks, float* norm_sq,
                      cudaStream_t stream);
 
+/* Parameter-side algebra of the graph conv (stgcan.py:222 `A * importance`, bias folded through the aggregation) and its
+ * backward: edge coefficients in forward / out-edge CSR order, column sums, per-joint bias table; gradients of the conv bias
+ * and the edge importance from the kernels' per-edge / per-joint sums. One launch each. dense_idx / bwd_perm: int64 [E]. */
+int fmm_gcn_prep_fwd(const float* A, const float* imp, const float* bg, const long long* dense_idx, const long long* bwd_perm,
+                     float* coef_f, float* coef_b, float* colsum, float* bias_eff, int K, int V, int Cout, int E,
+                     cudaStream_t stream);
+int fmm_gcn_prep_bwd(const float* A, const float* bg, const float* colsum, const float* TblR, int nrep, const float* dcoef,
+                     const long long* dense_idx, float* dbg, float* dimp, int K, int V, int Cout, int E, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * memory-bound kernels (one pass over an activation each)
  * ------------------------------------------------------------------------------------------- */

@@ -59,7 +59,9 @@ constexpr int kTapProducers = 256;
 
 // kEpi = 4 | 8 epilogue warps: wide output tiles (BN >= 128) are epilogue-bound and take two warps per
 // TMEM lane quadrant; narrow tiles run with 4 (fewer warps competing with the producers for issue slots).
-template <typename T, int kEpi>
+// kTaps only names the launch class (multi-tap temporal conv: tensor bound; 1x1 channel mix: HBM bound) so that profiler
+// output can be split per class; the code is identical.
+template <typename T, int kEpi, bool kTaps>
 __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   constexpr int kLoaderWarp = 8 + kEpi, kMmaWarp = 9 + kEpi;
   constexpr int kParts = ActTraits<T>::kParts;
@@ -725,21 +727,26 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   p.nbstages = nb;
   const size_t smem = nb * bstage_bytes * p.tps + ns * slot_bytes + 1024 + 2048 + bias_bytes;
   const bool wide = p.BN >= 128;
-#define FMM_LAUNCH_TAPCONV(TT, EPI)                                                                              \
+#define FMM_LAUNCH_TAPCONV2(TT, EPI, TAPS)                                                                       \
   do {                                                                                                           \
-    cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<TT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+    cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<TT, EPI, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem);                                                             \
     if (e != cudaSuccess) {                                                                                      \
       set_last_error("tapconv: smem attribute: %s", cudaGetErrorString(e));                                      \
       return FMM_ERR_SMEM;                                                                                       \
     }                                                                                                            \
-    tapconv_kernel<TT, EPI><<<grid, (10 + EPI) * 32, smem, stream>>>(p);                                         \
+    tapconv_kernel<TT, EPI, TAPS><<<grid, (10 + EPI) * 32, smem, stream>>>(p);                                   \
+  } while (0)
+#define FMM_LAUNCH_TAPCONV(TT, EPI)                                                                              \
+  do {                                                                                                           \
+    if (ntaps > 1) FMM_LAUNCH_TAPCONV2(TT, EPI, true); else FMM_LAUNCH_TAPCONV2(TT, EPI, false);                 \
   } while (0)
   if (dtype == FMM_DT_BF16) {
     if (wide) FMM_LAUNCH_TAPCONV(__nv_bfloat16, 8); else FMM_LAUNCH_TAPCONV(__nv_bfloat16, 4);
   } else {
     if (wide) FMM_LAUNCH_TAPCONV(float, 8); else FMM_LAUNCH_TAPCONV(float, 4);
   }
+#undef FMM_LAUNCH_TAPCONV2
 #undef FMM_LAUNCH_TAPCONV
   FMM_CHECK_LAUNCH("tapconv");
   return FMM_OK;

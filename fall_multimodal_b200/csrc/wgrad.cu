@@ -51,7 +51,8 @@ struct WgradParams {
 constexpr int kWgThreads = 288;  // warps 0-7 producers (0-3 also run the epilogue), 8 = MMA issuer
 constexpr int kWgProducers = 256;
 
-template <typename T>
+// kTaps only names the launch class for profilers (multi-tap: tensor bound; 1x1: HBM bound); the code is identical.
+template <typename T, bool kTaps>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   constexpr int kParts = ActTraits<T>::kParts;
   extern __shared__ uint8_t smem_raw[];
@@ -423,21 +424,21 @@ int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, c
   const size_t smem = ns * stage + 1024 + 256;
   const int grid = p.items * p.slices;
   cudaError_t e;
+#define FMM_LAUNCH_WGRAD(TT, TAPS)                                                                               \
+  do {                                                                                                           \
+    e = cudaFuncSetAttribute(wgrad_kernel<TT, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) {                                                                                      \
+      set_last_error("wgrad: smem attribute: %s", cudaGetErrorString(e));                                        \
+      return FMM_ERR_SMEM;                                                                                       \
+    }                                                                                                            \
+    wgrad_kernel<TT, TAPS><<<grid, kWgThreads, smem, stream>>>(p);                                               \
+  } while (0)
   if (dtype == FMM_DT_BF16) {
-    e = cudaFuncSetAttribute(wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_last_error("wgrad: smem attribute: %s", cudaGetErrorString(e));
-      return FMM_ERR_SMEM;
-    }
-    wgrad_kernel<__nv_bfloat16><<<grid, kWgThreads, smem, stream>>>(p);
+    if (ntaps > 1) FMM_LAUNCH_WGRAD(__nv_bfloat16, true); else FMM_LAUNCH_WGRAD(__nv_bfloat16, false);
   } else {
-    e = cudaFuncSetAttribute(wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_last_error("wgrad: smem attribute: %s", cudaGetErrorString(e));
-      return FMM_ERR_SMEM;
-    }
-    wgrad_kernel<float><<<grid, kWgThreads, smem, stream>>>(p);
+    if (ntaps > 1) FMM_LAUNCH_WGRAD(float, true); else FMM_LAUNCH_WGRAD(float, false);
   }
+#undef FMM_LAUNCH_WGRAD
   FMM_CHECK_LAUNCH("wgrad");
   return FMM_OK;
 }

@@ -1,7 +1,7 @@
 """Summarise an ncu `--metrics gpu__time_duration.sum --csv` launch list by kernel."""
 import collections, csv, sys
 path = sys.argv[1]
-lines = [l for l in open(path) if l.startswith('"')]
+lines = [l for l in open(path) if l.startswith('"') or l.startswith('ID,') or l[:1].isdigit()]
 agg = collections.defaultdict(lambda: [0, 0.0]); total = 0
 for row in csv.DictReader(lines):
     v = float(row['Metric Value'].replace(',', ''))

@@ -223,8 +223,6 @@ def bench_config3(args, dev, world, rank, barrier):
     B = GLOBAL_BATCH_3 // world
     torch.manual_seed(7)
     model = fmm.ThreeStreamSTGCAN(3, {"layout": LAYOUT, "strategy": "spatial"}, NUM_CLASS).to(dev).train()
-    if args.sync_bn and world > 1:
-        model.set_sync_bn(True)
     if world > 1:
         for p in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(p.data, 0)
@@ -269,7 +267,7 @@ def bench_config3(args, dev, world, rank, barrier):
     return {"workload": "3-stream GSTCAN (joints 3x64x33 + motion 2x63x33 + bones 3x64x33) + Linear(768, 11), train step "
                         "fwd+bwd+RMSprop, bf16", "metric": "train clips/sec fwd+bwd (3-stream GSTCAN)", "value": GLOBAL_BATCH_3 * steps / (ms / 1e3),
             "unit": "clips/s", "global_batch": GLOBAL_BATCH_3, "clips_per_gpu": B, "n_gpus": world, "scaling": "strong", "steps": steps,
-            "ms_per_step": ms / steps, "bn": "synchronised over the ranks" if (args.sync_bn and world > 1) else "per-shard statistics",
+            "ms_per_step": ms / steps, "bn": "per-shard statistics (SURVEY 8(e) option b)",
             "gradient_bytes_per_step": sum(p.numel() for p in model.parameters()) * 4, "loss": loss,
             "note": "efficiency vs N=1 = value(N) / (N * value(1)) over the driver's N = 1, 2, 4, 8 runs of this same line"}
 
@@ -870,7 +868,6 @@ def main():
     ap.add_argument("--torch-eager-gpu", action="store_true", help="(kept for compatibility: the eager leg is on by default)")
     ap.add_argument("--no-config3", action="store_true", help="skip the 3-stream / global-batch-1024 strong-scaling sub-benchmark")
     ap.add_argument("--no-extra", action="store_true", help="skip the TARGCN (config 4) and sensor (config 5) sub-benchmarks (N=1)")
-    ap.add_argument("--sync-bn", type=int, default=0, help="config3: 1 = BatchNorm statistics all-reduced over the ranks")
     ap.add_argument("--workload", default="gstcan", choices=["gstcan", "targcn"],
                     help="gstcan: BASELINE configs[1] (the headline, default); targcn: configs[3] (TARGCN T=300 V=25, 512 clips)")
     args = ap.parse_args()

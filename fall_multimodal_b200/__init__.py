@@ -5,6 +5,11 @@ from .stgcan import STGCAN, Channel_Attention, GraphConvolution, st_gcan  # noqa
 from .sensor import CNN1D, BiLSTM, ChannelAttention, CNN_BiLSTM  # noqa: F401
 from .tragcn import TARGCN  # noqa: F401
 from .fusion import ThreeStreamSTGCAN, TwoStreamSTGCAN, TwoStreamSTGCAN_CNN1D, TwoStreamSTGCAN_BiLSTM  # noqa: F401
+from .notebook import StreamSpatialTemporalGraph, TwoStreamSpatialTemporalGraph  # noqa: F401
+from .build_model import build_model  # noqa: F401
+from .head import linear_cross_entropy  # noqa: F401
+from .optim import FusedRMSprop  # noqa: F401
 
 __all__ = ["Graph", "register_layout", "STGCAN", "st_gcan", "GraphConvolution", "Channel_Attention", "CNN1D",
-           "TwoStreamSTGCAN", "TwoStreamSTGCAN_CNN1D", "TwoStreamSTGCAN_BiLSTM", "ThreeStreamSTGCAN", "BiLSTM", "ChannelAttention", "CNN_BiLSTM", "TARGCN"]
+           "TwoStreamSTGCAN", "TwoStreamSTGCAN_CNN1D", "TwoStreamSTGCAN_BiLSTM", "ThreeStreamSTGCAN", "BiLSTM", "ChannelAttention", "CNN_BiLSTM", "TARGCN",
+           "StreamSpatialTemporalGraph", "TwoStreamSpatialTemporalGraph", "build_model", "linear_cross_entropy", "FusedRMSprop"]

@@ -263,8 +263,33 @@ def main_musa():
     print("musa loss", res["loss"])
 
 
+def main_notebook():
+    """The notebook fusion model (GSTCAN_HAR_conv_10kfold.ipynb#cell1:L362-416 + #cell2): tuple input, BiLSTM sensor logits in
+    the concat, softmax output fed to CrossEntropyLoss. Classes exec()ed from the notebook cells, unmodified."""
+    import json
+    import warnings
+    torch.set_num_threads(4)
+    nb = json.load(open(os.path.join(ref_import.REF, "GSTCAN_HAR_conv_10kfold.ipynb")))
+    ns = {"device": torch.device("cpu")}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exec("".join(nb["cells"][2]["source"]), ns)
+        exec("".join(nb["cells"][1]["source"]), ns)
+        mod = ns["TwoStreamSpatialTemporalGraph"]({"layout": "coco_cut", "strategy": "spatial"}, 11)
+    shapes = fill_module(mod, seed=8)
+    c = dict(layout="coco_cut", strategy="spatial", num_class=11, N=6, T=12, L=30, I=15)
+    skel, sensor, target, _ = O.synthetic_batch(c["N"], c["T"], 14, 11, sensor_len=30, sensor_ch=15, seed=14)
+    mot = skel[:, :2, 1:] - skel[:, :2, :-1]
+    res = run_train_step(mod, lambda: mod((skel, mot, sensor)), target)
+    torch.save({"config": c, "shapes": shapes, "fill_seed": 8, "batch_seed": 14, "n_params": sum(p.numel() for p in mod.parameters()),
+                **res}, os.path.join(OUT, "nb_two_stream.pt"))
+    print("notebook two-stream loss", res["loss"], "params", sum(p.numel() for p in mod.parameters()))
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["tragcn"]:
+    if sys.argv[1:] == ["notebook"]:
+        main_notebook()
+    elif sys.argv[1:] == ["tragcn"]:
         main_tragcn()
     elif sys.argv[1:] == ["musa"]:
         main_musa()
@@ -272,3 +297,4 @@ if __name__ == "__main__":
         main()
         main_tragcn()
         main_musa()
+        main_notebook()

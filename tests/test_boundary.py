@@ -1,0 +1,114 @@
+"""Drop-in boundary odds and ends: ``build_model``, the notebooks' class names / tuple forward / double softmax,
+and checkpoints written by the UNMODIFIED reference modules loading into the package's modules."""
+import io
+import os
+
+import pytest
+import torch
+
+from oracle import stgcn_oracle as O
+from tests.golden_util import check_grads, load
+
+gpu = pytest.mark.gpu
+
+
+def _ref_available():
+    from oracle import build_ref, ref_import
+    return ref_import.available() and (os.path.isdir("/root/reference") or build_ref.verify())
+
+
+def test_build_model_names_and_errors():
+    from fall_multimodal_b200 import BiLSTM, STGCAN, TwoStreamSTGCAN, TwoStreamSTGCAN_BiLSTM, build_model
+
+    cfg = {"MODEL": {"NAME": "stgcn"}, "DATA": {"IN_CHANNELS": 3, "NUM_CLASSES": 11, "SENSOR_DIM": 15},
+           "GRAPH": {"LAYOUT": "coco_cut", "STRATEGY": "spatial"}}
+    want = {"stgcn": STGCAN, "bilstm": BiLSTM, "two_stgcan": TwoStreamSTGCAN, "two_stgcan_bilstm": TwoStreamSTGCAN_BiLSTM}
+    for name, cls in want.items():
+        cfg["MODEL"]["NAME"] = name
+        assert type(build_model(cfg)) is cls
+    cfg["MODEL"]["NAME"] = "nope"
+    with pytest.raises(RuntimeError, match="not implemented"):
+        build_model(cfg)
+
+
+def test_notebook_class_state_dict_matches_reference_fixture():
+    from fall_multimodal_b200 import TwoStreamSpatialTemporalGraph
+
+    fx = load("nb_two_stream")
+    m = TwoStreamSpatialTemporalGraph({"layout": "coco_cut", "strategy": "spatial"}, 11)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == fx["shapes"]
+    assert sum(p.numel() for p in m.parameters()) == fx["n_params"] == 4298291
+
+
+@pytest.mark.skipif(not _ref_available(), reason="reference tree not staged")
+@pytest.mark.parametrize("which", ["stgcan", "two_stream_bilstm", "checkpoint_pt"])
+def test_checkpoint_written_by_the_reference_loads(which):
+    """``torch.save`` of the real reference module (F2/main.py:328-341 layouts) -> ``load_reference_checkpoint`` -> identical tensors."""
+    import warnings
+
+    import fall_multimodal_b200 as fmm
+    from fall_multimodal_b200.checkpoint import load_reference_checkpoint
+    from oracle import ref_models as R
+
+    stg, _, _, comb = R.gstcan_modules("coco_cut")
+    ga = {"layout": "coco_cut", "strategy": "spatial"}
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if which == "stgcan":
+            ref, mine = stg.STGCAN(3, ga, 11), fmm.STGCAN(3, ga, 11)
+            blob = {"model_weight": ref.state_dict()}                                   # best_model.pt
+        else:
+            ref, mine = comb.TwoStreamSTGCAN_BiLSTM(3, ga, 11, 15), fmm.TwoStreamSTGCAN_BiLSTM(3, ga, 11, 15)
+            opt = torch.optim.RMSprop(ref.parameters(), lr=1e-3)
+            blob = {"model_weight": ref.state_dict()} if which == "two_stream_bilstm" else \
+                {"epoch": 7, "model_weight": ref.state_dict(), "optimizer": opt.state_dict(), "lr_scheduler": None, "scaler": None,
+                 "best_acc": 0.5}                                                          # checkpoint.pt
+    buf = io.BytesIO()
+    torch.save(blob, buf)
+    buf.seek(0)
+    rest = load_reference_checkpoint(mine, buf, strict=True)
+    rsd, msd = ref.state_dict(), mine.state_dict()
+    assert set(rsd) == set(msd)
+    for k in rsd:
+        assert torch.equal(rsd[k], msd[k]), k
+    if which == "checkpoint_pt":
+        assert rest["epoch"] == 7 and rest["best_acc"] == 0.5 and "optimizer" in rest
+
+
+@gpu
+def test_notebook_two_stream_matches_reference_fixture():
+    """Tuple input, BiLSTM logits in the concat, softmax output fed to CrossEntropyLoss: logits, loss and every
+    gradient against the fixture produced by the notebook's own classes; forward_loss (fused double softmax) agrees."""
+    from fall_multimodal_b200 import TwoStreamSpatialTemporalGraph
+
+    dev = torch.device("cuda:0")
+    fx = load("nb_two_stream")
+    c = fx["config"]
+    m = TwoStreamSpatialTemporalGraph({"layout": c["layout"], "strategy": c["strategy"]}, c["num_class"])
+    sd = m.state_dict()
+    sd.update(O.fill_state_dict(fx["shapes"], fx["fill_seed"]))
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    m.compute_dtype = torch.float32
+    skel, sensor, target, _ = O.synthetic_batch(c["N"], c["T"], 14, 11, sensor_len=c["L"], sensor_ch=c["I"], seed=fx["batch_seed"])
+    skel, sensor, target = skel.to(dev), sensor.to(dev), target.to(dev)
+    mot = skel[:, :2, 1:] - skel[:, :2, :-1]
+    out = m((skel, mot, sensor))
+    loss = torch.nn.CrossEntropyLoss()(out, target)
+    loss.backward()
+    ref = fx["logits"].to(dev)
+    assert (out.sum(-1) - 1).abs().max().item() < 1e-5                     # probabilities, as the notebook returns them
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-4 and abs(loss.item() - fx["loss"]) < 1e-4
+    assert torch.equal(out.argmax(-1), ref.argmax(-1))
+    worst = check_grads({k: p.grad for k, p in m.named_parameters()}, fx["grads"], 5e-2)    # ReLU-flip tolerant (see test_stgcan.py)
+    print(f"notebook two-stream: probabilities {err:.2e}, worst grad err vs reference fixture {worst:.2e}")
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad()
+    pred, loss2 = m.forward_loss((skel, mot, sensor), target)
+    loss2.backward()
+    assert (pred - out.detach()).abs().max().item() < 1e-5 and abs(loss2.item() - loss.item()) < 1e-5
+    gs = max(g.abs().max().item() for g in g1.values())
+    for k, p in m.named_parameters():
+        assert (p.grad - g1[k]).abs().max().item() <= 2e-4 * max(g1[k].abs().max().item(), 1e-3 * gs), k

@@ -127,6 +127,7 @@ _SIGNATURES = {
     "fmm_bn2_bwd_coef": [_P] * 12 + [c_float, C.c_double, c_int] + [_P] * 10 + [c_int, c_int, _P],
     "fmm_bn1_bwd_coef": [_P, _P, c_int, _P, _P, _P, C.c_double, c_int] + [_P] * 5 + [c_int, _P],
     "fmm_lstm_fwd": [_P] * 8 + [c_int] * 5 + [_P],
+    "fmm_lstm_infer": [_P] * 6 + [c_int] * 6 + [_P],
     "fmm_lstm_bwd": [_P] * 11 + [c_int] * 5 + [_P],
     "fmm_conv1d_k5_fwd": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
     "fmm_bn_relu_pool2_fwd": [_P, _P, _P, _P, c_int, c_int, c_int, _P],

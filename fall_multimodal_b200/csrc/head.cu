@@ -125,13 +125,17 @@ __global__ void head_ce_bwd_rows_kernel(const __grid_constant__ HeadArgs a) {
   }
 }
 
-// one block per 128 input features: dW[c][f] = sum_n dz[n][c] feat[n][f]; block 0 also writes dbias[c] = sum_n dz[n][c]
+// grid = (F / 128, batch slices): dW[c][f] += sum_{n in slice} dz[n][c] feat[n][f] (dW zeroed by the launcher: one block
+// looping over the whole batch took 180 us at N = 256, a latency-bound serial chain); slice 0 / block 0 also adds dbias
+constexpr int kHeadSlices = 16;
 __global__ void head_ce_bwd_w_kernel(const __grid_constant__ HeadArgs a) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n0 = static_cast<int>(static_cast<long long>(a.N) * blockIdx.y / gridDim.y);
+  const int n1 = static_cast<int>(static_cast<long long>(a.N) * (blockIdx.y + 1) / gridDim.y);
   if (blockIdx.x == 0 && threadIdx.x < a.C && a.dbias) {
     float s = 0.f;
-    for (int n = 0; n < a.N; ++n) s += a.dz[static_cast<size_t>(n) * a.C + threadIdx.x];
-    a.dbias[threadIdx.x] = s;
+    for (int n = n0; n < n1; ++n) s += a.dz[static_cast<size_t>(n) * a.C + threadIdx.x];
+    atomicAdd(a.dbias + threadIdx.x, s);
   }
   if (f >= a.F) return;
   int s = 0, off = 0;
@@ -141,7 +145,7 @@ __global__ void head_ce_bwd_w_kernel(const __grid_constant__ HeadArgs a) {
   float acc[kHeadMaxC];
 #pragma unroll
   for (int c = 0; c < kHeadMaxC; ++c) acc[c] = 0.f;
-  for (int n = 0; n < a.N; ++n) {
+  for (int n = n0; n < n1; ++n) {
     const float x = col[static_cast<size_t>(n) * wd];
     const float* d = a.dz + static_cast<size_t>(n) * a.C;
 #pragma unroll
@@ -150,7 +154,7 @@ __global__ void head_ce_bwd_w_kernel(const __grid_constant__ HeadArgs a) {
   }
 #pragma unroll
   for (int c = 0; c < kHeadMaxC; ++c)
-    if (c < a.C) a.dW[static_cast<size_t>(c) * a.F + f] = acc[c];
+    if (c < a.C) atomicAdd(a.dW + static_cast<size_t>(c) * a.F + f, acc[c]);
 }
 
 }  // namespace fmm
@@ -209,7 +213,10 @@ int fmm_head_ce_bwd(const fmm_head_args* a, cudaStream_t stream) {
   FMM_CHECK_ARG(a->gloss && a->dz && a->dW, "head_ce_bwd: null pointer");
   const HeadArgs& h = *reinterpret_cast<const HeadArgs*>(a);
   head_ce_bwd_rows_kernel<<<a->N, 256, 0, stream>>>(h);
-  head_ce_bwd_w_kernel<<<(a->F + 127) / 128, 128, 0, stream>>>(h);
+  cudaMemsetAsync(a->dW, 0, sizeof(float) * a->C * a->F, stream);
+  if (a->dbias) cudaMemsetAsync(a->dbias, 0, sizeof(float) * a->C, stream);
+  const int slices = a->N < kHeadSlices ? a->N : kHeadSlices;
+  head_ce_bwd_w_kernel<<<dim3((a->F + 127) / 128, slices), 128, 0, stream>>>(h);
   FMM_CHECK_LAUNCH("head_ce_bwd");
   return FMM_OK;
 }

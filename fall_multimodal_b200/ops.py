@@ -447,6 +447,16 @@ def lstm_fwd(x, w_ih, w_hh, b_ih, b_hh, out, gates=None, cseq=None):
     return out
 
 
+def lstm_infer(x, w_ih, w_hh, b_ih, b_hh, feat, mean_feature: bool):
+    """feat (N, ndir*H) = mean over T / last step of the bidirectional LSTM from zero state (tensor-core inference path)."""
+    N, Tn, I = x.shape
+    ndir, G, H = w_hh.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and feat.shape == (N, ndir * H) and feat.is_contiguous()
+    L.check(L.load().fmm_lstm_infer(L.ptr(x), L.ptr(w_ih), L.ptr(w_hh), L.ptr(b_ih), L.ptr(b_hh), L.ptr(feat), N, Tn, I, H, ndir,
+                                    int(mean_feature), L.stream()), "lstm_infer")
+    return feat
+
+
 def lstm_bwd(x, w_ih, w_hh, out, gates, cseq, dout, dw_ih, dw_hh, db, dx=None):
     N, Tn, I = x.shape
     ndir, G, H = w_hh.shape

@@ -170,12 +170,24 @@ class BiLSTM(nn.Module):
         self.batchnorm = nn.BatchNorm1d(hidden_size * 2)
         self.channelattention = ChannelAttention(hidden_size * 2)
         self.feature = feature
+        self.fast_inference = True     # no-grad forward: tensor-core recurrence (csrc/lstm_tc.cu) instead of the training kernel
         self.fc = nn.Sequential(nn.Flatten(), nn.Linear(hidden_size * 2, num_classes))
 
     def features(self, sensor):
         if not sensor.is_cuda:
             raise RuntimeError("fall_multimodal_b200.BiLSTM runs on CUDA (sm_100a) only; there is no CPU fallback")
         l = self.lstm1
+        needs_grad = torch.is_grad_enabled() and (sensor.requires_grad or any(p.requires_grad for p in l.parameters()))
+        if not needs_grad and self.fast_inference and sensor.shape[2] <= 39:
+            # inference: the recurrence on tensor cores (csrc/lstm_tc.cu), only the (N, 128) feature leaves the kernel
+            with torch.autocast("cuda", enabled=False):
+                x = sensor.float().contiguous()
+                wi = torch.stack([l.weight_ih_l0, l.weight_ih_l0_reverse]).float().contiguous()
+                wh = torch.stack([l.weight_hh_l0, l.weight_hh_l0_reverse]).float().contiguous()
+                bi = torch.stack([l.bias_ih_l0, l.bias_ih_l0_reverse]).float().contiguous()
+                bh = torch.stack([l.bias_hh_l0, l.bias_hh_l0_reverse]).float().contiguous()
+                feat = torch.empty(x.shape[0], 2 * self.hidden_size, device=x.device)
+                return ops.lstm_infer(x, wi, wh, bi, bh, feat, self.feature != "last")
         out = _LSTMFn.apply(sensor, l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0, l.weight_ih_l0_reverse,
                             l.weight_hh_l0_reverse, l.bias_ih_l0_reverse, l.bias_hh_l0_reverse)
         return out[:, -1, :] if self.feature == "last" else out.mean(dim=1)      # bilstm.py:52-55

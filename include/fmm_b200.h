@@ -157,6 +157,13 @@ int fmm_gcn_prep_fwd(const float* A, const float* imp, const float* bg, const lo
 int fmm_gcn_prep_bwd(const float* A, const float* bg, const float* colsum, const float* TblR, int nrep, const float* dcoef,
                      const long long* dense_idx, float* dbg, float* dimp, int K, int V, int Cout, int E, cudaStream_t stream);
 
+/* Inference path of the bidirectional LSTM (bilstm.py:29,48-55) on tensor cores: feat [N][ndir*64] = mean over T (mean_feature
+ * != 0) or the t = T-1 output, from zero state. 64 windows per CTA for the whole sequence, recurrent + input weights resident
+ * in registers as mma.sync fragments, 3xTF32 split (fp32-grade), state double buffered in shared memory. Weight layout as
+ * fmm_lstm_fwd. H = 64, I <= 39. */
+int fmm_lstm_infer(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* feat, int N,
+                   int T, int I, int H, int ndir, int mean_feature, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * memory-bound kernels (one pass over an activation each)
  * ------------------------------------------------------------------------------------------- */

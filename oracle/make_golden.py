@@ -277,7 +277,7 @@ def main_notebook():
         exec("".join(nb["cells"][1]["source"]), ns)
         mod = ns["TwoStreamSpatialTemporalGraph"]({"layout": "coco_cut", "strategy": "spatial"}, 11)
     shapes = fill_module(mod, seed=8)
-    c = dict(layout="coco_cut", strategy="spatial", num_class=11, N=6, T=12, L=30, I=15)
+    c = dict(layout="coco_cut", strategy="spatial", num_class=11, N=16, T=20, L=30, I=15)
     skel, sensor, target, _ = O.synthetic_batch(c["N"], c["T"], 14, 11, sensor_len=30, sensor_ch=15, seed=14)
     mot = skel[:, :2, 1:] - skel[:, :2, :-1]
     res = run_train_step(mod, lambda: mod((skel, mot, sensor)), target)

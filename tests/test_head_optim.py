@@ -172,3 +172,29 @@ def test_databn_kernels_match_batchnorm1d(dtype):
     ops.databn_bwd(dy, x, mean, rstd, dgb[:V * C], dgb[V * C:])
     assert (dgb[:V * C] - bn.weight.grad).abs().max().item() < 1e-4 * bn.weight.grad.abs().max().item()
     assert (dgb[V * C:] - bn.bias.grad).abs().max().item() < 1e-4 * bn.bias.grad.abs().max().item()
+
+
+@gpu
+@pytest.mark.parametrize("I,Tn,N", [(6, 128, 200), (15, 30, 70), (4, 30, 64), (32, 7, 130)])
+@pytest.mark.parametrize("feature", ["mean", "last"])
+def test_lstm_tensor_core_inference_matches_training_kernel_and_torch(I, Tn, N, feature):
+    """csrc/lstm_tc.cu (3xTF32 mma.sync recurrence) against nn.LSTM in fp64 and the scalar training kernel, ragged batch sizes."""
+    from fall_multimodal_b200 import BiLSTM
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    m = BiLSTM(I, 64, 1, 0.3, 11, feature).to(dev).eval()
+    x = torch.randn(N, Tn, I, device=dev) * 1.5
+    with torch.no_grad():
+        fast = m.features(x)
+        m.fast_inference = False
+        slow = m.features(x)
+        ref_lstm = torch.nn.LSTM(I, 64, 1, batch_first=True, bidirectional=True).to(dev).double()
+        ref_lstm.load_state_dict({k: v.double() for k, v in m.lstm1.state_dict().items()})
+        o = ref_lstm(x.double())[0]
+        ref = o[:, -1, :] if feature == "last" else o.mean(1)
+    assert fast.shape == (N, 128)
+    e_fast = (fast.double() - ref).abs().max().item() / ref.abs().max().item()
+    e_slow = (slow.double() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"I={I} T={Tn} {feature}: tensor-core path {e_fast:.2e}, scalar kernel {e_slow:.2e} vs fp64 nn.LSTM")
+    assert e_fast < 2e-5 and e_slow < 2e-5

@@ -74,6 +74,7 @@ class TrunkEngine:
         rp = self._csr_np["bwd_rowptr"]
         self.max_out_deg = int(max(int(rp[i + 1]) - int(rp[i]) for i in range(self.V)))
         self._wstreams = {}
+        self._pstreams = {}
 
     def csr(self, device):
         key = str(device)
@@ -90,6 +91,60 @@ class TrunkEngine:
         return self._dev[key]
 
     # ------------------------------------------------------------------------------------------
+    def _prepare(self, P: dict, dt: torch.dtype, need_grad: bool, dev, V: int):
+        """Everything that depends on the parameters only - the (K,V,V) adjacency algebra of every block and all weight
+        images of the forward AND backward GEMMs (~110 tiny launches, 0.6 ms serialised) - queued on a side stream at the start
+        of the step, off the critical path of the activation chain; block i waits for its own event."""
+        K = self.K
+        csr = self.csr(dev)
+        cur = torch.cuda.current_stream(dev)
+        key = (str(dev), cur.cuda_stream)
+        if key not in self._pstreams:
+            self._pstreams[key] = torch.cuda.Stream(device=dev)
+        side = self._pstreams[key]
+        side.wait_stream(cur)
+        prep = []
+        A = P["A"]
+        with torch.cuda.stream(side):
+            for i, (Cin, Cout, s, reskind) in enumerate(self.blocks):
+                pre = f"{self.block_key}.{i}."
+                d = {}
+                d["coef_f"], d["coef_b"], d["colsum"], d["bias_eff"] = ops.gcn_prep_fwd(
+                    A, P[f"edge_importance.{i}"], P[pre + "gcn.conv.bias"], csr["dense_idx"], csr["bwd_perm"], Cout)
+                Wg, Wt = P[pre + "gcn.conv.weight"], P[pre + "tcn.2.weight"]
+                d["fused"] = self.fused_gcn and ops.gcn_supported(dt, Cin, Cout, V)
+                if d["fused"]:
+                    d["wg"] = ops.gcn_pack(Wg.view(K * Cout, Cin), K, Cin, Cout)
+                else:
+                    d["wg"] = ops.tapconv_pack(Wg, Cout, K * Cin, Cout, Cin, 0, Cin, Cout * Cin, 1, 0, [0], dt)
+                d["wt"] = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, Cout * 9, 0, 9, 1, list(range(9)), dt)
+                if reskind == "conv":
+                    Wr = P[pre + "residual.0.weight"]
+                    d["wr"] = ops.tapconv_pack(Wr, Cout, Cin, Cout, Cin, 0, Cin, 0, 1, 0, [0], dt)
+                if need_grad:
+                    if s == 1:
+                        d["wt_d"] = [ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, 9, 0, Cout * 9, 1, list(range(9)), dt)]
+                    else:
+                        d["wt_d"] = [ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, 9, 0, Cout * 9, 1, [0, 2, 4, 6, 8], dt),
+                                     ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, 9, 0, Cout * 9, 1, [1, 3, 5, 7], dt)]
+                    d["fused_bwd"] = self.fused_gcn_bwd and ops.gcn_bwd_supported(dt, Cin, Cout, V, K, self.max_out_deg)
+                    if d["fused_bwd"]:
+                        d["wg_b"] = ops.gcn_pack_bwd(Wg.view(K * Cout, Cin), K, Cin, Cout)
+                    else:
+                        d["wg_b"] = ops.tapconv_pack(Wg, K * Cin, Cout, Cin, Cout, Cout * Cin, 1, 0, Cin, 0, [0], dt)
+                    if reskind == "conv":
+                        d["wr_d"] = ops.tapconv_pack(Wr, Cin, Cout, Cin, Cout, 0, 1, 0, Cin, 0, [0], dt)
+                for v in d.values():
+                    for t in (v if isinstance(v, list) else [v]):
+                        buf = t.buf if isinstance(t, ops.PackedWeight) else t
+                        if torch.is_tensor(buf):
+                            buf.record_stream(cur)
+                d["ev"] = torch.cuda.Event()
+                d["ev"].record(side)
+                prep.append(d)
+        return prep
+
+    # ------------------------------------------------------------------------------------------
     def forward(self, P: dict, skel: torch.Tensor, training: bool, dt: torch.dtype, need_grad: bool):
         """Returns (pooled feature (N,256) fp32, saved-state dict for backward)."""
         dev = skel.device
@@ -101,6 +156,9 @@ class TrunkEngine:
         NR = ops.NREP
         arena = _Arena(dev, 7 * 6 * NR * 256 + 4096 + 2 * V * C, 8 * N * 256 + 4096)
         sv = {"blocks": [], "N": N, "dt": dt, "training": training}
+        prep = self._prepare(P, dt, need_grad, dev, V)
+        sv["prep"] = prep
+        cur_stream = torch.cuda.current_stream(dev)
 
         # ---- data_bn (stgcan.py:213-218): per-(v,c) BatchNorm1d over (N,T), csrc/databn.cu; the normalised clip is written
         # once, already channels-last in the compute dtype ----
@@ -118,27 +176,25 @@ class TrunkEngine:
         for i, (Cin, Cout, s, reskind) in enumerate(self.blocks):
             pre = f"{self.block_key}.{i}."
             b = {"T": T}
-            # A*importance as edge coefficients (forward and out-edge order), its column sums and the conv bias folded through
-            # the aggregation: one launch (csrc/gcnprep.cu)
-            coef_f, coef_b, colsum, bias_eff = ops.gcn_prep_fwd(A, P[f"edge_importance.{i}"], P[pre + "gcn.conv.bias"],
-                                                                csr["dense_idx"], csr["bwd_perm"], Cout)
+            pp = prep[i]
+            cur_stream.wait_event(pp["ev"])       # this block's coefficient tables / weight images (side stream, _prepare)
+            coef_f, coef_b, colsum, bias_eff = pp["coef_f"], pp["coef_b"], pp["colsum"], pp["bias_eff"]
             Wg = P[pre + "gcn.conv.weight"]
             G = torch.empty(N, T, V, Cout, dtype=dt, device=dev)
             a1, b1, mean1, rstd1 = (torch.empty(Cout, dtype=torch.float32, device=dev) for _ in range(4))
             st = arena.f64(2 * NR * Cout)
-            fused = self.fused_gcn and ops.gcn_supported(dt, Cin, Cout, V)
+            fused = pp["fused"]
             if fused:
                 # north-star graph conv: adjacency aggregation in the tcgen05 GEMM prologue, BN1 statistics in its epilogue
                 # (csrc/gcn.cu); the K-times wider aggregated tensor only reaches HBM while the old wgrad still wants it
                 Xa = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev) if (need_grad and not self.fused_gcn_wgrad) else None
-                ops.gcn_fwd(x, ops.gcn_pack(Wg.view(K * Cout, Cin), K, Cin, Cout), G, csr["fwd_rowptr"], csr["fwd_src"], coef_f, K,
+                ops.gcn_fwd(x, pp["wg"], G, csr["fwd_rowptr"], csr["fwd_src"], coef_f, K,
                             self.kdeg, bias=bias_eff, ch_sum=st[:NR * Cout] if training else None,
                             ch_sq=st[NR * Cout:] if training else None, xa=Xa)
             else:
                 Xa = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
                 ops.agg_fwd(x, Xa, csr["fwd_rowptr"], csr["fwd_src"], coef_f, K)
-                pw_g = ops.tapconv_pack(Wg, Cout, K * Cin, Cout, Cin, 0, Cin, Cout * Cin, 1, 0, [0], dt)
-                ops.tapconv(Xa, pw_g, G, shifts=[0], tj=T, bias=bias_eff, bias_per_joint=True)
+                ops.tapconv(Xa, pp["wg"], G, shifts=[0], tj=T, bias=bias_eff, bias_per_joint=True)
                 # BN1 statistics (stgcan.py:112), applied inside the temporal conv's prologue
                 if training:
                     ops.colstats(G, st[:NR * Cout], st[NR * Cout:])
@@ -148,7 +204,7 @@ class TrunkEngine:
             # temporal conv 9x1 (stgcan.py:114-118)
             To = (T - 1) // s + 1
             Wt = P[pre + "tcn.2.weight"]
-            pw_t = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, Cout * 9, 0, 9, 1, list(range(9)), dt)
+            pw_t = pp["wt"]
             U = torch.empty(N, To, V, Cout, dtype=dt, device=dev)
             Hm = None
             if self.materialize_h and dt == torch.bfloat16:
@@ -185,7 +241,7 @@ class TrunkEngine:
             R = ar = br = meanr = rstdr = pw_r = None
             if reskind == "conv":
                 Wr = P[pre + "residual.0.weight"]
-                pw_r = ops.tapconv_pack(Wr, Cout, Cin, Cout, Cin, 0, Cin, 0, 1, 0, [0], dt)
+                pw_r = pp["wr"]
                 R = torch.empty(N, To, V, Cout, dtype=dt, device=dev)
                 ops.tapconv(x, pw_r, R, shifts=[0], tj=To, istride=s, bias=P[pre + "residual.0.bias"])
                 ar, br, meanr, rstdr = f32(Cout), f32(Cout), f32(Cout), f32(Cout)
@@ -258,6 +314,7 @@ class TrunkEngine:
             Cin, Cout, s, reskind = self.blocks[i]
             pre = f"{self.block_key}.{i}."
             b = sv["blocks"][i]
+            pp = sv["prep"][i]
             T, To = b["T"], b["To"]
             x, Xa, G, U, R, Y = b["x"], b["Xa"], b["G"], b["U"], b["R"], b["Y"]
             C4 = int(Cout / 4)
@@ -315,14 +372,11 @@ class TrunkEngine:
             grads[pre + "tcn.2.weight"] = dWs.permute(1, 2, 0).unsqueeze(-1)
             dH = torch.empty_like(G)
             if s == 1:
-                pw = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, 9, 0, Cout * 9, 1, list(range(9)), dt)
-                ops.tapconv(dU, pw, dH, shifts=[4 - m for m in range(9)], tj=T)
+                ops.tapconv(dU, pp["wt_d"][0], dH, shifts=[4 - m for m in range(9)], tj=T)
             else:
-                pw = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, 9, 0, Cout * 9, 1, [0, 2, 4, 6, 8], dt)
-                ops.tapconv(dU, pw, dH, shifts=[2, 1, 0, -1, -2], tj=(T + 1) // 2, ostride=2, ooff=0)
+                ops.tapconv(dU, pp["wt_d"][0], dH, shifts=[2, 1, 0, -1, -2], tj=(T + 1) // 2, ostride=2, ooff=0)
                 if T // 2 > 0:
-                    pw = ops.tapconv_pack(Wt, Cout, Cout, Cout, Cout, 0, 9, 0, Cout * 9, 1, [1, 3, 5, 7], dt)
-                    ops.tapconv(dU, pw, dH, shifts=[2, 1, 0, -1], tj=T // 2, ostride=2, ooff=1)
+                    ops.tapconv(dU, pp["wt_d"][1], dH, shifts=[2, 1, 0, -1], tj=T // 2, ostride=2, ooff=1)
 
             # ---- BN1 + ReLU backward ----
             T1, T2 = arena.f64(NR * Cout), arena.f64(NR * Cout)
@@ -343,13 +397,12 @@ class TrunkEngine:
             else:
                 wgrad_async(Xa, dG, dWg, shifts=[0], c2=Cin, s_m=0, s_c1=Cout * Cin, s_c2=1, s_co=Cin)
             grads[pre + "gcn.conv.weight"] = dWg
-            fused_bwd = self.fused_gcn_bwd and ops.gcn_bwd_supported(dt, Cin, Cout, V, K, self.max_out_deg)
+            fused_bwd = pp["fused_bwd"]
             dcoef = arena.f32(self.E)
             Pm = None
             if not fused_bwd:
-                pw_gT = ops.tapconv_pack(Wg, K * Cin, Cout, Cin, Cout, Cout * Cin, 1, 0, Cin, 0, [0], dt)
                 Pm = torch.empty(N, T, V, K * Cin, dtype=dt, device=dev)
-                ops.tapconv(dG, pw_gT, Pm, shifts=[0], tj=T)
+                ops.tapconv(dG, pp["wg_b"], Pm, shifts=[0], tj=T)
             fused_dcoef = Cin % 8 == 0
             if not fused_dcoef:
                 ops.agg_dcoef(x, Pm, dcoef, csr["fwd_src"], csr["dst"], csr["kk"], K)
@@ -365,15 +418,14 @@ class TrunkEngine:
                 grads[pre + "residual.0.weight"] = dWr
                 grads[pre + "residual.0.bias"] = sum_dR.view(NR, Cout).sum(0).float()
                 grads[pre + "residual.1.weight"], grads[pre + "residual.1.bias"] = dgr, dbr
-                pw_rT = ops.tapconv_pack(Wr, Cin, Cout, Cin, Cout, 0, 1, 0, Cin, 0, [0], dt)
                 addend = torch.zeros_like(x)
-                ops.tapconv(dR, pw_rT, addend, shifts=[0], tj=To, ostride=s, ooff=0)
+                ops.tapconv(dR, pp["wr_d"], addend, shifts=[0], tj=To, ostride=s, ooff=0)
 
             dx = torch.empty_like(x)
             coef_b = b["coef_b"]
             if fused_bwd:
                 # P = dG.W^T stays on chip: GEMM + transposed aggregation + edge-coefficient gradient in one kernel (csrc/gcn.cu)
-                ops.gcn_bwd(dG, ops.gcn_pack_bwd(Wg.view(K * Cout, Cin), K, Cin, Cout), dx, csr["bwd_rowptr"], csr["dst_b"],
+                ops.gcn_bwd(dG, pp["wg_b"], dx, csr["bwd_rowptr"], csr["dst_b"],
                             csr["kk_b"], coef_b, K, self.max_out_deg, addend=addend, x=x, eid=csr["eid_b"], dcoef=dcoef)
             elif fused_dcoef:
                 ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K, x=x,

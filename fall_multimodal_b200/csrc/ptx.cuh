@@ -90,6 +90,50 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// Thread-block clusters / CTA pairs: barriers of the peer CTA are reached through shared::cluster addresses.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait on a barrier that threads of the peer CTA arrive on (acquire at cluster scope).
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, unsigned* err, unsigned tag) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > FMM_WAIT_LIMIT_CYCLES) {
+      if (err) atomicCAS(err, 0u, 0x80000000u | (tag << 16) | (blockIdx.x & 0xffffu));
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+  if (g_wait_prof_enable && (threadIdx.x & 31) == 0) atomicAdd(&g_wait_prof[tag & 31], static_cast<unsigned long long>(clock64() - t0));
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -122,6 +166,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                : "memory");
 }
+// CTA-pair (cta_group::2) variants: one warp of EACH CTA of the pair allocates / frees
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {  // whole warp
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -152,6 +209,20 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uin
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// CTA-pair MMA: M = 256 rows split over the two CTAs (each reads its own A rows and its own half of the B rows from its
+// own shared memory at the descriptors' offsets; each accumulates its 128 rows x N columns in its own TMEM). Issued by ONE
+// thread of the leader CTA (cluster rank 0).
+__device__ __forceinline__ void umma2_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
   return ((smem_addr & 0x3ffffu) >> 4) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
 }
@@ -172,6 +243,13 @@ __device__ __forceinline__ bool elect_one() {
 // mbarrier arrive once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// CTA-pair commit: arrives on the barrier at this offset in BOTH CTAs of the pair once the leader's MMAs have completed.
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
                : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = lane base+i)
@@ -224,7 +302,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D, M = 128.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt  [15] A major  [16] B major
 //   (0 = K-major, 1 = MN-major)  [17,23) N >> 3  [24,29) M >> 4
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int n, int a_mn_major, int b_mn_major) {
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int n, int a_mn_major, int b_mn_major, int m = 128) {
   uint32_t d = 0;
   d |= 1u << 4;
   d |= 1u << 7;
@@ -232,7 +310,7 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int n, int a_mn_maj
   d |= static_cast<uint32_t>(a_mn_major & 1) << 15;
   d |= static_cast<uint32_t>(b_mn_major & 1) << 16;
   d |= static_cast<uint32_t>(n >> 3) << 17;
-  d |= static_cast<uint32_t>(128 >> 4) << 24;
+  d |= static_cast<uint32_t>(m >> 4) << 24;  // 256: CTA pair (cta_group::2)
   return d;
 }
 

@@ -22,6 +22,8 @@
 // optional BN/ReLU in place), 8-15 epilogue (two warps per TMEM lane quadrant, alternating 32-column
 // groups: TMEM -> regs -> bias -> global), 16 weight loader (bulk async copies of pre-packed weight
 // images), 17 MMA issuer (one elected lane) + TMEM allocator.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "producer.cuh"
 #include "ptx.cuh"
@@ -51,6 +53,7 @@ struct TapConvParams {
   int bias_smem; // > 0: this many floats of `bias` are staged in shared memory once per CTA (the epilogue's bias loads sit on
                  // the tile's critical path: a per-joint table read from global memory cost +50 % on the 1x1 graph convs)
   int res_local; // resident && 1: only the images of the CTA's own N tile (gridDim.x is a multiple of ntiles_n)
+  int dbg;       // dev experiments (FMM_TAP_DBG): 1 no window copies, 2 no stores, 4 relaxed waits, 8 no TMEM loads
   unsigned* err;
 };
 
@@ -61,16 +64,27 @@ constexpr int kTapProducers = 256;
 // TMEM lane quadrant; narrow tiles run with 4 (fewer warps competing with the producers for issue slots).
 // kTaps only names the launch class (multi-tap temporal conv: tensor bound; 1x1 channel mix: HBM bound) so that profiler
 // output can be split per class; the code is identical.
-template <typename T, int kEpi, bool kTaps>
+//
+// kPair: the kernel runs as CTA pairs (cluster of 2 = one TPC). The pair owns two row tiles of the same N tile; every MMA is
+// one `tcgen05.mma.cta_group::2` with M = 256, issued by the leader CTA (cluster rank 0): each CTA stages its own window
+// and only HALF of every weight image (BN/2 rows) - half the weight fill traffic from L2 and half the shared-memory read
+// bandwidth per FLOP, which is what bounds the single-CTA kernel on the wide layers (profiles/r02_summary.md). Producers and
+// epilogue warps of the peer CTA arrive on the LEADER's barriers through shared::cluster addresses; the leader's commits
+// are multicast to the barriers of both CTAs.
+template <typename T, int kEpi, bool kTaps, bool kPair>
 __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __grid_constant__ TapConvParams p) {
   constexpr int kLoaderWarp = 8 + kEpi, kMmaWarp = 9 + kEpi;
   constexpr int kParts = ActTraits<T>::kParts;
+  static_assert(!kPair || kParts == 1, "CTA pairs: bf16 activations only");
+  constexpr uint32_t kCtas = kPair ? 2u : 1u;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t slot_bytes = static_cast<uint32_t>(kParts) * p.win_atoms * 1024u;
   const uint32_t part_bytes_a = static_cast<uint32_t>(p.win_atoms) * 1024u;
-  const uint32_t bstage_bytes = static_cast<uint32_t>(kParts) * p.BN * 128u;
-  const uint32_t part_bytes_b = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t bstage_bytes = static_cast<uint32_t>(kParts) * p.BN * 128u / kCtas;  // this CTA's rows of one weight image
+  const uint32_t part_bytes_b = static_cast<uint32_t>(p.BN) * 128u / kCtas;
+  const uint32_t gimg_bytes = bstage_bytes * kCtas;                                    // one whole image in global memory
   const uint32_t slots0 = smem_base;
   const uint32_t bst0 = slots0 + p.nslots * slot_bytes;
   const uint32_t bring_bytes = bstage_bytes * static_cast<uint32_t>(p.tps);  // one ring stage = tps images
@@ -83,6 +97,8 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
   auto acc_full = [&](int s) { return bars0 + 8u * (2 * p.nslots + 2 * p.nbstages + s); };
   auto acc_empty = [&](int s) { return bars0 + 8u * (2 * p.nslots + 2 * p.nbstages + 2 + s); };
   const uint32_t tmem_slot = bars0 + 8u * (2 * p.nslots + 2 * p.nbstages + 4);
+  // leader only: "the peer CTA's half of weight stage s has landed" (one remote arrive per fill by the peer's forwarder)
+  auto peer_b_full = [&](int s) { return bars0 + 8u * (2 * p.nslots + 2 * p.nbstages + 5 + s); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,7 +111,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslots; ++s) {
-      mbar_init(win_full(s), kTapProducers);
+      mbar_init(win_full(s), kTapProducers * kCtas);
       mbar_init(win_empty(s), 1);
     }
     for (int s = 0; s < p.nbstages; ++s) {
@@ -104,13 +120,20 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), kEpi * 32);
+      mbar_init(acc_empty(s), kEpi * 32 * kCtas);
     }
+    if (kPair)
+      for (int s = 0; s < (p.resident ? 1 : p.nbstages); ++s) mbar_init(peer_b_full(s), 1);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc2(tmem_slot, tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, tmem_cols);
+      tmem_relinquish();
+    }
   }
   const uint32_t bias_s0 = bars0 + 2048u;  // behind the barrier block
   // staged as [Cout/4][rows][4]: the 8 joints of a tile read 8 neighbouring float4 (one conflict-free wavefront per load;
@@ -122,13 +145,21 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
   }
   const float* __restrict__ bias_tab = reinterpret_cast<const float*>(smem_raw + (bias_s0 - smem_u32(smem_raw)));
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // (pair: the peer's barriers are initialised before any remote arrive)
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int first_tile = blockIdx.x;
-  const int tile_step = gridDim.x;
+  // tile index = rows * ntiles_n + ntile; in pair mode `rows` counts PAIRS of row tiles and this CTA takes row tile 2*rows+rank
+  // (a row tile past the end decodes to columns >= ncols: zero window, no stores)
+  const int first_tile = kPair ? blockIdx.x >> 1 : blockIdx.x;
+  const int tile_step = kPair ? gridDim.x >> 1 : gridDim.x;
+  auto rest_of = [&](int tile) { return kPair ? (tile / p.ntiles_n) * 2 + static_cast<int>(rank) : tile / p.ntiles_n; };
+  // arrive on a barrier of the leader CTA (plain local arrive when the kernel is not paired)
+  const uint32_t leader_bars0 = kPair ? mapa_shared(bars0, 0) : bars0;
+  auto arrive_leader = [&](uint32_t bar) {
+    if (kPair) mbar_arrive_cluster(leader_bars0 + (bar - bars0)); else mbar_arrive(bar);
+  };
 
   if (warp < 8) {
     // ------------------------------ window producers ------------------------------
@@ -156,7 +187,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       int i_tlo = 0;
       const __nv_bfloat16* i_colp = Xb;
       auto decode_tile = [&]() {
-        const int rest = i_tile / p.ntiles_n;
+        const int rest = rest_of(i_tile);
         const int tchunk = rest % p.ntchunks;
         const int group = rest / p.ntchunks;
         const int col = group * 8 + q;
@@ -171,7 +202,9 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         if (i_tile < p.total_tiles) {
           const int cb = i_c * 64 + pc * 8;
           const bool col_ok = i_colok && cb < p.Cin;
+          if (p.dbg & 4) mbar_wait_relaxed(win_empty(i_slot), i_ph ^ 1u, p.err, 1, 32); else
           mbar_wait(win_empty(i_slot), i_ph ^ 1u, p.err, 1);
+          if (!(p.dbg & 1))
           cpasync_issue_chunk(i_colp + (col_ok ? cb : 0), pitch_t, col_ok, p.Tin, i_tlo, p.win_atoms, a0, 4,
                               slots0 + i_slot * slot_bytes + q * 128u + ((pc ^ q) << 4));
           if (++i_slot == p.nslots) {
@@ -189,7 +222,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       for (int d = 0; d < (D > 0 ? D : 1); ++d) issue_one();
       int slot = 0;
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
-        const int rest = tile / p.ntiles_n;
+        const int rest = rest_of(tile);
         const int tchunk = rest % p.ntchunks;
         const int group = rest / p.ntchunks;
         const int col = group * 8 + q;
@@ -213,14 +246,14 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
                                  slots0 + slot * slot_bytes + q * 128u + ((pc ^ q) << 4));
           }
           fence_proxy_async_smem();
-          mbar_arrive(win_full(slot));
+          arrive_leader(win_full(slot));
           if (++slot == p.nslots) slot = 0;
           issue_one();
         }
       }
     } else {
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
-      const int rest = tile / p.ntiles_n;
+      const int rest = rest_of(tile);
       const int tchunk = rest % p.ntchunks;
       const int group = rest / p.ntchunks;
       const int col = group * 8 + q;
@@ -247,7 +280,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
           produce_chunk<T, kParts, false>(colp + cb, pitch_t, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4, p.Cin - cb, vec_ok,
                                           sc, sh, false, sdst, part_bytes_a);
         fence_proxy_async_smem();
-        mbar_arrive(win_full(slot));
+        arrive_leader(win_full(slot));
         if (++slot == p.nslots) {
           slot = 0;
           ph ^= 1u;
@@ -267,16 +300,17 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
     const bool vec_ok = (p.Cout % 8) == 0;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
       const int ntile = tile % p.ntiles_n;
-      const int rest = tile / p.ntiles_n;
+      const int rest = rest_of(tile);
       const int tchunk = rest % p.ntchunks;
       const int group = rest / p.ntchunks;
       const int col = group * 8 + q;
       const bool col_ok = col < p.ncols;
       const int n = col_ok ? col / p.V : 0;
       const int v = col_ok ? col % p.V : 0;
+      if (p.dbg & 4) mbar_wait_relaxed(acc_full(as), aph, p.err, 2, 64); else
       mbar_wait(acc_full(as), aph, p.err, 2);
       tc_fence_after();
-      for (int mt = 0; mt < p.MT; ++mt) {
+      for (int mt = 0; mt < ((p.dbg & 8) ? 0 : p.MT); ++mt) {
       const int j = (tchunk * p.MT + mt) * 16 + (r >> 3);
       const bool row_ok = col_ok && (j < p.Tj);
       T* orow = O + (static_cast<size_t>(n) * p.Tout + (row_ok ? j * p.ostride + p.ooff : 0)) * p.V * p.Cout +
@@ -295,7 +329,9 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
           for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(corr[i]));
         }
         const int co0 = ntile * p.BN + cg * 32;
-        if (row_ok && vec_ok && co0 + 32 <= p.Cout) {
+        if (p.dbg & 2) {
+          if (acc[0] == 0x7fc12345u) orow[0] = from_f32<T>(0.f);
+        } else if (row_ok && vec_ok && co0 + 32 <= p.Cout) {
           // fast path: whole 32-column group in range
           if (p.bias) {
             const int vrow = p.bias_vstride ? v : 0;
@@ -345,7 +381,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       }
       }
       tc_fence_before();
-      mbar_arrive(acc_empty(as));
+      arrive_leader(acc_empty(as));
       if (++as == 2) {
         as = 0;
         aph ^= 1u;
@@ -360,10 +396,11 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       if (p.resident) {
         // all images once: one transaction barrier, one bulk copy per image
         if (first_tile < p.total_tiles) {
-          const size_t base = p.res_local ? static_cast<size_t>(first_tile % p.ntiles_n) * p.nbstages * bstage_bytes : 0;
+          const size_t base = (p.res_local ? static_cast<size_t>(first_tile % p.ntiles_n) * p.nbstages * gimg_bytes : 0) +
+                              static_cast<size_t>(rank) * bstage_bytes;
           mbar_arrive_expect_tx(b_full(0), static_cast<uint32_t>(p.nbstages) * bstage_bytes);
           for (int i = 0; i < p.nbstages; ++i)
-            bulk_g2s(bst0 + i * bstage_bytes, W + base + static_cast<size_t>(i) * bstage_bytes, bstage_bytes, b_full(0));
+            bulk_g2s(bst0 + i * bstage_bytes, W + base + static_cast<size_t>(i) * gimg_bytes, bstage_bytes, b_full(0));
         }
       } else
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
@@ -371,10 +408,17 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         for (int c = 0; c < p.nchunks; ++c) {
           for (int m = 0; m < p.ntaps; m += p.tps) {
             const uint32_t ntp = static_cast<uint32_t>(p.ntaps - m < p.tps ? p.ntaps - m : p.tps);
+            if (p.dbg & 4) mbar_wait_relaxed(b_empty(bs), bph ^ 1u, p.err, 3, 32); else
             mbar_wait(b_empty(bs), bph ^ 1u, p.err, 3);
             mbar_arrive_expect_tx(b_full(bs), ntp * bstage_bytes);
-            const size_t off = ((static_cast<size_t>(ntile) * p.nchunks + c) * p.ntaps + m) * bstage_bytes;
-            bulk_g2s(bst0 + bs * bring_bytes, W + off, ntp * bstage_bytes, b_full(bs));
+            const size_t off = ((static_cast<size_t>(ntile) * p.nchunks + c) * p.ntaps + m) * gimg_bytes +
+                               static_cast<size_t>(rank) * bstage_bytes;
+            if (kPair) {  // this CTA's rows of each image: one copy per image
+              for (uint32_t i = 0; i < ntp; ++i)
+                bulk_g2s(bst0 + bs * bring_bytes + i * bstage_bytes, W + off + static_cast<size_t>(i) * gimg_bytes, bstage_bytes, b_full(bs));
+            } else {
+              bulk_g2s(bst0 + bs * bring_bytes, W + off, ntp * bstage_bytes, b_full(bs));
+            }
             if (++bs == p.nbstages) {
               bs = 0;
               bph ^= 1u;
@@ -389,14 +433,47 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
     // The warp walks the loops converged; each group of MMAs (+ its commit) is issued inside ONE
     // elect_one() region with (lo, hi) descriptor halves: ~15 instructions per MMA instead of the
     // ~40 (and a divergence waterfall) a per-thread branch costs, which matters for narrow tiles.
-    {
-      const uint32_t idesc = make_idesc_bf16(p.BN, 0, 0);
+    auto wait_x = [&](uint32_t bar, uint32_t parity, unsigned tag) {  // barriers the peer CTA also arrives on
+      if (kPair) mbar_wait_cluster(bar, parity, p.err, tag); else mbar_wait(bar, parity, p.err, tag);
+    };
+    auto mma = [&](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t id, uint32_t acc) {
+      if (kPair) umma2_bf16_lh(d, alo, ahi, blo, bhi, id, acc); else umma_bf16_lh(d, alo, ahi, blo, bhi, id, acc);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (kPair) umma2_commit(bar); else umma_commit(bar);
+    };
+    if (kPair && rank != 0) {
+      // peer CTA of a pair: no MMAs to issue; forward "my half of weight stage s has landed" to the leader
+      if (p.resident) {
+        if (first_tile < p.total_tiles) {
+          mbar_wait(b_full(0), 0, p.err, 6);
+          if (lane == 0) arrive_leader(peer_b_full(0));
+        }
+      } else {
+        int bs = 0;
+        uint32_t bph = 0;
+        for (int tile = first_tile; tile < p.total_tiles; tile += tile_step)
+          for (int c = 0; c < p.nchunks; ++c)
+            for (int m0 = 0; m0 < p.ntaps; m0 += p.tps) {
+              mbar_wait_relaxed(b_full(bs), bph, p.err, 6, 32);
+              if (lane == 0) arrive_leader(peer_b_full(bs));
+              if (++bs == p.nbstages) {
+                bs = 0;
+                bph ^= 1u;
+              }
+            }
+      }
+    } else {
+      const uint32_t idesc = make_idesc_bf16(p.BN, 0, 0, kPair ? 256 : 128);
       const uint32_t a_sbo = static_cast<uint32_t>(p.istride) * 1024u;
       const uint32_t a_hi = desc_hi(a_sbo), b_hi = desc_hi(1024);
       const uint32_t pa_lo = part_bytes_a >> 4, pb_lo = part_bytes_b >> 4;
       int slot = 0, bs = 0, as = 0;
       uint32_t wph = 0, bph = 0, aph = 0;
-      if (p.resident && first_tile < p.total_tiles) mbar_wait(b_full(0), 0, p.err, 6);
+      if (p.resident && first_tile < p.total_tiles) {
+        mbar_wait(b_full(0), 0, p.err, 6);
+        if (kPair) mbar_wait_cluster(peer_b_full(0), 0, p.err, 7);
+      }
       if (p.resident && kParts == 1) {
         // Resident weights: nothing to wait for between taps, so ALL MMAs of a (tile, chunk) item are
         // issued back to back from one elected lane (2 adds per MMA); narrow tiles are otherwise bound
@@ -408,14 +485,15 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         const uint32_t mt_lo = 16u * static_cast<uint32_t>(p.istride) * 64u;  // second M tile: 16 positions later
         for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
           const int ntile = p.res_local ? 0 : tile % p.ntiles_n;  // index into the resident images
-          mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
+          wait_x(acc_empty(as), aph ^ 1u, 4);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * acc_stride;
           for (int c = 0; c < p.nchunks; ++c) {
-            mbar_wait(win_full(slot), wph, p.err, 5);
+            wait_x(win_full(slot), wph, 5);
             tc_fence_after();
             const uint32_t a_lo0 = desc_lo(slots0 + slot * slot_bytes, 16);
             const uint32_t b_lo0 = desc_lo(bst0, 16) + static_cast<uint32_t>((ntile * p.nchunks + c) * p.ntaps) * img_lo;
+            const long long tq0 = (p.dbg & 16) ? clock64() : 0;
             if (elect_one()) {
 #pragma unroll
               for (int m = 0; m < 9; ++m) {
@@ -423,16 +501,17 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
                   for (uint32_t mt = 0; mt < static_cast<uint32_t>(p.MT); ++mt) {
 #pragma unroll
                     for (uint32_t kk = 0; kk < 4; ++kk)
-                      umma_bf16_lh(d_tmem + mt * p.BN, a_lo0 + tap_lo[m] + mt * mt_lo + kk * 2u, a_hi,
+                      mma(d_tmem + mt * p.BN, a_lo0 + tap_lo[m] + mt * mt_lo + kk * 2u, a_hi,
                                    b_lo0 + m * img_lo + kk * 2u, b_hi, idesc,
                                    static_cast<uint32_t>(c) | static_cast<uint32_t>(m) | kk);
                   }
                 }
               }
-              umma_commit(win_empty(slot));
-              if (c == p.nchunks - 1) umma_commit(acc_full(as));
+              commit(win_empty(slot));
+              if (c == p.nchunks - 1) commit(acc_full(as));
             }
             __syncwarp();
+            if ((p.dbg & 16) && lane == 0) atomicAdd(&g_wait_prof[8], static_cast<unsigned long long>(clock64() - tq0));
             if (++slot == p.nslots) {
               slot = 0;
               wph ^= 1u;
@@ -446,16 +525,19 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       } else
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const int ntile = p.res_local ? 0 : tile % p.ntiles_n;  // only used to index resident images
-        mbar_wait(acc_empty(as), aph ^ 1u, p.err, 4);
+        wait_x(acc_empty(as), aph ^ 1u, 4);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * acc_stride;
         uint32_t accum = 0;
         for (int c = 0; c < p.nchunks; ++c) {
-          mbar_wait(win_full(slot), wph, p.err, 5);
+          wait_x(win_full(slot), wph, 5);
           const uint32_t a_slot = slots0 + slot * slot_bytes;
           for (int m0 = 0; m0 < p.ntaps; m0 += p.tps) {
             const int ntp = p.ntaps - m0 < p.tps ? p.ntaps - m0 : p.tps;
-            if (!p.resident) mbar_wait(b_full(bs), bph, p.err, 6);
+            if (!p.resident) {
+              mbar_wait(b_full(bs), bph, p.err, 6);
+              if (kPair) mbar_wait_cluster(peer_b_full(bs), bph, p.err, 7);
+            }
             tc_fence_after();
             const uint32_t b_img = p.resident ? static_cast<uint32_t>((ntile * p.nchunks + c) * p.ntaps + m0) : 0u;
             const uint32_t b_lo0 = desc_lo(p.resident ? bst0 + b_img * bstage_bytes : bst0 + bs * bring_bytes, 16);
@@ -469,7 +551,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
                     const uint32_t a_mt = a_lo + mt * a_sbo, d_mt = d_tmem + mt * p.BN;  // 16 positions = 16*a_sbo bytes = a_sbo 16-byte units
 #pragma unroll
                     for (uint32_t kk = 0; kk < 4; ++kk)
-                      umma_bf16_lh(d_mt, a_mt + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | static_cast<uint32_t>(mm) | kk);
+                      mma(d_mt, a_mt + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | static_cast<uint32_t>(mm) | kk);
                   }
                 } else {
 #pragma unroll
@@ -479,15 +561,15 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
                     const uint32_t pb[5] = {0, 2, 1, 0, 1};
 #pragma unroll
                     for (int e = 0; e < 5; ++e)
-                      umma_bf16_lh(d_tmem + p.BN, a_lo + pa[e] * pa_lo + kk * 2u, a_hi, b_lo + pb[e] * pb_lo + kk * 2u, b_hi,
+                      mma(d_tmem + p.BN, a_lo + pa[e] * pa_lo + kk * 2u, a_hi, b_lo + pb[e] * pb_lo + kk * 2u, b_hi,
                                    idesc, accum | static_cast<uint32_t>(mm) | kk | static_cast<uint32_t>(e));
-                    umma_bf16_lh(d_tmem, a_lo + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | static_cast<uint32_t>(mm) | kk);
+                    mma(d_tmem, a_lo + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | static_cast<uint32_t>(mm) | kk);
                   }
                 }
               }
-              if (!p.resident) umma_commit(b_empty(bs));
-              if (last) umma_commit(win_empty(slot));
-              if (last && c == p.nchunks - 1) umma_commit(acc_full(as));
+              if (!p.resident) commit(b_empty(bs));
+              if (last) commit(win_empty(slot));
+              if (last && c == p.nchunks - 1) commit(acc_full(as));
             }
             __syncwarp();
             accum = 1;
@@ -511,10 +593,10 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // (pair: the leader's MMAs read the peer's shared memory until here)
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (kPair) tmem_dealloc2(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -670,6 +752,15 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   // two M tiles per item when the accumulators fit (2 stages x 2 tiles x BN columns) and the window stays small
   const int bn_probe = pick_bn(Cout, dtype);
   p.MT = (dtype == FMM_DT_BF16 && istride == 1 && bn_probe <= 128 && Tj > 16) ? 2 : 1;
+  // CTA pairs (cta_group::2) for the multi-tap bf16 convs whose weights do not fit shared memory (256 channels: 1.18 MB of
+  // images streamed per row tile, L2 -> SM fill bound): half of every weight image per CTA. Measured (B200, N=256 clips):
+  // 256 ch 180 -> 150 us; 128 ch 90 -> 88 us (weights resident as halves, one M tile per item), 64 ch 59 -> 68 us (already
+  // resident, N = 64 MMAs are shared-memory-read bound either way) - so only BN = 256 runs paired by default (FMM_TAP_PAIR=2:
+  // every multi-tap launch, =0: none).
+  static const int pair_env = getenv("FMM_TAP_PAIR") ? atoi(getenv("FMM_TAP_PAIR")) : 1;
+  const bool pair = pair_env && (pair_env >= 2 || bn_probe >= 256) && dtype == FMM_DT_BF16 && ntaps > 1 && (Cin % 64) == 0 &&
+                    (Cout % 32) == 0 && (num_sms() % 2) == 0;
+  if (pair && bn_probe == 128) p.MT = 1;
   p.win_atoms = (16 * p.MT - 1) * istride + (mx - mn) + 1;
   p.BN = pick_bn(Cout, dtype);
   p.ntiles_n = ((Cout + 31) / 32 * 32 + p.BN - 1) / p.BN;
@@ -677,11 +768,13 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   p.ncols = N * V;
   p.ngroups = (p.ncols + 7) / 8;
   p.ntchunks = (Tj + 16 * p.MT - 1) / (16 * p.MT);
-  p.total_tiles = p.ngroups * p.ntchunks * p.ntiles_n;
+  p.total_tiles = pair ? (p.ngroups * p.ntchunks + 1) / 2 * p.ntiles_n : p.ngroups * p.ntchunks * p.ntiles_n;
   p.err = err;
+  static const int dbg_env = getenv("FMM_TAP_DBG") ? atoi(getenv("FMM_TAP_DBG")) : 0;
+  p.dbg = dbg_env;
   const int nparts = dtype == FMM_DT_F32 ? 3 : 1;
   const size_t slot_bytes = static_cast<size_t>(nparts) * p.win_atoms * 1024;
-  const size_t bstage_bytes = static_cast<size_t>(nparts) * p.BN * 128;
+  const size_t bstage_bytes = static_cast<size_t>(nparts) * p.BN * 128 / (pair ? 2 : 1);  // per CTA
   // the bias table ([V][Cout] for the per-joint bias of the graph conv, else [Cout]) rides along in shared memory when small
   const size_t bias_floats = bias ? static_cast<size_t>(bias_per_joint ? V : 1) * Cout : 0;
   p.bias_smem = (bias_floats > 0 && bias_floats * 4 <= 36 * 1024 && (Cout % 4) == 0) ? static_cast<int>(bias_floats) : 0;
@@ -692,12 +785,13 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   const int nimg = p.ntiles_n * p.nchunks * ntaps;
   int nb, ns;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (pair) grid = 2 * (p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2);
   p.resident = (nimg <= 96 && nimg * bstage_bytes + 3 * slot_bytes <= budget) ? 1 : 0;
   p.res_local = 0;
   // several N tiles whose images do not all fit: a CTA whose tiles all share one N tile (tile index = rows * ntiles_n
   // + ntile, stride gridDim.x) keeps just that tile's images
   const int nimg_tile = p.nchunks * ntaps;
-  if (!p.resident && p.ntiles_n > 1 && grid >= p.ntiles_n && nimg_tile <= 96 &&
+  if (!pair && !p.resident && p.ntiles_n > 1 && grid >= p.ntiles_n && nimg_tile <= 96 &&
       nimg_tile * bstage_bytes + 3 * slot_bytes <= budget) {
     p.resident = 1;
     p.res_local = 1;
@@ -729,24 +823,53 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   const bool wide = p.BN >= 128;
 #define FMM_LAUNCH_TAPCONV2(TT, EPI, TAPS)                                                                       \
   do {                                                                                                           \
-    cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<TT, EPI, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    cudaError_t e = cudaFuncSetAttribute(tapconv_kernel<TT, EPI, TAPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem);                                                             \
     if (e != cudaSuccess) {                                                                                      \
       set_last_error("tapconv: smem attribute: %s", cudaGetErrorString(e));                                      \
       return FMM_ERR_SMEM;                                                                                       \
     }                                                                                                            \
-    tapconv_kernel<TT, EPI, TAPS><<<grid, (10 + EPI) * 32, smem, stream>>>(p);                                   \
+    tapconv_kernel<TT, EPI, TAPS, false><<<grid, (10 + EPI) * 32, smem, stream>>>(p);                            \
+  } while (0)
+#define FMM_LAUNCH_TAPCONV_PAIR(EPI)                                                                             \
+  do {                                                                                                           \
+    auto kern = tapconv_kernel<__nv_bfloat16, EPI, true, true>;                                                  \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (e != cudaSuccess) {                                                                                      \
+      set_last_error("tapconv: smem attribute: %s", cudaGetErrorString(e));                                      \
+      return FMM_ERR_SMEM;                                                                                       \
+    }                                                                                                            \
+    cudaLaunchConfig_t cfg = {};                                                                                 \
+    cfg.gridDim = dim3(grid);                                                                                    \
+    cfg.blockDim = dim3((10 + EPI) * 32);                                                                        \
+    cfg.dynamicSmemBytes = smem;                                                                                 \
+    cfg.stream = stream;                                                                                         \
+    cudaLaunchAttribute at[1];                                                                                   \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                              \
+    at[0].val.clusterDim.x = 2;                                                                                  \
+    at[0].val.clusterDim.y = 1;                                                                                  \
+    at[0].val.clusterDim.z = 1;                                                                                  \
+    cfg.attrs = at;                                                                                              \
+    cfg.numAttrs = 1;                                                                                            \
+    e = cudaLaunchKernelEx(&cfg, kern, p);                                                                       \
+    if (e != cudaSuccess) {                                                                                      \
+      set_last_error("tapconv: pair launch: %s", cudaGetErrorString(e));                                         \
+      return FMM_ERR_CUDA;                                                                                       \
+    }                                                                                                            \
   } while (0)
 #define FMM_LAUNCH_TAPCONV(TT, EPI)                                                                              \
   do {                                                                                                           \
     if (ntaps > 1) FMM_LAUNCH_TAPCONV2(TT, EPI, true); else FMM_LAUNCH_TAPCONV2(TT, EPI, false);                 \
   } while (0)
-  if (dtype == FMM_DT_BF16) {
+  if (pair) {
+    if (wide) FMM_LAUNCH_TAPCONV_PAIR(8); else FMM_LAUNCH_TAPCONV_PAIR(4);
+  } else if (dtype == FMM_DT_BF16) {
     if (wide) FMM_LAUNCH_TAPCONV(__nv_bfloat16, 8); else FMM_LAUNCH_TAPCONV(__nv_bfloat16, 4);
   } else {
     if (wide) FMM_LAUNCH_TAPCONV(float, 8); else FMM_LAUNCH_TAPCONV(float, 4);
   }
 #undef FMM_LAUNCH_TAPCONV2
+#undef FMM_LAUNCH_TAPCONV_PAIR
 #undef FMM_LAUNCH_TAPCONV
   FMM_CHECK_LAUNCH("tapconv");
   return FMM_OK;

@@ -8,8 +8,8 @@ dev = torch.device("cuda:0")
 N, V, dt = 256, 33, torch.bfloat16
 lib = _lib.load()
 TAGS = {1: "producer<-win_empty (x256 thr)", 2: "epilogue<-acc_full (x128)", 3: "loader<-b_empty (x1)", 4: "mma<-acc_empty (x1)",
-        5: "mma<-win_full (x1)", 6: "mma<-b_full (x1)", 11: "wg producer<-empty (x256)", 12: "wg epilogue<-acc_full (x128)", 13: "wg mma<-full (x1)"}
-NTHR = {1: 8, 2: 4, 3: 1, 4: 1, 5: 1, 6: 1, 11: 8, 12: 4, 13: 1}  # sampling warps (lane 0 of each)
+        5: "mma<-win_full (x1)", 6: "mma<-b_full (x1)", 7: "mma<-peer_b_full (x1)", 8: "mma issue region (x1)", 11: "wg producer<-empty (x256)", 12: "wg epilogue<-acc_full (x128)", 13: "wg mma<-full (x1)"}
+NTHR = {1: 8, 2: 4, 3: 1, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 11: 8, 12: 4, 13: 1}  # sampling warps (lane 0 of each)
 
 def run(name, fn):
     fn(); torch.cuda.synchronize()
@@ -47,6 +47,11 @@ def wg(name, T, Cin, Cout, ntaps, stride, prologue):
     sh_ = list(range(-(ntaps // 2), ntaps // 2 + 1))
     run("wgrad " + name, lambda: ops.wgrad(x, dy, dw, shifts=sh_, istride=stride, in_scale=sc, in_shift=sh, in_relu=prologue, s_m=1, s_c2=ntaps, s_co=Cin * ntaps))
 
+if len(sys.argv) > 1 and sys.argv[1] == "plain":
+    tap("tcn_plain_b1", 64, 64, 64, 9, 1, False)
+    tap("tcn_plain_b4", 32, 128, 128, 9, 1, False)
+    tap("tcn_plain_b6", 16, 256, 256, 9, 1, False)
+    sys.exit(0)
 tap("tcn_fwd_b1", 64, 64, 64, 9, 1, True)
 tap("tcn_dgrad_b1", 64, 64, 64, 9, 1, False)
 tap("tcn_fwd_b6", 16, 256, 256, 9, 1, True)

@@ -45,6 +45,10 @@ CASES = [
     ("1x1_cout768", 2, 8, 9, 256, 768, [0], 1, False),
     ("1x1_s2_res", 2, 32, 6, 64, 128, [0], 2, False),
     ("t5_dgrad_even", 2, 16, 6, 128, 64, [2, 1, 0, -1, -2], 1, False),
+    # more row tiles than CTA pairs (148 SMs = 74 pairs): several waves, odd tile counts, the weight ring wraps many times
+    ("t9_c256_waves", 37, 16, 33, 256, 256, list(range(-4, 5)), 1, False),
+    ("t9_c128_waves", 21, 32, 33, 128, 128, list(range(-4, 5)), 1, False),
+    ("t9_c64_s2_waves", 23, 64, 33, 64, 64, list(range(-4, 5)), 2, True),
 ]
 
 

@@ -89,6 +89,39 @@ __device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
+// The same 8 activations as RAW bits: streaming kernels issue the loads of several rows back to back into Raw8 registers
+// and convert afterwards. With load8 in a rolled-up loop the compiler keeps ONE 16-byte load in flight per thread (load,
+// wait, convert, accumulate, next load: ncu r02, every row-walk kernel sat at 2.2-3.9 TB/s on exactly that).
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<__nv_bfloat16> {
+  uint4 u;
+};
+template <>
+struct Raw8<float> {
+  float4 a, b;
+};
+__device__ __forceinline__ void ldraw8(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& r) {
+  r.u = __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void ldraw8(const float* p, Raw8<float>& r) {
+  r.a = __ldg(reinterpret_cast<const float4*>(p));
+  r.b = __ldg(reinterpret_cast<const float4*>(p + 4));
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float (&f)[8]) {
+  f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
+  f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+
 // pack 8 fp32 -> 8 bf16 (one 16-byte chunk)
 __device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
   uint4 u;

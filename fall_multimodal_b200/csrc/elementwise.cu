@@ -250,46 +250,84 @@ __global__ void agg_dcoef_narrow_kernel(const T* __restrict__ x, const T* __rest
 // Every thread holds NV x 8 partial sums for channel group c8 (row lane rl). They are staged as
 // scratch[rl][c8n*8][NV] with plain conflict-free stores and summed over rl by C*NV threads:
 // shared-memory atomics cost ~2 cycles per lane and serialise the whole SM at the end of each block.
+// The staging area is laid out [j*NV+v][rl][c8] (the thread index fastest: consecutive lanes hit consecutive banks; the
+// [rl][c][v] layout it replaces cost a 15-way bank conflict per store, ncu r02).  red[c*NV+v] as before.
 template <int NV>
 __device__ __forceinline__ void block_channel_reduce(const float (&val)[NV][8], float* scratch, float* red, int c8,
                                                      int c8n, int rl, int RL) {
   const int C = c8n * 8;
-  float* mine = scratch + (static_cast<size_t>(rl) * C + c8 * 8) * NV;
+  const int nt = RL * c8n;   // threads that hold partial sums (= blockDim.x for the row-walk launches)
+  __syncthreads();           // the previous segment's readers are done with scratch / red
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int v = 0; v < NV; ++v) mine[j * NV + v] = val[v][j];
+    for (int v = 0; v < NV; ++v) scratch[static_cast<size_t>(j * NV + v) * nt + rl * c8n + c8] = val[v][j];
   __syncthreads();
   for (int i = threadIdx.x; i < C * NV; i += blockDim.x) {
+    const int c = i / NV, v = i - c * NV;
+    const float* col = scratch + static_cast<size_t>((c & 7) * NV + v) * nt + (c >> 3);
     float acc = 0.f;
-    for (int r = 0; r < RL; ++r) acc += scratch[static_cast<size_t>(r) * C * NV + i];
+    for (int r = 0; r < RL; ++r) acc += col[r * c8n];
     red[i] = acc;
   }
 }
 
+// Balanced persistent partition for the streaming kernels: the grid is ONE resident wave (SMs x blocks per SM) and block b
+// owns the rows [R*b/G, R*(b+1)/G) of the flattened (clip, frame*joint) row space - every block the same number of rows
+// (grids of N x T/chunk blocks ran 1.4-3.5 waves: up to half of the kernel was the partial last wave, ncu r02). A block's
+// range is walked clip by clip (per-clip coefficients / per-clip sums): `next` yields (n, r0, r1) with rows local to clip n.
+struct RowSegs {
+  long long cur, end;
+  int rows_per_n;
+  __device__ RowSegs(int N, int rows_per_n_) : rows_per_n(rows_per_n_) {
+    const long long total = static_cast<long long>(N) * rows_per_n_;
+    cur = total * blockIdx.x / gridDim.x;
+    end = total * (blockIdx.x + 1) / gridDim.x;
+  }
+  __device__ bool next(int& n, int& r0, int& r1) {
+    if (cur >= end) return false;
+    n = static_cast<int>(cur / rows_per_n);
+    const long long base = static_cast<long long>(n) * rows_per_n;
+    const long long e = end < base + rows_per_n ? end : base + rows_per_n;
+    r0 = static_cast<int>(cur - base);
+    r1 = static_cast<int>(e - base);
+    cur = e;
+    return true;
+  }
+};
+
 // colstats: per-channel sum / sum of squares (double) and optional per-(n,c) sums (float) of X.
 template <typename T>
 __global__ void colstats_kernel(const T* __restrict__ X, double* __restrict__ ch_sum, double* __restrict__ ch_sq,
-                                float* __restrict__ nc_sum, int Tn, int V, int C, int tchunk, int nrep) {
+                                float* __restrict__ nc_sum, int N, int Tn, int V, int C, int nrep) {
   extern __shared__ float red[];  // [C][2] followed by the [RL][C][2] staging area
   float* scratch = red + 2 * C;
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * tchunk * V;
-  const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
   const int c8n = C / 8;
   const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
+  RowSegs segs(N, Tn * V);
+  int n, r0, r1;
+  while (segs.next(n, r0, r1)) {
   const T* base = X + static_cast<size_t>(n) * Tn * V * C + c8 * 8;
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-#pragma unroll 4
-  for (int r = r0 + rl; r < r1; r += RL) {
-    float f[8];
-    load8(base + static_cast<size_t>(r) * C, f);
+  constexpr int U = 8;   // rows in flight per thread
+  for (int r = r0 + rl; r < r1; r += U * RL) {
+    Raw8<T> raw[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += f[j];
-      acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
+    for (int u = 0; u < U; ++u)
+      if (r + u * RL < r1) ldraw8(base + static_cast<size_t>(r + u * RL) * C, raw[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r + u * RL < r1) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += f[j];
+          acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
+        }
+      }
     }
   }
   block_channel_reduce<2>(acc, scratch, red, c8, c8n, rl, RL);
@@ -301,19 +339,20 @@ __global__ void colstats_kernel(const T* __restrict__ X, double* __restrict__ ch
     if (ch_sq) atomic_add_f64(ch_sq + ro + c, static_cast<double>(q));
     if (nc_sum) atomicAdd(nc_sum + static_cast<size_t>(n) * C + c, s);
   }
+  }
 }
 
 // block_out: y = relu(k1[n,c]*U + k0[n,c] + res), res = 0 | X | ar[c]*R + br[c]
 template <typename T>
 __global__ void block_out_kernel(const T* __restrict__ U, const float* __restrict__ k1, const float* __restrict__ k0,
                                  const T* __restrict__ res, const float* __restrict__ ar,
-                                 const float* __restrict__ br, T* __restrict__ Y, int Tn, int V, int C, int tchunk) {
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * tchunk * V;
-  const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
+                                 const float* __restrict__ br, T* __restrict__ Y, int N, int Tn, int V, int C) {
   const int c8n = C / 8;
   const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
   const int c0 = c8 * 8;
+  RowSegs segs(N, Tn * V);
+  int n, r0, r1;
+  while (segs.next(n, r0, r1)) {
   float a[8], b[8], ra[8], rb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -323,19 +362,32 @@ __global__ void block_out_kernel(const T* __restrict__ U, const float* __restric
     rb[j] = br ? br[c0 + j] : 0.f;
   }
   const size_t base = static_cast<size_t>(n) * Tn * V * C + c0;
-#pragma unroll 4
-  for (int r = r0 + rl; r < r1; r += RL) {
-    const size_t off = base + static_cast<size_t>(r) * C;
-    float u[8], rr[8], y[8];
-    load8(U + off, u);
-    if (res) load8(res + off, rr);
+  constexpr int NB = 4;   // rows in flight per thread
+  for (int r = r0 + rl; r < r1; r += NB * RL) {
+    Raw8<T> ru[NB], rres[NB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = fmaf(a[j], u[j], b[j]);
-      if (res) v += fmaf(ra[j], rr[j], rb[j]);
-      y[j] = fmaxf(v, 0.f);
-    }
-    store8(Y + off, y);
+    for (int q = 0; q < NB; ++q)
+      if (r + q * RL < r1) {
+        const size_t off = base + static_cast<size_t>(r + q * RL) * C;
+        ldraw8(U + off, ru[q]);
+        if (res) ldraw8(res + off, rres[q]);
+      }
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+      if (r + q * RL < r1) {
+        const size_t off = base + static_cast<size_t>(r + q * RL) * C;
+        float u[8], rr[8], y[8];
+        unpack8(ru[q], u);
+        if (res) unpack8(rres[q], rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = fmaf(a[j], u[j], b[j]);
+          if (res) v += fmaf(ra[j], rr[j], rb[j]);
+          y[j] = fmaxf(v, 0.f);
+        }
+        store8(Y + off, y);
+      }
+  }
   }
 }
 
@@ -343,10 +395,9 @@ __global__ void block_out_kernel(const T* __restrict__ U, const float* __restric
 // block so that the temporal conv and its weight gradient stream H with plain async copies)
 template <typename T>
 __global__ void affine_relu_kernel(const T* __restrict__ X, const float* __restrict__ a, const float* __restrict__ b,
-                                   T* __restrict__ H, int Tn, int V, int C, int tchunk) {
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * tchunk * V;
-  const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
+                                   T* __restrict__ H, int N, int Tn, int V, int C) {
+  const long long total = static_cast<long long>(N) * Tn * V;
+  const long long r0 = total * blockIdx.x / gridDim.x, r1 = total * (blockIdx.x + 1) / gridDim.x;
   const int c8n = C / 8;
   const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
   float sa[8], sb[8];
@@ -355,15 +406,22 @@ __global__ void affine_relu_kernel(const T* __restrict__ X, const float* __restr
     sa[j] = a[c8 * 8 + j];
     sb[j] = b[c8 * 8 + j];
   }
-  const size_t base = static_cast<size_t>(n) * Tn * V * C + c8 * 8;
-#pragma unroll 4
-  for (int r = r0 + rl; r < r1; r += RL) {
-    const size_t off = base + static_cast<size_t>(r) * C;
-    float f[8];
-    load8(X + off, f);
+  const size_t base = static_cast<size_t>(c8) * 8;
+  constexpr int NB = 8;   // rows in flight per thread
+  for (long long r = r0 + rl; r < r1; r += NB * RL) {
+    Raw8<T> raw[NB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(sa[j], f[j], sb[j]), 0.f);
-    store8(H + off, f);
+    for (int q = 0; q < NB; ++q)
+      if (r + q * RL < r1) ldraw8(X + base + static_cast<size_t>(r + q * RL) * C, raw[q]);
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+      if (r + q * RL < r1) {
+        float f[8];
+        unpack8(raw[q], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(sa[j], f[j], sb[j]), 0.f);
+        store8(H + base + static_cast<size_t>(r + q * RL) * C, f);
+      }
   }
 }
 
@@ -371,33 +429,46 @@ __global__ void affine_relu_kernel(const T* __restrict__ X, const float* __restr
 template <typename T>
 __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ U,
                                            const T* __restrict__ R, float* __restrict__ S1, float* __restrict__ S2,
-                                           float* __restrict__ S3, int Tn, int V, int C, int tchunk) {
+                                           float* __restrict__ S3, int N, int Tn, int V, int C) {
   extern __shared__ float red[];  // [C][3] followed by the [RL][C][3] staging area
   float* scratch = red + 3 * C;
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * tchunk * V;
-  const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
   const int c8n = C / 8;
   const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
+  RowSegs segs(N, Tn * V);
+  int n, r0, r1;
+  while (segs.next(n, r0, r1)) {
   const size_t base = static_cast<size_t>(n) * Tn * V * C + c8 * 8;
   float acc[3][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
-#pragma unroll 2
-  for (int r = r0 + rl; r < r1; r += RL) {
-    const size_t off = base + static_cast<size_t>(r) * C;
-    float g[8], y[8], u[8], rr[8];
-    load8(dY + off, g);
-    load8(Y + off, y);
-    load8(U + off, u);
-    if (R) load8(R + off, rr);
+  constexpr int NB = 2;   // rows in flight per thread (3-4 tensors each)
+  for (int r = r0 + rl; r < r1; r += NB * RL) {
+    Raw8<T> rg[NB], ry[NB], ru[NB], rres[NB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float d = y[j] > 0.f ? g[j] : 0.f;
-      acc[0][j] += d;
-      acc[1][j] = fmaf(d, u[j], acc[1][j]);
-      if (R) acc[2][j] = fmaf(d, rr[j], acc[2][j]);
-    }
+    for (int q = 0; q < NB; ++q)
+      if (r + q * RL < r1) {
+        const size_t off = base + static_cast<size_t>(r + q * RL) * C;
+        ldraw8(dY + off, rg[q]);
+        ldraw8(Y + off, ry[q]);
+        ldraw8(U + off, ru[q]);
+        if (R) ldraw8(R + off, rres[q]);
+      }
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+      if (r + q * RL < r1) {
+        float g[8], y[8], u[8], rr[8];
+        unpack8(rg[q], g);
+        unpack8(ry[q], y);
+        unpack8(ru[q], u);
+        if (R) unpack8(rres[q], rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = y[j] > 0.f ? g[j] : 0.f;
+          acc[0][j] += d;
+          acc[1][j] = fmaf(d, u[j], acc[1][j]);
+          if (R) acc[2][j] = fmaf(d, rr[j], acc[2][j]);
+        }
+      }
   }
   block_channel_reduce<3>(acc, scratch, red, c8, c8n, rl, RL);
   __syncthreads();
@@ -405,6 +476,7 @@ __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __
     atomicAdd(S1 + static_cast<size_t>(n) * C + c, red[3 * c]);
     atomicAdd(S2 + static_cast<size_t>(n) * C + c, red[3 * c + 1]);
     if (R) atomicAdd(S3 + static_cast<size_t>(n) * C + c, red[3 * c + 2]);
+  }
   }
 }
 
@@ -420,15 +492,18 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
                                      const float* __restrict__ r1, const float* __restrict__ r2,
                                      const float* __restrict__ r3, T* __restrict__ dU, T* __restrict__ dR,
                                      T* __restrict__ dPre, double* __restrict__ sum_dU,
-                                     double* __restrict__ sum_dR, int Tn, int V, int C, int tchunk, int nrep) {
+                                     double* __restrict__ sum_dR, int N, int Tn, int V, int C, int nrep) {
   extern __shared__ float red[];  // [C][2] followed by the [RL][C][2] staging area
   float* scratch = red + 2 * C;
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * tchunk * V;
-  const int r1r = min((blockIdx.x + 1) * tchunk, Tn) * V;
   const int c8n = C / 8;
   const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
   const int c0 = c8 * 8;
+  float acc[2][8];   // per-channel sums of the stored dU / dR over ALL of this block's rows: one flush at the end
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  RowSegs segs(N, Tn * V);
+  int n, r0, r1r;
+  while (segs.next(n, r0, r1r)) {
   float a1[8], a2[8], a3[8], b1[8], b2[8], b3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -439,18 +514,28 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
     b2[j] = R ? r2[c0 + j] : 0.f;
     b3[j] = R ? r3[c0 + j] : 0.f;
   }
-  float acc[2][8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   const size_t base = static_cast<size_t>(n) * Tn * V * C + c0;
-#pragma unroll 2
-  for (int r = r0 + rl; r < r1r; r += RL) {
-    const size_t off = base + static_cast<size_t>(r) * C;
+  constexpr int NB = 2;   // rows in flight per thread (3-4 tensors each)
+  for (int rb = r0 + rl; rb < r1r; rb += NB * RL) {
+    Raw8<T> rg[NB], ry[NB], ru[NB], rres[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+      if (rb + q * RL < r1r) {
+        const size_t off = base + static_cast<size_t>(rb + q * RL) * C;
+        ldraw8(dY + off, rg[q]);
+        ldraw8(Y + off, ry[q]);
+        ldraw8(U + off, ru[q]);
+        if (R) ldraw8(R + off, rres[q]);
+      }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+    if (rb + q * RL >= r1r) continue;
+    const size_t off = base + static_cast<size_t>(rb + q * RL) * C;
     float g[8], y[8], u[8], rr[8], ou[8], orr[8], d[8];
-    load8(dY + off, g);
-    load8(Y + off, y);
-    load8(U + off, u);
-    if (R) load8(R + off, rr);
+    unpack8(rg[q], g);
+    unpack8(ry[q], y);
+    unpack8(ru[q], u);
+    if (R) unpack8(rres[q], rr);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       d[j] = y[j] > 0.f ? g[j] : 0.f;
@@ -464,7 +549,10 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
     store8(dU + off, ou);
     if (R) store8(dR + off, orr);
     if (dPre) store8(dPre + off, d);
+    }
   }
+  }
+  if (!sum_dU && !sum_dR) return;
   block_channel_reduce<2>(acc, scratch, red, c8, c8n, rl, RL);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -478,12 +566,11 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
 template <typename T>
 __global__ void bn1_bwd_reduce_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
                                       const float* __restrict__ b1, double* __restrict__ T1,
-                                      double* __restrict__ T2, int Tn, int V, int C, int tchunk, int nrep) {
+                                      double* __restrict__ T2, int N, int Tn, int V, int C, int nrep) {
   extern __shared__ float red[];  // [C][2] followed by the [RL][C][2] staging area
   float* scratch = red + 2 * C;
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * tchunk * V;
-  const int r1 = min((blockIdx.x + 1) * tchunk, Tn) * V;
+  const long long total = static_cast<long long>(N) * Tn * V;
+  const long long r0 = total * blockIdx.x / gridDim.x, r1 = total * (blockIdx.x + 1) / gridDim.x;
   const int c8n = C / 8;
   const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = blockDim.x / c8n;
   float a[8], b[8];
@@ -495,19 +582,30 @@ __global__ void bn1_bwd_reduce_kernel(const T* __restrict__ dH, const T* __restr
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-  const size_t base = static_cast<size_t>(n) * Tn * V * C + c8 * 8;
-#pragma unroll 4
-  for (int r = r0 + rl; r < r1; r += RL) {
-    const size_t off = base + static_cast<size_t>(r) * C;
-    float g[8], h[8];
-    load8(dH + off, h);
-    load8(G + off, g);
+  const size_t base = static_cast<size_t>(c8) * 8;
+  constexpr int NB = 4;   // rows in flight per thread (2 tensors each)
+  for (long long r = r0 + rl; r < r1; r += NB * RL) {
+    Raw8<T> rh[NB], rg[NB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float d = fmaf(a[j], g[j], b[j]) > 0.f ? h[j] : 0.f;
-      acc[0][j] += d;
-      acc[1][j] = fmaf(d, g[j], acc[1][j]);
-    }
+    for (int q = 0; q < NB; ++q)
+      if (r + q * RL < r1) {
+        const size_t off = base + static_cast<size_t>(r + q * RL) * C;
+        ldraw8(dH + off, rh[q]);
+        ldraw8(G + off, rg[q]);
+      }
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+      if (r + q * RL < r1) {
+        float g[8], h[8];
+        unpack8(rh[q], h);
+        unpack8(rg[q], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = fmaf(a[j], g[j], b[j]) > 0.f ? h[j] : 0.f;
+          acc[0][j] += d;
+          acc[1][j] = fmaf(d, g[j], acc[1][j]);
+        }
+      }
   }
   block_channel_reduce<2>(acc, scratch, red, c8, c8n, rl, RL);
   __syncthreads();
@@ -520,13 +618,14 @@ __global__ void bn1_bwd_reduce_kernel(const T* __restrict__ dH, const T* __restr
 
 // bn1_bwd_apply: dG = c1[c]*dy1 + c2[c]*G + c3[c]  (dy1 as above); Tbl[v][c] += sum_{n,t} dG
 template <typename T>
-__global__ void bn1_bwd_apply_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
+__global__ void __launch_bounds__(512) bn1_bwd_apply_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
                                      const float* __restrict__ b1, const float* __restrict__ c1,
                                      const float* __restrict__ c2, const float* __restrict__ c3, T* __restrict__ dG,
-                                     float* __restrict__ Tbl, int Tn, int V, int C, int tchunk, int nrep) {
-  const int n = blockIdx.y;
-  const int t0 = blockIdx.x * tchunk;
-  const int t1 = min(t0 + tchunk, Tn);
+                                     float* __restrict__ Tbl, int N, int Tn, int V, int C, int nrep) {
+  // balanced persistent partition over the N*Tn frames (nothing here depends on the clip); fewer, longer blocks also
+  // mean fewer [V][C] table flushes: 8.6 M float atomics per launch at C = 256 with the old N x T/chunk grid
+  const long long frames = static_cast<long long>(N) * Tn;
+  const long long t0 = frames * blockIdx.x / gridDim.x, t1 = frames * (blockIdx.x + 1) / gridDim.x;
   const int c8n = C / 8;
   const int pairs = V * c8n;
   for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
@@ -541,18 +640,31 @@ __global__ void bn1_bwd_apply_kernel(const T* __restrict__ dH, const T* __restri
       k3[j] = c3[c0 + j];
     }
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = t0; t < t1; ++t) {
-      const size_t off = (static_cast<size_t>(n) * Tn + t) * V * C + static_cast<size_t>(i) * 8;
-      float g[8], h[8], o[8];
-      load8(dH + off, h);
-      load8(G + off, g);
+    constexpr int NB = sizeof(T) == 2 ? 4 : 2;   // frames in flight per thread (2 tensors each)
+    for (long long tb = t0; tb < t1; tb += NB) {
+      Raw8<T> rh[NB], rg[NB];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = fmaf(a[j], g[j], b[j]) > 0.f ? h[j] : 0.f;
-        o[j] = fmaf(k1[j], d, fmaf(k2[j], g[j], k3[j]));
-        acc[j] += to_f32(from_f32<T>(o[j]));
-      }
-      store8(dG + off, o);
+      for (int q = 0; q < NB; ++q)
+        if (tb + q < t1) {
+          const size_t off = static_cast<size_t>(tb + q) * V * C + static_cast<size_t>(i) * 8;
+          ldraw8(dH + off, rh[q]);
+          ldraw8(G + off, rg[q]);
+        }
+#pragma unroll
+      for (int q = 0; q < NB; ++q)
+        if (tb + q < t1) {
+          const size_t off = static_cast<size_t>(tb + q) * V * C + static_cast<size_t>(i) * 8;
+          float g[8], h[8], o[8];
+          unpack8(rh[q], h);
+          unpack8(rg[q], g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = fmaf(a[j], g[j], b[j]) > 0.f ? h[j] : 0.f;
+            o[j] = fmaf(k1[j], d, fmaf(k2[j], g[j], k3[j]));
+            acc[j] += to_f32(from_f32<T>(o[j]));
+          }
+          store8(dG + off, o);
+        }
     }
     if (Tbl) {
 #pragma unroll
@@ -573,6 +685,17 @@ static inline int pair_threads(int pairs) {
   const int iters = (pairs + 511) / 512;
   int t = ((pairs + iters - 1) / iters + 31) / 32 * 32;
   return t > 1024 ? 1024 : t;
+}
+
+// one resident wave of blocks for the balanced persistent kernels (capped for tiny inputs: >= 32 rows per block)
+template <typename Kern>
+static inline int resident_grid(Kern kernel, int threads, size_t smem, long long rows) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+  long long g = static_cast<long long>(nb) * num_sms();
+  const long long cap = (rows + 31) / 32;
+  if (g > cap) g = cap;
+  return static_cast<int>(g < 1 ? 1 : g);
 }
 
 static inline int pick_tchunk(int N, int Tn) {
@@ -656,10 +779,11 @@ int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, in
                  int dtype, cudaStream_t stream) {
   FMM_CHECK_ARG(nrep >= 1, "colstats: nrep");
   FMM_CHECK_ARG(X && N > 0 && Tn > 0 && V > 0 && C > 0 && C % 8 == 0, "colstats: bad args (C must be a multiple of 8)");
-  const int tchunk = pick_tchunk(N, Tn);
-  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  const int th = rowwalk_threads(C);
+  const size_t sm = (2 * C + th * 16) * sizeof(float);
+  const long long rows = static_cast<long long>(N) * Tn * V;
   FMM_DISPATCH(dtype, {
-    colstats_kernel<T><<<grid, rowwalk_threads(C), (2 * C + rowwalk_threads(C) * 16) * sizeof(float), stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, Tn, V, C, tchunk, nrep);
+    colstats_kernel<T><<<resident_grid(colstats_kernel<T>, th, sm, rows), th, sm, stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, N, Tn, V, C, nrep);
   })
   FMM_CHECK_LAUNCH("colstats");
   return FMM_OK;
@@ -668,10 +792,10 @@ int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, in
 int fmm_block_out(const void* U, const float* k1, const float* k0, const void* res, const float* ar, const float* br,
                   void* Y, int N, int Tn, int V, int C, int dtype, cudaStream_t stream) {
   FMM_CHECK_ARG(U && k1 && k0 && Y && C % 8 == 0, "block_out: bad args");
-  const int tchunk = pick_tchunk(N, Tn);
-  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  const int th = rowwalk_threads(C);
+  const long long rows = static_cast<long long>(N) * Tn * V;
   FMM_DISPATCH(dtype, {
-    block_out_kernel<T><<<grid, rowwalk_threads(C), 0, stream>>>((const T*)U, k1, k0, (const T*)res, ar, br, (T*)Y, Tn, V, C, tchunk);
+    block_out_kernel<T><<<resident_grid(block_out_kernel<T>, th, 0, rows), th, 0, stream>>>((const T*)U, k1, k0, (const T*)res, ar, br, (T*)Y, N, Tn, V, C);
   })
   FMM_CHECK_LAUNCH("block_out");
   return FMM_OK;
@@ -680,10 +804,10 @@ int fmm_block_out(const void* U, const float* k1, const float* k0, const void* r
 int fmm_affine_relu(const void* X, const float* a, const float* b, void* H, int N, int Tn, int V, int C, int dtype,
                     cudaStream_t stream) {
   FMM_CHECK_ARG(X && a && b && H && C % 8 == 0, "affine_relu: bad args");
-  const int tchunk = pick_tchunk(N, Tn);
-  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  const int th = rowwalk_threads(C);
+  const long long rows = static_cast<long long>(N) * Tn * V;
   FMM_DISPATCH(dtype, {
-    affine_relu_kernel<T><<<grid, rowwalk_threads(C), 0, stream>>>((const T*)X, a, b, (T*)H, Tn, V, C, tchunk);
+    affine_relu_kernel<T><<<resident_grid(affine_relu_kernel<T>, th, 0, rows), th, 0, stream>>>((const T*)X, a, b, (T*)H, N, Tn, V, C);
   })
   FMM_CHECK_LAUNCH("affine_relu");
   return FMM_OK;
@@ -692,11 +816,12 @@ int fmm_affine_relu(const void* X, const float* a, const float* b, void* H, int 
 int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const void* R, float* S1, float* S2,
                             float* S3, int N, int Tn, int V, int C, int dtype, cudaStream_t stream) {
   FMM_CHECK_ARG(dY && Y && U && S1 && S2 && C % 8 == 0 && (!R || S3), "blockout_bwd_reduce: bad args");
-  const int tchunk = pick_tchunk(N, Tn);
-  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  const int th = rowwalk_threads(C);
+  const size_t sm = (3 * C + th * 24) * sizeof(float);
+  const long long rows = static_cast<long long>(N) * Tn * V;
   FMM_DISPATCH(dtype, {
-    blockout_bwd_reduce_kernel<T><<<grid, rowwalk_threads(C), (3 * C + rowwalk_threads(C) * 24) * sizeof(float), stream>>>(
-        (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, S1, S2, S3, Tn, V, C, tchunk);
+    blockout_bwd_reduce_kernel<T><<<resident_grid(blockout_bwd_reduce_kernel<T>, th, sm, rows), th, sm, stream>>>(
+        (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, S1, S2, S3, N, Tn, V, C);
   })
   FMM_CHECK_LAUNCH("blockout_bwd_reduce");
   return FMM_OK;
@@ -709,12 +834,13 @@ int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* 
   FMM_CHECK_ARG(nrep >= 1, "bn2_bwd_apply: nrep");
   FMM_CHECK_ARG(dY && Y && U && k1 && k2 && k3 && dU && C % 8 == 0, "bn2_bwd_apply: bad args");
   FMM_CHECK_ARG(!R || (r1 && r2 && r3 && dR), "bn2_bwd_apply: residual branch needs r1..r3 and dR");
-  const int tchunk = pick_tchunk(N, Tn);
-  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  const int th = rowwalk_threads(C);
+  const size_t sm = (2 * C + th * 16) * sizeof(float);
+  const long long rows = static_cast<long long>(N) * Tn * V;
   FMM_DISPATCH(dtype, {
-    bn2_bwd_apply_kernel<T><<<grid, rowwalk_threads(C), (2 * C + rowwalk_threads(C) * 16) * sizeof(float), stream>>>(
+    bn2_bwd_apply_kernel<T><<<resident_grid(bn2_bwd_apply_kernel<T>, th, sm, rows), th, sm, stream>>>(
         (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, k1, k2, k3, r1, r2, r3, (T*)dU, (T*)dR, (T*)dPre, sum_dU,
-        sum_dR, Tn, V, C, tchunk, nrep);
+        sum_dR, N, Tn, V, C, nrep);
   })
   FMM_CHECK_LAUNCH("bn2_bwd_apply");
   return FMM_OK;
@@ -724,10 +850,11 @@ int fmm_bn1_bwd_reduce(const void* dH, const void* G, const float* a1, const flo
                        int nrep, int N, int Tn, int V, int C, int dtype, cudaStream_t stream) {
   FMM_CHECK_ARG(nrep >= 1, "bn1_bwd_reduce: nrep");
   FMM_CHECK_ARG(dH && G && a1 && b1 && T1 && T2 && C % 8 == 0, "bn1_bwd_reduce: bad args");
-  const int tchunk = pick_tchunk(N, Tn);
-  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  const int th = rowwalk_threads(C);
+  const size_t sm = (2 * C + th * 16) * sizeof(float);
+  const long long rows = static_cast<long long>(N) * Tn * V;
   FMM_DISPATCH(dtype, {
-    bn1_bwd_reduce_kernel<T><<<grid, rowwalk_threads(C), (2 * C + rowwalk_threads(C) * 16) * sizeof(float), stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, Tn, V, C, tchunk, nrep);
+    bn1_bwd_reduce_kernel<T><<<resident_grid(bn1_bwd_reduce_kernel<T>, th, sm, rows), th, sm, stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, N, Tn, V, C, nrep);
   })
   FMM_CHECK_LAUNCH("bn1_bwd_reduce");
   return FMM_OK;
@@ -738,10 +865,12 @@ int fmm_bn1_bwd_apply(const void* dH, const void* G, const float* a1, const floa
                       int dtype, cudaStream_t stream) {
   FMM_CHECK_ARG(nrep >= 1, "bn1_bwd_apply: nrep");
   FMM_CHECK_ARG(dH && G && a1 && b1 && c1 && c2 && c3 && dG && C % 8 == 0, "bn1_bwd_apply: bad args");
-  const int tchunk = pick_tchunk(N, Tn);
-  dim3 grid((Tn + tchunk - 1) / tchunk, N);
+  const int th = pair_threads(V * (C / 8));   // <= 512 (the kernel's launch bound)
+  const long long frames = static_cast<long long>(N) * Tn;
   FMM_DISPATCH(dtype, {
-    bn1_bwd_apply_kernel<T><<<grid, pair_threads(V * (C / 8)), 0, stream>>>((const T*)dH, (const T*)G, a1, b1, c1, c2, c3, (T*)dG, Tbl, Tn, V, C, tchunk, nrep);
+    int g = resident_grid(bn1_bwd_apply_kernel<T>, th, 0, frames * 32);
+    if (g > frames) g = static_cast<int>(frames);
+    bn1_bwd_apply_kernel<T><<<g, th, 0, stream>>>((const T*)dH, (const T*)G, a1, b1, c1, c2, c3, (T*)dG, Tbl, N, Tn, V, C, nrep);
   })
   FMM_CHECK_LAUNCH("bn1_bwd_apply");
   return FMM_OK;

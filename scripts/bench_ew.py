@@ -11,15 +11,28 @@ dt = torch.bfloat16
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 
-def timeit(fn, reps=5):
-    fn(); torch.cuda.synchronize()
+def _graph_us(body, reps=5):
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        body()
+    g.replay(); torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
-        flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     return min(ts)
+
+_flush_us = None
+
+def timeit(fn, reps=5):
+    """GPU time of one launch behind an L2 flush, without the host's launch latency: (flush + kernel) and (flush) are each
+    replayed from a CUDA graph and subtracted (events around an eager ctypes launch add ~10 us to a 30 us kernel)."""
+    global _flush_us
+    fn(); torch.cuda.synchronize()
+    if _flush_us is None:
+        _flush_us = _graph_us(lambda: flush.zero_())
+    return _graph_us(lambda: (flush.zero_(), fn())) - _flush_us
 
 def report(name, us, nbytes):
     print(f"{name:28s} {us:8.1f} us  {nbytes/us/1e3:7.0f} GB/s  ({nbytes/1e6:.0f} MB)")

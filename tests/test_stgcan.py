@@ -115,7 +115,7 @@ def test_stgcan_fp32_matches_reference_fixture(name):
     # (2) strict: against the fp64 oracle evaluated with the SAME ReLU decisions
     ograds, oout, flips, worst_pre = oracle_with_masks(m, fx, skel, target, dev)
     # (1) against the reference's own gradients (fixture): 1e-4 unless a ReLU decision differs from exact arithmetic
-    worst_fx = check_grads(grads, fx["grads"], FP32_TOL if flips == 0 else FLIP_TOL)
+    worst_fx = check_grads(grads, fx["grads"], FP32_TOL if flips == 0 else FLIP_TOL, truth=ograds)
     assert (out.double() - oout).abs().max().item() / oout.abs().max().item() < FP32_TOL
     assert worst_pre < 1e-4, f"a ReLU decision differs at |x|/max = {worst_pre:.2e}: not a rounding-level flip"
     gs = max(g.abs().max().item() for g in ograds.values())

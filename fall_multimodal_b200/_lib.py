@@ -99,7 +99,7 @@ _SIGNATURES = {
     "fmm_gcn_wgrad": [_P, _P, _P, _P, _P, _P, C.POINTER(c_int), c_ll, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "fmm_gcn_packed_bwd_bytes": [c_int, c_int, c_int],
     "fmm_gcn_pack_bwd": [_P, _P, c_int, c_int, c_int, _P],
-    "fmm_gcn_bwd": [_P] * 11 + [c_int, c_ll, c_int, c_int, c_int, c_int, _P, _P],
+    "fmm_gcn_bwd": [_P] * 11 + [c_int, c_int, c_ll, c_int, c_int, c_int, c_int, _P, _P],
     "fmm_databn_stats": [_P, _P, _P, c_int, c_int, c_int, c_int, _P],
     "fmm_databn_apply": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_databn_bwd": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],

@@ -12,7 +12,10 @@
 // Reference call sites: /root/reference/Fall_2_Spatial_Temporal_SR/Model/stgcan.py
 //   :54 (einsum nkctv,kvw->nctw, reassociated onto the input), :63-73 (SE pooling and scale),
 //   :112-119 (BatchNorm2d/ReLU around the temporal conv), :138-144 (attention, residual, ReLU).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "stream.cuh"
 
 namespace fmm {
 
@@ -449,7 +452,7 @@ __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __
       if (r + q * RL < r1) {
         const size_t off = base + static_cast<size_t>(r + q * RL) * C;
         ldraw8(dY + off, rg[q]);
-        ldraw8(Y + off, ry[q]);
+        if (Y) ldraw8(Y + off, ry[q]);
         ldraw8(U + off, ru[q]);
         if (R) ldraw8(R + off, rres[q]);
       }
@@ -458,12 +461,12 @@ __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __
       if (r + q * RL < r1) {
         float g[8], y[8], u[8], rr[8];
         unpack8(rg[q], g);
-        unpack8(ry[q], y);
+        if (Y) unpack8(ry[q], y);
         unpack8(ru[q], u);
         if (R) unpack8(rres[q], rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float d = y[j] > 0.f ? g[j] : 0.f;
+          const float d = (!Y || y[j] > 0.f) ? g[j] : 0.f;   // Y == null: dY arrives already masked (fmm_gcn_bwd relu_mask)
           acc[0][j] += d;
           acc[1][j] = fmaf(d, u[j], acc[1][j]);
           if (R) acc[2][j] = fmaf(d, rr[j], acc[2][j]);
@@ -523,7 +526,7 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
       if (rb + q * RL < r1r) {
         const size_t off = base + static_cast<size_t>(rb + q * RL) * C;
         ldraw8(dY + off, rg[q]);
-        ldraw8(Y + off, ry[q]);
+        if (Y) ldraw8(Y + off, ry[q]);
         ldraw8(U + off, ru[q]);
         if (R) ldraw8(R + off, rres[q]);
       }
@@ -533,12 +536,12 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
     const size_t off = base + static_cast<size_t>(rb + q * RL) * C;
     float g[8], y[8], u[8], rr[8], ou[8], orr[8], d[8];
     unpack8(rg[q], g);
-    unpack8(ry[q], y);
+    if (Y) unpack8(ry[q], y);
     unpack8(ru[q], u);
     if (R) unpack8(rres[q], rr);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      d[j] = y[j] > 0.f ? g[j] : 0.f;
+      d[j] = (!Y || y[j] > 0.f) ? g[j] : 0.f;   // Y == null: dY arrives already masked
       ou[j] = fmaf(a1[j], d[j], fmaf(a2[j], u[j], a3[j]));
       acc[0][j] += to_f32(from_f32<T>(ou[j]));
       if (R) {
@@ -613,6 +616,77 @@ __global__ void bn1_bwd_reduce_kernel(const T* __restrict__ dH, const T* __restr
     const size_t ro = static_cast<size_t>(replica_of_block(nrep)) * C;
     atomic_add_f64(T1 + ro + c, static_cast<double>(red[2 * c]));
     atomic_add_f64(T2 + ro + c, static_cast<double>(red[2 * c + 1]));
+  }
+}
+
+// The same reduction, inputs staged through the TMA ring of stream.cuh (the launcher's default).
+template <typename T>
+__global__ void __launch_bounds__(kStThreads, 1)
+    bn1_bwd_reduce_tma_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
+                              const float* __restrict__ b1, double* __restrict__ T1, double* __restrict__ T2, int N, int Tn,
+                              int V, int C, int nrep, int chunk_rows, unsigned* err) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  StreamPipe<2> pipe;
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * sizeof(T);
+  pipe.init(st_smem, static_cast<uint32_t>(chunk_rows) * row_bytes);
+  float* red = reinterpret_cast<float*>(st_smem + (pipe.empty0 + 8u * kStStages + 64u - smem_u32(st_smem)));
+  float* scratch = red + 2 * C;
+  ChunkIter it(static_cast<long long>(N) * Tn * V, 1, Tn * V, chunk_rows, false);
+  long long row0;
+  int nrows, n, i = 0;
+  if (threadIdx.x >= kStConsumers) {
+    if (threadIdx.x == kStConsumers) {
+      const void* const src[2] = {dH, G};
+      while (it.next(row0, nrows, n)) pipe.produce(i++, src, row0, nrows, row_bytes, err);
+    }
+    return;
+  }
+  const int c8n = C / 8;
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = kStConsumers / c8n;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = a1[c8 * 8 + j];
+    b[j] = b1[c8 * 8 + j];
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  const uint32_t toff = static_cast<uint32_t>(threadIdx.x) * 8u * sizeof(T);   // (rl * C + c8 * 8) elements
+  const uint32_t rstep = static_cast<uint32_t>(RL) * row_bytes;
+  while (it.next(row0, nrows, n)) {
+    const int s = pipe.acquire(i++, err);
+    uint32_t ah = pipe.tensor(s, 0) + toff, ag = pipe.tensor(s, 1) + toff;
+#pragma unroll 2
+    for (int r = rl; r < nrows; r += RL, ah += rstep, ag += rstep) {
+      float g[8], h[8];
+      lds8(ah, h, static_cast<const T*>(nullptr));
+      lds8(ag, g, static_cast<const T*>(nullptr));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = fmaf(a[j], g[j], b[j]) > 0.f ? h[j] : 0.f;
+        acc[0][j] += d;
+        acc[1][j] = fmaf(d, g[j], acc[1][j]);
+      }
+    }
+    pipe.release(s);
+  }
+  // block reduce among the consumer threads only (the producer warp has left): named barrier 1
+  {
+    const int nt = RL * c8n;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) scratch[static_cast<size_t>(j * 2 + v) * nt + rl * c8n + c8] = acc[v][j];
+    asm volatile("bar.sync 1, %0;" ::"n"(kStConsumers) : "memory");
+    for (int k = threadIdx.x; k < C * 2; k += kStConsumers) {
+      const int c = k >> 1, v = k & 1;
+      const float* col = scratch + static_cast<size_t>((c & 7) * 2 + v) * nt + (c >> 3);
+      float sum = 0.f;
+      for (int r = 0; r < RL; ++r) sum += col[r * c8n];
+      const size_t ro = static_cast<size_t>(replica_of_block(nrep)) * C;
+      atomic_add_f64((v ? T2 : T1) + ro + c, static_cast<double>(sum));
+    }
   }
 }
 
@@ -815,7 +889,7 @@ int fmm_affine_relu(const void* X, const float* a, const float* b, void* H, int 
 
 int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const void* R, float* S1, float* S2,
                             float* S3, int N, int Tn, int V, int C, int dtype, cudaStream_t stream) {
-  FMM_CHECK_ARG(dY && Y && U && S1 && S2 && C % 8 == 0 && (!R || S3), "blockout_bwd_reduce: bad args");
+  FMM_CHECK_ARG(dY && U && S1 && S2 && C % 8 == 0 && (!R || S3), "blockout_bwd_reduce: bad args");
   const int th = rowwalk_threads(C);
   const size_t sm = (3 * C + th * 24) * sizeof(float);
   const long long rows = static_cast<long long>(N) * Tn * V;
@@ -832,7 +906,7 @@ int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* 
                       void* dPre, double* sum_dU, double* sum_dR, int nrep, int N, int Tn, int V, int C, int dtype,
                       cudaStream_t stream) {
   FMM_CHECK_ARG(nrep >= 1, "bn2_bwd_apply: nrep");
-  FMM_CHECK_ARG(dY && Y && U && k1 && k2 && k3 && dU && C % 8 == 0, "bn2_bwd_apply: bad args");
+  FMM_CHECK_ARG(dY && U && k1 && k2 && k3 && dU && C % 8 == 0, "bn2_bwd_apply: bad args");
   FMM_CHECK_ARG(!R || (r1 && r2 && r3 && dR), "bn2_bwd_apply: residual branch needs r1..r3 and dR");
   const int th = rowwalk_threads(C);
   const size_t sm = (2 * C + th * 16) * sizeof(float);
@@ -853,6 +927,17 @@ int fmm_bn1_bwd_reduce(const void* dH, const void* G, const float* a1, const flo
   const int th = rowwalk_threads(C);
   const size_t sm = (2 * C + th * 16) * sizeof(float);
   const long long rows = static_cast<long long>(N) * Tn * V;
+  static const int tma_env = getenv("FMM_EW_TMA") ? atoi(getenv("FMM_EW_TMA")) : 1;
+  if (tma_env && kStConsumers % (C / 8) == 0 && rows >= 64) {
+    FMM_DISPATCH(dtype, {
+      const int cr = stream_chunk_rows(16 * 1024, C * sizeof(T), 1);
+      const size_t smem = StreamPipe<2>::bytes(cr * C * sizeof(T)) + 64 + (2 * C + kStConsumers * 16) * sizeof(float);
+      cudaFuncSetAttribute(bn1_bwd_reduce_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      bn1_bwd_reduce_tma_kernel<T><<<num_sms(), kStThreads, smem, stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, N, Tn, V, C, nrep, cr, nullptr);
+    })
+    FMM_CHECK_LAUNCH("bn1_bwd_reduce");
+    return FMM_OK;
+  }
   FMM_DISPATCH(dtype, {
     bn1_bwd_reduce_kernel<T><<<resident_grid(bn1_bwd_reduce_kernel<T>, th, sm, rows), th, sm, stream>>>((const T*)dH, (const T*)G, a1, b1, T1, T2, N, Tn, V, C, nrep);
   })

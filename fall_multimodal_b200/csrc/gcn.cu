@@ -874,6 +874,8 @@ struct GcnBwdParams {
   int V, K, Cin, Cout, D;   // D = maximum total out-degree of a joint (slots per joint)
   int NCC, nck, FPT, ntiles;
   int n_g, n_w, resident;
+  int relu_mask;        // 1: dx is stored as dx * (x > 0) - x is the ReLU output of the previous block, so the consumer of dx
+                        // (that block's backward) reads an already masked gradient and never touches its saved output again
   unsigned* err;
 };
 
@@ -898,7 +900,7 @@ __device__ __forceinline__ void gcn_bwd_rows(const GcnBwdParams& p, uint32_t tab
     const int f = row / p.V, v = row - f * p.V;
     const size_t goff = static_cast<size_t>(r) * p.Cin + cc * 64 + pc * 8;
     uint4 xa = make_uint4(0, 0, 0, 0), ad = make_uint4(0, 0, 0, 0);
-    if (p.dcoef) xa = *reinterpret_cast<const uint4*>(X + goff);
+    if (p.dcoef || p.relu_mask) xa = *reinterpret_cast<const uint4*>(X + goff);
     if (AD) ad = *reinterpret_cast<const uint4*>(AD + goff);
     uint2 en[D];
     uint4 u[D];
@@ -934,6 +936,10 @@ __device__ __forceinline__ void gcn_bwd_rows(const GcnBwdParams& p, uint32_t tab
         d = fmaf(xf[2 * l + 1], hi, d);
       }
       dc[i][j] += d;
+    }
+    if (p.relu_mask) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) acc[l] = xf[l] > 0.f ? acc[l] : 0.f;
     }
     *reinterpret_cast<uint4*>(DX + goff) = pack8_bf16(acc);
   }
@@ -1470,9 +1476,10 @@ int fmm_gcn_pack_bwd(const float* w, void* out, int K, int Cin, int Cout, cudaSt
 }
 
 int fmm_gcn_bwd(const void* dg, const void* x, const void* addend, void* dx, const void* wpk, const int* rowptr, const int* dst,
-                const int* kk, const float* coef, const int* eid, float* dcoef, int max_out_degree, long long rows, int V, int K,
-                int Cin, int Cout, unsigned* err, cudaStream_t stream) {
+                const int* kk, const float* coef, const int* eid, float* dcoef, int relu_mask, int max_out_degree, long long rows,
+                int V, int K, int Cin, int Cout, unsigned* err, cudaStream_t stream) {
   FMM_CHECK_ARG(dg && dx && wpk && rowptr && dst && kk && coef, "gcn_bwd: null pointer");
+  FMM_CHECK_ARG(!relu_mask || x, "gcn_bwd: relu_mask needs x");
   FMM_CHECK_ARG((dcoef == nullptr) || (x && eid), "gcn_bwd: dcoef needs x and eid");
   FMM_CHECK_ARG(rows > 0 && rows < (1ll << 31) && V > 0 && V <= kGcnMaxV && K > 0 && K <= 3 && rows % V == 0, "gcn_bwd: bad shape (rows=%lld V=%d K=%d)", rows, V, K);
   FMM_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cout <= 256 && Cin <= 512, "gcn_bwd: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
@@ -1488,6 +1495,7 @@ int fmm_gcn_bwd(const void* dg, const void* x, const void* addend, void* dx, con
   p.coef = coef;
   p.eid = eid;
   p.dcoef = dcoef;
+  p.relu_mask = relu_mask ? 1 : 0;
   p.R = rows;
   p.V = V;
   p.K = K;

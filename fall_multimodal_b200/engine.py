@@ -75,6 +75,7 @@ class TrunkEngine:
         self.max_out_deg = int(max(int(rp[i + 1]) - int(rp[i]) for i in range(self.V)))
         self._wstreams = {}
         self._pstreams = {}
+        self.premask = True   # fused graph-conv backward stores dx already masked by the previous block's ReLU
 
     def csr(self, device):
         key = str(device)
@@ -310,6 +311,9 @@ class TrunkEngine:
             with torch.cuda.stream(ws):
                 return ops.wgrad(*args, **kw)
 
+        # premasked: dY already carries the ReLU mask of this block's output - the fused graph-conv backward of the block
+        # above read that output anyway (edge gradient) and stored dx * (x > 0); Y is then never read again down here
+        premasked = False
         for i in reversed(range(len(self.blocks))):
             Cin, Cout, s, reskind = self.blocks[i]
             pre = f"{self.block_key}.{i}."
@@ -324,7 +328,8 @@ class TrunkEngine:
             # ---- relu / residual / SE scale: per-(n,c) reductions of dpre = dY*(Y>0) ----
             S1, S2 = arena.f32(N, Cout), arena.f32(N, Cout)
             S3 = arena.f32(N, Cout) if R is not None else None
-            ops.blockout_bwd_reduce(dY, Y, U, R, S1, S2, S3)
+            Ym = None if premasked else Y
+            ops.blockout_bwd_reduce(dY, Ym, U, R, S1, S2, S3)
 
             # ---- SE backward (tiny) ----
             dq, dp = f32(N, Cout), f32(N, Cout)
@@ -353,10 +358,10 @@ class TrunkEngine:
             grads[pre + "tcn.3.weight"], grads[pre + "tcn.3.bias"] = dg2, db2
             dU = torch.empty_like(U)
             dR = torch.empty_like(R) if R is not None else None
-            dPre = torch.empty_like(Y) if reskind == "identity" else None
+            dPre = torch.empty_like(Y) if (reskind == "identity" and not premasked) else None
             sum_dU = arena.f64(NR * Cout)
             sum_dR = arena.f64(NR * Cout) if R is not None else None
-            ops.bn2_bwd_apply(dY, Y, U, R, k1, k2, k3, r1, r2, r3, dU, dR, dPre, sum_dU, sum_dR)
+            ops.bn2_bwd_apply(dY, Ym, U, R, k1, k2, k3, r1, r2, r3, dU, dR, dPre, sum_dU, sum_dR)
             grads[pre + "tcn.2.bias"] = sum_dU.view(NR, Cout).sum(0).float()
 
             # ---- temporal conv: wgrad + dgrad ----
@@ -410,7 +415,7 @@ class TrunkEngine:
             # ---- residual branch ----
             addend = None
             if reskind == "identity":
-                addend = dPre
+                addend = dY if premasked else dPre   # gradient of the identity shortcut = the masked dY
             elif reskind == "conv":
                 Wr = P[pre + "residual.0.weight"]
                 dWr = arena.f32(Cout, Cin, 1, 1)
@@ -423,10 +428,12 @@ class TrunkEngine:
 
             dx = torch.empty_like(x)
             coef_b = b["coef_b"]
+            mask_dx = fused_bwd and i > 0 and self.premask   # x of block i > 0 is the ReLU output of block i - 1
             if fused_bwd:
                 # P = dG.W^T stays on chip: GEMM + transposed aggregation + edge-coefficient gradient in one kernel (csrc/gcn.cu)
                 ops.gcn_bwd(dG, pp["wg_b"], dx, csr["bwd_rowptr"], csr["dst_b"],
-                            csr["kk_b"], coef_b, K, self.max_out_deg, addend=addend, x=x, eid=csr["eid_b"], dcoef=dcoef)
+                            csr["kk_b"], coef_b, K, self.max_out_deg, addend=addend, x=x, eid=csr["eid_b"], dcoef=dcoef,
+                            relu_mask=mask_dx)
             elif fused_dcoef:
                 ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K, x=x,
                             eid=csr["eid_b"], dcoef=dcoef)
@@ -441,6 +448,7 @@ class TrunkEngine:
                 self.debug[i] = dict(dY=dY, dU=dU, dH=dH, dG=dG, P=Pm, dx=dx, S1=S1, S2=S2, dp=dp, dR=dR, c1=c1, c2=c2,
                                      c3=c3, T1=T1, T2=T2, saved=b)
             dY = dx
+            premasked = mask_dx
 
         if ws is not None:
             cur.wait_stream(ws)

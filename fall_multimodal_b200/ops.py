@@ -236,8 +236,9 @@ def gcn_bwd_supported(dtype, cin: int, cout: int, V: int, K: int, max_out_degree
     return gcn_supported(dtype, cin, cout, V) and K <= 3 and max_out_degree <= 8
 
 
-def gcn_bwd(dg, wpk, dx, rowptr, dst, kk, coef, K, max_out_degree, addend=None, x=None, eid=None, dcoef=None):
-    """dx = addend + A^T-aggregate(dG . W^T) with the GEMM result kept on chip; with x/eid/dcoef also the edge-coefficient gradient."""
+def gcn_bwd(dg, wpk, dx, rowptr, dst, kk, coef, K, max_out_degree, addend=None, x=None, eid=None, dcoef=None, relu_mask=False):
+    """dx = addend + A^T-aggregate(dG . W^T) with the GEMM result kept on chip; with x/eid/dcoef also the edge-coefficient gradient.
+    relu_mask: store dx * (x > 0) (x = the previous block's ReLU output), see include/fmm_b200.h."""
     L.require_device(dg)
     N, Tn, V, Cout = dg.shape
     Cin = dx.shape[-1]
@@ -248,7 +249,7 @@ def gcn_bwd(dg, wpk, dx, rowptr, dst, kk, coef, K, max_out_degree, addend=None, 
 
     def run():
         L.check(L.load().fmm_gcn_bwd(L.ptr(dg), L.ptr(x), L.ptr(addend), L.ptr(dx), L.ptr(wpk), L.ptr(rowptr), L.ptr(dst), L.ptr(kk),
-                                     L.ptr(coef), L.ptr(eid), L.ptr(dcoef), int(max_out_degree), rows, V, K, Cin, Cout,
+                                     L.ptr(coef), L.ptr(eid), L.ptr(dcoef), int(bool(relu_mask)), int(max_out_degree), rows, V, K, Cin, Cout,
                                      L.ptr(err_word(dg.device)), L.stream()), "gcn_bwd")
         return dx
 

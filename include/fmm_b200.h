@@ -92,12 +92,14 @@ int fmm_gcn_wgrad(const void* x, const void* dg, float* dw, const int* rowptr, c
  *   dcoef[eid[e]] += sum_{f,ci} x[(f,v)][ci] * P[(f, dst e)][kk e][ci]     (gradient of A*edge_importance, stgcan.py:222)
  * GEMM on tcgen05 (N = K*64 per 64-channel slab), transposed adjacency aggregation in the epilogue. CSR over v (out-edges):
  * rowptr[V+1], dst / kk / coef / eid [E] (device); max_out_degree = largest number of out-edges of a joint (host knowledge
- * of the static graph, <= 8). addend, x/eid/dcoef nullable. `wpk` from fmm_gcn_pack_bwd. K <= 3, rows % V == 0. */
+ * of the static graph, <= 8). addend, x/eid/dcoef nullable. `wpk` from fmm_gcn_pack_bwd. K <= 3, rows % V == 0.
+ * relu_mask = 1 stores dx * (x > 0): x is the ReLU output of the previous block (stgcan.py:135), whose backward then reads an
+ * already masked gradient (fmm_blockout_bwd_reduce / fmm_bn2_bwd_apply with Y = NULL) and never re-reads its output. */
 long long fmm_gcn_packed_bwd_bytes(int K, int Cin, int Cout);
 int fmm_gcn_pack_bwd(const float* w, void* out, int K, int Cin, int Cout, cudaStream_t stream);
 int fmm_gcn_bwd(const void* dg, const void* x, const void* addend, void* dx, const void* wpk, const int* rowptr, const int* dst,
-                const int* kk, const float* coef, const int* eid, float* dcoef, int max_out_degree, long long rows, int V, int K,
-                int Cin, int Cout, unsigned* err, cudaStream_t stream);
+                const int* kk, const float* coef, const int* eid, float* dcoef, int relu_mask, int max_out_degree, long long rows,
+                int V, int K, int Cin, int Cout, unsigned* err, cudaStream_t stream);
 
 /* data_bn (stgcan.py:212-218): BatchNorm1d(V*C) over (N,T) of the clip x (N,C,T,V) fp32, channel index v*C + c, written
  * once in the channels-last (N,T,V,C) activation layout. stats -> fmm_bn_finalize(count = N*T, C = V*C) -> apply; bwd gives

@@ -160,8 +160,15 @@ def test_gcn_bwd_matches_torch(layout, N, T, Cin, Cout, with_addend):
     dcoef = torch.zeros(src.numel(), dtype=torch.float32, device=dev)
     ops.gcn_bwd(dG, ops.gcn_pack_bwd(W, K, Cin, Cout), dx, rowptr_b, dst_b, kk_b, coef_b, K, maxdeg, addend=addend, x=x, eid=eid_b,
                 dcoef=dcoef)
+    # relu_mask: the same result times (x > 0), bit for bit (x plays the previous block's ReLU output)
+    dxm = torch.full_like(dx, float("nan"))
+    dcoef2 = torch.zeros_like(dcoef)
+    ops.gcn_bwd(dG, ops.gcn_pack_bwd(W, K, Cin, Cout), dxm, rowptr_b, dst_b, kk_b, coef_b, K, maxdeg, addend=addend, x=x, eid=eid_b,
+                dcoef=dcoef2, relu_mask=True)
     torch.cuda.synchronize()
     assert int(ops.err_word(dev).item()) == 0
+    assert torch.equal(dxm, torch.where(x > 0, dx, torch.zeros_like(dx))), "relu_mask must only zero the entries where x <= 0"
+    assert (dcoef2 - dcoef).abs().max().item() <= 1e-5 * dcoef.abs().max().item()
     # reference: P rounded to bf16 (what the staging tile holds), then exact arithmetic
     Wk = W.view(K, Cout, Cin).to(torch.bfloat16).double()
     P = torch.einsum("ntwo,koc->ntwkc", dG.double(), Wk).to(torch.bfloat16).double()

@@ -124,6 +124,7 @@ _SIGNATURES = {
     "fmm_se_fwd": [_P, _P, _P, c_float, _P, _P, _P, _P, _P, _P, c_float, c_float, c_int] + [_P] * 11 +
                   [c_int, c_int, c_int, _P],
     "fmm_se_bwd": [_P] * 13 + [c_int] + [_P] * 11 + [c_int, c_int, c_int, _P],
+    "fmm_se_bwd_params": [_P] * 8 + [c_int, c_int, c_int, _P],
     "fmm_bn2_bwd_coef": [_P] * 12 + [c_float, C.c_double, c_int] + [_P] * 10 + [c_int, c_int, _P],
     "fmm_bn1_bwd_coef": [_P, _P, c_int, _P, _P, _P, C.c_double, c_int] + [_P] * 5 + [c_int, _P],
     "fmm_lstm_fwd": [_P] * 8 + [c_int] * 5 + [_P],

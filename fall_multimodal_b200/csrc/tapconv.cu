@@ -53,6 +53,10 @@ struct TapConvParams {
   int bias_smem; // > 0: this many floats of `bias` are staged in shared memory once per CTA (the epilogue's bias loads sit on
                  // the tile's critical path: a per-joint table read from global memory cost +50 % on the 1x1 graph convs)
   int res_local; // resident && 1: only the images of the CTA's own N tile (gridDim.x is a multiple of ntiles_n)
+  int mtg;       // 1: the MT M-tiles of an item are MT consecutive column GROUPS at the same 16 positions (each with its own
+                 // window), not MT consecutive 16-position chunks of one group: short clips (T <= 16) still share every weight
+                 // image between two M tiles
+  int nacc;      // TMEM accumulator stages (2; 1 when MT * BN * 2 would exceed the 512 columns)
   int dbg;       // dev experiments (FMM_TAP_DBG): 1 no window copies, 2 no stores, 4 relaxed waits, 8 no TMEM loads
   unsigned* err;
 };
@@ -80,7 +84,9 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t slot_bytes = static_cast<uint32_t>(kParts) * p.win_atoms * 1024u;
+  const uint32_t slot_bytes = static_cast<uint32_t>(kParts) * p.win_atoms * 1024u * (p.mtg ? p.MT : 1);
+  const int MTT = p.mtg ? 1 : p.MT;   // 16-position chunks per item
+  const int MTG = p.mtg ? p.MT : 1;   // column groups per item
   const uint32_t part_bytes_a = static_cast<uint32_t>(p.win_atoms) * 1024u;
   const uint32_t bstage_bytes = static_cast<uint32_t>(kParts) * p.BN * 128u / kCtas;  // this CTA's rows of one weight image
   const uint32_t part_bytes_b = static_cast<uint32_t>(p.BN) * 128u / kCtas;
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
   // every MMA; keeping the small terms out of the big accumulator cuts those truncations 6x.
   const uint32_t acc_stride = (kParts == 1 ? 1u : 2u) * static_cast<uint32_t>(p.BN) * static_cast<uint32_t>(p.MT);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * acc_stride) tmem_cols <<= 1;
+  while (tmem_cols < static_cast<uint32_t>(p.nacc) * acc_stride) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslots; ++s) {
@@ -183,30 +189,41 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       uint32_t i_ph = 0;
       // per-tile decode of the issue-side iterator, refreshed only when it moves to a new tile (the
       // integer divisions are a real cost for the 1x1 GEMMs, whose items are only 16 KB each)
-      bool i_colok = false;
+      bool i_colok[2] = {false, false};
       int i_tlo = 0;
-      const __nv_bfloat16* i_colp = Xb;
+      const __nv_bfloat16* i_colp[2] = {Xb, Xb};
       auto decode_tile = [&]() {
         const int rest = rest_of(i_tile);
         const int tchunk = rest % p.ntchunks;
-        const int group = rest / p.ntchunks;
-        const int col = group * 8 + q;
-        i_colok = col < p.ncols;
-        const int n = i_colok ? col / p.V : 0;
-        const int v = i_colok ? col - n * p.V : 0;
-        i_tlo = tchunk * 16 * p.MT * p.istride + p.minshift;
-        i_colp = Xb + static_cast<size_t>(n) * p.Tin * pitch_t + static_cast<size_t>(v) * p.Cin;
+        const int gidx = rest / p.ntchunks;
+        i_tlo = tchunk * 16 * MTT * p.istride + p.minshift;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (g < MTG) {
+            const int col = (gidx * MTG + g) * 8 + q;
+            i_colok[g] = col < p.ncols;
+            const int n = i_colok[g] ? col / p.V : 0;
+            const int v = i_colok[g] ? col - n * p.V : 0;
+            i_colp[g] = Xb + static_cast<size_t>(n) * p.Tin * pitch_t + static_cast<size_t>(v) * p.Cin;
+          }
+        }
       };
       if (i_tile < p.total_tiles) decode_tile();
       auto issue_one = [&]() {
         if (i_tile < p.total_tiles) {
           const int cb = i_c * 64 + pc * 8;
-          const bool col_ok = i_colok && cb < p.Cin;
           if (p.dbg & 4) mbar_wait_relaxed(win_empty(i_slot), i_ph ^ 1u, p.err, 1, 32); else
           mbar_wait(win_empty(i_slot), i_ph ^ 1u, p.err, 1);
-          if (!(p.dbg & 1))
-          cpasync_issue_chunk(i_colp + (col_ok ? cb : 0), pitch_t, col_ok, p.Tin, i_tlo, p.win_atoms, a0, 4,
-                              slots0 + i_slot * slot_bytes + q * 128u + ((pc ^ q) << 4));
+          if (!(p.dbg & 1)) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              if (g < MTG) {
+                const bool col_ok = i_colok[g] && cb < p.Cin;
+                cpasync_issue_chunk(i_colp[g] + (col_ok ? cb : 0), pitch_t, col_ok, p.Tin, i_tlo, p.win_atoms, a0, 4,
+                                    slots0 + i_slot * slot_bytes + static_cast<uint32_t>(g * p.win_atoms) * 1024u + q * 128u + ((pc ^ q) << 4));
+              }
+            }
+          }
           if (++i_slot == p.nslots) {
             i_slot = 0;
             i_ph ^= 1u;
@@ -225,8 +242,8 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         const int rest = rest_of(tile);
         const int tchunk = rest % p.ntchunks;
         const int group = rest / p.ntchunks;
-        const int col = group * 8 + q;
-        const int t_lo = tchunk * 16 * p.MT * p.istride + p.minshift;
+        const int col = group * 8 + q;                    // (the in-place prologue is never combined with mtg)
+        const int t_lo = tchunk * 16 * MTT * p.istride + p.minshift;
         for (int c = 0; c < p.nchunks; ++c) {
           // finish item (tile, c) FIRST and only then queue the copies of item +D: queueing needs the
           // slot the MMAs of the previous item are still reading, and waiting for it before the
@@ -302,16 +319,16 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       const int ntile = tile % p.ntiles_n;
       const int rest = rest_of(tile);
       const int tchunk = rest % p.ntchunks;
-      const int group = rest / p.ntchunks;
-      const int col = group * 8 + q;
-      const bool col_ok = col < p.ncols;
-      const int n = col_ok ? col / p.V : 0;
-      const int v = col_ok ? col % p.V : 0;
+      const int gidx = rest / p.ntchunks;
       if (p.dbg & 4) mbar_wait_relaxed(acc_full(as), aph, p.err, 2, 64); else
       mbar_wait(acc_full(as), aph, p.err, 2);
       tc_fence_after();
       for (int mt = 0; mt < ((p.dbg & 8) ? 0 : p.MT); ++mt) {
-      const int j = (tchunk * p.MT + mt) * 16 + (r >> 3);
+      const int col = (p.mtg ? gidx * p.MT + mt : gidx) * 8 + q;
+      const bool col_ok = col < p.ncols;
+      const int n = col_ok ? col / p.V : 0;
+      const int v = col_ok ? col % p.V : 0;
+      const int j = (p.mtg ? tchunk : tchunk * p.MT + mt) * 16 + (r >> 3);
       const bool row_ok = col_ok && (j < p.Tj);
       T* orow = O + (static_cast<size_t>(n) * p.Tout + (row_ok ? j * p.ostride + p.ooff : 0)) * p.V * p.Cout +
                 static_cast<size_t>(v) * p.Cout;
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
       }
       tc_fence_before();
       arrive_leader(acc_empty(as));
-      if (++as == 2) {
+      if (++as == p.nacc) {
         as = 0;
         aph ^= 1u;
       }
@@ -482,7 +499,8 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
 #pragma unroll
         for (int m = 0; m < 9; ++m) tap_lo[m] = static_cast<uint32_t>(p.shift[m] - p.minshift) * 64u;  // atoms, 16-byte units
         const uint32_t img_lo = bstage_bytes >> 4;
-        const uint32_t mt_lo = 16u * static_cast<uint32_t>(p.istride) * 64u;  // second M tile: 16 positions later
+        // second M tile: 16 positions later in the same window, or the next column group's window
+        const uint32_t mt_lo = p.mtg ? static_cast<uint32_t>(p.win_atoms) * 64u : 16u * static_cast<uint32_t>(p.istride) * 64u;
         for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
           const int ntile = p.res_local ? 0 : tile % p.ntiles_n;  // index into the resident images
           wait_x(acc_empty(as), aph ^ 1u, 4);
@@ -517,7 +535,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
               wph ^= 1u;
             }
           }
-          if (++as == 2) {
+          if (++as == p.nacc) {
             as = 0;
             aph ^= 1u;
           }
@@ -548,7 +566,8 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
                 const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(mm) * (bstage_bytes >> 4);
                 if (kParts == 1) {
                   for (uint32_t mt = 0; mt < static_cast<uint32_t>(p.MT); ++mt) {
-                    const uint32_t a_mt = a_lo + mt * a_sbo, d_mt = d_tmem + mt * p.BN;  // 16 positions = 16*a_sbo bytes = a_sbo 16-byte units
+                    // 16 positions = 16*a_sbo bytes = a_sbo 16-byte units; mtg: the next column group's window
+                    const uint32_t a_mt = a_lo + mt * (p.mtg ? static_cast<uint32_t>(p.win_atoms) * 64u : a_sbo), d_mt = d_tmem + mt * p.BN;
 #pragma unroll
                     for (uint32_t kk = 0; kk < 4; ++kk)
                       mma(d_mt, a_mt + kk * 2u, a_hi, b_lo + kk * 2u, b_hi, idesc, accum | static_cast<uint32_t>(mm) | kk);
@@ -583,7 +602,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
             wph ^= 1u;
           }
         }
-        if (++as == 2) {
+        if (++as == p.nacc) {
           as = 0;
           aph ^= 1u;
         }
@@ -761,19 +780,27 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   const bool pair = pair_env && (pair_env >= 2 || bn_probe >= 256) && dtype == FMM_DT_BF16 && ntaps > 1 && (Cin % 64) == 0 &&
                     (Cout % 32) == 0 && (num_sms() % 2) == 0;
   if (pair && bn_probe == 128) p.MT = 1;
-  p.win_atoms = (16 * p.MT - 1) * istride + (mx - mn) + 1;
+  // 256-column pairs: two column groups per item (every weight half-image feeds 2 x 4 MMAs: half the L2 -> SM weight
+  // stream, which bounds this shape) on a single 512-column accumulator stage
+  static const int mtg_env = getenv("FMM_TAP_MTG") ? atoi(getenv("FMM_TAP_MTG")) : 1;
+  p.mtg = (pair && mtg_env && bn_probe >= 256 && in_scale == nullptr) ? 1 : 0;
+  if (p.mtg) p.MT = 2;
+  p.nacc = (dtype == FMM_DT_BF16 && p.MT * bn_probe * 2 > 512) ? 1 : 2;
+  p.win_atoms = (16 * (p.mtg ? 1 : p.MT) - 1) * istride + (mx - mn) + 1;
   p.BN = pick_bn(Cout, dtype);
   p.ntiles_n = ((Cout + 31) / 32 * 32 + p.BN - 1) / p.BN;
   p.nchunks = (Cin + 63) / 64;
   p.ncols = N * V;
   p.ngroups = (p.ncols + 7) / 8;
-  p.ntchunks = (Tj + 16 * p.MT - 1) / (16 * p.MT);
-  p.total_tiles = pair ? (p.ngroups * p.ntchunks + 1) / 2 * p.ntiles_n : p.ngroups * p.ntchunks * p.ntiles_n;
+  const int mtt = p.mtg ? 1 : p.MT;
+  p.ntchunks = (Tj + 16 * mtt - 1) / (16 * mtt);
+  const int gunits = p.mtg ? (p.ngroups + p.MT - 1) / p.MT : p.ngroups;   // column-group units of one item
+  p.total_tiles = pair ? (gunits * p.ntchunks + 1) / 2 * p.ntiles_n : gunits * p.ntchunks * p.ntiles_n;
   p.err = err;
   static const int dbg_env = getenv("FMM_TAP_DBG") ? atoi(getenv("FMM_TAP_DBG")) : 0;
   p.dbg = dbg_env;
   const int nparts = dtype == FMM_DT_F32 ? 3 : 1;
-  const size_t slot_bytes = static_cast<size_t>(nparts) * p.win_atoms * 1024;
+  const size_t slot_bytes = static_cast<size_t>(nparts) * p.win_atoms * 1024 * (p.mtg ? p.MT : 1);
   const size_t bstage_bytes = static_cast<size_t>(nparts) * p.BN * 128 / (pair ? 2 : 1);  // per CTA
   // the bias table ([V][Cout] for the per-joint bias of the graph conv, else [Cout]) rides along in shared memory when small
   const size_t bias_floats = bias ? static_cast<size_t>(bias_per_joint ? V : 1) * Cout : 0;

@@ -167,9 +167,25 @@ __global__ void se_bwd_a_kernel(const float* __restrict__ S1, const float* __res
     dq[i] = v;
   }
   __syncthreads();
+  // dhr[j] = sum_c dq[c] W2[c][j]: all threads take part - (blockDim / C4) partial sums per hidden channel j, combined
+  // through shared memory (the C4 <= 64 threads x C serial steps of the first version made this a 26 us kernel)
+  float* part = sdq + C;                       // [blockDim.x]
+  const int G = C4 <= static_cast<int>(blockDim.x) ? blockDim.x / C4 : 1;
+  if (C4 <= static_cast<int>(blockDim.x)) {
+    const int j = threadIdx.x % C4, g = threadIdx.x / C4;
+    float acc = 0.f;
+    if (g < G)
+      for (int c = g; c < C; c += G) acc = fmaf(sdq[c], W2[static_cast<size_t>(c) * C4 + j], acc);
+    part[threadIdx.x] = acc;
+  }
+  __syncthreads();
   for (int j = threadIdx.x; j < C4; j += blockDim.x) {
     float acc = 0.f;
-    for (int c = 0; c < C; ++c) acc = fmaf(sdq[c], W2[static_cast<size_t>(c) * C4 + j], acc);
+    if (C4 <= static_cast<int>(blockDim.x)) {
+      for (int g = 0; g < G; ++g) acc += part[g * C4 + j];
+    } else {
+      for (int c = 0; c < C; ++c) acc = fmaf(sdq[c], W2[static_cast<size_t>(c) * C4 + j], acc);
+    }
     const float pre = fmaf(ah[j], h[static_cast<size_t>(n) * C4 + j], bh[j]);
     dhr[static_cast<size_t>(n) * C4 + j] = pre > 0.f ? acc : 0.f;
     r_out[static_cast<size_t>(n) * C4 + j] = fmaxf(pre, 0.f);
@@ -411,14 +427,28 @@ int fmm_se_bwd(const float* S1, const float* S2, const float* a2, const float* b
                float* dW1, float* db1, float* dgamma, float* dbeta, float* dW2, float* db2se, int N, int C, int C4,
                cudaStream_t stream) {
   FMM_CHECK_ARG(S1 && S2 && a2 && b2 && s && p && h && ah && bh && hmean && hrstd && W1 && W2 && dq && dhr && r && dh &&
-                    dp && dW1 && db1 && dgamma && dbeta && dW2 && db2se,
+                    dp && dgamma && dbeta,
                 "se_bwd: bad args");
-  se_bwd_a_kernel<<<N, 256, C * sizeof(float), stream>>>(S1, S2, a2, b2, s, h, ah, bh, W2, dq, dhr, r, C, C4);
+  FMM_CHECK_ARG((dW1 && db1 && dW2 && db2se) || (!dW1 && !db1 && !dW2 && !db2se), "se_bwd: dW1/db1/dW2/db2se all or none");
+  se_bwd_a_kernel<<<N, 256, (C + 256) * sizeof(float), stream>>>(S1, S2, a2, b2, s, h, ah, bh, W2, dq, dhr, r, C, C4);
   se_bwd_bn_kernel<<<C4, 128, 0, stream>>>(dhr, h, ah, hmean, hrstd, training, dh, dgamma, dbeta, N, C4);
   se_bwd_dp_kernel<<<N, 256, C4 * sizeof(float), stream>>>(dh, W1, dp, C, C4);
-  small_tn_gemm_kernel<<<C, 256, 0, stream>>>(dq, r, dW2, db2se, N, C, C4);   // dW2[c][j] = sum_n dq[n,c] r[n,j]
-  small_tn_gemm_kernel<<<C4, 256, 0, stream>>>(dh, p, dW1, db1, N, C4, C);   // dW1[j][c] = sum_n dh[n,j] p[n,c]
+  if (dW2) {
+    small_tn_gemm_kernel<<<C, 256, 0, stream>>>(dq, r, dW2, db2se, N, C, C4);   // dW2[c][j] = sum_n dq[n,c] r[n,j]
+    small_tn_gemm_kernel<<<C4, 256, 0, stream>>>(dh, p, dW1, db1, N, C4, C);   // dW1[j][c] = sum_n dh[n,j] p[n,c]
+  }
   FMM_CHECK_LAUNCH("se_bwd");
+  return FMM_OK;
+}
+
+// The two weight-gradient products of fmm_se_bwd on their own (fmm_se_bwd called with dW1 = db1 = dW2 = db2se = NULL):
+// nothing on the activation-gradient chain depends on them, so the caller can run them on a side stream.
+int fmm_se_bwd_params(const float* dq, const float* r, const float* dh, const float* p, float* dW1, float* db1, float* dW2,
+                      float* db2se, int N, int C, int C4, cudaStream_t stream) {
+  FMM_CHECK_ARG(dq && r && dh && p && dW1 && db1 && dW2 && db2se && N > 0 && C > 0 && C4 > 0, "se_bwd_params: bad args");
+  small_tn_gemm_kernel<<<C, 256, 0, stream>>>(dq, r, dW2, db2se, N, C, C4);
+  small_tn_gemm_kernel<<<C4, 256, 0, stream>>>(dh, p, dW1, db1, N, C4, C);
+  FMM_CHECK_LAUNCH("se_bwd_params");
   return FMM_OK;
 }
 

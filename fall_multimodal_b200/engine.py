@@ -311,6 +311,15 @@ class TrunkEngine:
             with torch.cuda.stream(ws):
                 return ops.wgrad(*args, **kw)
 
+        def side(fn, *args):
+            """Parameter-gradient-only launches (nothing downstream in this step reads them): off the activation chain."""
+            if ws is None:
+                return fn(*args)
+            ws.wait_stream(cur)
+            keep.append(args)
+            with torch.cuda.stream(ws):
+                return fn(*args)
+
         # premasked: dY already carries the ReLU mask of this block's output - the fused graph-conv backward of the block
         # above read that output anyway (edge gradient) and stored dx * (x > 0); Y is then never read again down here
         premasked = False
@@ -337,8 +346,9 @@ class TrunkEngine:
             dW1, db1, dgh, dbh = arena.f32(C4, Cout), arena.f32(C4), arena.f32(C4), arena.f32(C4)
             dW2, db2se = arena.f32(Cout, C4), arena.f32(Cout)
             ops.se_bwd(S1, S2, b["a2"], b["b2"], b["s"], b["p"], b["h"], b["ah"], b["bh"], b["hmean"], b["hrstd"],
-                       P[ca + "1.weight"], P[ca + "4.weight"], training, dq, dhr, r_, dh, dp, dW1, db1, dgh, dbh,
-                       dW2, db2se)
+                       P[ca + "1.weight"], P[ca + "4.weight"], training, dq, dhr, r_, dh, dp, None, None, dgh, dbh,
+                       None, None)
+            side(ops.se_bwd_params, dq, r_, dh, b["p"], dW1, db1, dW2, db2se)
             grads[ca + "1.weight"] = dW1.view(C4, Cout, 1, 1)
             grads[ca + "1.bias"] = db1
             grads[ca + "2.weight"] = dgh
@@ -441,7 +451,7 @@ class TrunkEngine:
                 ops.agg_bwd(Pm, addend, dx, csr["bwd_rowptr"], csr["dst_b"], csr["kk_b"], coef_b, K)
             # d(conv bias) and d(edge importance) from the per-joint sums of dG and the per-edge sums: one launch
             dbg, dimp = arena.f32(K * Cout), arena.f32(K, V, V)
-            ops.gcn_prep_bwd(A, P[pre + "gcn.conv.bias"], b["colsum"], TblR, dcoef, csr["dense_idx"], dbg, dimp)
+            side(ops.gcn_prep_bwd, A, P[pre + "gcn.conv.bias"], b["colsum"], TblR, dcoef, csr["dense_idx"], dbg, dimp)
             grads[pre + "gcn.conv.bias"] = dbg
             grads[f"edge_importance.{i}"] = dimp
             if self.debug is not None:

@@ -386,6 +386,14 @@ def se_bwd(S1, S2, a2, b2, s, p, h, ah, bh, hmean, hrstd, W1, W2, training, dq, 
             "se_bwd")
 
 
+def se_bwd_params(dq, r, dh, p, dW1, db1, dW2, db2se):
+    """The weight-gradient products of the SE block (after `se_bwd(..., dW1=None, db1=None, dW2=None, db2se=None)`)."""
+    N, C = dq.shape
+    C4 = dh.shape[1]
+    L.check(L.load().fmm_se_bwd_params(L.ptr(dq), L.ptr(r), L.ptr(dh), L.ptr(p), L.ptr(dW1), L.ptr(db1), L.ptr(dW2),
+                                       L.ptr(db2se), N, C, C4, L.stream()), "se_bwd_params")
+
+
 def bn2_bwd_coef(S1, S2, S3, pool, dp, s, a2, mean2, rstd2, ar, meanr, rstdr, M, count, training, k1, k2, k3, r1,
                  r2, r3, dgamma2, dbeta2, dgammar, dbetar):
     N, C = S1.shape

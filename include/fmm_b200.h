@@ -222,6 +222,11 @@ int fmm_se_bwd(const float* S1, const float* S2, const float* a2, const float* b
                const float* W1, const float* W2, int training, float* dq, float* dhr, float* r, float* dh, float* dp,
                float* dW1, float* db1, float* dgamma, float* dbeta, float* dW2, float* db2se, int N, int C, int C4,
                cudaStream_t stream);
+/* The two weight-gradient products of fmm_se_bwd on their own (call fmm_se_bwd with dW1 = db1 = dW2 = db2se = NULL first):
+ * dW2[c][j] += sum_n dq[n,c] r[n,j], db2se[c] += sum_n dq[n,c]; dW1[j][c] += sum_n dh[n,j] p[n,c], db1[j] += sum_n dh[n,j]
+ * (channel_attention_module.atten.4 / .1 of stgcan.py:63-70). Nothing on the activation-gradient chain depends on them. */
+int fmm_se_bwd_params(const float* dq, const float* r, const float* dh, const float* p, float* dW1, float* db1, float* dW2,
+                      float* db2se, int N, int C, int C4, cudaStream_t stream);
 int fmm_bn2_bwd_coef(const float* S1, const float* S2, const float* S3, const float* pool, const float* dp,
                      const float* s, const float* a2, const float* mean2, const float* rstd2, const float* ar,
                      const float* meanr, const float* rstdr, float M, double count, int training, float* k1, float* k2,

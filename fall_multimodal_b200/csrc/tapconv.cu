@@ -806,7 +806,9 @@ int fmm_tapconv(const void* x, void* out, const void* wpk, const float* in_scale
   const size_t bias_floats = bias ? static_cast<size_t>(bias_per_joint ? V : 1) * Cout : 0;
   p.bias_smem = (bias_floats > 0 && bias_floats * 4 <= 36 * 1024 && (Cout % 4) == 0) ? static_cast<int>(bias_floats) : 0;
   const size_t bias_bytes = (static_cast<size_t>(p.bias_smem) * 4 + 15) / 16 * 16;
-  const size_t budget = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers*/ - bias_bytes;
+  // shared-memory budget (FMM_TAP_SMEM_KB caps it: leaving a few KB lets small kernels of another stream share the SM)
+  static const int smem_kb = getenv("FMM_TAP_SMEM_KB") ? atoi(getenv("FMM_TAP_SMEM_KB")) : 227;
+  const size_t budget = static_cast<size_t>(smem_kb) * 1024 - 1024 /*align*/ - 2048 /*barriers*/ - bias_bytes;
   // Weights: keep every image resident when they fit next to >= 3 window slots (no per-tap barrier
   // round trips at all); otherwise stream them through as deep a ring as fits beside 4 slots.
   const int nimg = p.ntiles_n * p.nchunks * ntaps;

@@ -375,7 +375,8 @@ int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, c
   const int nparts = dtype == FMM_DT_F32 ? 3 : 1;
   const int cout64 = (Cout + 63) / 64 * 64;
   if (nparts == 1) {
-    p.JT = 16;
+    static const int kWgJt = getenv("FMM_WG_JT") ? atoi(getenv("FMM_WG_JT")) : 16;
+    p.JT = (ntaps > 1 && Cin > 64) ? kWgJt : 16;
     p.MCH = Cin > 64 ? 2 : 1;
     // multi-tap: the accumulators of a tap group share TMEM (TG * BN <= 512). N = 64 MMAs run at ~57 cycles (shared-memory
     // bound, floor 32); N = 128 runs at its 64-cycle floor, so wide layers take 128-column tiles (4 taps per group)
@@ -417,7 +418,8 @@ int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, c
   const size_t b_bytes = static_cast<size_t>(nparts) * (p.BN / 64) * p.JT * 1024;
   const size_t stage = a_bytes + b_bytes + 1024;
   const size_t budget = 227 * 1024 - 1024 - 256;
-  int ns = 3;
+  static const int kWgNsMax = getenv("FMM_WG_NS_MAX") ? atoi(getenv("FMM_WG_NS_MAX")) : 3;
+  int ns = kWgNsMax;
   while (ns > 1 && ns * stage > budget) --ns;
   FMM_CHECK_ARG(ns * stage <= budget, "wgrad: stage does not fit shared memory (%zu bytes)", stage);
   p.nstages = ns;

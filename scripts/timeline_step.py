@@ -59,8 +59,8 @@ import collections
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in ev:
     n = e["name"].split("(")[0][:70]; agg[n][0] += 1; agg[n][1] += e["dur"]
-for n, (c, d) in sorted(agg.items(), key=lambda x: -x[1][1])[:24]:
-    print(f"  {d:8.0f} us {c:4d}x  {n}")
+for n, (c, d) in sorted(agg.items(), key=lambda x: -x[1][1])[:70]:
+    print(f"  {d:8.0f} us {c:4d}x  avg {d/c:6.1f}  {n}")
 # biggest gaps without any GEMM-class kernel
 gaps = []
 cur = t0

@@ -349,6 +349,8 @@ class Model(nn.Module):
     """``Model(num_class, num_point, max_frame, graph, bias, edge, block_size, embed_dim=32, n_stage=2, act_type='relu')``
     (musa_model.py:492-545); ``forward(x[N,3,T,V]) -> (N,num_class)``."""
 
+    _sep_tcn_tail = True   # Ablation (musa_model.py:593-686): the same two streams without the closing Sep_TCN
+
     def __init__(self, num_class, num_point, max_frame, graph, bias, edge, block_size, embed_dim=32, n_stage=2, act_type="relu"):
         super().__init__()
         self.num_classes = num_class
@@ -365,11 +367,13 @@ class Model(nn.Module):
                         SepTemporal_Block(embed_dim * 2, tw, bias, act_type, edge, A, num_point, keep_prob, block_size, 0, stride=1),
                         SepTemporal_Block(embed_dim * 2, tw + 2, bias, act_type, edge, A, num_point, keep_prob, block_size, 0, stride=2)]
             embed_dim *= 2
-        pos += [Sep_TCN(embed_dim, embed_dim * 2)]
-        mot += [Sep_TCN(embed_dim, embed_dim * 2)]
+        if self._sep_tcn_tail:
+            pos += [Sep_TCN(embed_dim, embed_dim * 2)]
+            mot += [Sep_TCN(embed_dim, embed_dim * 2)]
+            embed_dim *= 2
         self.stream_pos = nn.Sequential(*pos)
         self.stream_mot = nn.Sequential(*mot)
-        self.fc = Classification_Module(embed_dim * 4 + 3, num_class)
+        self.fc = Classification_Module(embed_dim * 2 + 3, num_class)       # :545 (embed_dim*4+3) / :643 (embed_dim*2+3)
         self.compute_dtype = None
 
     def forward(self, x):
@@ -386,3 +390,11 @@ class Model(nn.Module):
             feat = torch.cat([_Pool.apply(out), _Pool.apply(out2), x.float().flatten(2).mean(2)], dim=-1)   # :574-585
             y = self.fc(feat)
         return y.to(dt) if dt == torch.bfloat16 else y
+
+
+class Ablation(Model):
+    """``Ablation(...)`` (musa_model.py:593-686): `Model` without the two closing ``Sep_TCN`` stages - the pooled features are
+    the outputs of the last ``SepTemporal_Block`` of each stream, the classifier sees ``2 * C + 3`` features. Same constructor
+    arguments, state_dict keys and forward signature as the reference class."""
+
+    _sep_tcn_tail = False

@@ -220,9 +220,9 @@ def main_tragcn():
     print("targcn_v25_t16_autocast loss", float(loss.detach()))
 
 
-def main_musa():
-    """musa Model of Multimodal_Fall3/main.py:307-320: train step with DropBlock / Dropout switched off
-    (keep_prob = 1, p = 0: the random masks are the only thing that cannot be pinned) + eval logits."""
+def main_musa(cls_name="Model", out_name="musa_coco_uniform.pt"):
+    """musa Model (and Ablation, musa_model.py:593-686) of Multimodal_Fall3/main.py:307-320: train step with
+    DropBlock / Dropout switched off (keep_prob = 1, p = 0: the random masks are the only thing that cannot be pinned) + eval logits."""
     import warnings
     from oracle import musa_oracle as MO
     torch.set_num_threads(4)
@@ -230,8 +230,8 @@ def main_musa():
     c = dict(N=8, T=30, V=14, fill_seed=3, batch_seed=13)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        mod = mm.Model(num_class=11, num_point=14, max_frame=300, graph=mm.adjGraph(layout="coco_cut", strategy="uniform"),
-                       bias=True, edge=True, block_size=41, embed_dim=64, n_stage=1, act_type="tanh")
+        mod = getattr(mm, cls_name)(num_class=11, num_point=14, max_frame=300, graph=mm.adjGraph(layout="coco_cut", strategy="uniform"),
+                                    bias=True, edge=True, block_size=41, embed_dim=64, n_stage=1, act_type="tanh")
     sd = mod.state_dict()
     shapes = {k: tuple(v.shape) for k, v in sd.items()}
     sd.update(MO.fill_musa(shapes, c["fill_seed"]))
@@ -259,8 +259,8 @@ def main_musa():
         else:
             ref32_err[k] = float((a["vals"].double() - b["vals"].double()).abs().max())
     torch.save({"config": c, "shapes": shapes, "A": sd["stream_pos.0.A"].clone(), "n_params": sum(p.numel() for p in mod.parameters()),
-                "ref32_logits": res32["logits"], "ref32_grad_abs_err": ref32_err, **res}, os.path.join(OUT, "musa_coco_uniform.pt"))
-    print("musa loss", res["loss"])
+                "ref32_logits": res32["logits"], "ref32_grad_abs_err": ref32_err, **res}, os.path.join(OUT, out_name))
+    print("musa", cls_name, "loss", res["loss"])
 
 
 def main_notebook():
@@ -293,6 +293,8 @@ if __name__ == "__main__":
         main_tragcn()
     elif sys.argv[1:] == ["musa"]:
         main_musa()
+    elif sys.argv[1:] == ["musa_ablation"]:
+        main_musa("Ablation", "musa_ablation_coco_uniform.pt")
     else:
         main()
         main_tragcn()

@@ -51,24 +51,24 @@ def sep_tcn(x, sd, p, training):
     return _dws(_dws(x, sd, p + "sep31.", training, 3), sd, p + "sep11.", training, 1) + res                            # :469-474
 
 
-def stream(x, sd, p, training, act, n_stage):
+def stream(x, sd, p, training, act, n_stage, tail=True):
     i = 0
     for _ in range(n_stage):
         x = spatial_graph_conv(x, sd, f"{p}{i}.", training, act)
         x = sep_temporal_block(x, sd, f"{p}{i + 1}.", training, act, 3, 1)
         x = sep_temporal_block(x, sd, f"{p}{i + 2}.", training, act, 5, 2)
         i += 3
-    return sep_tcn(x, sd, f"{p}{i}.", training)
+    return sep_tcn(x, sd, f"{p}{i}.", training) if tail else x
 
 
-def musa_forward(sd, x, training=False, act="tanh", n_stage=1):
-    """Model.forward (:547-591); x (N,3,T,V) -> (N,num_class)."""
+def musa_forward(sd, x, training=False, act="tanh", n_stage=1, ablation=False):
+    """Model.forward (:547-591) / Ablation.forward (:646-686: no closing Sep_TCN); x (N,3,T,V) -> (N,num_class)."""
     N = x.shape[0]
     mot = x[:, :2, :-1] - x[:, :2, 1:]                                                                                  # :549
     pos = torch.relu(F.conv2d(x, sd["joint_embed_pos.cnn.0.cnn.weight"], sd["joint_embed_pos.cnn.0.cnn.bias"]))
     mo = torch.relu(F.conv2d(mot, sd["joint_embed_mos.cnn.0.cnn.weight"], sd["joint_embed_mos.cnn.0.cnn.bias"]))
-    out = stream(pos, sd, "stream_pos.", training, act, n_stage)
-    out2 = stream(mo, sd, "stream_mot.", training, act, n_stage)
+    out = stream(pos, sd, "stream_pos.", training, act, n_stage, tail=not ablation)
+    out2 = stream(mo, sd, "stream_mot.", training, act, n_stage, tail=not ablation)
     feat = torch.cat([out.flatten(2).mean(2), out2.flatten(2).mean(2), x.flatten(2).mean(2)], dim=-1)                  # :574-585
     h = F.leaky_relu(F.linear(feat, sd["fc.seq.0.weight"], sd["fc.seq.0.bias"]))
     h = F.leaky_relu(F.layer_norm(h, (h.shape[-1],), sd["fc.seq.2.weight"], sd["fc.seq.2.bias"]))

@@ -18,15 +18,24 @@ for row in csv.DictReader(lines):
     per[row["ID"]][m] = v
 
 
+# keep only the last complete train step: the launches after the second-to-last optimizer kernel up to the last one
+ids = sorted(per, key=int)
+opt = [i for i in ids if "rmsprop_kernel" in per[i]["name"]]
+if len(opt) >= 2:
+    lo, hi = int(opt[-2]), int(opt[-1])
+    per = {i: per[i] for i in ids if lo < int(i) <= hi}
+    print(f"last step: launches {lo + 1}..{hi} ({len(per)} kernels)")
+
+
 def klass(name):
     if "gcn_fwd_kernel" in name: return "gcn_fwd"
     if "gcn_wgrad_kernel" in name: return "gcn_wgrad"
     if "gcn_bwd_kernel" in name: return "gcn_bwd"
-    def last_arg(n, key):      # "...kernel<__nv_bfloat16, 8, 1>(...)": the class flag is the last template argument (1 / true)
-        a = n.split(key + "<", 1)[1].split(">", 1)[0].split(",")[-1].strip()
+    def arg(n, key, i):        # "...tapconv_kernel<__nv_bfloat16, 8, 1, 0>(...)": kTaps is template argument i (1 / true)
+        a = n.split(key + "<", 1)[1].split(">", 1)[0].split(",")[i].strip()
         return a in ("1", "true", "(bool)1")
-    if "fmm::tapconv_kernel<" in name: return "tapconv_taps" if last_arg(name, "tapconv_kernel") else "tapconv_1x1"
-    if "fmm::wgrad_kernel<" in name: return "wgrad_taps" if last_arg(name, "wgrad_kernel") else "wgrad_1x1"
+    if "fmm::tapconv_kernel<" in name: return "tapconv_taps" if arg(name, "tapconv_kernel", 2) else "tapconv_1x1"
+    if "fmm::wgrad_kernel<" in name: return "wgrad_taps" if arg(name, "wgrad_kernel", 1) else "wgrad_1x1"
     return None
 
 

@@ -12,10 +12,10 @@ from tests.golden_util import load
 gpu = pytest.mark.gpu
 
 
-def _build(fx, dev):
-    from fall_multimodal_b200.musa import Model, adjGraph
-    m = Model(num_class=11, num_point=14, max_frame=300, graph=adjGraph(layout="coco_cut", strategy="uniform"), bias=True,
-              edge=True, block_size=41, embed_dim=64, n_stage=1, act_type="tanh")
+def _build(fx, dev, ablation=False):
+    from fall_multimodal_b200.musa import Ablation, Model, adjGraph
+    m = (Ablation if ablation else Model)(num_class=11, num_point=14, max_frame=300, graph=adjGraph(layout="coco_cut", strategy="uniform"), bias=True,
+                                          edge=True, block_size=41, embed_dim=64, n_stage=1, act_type="tanh")
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     assert shapes == fx["shapes"]
     assert torch.allclose(m.state_dict()["stream_pos.0.A"], fx["A"].float(), atol=1e-7)
@@ -66,11 +66,12 @@ def test_dwconv_and_bn_act_against_torch():
 
 
 @gpu
-def test_musa_model_matches_reference_fixture():
-    fx = load("musa_coco_uniform")
+@pytest.mark.parametrize("name,ablation", [("musa_coco_uniform", False), ("musa_ablation_coco_uniform", True)])
+def test_musa_model_matches_reference_fixture(name, ablation):
+    fx = load(name)
     c = fx["config"]
     dev = torch.device("cuda:0")
-    m = _build(fx, dev).train()
+    m = _build(fx, dev, ablation).train()
     for mod in m.modules():
         if hasattr(mod, "keep_prob"):
             mod.keep_prob = 1                      # the fixture switches the random DropBlock / Dropout off
@@ -107,7 +108,7 @@ def test_musa_model_matches_reference_fixture():
         ev = m(skel.to(dev))
     # the train step above moved the running statistics: compare eval against the oracle on the CURRENT state
     sd = {k: v.detach().cpu().double() if v.is_floating_point() else v.cpu() for k, v in m.state_dict().items()}
-    evo = MO.musa_forward(sd, skel.double(), training=False)
+    evo = MO.musa_forward(sd, skel.double(), training=False, ablation=ablation)
     assert (ev.double().cpu() - evo).abs().max().item() / evo.abs().max().item() < 1e-4
 
 

@@ -21,6 +21,7 @@
 // The same file holds the weight-gradient twin (gcn_wgrad): dW[k*Cout+co][ci] = sum_r dG[r][co] * A_k[r][ci] with the
 // aggregated operand re-derived in the prologue by the same producer code, so the backward pass needs no saved copy of it.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -625,6 +626,440 @@ gcn_fwd_kernel(const __grid_constant__ GcnFwdParams p, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   if (warp == kGcnProducerWarps + kGcnEpiWarps + 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gcn_fwd, tensor-core aggregation (Cout <= 128, K*V <= 128, V <= 48).
+//
+// The CUDA-core producers of gcn_fwd_kernel issue ~514 instructions per warp and tile, 10 % of them FMAs (ncu r02): the kernel
+// is issue bound on the adjacency product although that product is 20-190x cheaper in FLOPs than the channel mix. Here the
+// adjacency product runs on the tensor core as well: per frame f and 64-channel slab,
+//     Xa_f[(k,w)][c] = sum_v A_hat[(k,w)][v] * x_f[v][c]
+// is three tcgen05 MMAs (M = 128 lanes = (partition k, target joint w), N = 64 channels, K = V padded to 48): A operand = the
+// adjacency `A_hat` as a constant K-major image (bf16 coefficients, built once per CTA from the edge table), B operand = the frame
+// as TMA delivered it ([v][64 ch] rows = the MMA's K index: an MN-major operand), D = a 64-column TMEM buffer. Four converter
+// warps (one TMEM lane each) round lane (k,w) to bf16 and store it as row (f,w) of operand image k of the channel GEMM, which
+// then runs exactly as in gcn_fwd_kernel (same weight images, epilogue, statistics, TMA store).
+//
+// Roles (15 warps): 0-3 converters, 4-11 epilogue (two groups, one per accumulator stage), 12 frame loader (TMA), 13 weight
+// loader, 14 aggregation MMA issuer + TMEM allocator, 15 channel-GEMM MMA issuer.
+// ------------------------------------------------------------------------------------------
+constexpr int kTcConvWarps = 4;
+constexpr int kTcThreads = (kTcConvWarps + kGcnEpiWarps + 4) * 32;
+constexpr int kTcFrameRows = 48;                       // K extent of the aggregation MMA (rows V..47 of a region stay zero)
+constexpr uint32_t kTcFrameBytes = kTcFrameRows * 128u;
+constexpr int kTcMaxFrames = 8;                        // frames a 128-row tile can touch (V >= 19)
+
+struct GcnTcParams {
+  GcnFwdParams f;
+  int FB;          // frames per batch: one barrier round trip, FB x 3 aggregation MMAs, FB TMEM buffers of 64 columns
+  int n_fr;        // batch stages in the frame ring (FB regions each)
+  int n_grp;       // operand-image groups (K images each)
+  int nf_max;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gcn_fwd_tc_kernel(const __grid_constant__ GcnTcParams q, const __grid_constant__ CUtensorMap tm_xf,
+                  const __grid_constant__ CUtensorMap tm_g) {
+  const GcnFwdParams& p = q.f;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t ahat0 = base;                                                  // [128][64] bf16 K-major SW128
+  const uint32_t fr0 = ahat0 + kGcnChunkBytes;                                  // frame ring
+  const uint32_t a0 = fr0 + q.n_fr * q.FB * kTcFrameBytes;                      // operand images: [group][k] x 16 KB
+  const uint32_t b0 = a0 + q.n_grp * p.K * kGcnChunkBytes;                      // weight images
+  const uint32_t stg0 = b0 + p.n_b * b_bytes;                                   // staging, one [32][64] bf16 tile per epilogue warp
+  const uint32_t bias0 = stg0 + static_cast<uint32_t>(kGcnEpiWarps) * 4096u;
+  const uint32_t bias_bytes = (p.bias ? static_cast<uint32_t>(p.V * p.Cout) * 4u : 0u);
+  const uint32_t bars0 = (bias0 + bias_bytes + 15u) & ~15u;
+  auto fr_full = [&](int s) { return bars0 + 8u * s; };
+  auto fr_empty = [&](int s) { return bars0 + 8u * (q.n_fr + s); };
+  const uint32_t bars1 = bars0 + 16u * q.n_fr;
+  auto agg_full = [&](int s) { return bars1 + 8u * s; };
+  auto agg_empty = [&](int s) { return bars1 + 8u * (2 + s); };
+  auto a_full = [&](int s) { return bars1 + 8u * (4 + s); };
+  auto a_empty = [&](int s) { return bars1 + 8u * (4 + q.n_grp + s); };
+  const uint32_t bars2 = bars1 + 8u * (4 + 2 * q.n_grp);
+  auto b_full = [&](int s) { return bars2 + 8u * s; };
+  auto b_empty = [&](int s) { return bars2 + 8u * (p.n_b + s); };
+  auto acc_full = [&](int s) { return bars2 + 8u * (2 * p.n_b + s); };
+  auto acc_empty = [&](int s) { return bars2 + 8u * (2 * p.n_b + 2 + s); };
+  const uint32_t tmem_slot = bars2 + 8u * (2 * p.n_b + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int kEpi0 = kTcConvWarps, kLoadW = kTcConvWarps + kGcnEpiWarps, kWgtW = kLoadW + 1, kAggW = kLoadW + 2, kMmaW = kLoadW + 3;
+  const uint32_t tmem_cols = 512;   // 2 x BN accumulator columns + 2 x FB x 64 aggregation columns
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < q.n_fr; ++s) {
+      mbar_init(fr_full(s), 1);
+      mbar_init(fr_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(agg_full(s), 1);
+      mbar_init(agg_empty(s), kTcConvWarps * 32);
+    }
+    for (int s = 0; s < q.n_grp; ++s) {
+      mbar_init(a_full(s), kTcConvWarps * 32);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < p.n_b; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kAggW) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp == kLoadW && lane == 0) {
+    tma_prefetch_desc(&tm_xf);
+    tma_prefetch_desc(&tm_g);
+  }
+  // zero A_hat and the frame ring (rows V..47 of every region are never written again), then scatter the coefficients
+  for (uint32_t i = threadIdx.x; i < (kGcnChunkBytes + q.n_fr * q.FB * kTcFrameBytes) / 16u; i += blockDim.x)
+    sts128g(ahat0 + 16u * i, make_uint4(0, 0, 0, 0));
+  for (int i = threadIdx.x; i < (p.bias ? p.V * p.Cout : 0); i += blockDim.x) {
+    const int v = i / p.Cout, c = i - v * p.Cout;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias0 + 4u * (((c >> 2) * p.V + v) * 4 + (c & 3))), "f"(p.bias[i]) : "memory");
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < p.K * p.V; l += blockDim.x) {   // row l = (k, w): its in-edges (CSR over (k, w))
+    for (int e = p.rowptr[l]; e < p.rowptr[l + 1]; ++e) {
+      const uint32_t v = static_cast<uint32_t>(p.src[e]);
+      const __nv_bfloat16 c = __float2bfloat16_rn(p.coef[e]);
+      const uint32_t addr = ahat0 + static_cast<uint32_t>(l) * 128u + (((v >> 3) ^ (static_cast<uint32_t>(l) & 7u)) << 4) + (v & 7u) * 2u;
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__bfloat16_as_ushort(c)) : "memory");
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tmem_agg = tmem_base + 2u * static_cast<uint32_t>(p.BN);
+
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  const int nchunk = p.NCC * p.K;
+  const long long nframes = p.R / p.V;
+  // frames touched by a tile: f0 = r0 / V .. f1 = min(last row, R-1) / V
+  auto frames_of = [&](int tile, int& f0, int& nf) {
+    const long long r0 = static_cast<long long>(tile) * kGcnTileRows;
+    long long r1 = r0 + kGcnTileRows - 1;
+    if (r1 > p.R - 1) r1 = p.R - 1;
+    f0 = static_cast<int>(r0 / p.V);
+    nf = static_cast<int>(r1 / p.V) - f0 + 1;
+  };
+
+  if (warp < kTcConvWarps) {
+    // ------------------------------ converters: TMEM lane (k,w) -> row (f,w) of operand image k ------------------------------
+    const int l = warp * 32 + lane;
+    const bool lane_ok = l < p.K * p.V;
+    const int k = lane_ok ? l / p.V : 0, w = lane_ok ? l - k * p.V : 0;
+    int ab = 0, grp = 0;
+    uint32_t abph = 0, gph = 0;
+    for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
+      int f0, nf;
+      frames_of(tile, f0, nf);
+      const long long r0 = static_cast<long long>(tile) * kGcnTileRows;
+      for (int cc = 0; cc < p.NCC; ++cc) {
+        mbar_wait_relaxed(a_empty(grp), gph ^ 1u, p.err, 2, 20);
+        const uint32_t img = a0 + static_cast<uint32_t>(grp * p.K + k) * kGcnChunkBytes;
+        for (int j = 0; j < nf; ++j) {
+          const int fi = j % q.FB;
+          if (fi == 0) {
+            mbar_wait_relaxed(agg_full(ab), abph, p.err, 1, 20);
+            tc_fence_after();
+          }
+          const bool last_of_batch = fi == q.FB - 1 || j == nf - 1;
+          const long long tr = static_cast<long long>(f0 + j) * p.V + w - r0;
+          const bool row_ok = lane_ok && tr >= 0 && tr < kGcnTileRows;
+          const uint32_t taddr = tmem_agg + static_cast<uint32_t>(ab * q.FB + fi) * 64u + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t vv[32];
+            tmem_ld32(taddr + h * 32, vv);
+            tmem_ld_wait();
+            if (h == 1 && last_of_batch) {
+              tc_fence_before();
+              mbar_arrive(agg_empty(ab));   // the whole batch is in registers / stored
+            }
+            if (row_ok) {
+              const uint32_t row = static_cast<uint32_t>(tr);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(vv[g * 8 + i]);
+                sts128g(img + row * 128u + ((static_cast<uint32_t>(h * 4 + g) ^ (row & 7u)) << 4), pack8_bf16(f));
+              }
+            }
+          }
+          if (last_of_batch && ++ab == 2) {
+            ab = 0;
+            abph ^= 1u;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(a_full(grp));
+        if (++grp == q.n_grp) {
+          grp = 0;
+          gph ^= 1u;
+        }
+      }
+    }
+  } else if (warp < kEpi0 + kGcnEpiWarps) {
+    // ---------------------------------- epilogue (as gcn_fwd_kernel) ----------------------------------
+    const int ew = warp - kEpi0;
+    const int quad = ew & 3, grp = ew >> 2;
+    const uint32_t stg = stg0 + static_cast<uint32_t>(ew) * 4096u;
+    const bool stats = p.ch_sum != nullptr;
+    const int npass = p.BN / 64;
+    float st[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) st[a][b] = 0.f;
+    uint32_t acph = 0;
+    int it = 0;
+    for (int tile = first_tile; tile < p.ntiles; tile += tile_step, ++it) {
+      if ((it & 1) != grp) continue;
+      const long long r0 = static_cast<long long>(tile) * kGcnTileRows;
+      const long long r = r0 + quad * 32 + lane;
+      const bool row_ok = r < p.R;
+      const int w = static_cast<int>((row_ok ? r : 0) % p.V);
+      mbar_wait_relaxed(acc_full(grp), acph, p.err, 3, 20);
+      acph ^= 1u;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(grp) * static_cast<uint32_t>(p.BN) + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll
+      for (int c64 = 0; c64 < 2; ++c64) {
+        if (c64 < npass) {
+          const bool prof = g_wait_prof_enable != 0;
+          long long tq = prof ? clock64() : 0;
+          if (lane == 0) tma_wait_read<0>();
+          __syncwarp();
+          if (prof && lane == 0) { const long long t = clock64(); atomicAdd(&g_wait_prof[20], static_cast<unsigned long long>(t - tq)); tq = t; }
+          const uint32_t srow = stg + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t vv[32];
+            tmem_ld32(taddr + c64 * 64 + h * 32, vv);
+            tmem_ld_wait();
+            if (h == 1 && c64 == npass - 1) {
+              tc_fence_before();
+              mbar_arrive(acc_empty(grp));
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(vv[g * 8 + i]);
+              if (p.bias) {
+                const int co = c64 * 64 + h * 32 + g * 8;
+                const uint4 ba = lds128(bias0 + 16u * static_cast<uint32_t>((co >> 2) * p.V + w));
+                const uint4 bb = lds128(bias0 + 16u * static_cast<uint32_t>(((co >> 2) + 1) * p.V + w));
+                f[0] += __uint_as_float(ba.x); f[1] += __uint_as_float(ba.y); f[2] += __uint_as_float(ba.z); f[3] += __uint_as_float(ba.w);
+                f[4] += __uint_as_float(bb.x); f[5] += __uint_as_float(bb.y); f[6] += __uint_as_float(bb.z); f[7] += __uint_as_float(bb.w);
+              }
+              if (!row_ok) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = 0.f;
+              }
+              sts128g(srow + ((static_cast<uint32_t>(h * 4 + g) ^ (static_cast<uint32_t>(lane) & 7u)) << 4), pack8_bf16(f));
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (prof && lane == 0) { const long long t = clock64(); atomicAdd(&g_wait_prof[21], static_cast<unsigned long long>(t - tq)); tq = t; }
+          if (lane == 0) {
+            tma_store_2d(&tm_g, c64 * 64, static_cast<int>(r0) + quad * 32, stg);
+            tma_commit();
+          }
+          if (stats) {
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const uint32_t piece = static_cast<uint32_t>(lane) >> 2, word = (static_cast<uint32_t>(lane) & 3u) * 4u;
+#pragma unroll 8
+            for (uint32_t rr = 0; rr < 32; ++rr) {
+              const uint32_t u = lds32(stg + rr * 128u + ((piece ^ (rr & 7u)) << 4) + word);
+              const float lo = __uint_as_float(u << 16), hi = __uint_as_float(u & 0xffff0000u);
+              s0 += lo; s1 += hi;
+              q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+            }
+            st[c64][0] += s0; st[c64][1] += q0; st[c64][2] += s1; st[c64][3] += q1;
+          }
+          if (prof && lane == 0) atomicAdd(&g_wait_prof[22], static_cast<unsigned long long>(clock64() - tq));
+        }
+      }
+    }
+    if (lane == 0) tma_wait_read<0>();
+    __syncwarp();
+    if (stats) {
+#pragma unroll
+      for (int c64 = 0; c64 < 2; ++c64)
+        if (c64 < npass)
+          sts128g(stg + 8u * static_cast<uint32_t>(c64 * 64 + 2 * lane),
+                  make_uint4(__float_as_uint(st[c64][0]), __float_as_uint(st[c64][1]), __float_as_uint(st[c64][2]), __float_as_uint(st[c64][3])));
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int t = threadIdx.x - kEpi0 * 32;  // 0..255
+      const int rep = blockIdx.x % p.nrep;
+      for (int c = t; c < p.BN && c < p.Cout; c += kGcnEpiWarps * 32) {
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < kGcnEpiWarps; ++wq) {
+          const uint2 u = lds64(stg0 + static_cast<uint32_t>(wq) * 4096u + 8u * c);
+          sum += __uint_as_float(u.x);
+          sq += __uint_as_float(u.y);
+        }
+        atomicAdd(p.ch_sum + static_cast<size_t>(rep) * p.Cout + c, static_cast<double>(sum));
+        atomicAdd(p.ch_sq + static_cast<size_t>(rep) * p.Cout + c, static_cast<double>(sq));
+      }
+    }
+  } else if (warp == kLoadW) {
+    // ------------------------------ frame loader: one TMA box [V rows][64 ch] per frame and slab ------------------------------
+    if (lane == 0) {
+      int fs = 0;
+      uint32_t fph = 0;
+      for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
+        int f0, nf;
+        frames_of(tile, f0, nf);
+        for (int cc = 0; cc < p.NCC; ++cc)
+          for (int j0 = 0; j0 < nf; j0 += q.FB) {
+            const int nfb = nf - j0 < q.FB ? nf - j0 : q.FB;
+            mbar_wait_relaxed(fr_empty(fs), fph ^ 1u, p.err, 4, 40);
+            mbar_arrive_expect_tx(fr_full(fs), static_cast<uint32_t>(nfb * p.V) * 128u);
+            for (int fi = 0; fi < nfb; ++fi)
+              tma_load_2d(fr0 + (fs * q.FB + fi) * kTcFrameBytes, &tm_xf, cc * 64, (f0 + j0 + fi) * p.V, fr_full(fs));
+            if (++fs == q.n_fr) {
+              fs = 0;
+              fph ^= 1u;
+            }
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWgtW) {
+    // -------------------------------- weight loader (as gcn_fwd_kernel) --------------------------------
+    if (lane == 0 && first_tile < p.ntiles) {
+      const uint8_t* W = reinterpret_cast<const uint8_t*>(p.wpk);
+      if (p.resident) {
+        mbar_arrive_expect_tx(b_full(0), static_cast<uint32_t>(nchunk) * b_bytes);
+        for (int i = 0; i < nchunk; ++i) bulk_g2s(b0 + i * b_bytes, W + static_cast<size_t>(i) * b_bytes, b_bytes, b_full(0));
+      } else {
+        int bs = 0;
+        uint32_t bph = 0;
+        for (int tile = first_tile; tile < p.ntiles; tile += tile_step)
+          for (int i = 0; i < nchunk; ++i) {
+            mbar_wait_relaxed(b_empty(bs), bph ^ 1u, p.err, 5, 40);
+            mbar_arrive_expect_tx(b_full(bs), b_bytes);
+            bulk_g2s(b0 + bs * b_bytes, W + static_cast<size_t>(i) * b_bytes, b_bytes, b_full(bs));
+            if (++bs == p.n_b) {
+              bs = 0;
+              bph ^= 1u;
+            }
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kAggW) {
+    // ------------------------------ aggregation MMAs: D[(k,w)][c] = A_hat . x_f ------------------------------
+    const uint32_t idesc = make_idesc_bf16(64, 0, 1);          // A K-major, B MN-major, N = 64
+    const uint32_t hi = desc_hi(1024);
+    const uint32_t a_lo = desc_lo(ahat0, 16);
+    int fs = 0, ab = 0;
+    uint32_t fph = 0, abph = 0;
+    for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
+      int f0, nf;
+      frames_of(tile, f0, nf);
+      for (int cc = 0; cc < p.NCC; ++cc)
+        for (int j0 = 0; j0 < nf; j0 += q.FB) {
+          const uint32_t nfb = static_cast<uint32_t>(nf - j0 < q.FB ? nf - j0 : q.FB);
+          mbar_wait(fr_full(fs), fph, p.err, 10);
+          mbar_wait(agg_empty(ab), abph ^ 1u, p.err, 11);
+          tc_fence_after();
+          const uint32_t b_lo0 = desc_lo(fr0 + fs * q.FB * kTcFrameBytes, 16);
+          const uint32_t d0 = tmem_agg + static_cast<uint32_t>(ab * q.FB) * 64u;
+          if (elect_one()) {
+            for (uint32_t fi = 0; fi < nfb; ++fi) {
+#pragma unroll
+              for (uint32_t kk = 0; kk < kTcFrameRows / 16; ++kk)   // A: +32 bytes per 16 k; B: +16 rows = 2048 bytes
+                umma_bf16_lh(d0 + fi * 64u, a_lo + kk * 2u, hi, b_lo0 + fi * (kTcFrameBytes >> 4) + kk * 128u, hi, idesc, kk);
+            }
+            umma_commit(agg_full(ab));
+            umma_commit(fr_empty(fs));
+          }
+          __syncwarp();
+          if (++fs == q.n_fr) {
+            fs = 0;
+            fph ^= 1u;
+          }
+          if (++ab == 2) {
+            ab = 0;
+            abph ^= 1u;
+          }
+        }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------- channel-GEMM MMA issuer ----------------------------------
+    const uint32_t idesc = make_idesc_bf16(p.BN, 0, 0);
+    const uint32_t hi = desc_hi(1024);
+    int grp = 0, bs = 0, acs = 0;
+    uint32_t gph = 0, bph = 0, acph = 0;
+    if (p.resident && first_tile < p.ntiles) mbar_wait(b_full(0), 0, p.err, 6);
+    for (int tile = first_tile; tile < p.ntiles; tile += tile_step) {
+      mbar_wait(acc_empty(acs), acph ^ 1u, p.err, 7);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acs) * static_cast<uint32_t>(p.BN);
+      for (int cc = 0; cc < p.NCC; ++cc) {
+        mbar_wait(a_full(grp), gph, p.err, 8);
+        for (int k = 0; k < p.K; ++k) {
+          const int i = cc * p.K + k;
+          if (!p.resident) mbar_wait(b_full(bs), bph, p.err, 9);
+          tc_fence_after();
+          const uint32_t a_lo = desc_lo(a0 + static_cast<uint32_t>(grp * p.K + k) * kGcnChunkBytes, 16);
+          const uint32_t b_lo = desc_lo(p.resident ? b0 + i * b_bytes : b0 + bs * b_bytes, 16);
+          if (elect_one()) {
+#pragma unroll
+            for (uint32_t kk = 0; kk < 4; ++kk)
+              umma_bf16_lh(d_tmem, a_lo + kk * 2u, hi, b_lo + kk * 2u, hi, idesc, static_cast<uint32_t>(i) | kk);
+            if (k == p.K - 1) umma_commit(a_empty(grp));
+            if (!p.resident) umma_commit(b_empty(bs));
+            if (i == nchunk - 1) umma_commit(acc_full(acs));
+          }
+          __syncwarp();
+          if (!p.resident && ++bs == p.n_b) {
+            bs = 0;
+            bph ^= 1u;
+          }
+        }
+        if (++grp == q.n_grp) {
+          grp = 0;
+          gph ^= 1u;
+        }
+      }
+      if (++acs == 2) {
+        acs = 0;
+        acph ^= 1u;
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kAggW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -1363,6 +1798,53 @@ int fmm_gcn_fwd(const void* x, void* g, void* xa, const void* wpk, const float* 
   while (p.n_raw < 3 && used + kGcnRawBytes <= budget) {
     ++p.n_raw;
     used += kGcnRawBytes;
+  }
+  // tensor-core aggregation (gcn_fwd_tc_kernel) where its shape limits hold and everything fits shared memory
+  // opt-in (FMM_GCN_TC=1, read per call): measured 7 % faster than the CUDA-core aggregation at 64 -> 64 and 128 -> 128, equal at
+  // 64 -> 128 (same box), but the adjacency coefficients are rounded to bf16 in the forward only (the backward kernels keep fp32
+  // coefficients), which moved the bf16 gradient-error median of the 7-block model from 0.085 to 0.102 (torch autocast: 0.087)
+  const char* tc_str = getenv("FMM_GCN_TC");
+  const int tc_env = tc_str ? atoi(tc_str) : 0;
+  if (tc_env && !xa && Cout <= 128 && K * V <= 128 && V <= kTcFrameRows && rows % V == 0 && (kGcnTileRows + V - 1) / V + 1 <= kTcMaxFrames) {
+    GcnTcParams q;
+    q.f = p;
+    q.FB = (512 - 2 * Cout) / 128;          // two sets of FB 64-column aggregation buffers next to the 2 x Cout accumulators
+    if (q.FB > 3) q.FB = 3;
+    q.n_fr = 2;
+    q.n_grp = 2;
+    q.nf_max = (kGcnTileRows + V - 1) / V + 1;
+    const size_t tfixed = ((static_cast<size_t>(bias ? V * Cout : 0) * 4 + 15) & ~15ull) + kGcnEpiWarps * 4096 + 1024 /*barriers*/ +
+                          1024 /*align*/ + kGcnChunkBytes + static_cast<size_t>(q.n_fr) * q.FB * kTcFrameBytes +
+                          static_cast<size_t>(q.n_grp) * K * kGcnChunkBytes;
+    if (tfixed + 2 * b_bytes <= budget) {
+      if (tfixed + nchunk * b_bytes <= budget) {
+        q.f.resident = 1;
+        q.f.n_b = nchunk;
+      } else {
+        q.f.resident = 0;
+        q.f.n_b = static_cast<int>((budget - tfixed) / b_bytes);
+        if (q.f.n_b > 4) q.f.n_b = 4;
+      }
+      size_t tused = tfixed + q.f.n_b * b_bytes;
+      while (q.n_fr < 4 && tused + q.FB * kTcFrameBytes <= budget) {   // deeper frame ring with what is left
+        ++q.n_fr;
+        tused += q.FB * kTcFrameBytes;
+      }
+      CUtensorMap tm_xf, tm_gt;
+      int st2 = make_tmap_2d(&tm_xf, x, rows, Cin, V, 64, true);
+      if (st2 != FMM_OK) return st2;
+      st2 = make_tmap_2d(&tm_gt, g, rows, Cout, 32, 64, true);
+      if (st2 != FMM_OK) return st2;
+      cudaError_t e2 = cudaFuncSetAttribute(gcn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tused));
+      if (e2 != cudaSuccess) {
+        set_last_error("gcn_fwd (tc): smem attribute (%zu bytes): %s", tused, cudaGetErrorString(e2));
+        return FMM_ERR_SMEM;
+      }
+      const int tgrid = p.ntiles < num_sms() ? p.ntiles : num_sms();
+      gcn_fwd_tc_kernel<<<tgrid, kTcThreads, tused, stream>>>(q, tm_xf, tm_gt);
+      FMM_CHECK_LAUNCH("gcn_fwd (tc)");
+      return FMM_OK;
+    }
   }
   CUtensorMap tm_x, tm_g, tm_xa;
   int st = make_tmap_2d(&tm_x, x, rows, Cin, kGcnRawBox, 64, false);

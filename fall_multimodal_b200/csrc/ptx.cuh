@@ -95,6 +95,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
       asm volatile("trap;");
     }
   }
+  if (g_wait_prof_enable && (threadIdx.x & 31) == 0) atomicAdd(&g_wait_prof[tag & 31], static_cast<unsigned long long>(clock64() - t0));
 }
 
 // ----------------------------------------------------------------------------------------

@@ -73,6 +73,43 @@ def test_gcn_fwd_matches_torch(layout, N, T, Cin, Cout):
 
 
 @gpu
+@pytest.mark.parametrize("layout,N,T,Cin,Cout", [c for c in CASES if c[4] <= 128] + [("mediapipe33", 37, 20, 128, 128), ("mediapipe33", 64, 16, 64, 64)])
+def test_gcn_fwd_tensor_core_aggregation(layout, N, T, Cin, Cout, monkeypatch):
+    """The opt-in forward with the adjacency product on the tensor core (FMM_GCN_TC=1: per-frame A_hat . x_f as tcgen05 MMAs into
+    TMEM, converted to the operand images of the channel GEMM) against the same references and against the default kernel.
+    The edge coefficients are bf16 on this path: one extra rounding of ~2^-9 relative per coefficient."""
+    from fall_multimodal_b200 import ops
+
+    dev = torch.device("cuda:0")
+    A, Ahat, K, V, rowptr, src, coef, x, W, bias, kdeg = _setup(layout, N, T, Cin, Cout, dev, seed=21)
+    if K * V > 128:
+        pytest.skip("K*V lanes exceed one MMA tile")
+    wpk = ops.gcn_pack(W, K, Cin, Cout)
+    outs, stats = [], []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("FMM_GCN_TC", tc)
+        G = torch.full((N, T, V, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
+        s1 = torch.zeros(ops.NREP * Cout, dtype=torch.float64, device=dev)
+        s2 = torch.zeros(ops.NREP * Cout, dtype=torch.float64, device=dev)
+        ops.gcn_fwd(x, wpk, G, rowptr, src, coef, K, kdeg, bias=bias, ch_sum=s1, ch_sq=s2)
+        torch.cuda.synchronize()
+        assert int(ops.err_word(dev).item()) == 0
+        assert torch.isfinite(G.float()).all()
+        outs.append(G)
+        stats.append((s1.view(ops.NREP, Cout).sum(0), s2.view(ops.NREP, Cout).sum(0)))
+    g_exact = torch.einsum("ntvc,kvw,koc->ntwo", x.double(), Ahat.double(), W.view(K, Cout, Cin).double()) + bias.double()
+    scale = g_exact.abs().max().item()
+    e0 = (outs[0].double() - g_exact).abs().max().item() / scale
+    e1 = (outs[1].double() - g_exact).abs().max().item() / scale
+    assert e1 < 2e-2 and e1 < 2.0 * e0 + 4e-3, f"tensor-core aggregation err {e1:.2e} (default kernel {e0:.2e})"
+    assert (outs[1].float() - outs[0].float()).abs().max().item() / scale < 1.2e-2
+    # statistics of what THIS path stored
+    Gf = outs[1].double().reshape(-1, Cout)
+    assert (stats[1][0] - Gf.sum(0)).abs().max().item() <= 1e-4 * max(1.0, Gf.abs().sum(0).max().item())
+    assert (stats[1][1] - (Gf * Gf).sum(0)).abs().max().item() <= 1e-4 * (Gf * Gf).sum(0).max().item()
+
+
+@gpu
 def test_gcn_fwd_without_optional_outputs_and_bench_shape():
     """No bias / statistics / xa; a bench-sized launch (N=256, T=64, V=33, 64->64) checked on a row sample."""
     from fall_multimodal_b200 import ops

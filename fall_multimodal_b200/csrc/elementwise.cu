@@ -17,6 +17,10 @@
 #include "common.cuh"
 #include "stream.cuh"
 
+#ifndef FMM_EW_MINB
+#define FMM_EW_MINB 3   // resident 256-thread blocks per SM the streaming kernels are compiled for (<= 85 registers)
+#endif
+
 namespace fmm {
 
 constexpr int kEwThreads = 256;
@@ -301,7 +305,7 @@ struct RowSegs {
 
 // colstats: per-channel sum / sum of squares (double) and optional per-(n,c) sums (float) of X.
 template <typename T>
-__global__ void colstats_kernel(const T* __restrict__ X, double* __restrict__ ch_sum, double* __restrict__ ch_sq,
+__global__ void __launch_bounds__(256, FMM_EW_MINB) colstats_kernel(const T* __restrict__ X, double* __restrict__ ch_sum, double* __restrict__ ch_sq,
                                 float* __restrict__ nc_sum, int N, int Tn, int V, int C, int nrep) {
   extern __shared__ float red[];  // [C][2] followed by the [RL][C][2] staging area
   float* scratch = red + 2 * C;
@@ -429,8 +433,8 @@ __global__ void affine_relu_kernel(const T* __restrict__ X, const float* __restr
 }
 
 // blockout_bwd_reduce: dpre = dY*(Y>0); S1[n,c]=sum dpre; S2[n,c]=sum dpre*U; S3[n,c]=sum dpre*R
-template <typename T>
-__global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ U,
+template <typename T, bool kRes, bool kMask>   // residual-conv branch present / dY still needs the ReLU mask
+__global__ void __launch_bounds__(256, FMM_EW_MINB) blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ U,
                                            const T* __restrict__ R, float* __restrict__ S1, float* __restrict__ S2,
                                            float* __restrict__ S3, int N, int Tn, int V, int C) {
   extern __shared__ float red[];  // [C][3] followed by the [RL][C][3] staging area
@@ -444,32 +448,32 @@ __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __
   float acc[3][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
-  constexpr int NB = 2;   // rows in flight per thread (3-4 tensors each)
+  constexpr int NB = (kRes || kMask) ? 2 : 4;   // rows in flight per thread (2-4 tensors each)
   for (int r = r0 + rl; r < r1; r += NB * RL) {
-    Raw8<T> rg[NB], ry[NB], ru[NB], rres[NB];
+    Raw8<T> rg[NB], ry[kMask ? NB : 1], ru[NB], rres[kRes ? NB : 1];
 #pragma unroll
     for (int q = 0; q < NB; ++q)
       if (r + q * RL < r1) {
         const size_t off = base + static_cast<size_t>(r + q * RL) * C;
         ldraw8(dY + off, rg[q]);
-        if (Y) ldraw8(Y + off, ry[q]);
+        if (kMask) ldraw8(Y + off, ry[q]);
         ldraw8(U + off, ru[q]);
-        if (R) ldraw8(R + off, rres[q]);
+        if (kRes) ldraw8(R + off, rres[q]);
       }
 #pragma unroll
     for (int q = 0; q < NB; ++q)
       if (r + q * RL < r1) {
         float g[8], y[8], u[8], rr[8];
         unpack8(rg[q], g);
-        if (Y) unpack8(ry[q], y);
+        if (kMask) unpack8(ry[q], y);
         unpack8(ru[q], u);
-        if (R) unpack8(rres[q], rr);
+        if (kRes) unpack8(rres[q], rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float d = (!Y || y[j] > 0.f) ? g[j] : 0.f;   // Y == null: dY arrives already masked (fmm_gcn_bwd relu_mask)
+          const float d = (!kMask || y[j] > 0.f) ? g[j] : 0.f;   // Y == null: dY arrives already masked (fmm_gcn_bwd relu_mask)
           acc[0][j] += d;
           acc[1][j] = fmaf(d, u[j], acc[1][j]);
-          if (R) acc[2][j] = fmaf(d, rr[j], acc[2][j]);
+          if (kRes) acc[2][j] = fmaf(d, rr[j], acc[2][j]);
         }
       }
   }
@@ -478,7 +482,7 @@ __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     atomicAdd(S1 + static_cast<size_t>(n) * C + c, red[3 * c]);
     atomicAdd(S2 + static_cast<size_t>(n) * C + c, red[3 * c + 1]);
-    if (R) atomicAdd(S3 + static_cast<size_t>(n) * C + c, red[3 * c + 2]);
+    if (kRes) atomicAdd(S3 + static_cast<size_t>(n) * C + c, red[3 * c + 2]);
   }
   }
 }
@@ -488,8 +492,10 @@ __global__ void blockout_bwd_reduce_kernel(const T* __restrict__ dY, const T* __
 //   dR = r1[c]*dpre + r2[c]*R + r3[c]            (if R)
 //   dPre = dpre                                   (if dPre: identity residual)
 //   colsum_dU[c] += sum dU (as stored), colsum_dR[c] += sum dR   (optional, double)
-template <typename T>
-__global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ U,
+// kRes / kMask: residual-conv branch present / dY still needs the ReLU mask (compile-time: the unused coefficient and raw
+// registers of the common pre-masked identity block are what kept this kernel at one block per SM)
+template <typename T, bool kRes, bool kMask>
+__global__ void __launch_bounds__(256, kRes ? 2 : 3) bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ U,
                                      const T* __restrict__ R, const float* __restrict__ k1,
                                      const float* __restrict__ k2, const float* __restrict__ k3,
                                      const float* __restrict__ r1, const float* __restrict__ r2,
@@ -507,28 +513,30 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
   RowSegs segs(N, Tn * V);
   int n, r0, r1r;
   while (segs.next(n, r0, r1r)) {
-  float a1[8], a2[8], a3[8], b1[8], b2[8], b3[8];
+  float a1[8], a2[8], a3[8], b1[kRes ? 8 : 1], b2[kRes ? 8 : 1], b3[kRes ? 8 : 1];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     a1[j] = k1[static_cast<size_t>(n) * C + c0 + j];
     a2[j] = k2[c0 + j];
     a3[j] = k3[static_cast<size_t>(n) * C + c0 + j];
-    b1[j] = R ? r1[c0 + j] : 0.f;
-    b2[j] = R ? r2[c0 + j] : 0.f;
-    b3[j] = R ? r3[c0 + j] : 0.f;
+    if (kRes) {
+      b1[j] = r1[c0 + j];
+      b2[j] = r2[c0 + j];
+      b3[j] = r3[c0 + j];
+    }
   }
   const size_t base = static_cast<size_t>(n) * Tn * V * C + c0;
   constexpr int NB = 2;   // rows in flight per thread (3-4 tensors each)
   for (int rb = r0 + rl; rb < r1r; rb += NB * RL) {
-    Raw8<T> rg[NB], ry[NB], ru[NB], rres[NB];
+    Raw8<T> rg[NB], ry[kMask ? NB : 1], ru[NB], rres[kRes ? NB : 1];
 #pragma unroll
     for (int q = 0; q < NB; ++q)
       if (rb + q * RL < r1r) {
         const size_t off = base + static_cast<size_t>(rb + q * RL) * C;
         ldraw8(dY + off, rg[q]);
-        if (Y) ldraw8(Y + off, ry[q]);
+        if (kMask) ldraw8(Y + off, ry[q]);
         ldraw8(U + off, ru[q]);
-        if (R) ldraw8(R + off, rres[q]);
+        if (kRes) ldraw8(R + off, rres[q]);
       }
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
@@ -536,21 +544,21 @@ __global__ void bn2_bwd_apply_kernel(const T* __restrict__ dY, const T* __restri
     const size_t off = base + static_cast<size_t>(rb + q * RL) * C;
     float g[8], y[8], u[8], rr[8], ou[8], orr[8], d[8];
     unpack8(rg[q], g);
-    if (Y) unpack8(ry[q], y);
+    if (kMask) unpack8(ry[q], y);
     unpack8(ru[q], u);
-    if (R) unpack8(rres[q], rr);
+    if (kRes) unpack8(rres[q], rr);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      d[j] = (!Y || y[j] > 0.f) ? g[j] : 0.f;   // Y == null: dY arrives already masked
+      d[j] = (!kMask || y[j] > 0.f) ? g[j] : 0.f;   // !kMask (Y == null): dY arrives already masked
       ou[j] = fmaf(a1[j], d[j], fmaf(a2[j], u[j], a3[j]));
       acc[0][j] += to_f32(from_f32<T>(ou[j]));
-      if (R) {
+      if (kRes) {
         orr[j] = fmaf(b1[j], d[j], fmaf(b2[j], rr[j], b3[j]));
         acc[1][j] += to_f32(from_f32<T>(orr[j]));
       }
     }
     store8(dU + off, ou);
-    if (R) store8(dR + off, orr);
+    if (kRes) store8(dR + off, orr);
     if (dPre) store8(dPre + off, d);
     }
   }
@@ -893,10 +901,17 @@ int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const 
   const int th = rowwalk_threads(C);
   const size_t sm = (3 * C + th * 24) * sizeof(float);
   const long long rows = static_cast<long long>(N) * Tn * V;
+#define FMM_BOUT_REDUCE(RES, MASK)                                                                                     \
+  blockout_bwd_reduce_kernel<T, RES, MASK><<<resident_grid(blockout_bwd_reduce_kernel<T, RES, MASK>, th, sm, rows), th, sm, stream>>>( \
+      (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, S1, S2, S3, N, Tn, V, C)
   FMM_DISPATCH(dtype, {
-    blockout_bwd_reduce_kernel<T><<<resident_grid(blockout_bwd_reduce_kernel<T>, th, sm, rows), th, sm, stream>>>(
-        (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, S1, S2, S3, N, Tn, V, C);
+    if (R) {
+      if (Y) FMM_BOUT_REDUCE(true, true); else FMM_BOUT_REDUCE(true, false);
+    } else {
+      if (Y) FMM_BOUT_REDUCE(false, true); else FMM_BOUT_REDUCE(false, false);
+    }
   })
+#undef FMM_BOUT_REDUCE
   FMM_CHECK_LAUNCH("blockout_bwd_reduce");
   return FMM_OK;
 }
@@ -911,11 +926,17 @@ int fmm_bn2_bwd_apply(const void* dY, const void* Y, const void* U, const void* 
   const int th = rowwalk_threads(C);
   const size_t sm = (2 * C + th * 16) * sizeof(float);
   const long long rows = static_cast<long long>(N) * Tn * V;
+#define FMM_BN2_APPLY(RES, MASK)                                                                                       \
+  bn2_bwd_apply_kernel<T, RES, MASK><<<resident_grid(bn2_bwd_apply_kernel<T, RES, MASK>, th, sm, rows), th, sm, stream>>>( \
+      (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, k1, k2, k3, r1, r2, r3, (T*)dU, (T*)dR, (T*)dPre, sum_dU, sum_dR, N, Tn, V, C, nrep)
   FMM_DISPATCH(dtype, {
-    bn2_bwd_apply_kernel<T><<<resident_grid(bn2_bwd_apply_kernel<T>, th, sm, rows), th, sm, stream>>>(
-        (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, k1, k2, k3, r1, r2, r3, (T*)dU, (T*)dR, (T*)dPre, sum_dU,
-        sum_dR, N, Tn, V, C, nrep);
+    if (R) {
+      if (Y) FMM_BN2_APPLY(true, true); else FMM_BN2_APPLY(true, false);
+    } else {
+      if (Y) FMM_BN2_APPLY(false, true); else FMM_BN2_APPLY(false, false);
+    }
   })
+#undef FMM_BN2_APPLY
   FMM_CHECK_LAUNCH("bn2_bwd_apply");
   return FMM_OK;
 }

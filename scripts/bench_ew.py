@@ -65,6 +65,8 @@ for (T, C) in ((64, 64), (32, 128), (16, 256)):
     sums = torch.zeros(NR * C, dtype=torch.float64, device=dev)
     if not only or only in "bn2_bwd_apply":
         report(tag + "bn2_bwd_apply(identity)", timeit(lambda: ops.bn2_bwd_apply(dY, Y, U, None, k1, k2, k0, None, None, None, dU, None, dPre, sums, None)), 5 * S)
+        report(tag + "bn2_bwd_apply(pre-masked)", timeit(lambda: ops.bn2_bwd_apply(dY, None, U, None, k1, k2, k0, None, None, None, dU, None, None, sums, None)), 3 * S)
+        report(tag + "blockout_bwd_reduce(pre-masked)", timeit(lambda: ops.blockout_bwd_reduce(dY, None, U, None, S1, S2, None)), 2 * S)
     a1, b1 = f32(C), f32(C) - 0.5
     T1, T2 = torch.zeros(NR * C, dtype=torch.float64, device=dev), torch.zeros(NR * C, dtype=torch.float64, device=dev)
     if not only or only in "bn1_bwd_reduce":

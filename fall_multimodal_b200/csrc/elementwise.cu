@@ -756,6 +756,84 @@ __global__ void __launch_bounds__(512) bn1_bwd_apply_kernel(const T* __restrict_
   }
 }
 
+// bn1_bwd_apply with the two inputs staged through the TMA ring of stream.cuh. Chunks are whole frames; consumer thread t owns the
+// (joint, channel-group) pairs t, t + 256, ... of every frame (the channel group is the same for all of them: 256 is a multiple
+// of C/8), keeps their [v][c] table sums in registers and flushes them once.
+template <typename T, int MP>   // MP = pairs per thread = ceil(V * C/8 / 256)
+__global__ void __launch_bounds__(kStThreads, 1)
+    bn1_bwd_apply_tma_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
+                             const float* __restrict__ b1, const float* __restrict__ c1, const float* __restrict__ c2,
+                             const float* __restrict__ c3, T* __restrict__ dG, float* __restrict__ Tbl, int N, int Tn, int V, int C,
+                             int nrep, int chunk_rows, unsigned* err) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  StreamPipe<2> pipe;
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * sizeof(T);
+  pipe.init(st_smem, static_cast<uint32_t>(chunk_rows) * row_bytes);
+  ChunkIter it(static_cast<long long>(N) * Tn * V, V, Tn * V, chunk_rows, false);
+  long long row0;
+  int nrows, n, i = 0;
+  if (threadIdx.x >= kStConsumers) {
+    if (threadIdx.x == kStConsumers) {
+      const void* const src[2] = {dH, G};
+      while (it.next(row0, nrows, n)) pipe.produce(i++, src, row0, nrows, row_bytes, err);
+    }
+    return;
+  }
+  const int c8n = C / 8, pairs = V * c8n;
+  const int c0 = (threadIdx.x % c8n) * 8;
+  float a[8], b[8], k1[8], k2[8], k3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = a1[c0 + j];
+    b[j] = b1[c0 + j];
+    k1[j] = c1[c0 + j];
+    k2[j] = c2[c0 + j];
+    k3[j] = c3[c0 + j];
+  }
+  float acc[MP][8];
+#pragma unroll
+  for (int m = 0; m < MP; ++m)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[m][j] = 0.f;
+  const uint32_t frame_bytes = static_cast<uint32_t>(V) * row_bytes;
+  while (it.next(row0, nrows, n)) {
+    const int s = pipe.acquire(i++, err);
+    const uint32_t sh = pipe.tensor(s, 0), sg = pipe.tensor(s, 1);
+    const int nfr = nrows / V;
+    for (int f = 0; f < nfr; ++f) {
+#pragma unroll
+      for (int m = 0; m < MP; ++m) {
+        const int pi = static_cast<int>(threadIdx.x) + m * kStConsumers;
+        if (pi < pairs) {
+          const uint32_t so = static_cast<uint32_t>(f) * frame_bytes + static_cast<uint32_t>(pi) * 8u * sizeof(T);
+          float g[8], h[8], o[8];
+          lds8(sh + so, h, static_cast<const T*>(nullptr));
+          lds8(sg + so, g, static_cast<const T*>(nullptr));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = fmaf(a[j], g[j], b[j]) > 0.f ? h[j] : 0.f;
+            o[j] = fmaf(k1[j], d, fmaf(k2[j], g[j], k3[j]));
+            acc[m][j] += to_f32(from_f32<T>(o[j]));
+          }
+          store8(dG + (static_cast<size_t>(row0) + static_cast<size_t>(f) * V) * C + static_cast<size_t>(pi) * 8, o);
+        }
+      }
+    }
+    pipe.release(s);
+  }
+  if (Tbl) {
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      const int pi = static_cast<int>(threadIdx.x) + m * kStConsumers;
+      if (pi < pairs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          atomicAdd(Tbl + static_cast<size_t>(replica_of_block(nrep)) * V * C + static_cast<size_t>(pi) * 8 + j, acc[m][j]);
+      }
+    }
+  }
+}
+
 // threads for the row-walk kernels: a multiple of the channel groups (fixed c8 per thread)
 static inline int rowwalk_threads(int C) {
   const int c8n = C / 8;
@@ -973,6 +1051,34 @@ int fmm_bn1_bwd_apply(const void* dH, const void* G, const float* a1, const floa
   FMM_CHECK_ARG(dH && G && a1 && b1 && c1 && c2 && c3 && dG && C % 8 == 0, "bn1_bwd_apply: bad args");
   const int th = pair_threads(V * (C / 8));   // <= 512 (the kernel's launch bound)
   const long long frames = static_cast<long long>(N) * Tn;
+  {
+    const char* tma_str = getenv("FMM_EW_TMA");
+    const int c8n = C / 8, mp = (V * c8n + kStConsumers - 1) / kStConsumers;
+    const size_t es = dtype == FMM_DT_BF16 ? 2 : 4;
+    const int cr = stream_chunk_rows(16 * 1024, C * es, V);
+    const size_t smem = StreamPipe<2>::bytes(static_cast<uint32_t>(cr * C * es));
+    if ((!tma_str || atoi(tma_str)) && kStConsumers % c8n == 0 && mp >= 1 && mp <= 5 && frames >= 2 && smem <= 200 * 1024) {
+#define FMM_BN1_APPLY_TMA(MPV)                                                                                              \
+  do {                                                                                                                     \
+    cudaFuncSetAttribute(bn1_bwd_apply_tma_kernel<T, MPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    int g = num_sms() < frames ? num_sms() : static_cast<int>(frames);                                                     \
+    bn1_bwd_apply_tma_kernel<T, MPV><<<g, kStThreads, smem, stream>>>((const T*)dH, (const T*)G, a1, b1, c1, c2, c3, (T*)dG, Tbl, N, \
+                                                                      Tn, V, C, nrep, cr, nullptr);                       \
+  } while (0)
+      FMM_DISPATCH(dtype, {
+        switch (mp) {
+          case 1: FMM_BN1_APPLY_TMA(1); break;
+          case 2: FMM_BN1_APPLY_TMA(2); break;
+          case 3: FMM_BN1_APPLY_TMA(3); break;
+          case 4: FMM_BN1_APPLY_TMA(4); break;
+          default: FMM_BN1_APPLY_TMA(5); break;
+        }
+      })
+#undef FMM_BN1_APPLY_TMA
+      FMM_CHECK_LAUNCH("bn1_bwd_apply");
+      return FMM_OK;
+    }
+  }
   FMM_DISPATCH(dtype, {
     int g = resident_grid(bn1_bwd_apply_kernel<T>, th, 0, frames * 32);
     if (g > frames) g = static_cast<int>(frames);

@@ -698,6 +698,164 @@ __global__ void __launch_bounds__(kStThreads, 1)
   }
 }
 
+// Block reduce among the kStConsumers consumer threads of a TMA-staged kernel (the producer warp does not take part: named
+// barrier 1): NV x 8 partial sums per thread -> red[c * NV + v].
+template <int NV>
+__device__ __forceinline__ void consumer_channel_reduce(const float (&val)[NV][8], float* scratch, float* red, int C, int c8,
+                                                        int c8n, int rl, int RL) {
+  const int nt = RL * c8n;
+  asm volatile("bar.sync 1, %0;" ::"n"(kStConsumers) : "memory");   // readers of the previous flush are done
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) scratch[static_cast<size_t>(j * NV + v) * nt + rl * c8n + c8] = val[v][j];
+  asm volatile("bar.sync 1, %0;" ::"n"(kStConsumers) : "memory");
+  for (int i = threadIdx.x; i < C * NV; i += kStConsumers) {
+    const int c = i / NV, v = i - c * NV;
+    const float* col = scratch + static_cast<size_t>((c & 7) * NV + v) * nt + (c >> 3);
+    float acc = 0.f;
+    for (int r = 0; r < RL; ++r) acc += col[r * c8n];
+    red[i] = acc;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kStConsumers) : "memory");
+}
+
+// blockout_bwd_reduce with its 2-4 inputs staged through the TMA ring (chunks never straddle a clip: sums are per clip)
+template <typename T, bool kRes, bool kMask>
+__global__ void __launch_bounds__(kStThreads, 1)
+    blockout_bwd_reduce_tma_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ U, const T* __restrict__ R,
+                                   float* __restrict__ S1, float* __restrict__ S2, float* __restrict__ S3, int N, int Tn, int V,
+                                   int C, int chunk_rows, unsigned* err) {
+  constexpr int NT = 2 + (kRes ? 1 : 0) + (kMask ? 1 : 0);
+  constexpr int iU = 1, iY = 2, iR = kMask ? 3 : 2;
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  StreamPipe<NT> pipe;
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * sizeof(T);
+  pipe.init(st_smem, static_cast<uint32_t>(chunk_rows) * row_bytes);
+  float* red = reinterpret_cast<float*>(st_smem + (pipe.empty0 + 8u * kStStages + 64u - smem_u32(st_smem)));
+  float* scratch = red + 3 * C;
+  ChunkIter it(static_cast<long long>(N) * Tn * V, 1, Tn * V, chunk_rows, true);
+  long long row0;
+  int nrows, n, i = 0;
+  if (threadIdx.x >= kStConsumers) {
+    if (threadIdx.x == kStConsumers) {
+      const void* src[NT];
+      src[0] = dY;
+      src[iU] = U;
+      if (kMask) src[iY] = Y;
+      if (kRes) src[iR] = R;
+      const void* const(&csrc)[NT] = src;
+      while (it.next(row0, nrows, n)) pipe.produce(i++, csrc, row0, nrows, row_bytes, err);
+    }
+    return;
+  }
+  const int c8n = C / 8;
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = kStConsumers / c8n;
+  float acc[3][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
+  const uint32_t toff = static_cast<uint32_t>(threadIdx.x) * 8u * sizeof(T);
+  const uint32_t rstep = static_cast<uint32_t>(RL) * row_bytes;
+  int cur_n = -1;
+  auto flush = [&](int nn) {
+    consumer_channel_reduce<3>(acc, scratch, red, C, c8, c8n, rl, RL);
+    for (int c = threadIdx.x; c < C; c += kStConsumers) {
+      atomicAdd(S1 + static_cast<size_t>(nn) * C + c, red[3 * c]);
+      atomicAdd(S2 + static_cast<size_t>(nn) * C + c, red[3 * c + 1]);
+      if (kRes) atomicAdd(S3 + static_cast<size_t>(nn) * C + c, red[3 * c + 2]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
+  };
+  while (it.next(row0, nrows, n)) {
+    if (n != cur_n) {
+      if (cur_n >= 0) flush(cur_n);
+      cur_n = n;
+    }
+    const int s = pipe.acquire(i++, err);
+    uint32_t off = toff;
+#pragma unroll 2
+    for (int r = rl; r < nrows; r += RL, off += rstep) {
+      float g[8], y[8], u[8], rr[8];
+      lds8(pipe.tensor(s, 0) + off, g, static_cast<const T*>(nullptr));
+      lds8(pipe.tensor(s, iU) + off, u, static_cast<const T*>(nullptr));
+      if (kMask) lds8(pipe.tensor(s, iY) + off, y, static_cast<const T*>(nullptr));
+      if (kRes) lds8(pipe.tensor(s, iR) + off, rr, static_cast<const T*>(nullptr));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = (!kMask || y[j] > 0.f) ? g[j] : 0.f;
+        acc[0][j] += d;
+        acc[1][j] = fmaf(d, u[j], acc[1][j]);
+        if (kRes) acc[2][j] = fmaf(d, rr[j], acc[2][j]);
+      }
+    }
+    pipe.release(s);
+  }
+  if (cur_n >= 0) flush(cur_n);
+}
+
+// colstats with the input staged through the TMA ring
+template <typename T>
+__global__ void __launch_bounds__(kStThreads, 1)
+    colstats_tma_kernel(const T* __restrict__ X, double* __restrict__ ch_sum, double* __restrict__ ch_sq, float* __restrict__ nc_sum,
+                        int N, int Tn, int V, int C, int nrep, int chunk_rows, unsigned* err) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  StreamPipe<1> pipe;
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * sizeof(T);
+  pipe.init(st_smem, static_cast<uint32_t>(chunk_rows) * row_bytes);
+  float* red = reinterpret_cast<float*>(st_smem + (pipe.empty0 + 8u * kStStages + 64u - smem_u32(st_smem)));
+  float* scratch = red + 2 * C;
+  ChunkIter it(static_cast<long long>(N) * Tn * V, 1, Tn * V, chunk_rows, nc_sum != nullptr);
+  long long row0;
+  int nrows, n, i = 0;
+  if (threadIdx.x >= kStConsumers) {
+    if (threadIdx.x == kStConsumers) {
+      const void* const src[1] = {X};
+      while (it.next(row0, nrows, n)) pipe.produce(i++, src, row0, nrows, row_bytes, err);
+    }
+    return;
+  }
+  const int c8n = C / 8;
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n, RL = kStConsumers / c8n;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  const uint32_t toff = static_cast<uint32_t>(threadIdx.x) * 8u * sizeof(T);
+  const uint32_t rstep = static_cast<uint32_t>(RL) * row_bytes;
+  int cur_n = -1;
+  auto flush = [&](int nn) {
+    consumer_channel_reduce<2>(acc, scratch, red, C, c8, c8n, rl, RL);
+    for (int c = threadIdx.x; c < C; c += kStConsumers) {
+      const size_t ro = static_cast<size_t>(replica_of_block(nrep)) * C;
+      if (ch_sum) atomic_add_f64(ch_sum + ro + c, static_cast<double>(red[2 * c]));
+      if (ch_sq) atomic_add_f64(ch_sq + ro + c, static_cast<double>(red[2 * c + 1]));
+      if (nc_sum) atomicAdd(nc_sum + static_cast<size_t>(nn) * C + c, red[2 * c]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  };
+  while (it.next(row0, nrows, n)) {
+    if (nc_sum && n != cur_n) {
+      if (cur_n >= 0) flush(cur_n);
+    }
+    cur_n = n;
+    const int s = pipe.acquire(i++, err);
+    uint32_t a = pipe.tensor(s, 0) + toff;
+#pragma unroll 4
+    for (int r = rl; r < nrows; r += RL, a += rstep) {
+      float f[8];
+      lds8(a, f, static_cast<const T*>(nullptr));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += f[j];
+        acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
+      }
+    }
+    pipe.release(s);
+  }
+  if (cur_n >= 0) flush(cur_n);
+}
+
 // bn1_bwd_apply: dG = c1[c]*dy1 + c2[c]*G + c3[c]  (dy1 as above); Tbl[v][c] += sum_{n,t} dG
 template <typename T>
 __global__ void __launch_bounds__(512) bn1_bwd_apply_kernel(const T* __restrict__ dH, const T* __restrict__ G, const float* __restrict__ a1,
@@ -942,6 +1100,19 @@ int fmm_colstats(const void* X, double* ch_sum, double* ch_sq, float* nc_sum, in
   const int th = rowwalk_threads(C);
   const size_t sm = (2 * C + th * 16) * sizeof(float);
   const long long rows = static_cast<long long>(N) * Tn * V;
+  {
+    const char* tma_str = getenv("FMM_EW_TMA");
+    if ((!tma_str || atoi(tma_str)) && kStConsumers % (C / 8) == 0 && rows >= 64) {
+      FMM_DISPATCH(dtype, {
+        const int cr = stream_chunk_rows(32 * 1024, C * sizeof(T), 1);
+        const size_t smem = StreamPipe<1>::bytes(cr * C * sizeof(T)) + 64 + (2 * C + kStConsumers * 16) * sizeof(float);
+        cudaFuncSetAttribute(colstats_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        colstats_tma_kernel<T><<<num_sms(), kStThreads, smem, stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, N, Tn, V, C, nrep, cr, nullptr);
+      })
+      FMM_CHECK_LAUNCH("colstats");
+      return FMM_OK;
+    }
+  }
   FMM_DISPATCH(dtype, {
     colstats_kernel<T><<<resident_grid(colstats_kernel<T>, th, sm, rows), th, sm, stream>>>((const T*)X, ch_sum, ch_sq, nc_sum, N, Tn, V, C, nrep);
   })
@@ -979,6 +1150,31 @@ int fmm_blockout_bwd_reduce(const void* dY, const void* Y, const void* U, const 
   const int th = rowwalk_threads(C);
   const size_t sm = (3 * C + th * 24) * sizeof(float);
   const long long rows = static_cast<long long>(N) * Tn * V;
+  {
+    const char* tma_str = getenv("FMM_EW_TMA");
+    if ((!tma_str || atoi(tma_str)) && kStConsumers % (C / 8) == 0 && rows >= 64) {
+      const int live = 2 + (R ? 1 : 0) + (Y ? 1 : 0);
+#define FMM_BOUT_REDUCE_TMA(RES, MASK)                                                                                        \
+  do {                                                                                                                        \
+    const int cr = stream_chunk_rows(32 * 1024 / live, C * sizeof(T), 1);                                                     \
+    const size_t smem = StreamPipe<2 + (RES ? 1 : 0) + (MASK ? 1 : 0)>::bytes(cr * C * sizeof(T)) + 64 +                       \
+                        (3 * C + kStConsumers * 24) * sizeof(float);                                                           \
+    cudaFuncSetAttribute(blockout_bwd_reduce_tma_kernel<T, RES, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    blockout_bwd_reduce_tma_kernel<T, RES, MASK><<<num_sms(), kStThreads, smem, stream>>>(                                     \
+        (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, S1, S2, S3, N, Tn, V, C, cr, nullptr);                            \
+  } while (0)
+      FMM_DISPATCH(dtype, {
+        if (R) {
+          if (Y) FMM_BOUT_REDUCE_TMA(true, true); else FMM_BOUT_REDUCE_TMA(true, false);
+        } else {
+          if (Y) FMM_BOUT_REDUCE_TMA(false, true); else FMM_BOUT_REDUCE_TMA(false, false);
+        }
+      })
+#undef FMM_BOUT_REDUCE_TMA
+      FMM_CHECK_LAUNCH("blockout_bwd_reduce");
+      return FMM_OK;
+    }
+  }
 #define FMM_BOUT_REDUCE(RES, MASK)                                                                                     \
   blockout_bwd_reduce_kernel<T, RES, MASK><<<resident_grid(blockout_bwd_reduce_kernel<T, RES, MASK>, th, sm, rows), th, sm, stream>>>( \
       (const T*)dY, (const T*)Y, (const T*)U, (const T*)R, S1, S2, S3, N, Tn, V, C)

@@ -15,6 +15,7 @@
 // Work split: item = (ci tile, tap group, co tile) keeps TG accumulators [128 x BN] resident in
 // TMEM; the row dimension is sliced across CTAs and the partial results are added to global
 // memory with fp32 atomics (dW must be zeroed by the caller).
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -335,9 +336,206 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// wgrad with tensor-map TMA operand stages (bf16, no fused prologue: the engine's path).
+//
+// The cp.async producers above need 5 120 LDGSTS (20 per thread, ~1 300 issue cycles) per 81 KB stage and only two stages fit:
+// the MMA warp waits on operand stages ~40 % of the kernel at C >= 128 (wait-site profile, profiles/r02_summary.md). Here the
+// column groups are CLIP-ALIGNED (ceil(V/8) groups per clip, the last one padded with zero columns: 33 of 40 rows carry data at
+// V = 33), which makes every operand tile one box of a 4-D tensor map over [n][t][v][c]: {64 ch, 8 joints, W frames, 1 clip},
+// out-of-range frames (the conv's zero padding) and joints are zero-filled by the TMA engine. One lane issues MCH + BN/64 boxes
+// per stage; the window lands in exactly the [frame][8 joints][64 ch] SWIZZLE_128B image the MMA descriptors expect.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
+template <bool kTaps>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tma_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.MCH) * p.win_atoms * 1024u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN / 64) * p.JT * 1024u;
+  const uint32_t stage_bytes = a_bytes + b_bytes + 1024u;  // +1 atom of slack: MCH=1 reads one atom past A
+  const uint32_t bars0 = smem_base + p.nstages * stage_bytes;
+  auto full = [&](int s) { return bars0 + 8u * s; };
+  auto empty = [&](int s) { return bars0 + 8u * (p.nstages + s); };
+  const uint32_t acc_full = bars0 + 8u * (2 * p.nstages);
+  const uint32_t tmem_slot = acc_full + 8u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t acc_stride = static_cast<uint32_t>(p.BN);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(p.TG) * acc_stride) tmem_cols <<= 1;
+
+  const int item = blockIdx.x % p.items;
+  const int slice = blockIdx.x / p.items;
+  const int co_tile = item % p.co_tiles;
+  const int tg = (item / p.co_tiles) % p.tap_groups;
+  const int ci_tile = item / (p.co_tiles * p.tap_groups);
+  const int acc0 = tg * p.TG;
+  const int mt = (p.nacc_total - acc0) < p.TG ? (p.nacc_total - acc0) : p.TG;
+  const int m0 = p.pair ? 2 * acc0 : acc0;
+  const int tstep = p.pair ? 2 : 1;
+  const int my_units = slice < p.total_units ? (p.total_units - slice + p.slices - 1) / p.slices : 0;
+  const int gpc = (p.V + 7) / 8;   // column groups per clip
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_dy)) : "memory");
+  }
+  // the slack atom behind every A image is read by the tap-pair MMAs (rows 64..127 of the last tap pair): keep it finite
+  for (int s = threadIdx.x; s < p.nstages * 64; s += blockDim.x) {
+    const uint32_t addr = smem_base + (s / 64) * stage_bytes + a_bytes + b_bytes + (s % 64) * 16u;
+    asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (my_units > 0) {
+    if (warp == 7 && lane == 0) {
+      // ------------------------------ TMA producer (one lane) ------------------------------
+      int st = 0;
+      uint32_t ph = 0;
+      for (int u = slice; u < p.total_units; u += p.slices) {
+        const int jchunk = u % p.njchunks;
+        const int group = u / p.njchunks;
+        const int n = group / gpc, v0 = (group - n * gpc) * 8;
+        const int j0 = jchunk * p.JT;
+        const int t_lo = j0 * p.istride + p.minshift;
+        mbar_wait_relaxed(empty(st), ph ^ 1u, p.err, 11, 32);
+        const uint32_t a_base = smem_base + st * stage_bytes;
+        mbar_arrive_expect_tx(full(st), a_bytes + b_bytes);
+        for (int h = 0; h < p.MCH; ++h)
+          tma_load_4d(a_base + h * p.win_atoms * 1024u, &tm_x, (ci_tile * p.MCH + h) * 64, v0, t_lo, n, full(st));
+        for (int h = 0; h < p.BN / 64; ++h)
+          tma_load_4d(a_base + a_bytes + h * p.JT * 1024u, &tm_dy, co_tile * p.BN + h * 64, v0, j0, n, full(st));
+        if (++st == p.nstages) {
+          st = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+    if (warp < 4) {
+      // ------------------------------ epilogue ------------------------------
+      mbar_wait_relaxed(acc_full, 0, p.err, 12, 256);
+      tc_fence_after();
+      const int row = warp * 32 + lane;  // channel inside the ci tile (pair mode: rows 64..127 = next tap)
+      const int second = (p.pair && row >= 64) ? 1 : 0;
+      const int ci = ci_tile * p.MCH * 64 + (second ? row - 64 : row);
+      const bool ci_ok = (p.pair || row < p.MCH * 64) && ci < p.Cin;
+      const long long ci_off = ci_ok ? (ci / p.C2) * p.s_c1 + (ci % p.C2) * p.s_c2 : 0;
+      for (int t = 0; t < mt; ++t) {
+        for (int cg = 0; cg < p.BN / 32; ++cg) {
+          uint32_t acc[32];
+          const uint32_t taddr = tmem_base + static_cast<uint32_t>(t) * acc_stride + static_cast<uint32_t>(cg * 32) +
+                                 (static_cast<uint32_t>(warp * 32) << 16);
+          tmem_ld32(taddr, acc);
+          tmem_ld_wait();
+          if (ci_ok && m0 + t * tstep + second < p.ntaps) {
+            float* dst = p.dw + (m0 + t * tstep + second) * p.s_m + ci_off;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int co = co_tile * p.BN + cg * 32 + i;
+              if (co < p.Cout) atomicAdd(dst + co * p.s_co, __uint_as_float(acc[i]));
+            }
+          }
+        }
+      }
+    } else if (warp == 8) {
+      // ---------------------------------- MMA issuer ----------------------------------
+      const uint32_t idesc = make_idesc_bf16(p.BN, 1, 1);
+      const uint32_t a_sbo = static_cast<uint32_t>(p.istride) * 1024u;
+      const uint32_t a_lbo = p.MCH == 2 ? static_cast<uint32_t>(p.win_atoms) * 1024u : 1024u;
+      const uint32_t b_lbo = static_cast<uint32_t>(p.JT) * 1024u;
+      const uint32_t a_hi = desc_hi(a_sbo), b_hi = desc_hi(1024);
+      const uint32_t a_kstep = (2u * a_sbo) >> 4, b_kstep = 2048u >> 4;
+      int st = 0;
+      uint32_t ph = 0;
+      uint32_t accum = 0;
+      for (int it = 0; it < my_units; ++it) {
+        mbar_wait(full(st), ph, p.err, 13);
+        tc_fence_after();
+        const uint32_t a_base = smem_base + st * stage_bytes;
+        const uint32_t b_lo0 = desc_lo(a_base + a_bytes, b_lbo);
+        if (elect_one()) {
+          for (int t = 0; t < mt; ++t) {
+            const uint32_t a_lo0 = desc_lo(a_base + static_cast<uint32_t>(p.shift[m0 + t * tstep] - p.minshift) * 1024u, a_lbo);
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(t) * acc_stride;
+            for (int kk = 0; kk < p.JT / 2; ++kk)
+              umma_bf16_lh(d_tmem, a_lo0 + kk * a_kstep, a_hi, b_lo0 + kk * b_kstep, b_hi, idesc, accum | static_cast<uint32_t>(kk));
+          }
+          umma_commit(empty(st));
+          if (it == my_units - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+        accum = 1;
+        if (++st == p.nstages) {
+          st = 0;
+          ph ^= 1u;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 }  // namespace fmm
 
 using namespace fmm;
+
+namespace {
+typedef CUresult (*WgEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+WgEncodeTiledFn wg_encode_fn() {
+  static WgEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<WgEncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// bf16 activation [N][T][V][C] (channels-last), box {64 channels, 8 joints, frames, 1 clip}, SWIZZLE_128B, zero fill out of range
+bool make_tmap_act(CUtensorMap* map, const void* base, int N, int T, int V, int C, int box_frames) {
+  WgEncodeTiledFn fn = wg_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(V), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(V) * C * 2, static_cast<cuuint64_t>(T) * V * C * 2};
+  cuuint32_t box[4] = {64, 8, static_cast<cuuint32_t>(box_frames), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
 
 extern "C" {
 
@@ -424,6 +622,38 @@ int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, c
   FMM_CHECK_ARG(ns * stage <= budget, "wgrad: stage does not fit shared memory (%zu bytes)", stage);
   p.nstages = ns;
   const size_t smem = ns * stage + 1024 + 256;
+  // TMA operand stages (clip-aligned column groups) for plain bf16 launches on whole 64-channel chunks
+  {
+    const char* tma_str = getenv("FMM_WG_TMA");
+    const int use_tma = tma_str ? atoi(tma_str) : 1;
+    if (use_tma && dtype == FMM_DT_BF16 && !in_scale && Cin % 64 == 0 && Cout % 64 == 0 && Cout % p.BN == 0 && p.win_atoms <= 256 && p.JT <= 256) {
+      WgradParams q = p;
+      const int gpc = (V + 7) / 8;
+      q.ngroups = N * gpc;
+      q.total_units = q.ngroups * q.njchunks;
+      int sl = num_sms() / q.items;
+      if (sl < 1) sl = 1;
+      if (sl > q.total_units) sl = q.total_units;
+      q.slices = sl;
+      CUtensorMap tm_x, tm_dy;
+      if (make_tmap_act(&tm_x, x, N, Tin, V, Cin, q.win_atoms) && make_tmap_act(&tm_dy, dy, N, Tj, V, Cout, q.JT)) {
+        cudaError_t e2;
+        if (ntaps > 1) {
+          e2 = cudaFuncSetAttribute(wgrad_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e2 == cudaSuccess) wgrad_tma_kernel<true><<<q.items * q.slices, kWgThreads, smem, stream>>>(q, tm_x, tm_dy);
+        } else {
+          e2 = cudaFuncSetAttribute(wgrad_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e2 == cudaSuccess) wgrad_tma_kernel<false><<<q.items * q.slices, kWgThreads, smem, stream>>>(q, tm_x, tm_dy);
+        }
+        if (e2 != cudaSuccess) {
+          set_last_error("wgrad (tma): smem attribute: %s", cudaGetErrorString(e2));
+          return FMM_ERR_SMEM;
+        }
+        FMM_CHECK_LAUNCH("wgrad (tma)");
+        return FMM_OK;
+      }
+    }
+  }
   const int grid = p.items * p.slices;
   cudaError_t e;
 #define FMM_LAUNCH_WGRAD(TT, TAPS)                                                                               \

@@ -626,7 +626,10 @@ int fmm_wgrad(const void* x, const void* dy, float* dw, const float* in_scale, c
   {
     const char* tma_str = getenv("FMM_WG_TMA");
     const int use_tma = tma_str ? atoi(tma_str) : 1;
-    if (use_tma && dtype == FMM_DT_BF16 && !in_scale && Cin % 64 == 0 && Cout % 64 == 0 && Cout % p.BN == 0 && p.win_atoms <= 256 && p.JT <= 256) {
+    // (64-channel inputs keep the cp.async producers: their tap-pair N = 64 MMAs are shared-memory bound and the 21 % of
+    // zero-padded columns cost more than the producers did: 78.8 us against 72.7 us at 64 -> 64, T = 64; FMM_WG_TMA=2 forces TMA)
+    if (use_tma && (Cin >= 128 || use_tma >= 2) && dtype == FMM_DT_BF16 && !in_scale && Cin % 64 == 0 && Cout % 64 == 0 && Cout % p.BN == 0 &&
+        p.win_atoms <= 256 && p.JT <= 256) {
       WgradParams q = p;
       const int gpc = (V + 7) / 8;
       q.ngroups = N * gpc;

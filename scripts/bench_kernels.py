@@ -75,6 +75,9 @@ wg("tcn_wgrad_b1", 64, 64, 64, 9, 1, True)
 wg("tcn_wgrad_b4", 32, 128, 128, 9, 1, True)
 wg("tcn_wgrad_b5", 32, 256, 256, 9, 2, True)
 wg("tcn_wgrad_b6", 16, 256, 256, 9, 1, True)
+wg("tcn_wgrad_plain_b1", 64, 64, 64, 9, 1, False)
+wg("tcn_wgrad_plain_b3", 64, 128, 128, 9, 2, False)
+wg("tcn_wgrad_plain_b5", 32, 256, 256, 9, 2, False)
 wg("tcn_wgrad_plain_b6", 16, 256, 256, 9, 1, False)
 wg("tcn_wgrad_plain_b4", 32, 128, 128, 9, 1, False)
 wg("gcn_wgrad_b1", 64, 192, 64, 1, 1, False)

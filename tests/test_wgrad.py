@@ -16,6 +16,12 @@ CASES = [
     ("t9_s2_c128", 2, 31, 7, 128, 128, list(range(-4, 5)), 2, True),
     ("t9_s1_c256", 2, 16, 9, 256, 256, list(range(-4, 5)), 1, True),
     ("big_rows", 16, 64, 33, 64, 64, list(range(-4, 5)), 1, True),
+    # plain operands with >= 128 input channels: tensor-map TMA stages on clip-aligned column groups (V = 33: 5 groups per
+    # clip, the last one 1 joint + 7 zero columns; V = 14: 6 zero columns; frames outside the clip zero-filled by the TMA)
+    ("t9_s1_c128_tma", 5, 40, 33, 128, 128, list(range(-4, 5)), 1, False),
+    ("t9_s2_c256_tma", 3, 31, 14, 256, 256, list(range(-4, 5)), 2, False),
+    ("t9_c256_t16_tma", 11, 16, 33, 256, 256, list(range(-4, 5)), 1, False),
+    ("t5_c128_256_tma", 4, 23, 25, 128, 256, [2, 1, 0, -1, -2], 1, False),
 ]
 
 

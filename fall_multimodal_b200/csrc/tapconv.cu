@@ -173,7 +173,10 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
     const int pt = threadIdx.x;       // 0..255
     const int pc = pt & 7;            // 16-byte piece = 8 channels
     const int q = (pt >> 3) & 7;      // column inside the group
-    const int a0 = pt >> 6;           // atoms a0, a0+4, ...
+    // atoms a0, a0+4, ...; a single-tap strided conv (the residual 1x1, stride 2) only ever reads every istride-th frame of its
+    // window through the descriptor's SBO, so only those atoms are fetched: a0*is, (a0+4)*is, ...
+    const int askip = (p.ntaps == 1) ? p.istride : 1;
+    const int a0 = (pt >> 6) * askip;
     const bool vec_ok = (p.Cin % 8) == 0;
     const bool affine = p.in_scale != nullptr;
     const size_t pitch_t = static_cast<size_t>(p.V) * p.Cin;
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
             for (int g = 0; g < 2; ++g) {
               if (g < MTG) {
                 const bool col_ok = i_colok[g] && cb < p.Cin;
-                cpasync_issue_chunk(i_colp[g] + (col_ok ? cb : 0), pitch_t, col_ok, p.Tin, i_tlo, p.win_atoms, a0, 4,
+                cpasync_issue_chunk(i_colp[g] + (col_ok ? cb : 0), pitch_t, col_ok, p.Tin, i_tlo, p.win_atoms, a0, 4 * askip,
                                     slots0 + i_slot * slot_bytes + static_cast<uint32_t>(g * p.win_atoms) * 1024u + q * 128u + ((pc ^ q) << 4));
               }
             }
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
               sc[i] = ok ? p.in_scale[cb + i] : 1.f;
               sh[i] = ok ? p.in_shift[cb + i] : 0.f;
             }
-            inplace_affine_chunk(col_ok, p.Tin, t_lo, p.win_atoms, a0, 4, sc, sh, p.in_relu != 0,
+            inplace_affine_chunk(col_ok, p.Tin, t_lo, p.win_atoms, a0, 4 * askip, sc, sh, p.in_relu != 0,
                                  slots0 + slot * slot_bytes + q * 128u + ((pc ^ q) << 4));
           }
           fence_proxy_async_smem();
@@ -291,10 +294,10 @@ __global__ void __launch_bounds__((10 + kEpi) * 32, 1) tapconv_kernel(const __gr
         mbar_wait(win_empty(slot), ph ^ 1u, p.err, 1);
         const uint32_t sdst = slots0 + slot * slot_bytes + q * 128u + ((pc ^ q) << 4);
         if (affine)
-          produce_chunk<T, kParts, true>(colp + cb, pitch_t, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4, p.Cin - cb, vec_ok,
+          produce_chunk<T, kParts, true>(colp + cb, pitch_t, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4 * askip, p.Cin - cb, vec_ok,
                                          sc, sh, p.in_relu != 0, sdst, part_bytes_a);
         else
-          produce_chunk<T, kParts, false>(colp + cb, pitch_t, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4, p.Cin - cb, vec_ok,
+          produce_chunk<T, kParts, false>(colp + cb, pitch_t, col_ok, p.Tin, t_lo, p.win_atoms, a0, 4 * askip, p.Cin - cb, vec_ok,
                                           sc, sh, false, sdst, part_bytes_a);
         fence_proxy_async_smem();
         arrive_leader(win_full(slot));

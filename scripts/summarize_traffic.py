@@ -36,6 +36,7 @@ def klass(name):
         return a in ("1", "true", "(bool)1")
     if "fmm::tapconv_kernel<" in name: return "tapconv_taps" if arg(name, "tapconv_kernel", 2) else "tapconv_1x1"
     if "fmm::wgrad_kernel<" in name: return "wgrad_taps" if arg(name, "wgrad_kernel", 1) else "wgrad_1x1"
+    if "fmm::wgrad_tma_kernel<" in name: return "wgrad_taps" if arg(name, "wgrad_tma_kernel", 0) else "wgrad_1x1"
     return None
 
 

@@ -147,6 +147,10 @@ _SIGNATURES = {
     "fmm_bgemm": [_P, _P],
     "fmm_tg_cell_fwd": [_P, c_int, _P],
     "fmm_tg_cell_bwd": [_P, c_int, _P],
+    "fmm_gruscan_geometry": [c_int, _P, _P],
+    "fmm_gruscan": [_P, c_int, _P],
+    "fmm_gruscan_export_xc": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_gruscan_export_fs": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
     "fmm_tg_softmax_fwd": [_P, c_ll, c_int, c_int, c_int, _P],
     "fmm_tg_softmax_bwd": [_P, _P, c_ll, c_int, c_int, c_int, _P],
     "fmm_tg_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, c_ll, c_int, c_float, c_int, _P],
@@ -182,6 +186,12 @@ CellBwdArgs = _struct("CellBwdArgs", [
     (c_void_p, "S carry dz dxc0 dxc1 dx"), (c_ll, "dxb dxv"), (c_void_p, "hprev"), (c_ll, "hb hv"),
     (c_void_p, "zr lg dpre_g dlin_g dH"), (c_ll, "db dv"), (c_void_p, "z1 hprev1"), (c_ll, "hb1 hv1"),
     (c_void_p, "hc1 lu1 dpre_u dlin_u"), (c_int, "mode dx_accum do_bwd1 B V Din H Cp")])
+
+
+# mirror of fmm_gruscan_args (include/fmm_b200.h, csrc/gruscan.cu)
+GruScanArgs = _struct("GruScanArgs", [
+    (c_void_p, "xb px xcg xcu fs hout W Lw cs S bg bl dhout"), (c_ll, "dh_b dh_t dh_v"), (c_void_p, "dxu dxgz dxgr WT LT err"),
+    (c_int, "B T V KS xb_slices xb_slot0 NC tsplit")])
 
 
 # mirror of fmm_head_args (include/fmm_b200.h, csrc/head.cu)

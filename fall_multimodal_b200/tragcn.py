@@ -204,8 +204,15 @@ class _GraphGRUScan(Function):
 
     @staticmethod
     def backward(ctx, dH):
-        x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU = ctx.saved
+        saved = ctx.saved
         ctx.saved = None
+        return _bptt_steps(*saved, dH, ctx.need_dx)
+
+
+def _bptt_steps(x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU, dH, need_dx):
+    """Host-driven BPTT over the row-major saved tensors of one layer (4 launches per step), then the batched
+    GEMMs for dS and the weight gradients. Returns (dX, dS, dWg, dWu)."""
+    if True:
         with torch.autocast("cuda", enabled=False):
             dt = x.dtype
             B, T, V, Din = x.shape
@@ -224,7 +231,7 @@ class _GraphGRUScan(Function):
             Wg_d, Wu_d = Wg.clone(), Wu.clone()
             Wg_d[:, :, Cin:] = 0
             Wu_d[:, :, Cin:] = 0
-            dX = torch.empty(B, T, V, Din, dtype=dt, device=dev) if ctx.need_dx else None
+            dX = torch.empty(B, T, V, Din, dtype=dt, device=dev) if need_dx else None
             dims = (B, V, Din, H, Cp)
 
             def hp(t):
@@ -258,6 +265,120 @@ class _GraphGRUScan(Function):
                 bgemm(XC, 0, (T * B * V * Cp, Cp, 1, V * Cp, 0, 0), dPL, 0, (T * B * V * Co, Co, 1, V * Co, 0, 0),
                       dW, 0, (V * Cp * Co, Cp * Co, Co, 1), (2, V), Cp, Co, (T * B, 1, 1))
         return dX, dS, dWg, dWu
+
+
+# ------------------------------------------------------------------------------------------------
+# persistent scan (csrc/gruscan.cu): one launch per layer instead of 4 per time step
+# ------------------------------------------------------------------------------------------------
+_handoff = None    # (data_ptr of a layer's output, its blocked state tensor): the next layer reads its input already blocked
+
+
+def gruscan_geometry(V):
+    """(clips per cluster, joint slots per warp) of the persistent scan for V joints (fmm_gruscan_geometry)."""
+    return (32 if V <= 25 else 16), (2 if V <= 16 else 4)
+
+
+def gruscan_supported(x, H):
+    import os
+    return (x.dtype == torch.bfloat16 and H == 64 and x.shape[2] <= 32 and x.shape[1] >= 1
+            and os.environ.get("FMM_GRUSCAN", "1") != "0")
+
+
+def _block_input(x, S, BC, NC):
+    """x (B,T,V,Din) -> blocked (T,NC,KS,2,V,BC,8): slice pm=0 the input, pm=1 its adjacency mix, channels zero-padded to 16."""
+    B, T, V, Din = x.shape
+    Kx = (Din + 15) // 16 * 16
+    xp = x.new_zeros(NC * BC, T, V, Kx)
+    xp[:B, :, :, :Din] = x
+    xm = torch.einsum("nm,btmc->btnc", S, xp.float()).to(x.dtype)
+    st = torch.stack([xp, xm], 0).view(2, NC, BC, T, V, Kx // 8, 8)
+    return st.permute(3, 1, 5, 0, 4, 2, 6).contiguous()
+
+
+def _scan_call(mode, B, T, V, NC, **kw):
+    a = L.GruScanArgs()
+    for k in ("xb", "px", "xcg", "xcu", "fs", "hout", "W", "Lw", "cs", "S", "bg", "bl", "dhout", "dxu", "dxgz", "dxgr", "WT", "LT", "err"):
+        t = kw.get(k)
+        setattr(a, k, t.data_ptr() if t is not None else None)
+    a.dh_b, a.dh_t, a.dh_v = kw.get("dh_strides", (0, 0, 0))
+    a.B, a.T, a.V, a.NC = B, T, V, NC
+    a.KS, a.xb_slices, a.xb_slot0, a.tsplit = kw.get("KS", 8), kw.get("xb_slices", 8), kw.get("xb_slot0", 0), kw.get("tsplit", 1)
+    L.check(L.load().fmm_gruscan(C.byref(a), mode, L.stream()), "gruscan")
+
+
+class _GraphGRUScanP(Function):
+    """Same contract as _GraphGRUScan (one AVWDCRNN layer from the zero state) on the persistent kernels: the input
+    half of both EmbGCN products for all steps (gruscan mode 0), then ONE launch for the T recurrent steps (mode 1).
+    ``cs`` (V,) is the column scale folded into WW*[1] (EmbGCN.py:77), needed unfolded by the kernel."""
+
+    @staticmethod
+    def forward(ctx, x, S, WWg, WWu, cs):
+        global _handoff
+        with torch.autocast("cuda", enabled=False):
+            dt = x.dtype
+            B, T, V, Din = x.shape
+            H, Cp = 64, WWu.shape[2]
+            dev = x.device
+            need = any(ctx.needs_input_grad)
+            BC, NPW = gruscan_geometry(V)
+            NC = (B + BC - 1) // BC
+            ITEMS = 8 * NPW * (BC // 16)
+            S = S.contiguous().float()
+            cs = cs.contiguous().float()
+            WWg, WWu = WWg.float(), WWu.float()
+            Wh = torch.cat([WWg[0][:, :H], WWu[0][:, :H]], 2).to(dt).contiguous()                      # (V,64,192)
+            Lh = (torch.cat([WWg[1][0, :H], WWu[1][0, :H]], 1) / cs[0]).to(dt).contiguous()            # (64,192)
+            Kx = (Din + 15) // 16 * 16
+            Wx = torch.zeros(V, Kx, 3 * H, dtype=torch.float32, device=dev)
+            Wx[:, :Din] = torch.cat([WWg[0][:, H:H + Din], WWu[0][:, H:H + Din]], 2)
+            Lx = torch.zeros(Kx, 3 * H, dtype=torch.float32, device=dev)
+            Lx[:Din] = torch.cat([WWg[1][0, H:H + Din], WWu[1][0, H:H + Din]], 1) / cs[0]
+            bg = torch.cat([WWg[0][:, H + Din], WWu[0][:, H + Din]], 1).contiguous()                   # (V,192)
+            bl = torch.cat([WWg[1][0, H + Din], WWu[1][0, H + Din]]).contiguous()                      # (192,)
+            blk_shape = (NC, 8, 2, V, BC, 8)
+            if _handoff is not None and _handoff[0] == x.data_ptr() and tuple(_handoff[1].shape) == (T + 1, *blk_shape) and Din == H:
+                xb, xb_slices, slot0 = _handoff[1], 8, 1
+            else:
+                xb, xb_slices, slot0 = _block_input(x.contiguous(), S, BC, NC), Kx // 8, 0
+            _handoff = None
+            px = torch.empty(T, NC, 8, ITEMS, 3, 32, 8, dtype=dt, device=dev)
+            xcg = torch.empty(T + 1, *blk_shape, dtype=dt, device=dev)
+            xcg[0].zero_()
+            xcu = torch.empty(T, *blk_shape, dtype=dt, device=dev)
+            fs = torch.empty(T, NC, 8, ITEMS, 4, 32, 8, dtype=dt, device=dev) if need else None
+            Hout = torch.empty(B, T, V, H, dtype=dt, device=dev)
+            err = torch.zeros(1, dtype=torch.int32, device=dev)
+            _scan_call(0, B, T, V, NC, xb=xb, px=px, W=Wx.to(dt).contiguous(), Lw=Lx.to(dt).contiguous(), cs=cs, S=S, bg=bg, bl=bl, err=err,
+                       KS=Kx // 8, xb_slices=xb_slices, xb_slot0=slot0, tsplit=max(1, min(T, 18 // NC)))
+            _scan_call(1, B, T, V, NC, px=px, xcg=xcg, xcu=xcu, fs=fs, hout=Hout, W=Wh, Lw=Lh, cs=cs, S=S, err=err)
+            _handoff = (Hout.data_ptr(), xcg)
+            if need:
+                ctx.saved = (x, S, WWg.to(dt).contiguous(), WWu.to(dt).contiguous(), Hout, xcg, xcu, fs, xb, xb_slices, slot0, Kx // 8)
+                ctx.need_dx = ctx.needs_input_grad[0]
+        return Hout
+
+    @staticmethod
+    def backward(ctx, dH):
+        x, S, Wg, Wu, Hout, xcg, xcu, fs, xb, xb_slices, slot0, KS = ctx.saved
+        ctx.saved = None
+        with torch.autocast("cuda", enabled=False):
+            dt, dev = x.dtype, x.device
+            B, T, V, Din = x.shape
+            H, Cp = 64, Wu.shape[2]
+            lib = L.load()
+            XCg = torch.empty(2, T, B, V, Cp, dtype=dt, device=dev)
+            XCu = torch.empty(2, T, B, V, Cp, dtype=dt, device=dev)
+            for blk, out in ((xcg, XCg), (xcu, XCu)):
+                L.check(lib.fmm_gruscan_export_xc(blk.data_ptr(), xb.data_ptr(), out.data_ptr(), T, B, V, KS, xb_slices, slot0, Din, Cp,
+                                                  L.stream()), "gruscan_export_xc")
+            ZR = torch.empty(T, B, V, 2 * H, dtype=dt, device=dev)
+            LG = torch.empty(T, B, V, 2 * H, dtype=dt, device=dev)
+            HC = torch.empty(T, B, V, H, dtype=dt, device=dev)
+            LU = torch.empty(T, B, V, H, dtype=dt, device=dev)
+            L.check(lib.fmm_gruscan_export_fs(fs.data_ptr(), ZR.data_ptr(), LG.data_ptr(), HC.data_ptr(), LU.data_ptr(), T, B, V, L.stream()),
+                    "gruscan_export_fs")
+            del xcg, xcu, fs, xb
+        return (*_bptt_steps(x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU, dH, ctx.need_dx), None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -689,7 +810,13 @@ class AVWDCRNN(nn.Module):
             cur = x
             for cell in self.dcrnn_cells:
                 Cp = (cell.dim_in + cell.hidden_dim + 1 + 7) // 8 * 8
-                cur = _GraphGRUScan.apply(cur.contiguous(), S, cell.gate.stage_weights(E, Cp, cell.hidden_dim), cell.update.stage_weights(E, Cp, cell.hidden_dim))
+                Wg, Wu = cell.gate.stage_weights(E, Cp, cell.hidden_dim), cell.update.stage_weights(E, Cp, cell.hidden_dim)
+                if gruscan_supported(cur, cell.hidden_dim):
+                    cur = _GraphGRUScanP.apply(cur.contiguous(), S, Wg, Wu, cell.gate._colscale)
+                else:
+                    cur = _GraphGRUScan.apply(cur.contiguous(), S, Wg, Wu)
+            global _handoff
+            _handoff = None
         return self.trans_layer_T(cur)
 
 

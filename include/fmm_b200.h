@@ -327,6 +327,42 @@ typedef struct fmm_cell_bwd_args {
 int fmm_tg_cell_fwd(const fmm_cell_fwd_args* args, int dtype, cudaStream_t stream);
 int fmm_tg_cell_bwd(const fmm_cell_bwd_args* args, int dtype, cudaStream_t stream);
 
+/* Persistent graph-GRU scan (csrc/gruscan.cu; GRU.py:17-27 around EmbGCN.py:69-89, the time loop of
+ * TRAGCN.py:158-166 as ONE launch per layer and direction). bf16, 64 hidden channels, V <= 32 joints. Clusters of 8 CTAs
+ * own BC clips each (fmm_gruscan_geometry); CTA j of a cluster owns hidden channels 8j..8j+7 of every joint.
+ *   blocked state   XC[slot][cluster][8 slices][pm: 0 plain, 1 mixed][V][BC][8]
+ *   fragment order  PX[t][cluster][8][item][3][32 lanes][8], FS[...][4][32][8]; item = (warp * NPW + q) * (BC/16) + mt
+ * mode 0: input half of both EmbGCN products for every step (parallel over t, `tsplit` clusters per clip group);
+ * mode 1: forward scan (xcg slot t+1 / xcu slot t / fs / hout written);
+ * mode 2: backward scan (dxu / dxgz / dxgr slot t written: pre-activation gradients of the candidate, z and r products). */
+typedef struct fmm_gruscan_args {
+  const void* xb;
+  void* px;
+  void* xcg;
+  void* xcu;
+  void* fs;
+  void* hout;
+  const void* W;      /* [V][K][192] bf16, columns (z 64 | r 64 | candidate 64) */
+  const void* Lw;     /* [K][192] bf16 */
+  const float* cs;    /* [V] */
+  const float* S;     /* [V][V] */
+  const float* bg;    /* [V][192] */
+  const float* bl;    /* [192] */
+  const void* dhout; long long dh_b, dh_t, dh_v;
+  void* dxu; void* dxgz; void* dxgr;
+  const void* WT;     /* [V][192][64] bf16 */
+  const void* LT;     /* [192][64] bf16 */
+  unsigned* err;
+  int B, T, V, KS, xb_slices, xb_slot0, NC, tsplit;
+} fmm_gruscan_args;
+int fmm_gruscan_geometry(int V, int* BC, int* NPW);
+int fmm_gruscan(const fmm_gruscan_args* args, int mode, cudaStream_t stream);
+/* blocked state (+ blocked input) -> row-major [2: mixed, plain][T][B][V][Cp] with columns [h 64 | x Din | 1 | 0] */
+int fmm_gruscan_export_xc(const void* xc, const void* xb, void* out, int T, int B, int V, int KS, int xb_slices, int xb_slot0,
+                          int Din, int Cp, cudaStream_t stream);
+/* fragment-order gate values -> ZR, LG [T][B][V][128], HC, LU [T][B][V][64] */
+int fmm_gruscan_export_fs(const void* fs, void* ZR, void* LG, void* HC, void* LU, int T, int B, int V, cudaStream_t stream);
+
 /* Time-axis attention pieces (TA.py:55-68): in-place row softmax over the first L of Lp entries (+ backward,
  * written over dp), LayerNorm over C of (a + b) with saved mean/rstd (+ backward; dgamma/dbeta accumulate),
  * positional encoding add, ReLU mask. */

@@ -148,6 +148,7 @@ _SIGNATURES = {
     "fmm_tg_cell_fwd": [_P, c_int, _P],
     "fmm_tg_cell_bwd": [_P, c_int, _P],
     "fmm_gruscan_geometry": [c_int, _P, _P],
+    "fmm_gruscan_max_clusters": [c_int],
     "fmm_gruscan": [_P, c_int, _P],
     "fmm_gruscan_export_xc": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_gruscan_export_fs": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
@@ -190,7 +191,7 @@ CellBwdArgs = _struct("CellBwdArgs", [
 
 # mirror of fmm_gruscan_args (include/fmm_b200.h, csrc/gruscan.cu)
 GruScanArgs = _struct("GruScanArgs", [
-    (c_void_p, "xb px xcg xcu fs hout W Lw cs S bg bl dhout"), (c_ll, "dh_b dh_t dh_v"), (c_void_p, "dxu dxgz dxgr WT LT err"),
+    (c_void_p, "xb px xcg xcu fs hout W Lw cs S bg bl dhout"), (c_ll, "dh_b dh_t dh_v"), (c_void_p, "dxu dxgz dxgr WT LT err prof"),
     (c_int, "B T V KS xb_slices xb_slot0 NC tsplit")])
 
 

@@ -45,6 +45,7 @@ struct GruScanArgs {
   const void* WT;    // [V][192][64] bf16: WT[n][col][k] = W[n][k][col]
   const void* LT;    // [192][64]
   unsigned* err;
+  unsigned long long* prof;   // dev aid: 16 cycle counters of cluster 0 / CTA 0 / thread 0 (null: off)
   int B, T, V, KS, xb_slices, xb_slot0, NC, tsplit;
 };
 
@@ -90,7 +91,13 @@ __device__ __forceinline__ uint32_t pk(float a, float b) {
 __device__ __forceinline__ float lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 __device__ __forceinline__ float rb(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
-__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + __expf(-x)); }
+// one MUFU each (tanh.approx: relative error 2^-11, below the bf16 rounding every gate value gets)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 __device__ __forceinline__ float dsilu(float x) {
   const float s = sigm(x);
   return s * (1.f + x * (1.f - s));
@@ -241,6 +248,14 @@ __global__ void __launch_bounds__(NT, 1) gruscan_kernel(const GruScanArgs p) {
 
   uint32_t ph = 0;
   bf16* px = reinterpret_cast<bf16*>(p.px);
+  const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long pt = prof_on ? clock64() : 0;
+#define GS_PROF(slot)                                  \
+  if (prof_on) {                                       \
+    const long long now = clock64();                   \
+    atomicAdd(&p.prof[slot], (unsigned long long)(now - pt)); \
+    pt = now;                                          \
+  }
 
   if constexpr (MODE == 0) {
     const bf16* xb = reinterpret_cast<const bf16*>(p.xb);
@@ -312,22 +327,35 @@ __global__ void __launch_bounds__(NT, 1) gruscan_kernel(const GruScanArgs p) {
 
     for (int t = 0; t < T; ++t) {
       const size_t blk = ((size_t)t * NC + nc) * CL + j;
+      // next step's input half -> L2 while this step runs (the loads below then see L2 latency, not DRAM latency)
+      if (t + 1 < T) {
+        const char* nx = reinterpret_cast<const char*>(px + (((blk + (size_t)NC * CL) * ITEMS + (size_t)w * NPW * MT) * 3) * 256);
+#pragma unroll
+        for (int i = 0; i < (NPW * MT * 3 * 4 + 31) / 32; ++i)
+          if (lane + 32 * i < NPW * MT * 3 * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)(lane + 32 * i) * 128));
+      }
       // ------------------------------------------------ gate half step: z, r (GRU.py:21-22)
       if (t > 0) {
         mbar_wait(bar, ph & 1, p.err, 2);
         ++ph;
       }
+      GS_PROF(0)
       {
         bf16* xu = xcu + blk * slice_el;   // this CTA's slice: [pm][V][BC][8]
+        const bf16* pxw = px + ((blk * ITEMS + (size_t)w * NPW * MT) * 3) * 256 + lane * 8;   // this warp's items of step t
+        uint4 n0 = *reinterpret_cast<const uint4*>(pxw), n1 = *reinterpret_cast<const uint4*>(pxw + 256);
 #pragma unroll
-        for (int q = 0; q < NPW; ++q) {
+        for (int it = 0; it < NPW * MT; ++it) {
+          const int q = it / MT, mt = it % MT;
           const int n = w + 8 * q;
-          if (n >= V) continue;
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
+          if (n >= V) break;
+          {
             const int item = (w * NPW + q) * MT + mt;
-            const bf16* pxi = px + ((blk * ITEMS + item) * 3) * 256 + lane * 8;
-            const uint4 c0 = *reinterpret_cast<const uint4*>(pxi), c1 = *reinterpret_cast<const uint4*>(pxi + 256);
+            const uint4 c0 = n0, c1 = n1;
+            if (it + 1 < NPW * MT && w + 8 * ((it + 1) / MT) < V) {
+              n0 = *reinterpret_cast<const uint4*>(pxw + (it + 1) * 768);
+              n1 = *reinterpret_cast<const uint4*>(pxw + (it + 1) * 768 + 256);
+            }
             float a1[2][4], a2[2][4];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
@@ -376,10 +404,14 @@ __global__ void __launch_bounds__(NT, 1) gruscan_kernel(const GruScanArgs p) {
             }
           }
         }
+        GS_PROF(1)
         __syncthreads();
         mix_slice<MT>(stg, ssm, V, VP, w, lane, xu + (size_t)V * BC * 8);
+        GS_PROF(2)
         publish_global();
+        GS_PROF(3)
         cluster_sync_all();
+        GS_PROF(4)
         if (threadIdx.x == 0) {
           mbar_arrive_expect_tx(bar, CL * slice_bytes);
           bulk_g2s_mc(buf + j * slice_bytes, xu, slice_bytes, bar, (uint16_t)0xff);
@@ -388,17 +420,20 @@ __global__ void __launch_bounds__(NT, 1) gruscan_kernel(const GruScanArgs p) {
       // ------------------------------------------------ candidate half step + state update (GRU.py:23-26)
       mbar_wait(bar, ph & 1, p.err, 3);
       ++ph;
+      GS_PROF(5)
       {
         bf16* xg = xcg + (((size_t)(t + 1) * NC + nc) * CL + j) * slice_el;
+        const bf16* pxw = px + ((blk * ITEMS + (size_t)w * NPW * MT) * 3) * 256 + lane * 8 + 512;
+        uint4 n2 = *reinterpret_cast<const uint4*>(pxw);
 #pragma unroll
-        for (int q = 0; q < NPW; ++q) {
+        for (int it = 0; it < NPW * MT; ++it) {
+          const int q = it / MT, mt = it % MT;
           const int n = w + 8 * q;
-          if (n >= V) continue;
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
+          if (n >= V) break;
+          {
             const int item = (w * NPW + q) * MT + mt;
-            const bf16* pxi = px + ((blk * ITEMS + item) * 3) * 256 + lane * 8;
-            const uint4 c2 = *reinterpret_cast<const uint4*>(pxi + 512);
+            const uint4 c2 = n2;
+            if (it + 1 < NPW * MT && w + 8 * ((it + 1) / MT) < V) n2 = *reinterpret_cast<const uint4*>(pxw + (it + 1) * 768);
             float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
@@ -417,7 +452,7 @@ __global__ void __launch_bounds__(NT, 1) gruscan_kernel(const GruScanArgs p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               lu[i] = csn * a2[i] + lxu[i];
-              hc[i] = rb(tanhf(a1[i] + pxu[i] + lu[i] * sigm(lu[i])));
+              hc[i] = rb(tanh_fast(a1[i] + pxu[i] + lu[i] * sigm(lu[i])));
               hn[i] = zv[i] * hp[i] + (1.f - zv[i]) * hc[i];
             }
             if (fs) {
@@ -437,10 +472,14 @@ __global__ void __launch_bounds__(NT, 1) gruscan_kernel(const GruScanArgs p) {
             }
           }
         }
+        GS_PROF(6)
         __syncthreads();
         mix_slice<MT>(stg, ssm, V, VP, w, lane, xg + (size_t)V * BC * 8);
+        GS_PROF(7)
         publish_global();
+        GS_PROF(8)
         cluster_sync_all();
+        GS_PROF(9)
         if (t + 1 < T && threadIdx.x == 0) {
           mbar_arrive_expect_tx(bar, CL * slice_bytes);
           bulk_g2s_mc(buf + j * slice_bytes, xg, slice_bytes, bar, (uint16_t)0xff);
@@ -562,6 +601,39 @@ int fmm_gruscan_geometry(int V, int* BC, int* NPW) {
   if (BC) *BC = V <= 25 ? 32 : 16;
   if (NPW) *NPW = V <= 16 ? 2 : 4;
   return 1;
+}
+
+// how many clusters of the forward scan can be resident at once on the current device (cudaOccupancyMaxActiveClusters)
+int fmm_gruscan_max_clusters(int V) {
+  using namespace fmm;
+  if (V < 1 || V > 32) return 0;
+  int n = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gs::CL * 64);
+  cfg.blockDim = dim3(gs::NT);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = gs::CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+#define FMM_GS_OCC(NPW, MT)                                                                                   \
+  do {                                                                                                        \
+    cfg.dynamicSmemBytes = gs::smem_bytes<MT>(V);                                                             \
+    cudaFuncSetAttribute(gs::gruscan_kernel<NPW, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes); \
+    e = cudaOccupancyMaxActiveClusters(&n, gs::gruscan_kernel<NPW, MT, 1>, &cfg);                            \
+  } while (0)
+  if (V <= 16) FMM_GS_OCC(2, 2);
+  else if (V <= 25) FMM_GS_OCC(4, 2);
+  else FMM_GS_OCC(4, 1);
+#undef FMM_GS_OCC
+  if (e != cudaSuccess) {
+    set_last_error("gruscan_max_clusters: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return n;
 }
 
 // mode 0: input half of both EmbGCN products for all steps; mode 1: forward scan

@@ -270,6 +270,7 @@ def _bptt_steps(x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU, dH, need_dx):
 # ------------------------------------------------------------------------------------------------
 # persistent scan (csrc/gruscan.cu): one launch per layer instead of 4 per time step
 # ------------------------------------------------------------------------------------------------
+scan_prof = None   # dev aid: {mode: int64 cuda tensor of 16 counters} -> per-segment cycles of cluster 0 / CTA 0 (csrc/gruscan.cu)
 _handoff = None    # (data_ptr of a layer's output, its blocked state tensor): the next layer reads its input already blocked
 
 
@@ -297,10 +298,12 @@ def _block_input(x, S, BC, NC):
 
 def _scan_call(mode, B, T, V, NC, **kw):
     a = L.GruScanArgs()
-    for k in ("xb", "px", "xcg", "xcu", "fs", "hout", "W", "Lw", "cs", "S", "bg", "bl", "dhout", "dxu", "dxgz", "dxgr", "WT", "LT", "err"):
+    for k in ("xb", "px", "xcg", "xcu", "fs", "hout", "W", "Lw", "cs", "S", "bg", "bl", "dhout", "dxu", "dxgz", "dxgr", "WT", "LT", "err", "prof"):
         t = kw.get(k)
         setattr(a, k, t.data_ptr() if t is not None else None)
     a.dh_b, a.dh_t, a.dh_v = kw.get("dh_strides", (0, 0, 0))
+    if scan_prof is not None and mode in scan_prof:
+        a.prof = scan_prof[mode].data_ptr()
     a.B, a.T, a.V, a.NC = B, T, V, NC
     a.KS, a.xb_slices, a.xb_slot0, a.tsplit = kw.get("KS", 8), kw.get("xb_slices", 8), kw.get("xb_slot0", 0), kw.get("tsplit", 1)
     L.check(L.load().fmm_gruscan(C.byref(a), mode, L.stream()), "gruscan")

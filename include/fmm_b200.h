@@ -353,9 +353,11 @@ typedef struct fmm_gruscan_args {
   const void* WT;     /* [V][192][64] bf16 */
   const void* LT;     /* [192][64] bf16 */
   unsigned* err;
+  unsigned long long* prof; /* dev aid: 16 cycle counters (null: off) */
   int B, T, V, KS, xb_slices, xb_slot0, NC, tsplit;
 } fmm_gruscan_args;
 int fmm_gruscan_geometry(int V, int* BC, int* NPW);
+int fmm_gruscan_max_clusters(int V); /* resident clusters of the scan on the current device */
 int fmm_gruscan(const fmm_gruscan_args* args, int mode, cudaStream_t stream);
 /* blocked state (+ blocked input) -> row-major [2: mixed, plain][T][B][V][Cp] with columns [h 64 | x Din | 1 | 0] */
 int fmm_gruscan_export_xc(const void* xc, const void* xb, void* out, int T, int B, int V, int KS, int xb_slices, int xb_slot0,

@@ -152,6 +152,7 @@ _SIGNATURES = {
     "fmm_gruscan": [_P, c_int, _P],
     "fmm_gruscan_export_xc": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_gruscan_export_fs": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
+    "fmm_tattn": [_P, c_int, _P],
     "fmm_tg_softmax_fwd": [_P, c_ll, c_int, c_int, c_int, _P],
     "fmm_tg_softmax_bwd": [_P, _P, c_ll, c_int, c_int, c_int, _P],
     "fmm_tg_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, c_ll, c_int, c_float, c_int, _P],
@@ -193,6 +194,10 @@ CellBwdArgs = _struct("CellBwdArgs", [
 GruScanArgs = _struct("GruScanArgs", [
     (c_void_p, "xb px xcg xcu fs hout W Lw cs S bg bl dhout"), (c_ll, "dh_b dh_t dh_v"), (c_void_p, "dxu dxgz dxgr WT LT err prof"),
     (c_int, "B T V KS xb_slices xb_slot0 NC tsplit")])
+
+
+# mirror of fmm_tattn_args (include/fmm_b200.h, csrc/tattn.cu)
+TAttnArgs = _struct("TAttnArgs", [(c_void_p, "q k v out lse dout dq dk dv"), (c_int, "B V T Tp F"), (c_float, "scale")])
 
 
 # mirror of fmm_head_args (include/fmm_b200.h, csrc/head.cu)

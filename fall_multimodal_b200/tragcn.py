@@ -573,6 +573,51 @@ class _Attention(Function):
         return dq, dk, dv
 
 
+def tattn_supported(q, v):
+    import os
+    return (q.dtype == torch.bfloat16 and v.shape[3] == 64 and q.shape[1] <= 64 and q.shape[3] <= 320 and q.shape[3] % 64 == 0
+            and os.environ.get("FMM_TATTN", "1") != "0")
+
+
+class _AttentionF(Function):
+    """Same contract as _Attention on the flash-style kernels of csrc/tattn.cu: one launch per direction, the (B,V,T,T)
+    scores / probabilities are never written (only a (B*V,Tp) log-sum-exp is saved)."""
+
+    @staticmethod
+    def _args(q, k, v, out, lse, T):
+        a = L.TAttnArgs()
+        a.q, a.k, a.v, a.out, a.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr()
+        a.B, a.F, a.V, a.Tp = q.shape
+        a.T = T
+        a.scale = 1.0 / math.sqrt(v.shape[3])
+        return a
+
+    @staticmethod
+    def forward(ctx, q, k, v):
+        with torch.autocast("cuda", enabled=False):
+            q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+            B, F, V, Tp = q.shape
+            T, Cc = v.shape[2], v.shape[3]
+            out = torch.empty(B, T, V, Cc, dtype=q.dtype, device=q.device)
+            lse = torch.empty(B * V, Tp, dtype=torch.float32, device=q.device)
+            a = _AttentionF._args(q, k, v, out, lse, T)
+            L.check(L.load().fmm_tattn(C.byref(a), 0, L.stream()), "tattn")
+        ctx.saved = (q, k, v, out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, out, lse = ctx.saved
+        ctx.saved = None
+        with torch.autocast("cuda", enabled=False):
+            do = do.to(q.dtype).contiguous()
+            dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+            a = _AttentionF._args(q, k, v, out, lse, v.shape[2])
+            a.dout, a.dq, a.dk, a.dv = do.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+            L.check(L.load().fmm_tattn(C.byref(a), 1, L.stream()), "tattn")
+        return dq, dk, dv
+
+
 class _ValueProj(Function):
     """v = vff(x) (TA.py:45,50) written straight into (B,V,T,C) order; x (B,T,V,C)."""
 
@@ -758,7 +803,7 @@ class Transform(nn.Module):
         q = _TimeConv.apply(xT, self.conv1.weight, self.conv1.bias, T)
         k = _TimeConv.apply(xT, self.conv2.weight, self.conv2.bias, T)
         v = _ValueProj.apply(x, self.vff.weight, self.vff.bias)
-        att = _Attention.apply(q, k, v)
+        att = (_AttentionF if tattn_supported(q, v) else _Attention).apply(q, k, v)
         val = _LayerNorm2.apply(att, x, self.ln.weight, self.ln.bias, self.ln.eps)
         h = _Linear.apply(val, self.ff[0].weight, self.ff[0].bias, True, None)
         h = _Linear.apply(h, self.ff[2].weight, self.ff[2].bias, False, None)

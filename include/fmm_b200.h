@@ -365,6 +365,21 @@ int fmm_gruscan_export_xc(const void* xc, const void* xb, void* out, int T, int 
 /* fragment-order gate values -> ZR, LG [T][B][V][128], HC, LU [T][B][V][64] */
 int fmm_gruscan_export_fs(const void* fs, void* ZR, void* LG, void* HC, void* LU, int T, int B, int V, cudaStream_t stream);
 
+/* Flash-style time-axis attention (csrc/tattn.cu; TA.py:55-62 softmax(q k^T / sqrt(c), -1) v per (clip, joint)): one CTA per
+ * head, the (B,V,T,T) scores are never written. q, k feature-major (B,F,V,Tp) as the time-as-channel convolutions leave them,
+ * v (B,V,T,64), out / dout (B,T,V,64), lse (B*V,Tp) fp32 (log2 domain). bf16, F <= 64, Tp % 64 == 0, Tp <= 320.
+ * mode 0: forward (out, lse); mode 1: backward (dq, dk, dv; every column of dq / dk up to Tp is written). */
+typedef struct fmm_tattn_args {
+  const void* q; const void* k; const void* v;
+  void* out;
+  float* lse;
+  const void* dout;
+  void* dq; void* dk; void* dv;
+  int B, V, T, Tp, F;
+  float scale;
+} fmm_tattn_args;
+int fmm_tattn(const fmm_tattn_args* args, int mode, cudaStream_t stream);
+
 /* Time-axis attention pieces (TA.py:55-68): in-place row softmax over the first L of Lp entries (+ backward,
  * written over dp), LayerNorm over C of (a + b) with saved mean/rstd (+ backward; dgamma/dbeta accumulate),
  * positional encoding add, ReLU mask. */

@@ -151,6 +151,7 @@ _SIGNATURES = {
     "fmm_gruscan_max_clusters": [c_int],
     "fmm_gruscan": [_P, c_int, _P],
     "fmm_gruscan_export_xc": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "fmm_gruscan_export_dg": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
     "fmm_gruscan_export_fs": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
     "fmm_tattn": [_P, c_int, _P],
     "fmm_tg_softmax_fwd": [_P, c_ll, c_int, c_int, c_int, _P],

@@ -491,6 +491,289 @@ __global__ void __launch_bounds__(NT, 1) gruscan_kernel(const GruScanArgs p) {
 
 
 // ---------------------------------------------------------------------------------------------------------
+// Backward scan (BPTT of GRU.py:17-26 through both EmbGCN products, one launch per layer). Same ownership as the forward:
+// CTA j owns hidden channels 8j..8j+7 of every joint. Per step three exchanges of pre-activation gradients (candidate, z, r -
+// 64 channels each, so the two forward-sized state buffers suffice): every CTA stores its slice of (Linear-path, graph-path)
+// gradients to the blocked global tensors - which are also what the weight / input / supports gradients are computed from after
+// the sweep - and multicasts it to the cluster; the products dG . W_n^T (per-node weights transposed, this CTA's 8 output
+// channels, B fragments in registers) give the gradient of the mixed and of the plain stage input; the transposed adjacency mix
+// runs on the own slice in shared memory (S^T - I on the tensor core, in place), the identity and Linear-path terms stay fp32.
+// ---------------------------------------------------------------------------------------------------------
+// stg[m][clip][c] <- sum_n A[m][n] stg[n][clip][c] (A = the bf16 matrix at ssm), in place: each clip column belongs to one warp
+template <int MT>
+__device__ __forceinline__ void mix_inplace(uint32_t stg, uint32_t ssm, int V, int VP, int w, int lane) {
+  constexpr int BC = 16 * MT, CPW = BC / 8;
+  const int g = lane >> 2, tq = lane & 3;
+  const int nmt = VP >> 4;
+  uint32_t af[2][2][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+      if (mi < nmt && kk < nmt)
+        ldsm_x4(ssm + ((mi * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * (VP + 8) + kk * 16 + (lane >> 4) * 8) * 2, af[mi][kk]);
+#pragma unroll
+  for (int c = 0; c < CPW; ++c) {
+    const int cl = w * CPW + c;
+    float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+      if (kk < nmt) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(stg + ((kk * 16 + (lane & 15)) * BC + cl) * 16, b0, b1);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+          if (mi < nmt) mma16816(d[mi], af[mi][kk], b0, b1);
+      }
+    __syncwarp();
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int n = mi * 16 + g + 8 * half;
+        if (mi < nmt && n < V) sts32(stg + (n * BC + cl) * 16 + tq * 4, pk(d[mi][2 * half], d[mi][2 * half + 1]));
+      }
+  }
+}
+
+template <int NPW, int MT>
+__global__ void __launch_bounds__(NT, 1) gruscan_bwd_kernel(const GruScanArgs p) {
+  constexpr int BC = 16 * MT, ITEMS = NW * NPW * MT;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int V = p.V, VP = (V + 15) & ~15, T = p.T, NC = p.NC;
+  const uint32_t slice_bytes = 2u * V * BC * 16;
+  const size_t slice_el = (size_t)V * BC * 16;
+  const uint32_t buf = smem_u32(smem_raw);
+  const uint32_t stg = buf + CL * slice_bytes;
+  const uint32_t ls = stg + VP * BC * 16;
+  const uint32_t ssm = ls + 24 * 72 * 2;
+  const uint32_t csm_a = ssm + 32 * 40 * 2;
+  const uint32_t bar = csm_a + 32 * 4;
+  bf16* Ssm = reinterpret_cast<bf16*>(smem_raw + (ssm - buf));
+  float* csm = reinterpret_cast<float*>(smem_raw + (csm_a - buf));
+  const int j = (int)cluster_ctarank();
+  const int nc = blockIdx.x / CL;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+
+  // B fragments of W_n^T: product X (0 candidate, 1 z, 2 r) reads columns cb(X)..cb(X)+63 of row 8j+g of W[n] (64 x 192)
+  uint32_t wreg[NPW][24];
+  {
+    const uint32_t* W32 = reinterpret_cast<const uint32_t*>(p.W);
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+      const int n = w + 8 * q;
+#pragma unroll
+      for (int X = 0; X < 3; ++X)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int col = (X == 0 ? 128 : X == 1 ? 0 : 64) + ks * 16 + 2 * tq + 8 * r;
+            wreg[q][X * 8 + ks * 2 + r] = n < V ? W32[(((size_t)n * 64 + 8 * j + g) * 192 + col) >> 1] : 0u;
+          }
+    }
+    const uint16_t* Lu = reinterpret_cast<const uint16_t*>(p.Lw);
+    uint16_t* Lsu = reinterpret_cast<uint16_t*>(smem_raw + (ls - buf));
+    for (int i = threadIdx.x; i < 24 * 64; i += NT) {
+      const int c = i >> 6, k = i & 63, X = c >> 3;
+      Lsu[c * 72 + k] = Lu[(size_t)(8 * j + (c & 7)) * 192 + (X == 0 ? 128 : X == 1 ? 0 : 64) + k];
+    }
+    for (int i = threadIdx.x; i < VP * (VP + 8); i += NT) {
+      const int m = i / (VP + 8), n = i % (VP + 8);
+      float v = 0.f;
+      if (n < V && m < V) v = p.S[n * V + m] - (n == m ? 1.f : 0.f);   // transposed: row m of the A operand holds S[:, m]
+      Ssm[i] = __float2bfloat16_rn(v);
+    }
+    if (threadIdx.x < 32) csm[threadIdx.x] = (threadIdx.x < V) ? p.cs[threadIdx.x] : 0.f;
+    for (int i = threadIdx.x; i < VP * BC * 4; i += NT) sts32(stg + i * 4, 0u);
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+
+  const bf16* fs = reinterpret_cast<const bf16*>(p.fs);
+  const bf16* dho = reinterpret_cast<const bf16*>(p.dhout);
+  bf16* dxu = reinterpret_cast<bf16*>(p.dxu);
+  bf16* dxgz = reinterpret_cast<bf16*>(p.dxgz);
+  bf16* dxgr = reinterpret_cast<bf16*>(p.dxgr);
+  float carry[NPW][MT][4];
+  uint32_t dpart[NPW][MT][2];
+#pragma unroll
+  for (int q = 0; q < NPW; ++q)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) carry[q][mt][i] = 0.f;
+      dpart[q][mt][0] = dpart[q][mt][1] = 0u;
+    }
+  uint32_t ph = 0;
+  const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long pt = prof_on ? clock64() : 0;
+
+  // products of one phase: graph path (mixed-input gradient before the mix) -> stg, identity + Linear path -> `direct`
+  auto send = [&](const bf16* src) {
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(bar, CL * slice_bytes);
+      bulk_g2s_mc(buf + j * slice_bytes, src, slice_bytes, bar, (uint16_t)0xff);
+    }
+  };
+
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t blk = ((size_t)t * NC + nc) * CL + j;
+    const bf16* fsw = fs + ((blk * ITEMS + (size_t)w * NPW * MT) * 4) * 256 + lane * 8;
+    bf16* su = dxu + blk * slice_el;
+    bf16* sz = dxgz + blk * slice_el;
+    bf16* sr = dxgr + blk * slice_el;
+    if (t > 0) {   // previous step's saved gate values -> L2
+      const char* nx = reinterpret_cast<const char*>(fs + (((blk - (size_t)NC * CL) * ITEMS + (size_t)w * NPW * MT) * 4) * 256);
+#pragma unroll
+      for (int i = 0; i < (NPW * MT * 4 * 4 + 31) / 32; ++i)
+        if (lane + 32 * i < NPW * MT * 4 * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)(lane + 32 * i) * 128));
+    }
+    // ------------------------------------------------ A: state update and candidate backward (elementwise)
+#pragma unroll
+    for (int it = 0; it < NPW * MT; ++it) {
+      const int q = it / MT, mt = it % MT;
+      const int n = w + 8 * q;
+      if (n >= V) break;
+      const uint4 c0 = *reinterpret_cast<const uint4*>(fsw + it * 1024), c1 = *reinterpret_cast<const uint4*>(fsw + it * 1024 + 256),
+                  c2 = *reinterpret_cast<const uint4*>(fsw + it * 1024 + 512), c3 = *reinterpret_cast<const uint4*>(fsw + it * 1024 + 768);
+      float z[4], hc[4], hp[4], lgz[4], lu[4], g1u[4], g2u[4], g1z[4], g2z[4];
+      unpack4(c0.x, c0.y, z); unpack4(c1.x, c1.y, hc); unpack4(c1.z, c1.w, hp); unpack4(c2.x, c2.y, lgz); unpack4(c3.x, c3.y, lu);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int b = nc * BC + mt * 16 + g + 8 * half;
+        float d0 = 0.f, d1 = 0.f;
+        if (b < p.B) {
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(dho + (size_t)b * p.dh_b + (size_t)t * p.dh_t + (size_t)n * p.dh_v + 8 * j + 2 * tq);
+          d0 = lo(u);
+          d1 = hi(u);
+        }
+        carry[q][mt][2 * half] += d0;
+        carry[q][mt][2 * half + 1] += d1;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dh = carry[q][mt][i];
+        const float dz = dh * (hp[i] - hc[i]);
+        const float dpu = dh * (1.f - z[i]) * (1.f - hc[i] * hc[i]);
+        carry[q][mt][i] = dh * z[i];
+        g1u[i] = dpu;
+        g2u[i] = dpu * dsilu(lu[i]);
+        g1z[i] = dz * z[i] * (1.f - z[i]);
+        g2z[i] = g1z[i] * dsilu(lgz[i]);
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const size_t row = (size_t)n * BC + mt * 16 + g + 8 * half;
+        *reinterpret_cast<uint32_t*>(su + row * 8 + 2 * tq) = pk(g2u[2 * half], g2u[2 * half + 1]);                        // pm 0: Linear path
+        *reinterpret_cast<uint32_t*>(su + (size_t)V * BC * 8 + row * 8 + 2 * tq) = pk(g1u[2 * half], g1u[2 * half + 1]);   // pm 1: graph path
+        *reinterpret_cast<uint32_t*>(sz + row * 8 + 2 * tq) = pk(g2z[2 * half], g2z[2 * half + 1]);
+        *reinterpret_cast<uint32_t*>(sz + (size_t)V * BC * 8 + row * 8 + 2 * tq) = pk(g1z[2 * half], g1z[2 * half + 1]);
+      }
+    }
+    GS_PROF(0)
+    publish_global();
+    cluster_sync_all();
+    send(su);
+    GS_PROF(1)
+    // ------------------------------------------------ B, C, D: products of the candidate, z and r gradients
+#pragma unroll 1
+    for (int X = 0; X < 3; ++X) {
+      mbar_wait(bar, ph & 1, p.err, 4 + X);
+      ++ph;
+      GS_PROF(2)
+#pragma unroll
+      for (int it = 0; it < NPW * MT; ++it) {
+        const int q = it / MT, mt = it % MT;
+        const int n = w + 8 * q;
+        if (n >= V) break;
+        float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t am[4], ap[4];
+          ldsm_x4(a_addr(buf, slice_bytes, V, BC, 1, n, mt, ks, lane), am);
+          ldsm_x4(a_addr(buf, slice_bytes, V, BC, 0, n, mt, ks, lane), ap);
+          const uint32_t w0 = X == 0 ? wreg[q][ks * 2] : X == 1 ? wreg[q][8 + ks * 2] : wreg[q][16 + ks * 2];
+          const uint32_t w1 = X == 0 ? wreg[q][ks * 2 + 1] : X == 1 ? wreg[q][8 + ks * 2 + 1] : wreg[q][16 + ks * 2 + 1];
+          mma16816(a1, am, w0, w1);
+          const uint32_t la = ls + ((X * 8 + g) * 72 + ks * 16 + 2 * tq) * 2;
+          mma16816(a2, ap, lds32(la), lds32(la + 16));
+        }
+        const float csn = csm[n];
+        float dir[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dir[i] = a1[i] + csn * a2[i];
+        if (X == 0) {
+          const uint4 c0 = *reinterpret_cast<const uint4*>(fsw + it * 1024), c1 = *reinterpret_cast<const uint4*>(fsw + it * 1024 + 256);
+          float r[4], hp[4], part[4];
+          unpack4(c0.z, c0.w, r); unpack4(c1.z, c1.w, hp);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            carry[q][mt][i] += dir[i] * r[i];
+            part[i] = dir[i] * hp[i] * r[i] * (1.f - r[i]);
+          }
+          dpart[q][mt][0] = pk(part[0], part[1]);
+          dpart[q][mt][1] = pk(part[2], part[3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) carry[q][mt][i] += dir[i];
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) sts32(stg + ((n * BC + mt * 16 + g + 8 * half) * 16) + tq * 4, pk(a1[2 * half], a1[2 * half + 1]));
+      }
+      GS_PROF(3)
+      __syncthreads();
+      mix_inplace<MT>(stg, ssm, V, VP, w, lane);
+      __syncthreads();
+      GS_PROF(4)
+#pragma unroll
+      for (int it = 0; it < NPW * MT; ++it) {
+        const int q = it / MT, mt = it % MT;
+        const int n = w + 8 * q;
+        if (n >= V) break;
+        float mx[4];
+        unpack4(lds32(stg + ((n * BC + mt * 16 + g) * 16) + tq * 4), lds32(stg + ((n * BC + mt * 16 + g + 8) * 16) + tq * 4), mx);
+        if (X == 0) {
+          const uint4 c0 = *reinterpret_cast<const uint4*>(fsw + it * 1024), c1 = *reinterpret_cast<const uint4*>(fsw + it * 1024 + 256),
+                      c2 = *reinterpret_cast<const uint4*>(fsw + it * 1024 + 512);
+          float r[4], hp[4], lgr[4], part[4], g1r[4], g2r[4];
+          unpack4(c0.z, c0.w, r); unpack4(c1.z, c1.w, hp); unpack4(c2.z, c2.w, lgr);
+          unpack4(dpart[q][mt][0], dpart[q][mt][1], part);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            carry[q][mt][i] += mx[i] * r[i];
+            g1r[i] = part[i] + mx[i] * hp[i] * r[i] * (1.f - r[i]);
+            g2r[i] = g1r[i] * dsilu(lgr[i]);
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const size_t row = (size_t)n * BC + mt * 16 + g + 8 * half;
+            *reinterpret_cast<uint32_t*>(sr + row * 8 + 2 * tq) = pk(g2r[2 * half], g2r[2 * half + 1]);
+            *reinterpret_cast<uint32_t*>(sr + (size_t)V * BC * 8 + row * 8 + 2 * tq) = pk(g1r[2 * half], g1r[2 * half + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) carry[q][mt][i] += mx[i];
+        }
+      }
+      GS_PROF(5)
+      if (X < 2) {
+        if (X == 0) publish_global();
+        cluster_sync_all();
+        send(X == 0 ? sz : sr);
+        GS_PROF(6)
+      }
+      // after X == 2 the next step's phase A ends with the cluster barrier that orders the reuse of buf and stg
+    }
+  }
+  cluster_sync_all();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Export of the blocked / fragment-order tensors to the row-major tensors the batched GEMMs (weight gradients,
 // input gradients, dS) read: XC std = [2: mixed, plain][T][B][V][Cp] with the cell-input layout [h 64 | x Din | 1 | 0].
 // ---------------------------------------------------------------------------------------------------------
@@ -530,6 +813,29 @@ __global__ void __launch_bounds__(256) export_xc_kernel(const bf16* __restrict__
   }
 }
 
+// blocked pre-activation gradients -> dPLu [2: graph, Linear][T][B][V][64], dPLg [2][T][B][V][128] (z | r)
+__global__ void __launch_bounds__(256) export_dg_kernel(const bf16* __restrict__ dxu, const bf16* __restrict__ dxgz, const bf16* __restrict__ dxgr,
+                                                        bf16* __restrict__ dPLu, bf16* __restrict__ dPLg, int T, int B, int V, int NC, int BC) {
+  const int t = blockIdx.x / NC, nc = blockIdx.x % NC;
+  const size_t slice_el = (size_t)V * BC * 16;
+  const int total = 2 * V * BC * 24;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int k = i % 24;
+    int r = i / 24;
+    const int clip = r % BC;
+    r /= BC;
+    const int n = r % V, pstd = r / V;
+    const int b = nc * BC + clip;
+    if (b >= B) continue;
+    const int pm = 1 - pstd;
+    const bf16* src = k < 8 ? dxu : k < 16 ? dxgz : dxgr;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (((size_t)t * NC + nc) * CL + (k & 7)) * slice_el + ((size_t)(pm * V + n) * BC + clip) * 8);
+    const size_t row = (((size_t)pstd * T + t) * B + b) * V + n;
+    if (k < 8) *reinterpret_cast<uint4*>(dPLu + row * 64 + k * 8) = v;
+    else *reinterpret_cast<uint4*>(dPLg + row * 128 + (k - 8) * 8) = v;
+  }
+}
+
 // FS (fragment order) -> ZR, LG [T][B][V][128], HC, LU [T][B][V][64]
 __global__ void __launch_bounds__(256) export_fs_kernel(const bf16* __restrict__ fs, bf16* __restrict__ ZR, bf16* __restrict__ LG,
                                                         bf16* __restrict__ HC, bf16* __restrict__ LU, int T, int B, int V, int NC, int NPW,
@@ -562,8 +868,17 @@ __global__ void __launch_bounds__(256) export_fs_kernel(const bf16* __restrict__
 }
 
 template <int NPW, int MT, int MODE>
+struct ScanKernel {
+  static constexpr auto fn = gruscan_kernel<NPW, MT, MODE>;
+};
+template <int NPW, int MT>
+struct ScanKernel<NPW, MT, 2> {
+  static constexpr auto fn = gruscan_bwd_kernel<NPW, MT>;
+};
+
+template <int NPW, int MT, int MODE>
 int launch_scan(const GruScanArgs& a, cudaStream_t stream) {
-  auto kern = gruscan_kernel<NPW, MT, MODE>;
+  auto kern = ScanKernel<NPW, MT, MODE>::fn;
   const size_t smem = smem_bytes<MT>(a.V);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
@@ -636,16 +951,18 @@ int fmm_gruscan_max_clusters(int V) {
   return n;
 }
 
-// mode 0: input half of both EmbGCN products for all steps; mode 1: forward scan
+// mode 0: input half of both EmbGCN products for all steps; mode 1: forward scan; mode 2: backward scan
 int fmm_gruscan(const fmm::GruScanArgs* a, int mode, cudaStream_t stream) {
   using namespace fmm;
   FMM_CHECK_ARG(a && a->V >= 1 && a->V <= 32 && a->T >= 1 && a->B >= 1, "gruscan: bad sizes");
   const int BC = a->V <= 25 ? 32 : 16;
   FMM_CHECK_ARG(a->NC == (a->B + BC - 1) / BC, "gruscan: NC must be ceil(B / %d)", BC);
-  FMM_CHECK_ARG(mode == 0 || mode == 1, "gruscan: mode %d", mode);
+  FMM_CHECK_ARG(mode >= 0 && mode <= 2, "gruscan: mode %d", mode);
+  if (mode == 2) FMM_CHECK_ARG(a->fs && a->dhout && a->dxu && a->dxgz && a->dxgr, "gruscan: backward needs fs, dhout, dxu, dxgz, dxgr");
   if (mode == 0) FMM_CHECK_ARG(a->KS >= 2 && a->KS <= 8 && a->KS % 2 == 0 && a->tsplit >= 1 && a->xb_slices >= a->KS, "gruscan: bad xpart geometry");
   int rc;
-#define FMM_GS(NPW, MT) (mode == 0 ? gs::launch_scan<NPW, MT, 0>(*a, stream) : gs::launch_scan<NPW, MT, 1>(*a, stream))
+#define FMM_GS(NPW, MT) \
+  (mode == 0 ? gs::launch_scan<NPW, MT, 0>(*a, stream) : mode == 1 ? gs::launch_scan<NPW, MT, 1>(*a, stream) : gs::launch_scan<NPW, MT, 2>(*a, stream))
   if (a->V <= 16) rc = FMM_GS(2, 2);
   else if (a->V <= 25) rc = FMM_GS(4, 2);
   else rc = FMM_GS(4, 1);
@@ -663,6 +980,17 @@ int fmm_gruscan_export_xc(const void* xc, const void* xb, void* out, int T, int 
   gs::export_xc_kernel<<<T * NC, 256, 0, stream>>>(reinterpret_cast<const gs::bf16*>(xc), reinterpret_cast<const gs::bf16*>(xb),
                                                     reinterpret_cast<gs::bf16*>(out), T, B, V, NC, BC, KS, xb_slices, xb_slot0, Din, Cp);
   FMM_CHECK_LAUNCH("gruscan_export_xc");
+  return FMM_OK;
+}
+
+int fmm_gruscan_export_dg(const void* dxu, const void* dxgz, const void* dxgr, void* dPLu, void* dPLg, int T, int B, int V, cudaStream_t stream) {
+  using namespace fmm;
+  FMM_CHECK_ARG(V >= 1 && V <= 32, "gruscan_export_dg: bad sizes");
+  const int BC = V <= 25 ? 32 : 16, NC = (B + BC - 1) / BC;
+  gs::export_dg_kernel<<<T * NC, 256, 0, stream>>>(reinterpret_cast<const gs::bf16*>(dxu), reinterpret_cast<const gs::bf16*>(dxgz),
+                                                    reinterpret_cast<const gs::bf16*>(dxgr), reinterpret_cast<gs::bf16*>(dPLu),
+                                                    reinterpret_cast<gs::bf16*>(dPLg), T, B, V, NC, BC);
+  FMM_CHECK_LAUNCH("gruscan_export_dg");
   return FMM_OK;
 }
 

@@ -209,6 +209,27 @@ class _GraphGRUScan(Function):
         return _bptt_steps(*saved, dH, ctx.need_dx)
 
 
+def _bptt_tail(XCg, XCu, dXg, dXu, dPLg, dPLu, T, B, V, Cp, H):
+    """Batched GEMMs after the serial sweep: dS from the graph-path input gradients of every step (dXg / dXu, (>=T,B,V,Cp)),
+    the weight gradients of both stages from the saved stage inputs XC* (2,T,B,V,Cp) and pre-activation gradients dPL*."""
+    dev = XCg.device
+    if True:
+        if True:
+            # dS[n][m] = sum_{t,b,c} dXC0[t,b,n,c] cat[t,b,m,c] for both stages: split-K GEMMs over (t*b, c)
+            dS = torch.zeros(V, V, dtype=torch.float32, device=dev)
+            sk = _splitk(V, V, 1, T * B * Cp)
+            for dXs, XC in ((dXg, XCg), (dXu, XCu)):
+                bgemm(dXs, 0, (0, 0, Cp, V * Cp, 1, 0), XC[1], 0, (0, 0, Cp, V * Cp, 1, 0), dS, 0, (0, 0, V, 1), (1, 1), V, V,
+                      (T * B, Cp, 1), splitk=sk)
+            # weight gradients of both stages: one batched GEMM each over every (t, clip) pair
+            dWg = torch.empty(2, V, Cp, 2 * H, dtype=torch.float32, device=dev)
+            dWu = torch.empty(2, V, Cp, H, dtype=torch.float32, device=dev)
+            for XC, dPL, dW, Co in ((XCg, dPLg, dWg, 2 * H), (XCu, dPLu, dWu, H)):
+                bgemm(XC, 0, (T * B * V * Cp, Cp, 1, V * Cp, 0, 0), dPL, 0, (T * B * V * Co, Co, 1, V * Co, 0, 0),
+                      dW, 0, (V * Cp * Co, Cp * Co, Co, 1), (2, V), Cp, Co, (T * B, 1, 1))
+    return dS, dWg, dWu
+
+
 def _bptt_steps(x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU, dH, need_dx):
     """Host-driven BPTT over the row-major saved tensors of one layer (4 launches per step), then the batched
     GEMMs for dS and the weight gradients. Returns (dX, dS, dWg, dWu)."""
@@ -252,18 +273,7 @@ def _bptt_steps(x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU, dH, need_dx):
                              dpre_u=dPLu[0, t - 1], dlin_u=dPLu[1, t - 1])
                 else:
                     cell_bwd(2, dims, S, carry, DZ, dt, dxc0=dXg[t], dxc1=dXg[T], dx=dxt, dx_accum=True)
-            # dS[n][m] = sum_{t,b,c} dXC0[t,b,n,c] cat[t,b,m,c] for both stages: split-K GEMMs over (t*b, c)
-            dS = torch.zeros(V, V, dtype=torch.float32, device=dev)
-            sk = _splitk(V, V, 1, T * B * Cp)
-            for dXs, XC in ((dXg, XCg), (dXu, XCu)):
-                bgemm(dXs, 0, (0, 0, Cp, V * Cp, 1, 0), XC[1], 0, (0, 0, Cp, V * Cp, 1, 0), dS, 0, (0, 0, V, 1), (1, 1), V, V,
-                      (T * B, Cp, 1), splitk=sk)
-            # weight gradients of both stages: one batched GEMM each over every (t, clip) pair
-            dWg = torch.empty(2, V, Cp, 2 * H, dtype=torch.float32, device=dev)
-            dWu = torch.empty(2, V, Cp, H, dtype=torch.float32, device=dev)
-            for XC, dPL, dW, Co in ((XCg, dPLg, dWg, 2 * H), (XCu, dPLu, dWu, H)):
-                bgemm(XC, 0, (T * B * V * Cp, Cp, 1, V * Cp, 0, 0), dPL, 0, (T * B * V * Co, Co, 1, V * Co, 0, 0),
-                      dW, 0, (V * Cp * Co, Cp * Co, Co, 1), (2, V), Cp, Co, (T * B, 1, 1))
+            dS, dWg, dWu = _bptt_tail(XCg, XCu, dXg, dXu, dPLg, dPLu, T, B, V, Cp, H)
         return dX, dS, dWg, dWu
 
 
@@ -356,13 +366,14 @@ class _GraphGRUScanP(Function):
             _scan_call(1, B, T, V, NC, px=px, xcg=xcg, xcu=xcu, fs=fs, hout=Hout, W=Wh, Lw=Lh, cs=cs, S=S, err=err)
             _handoff = (Hout.data_ptr(), xcg)
             if need:
-                ctx.saved = (x, S, WWg.to(dt).contiguous(), WWu.to(dt).contiguous(), Hout, xcg, xcu, fs, xb, xb_slices, slot0, Kx // 8)
+                ctx.saved = (x, S, WWg.to(dt).contiguous(), WWu.to(dt).contiguous(), Hout, xcg, xcu, fs, xb, xb_slices, slot0, Kx // 8, Wh, Lh, cs)
                 ctx.need_dx = ctx.needs_input_grad[0]
         return Hout
 
     @staticmethod
     def backward(ctx, dH):
-        x, S, Wg, Wu, Hout, xcg, xcu, fs, xb, xb_slices, slot0, KS = ctx.saved
+        import os
+        x, S, Wg, Wu, Hout, xcg, xcu, fs, xb, xb_slices, slot0, KS, Wh, Lh, cs = ctx.saved
         ctx.saved = None
         with torch.autocast("cuda", enabled=False):
             dt, dev = x.dtype, x.device
@@ -374,14 +385,49 @@ class _GraphGRUScanP(Function):
             for blk, out in ((xcg, XCg), (xcu, XCu)):
                 L.check(lib.fmm_gruscan_export_xc(blk.data_ptr(), xb.data_ptr(), out.data_ptr(), T, B, V, KS, xb_slices, slot0, Din, Cp,
                                                   L.stream()), "gruscan_export_xc")
-            ZR = torch.empty(T, B, V, 2 * H, dtype=dt, device=dev)
-            LG = torch.empty(T, B, V, 2 * H, dtype=dt, device=dev)
-            HC = torch.empty(T, B, V, H, dtype=dt, device=dev)
-            LU = torch.empty(T, B, V, H, dtype=dt, device=dev)
-            L.check(lib.fmm_gruscan_export_fs(fs.data_ptr(), ZR.data_ptr(), LG.data_ptr(), HC.data_ptr(), LU.data_ptr(), T, B, V, L.stream()),
-                    "gruscan_export_fs")
-            del xcg, xcu, fs, xb
-        return (*_bptt_steps(x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU, dH, ctx.need_dx), None)
+            if os.environ.get("FMM_GRUSCAN_BWD", "1") == "0":      # host-driven BPTT over the exported gate values (dev aid)
+                ZR = torch.empty(T, B, V, 2 * H, dtype=dt, device=dev)
+                LG = torch.empty(T, B, V, 2 * H, dtype=dt, device=dev)
+                HC = torch.empty(T, B, V, H, dtype=dt, device=dev)
+                LU = torch.empty(T, B, V, H, dtype=dt, device=dev)
+                L.check(lib.fmm_gruscan_export_fs(fs.data_ptr(), ZR.data_ptr(), LG.data_ptr(), HC.data_ptr(), LU.data_ptr(), T, B, V, L.stream()),
+                        "gruscan_export_fs")
+                del xcg, xcu, fs, xb
+                return (*_bptt_steps(x, S, Wg, Wu, Hout, XCg, XCu, ZR, LG, HC, LU, dH, ctx.need_dx), None)
+            # one launch for the serial sweep (gruscan mode 2), then batched GEMMs over all (t, clip) pairs
+            BC, _ = gruscan_geometry(V)
+            NC = (B + BC - 1) // BC
+            dH = dH.to(dt).contiguous()
+            blk_shape = (T, NC, 8, 2, V, BC, 8)
+            dxu = torch.empty(blk_shape, dtype=dt, device=dev)
+            dxgz = torch.empty(blk_shape, dtype=dt, device=dev)
+            dxgr = torch.empty(blk_shape, dtype=dt, device=dev)
+            err = torch.zeros(1, dtype=torch.int32, device=dev)
+            _scan_call(2, B, T, V, NC, fs=fs, dhout=dH, dh_strides=(T * V * H, V * H, H), dxu=dxu, dxgz=dxgz, dxgr=dxgr, W=Wh, Lw=Lh, cs=cs, S=S,
+                       err=err)
+            dPLu = torch.empty(2, T, B, V, H, dtype=dt, device=dev)
+            dPLg = torch.empty(2, T, B, V, 2 * H, dtype=dt, device=dev)
+            L.check(lib.fmm_gruscan_export_dg(dxu.data_ptr(), dxgz.data_ptr(), dxgr.data_ptr(), dPLu.data_ptr(), dPLg.data_ptr(), T, B, V,
+                                              L.stream()), "gruscan_export_dg")
+            del dxu, dxgz, dxgr, xcg, xcu, fs, xb
+            # input gradients of both stages for every step: [0] graph path (before the transposed mix), [1] Linear path
+            Cin = Din + H
+            Wg_d, Wu_d = Wg.clone(), Wu.clone()
+            Wg_d[:, :, Cin:] = 0
+            Wu_d[:, :, Cin:] = 0
+            dXg = torch.empty(2, T, B, V, Cp, dtype=dt, device=dev)
+            dXu = torch.empty(2, T, B, V, Cp, dtype=dt, device=dev)
+            _stage_dgrad(dPLg, Wg_d, dXg[0], dXg[1], T * B, V, Cp, 2 * H, T * B * V * 2 * H)
+            _stage_dgrad(dPLu, Wu_d, dXu[0], dXu[1], T * B, V, Cp, H, T * B * V * H)
+            dX = None
+            if ctx.need_dx:
+                dmx = (dXg[0, ..., H:Cin].float() + dXu[0, ..., H:Cin].float()).view(T * B, V, Din)
+                dX = torch.matmul(S.t(), dmx).view(T, B, V, Din)
+                dX += dXg[1, ..., H:Cin]
+                dX += dXu[1, ..., H:Cin]
+                dX = dX.permute(1, 0, 2, 3).to(dt).contiguous()
+            dS, dWg, dWu = _bptt_tail(XCg, XCu, dXg[0], dXu[0], dPLg, dPLu, T, B, V, Cp, H)
+        return dX, dS, dWg, dWu, None
 
 
 # ------------------------------------------------------------------------------------------------

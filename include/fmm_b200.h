@@ -362,6 +362,9 @@ int fmm_gruscan(const fmm_gruscan_args* args, int mode, cudaStream_t stream);
 /* blocked state (+ blocked input) -> row-major [2: mixed, plain][T][B][V][Cp] with columns [h 64 | x Din | 1 | 0] */
 int fmm_gruscan_export_xc(const void* xc, const void* xb, void* out, int T, int B, int V, int KS, int xb_slices, int xb_slot0,
                           int Din, int Cp, cudaStream_t stream);
+/* blocked pre-activation gradients of the backward scan -> dPLu [2: graph, Linear][T][B][V][64], dPLg [2][T][B][V][128] */
+int fmm_gruscan_export_dg(const void* dxu, const void* dxgz, const void* dxgr, void* dPLu, void* dPLg, int T, int B, int V,
+                          cudaStream_t stream);
 /* fragment-order gate values -> ZR, LG [T][B][V][128], HC, LU [T][B][V][64] */
 int fmm_gruscan_export_fs(const void* fs, void* ZR, void* LG, void* HC, void* LU, int T, int B, int V, cudaStream_t stream);
 

@@ -634,26 +634,54 @@ __global__ void __launch_bounds__(NT, 1) gruscan_bwd_kernel(const GruScanArgs p)
         if (lane + 32 * i < NPW * MT * 4 * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)(lane + 32 * i) * 128));
     }
     // ------------------------------------------------ A: state update and candidate backward (elementwise)
+    // (loads of item it+1 are issued before the maths of item it; the previous step's dH rows were prefetched to L2)
+    auto load_dh = [&](int it, int tt, uint32_t (&d)[2]) {
+      const int q = it / MT, mt = it % MT, n = w + 8 * q;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int b = nc * BC + mt * 16 + g + 8 * half;
+        d[half] = (b < p.B && n < V)
+                      ? *reinterpret_cast<const uint32_t*>(dho + (size_t)b * p.dh_b + (size_t)tt * p.dh_t + (size_t)n * p.dh_v + 8 * j + 2 * tq)
+                      : 0u;
+      }
+    };
+    if (t > 0 && tq == 0) {
+#pragma unroll
+      for (int it = 0; it < NPW * MT; ++it) {
+        const int q = it / MT, mt = it % MT, n = w + 8 * q;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int b = nc * BC + mt * 16 + g + 8 * half;
+          if (b < p.B && n < V)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(dho + (size_t)b * p.dh_b + (size_t)(t - 1) * p.dh_t + (size_t)n * p.dh_v + 8 * j));
+        }
+      }
+    }
+    uint32_t nd[2];
+    uint2 nz = *reinterpret_cast<const uint2*>(fsw), nlz = *reinterpret_cast<const uint2*>(fsw + 512), nlu = *reinterpret_cast<const uint2*>(fsw + 768);
+    uint4 nh = *reinterpret_cast<const uint4*>(fsw + 256);
+    load_dh(0, t, nd);
 #pragma unroll
     for (int it = 0; it < NPW * MT; ++it) {
       const int q = it / MT, mt = it % MT;
       const int n = w + 8 * q;
       if (n >= V) break;
-      const uint4 c0 = *reinterpret_cast<const uint4*>(fsw + it * 1024), c1 = *reinterpret_cast<const uint4*>(fsw + it * 1024 + 256),
-                  c2 = *reinterpret_cast<const uint4*>(fsw + it * 1024 + 512), c3 = *reinterpret_cast<const uint4*>(fsw + it * 1024 + 768);
+      const uint2 cz = nz, clz = nlz, clu = nlu;
+      const uint4 c1 = nh;
+      const uint32_t cd[2] = {nd[0], nd[1]};
+      if (it + 1 < NPW * MT && w + 8 * ((it + 1) / MT) < V) {
+        nz = *reinterpret_cast<const uint2*>(fsw + (it + 1) * 1024);
+        nh = *reinterpret_cast<const uint4*>(fsw + (it + 1) * 1024 + 256);
+        nlz = *reinterpret_cast<const uint2*>(fsw + (it + 1) * 1024 + 512);
+        nlu = *reinterpret_cast<const uint2*>(fsw + (it + 1) * 1024 + 768);
+        load_dh(it + 1, t, nd);
+      }
       float z[4], hc[4], hp[4], lgz[4], lu[4], g1u[4], g2u[4], g1z[4], g2z[4];
-      unpack4(c0.x, c0.y, z); unpack4(c1.x, c1.y, hc); unpack4(c1.z, c1.w, hp); unpack4(c2.x, c2.y, lgz); unpack4(c3.x, c3.y, lu);
+      unpack4(cz.x, cz.y, z); unpack4(c1.x, c1.y, hc); unpack4(c1.z, c1.w, hp); unpack4(clz.x, clz.y, lgz); unpack4(clu.x, clu.y, lu);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const int b = nc * BC + mt * 16 + g + 8 * half;
-        float d0 = 0.f, d1 = 0.f;
-        if (b < p.B) {
-          const uint32_t u = *reinterpret_cast<const uint32_t*>(dho + (size_t)b * p.dh_b + (size_t)t * p.dh_t + (size_t)n * p.dh_v + 8 * j + 2 * tq);
-          d0 = lo(u);
-          d1 = hi(u);
-        }
-        carry[q][mt][2 * half] += d0;
-        carry[q][mt][2 * half + 1] += d1;
+        carry[q][mt][2 * half] += lo(cd[half]);
+        carry[q][mt][2 * half + 1] += hi(cd[half]);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {

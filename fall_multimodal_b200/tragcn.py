@@ -209,6 +209,30 @@ class _GraphGRUScan(Function):
         return _bptt_steps(*saved, dH, ctx.need_dx)
 
 
+def pn_dgrad(dPL, Wd, out, c0=0, ncols=None, bias=None, relu=False):
+    """out[row][n][c0:c0+ncols] = act(dPL[row][n][:] . Wd[n][c0:c0+ncols][:]^T + bias) for one path (csrc/pnode.cu):
+    dPL (R,V,K), Wd (V,Cp,K), out (R,V,Cp); V = 1 is a Linear layer."""
+    R, V, K = dPL.shape
+    Cp = Wd.shape[1]
+    ncols = Cp - c0 if ncols is None else ncols
+    L.check(L.load().fmm_pn_dgrad(dPL.data_ptr(), Wd.data_ptr(), out.data_ptr(), 1, R, V, K, Cp, c0, ncols,
+                                  bias.data_ptr() if bias is not None else None, int(relu), L.stream()), "pn_dgrad")
+
+
+def _pn_linear_ok(x, Kin, Nout, out_dtype):
+    return x.dtype == torch.bfloat16 and (out_dtype is None or out_dtype == torch.bfloat16) and Kin in (64, 128) and Nout in (64, 128)
+
+
+def pn_wgrad(XC, dPL, dW):
+    """dW[p][n] = sum_rows XC[p][row][n][:]^T dPL[p][row][n][:] (csrc/pnode.cu): XC (P,..rows..,V,Cp), dPL (P,..rows..,V,Co) -> dW (P,V,Cp,Co) fp32."""
+    P, V, Cp, Co = dW.shape
+    R = XC.numel() // (P * V * Cp)
+    ch = L.load().fmm_pn_wgrad_chunks(P, R, V)
+    part = torch.empty(ch, P, V, Cp, Co, dtype=torch.float32, device=XC.device)
+    L.check(L.load().fmm_pn_wgrad(XC.data_ptr(), dPL.data_ptr(), part.data_ptr(), P, R, V, Cp, Co, L.stream()), "pn_wgrad")
+    torch.sum(part, 0, out=dW)
+
+
 def _bptt_tail(XCg, XCu, dXg, dXu, dPLg, dPLu, T, B, V, Cp, H):
     """Batched GEMMs after the serial sweep: dS from the graph-path input gradients of every step (dXg / dXu, (>=T,B,V,Cp)),
     the weight gradients of both stages from the saved stage inputs XC* (2,T,B,V,Cp) and pre-activation gradients dPL*."""
@@ -225,8 +249,11 @@ def _bptt_tail(XCg, XCu, dXg, dXu, dPLg, dPLu, T, B, V, Cp, H):
             dWg = torch.empty(2, V, Cp, 2 * H, dtype=torch.float32, device=dev)
             dWu = torch.empty(2, V, Cp, H, dtype=torch.float32, device=dev)
             for XC, dPL, dW, Co in ((XCg, dPLg, dWg, 2 * H), (XCu, dPLu, dWu, H)):
-                bgemm(XC, 0, (T * B * V * Cp, Cp, 1, V * Cp, 0, 0), dPL, 0, (T * B * V * Co, Co, 1, V * Co, 0, 0),
-                      dW, 0, (V * Cp * Co, Cp * Co, Co, 1), (2, V), Cp, Co, (T * B, 1, 1))
+                if XC.dtype == torch.bfloat16 and Cp <= 144 and Co in (64, 128):
+                    pn_wgrad(XC, dPL, dW)
+                else:
+                    bgemm(XC, 0, (T * B * V * Cp, Cp, 1, V * Cp, 0, 0), dPL, 0, (T * B * V * Co, Co, 1, V * Co, 0, 0),
+                          dW, 0, (V * Cp * Co, Cp * Co, Co, 1), (2, V), Cp, Co, (T * B, 1, 1))
     return dS, dWg, dWu
 
 
@@ -362,7 +389,7 @@ class _GraphGRUScanP(Function):
             Hout = torch.empty(B, T, V, H, dtype=dt, device=dev)
             err = torch.zeros(1, dtype=torch.int32, device=dev)
             _scan_call(0, B, T, V, NC, xb=xb, px=px, W=Wx.to(dt).contiguous(), Lw=Lx.to(dt).contiguous(), cs=cs, S=S, bg=bg, bl=bl, err=err,
-                       KS=Kx // 8, xb_slices=xb_slices, xb_slot0=slot0, tsplit=max(1, min(T, 18 // NC)))
+                       KS=Kx // 8, xb_slices=xb_slices, xb_slot0=slot0, tsplit=max(1, min(T, 15)))
             _scan_call(1, B, T, V, NC, px=px, xcg=xcg, xcu=xcu, fs=fs, hout=Hout, W=Wh, Lw=Lh, cs=cs, S=S, err=err)
             _handoff = (Hout.data_ptr(), xcg)
             if need:
@@ -417,8 +444,11 @@ class _GraphGRUScanP(Function):
             Wu_d[:, :, Cin:] = 0
             dXg = torch.empty(2, T, B, V, Cp, dtype=dt, device=dev)
             dXu = torch.empty(2, T, B, V, Cp, dtype=dt, device=dev)
-            _stage_dgrad(dPLg, Wg_d, dXg[0], dXg[1], T * B, V, Cp, 2 * H, T * B * V * 2 * H)
-            _stage_dgrad(dPLu, Wu_d, dXu[0], dXu[1], T * B, V, Cp, H, T * B * V * H)
+            for dPL, Wd, dXs in ((dPLg, Wg_d, dXg), (dPLu, Wu_d, dXu)):
+                Wt = Wd                                                    # W[p][n][c][o]: the kernel reads row c = output column c
+                pn_dgrad(dPL[0].view(T * B, V, -1), Wt[0], dXs[0].view(T * B, V, Cp))
+                if ctx.need_dx:
+                    pn_dgrad(dPL[1].view(T * B, V, -1), Wt[1], dXs[1].view(T * B, V, Cp), c0=H, ncols=Cp - H)
             dX = None
             if ctx.need_dx:
                 dmx = (dXg[0, ..., H:Cin].float() + dXu[0, ..., H:Cin].float()).view(T * B, V, Din)
@@ -463,8 +493,12 @@ class _Linear(Function):
             Wc = W.to(x.dtype).contiguous()
             Kin, Nout, R = x.shape[-1], W.shape[0], _rows(x)
             y = torch.empty(*x.shape[:-1], Nout, dtype=out_dtype or x.dtype, device=x.device)
-            bgemm(x, 0, (0, 0, Kin, 1, 0, 0), Wc, 0, (0, 0, Kin, 1, 0, 0), y, 0, (0, 0, Nout, 1), (1, 1), R, Nout,
-                  (Kin, 1, 1), act=1 if relu else 0, bias_n=b.float().contiguous() if b is not None else None)
+            if _pn_linear_ok(x, Kin, Nout, out_dtype):      # row-streaming kernel (csrc/pnode.cu): HBM bound instead of tile bound
+                pn_dgrad(x.view(R, 1, Kin), Wc.view(1, Nout, Kin), y.view(R, 1, Nout), bias=b.float().contiguous() if b is not None else None,
+                         relu=relu)
+            else:
+                bgemm(x, 0, (0, 0, Kin, 1, 0, 0), Wc, 0, (0, 0, Kin, 1, 0, 0), y, 0, (0, 0, Nout, 1), (1, 1), R, Nout,
+                      (Kin, 1, 1), act=1 if relu else 0, bias_n=b.float().contiguous() if b is not None else None)
         ctx.saved = (x, Wc, y if relu else None)
         ctx.has_bias = b is not None
         return y
@@ -480,13 +514,20 @@ class _Linear(Function):
                 dy = dy.clone()
                 L.check(L.load().fmm_tg_relu_mask(dy.data_ptr(), y.data_ptr(), dy.numel(), _dt(dy), L.stream()), "tg_relu_mask")
             dx = None
+            fast = _pn_linear_ok(x, Kin, Nout, None)
             if ctx.needs_input_grad[0]:
                 dx = torch.empty_like(x)
-                bgemm(dy, 0, (0, 0, Nout, 1, 0, 0), Wc, 0, (0, 0, 1, Kin, 0, 0), dx, 0, (0, 0, Kin, 1), (1, 1), R, Kin,
-                      (Nout, 1, 1))
+                if fast:
+                    pn_dgrad(dy.view(R, 1, Nout), Wc.t().contiguous().view(1, Kin, Nout), dx.view(R, 1, Kin))
+                else:
+                    bgemm(dy, 0, (0, 0, Nout, 1, 0, 0), Wc, 0, (0, 0, 1, Kin, 0, 0), dx, 0, (0, 0, Kin, 1), (1, 1), R, Kin,
+                          (Nout, 1, 1))
             dW = torch.zeros(Nout, Kin, dtype=torch.float32, device=x.device)
-            bgemm(dy, 0, (0, 0, 1, Nout, 0, 0), x, 0, (0, 0, 1, Kin, 0, 0), dW, 0, (0, 0, Kin, 1), (1, 1), Nout, Kin,
-                  (R, 1, 1), splitk=_splitk(Nout, Kin, 1, R))
+            if fast:
+                pn_wgrad(dy.view(1, R, 1, Nout), x.view(1, R, 1, Kin), dW.view(1, 1, Nout, Kin))
+            else:
+                bgemm(dy, 0, (0, 0, 1, Nout, 0, 0), x, 0, (0, 0, 1, Kin, 0, 0), dW, 0, (0, 0, Kin, 1), (1, 1), Nout, Kin,
+                      (R, 1, 1), splitk=_splitk(Nout, Kin, 1, R))
             db = _colsum(dy) if ctx.has_bias else None
         return dx, dW, db, None, None
 

@@ -368,6 +368,16 @@ int fmm_gruscan_export_dg(const void* dxu, const void* dxgz, const void* dxgr, v
 /* fragment-order gate values -> ZR, LG [T][B][V][128], HC, LU [T][B][V][64] */
 int fmm_gruscan_export_fs(const void* fs, void* ZR, void* LG, void* HC, void* LU, int T, int B, int V, cudaStream_t stream);
 
+/* Row-streaming per-node GEMMs for the batched work after the graph-GRU sweep (csrc/pnode.cu; EmbGCN.py:80-86 has one weight
+ * matrix per joint): bf16 operands, rows = T*B.
+ *   pn_dgrad: OUT[p][row][n][c0 + c] = sum_k IN[p][row][n][k] W[p][n][c0 + c][k], c < ncols (K in {64,128}, Cp <= 144)
+ *   pn_wgrad: part[chunk][p][n][c][o] = sum over the chunk's rows of XC[p][row][n][c] DY[p][row][n][o] (Co in {64,128}); the caller
+ *             sums over fmm_pn_wgrad_chunks(P, rows, V) chunks */
+int fmm_pn_dgrad(const void* in, const void* W, void* out, int P, long long rows, int V, int K, int Cp, int c0, int ncols, const float* bias,
+                 int relu, cudaStream_t stream); /* + bias[c0 + c] (fp32, may be null), optional ReLU: V = 1 is a Linear layer (TA.py:33-37) */
+int fmm_pn_wgrad_chunks(int P, long long rows, int V);
+int fmm_pn_wgrad(const void* xc, const void* dy, float* part, int P, long long rows, int V, int Cp, int Co, cudaStream_t stream);
+
 /* Flash-style time-axis attention (csrc/tattn.cu; TA.py:55-62 softmax(q k^T / sqrt(c), -1) v per (clip, joint)): one CTA per
  * head, the (B,V,T,T) scores are never written. q, k feature-major (B,F,V,Tp) as the time-as-channel convolutions leave them,
  * v (B,V,T,64), out / dout (B,T,V,64), lse (B*V,Tp) fp32 (log2 domain). bf16, F <= 64, Tp % 64 == 0, Tp <= 320.

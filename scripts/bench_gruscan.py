@@ -79,3 +79,16 @@ TG.scan_prof = None
 with torch.no_grad():
     timed("per-step path, layer 1 forward (eager)", lambda: TG._GraphGRUScan.apply(x, S, ww(3, 128, cs), ww(3, 64, cs)), n=2)
     timed("per-step path, layer 2 forward (eager)", lambda: TG._GraphGRUScan.apply(h1, S, ww(64, 128, cs), ww(64, 64, cs)), n=2)
+# backward scan profile (gruscan mode 2)
+TG.scan_prof = {2: torch.zeros(16, dtype=torch.int64, device=dev)}
+Wg, Wu = ww(64, 128, cs).requires_grad_(True), ww(64, 64, cs).requires_grad_(True)
+xi = h1.clone().requires_grad_(True)
+out = TG._GraphGRUScanP.apply(xi, S, Wg, Wu, cs)
+TG._handoff = None
+g = torch.randn_like(out)
+TG._scan_call = hooked
+out.backward(g)
+torch.cuda.synchronize()
+c = TG.scan_prof[2].tolist()
+names = ["A.elementwise", "A.publish+clsync", "wait", "items", "sync+mix+sync", "post", "publish+clsync"]
+print("backward scan, cycles per step of CTA 0 / thread 0:", {n: round(v / T) for n, v in zip(names, c)}, "total", round(sum(c) / T))

@@ -152,6 +152,7 @@ _SIGNATURES = {
     "fmm_gruscan": [_P, c_int, _P],
     "fmm_gruscan_export_xc": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_gruscan_export_dg": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
+    "fmm_gruscan_mix_dx": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "fmm_gruscan_export_fs": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
     "fmm_tattn": [_P, c_int, _P],
     "fmm_pn_dgrad": [_P, _P, _P, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
@@ -201,7 +202,7 @@ GruScanArgs = _struct("GruScanArgs", [
 
 
 # mirror of fmm_tattn_args (include/fmm_b200.h, csrc/tattn.cu)
-TAttnArgs = _struct("TAttnArgs", [(c_void_p, "q k v out lse dout dq dk dv"), (c_int, "B V T Tp F"), (c_float, "scale")])
+TAttnArgs = _struct("TAttnArgs", [(c_void_p, "q k v out lse dout dq dk dv"), (c_int, "B V T Tp F"), (c_float, "scale"), (c_int, "v_btvc")])
 
 
 # mirror of fmm_head_args (include/fmm_b200.h, csrc/head.cu)

@@ -864,6 +864,42 @@ __global__ void __launch_bounds__(256) export_dg_kernel(const bf16* __restrict__
   }
 }
 
+// dX[b][t][n][c] = sum_m S[m][n] (dXg[0] + dXu[0])[t][b][m][c0 + c] + (dXg[1] + dXu[1])[t][b][n][c0 + c]: the transposed adjacency
+// mix of the graph-path input gradients plus the Linear-path ones, both stages, one block per (t, clip)
+__global__ void __launch_bounds__(256) mix_dx_kernel(const bf16* __restrict__ dXg, const bf16* __restrict__ dXu, const float* __restrict__ S,
+                                                     bf16* __restrict__ dX, int T, int B, int V, int Cp, int c0, int Din) {
+  extern __shared__ float sm_dx[];
+  float* Ss = sm_dx;               // [V][V]
+  float* gs_ = sm_dx + V * V;      // [V][Din]
+  const int t = blockIdx.x / B, b = blockIdx.x % B;
+  const size_t path = (size_t)T * B * V * Cp, row0 = ((size_t)t * B + b) * V;
+  for (int i = threadIdx.x; i < V * V; i += blockDim.x) Ss[i] = S[i];
+  const int D8 = Din >> 3;
+  for (int i = threadIdx.x; i < V * D8; i += blockDim.x) {
+    const int m = i / D8, c = (i % D8) * 8;
+    float a[8], e[8];
+    load8(dXg + (row0 + m) * Cp + c0 + c, a);
+    load8(dXu + (row0 + m) * Cp + c0 + c, e);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) gs_[m * Din + c + q] = a[q] + e[q];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < V * D8; i += blockDim.x) {
+    const int n = i / D8, c = (i % D8) * 8;
+    float a[8], e[8], o[8];
+    load8(dXg + path + (row0 + n) * Cp + c0 + c, a);
+    load8(dXu + path + (row0 + n) * Cp + c0 + c, e);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = a[q] + e[q];
+    for (int m = 0; m < V; ++m) {
+      const float sv = Ss[m * V + n];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] += sv * gs_[m * Din + c + q];
+    }
+    store8(dX + (((size_t)b * T + t) * V + n) * Din + c, o);
+  }
+}
+
 // FS (fragment order) -> ZR, LG [T][B][V][128], HC, LU [T][B][V][64]
 __global__ void __launch_bounds__(256) export_fs_kernel(const bf16* __restrict__ fs, bf16* __restrict__ ZR, bf16* __restrict__ LG,
                                                         bf16* __restrict__ HC, bf16* __restrict__ LU, int T, int B, int V, int NC, int NPW,
@@ -1019,6 +1055,18 @@ int fmm_gruscan_export_dg(const void* dxu, const void* dxgz, const void* dxgr, v
                                                     reinterpret_cast<const gs::bf16*>(dxgr), reinterpret_cast<gs::bf16*>(dPLu),
                                                     reinterpret_cast<gs::bf16*>(dPLg), T, B, V, NC, BC);
   FMM_CHECK_LAUNCH("gruscan_export_dg");
+  return FMM_OK;
+}
+
+// dX (B,T,V,Din) from the input gradients of both stages, dXg / dXu (2,T,B,V,Cp): columns c0..c0+Din-1, Din % 8 == 0
+int fmm_gruscan_mix_dx(const void* dXg, const void* dXu, const float* S, void* dX, int T, int B, int V, int Cp, int c0, int Din,
+                       cudaStream_t stream) {
+  using namespace fmm;
+  FMM_CHECK_ARG(V >= 1 && V <= 64 && Din % 8 == 0 && c0 % 8 == 0 && c0 + Din <= Cp && Cp % 8 == 0, "gruscan_mix_dx: bad sizes");
+  const size_t smem = (size_t)(V * V + V * Din) * sizeof(float);
+  gs::mix_dx_kernel<<<T * B, 256, smem, stream>>>(reinterpret_cast<const gs::bf16*>(dXg), reinterpret_cast<const gs::bf16*>(dXu), S,
+                                                  reinterpret_cast<gs::bf16*>(dX), T, B, V, Cp, c0, Din);
+  FMM_CHECK_LAUNCH("gruscan_mix_dx");
   return FMM_OK;
 }
 

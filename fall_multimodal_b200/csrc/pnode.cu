@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(NT, 1) pn_wgrad_kernel(const bf16* __restrict_
       }
 #pragma unroll
       for (int mi9 = 0; mi9 < MT; ++mi9) {
+        if (mi9 * 16 >= Cp) break;
         uint32_t a[4];
         const int mi = lane >> 3, r = lane & 7;
         // A fragment: XC tile [row = k][c = m] (k-major)

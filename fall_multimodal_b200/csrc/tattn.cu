@@ -22,6 +22,7 @@ struct TAttnArgs {
   void* dq; void* dk; void* dv;                  // (B,F,V,Tp), (B,F,V,Tp), (B,V,T,64) bf16
   int B, V, T, Tp, F;
   float scale;
+  int v_btvc;                                    // 1: v and dv are (B,T,V,64) like out (the value projection is a plain Linear layer then)
 };
 
 namespace ta {
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(NT, 1) tattn_fwd_kernel(const TAttnArgs p) {
   const bf16* kh = reinterpret_cast<const bf16*>(p.k) + ((size_t)b * F * V + v) * Tp;
   load_fmajor(Qs, qh, F, V, Tp, qstr);
   load_fmajor(Ks, kh, F, V, Tp, qstr);
-  load_rows(Vs, reinterpret_cast<const bf16*>(p.v) + (size_t)h * T * C, C, T, Tp);
+  if (p.v_btvc) load_rows(Vs, reinterpret_cast<const bf16*>(p.v) + (size_t)b * T * V * C + (size_t)v * C, (long long)V * C, T, Tp);
+  else load_rows(Vs, reinterpret_cast<const bf16*>(p.v) + (size_t)h * T * C, C, T, Tp);
   cp_wait_all();
   __syncthreads();
   const float sc2 = p.scale * 1.4426950408889634f;
@@ -205,7 +207,8 @@ __global__ void __launch_bounds__(NT, 1) tattn_bwd_kernel(const TAttnArgs p) {
   const bf16* oh = reinterpret_cast<const bf16*>(p.out) + (size_t)b * T * V * C + (size_t)v * C;
   load_fmajor(Qs, qh, F, V, Tp, qstr);
   load_fmajor(Ks, kh, F, V, Tp, qstr);
-  load_rows(Vs, reinterpret_cast<const bf16*>(p.v) + (size_t)h * T * C, C, T, Tp);
+  if (p.v_btvc) load_rows(Vs, reinterpret_cast<const bf16*>(p.v) + (size_t)b * T * V * C + (size_t)v * C, (long long)V * C, T, Tp);
+  else load_rows(Vs, reinterpret_cast<const bf16*>(p.v) + (size_t)h * T * C, C, T, Tp);
   load_rows(dOs, doh, (long long)V * C, T, Tp);
   for (int t = threadIdx.x; t < Tp; t += NT) lse_s[t] = p.lse[(size_t)h * Tp + t];
   cp_wait_all();
@@ -307,14 +310,15 @@ __global__ void __launch_bounds__(NT, 1) tattn_bwd_kernel(const TAttnArgs p) {
         mma16816(dk[2 * np + 1], da, bb[2], bb[3]);
       }
     }
-    bf16* dvh = reinterpret_cast<bf16*>(p.dv) + (size_t)h * T * C;
+    bf16* dvh = reinterpret_cast<bf16*>(p.dv) + (p.v_btvc ? (size_t)b * T * V * C + (size_t)v * C : (size_t)h * T * C);
+    const size_t dvs = p.v_btvc ? (size_t)V * C : (size_t)C;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int key = n0 + g + 8 * half;
       if (key < T) {
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
-          *reinterpret_cast<uint32_t*>(dvh + (size_t)key * C + nt * 8 + 2 * tq) = pk(dv[nt][2 * half], dv[nt][2 * half + 1]);
+          *reinterpret_cast<uint32_t*>(dvh + (size_t)key * dvs + nt * 8 + 2 * tq) = pk(dv[nt][2 * half], dv[nt][2 * half + 1]);
       }
     }
     store_fmajor(dk, reinterpret_cast<bf16*>(p.dk) + ((size_t)b * F * V + v) * Tp, n0);

@@ -451,11 +451,16 @@ class _GraphGRUScanP(Function):
                     pn_dgrad(dPL[1].view(T * B, V, -1), Wt[1], dXs[1].view(T * B, V, Cp), c0=H, ncols=Cp - H)
             dX = None
             if ctx.need_dx:
-                dmx = (dXg[0, ..., H:Cin].float() + dXu[0, ..., H:Cin].float()).view(T * B, V, Din)
-                dX = torch.matmul(S.t(), dmx).view(T, B, V, Din)
-                dX += dXg[1, ..., H:Cin]
-                dX += dXu[1, ..., H:Cin]
-                dX = dX.permute(1, 0, 2, 3).to(dt).contiguous()
+                dX = torch.empty(B, T, V, Din, dtype=dt, device=dev)
+                if Din % 8 == 0:     # dX = S^T (dXg0 + dXu0)[x columns] + (dXg1 + dXu1)[x columns] in one pass
+                    L.check(lib.fmm_gruscan_mix_dx(dXg.data_ptr(), dXu.data_ptr(), S.data_ptr(), dX.data_ptr(), T, B, V, Cp, H, Din, L.stream()),
+                            "gruscan_mix_dx")
+                else:
+                    dmx = (dXg[0, ..., H:Cin].float() + dXu[0, ..., H:Cin].float()).view(T * B, V, Din)
+                    d32 = torch.matmul(S.t(), dmx).view(T, B, V, Din)
+                    d32 += dXg[1, ..., H:Cin]
+                    d32 += dXu[1, ..., H:Cin]
+                    dX.copy_(d32.permute(1, 0, 2, 3))
             dS, dWg, dWu = _bptt_tail(XCg, XCu, dXg[0], dXu[0], dPLg, dPLu, T, B, V, Cp, H)
         return dX, dS, dWg, dWu, None
 
@@ -671,25 +676,28 @@ class _AttentionF(Function):
     scores / probabilities are never written (only a (B*V,Tp) log-sum-exp is saved)."""
 
     @staticmethod
-    def _args(q, k, v, out, lse, T):
+    def _args(q, k, v, out, lse, T, btvc):
         a = L.TAttnArgs()
         a.q, a.k, a.v, a.out, a.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr()
         a.B, a.F, a.V, a.Tp = q.shape
         a.T = T
         a.scale = 1.0 / math.sqrt(v.shape[3])
+        a.v_btvc = int(btvc)
         return a
 
     @staticmethod
-    def forward(ctx, q, k, v):
+    def forward(ctx, q, k, v, btvc=False):
+        """``btvc``: v is (B,T,V,C) (the layout of the layer input, so the value projection is a plain Linear) instead of (B,V,T,C)."""
         with torch.autocast("cuda", enabled=False):
             q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
             B, F, V, Tp = q.shape
-            T, Cc = v.shape[2], v.shape[3]
+            T, Cc = (v.shape[1] if btvc else v.shape[2]), v.shape[3]
             out = torch.empty(B, T, V, Cc, dtype=q.dtype, device=q.device)
             lse = torch.empty(B * V, Tp, dtype=torch.float32, device=q.device)
-            a = _AttentionF._args(q, k, v, out, lse, T)
+            a = _AttentionF._args(q, k, v, out, lse, T, btvc)
             L.check(L.load().fmm_tattn(C.byref(a), 0, L.stream()), "tattn")
         ctx.saved = (q, k, v, out, lse)
+        ctx.T, ctx.btvc = T, btvc
         return out
 
     @staticmethod
@@ -699,10 +707,10 @@ class _AttentionF(Function):
         with torch.autocast("cuda", enabled=False):
             do = do.to(q.dtype).contiguous()
             dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-            a = _AttentionF._args(q, k, v, out, lse, v.shape[2])
+            a = _AttentionF._args(q, k, v, out, lse, ctx.T, ctx.btvc)
             a.dout, a.dq, a.dk, a.dv = do.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
             L.check(L.load().fmm_tattn(C.byref(a), 1, L.stream()), "tattn")
-        return dq, dk, dv
+        return dq, dk, dv, None
 
 
 class _ValueProj(Function):
@@ -889,8 +897,12 @@ class Transform(nn.Module):
         xT = _TimeToChannels.apply(x)
         q = _TimeConv.apply(xT, self.conv1.weight, self.conv1.bias, T)
         k = _TimeConv.apply(xT, self.conv2.weight, self.conv2.bias, T)
-        v = _ValueProj.apply(x, self.vff.weight, self.vff.bias)
-        att = (_AttentionF if tattn_supported(q, v) else _Attention).apply(q, k, v)
+        if tattn_supported(q, x):
+            v = _Linear.apply(x, self.vff.weight, self.vff.bias, False, None)          # (B,T,V,C): read in place by the attention kernel
+            att = _AttentionF.apply(q, k, v, True)
+        else:
+            v = _ValueProj.apply(x, self.vff.weight, self.vff.bias)
+            att = _Attention.apply(q, k, v)
         val = _LayerNorm2.apply(att, x, self.ln.weight, self.ln.bias, self.ln.eps)
         h = _Linear.apply(val, self.ff[0].weight, self.ff[0].bias, True, None)
         h = _Linear.apply(h, self.ff[2].weight, self.ff[2].bias, False, None)

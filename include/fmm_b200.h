@@ -365,6 +365,9 @@ int fmm_gruscan_export_xc(const void* xc, const void* xb, void* out, int T, int 
 /* blocked pre-activation gradients of the backward scan -> dPLu [2: graph, Linear][T][B][V][64], dPLg [2][T][B][V][128] */
 int fmm_gruscan_export_dg(const void* dxu, const void* dxgz, const void* dxgr, void* dPLu, void* dPLg, int T, int B, int V,
                           cudaStream_t stream);
+/* dX (B,T,V,Din) = S^T (dXg[0] + dXu[0])[.., c0:c0+Din] + (dXg[1] + dXu[1])[.., c0:c0+Din] from the stage input gradients (2,T,B,V,Cp) */
+int fmm_gruscan_mix_dx(const void* dXg, const void* dXu, const float* S, void* dX, int T, int B, int V, int Cp, int c0, int Din,
+                       cudaStream_t stream);
 /* fragment-order gate values -> ZR, LG [T][B][V][128], HC, LU [T][B][V][64] */
 int fmm_gruscan_export_fs(const void* fs, void* ZR, void* LG, void* HC, void* LU, int T, int B, int V, cudaStream_t stream);
 
@@ -390,6 +393,7 @@ typedef struct fmm_tattn_args {
   void* dq; void* dk; void* dv;
   int B, V, T, Tp, F;
   float scale;
+  int v_btvc; /* 1: v and dv are (B,T,V,64) */
 } fmm_tattn_args;
 int fmm_tattn(const fmm_tattn_args* args, int mode, cudaStream_t stream);
 

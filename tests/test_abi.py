@@ -90,7 +90,7 @@ def test_descriptor_structs_match_the_c_header(tmp_path):
               "fmm_cell_bwd_args": (_lib.CellBwdArgs, ["S", "dz", "dx", "dxv", "lg", "dH", "z1", "hv1", "dlin_u", "mode", "Cp"]),
               "fmm_gruscan_args": (_lib.GruScanArgs, ["xb", "hout", "bl", "dhout", "dh_b", "dh_v", "dxu", "LT", "err", "B", "KS", "xb_slot0",
                                                       "tsplit"]),
-              "fmm_tattn_args": (_lib.TAttnArgs, ["q", "v", "out", "lse", "dout", "dv", "B", "Tp", "F", "scale"]),
+              "fmm_tattn_args": (_lib.TAttnArgs, ["q", "v", "out", "lse", "dout", "dv", "B", "Tp", "F", "scale", "v_btvc"]),
               "fmm_head_args": (_lib.HeadArgs, ["feat", "dfeat", "width", "nseg", "W", "target", "prob2", "gloss", "dbias", "N", "F",
                                                 "pre_softmax", "smoothing"])}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fmm_b200.h"', "int main(void) {"]

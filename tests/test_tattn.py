@@ -38,15 +38,21 @@ def test_flash_attention_matches_fp64(B, V, T, F):
     truth = _truth(*leaves, T)
     truth.backward(go.double())
     res = {}
-    for name, fn in (("bgemm", _Attention), ("flash", _AttentionF)):
+    for name, fn in (("bgemm", _Attention), ("flash", _AttentionF), ("flash_btvc", _AttentionF)):
         ins = [t.clone().requires_grad_(True) for t in (q, k, v)]
-        out = fn.apply(*ins)
+        if name == "flash_btvc":      # v handed over in the layer's own (B,T,V,C) order
+            ins[2] = v.permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+            out = fn.apply(*ins, True)
+        else:
+            out = fn.apply(*ins)
         out.backward(go)
         torch.cuda.synchronize()
-        res[name] = [_rel(out, truth)] + [_rel(i.grad[..., :T] if n < 2 else i.grad, l.grad[..., :T] if n < 2 else l.grad)
-                                          for n, (i, l) in enumerate(zip(ins, leaves))]
-        if name == "flash":     # the padded time columns of dq / dk are written, as zeros
+        gv = ins[2].grad.permute(0, 2, 1, 3) if name == "flash_btvc" else ins[2].grad
+        res[name] = [_rel(out, truth), _rel(ins[0].grad[..., :T], leaves[0].grad[..., :T]), _rel(ins[1].grad[..., :T], leaves[1].grad[..., :T]),
+                     _rel(gv, leaves[2].grad)]
+        if name != "bgemm":     # the padded time columns of dq / dk are written, as zeros
             assert ins[0].grad[..., T:].abs().max().item() == 0 and ins[1].grad[..., T:].abs().max().item() == 0
     print(f"B{B} V{V} T{T} F{F}: (out, dq, dk, dv) bgemm {['%.2e' % e for e in res['bgemm']]} / flash {['%.2e' % e for e in res['flash']]}")
-    for ef, eb in zip(res["flash"], res["bgemm"]):
-        assert ef < 2e-2 and ef <= 1.25 * eb + 3e-3, (ef, eb)
+    for name in ("flash", "flash_btvc"):
+        for ef, eb in zip(res[name], res["bgemm"]):
+            assert ef < 2e-2 and ef <= 1.25 * eb + 3e-3, (name, ef, eb)

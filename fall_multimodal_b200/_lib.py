@@ -156,6 +156,8 @@ _SIGNATURES = {
     "fmm_gruscan_export_fs": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
     "fmm_tattn": [_P, c_int, _P],
     "fmm_pn_dgrad": [_P, _P, _P, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
+    "fmm_pn_ds_parts": [],
+    "fmm_pn_ds": [_P, _P, _P, c_ll, c_int, c_int, _P],
     "fmm_pn_wgrad_chunks": [c_int, c_ll, c_int],
     "fmm_pn_wgrad": [_P, _P, _P, c_int, c_ll, c_int, c_int, c_int, _P],
     "fmm_tg_softmax_fwd": [_P, c_ll, c_int, c_int, c_int, _P],

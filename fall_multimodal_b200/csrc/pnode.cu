@@ -217,6 +217,70 @@ __global__ void __launch_bounds__(NT, 1) pn_wgrad_kernel(const bf16* __restrict_
       }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// dS partials: part[cta][n][m] = sum over the CTA's rows and all c of G[row][n][c] * X[row][m][c]   (V <= 32, Cp <= 144).
+// Each of 4 warps streams its own (t, clip) rows through a private 2-stage cp.async ring: per row one (V x Cp).(Cp x V) product.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) pn_ds_kernel(const bf16* __restrict__ G, const bf16* __restrict__ X, float* __restrict__ part,
+                                                       long long rows, int V, int Cp) {
+  constexpr int XS = 144 + 8;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  const uint32_t base = smem_u32(smem_raw) + w * (4 * 32 * XS * 2);     // [stage][G | X][32][XS]
+  for (int i = lane; i < 4 * 32 * (XS / 8); i += 32) sts16z(base + i * 16);
+  __syncwarp();
+  const int c8 = Cp >> 3;
+  const long long wid = (long long)blockIdx.x * 4 + w, nw = (long long)gridDim.x * 4;
+  auto load_row = [&](long long row, int stage) {
+    for (int i = lane; i < V * c8; i += 32) {
+      const int n = i / c8, k8 = i % c8;
+      cp16(base + (((stage * 2 + 0) * 32 + n) * XS + k8 * 8) * 2, G + ((size_t)row * V + n) * Cp + k8 * 8);
+      cp16(base + (((stage * 2 + 1) * 32 + n) * XS + k8 * 8) * 2, X + ((size_t)row * V + n) * Cp + k8 * 8);
+    }
+  };
+  float acc[2][4][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mi][nt][i] = 0.f;
+  if (wid < rows) load_row(wid, 0);
+  cp_commit();
+  int st = 0;
+  for (long long row = wid; row < rows; row += nw, st ^= 1) {
+    if (row + nw < rows) load_row(row + nw, st ^ 1);
+    cp_commit();
+    cp_wait<1>();
+    __syncwarp();
+    const uint32_t Gs = base + (st * 2 + 0) * 32 * XS * 2, Xs = base + (st * 2 + 1) * 32 * XS * 2;
+    const int mi4 = lane >> 3, r = lane & 7;
+    for (int ks = 0; ks < ((Cp + 15) >> 4); ++ks) {
+      uint32_t a[2][4], bb[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) ldsm_x4(Gs + ((mi * 16 + (mi4 & 1) * 8 + r) * XS + ks * 16 + (mi4 >> 1) * 8) * 2, a[mi]);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) ldsm_x4(Xs + ((np * 16 + (mi4 >> 1) * 8 + r) * XS + ks * 16 + (mi4 & 1) * 8) * 2, bb[np]);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          mma16816(acc[mi][2 * np], a[mi], bb[np][0], bb[np][1]);
+          mma16816(acc[mi][2 * np + 1], a[mi], bb[np][2], bb[np][3]);
+        }
+    }
+    __syncwarp();
+  }
+  float* dst = part + ((size_t)blockIdx.x * 4 + w) * 32 * 32;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+        *reinterpret_cast<float2*>(dst + (mi * 16 + g + 8 * half) * 32 + nt * 8 + 2 * tq) = make_float2(acc[mi][nt][2 * half], acc[mi][nt][2 * half + 1]);
+}
+
 }  // namespace pn
 }  // namespace fmm
 
@@ -277,6 +341,22 @@ int fmm_pn_wgrad(const void* xc, const void* dy, float* part, int P, long long r
   if (Co == 64) FMM_PN_WG(1); else FMM_PN_WG(2);
 #undef FMM_PN_WG
   FMM_CHECK_LAUNCH("pn_wgrad");
+  return FMM_OK;
+}
+
+// part[i][n][m] (i < fmm_pn_ds_parts(), 32 x 32 fp32 each) = partial sums of sum_{row,c} G[row][n][c] X[row][m][c]; G, X (rows,V,Cp) bf16
+int fmm_pn_ds_parts(void) { return 4 * 2 * fmm::num_sms(); }
+int fmm_pn_ds(const void* G, const void* X, float* part, long long rows, int V, int Cp, cudaStream_t stream) {
+  using namespace fmm;
+  FMM_CHECK_ARG(V >= 1 && V <= 32 && Cp % 8 == 0 && Cp <= 144 && rows >= 1, "pn_ds: unsupported sizes (V=%d Cp=%d)", V, Cp);
+  const size_t smem = (size_t)4 * 4 * 32 * (144 + 8) * 2;
+  cudaError_t e = cudaFuncSetAttribute(pn::pn_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_last_error("pn_ds: smem attribute: %s", cudaGetErrorString(e));
+    return FMM_ERR_SMEM;
+  }
+  pn::pn_ds_kernel<<<2 * num_sms(), 128, smem, stream>>>(reinterpret_cast<const pn::bf16*>(G), reinterpret_cast<const pn::bf16*>(X), part, rows, V, Cp);
+  FMM_CHECK_LAUNCH("pn_ds");
   return FMM_OK;
 }
 

@@ -243,8 +243,13 @@ def _bptt_tail(XCg, XCu, dXg, dXu, dPLg, dPLu, T, B, V, Cp, H):
             dS = torch.zeros(V, V, dtype=torch.float32, device=dev)
             sk = _splitk(V, V, 1, T * B * Cp)
             for dXs, XC in ((dXg, XCg), (dXu, XCu)):
-                bgemm(dXs, 0, (0, 0, Cp, V * Cp, 1, 0), XC[1], 0, (0, 0, Cp, V * Cp, 1, 0), dS, 0, (0, 0, V, 1), (1, 1), V, V,
-                      (T * B, Cp, 1), splitk=sk)
+                if XC.dtype == torch.bfloat16 and V <= 32 and Cp <= 144:       # row-streaming kernel (csrc/pnode.cu), partials summed here
+                    part = torch.empty(L.load().fmm_pn_ds_parts(), 32, 32, dtype=torch.float32, device=dev)
+                    L.check(L.load().fmm_pn_ds(dXs.data_ptr(), XC[1].data_ptr(), part.data_ptr(), T * B, V, Cp, L.stream()), "pn_ds")
+                    dS += part.sum(0)[:V, :V]
+                else:
+                    bgemm(dXs, 0, (0, 0, Cp, V * Cp, 1, 0), XC[1], 0, (0, 0, Cp, V * Cp, 1, 0), dS, 0, (0, 0, V, 1), (1, 1), V, V,
+                          (T * B, Cp, 1), splitk=sk)
             # weight gradients of both stages: one batched GEMM each over every (t, clip) pair
             dWg = torch.empty(2, V, Cp, 2 * H, dtype=torch.float32, device=dev)
             dWu = torch.empty(2, V, Cp, H, dtype=torch.float32, device=dev)

@@ -379,6 +379,9 @@ int fmm_gruscan_export_fs(const void* fs, void* ZR, void* LG, void* HC, void* LU
 int fmm_pn_dgrad(const void* in, const void* W, void* out, int P, long long rows, int V, int K, int Cp, int c0, int ncols, const float* bias,
                  int relu, cudaStream_t stream); /* + bias[c0 + c] (fp32, may be null), optional ReLU: V = 1 is a Linear layer (TA.py:33-37) */
 int fmm_pn_wgrad_chunks(int P, long long rows, int V);
+/* supports gradient: part[i][n][m] (i < fmm_pn_ds_parts(), 32 x 32 fp32 each, summed by the caller) of sum_{row,c} G[row][n][c] X[row][m][c] */
+int fmm_pn_ds_parts(void);
+int fmm_pn_ds(const void* G, const void* X, float* part, long long rows, int V, int Cp, cudaStream_t stream);
 int fmm_pn_wgrad(const void* xc, const void* dy, float* part, int P, long long rows, int V, int Cp, int Co, cudaStream_t stream);
 
 /* Flash-style time-axis attention (csrc/tattn.cu; TA.py:55-62 softmax(q k^T / sqrt(c), -1) v per (clip, joint)): one CTA per

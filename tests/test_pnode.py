@@ -43,3 +43,20 @@ def test_pn_wgrad(P, R, V, Cp, Co):
     pn_wgrad(xc, dy, dW)
     ref = torch.einsum("prnc,prno->pnco", xc.double(), dy.double())
     assert _rel(dW, ref) < 1e-5
+
+
+@gpu
+@pytest.mark.parametrize("R,V,Cp", [(2000, 25, 136), (333, 14, 72), (5, 30, 144)])
+def test_pn_ds(R, V, Cp):
+    """Supports gradient partials: sum_{row,c} G[row][n][c] X[row][m][c] (EmbGCN.py:83 backward)."""
+    from fall_multimodal_b200 import _lib as L
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(R)
+    G = torch.randn(R, V, Cp, generator=g).to(dev).bfloat16()
+    X = torch.randn(R, V, Cp, generator=g).to(dev).bfloat16()
+    part = torch.empty(L.load().fmm_pn_ds_parts(), 32, 32, dtype=torch.float32, device=dev)
+    L.check(L.load().fmm_pn_ds(G.data_ptr(), X.data_ptr(), part.data_ptr(), R, V, Cp, L.stream()), "pn_ds")
+    got = part.sum(0)
+    ref = torch.einsum("rnc,rmc->nm", G.double(), X.double())
+    assert _rel(got[:V, :V], ref) < 1e-5
+    assert got[V:].abs().max().item() == 0 and got[:, V:].abs().max().item() == 0

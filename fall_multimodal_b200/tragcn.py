@@ -215,8 +215,9 @@ def pn_dgrad(dPL, Wd, out, c0=0, ncols=None, bias=None, relu=False):
     R, V, K = dPL.shape
     Cp = Wd.shape[1]
     ncols = Cp - c0 if ncols is None else ncols
-    L.check(L.load().fmm_pn_dgrad(dPL.data_ptr(), Wd.data_ptr(), out.data_ptr(), 1, R, V, K, Cp, c0, ncols,
-                                  bias.data_ptr() if bias is not None else None, int(relu), L.stream()), "pn_dgrad")
+    _timed("pnode", 2.0 * R * V * K * ncols, float(R * V * (K + ncols) * 2),
+           lambda: L.check(L.load().fmm_pn_dgrad(dPL.data_ptr(), Wd.data_ptr(), out.data_ptr(), 1, R, V, K, Cp, c0, ncols,
+                                                 bias.data_ptr() if bias is not None else None, int(relu), L.stream()), "pn_dgrad"))
 
 
 def _pn_linear_ok(x, Kin, Nout, out_dtype):
@@ -229,7 +230,8 @@ def pn_wgrad(XC, dPL, dW):
     R = XC.numel() // (P * V * Cp)
     ch = L.load().fmm_pn_wgrad_chunks(P, R, V)
     part = torch.empty(ch, P, V, Cp, Co, dtype=torch.float32, device=XC.device)
-    L.check(L.load().fmm_pn_wgrad(XC.data_ptr(), dPL.data_ptr(), part.data_ptr(), P, R, V, Cp, Co, L.stream()), "pn_wgrad")
+    _timed("pnode", 2.0 * P * R * V * Cp * Co, float(P * R * V * (Cp + Co) * 2),
+           lambda: L.check(L.load().fmm_pn_wgrad(XC.data_ptr(), dPL.data_ptr(), part.data_ptr(), P, R, V, Cp, Co, L.stream()), "pn_wgrad"))
     torch.sum(part, 0, out=dW)
 
 
@@ -245,7 +247,8 @@ def _bptt_tail(XCg, XCu, dXg, dXu, dPLg, dPLu, T, B, V, Cp, H):
             for dXs, XC in ((dXg, XCg), (dXu, XCu)):
                 if XC.dtype == torch.bfloat16 and V <= 32 and Cp <= 144:       # row-streaming kernel (csrc/pnode.cu), partials summed here
                     part = torch.empty(L.load().fmm_pn_ds_parts(), 32, 32, dtype=torch.float32, device=dev)
-                    L.check(L.load().fmm_pn_ds(dXs.data_ptr(), XC[1].data_ptr(), part.data_ptr(), T * B, V, Cp, L.stream()), "pn_ds")
+                    _timed("pnode", 2.0 * T * B * V * V * Cp, float(2 * T * B * V * Cp * 2),
+                           lambda: L.check(L.load().fmm_pn_ds(dXs.data_ptr(), XC[1].data_ptr(), part.data_ptr(), T * B, V, Cp, L.stream()), "pn_ds"))
                     dS += part.sum(0)[:V, :V]
                 else:
                     bgemm(dXs, 0, (0, 0, Cp, V * Cp, 1, 0), XC[1], 0, (0, 0, Cp, V * Cp, 1, 0), dS, 0, (0, 0, V, 1), (1, 1), V, V,
@@ -348,7 +351,14 @@ def _scan_call(mode, B, T, V, NC, **kw):
         a.prof = scan_prof[mode].data_ptr()
     a.B, a.T, a.V, a.NC = B, T, V, NC
     a.KS, a.xb_slices, a.xb_slot0, a.tsplit = kw.get("KS", 8), kw.get("xb_slices", 8), kw.get("xb_slot0", 0), kw.get("tsplit", 1)
-    L.check(L.load().fmm_gruscan(C.byref(a), mode, L.stream()), "gruscan")
+    BC = gruscan_geometry(V)[0]
+    rows = T * NC * BC * V
+    K = a.KS * 8 if mode == 0 else 64
+    nbytes = sum(kw[k].numel() * kw[k].element_size() for k in ("px", "xcg", "xcu", "fs", "hout", "dxu", "dxgz", "dxgr", "dhout") if kw.get(k) is not None)
+    if mode == 0:
+        nbytes += rows * K * 2 * 2
+    _timed(("gruscan_xpart", "gruscan_fwd", "gruscan_bwd")[mode], 2.0 * rows * K * 192 * 2, float(nbytes),
+           lambda: L.check(L.load().fmm_gruscan(C.byref(a), mode, L.stream()), "gruscan"))
 
 
 class _GraphGRUScanP(Function):
@@ -700,7 +710,8 @@ class _AttentionF(Function):
             out = torch.empty(B, T, V, Cc, dtype=q.dtype, device=q.device)
             lse = torch.empty(B * V, Tp, dtype=torch.float32, device=q.device)
             a = _AttentionF._args(q, k, v, out, lse, T, btvc)
-            L.check(L.load().fmm_tattn(C.byref(a), 0, L.stream()), "tattn")
+            _timed("tattn_fwd", 4.0 * B * V * Tp * Tp * 64, float((q.numel() + k.numel() + v.numel() + out.numel()) * 2),
+                   lambda: L.check(L.load().fmm_tattn(C.byref(a), 0, L.stream()), "tattn"))
         ctx.saved = (q, k, v, out, lse)
         ctx.T, ctx.btvc = T, btvc
         return out
@@ -714,7 +725,9 @@ class _AttentionF(Function):
             dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
             a = _AttentionF._args(q, k, v, out, lse, ctx.T, ctx.btvc)
             a.dout, a.dq, a.dk, a.dv = do.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
-            L.check(L.load().fmm_tattn(C.byref(a), 1, L.stream()), "tattn")
+            Bq, _, Vq, Tp = q.shape
+            _timed("tattn_bwd", 14.0 * Bq * Vq * Tp * Tp * 64, float((2 * q.numel() + 2 * k.numel() + 2 * v.numel() + 2 * out.numel()) * 2),
+                   lambda: L.check(L.load().fmm_tattn(C.byref(a), 1, L.stream()), "tattn"))
         return dq, dk, dv, None
 
 

@@ -891,12 +891,56 @@ class EmbGCN(nn.Module):
                             torch.cat([Wl[:, Dx:], Wl[:, :Dx], bl[:, None], z], 1)])
 
 
-class GRU(nn.Module):
-    def __init__(self, node_num, dim_in, dim_out, adj, cheb_k, embed_dim):
+class EmbGCN_noGate(nn.Module):
+    """EmbGCN.py:91-109 (the "TARGCN-noGate" import variant of GRU.py:4): the per-node product without the static-adjacency
+    gate. Same kernels: the Linear path of the stage weights is zero, so its SiLU term vanishes."""
+
+    def __init__(self, dim_in, dim_out, adj, cheb_k, embed_dim):
         super().__init__()
+        self.register_buffer("_colscale", torch.ones(adj.shape[0]), persistent=False)
+        self.weights_pool = nn.Parameter(torch.randn(embed_dim, dim_in, dim_out) * 0.02)
+        self.bias_pool = nn.Parameter(torch.randn(embed_dim, dim_out) * 0.02)
+
+    def stage_weights(self, E, Cp, H):
+        Cin, Co = self.weights_pool.shape[1], self.weights_pool.shape[2]
+        Wn = torch.einsum("nd,dio->nio", E, self.weights_pool)
+        bn = E @ self.bias_pool
+        Dx = Cin - H
+        g = torch.cat([Wn[:, Dx:], Wn[:, :Dx], bn[:, None], E.new_zeros(E.shape[0], Cp - Cin - 1, Co)], 1)
+        return torch.stack([g, torch.zeros_like(g)])
+
+
+class EmbGCN_linear(nn.Module):
+    """EmbGCN.py:111-123 (the "TARGCN-linear" variant, GRU.py:5): one shared Linear on the adjacency-mixed input = the graph path
+    with the same weights for every joint."""
+
+    def __init__(self, dim_in, dim_out, adj, cheb_k, embed_dim):
+        super().__init__()
+        self.cheb_k = cheb_k
+        self.register_buffer("_colscale", torch.ones(adj.shape[0]), persistent=False)
+        self.linear = nn.Linear(dim_in, dim_out, bias=True)
+
+    def stage_weights(self, E, Cp, H):
+        V = E.shape[0]
+        Co, Cin = self.linear.weight.shape
+        Wt = self.linear.weight.t()
+        Dx = Cin - H
+        g = torch.cat([Wt[Dx:], Wt[:Dx], self.linear.bias[None], E.new_zeros(Cp - Cin - 1, Co)], 0)[None].expand(V, Cp, Co)
+        return torch.stack([g, torch.zeros_like(g)])
+
+
+_GCN_VARIANTS = {"EmbGCN": EmbGCN, "EmbGCN_noGate": EmbGCN_noGate, "EmbGCN_linear": EmbGCN_linear}
+
+
+class GRU(nn.Module):
+    """``gcn``: the graph convolution class (or its name); the reference picks it by editing the import at GRU.py:3-6."""
+
+    def __init__(self, node_num, dim_in, dim_out, adj, cheb_k, embed_dim, gcn=EmbGCN):
+        super().__init__()
+        gcn = _GCN_VARIANTS[gcn] if isinstance(gcn, str) else gcn
         self.node_num, self.hidden_dim, self.dim_in = node_num, dim_out, dim_in
-        self.gate = EmbGCN(dim_in + dim_out, 2 * dim_out, adj, cheb_k, embed_dim)
-        self.update = EmbGCN(dim_in + dim_out, dim_out, adj, cheb_k, embed_dim)
+        self.gate = gcn(dim_in + dim_out, 2 * dim_out, adj, cheb_k, embed_dim)
+        self.update = gcn(dim_in + dim_out, dim_out, adj, cheb_k, embed_dim)
 
 
 class Transform(nn.Module):
@@ -956,13 +1000,13 @@ class transformer_layer(nn.Module):
 
 
 class AVWDCRNN(nn.Module):
-    def __init__(self, node_num, dim_in, dim_out, cheb_k, embed_dim, adj, num_layers=1, seq_len=30):
+    def __init__(self, node_num, dim_in, dim_out, cheb_k, embed_dim, adj, num_layers=1, seq_len=30, gcn=EmbGCN):
         super().__init__()
         assert num_layers >= 1, "At least one GRU layer in the Encoder."
         self.node_num, self.input_dim, self.num_layers = node_num, dim_in, num_layers
-        self.dcrnn_cells = nn.ModuleList([GRU(node_num, dim_in, dim_out, adj, cheb_k, embed_dim)])
+        self.dcrnn_cells = nn.ModuleList([GRU(node_num, dim_in, dim_out, adj, cheb_k, embed_dim, gcn)])
         for _ in range(1, num_layers):
-            self.dcrnn_cells.append(GRU(node_num, dim_out, dim_out, adj, cheb_k, embed_dim))
+            self.dcrnn_cells.append(GRU(node_num, dim_out, dim_out, adj, cheb_k, embed_dim, gcn))
         self.trans_layer_T = transformer_layer(dim_out, dim_out, 2, 2, seq_len=seq_len)
 
     def forward(self, x, node_embeddings):
@@ -991,7 +1035,7 @@ class TARGCN(nn.Module):
     is built for (the reference hard-codes 30 as a default argument of Transform / PositionalEncoding)."""
 
     def __init__(self, input_dim=3, num_classes=11, num_nodes=14, rnn_units=64, output_dim=64, horizon=30, num_layers=2,
-                 embed_dim=64, cheb_k=2, adj=None, seq_len=30):
+                 embed_dim=64, cheb_k=2, adj=None, seq_len=30, gcn="EmbGCN"):
         super().__init__()
         if rnn_units % 32 or rnn_units > 256:
             raise NotImplementedError("rnn_units must be a multiple of 32 up to 256")
@@ -1004,7 +1048,7 @@ class TARGCN(nn.Module):
         adj = torch.as_tensor(adj, dtype=torch.float32)
         assert adj.shape == (num_nodes, num_nodes)
         self.node_embeddings = nn.Parameter(torch.randn(num_nodes, embed_dim))
-        self.encoder = AVWDCRNN(num_nodes, input_dim, rnn_units, cheb_k, embed_dim, adj, num_layers, seq_len)
+        self.encoder = AVWDCRNN(num_nodes, input_dim, rnn_units, cheb_k, embed_dim, adj, num_layers, seq_len, gcn)
         self.end_conv = nn.Conv2d(6, horizon * output_dim, kernel_size=(1, rnn_units), bias=True)
         self.fc = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(output_dim, num_classes))
         self.compute_dtype = None

@@ -45,7 +45,25 @@ def emb_gcn_invariants(sd, prefix, E, sym):
     return supports, colscale, weights, bias
 
 
+def emb_gcn_nogate(x, E, sd, prefix):
+    """EmbGCN_noGate.forward (EmbGCN.py:99-109): the per-node product alone."""
+    V = E.shape[0]
+    supports = F.softmax(F.relu(E @ E.t()), dim=1) + torch.eye(V, dtype=E.dtype, device=E.device)
+    weights = torch.einsum("nd,dio->nio", E, sd[prefix + "weights_pool"])
+    bias = E @ sd[prefix + "bias_pool"]
+    return torch.einsum("bni,nio->bno", torch.einsum("nm,bmc->bnc", supports, x), weights) + bias
+
+
+def emb_gcn_linear(x, E, sd, prefix):
+    """EmbGCN_linear.forward (EmbGCN.py:116-123): one shared Linear on the adjacency-mixed input."""
+    V = E.shape[0]
+    supports = F.softmax(F.relu(E @ E.t()), dim=1) + torch.eye(V, dtype=E.dtype, device=E.device)
+    return F.linear(torch.einsum("nm,bmc->bnc", supports, x), sd[prefix + "linear.weight"], sd[prefix + "linear.bias"])
+
+
 def emb_gcn(x, inv, sd, prefix):
+    if isinstance(inv, tuple) and len(inv) == 2:          # (variant name, E): the import-time variants of GRU.py:3-6
+        return (emb_gcn_nogate if inv[0] == "noGate" else emb_gcn_linear)(x, inv[1], sd, prefix)
     supports, colscale, weights, bias = inv
     x_static = F.linear(colscale[None, :, None] * x, sd[prefix + "linear.weight"], sd[prefix + "linear.bias"])  # :77-78
     x_g = torch.einsum("nm,bmc->bnc", supports, x)                                     # :83
@@ -75,15 +93,15 @@ def transform(x, sd, prefix):
     return F.layer_norm(y, (c,), sd[prefix + "lnff.weight"], sd[prefix + "lnff.bias"])
 
 
-def encoder(sd, x, sym, num_layers=2, H=64, trans_layers=2, collect=None):
+def encoder(sd, x, sym, num_layers=2, H=64, trans_layers=2, collect=None, variant=None):
     """AVWDCRNN.forward (TRAGCN.py:150-169) from the zero state; x (B,T,V,Din) -> (B,T,V,H)."""
     E = sd["node_embeddings"]
     B, T, V, _ = x.shape
     cur = x
     for i in range(num_layers):
         p = f"encoder.dcrnn_cells.{i}."
-        inv_g = emb_gcn_invariants(sd, p + "gate.", E, sym)
-        inv_u = emb_gcn_invariants(sd, p + "update.", E, sym)
+        inv_g = emb_gcn_invariants(sd, p + "gate.", E, sym) if variant is None else (variant, E)
+        inv_u = emb_gcn_invariants(sd, p + "update.", E, sym) if variant is None else (variant, E)
         state = torch.zeros(B, V, H, dtype=x.dtype, device=x.device)
         states = []
         for t in range(T):
@@ -100,12 +118,12 @@ def encoder(sd, x, sym, num_layers=2, H=64, trans_layers=2, collect=None):
     return cur
 
 
-def targcn_forward(sd, source, adj=None, horizon=30, output_dim=64, num_layers=2, collect=None):
+def targcn_forward(sd, source, adj=None, horizon=30, output_dim=64, num_layers=2, collect=None, variant=None):
     """TARGCN.forward (TRAGCN.py:209-224); source (B,T,V,D) -> (B,num_classes)."""
     V = source.shape[2]
     adj = torch.ones(V, V) if adj is None else adj                                        # :191
     sym = sym_norm_adj(adj)
-    out = encoder(sd, source, sym, num_layers=num_layers, collect=collect)[:, -6:]       # :215
+    out = encoder(sd, source, sym, num_layers=num_layers, collect=collect, variant=variant)[:, -6:]       # :215
     out = F.conv2d(out, sd["end_conv.weight"], sd["end_conv.bias"])                       # (B, horizon*C, V, 1)
     out = out.squeeze(-1).reshape(-1, horizon, output_dim, V).permute(0, 1, 3, 2)         # :220-221
     feat = out.permute(0, 3, 1, 2).mean(dim=(2, 3))                                       # AdaptiveAvgPool2d(1)+Flatten

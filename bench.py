@@ -211,14 +211,15 @@ def run_reference(args):
 GLOBAL_BATCH_3 = 1024
 
 
-def bench_config3(args, dev, world, rank, barrier):
+def bench_config3(args, dev, world, rank, barrier, sync_bn=False):
     """BASELINE configs[2]: 3-stream joint/bone/motion GSTCAN, GLOBAL batch 1024 sharded over the ranks (strong scaling),
-    bf16, NCCL gradient all-reduce bucketed behind backward, whole step as a CUDA graph. Every rank runs this."""
+    bf16, NCCL gradient all-reduce bucketed behind backward, whole step as a CUDA graph. Every rank runs this.
+    sync_bn: BatchNorm statistics of the global batch (parallel.convert_sync_batchnorm) instead of per-shard ones."""
     import torch.distributed as dist
 
     import fall_multimodal_b200 as fmm
     from fall_multimodal_b200.graphs import GraphedStep
-    from fall_multimodal_b200.parallel import GradBuckets
+    from fall_multimodal_b200.parallel import GradBuckets, convert_sync_batchnorm
 
     B = GLOBAL_BATCH_3 // world
     torch.manual_seed(7)
@@ -226,6 +227,8 @@ def bench_config3(args, dev, world, rank, barrier):
     if world > 1:
         for p in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(p.data, 0)
+    if sync_bn:
+        convert_sync_batchnorm(model, strict=True)
     opt = torch.optim.RMSprop(model.parameters(), lr=1e-3, capturable=True)
     buckets = GradBuckets([list(model.fc.parameters()) + list(model.stgcan_3.parameters()), list(model.stgcan_2.parameters()),
                            list(model.stgcan_1.parameters())])
@@ -267,7 +270,9 @@ def bench_config3(args, dev, world, rank, barrier):
     return {"workload": "3-stream GSTCAN (joints 3x64x33 + motion 2x63x33 + bones 3x64x33) + Linear(768, 11), train step "
                         "fwd+bwd+RMSprop, bf16", "metric": "train clips/sec fwd+bwd (3-stream GSTCAN)", "value": GLOBAL_BATCH_3 * steps / (ms / 1e3),
             "unit": "clips/s", "global_batch": GLOBAL_BATCH_3, "clips_per_gpu": B, "n_gpus": world, "scaling": "strong", "steps": steps,
-            "ms_per_step": ms / steps, "bn": "per-shard statistics (SURVEY 8(e) option b)",
+            "ms_per_step": ms / steps,
+            "bn": ("global-batch statistics (SyncBN, SURVEY 8(e) option a: <= 3 small collectives per block and direction, captured "
+                   "in the step's graph)" if sync_bn else "per-shard statistics (SURVEY 8(e) option b)"),
             "gradient_bytes_per_step": sum(p.numel() for p in model.parameters()) * 4, "loss": loss,
             "note": "efficiency vs N=1 = value(N) / (N * value(1)) over the driver's N = 1, 2, 4, 8 runs of this same line"}
 
@@ -504,6 +509,10 @@ def run_ours(args):
         graphed = eager_step = None   # drop the captured step (its memory pool) before the next model is built
         torch.cuda.empty_cache()
         config3 = bench_config3(args, dev, world, rank, barrier)
+        if world > 1 and args.config3_sync_bn:
+            torch.cuda.empty_cache()
+            sb = bench_config3(args, dev, world, rank, barrier, sync_bn=True)
+            config3["sync_bn"] = {k: sb[k] for k in ("value", "unit", "ms_per_step", "steps", "bn", "loss")}
 
     if rank == 0:
         peaks = {}
@@ -884,6 +893,7 @@ def main():
     ap.add_argument("--no-torch-eager", action="store_true", help="skip the stock PyTorch/cuDNN eager leg on the same GPU (N=1)")
     ap.add_argument("--torch-eager-gpu", action="store_true", help="(kept for compatibility: the eager leg is on by default)")
     ap.add_argument("--no-config3", action="store_true", help="skip the 3-stream / global-batch-1024 strong-scaling sub-benchmark")
+    ap.add_argument("--config3-sync-bn", type=int, default=0, help="1: N > 1 also times config 3 with SyncBN (global-batch statistics)")
     ap.add_argument("--no-extra", action="store_true", help="skip the TARGCN (config 4) and sensor (config 5) sub-benchmarks (N=1)")
     ap.add_argument("--workload", default="gstcan", choices=["gstcan", "targcn"],
                     help="gstcan: BASELINE configs[1] (the headline, default); targcn: configs[3] (TARGCN T=300 V=25, 512 clips)")

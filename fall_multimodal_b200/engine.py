@@ -76,6 +76,14 @@ class TrunkEngine:
         self._wstreams = {}
         self._pstreams = {}
         self.premask = True   # fused graph-conv backward stores dx already masked by the previous block's ReLU
+        # SyncBN (SURVEY 8(e) option a): None = per-shard statistics; True / a process group = every BatchNorm of the trunk
+        # (data_bn, BN1, BN2, residual BN, the SE block's BatchNorm over the batch axis) normalises with the statistics of the
+        # GLOBAL batch. Set through parallel.convert_sync_batchnorm. Per block and direction at most three small collectives:
+        # forward  all-reduce(BN1 sums), all-reduce(BN2 sums) [+ residual-BN sums in the two strided blocks], all-gather(SE pool);
+        # backward all-gather(per-clip sums S1..S3 of the block tail), all-reduce(BN1 gradient sums).
+        # The per-clip (N,C) tensors of the SE / BN2-coefficient kernels are tiny, so they are gathered and every rank runs those
+        # kernels on the global N (unchanged kernels, global BatchNorm over N for free) and keeps its own rows.
+        self.sync_bn = None
 
     def csr(self, device):
         key = str(device)
@@ -145,6 +153,20 @@ class TrunkEngine:
                 prep.append(d)
         return prep
 
+    def _sync(self, training: bool):
+        """(torch.distributed, group, world, rank) when batch statistics are exchanged in this pass, else None."""
+        if not training or self.sync_bn is None or self.sync_bn is False:
+            return None
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            return None
+        group = None if self.sync_bn is True else self.sync_bn
+        world = dist.get_world_size(group)
+        if world == 1:
+            return None
+        return dist, group, world, dist.get_rank(group)
+
     # ------------------------------------------------------------------------------------------
     def forward(self, P: dict, skel: torch.Tensor, training: bool, dt: torch.dtype, need_grad: bool):
         """Returns (pooled feature (N,256) fp32, saved-state dict for backward)."""
@@ -157,6 +179,9 @@ class TrunkEngine:
         NR = ops.NREP
         arena = _Arena(dev, 7 * 6 * NR * 256 + 4096 + 2 * V * C, 8 * N * 256 + 4096)
         sv = {"blocks": [], "N": N, "dt": dt, "training": training}
+        sy = self._sync(training)           # SyncBN: every rank must hold the same number of clips
+        W = sy[2] if sy else 1
+        sv["sync"] = sy
         prep = self._prepare(P, dt, need_grad, dev, V)
         sv["prep"] = prep
         cur_stream = torch.cuda.current_stream(dev)
@@ -169,7 +194,9 @@ class TrunkEngine:
         a0, b0, mean0, rstd0 = (torch.empty(VC, dtype=torch.float32, device=dev) for _ in range(4))
         if training:
             ops.databn_stats(xin, st0[:VC], st0[VC:])
-        ops.bn_finalize(st0[:VC], st0[VC:], N * T, P["data_bn.weight"], P["data_bn.bias"], P["data_bn.running_mean"],
+            if sy:
+                sy[0].all_reduce(st0, group=sy[1])
+        ops.bn_finalize(st0[:VC], st0[VC:], N * T * W, P["data_bn.weight"], P["data_bn.bias"], P["data_bn.running_mean"],
                         P["data_bn.running_var"], training, a0, b0, mean0, rstd0)
         x = ops.databn_apply(xin, a0, b0, torch.empty(N, T, V, C, dtype=dt, device=dev))
         sv["data_bn"] = (xin, mean0, rstd0)
@@ -199,7 +226,9 @@ class TrunkEngine:
                 # BN1 statistics (stgcan.py:112), applied inside the temporal conv's prologue
                 if training:
                     ops.colstats(G, st[:NR * Cout], st[NR * Cout:])
-            ops.bn_finalize(st[:NR * Cout], st[NR * Cout:], N * T * V, P[pre + "tcn.0.weight"], P[pre + "tcn.0.bias"],
+            if sy:
+                sy[0].all_reduce(st, group=sy[1])
+            ops.bn_finalize(st[:NR * Cout], st[NR * Cout:], N * T * V * W, P[pre + "tcn.0.weight"], P[pre + "tcn.0.bias"],
                             P[pre + "tcn.0.running_mean"], P[pre + "tcn.0.running_var"], training, a1, b1, mean1, rstd1)
 
             # temporal conv 9x1 (stgcan.py:114-118)
@@ -224,19 +253,27 @@ class TrunkEngine:
                 ops.colstats(U, st2[:NR * Cout], st2[NR * Cout:], pool)
             else:
                 ops.colstats(U, None, None, pool)
-            ops.bn_finalize(st2[:NR * Cout], st2[NR * Cout:], N * To * V, P[pre + "tcn.3.weight"], P[pre + "tcn.3.bias"],
+            if sy:
+                sy[0].all_reduce(st2, group=sy[1])
+            ops.bn_finalize(st2[:NR * Cout], st2[NR * Cout:], N * To * V * W, P[pre + "tcn.3.weight"], P[pre + "tcn.3.bias"],
                             P[pre + "tcn.3.running_mean"], P[pre + "tcn.3.running_var"], training, a2, b2, mean2, rstd2)
 
             # squeeze-excite (stgcan.py:63-70)
             C4 = int(Cout / 4)
             ca = pre + "channel_attention_module.atten."
             f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
-            p_, h_, s_, k1, k0 = f32(N, Cout), f32(N, C4), f32(N, Cout), f32(N, Cout), f32(N, Cout)
+            Ns = N * W
+            if sy:   # the SE block's BatchNorm runs over the batch axis: gather the pooled rows, evaluate the block on the global N
+                pool_l, pool = pool, f32(Ns, Cout)
+                sy[0].all_gather_into_tensor(pool, pool_l.contiguous(), group=sy[1])
+            p_, h_, s_, k1, k0 = f32(Ns, Cout), f32(Ns, C4), f32(Ns, Cout), f32(Ns, Cout), f32(Ns, Cout)
             ah, bh, hmean, hrstd = f32(C4), f32(C4), f32(C4), f32(C4)
             M = To * V
             ops.se_fwd(pool, a2, b2, 1.0 / M, P[ca + "1.weight"], P[ca + "1.bias"], P[ca + "2.weight"],
                        P[ca + "2.bias"], P[ca + "2.running_mean"], P[ca + "2.running_var"], training,
                        P[ca + "4.weight"], P[ca + "4.bias"], p_, h_, ah, bh, hmean, hrstd, s_, k1, k0)
+            if sy:
+                k1, k0 = k1[sy[3] * N:(sy[3] + 1) * N], k0[sy[3] * N:(sy[3] + 1) * N]
 
             # residual branch (stgcan.py:123-133)
             R = ar = br = meanr = rstdr = pw_r = None
@@ -249,7 +286,9 @@ class TrunkEngine:
                 st3 = arena.f64(2 * NR * Cout)
                 if training:
                     ops.colstats(R, st3[:NR * Cout], st3[NR * Cout:])
-                ops.bn_finalize(st3[:NR * Cout], st3[NR * Cout:], N * To * V, P[pre + "residual.1.weight"],
+                    if sy:
+                        sy[0].all_reduce(st3, group=sy[1])
+                ops.bn_finalize(st3[:NR * Cout], st3[NR * Cout:], N * To * V * W, P[pre + "residual.1.weight"],
                                 P[pre + "residual.1.bias"], P[pre + "residual.1.running_mean"],
                                 P[pre + "residual.1.running_var"], training, ar, br, meanr, rstdr)
                 res = R
@@ -295,6 +334,13 @@ class TrunkEngine:
         z32 = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)
         dY = (dfeat / sv["M_last"]).to(dt)[:, None, None, :].expand(N, sv["T_last"], V, 256).contiguous()
         cur = torch.cuda.current_stream(dev)
+        sy = sv.get("sync")
+        W = sy[2] if sy else 1
+        Ns = N * W
+        rows = slice(sy[3] * N, (sy[3] + 1) * N) if sy else slice(None)
+        # SyncBN: gradients of the BatchNorm / SE parameters come out of kernels that ran on the GLOBAL batch; divided by the
+        # world size at the end they are this rank's share, so the data-parallel gradient average reproduces the global sum
+        glob = []
         ws = None
         if self.overlap_wgrad:
             key = (str(dev), cur.cuda_stream)
@@ -339,10 +385,16 @@ class TrunkEngine:
             S3 = arena.f32(N, Cout) if R is not None else None
             Ym = None if premasked else Y
             ops.blockout_bwd_reduce(dY, Ym, U, R, S1, S2, S3)
+            if sy:   # one gather per block: the per-clip sums of every rank, (world, nS, N, C) -> nS x (world * N, C)
+                loc = torch.stack([S1, S2] + ([S3] if S3 is not None else []))
+                gat = torch.empty((W,) + tuple(loc.shape), dtype=torch.float32, device=dev)
+                sy[0].all_gather_into_tensor(gat, loc, group=sy[1])
+                gat = gat.transpose(0, 1).reshape(loc.shape[0], Ns, Cout)
+                S1, S2, S3 = gat[0], gat[1], (gat[2] if S3 is not None else None)
 
             # ---- SE backward (tiny) ----
-            dq, dp = f32(N, Cout), f32(N, Cout)
-            dhr, r_, dh = f32(N, C4), f32(N, C4), f32(N, C4)
+            dq, dp = f32(Ns, Cout), f32(Ns, Cout)
+            dhr, r_, dh = f32(Ns, C4), f32(Ns, C4), f32(Ns, C4)
             dW1, db1, dgh, dbh = arena.f32(C4, Cout), arena.f32(C4), arena.f32(C4), arena.f32(C4)
             dW2, db2se = arena.f32(Cout, C4), arena.f32(Cout)
             ops.se_bwd(S1, S2, b["a2"], b["b2"], b["s"], b["p"], b["h"], b["ah"], b["bh"], b["hmean"], b["hrstd"],
@@ -355,17 +407,21 @@ class TrunkEngine:
             grads[ca + "2.bias"] = dbh
             grads[ca + "4.weight"] = dW2.view(Cout, C4, 1, 1)
             grads[ca + "4.bias"] = db2se
+            glob += [dW1, db1, dgh, dbh, dW2, db2se]
 
             # ---- BN2 (+ residual BN) backward folded into affine coefficients ----
-            k1, k3, k2 = f32(N, Cout), f32(N, Cout), f32(Cout)
+            k1, k3, k2 = f32(Ns, Cout), f32(Ns, Cout), f32(Cout)
             dg2, db2 = arena.f32(Cout), arena.f32(Cout)
             r1 = r2 = r3 = dgr = dbr = None
             if R is not None:
                 r1, r2, r3 = f32(Cout), f32(Cout), f32(Cout)
                 dgr, dbr = arena.f32(Cout), arena.f32(Cout)
             ops.bn2_bwd_coef(S1, S2, S3, b["pool"], dp, b["s"], b["a2"], b["mean2"], b["rstd2"], b["ar"],
-                             b["meanr"], b["rstdr"], M, N * M, training, k1, k2, k3, r1, r2, r3, dg2, db2, dgr, dbr)
+                             b["meanr"], b["rstdr"], M, Ns * M, training, k1, k2, k3, r1, r2, r3, dg2, db2, dgr, dbr)
             grads[pre + "tcn.3.weight"], grads[pre + "tcn.3.bias"] = dg2, db2
+            glob += [dg2, db2] + ([dgr, dbr] if R is not None else [])
+            if sy:
+                k1, k3 = k1[rows], k3[rows]
             dU = torch.empty_like(U)
             dR = torch.empty_like(R) if R is not None else None
             dPre = torch.empty_like(Y) if (reskind == "identity" and not premasked) else None
@@ -394,12 +450,16 @@ class TrunkEngine:
                     ops.tapconv(dU, pp["wt_d"][1], dH, shifts=[2, 1, 0, -1], tj=T // 2, ostride=2, ooff=1)
 
             # ---- BN1 + ReLU backward ----
-            T1, T2 = arena.f64(NR * Cout), arena.f64(NR * Cout)
+            T12 = arena.f64(2 * NR * Cout)
+            T1, T2 = T12[:NR * Cout], T12[NR * Cout:]
             ops.bn1_bwd_reduce(dH, G, b["a1"], b["b1"], T1, T2)
+            if sy:
+                sy[0].all_reduce(T12, group=sy[1])
             c1, c2, c3 = f32(Cout), f32(Cout), f32(Cout)
             dg1, db1n = arena.f32(Cout), arena.f32(Cout)
-            ops.bn1_bwd_coef(T1, T2, b["a1"], b["mean1"], b["rstd1"], N * T * V, training, c1, c2, c3, dg1, db1n)
+            ops.bn1_bwd_coef(T1, T2, b["a1"], b["mean1"], b["rstd1"], N * T * V * W, training, c1, c2, c3, dg1, db1n)
             grads[pre + "tcn.0.weight"], grads[pre + "tcn.0.bias"] = dg1, db1n
+            glob += [dg1, db1n]
             dG = torch.empty_like(G)
             TblR = arena.f32(NR, V, Cout)
             ops.bn1_bwd_apply(dH, G, b["a1"], b["b1"], c1, c2, c3, dG, TblR)
@@ -463,6 +523,8 @@ class TrunkEngine:
         if ws is not None:
             cur.wait_stream(ws)
             keep.clear()
+        if sy:
+            torch._foreach_mul_(glob, 1.0 / W)
         # ---- data_bn backward (input itself needs no gradient) ----
         xin, mean0, rstd0 = sv["data_bn"]
         VC = V * self.in_channels

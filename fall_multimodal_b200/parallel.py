@@ -13,9 +13,11 @@ exchange of one trunk overlaps the backward kernels of the next. ``wait()`` flus
 filled up (parameters without a gradient) and joins the communication stream before the optimizer
 step. With a single rank nothing is copied or exchanged at all.
 
-BatchNorm statistics are per shard (each rank normalises over its own clips), i.e. DP parity is
-"every shard matches the single-device result on that shard, gradients are the mean of the shard
-gradients" (option b).
+BatchNorm statistics are per shard by default (each rank normalises over its own clips), i.e. DP parity
+is "every shard matches the single-device result on that shard, gradients are the mean of the shard
+gradients" (option b). ``convert_sync_batchnorm(model)`` switches the GSTCAN trunks to
+global-batch statistics (option a): DP parity is then "N ranks x B/N clips == one device x B clips",
+logits, running statistics and (averaged) gradients alike (engine.py: TrunkEngine.sync_bn).
 """
 from __future__ import annotations
 
@@ -114,3 +116,32 @@ class GradBuckets:
         if self._comm_stream is not None and self._comm_used:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
             self._comm_used = False
+
+
+def convert_sync_batchnorm(model: torch.nn.Module, process_group=None, strict: bool = False) -> torch.nn.Module:
+    """SyncBN for the GSTCAN trunks of ``model`` (same call shape as ``torch.nn.SyncBatchNorm.convert_sync_batchnorm``).
+
+    Every BatchNorm inside a trunk - ``data_bn``, the two of each block's ``tcn``, the residual one and the squeeze-excite
+    block's BatchNorm over the batch axis (stgcan.py:63-70, 110-133, 213-218) - then uses the statistics of the global batch:
+    per block and direction at most three small collectives (all-reduce of the fused (sum, sum^2) accumulators, one all-gather
+    of the per-clip (N, C) rows of the SE / block-tail reductions), enqueued on the compute stream so they are captured with the
+    step's CUDA graph. All ranks must hold the same number of clips. The sensor branch's BatchNorm1d layers (CNN1D / BiLSTM
+    tail: a few hundred channels-rows per step) keep per-shard statistics; ``strict=True`` raises if the model has any.
+    ``process_group=False`` switches the trunks back to per-shard statistics."""
+    from .stgcan import STGCAN
+
+    n = 0
+    trunk_bn = set()
+    for m in model.modules():
+        if isinstance(m, STGCAN):
+            m._engine.sync_bn = None if process_group is False else (True if process_group is None else process_group)
+            n += 1
+            trunk_bn.update(id(x) for x in m.modules() if isinstance(x, torch.nn.modules.batchnorm._BatchNorm))
+    if n == 0:
+        raise ValueError("convert_sync_batchnorm: the model has no GSTCAN trunk")
+    if strict:
+        other = [k for k, x in model.named_modules()
+                 if isinstance(x, torch.nn.modules.batchnorm._BatchNorm) and id(x) not in trunk_bn]
+        if other:
+            raise NotImplementedError(f"convert_sync_batchnorm(strict=True): BatchNorm layers outside the trunks stay per shard: {other}")
+    return model

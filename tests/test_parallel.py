@@ -53,3 +53,28 @@ def test_bucketed_allreduce_matches_full_batch():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_convert_sync_batchnorm_marks_every_trunk():
+    """Host logic of SyncBN selection (parallel.convert_sync_batchnorm); the exchange itself is GPU-tested on two NCCL ranks
+    (tests/test_parity_baseline.py::test_syncbn_two_ranks_match_global_batch)."""
+    import pytest
+    import fall_multimodal_b200 as fmm
+    from fall_multimodal_b200.parallel import convert_sync_batchnorm
+
+    ga = {"layout": "mediapipe33", "strategy": "spatial"}
+    m3 = fmm.ThreeStreamSTGCAN(3, ga, 11)
+    assert all(t._engine.sync_bn is None for t in (m3.stgcan_1, m3.stgcan_2, m3.stgcan_3))
+    assert convert_sync_batchnorm(m3, strict=True) is m3
+    assert all(t._engine.sync_bn is True for t in (m3.stgcan_1, m3.stgcan_2, m3.stgcan_3))
+    assert m3.stgcan_1._engine._sync(True) is None        # no process group initialised: per-device statistics
+    assert m3.stgcan_1._engine._sync(False) is None
+    convert_sync_batchnorm(m3, process_group=False)
+    assert all(t._engine.sync_bn is None for t in (m3.stgcan_1, m3.stgcan_2, m3.stgcan_3))
+    m2 = fmm.TwoStreamSTGCAN_CNN1D(3, ga, 11, 15, 30)
+    convert_sync_batchnorm(m2)                              # trunks converted, the sensor branch stays per shard
+    assert m2.stgcan_1._engine.sync_bn is True
+    with pytest.raises(NotImplementedError):
+        convert_sync_batchnorm(m2, strict=True)
+    with pytest.raises(ValueError):
+        convert_sync_batchnorm(fmm.CNN1D(15, 30))

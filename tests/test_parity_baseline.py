@@ -304,6 +304,10 @@ def _dp_worker(rank, world, port, q):
             m.load_state_dict(state)        # running stats back to the pre-step values
             per.append(shard_grads(m, slice(r * n_per, (r + 1) * n_per)))
         gs = max(g.abs().max().item() for g in per[0].values())
+        m.load_state_dict(state)
+        again = shard_grads(m, slice(0, n_per))            # noise floor: shard 0 once more on the same single-GPU code
+        noise = sorted((again[k] - per[0][k]).abs().max().item() / max(per[0][k].abs().max().item(), 1e-3 * gs) for k in again)
+        n_med, n_worst = noise[len(noise) // 2], noise[-1]
         errs = []
         for k in got:
             want = sum(p[k] for p in per) / world
@@ -313,8 +317,8 @@ def _dp_worker(rank, world, port, q):
         # two runs of the same shard differ by fp32 summation order (atomics); on this tiny shard (8 clips x 16 frames) that
         # flips a handful of ReLU decisions, each moving some gradient by a whole element: the typical tensor must agree to
         # rounding, the worst one to the flip level measured for two runs of the SAME single-GPU code
-        ok = med < 1e-5 and worst < 2e-2
-        worst = (med, worst)
+        ok = med < max(1e-5, 4 * n_med) and worst < max(2e-2, 4 * n_worst)
+        worst = dict(median=med, worst=worst, noise_median=n_med, noise_worst=n_worst)
     q.put((rank, ok, worst))
     dist.barrier()
     dist.destroy_process_group()
@@ -337,4 +341,119 @@ def test_data_parallel_nccl_two_ranks_matches_shard_mean():
     for p in procs:
         p.join(timeout=120)
     print("DP (2 NCCL ranks) gradient err vs mean of shard gradients:", res)
+    assert all(ok for _, ok, _ in res), res
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# SyncBN (SURVEY 8(e) option a): two NCCL ranks x B/2 clips == one device x B clips == the fp64 oracle on B clips
+# --------------------------------------------------------------------------------------------------------------------
+def _three_stream(dev, seed=5):
+    import fall_multimodal_b200 as fmm
+
+    m = fmm.ThreeStreamSTGCAN(3, {"layout": "mediapipe33", "strategy": "spatial"}, NC)
+    sd = m.state_dict()
+    fill = O.fill_state_dict({k: tuple(v.shape) for k, v in sd.items() if k != "parents"}, seed)
+    sd.update(fill)
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    m.compute_dtype = torch.float32
+    return m
+
+
+def _syncbn_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from fall_multimodal_b200.parallel import GradBuckets, convert_sync_batchnorm
+
+    Tn, n_per = 16, 8
+    B = world * n_per
+    skel, _, target, _ = O.synthetic_batch(B, Tn, V, NC, sensor_len=L, sensor_ch=CS, seed=91)
+    skel, target = skel.to(dev), target.to(dev)
+    sl = slice(rank * n_per, (rank + 1) * n_per)
+    loss_fn = torch.nn.CrossEntropyLoss()
+
+    # (a) the global batch on this one device, per-device statistics = global statistics
+    g = _three_stream(dev)
+    state0 = {k: v.clone() for k, v in g.state_dict().items()}
+    out_g = g(skel)
+    loss_fn(out_g, target).backward()
+    grads_g = {k: p.grad.detach().clone() for k, p in g.named_parameters() if p.grad is not None}
+    bufs_g = {k: v.clone() for k, v in g.state_dict().items() if "running_" in k}
+    # noise floor: the SAME single-device global batch once more (fp32 atomics order -> a few ReLU decisions flip on 16 tiny clips)
+    g.load_state_dict(state0)
+    for p in g.parameters():
+        p.grad = None
+    loss_fn(g(skel), target).backward()
+    gs0 = max(v.abs().max().item() for v in grads_g.values())
+    noise = sorted((p.grad - grads_g[k]).abs().max().item() / max(grads_g[k].abs().max().item(), 1e-3 * gs0)
+                   for k, p in g.named_parameters() if p.grad is not None)
+    n_med, n_worst = noise[len(noise) // 2], noise[-1]
+
+    # (b) this rank's shard with SyncBN, gradients averaged over the ranks
+    m = _three_stream(dev)
+    m.load_state_dict(state0)
+    convert_sync_batchnorm(m, strict=True)
+    buckets = GradBuckets([list(m.fc.parameters()), list(m.stgcan_3.parameters()), list(m.stgcan_2.parameters()),
+                           list(m.stgcan_1.parameters())])
+    buckets.zero_grad()
+    out = m(skel[sl])
+    loss_fn(out, target[sl]).backward()
+    buckets.wait()
+    torch.cuda.synchronize()
+    got = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    bufs = {k: v.clone() for k, v in m.state_dict().items() if "running_" in k}
+    buckets.close()
+
+    e_out = (out - out_g[sl]).abs().max().item() / out_g.abs().max().item()
+    e_buf = max((bufs[k] - bufs_g[k]).abs().max().item() / max(bufs_g[k].abs().max().item(), 1e-6) for k in bufs_g)
+    gs = max(v.abs().max().item() for v in grads_g.values())
+    errs = sorted((got[k] - grads_g[k]).abs().max().item() / max(grads_g[k].abs().max().item(), 1e-3 * gs) for k in grads_g)
+    med, worst = errs[len(errs) // 2], errs[-1]
+    va = torch.cat([got[k].flatten().double() for k in grads_g])
+    vb = torch.cat([grads_g[k].flatten().double() for k in grads_g])
+    cos = (va @ vb / (va.norm() * vb.norm())).item()
+
+    # (c) rank 0: the fp64 oracle on the global batch (the reference's own BatchNorm semantics at batch B)
+    e_or = None
+    if rank == 0:
+        osd = {k: (v.double().clone() if v.is_floating_point() else v.clone()) for k, v in state0.items()}
+        with torch.no_grad():
+            ref = O.three_stream_forward(osd, skel.double(), osd["parents"], training=True)
+        e_or = (out.double() - ref[sl]).abs().max().item() / ref.abs().max().item()
+    # typical tensor to rounding; the worst at the ReLU-flip level two runs of the same single-GPU code show on 16 tiny clips
+    # forward (logits, running statistics, fp64 oracle): deterministic, 1e-4. Gradients: measured 1e-5 (median tensor) when no ReLU
+    # decision flipped and 3e-4 when one did (the single-device global batch differs from ITSELF by noise_median 1e-6 .. 1e-4 and
+    # noise_worst 3e-2 between two runs: fp32 atomics order on 16 tiny clips); a backward without the cross-rank mean terms is off
+    # by O(1) in most tensors. Gate: the full gradient vectors parallel to 1e-5, the median tensor below 1e-3, the worst tensor at
+    # the measured run-to-run level.
+    ok = (e_out < 1e-4 and e_buf < 1e-4 and med < 1e-3 and worst < max(5e-2, 4 * n_worst) and cos > 1 - 1e-5
+          and (e_or is None or e_or < 1e-4))
+    q.put((rank, ok, dict(logits=e_out, running=e_buf, grad_median=med, grad_worst=worst, grad_cos=cos, noise_median=n_med,
+                          noise_worst=n_worst, logits_vs_fp64_oracle=e_or, tensors=len(errs))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@gpu
+@pytest.mark.timeout(900)
+def test_syncbn_two_ranks_match_global_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    print("SyncBN (2 NCCL ranks x 8 clips) vs one device x 16 clips:", res)
     assert all(ok for _, ok, _ in res), res

@@ -511,8 +511,11 @@ def run_ours(args):
         config3 = bench_config3(args, dev, world, rank, barrier)
         if world > 1 and args.config3_sync_bn:
             torch.cuda.empty_cache()
-            sb = bench_config3(args, dev, world, rank, barrier, sync_bn=True)
-            config3["sync_bn"] = {k: sb[k] for k in ("value", "unit", "ms_per_step", "steps", "bn", "loss")}
+            try:
+                sb = bench_config3(args, dev, world, rank, barrier, sync_bn=True)
+                config3["sync_bn"] = {k: sb[k] for k in ("value", "unit", "ms_per_step", "steps", "bn", "loss")}
+            except Exception as e:   # same code on every rank: a failure is raised by all of them
+                config3["sync_bn"] = {"error": repr(e)[:300]}
 
     if rank == 0:
         peaks = {}
@@ -893,7 +896,7 @@ def main():
     ap.add_argument("--no-torch-eager", action="store_true", help="skip the stock PyTorch/cuDNN eager leg on the same GPU (N=1)")
     ap.add_argument("--torch-eager-gpu", action="store_true", help="(kept for compatibility: the eager leg is on by default)")
     ap.add_argument("--no-config3", action="store_true", help="skip the 3-stream / global-batch-1024 strong-scaling sub-benchmark")
-    ap.add_argument("--config3-sync-bn", type=int, default=0, help="1: N > 1 also times config 3 with SyncBN (global-batch statistics)")
+    ap.add_argument("--config3-sync-bn", type=int, default=1, help="1: N > 1 also times config 3 with SyncBN (global-batch statistics)")
     ap.add_argument("--no-extra", action="store_true", help="skip the TARGCN (config 4) and sensor (config 5) sub-benchmarks (N=1)")
     ap.add_argument("--workload", default="gstcan", choices=["gstcan", "targcn"],
                     help="gstcan: BASELINE configs[1] (the headline, default); targcn: configs[3] (TARGCN T=300 V=25, 512 clips)")

@@ -221,7 +221,8 @@ def bench_config3(args, dev, world, rank, barrier, sync_bn=False):
     from fall_multimodal_b200.graphs import GraphedStep
     from fall_multimodal_b200.parallel import GradBuckets, convert_sync_batchnorm
 
-    B = GLOBAL_BATCH_3 // world
+    gb3 = int(getattr(args, "config3_batch", 0) or GLOBAL_BATCH_3)
+    B = gb3 // world
     torch.manual_seed(7)
     model = fmm.ThreeStreamSTGCAN(3, {"layout": LAYOUT, "strategy": "spatial"}, NUM_CLASS).to(dev).train()
     if world > 1:
@@ -268,8 +269,8 @@ def bench_config3(args, dev, world, rank, barrier, sync_bn=False):
     graphed = None
     torch.cuda.empty_cache()
     return {"workload": "3-stream GSTCAN (joints 3x64x33 + motion 2x63x33 + bones 3x64x33) + Linear(768, 11), train step "
-                        "fwd+bwd+RMSprop, bf16", "metric": "train clips/sec fwd+bwd (3-stream GSTCAN)", "value": GLOBAL_BATCH_3 * steps / (ms / 1e3),
-            "unit": "clips/s", "global_batch": GLOBAL_BATCH_3, "clips_per_gpu": B, "n_gpus": world, "scaling": "strong", "steps": steps,
+                        "fwd+bwd+RMSprop, bf16", "metric": "train clips/sec fwd+bwd (3-stream GSTCAN)", "value": gb3 * steps / (ms / 1e3),
+            "unit": "clips/s", "global_batch": gb3, "clips_per_gpu": B, "n_gpus": world, "scaling": "strong", "steps": steps,
             "ms_per_step": ms / steps,
             "bn": ("global-batch statistics (SyncBN, SURVEY 8(e) option a: <= 3 small collectives per block and direction, captured "
                    "in the step's graph)" if sync_bn else "per-shard statistics (SURVEY 8(e) option b)"),
@@ -897,6 +898,7 @@ def main():
     ap.add_argument("--torch-eager-gpu", action="store_true", help="(kept for compatibility: the eager leg is on by default)")
     ap.add_argument("--no-config3", action="store_true", help="skip the 3-stream / global-batch-1024 strong-scaling sub-benchmark")
     ap.add_argument("--config3-sync-bn", type=int, default=1, help="1: N > 1 also times config 3 with SyncBN (global-batch statistics)")
+    ap.add_argument("--config3-batch", type=int, default=0, help="global batch of the config-3 sub-benchmark (default 1024, BASELINE configs[2])")
     ap.add_argument("--no-extra", action="store_true", help="skip the TARGCN (config 4) and sensor (config 5) sub-benchmarks (N=1)")
     ap.add_argument("--workload", default="gstcan", choices=["gstcan", "targcn"],
                     help="gstcan: BASELINE configs[1] (the headline, default); targcn: configs[3] (TARGCN T=300 V=25, 512 clips)")

@@ -446,7 +446,16 @@ def run_ours(args):
         # whole step (zero_grad .. optimizer.step) as one CUDA graph on static input tensors
         from fall_multimodal_b200.graphs import GraphedStep
 
-        graphed = GraphedStep(step, (skel, sensor, target), warmup=2)
+        # the two trunks run on concurrent streams: with every persistent kernel sized for half of the SMs their kernels sit side
+        # by side instead of taking turns on the whole chip (ops.set_sm_limit is read at launch time = baked into the capture;
+        # everything after the capture - per-kernel roofline leg, config 3 / 4 / 5 - runs with the full chip again)
+        sm_split = bool(args.streams) and bool(args.sm_split)
+        if sm_split:
+            ops.set_sm_limit(torch.cuda.get_device_properties(dev).multi_processor_count // 2)
+        try:
+            graphed = GraphedStep(step, (skel, sensor, target), warmup=2)
+        finally:
+            ops.set_sm_limit(0)
         eager_step = step
 
         def step(sk, se, tg):  # noqa: F811
@@ -607,7 +616,7 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "clips_per_gpu": B, "global_batch": world * B, "T": T, "V": V,
                            "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) >> 126 MB L2",
-                           "bn": "per-shard statistics", "streams": bool(args.streams), "cuda_graph": bool(args.graph),
+                           "bn": "per-shard statistics", "streams": bool(args.streams), "sm_split": bool(args.streams and args.sm_split and args.graph), "cuda_graph": bool(args.graph),
                            "step": "torch CrossEntropyLoss + torch.optim.RMSprop" if args.stock_step else
                                    "fused head + cross-entropy kernel, multi-tensor RMSprop kernel"},
                 "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -891,6 +900,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips per CPU-baseline step (bounded sample)")
     ap.add_argument("--streams", type=int, default=1, help="1: run the independent branches (two trunks, sensor) on side streams")
+    ap.add_argument("--sm-split", type=int, default=1, help="1: with --streams and --graph, persistent kernels of the captured step are sized for half of the SMs (two trunks side by side)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the whole train step as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stock-step", type=int, default=0, help="1: torch CrossEntropyLoss + torch.optim.RMSprop instead of the fused head/loss and optimizer kernels")

@@ -87,6 +87,7 @@ _SIGNATURES = {
     "fmm_debug_mma_probe": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "fmm_debug_wait_profile": [c_int, _P],
     "fmm_device_supported": [],
+    "fmm_set_sm_limit": [c_int],
     "fmm_tapconv_bn": [c_int, c_int],
     "fmm_tapconv_packed_bytes": [c_int, c_int, c_int, c_int],
     "fmm_tapconv_pack": [_P, _P, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_int,

@@ -39,6 +39,13 @@ def _timed(kind, flops, nbytes, fn):
     return out
 
 
+def set_sm_limit(n: int) -> int:
+    """Grid budget of the persistent kernels (``fmm_set_sm_limit``): 0 = all SMs; ``sm_count // 2`` while the two trunks of a fusion
+    model run on concurrent streams lets their kernels sit side by side. Read at launch time, so a captured graph keeps the value it
+    was captured with. Returns the previous value."""
+    return int(L.load().fmm_set_sm_limit(int(n)))
+
+
 class PackedWeight:
     """Weights of one tap-conv, converted to the tensor-core shared-memory images."""
 

@@ -9,7 +9,7 @@ from fall_multimodal_b200.optim import FusedRMSprop
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-B = 256
+B = int(os.environ.get("B", 256))
 model = fmm.TwoStreamSTGCAN_CNN1D(3, {"layout": bench.LAYOUT, "strategy": "spatial"}, bench.NUM_CLASS, bench.SENSOR_C, bench.SENSOR_L).to(dev).train()
 opt = FusedRMSprop(model.parameters(), lr=1e-4)
 skel, sensor, target = (t.to(dev) for t in bench.synthetic(B, 42))
@@ -50,11 +50,14 @@ def union(evs):
 gem = [e for e in ev if any(k in e["name"] for k in GEMM)]
 print(f"kernels {len(ev)}  wall {t1 - t0:.0f} us  busy(union) {union(ev):.0f} us  sum of durations {sum(e['dur'] for e in ev):.0f} us")
 print(f"GEMM-class: {len(gem)} launches, sum {sum(e['dur'] for e in gem):.0f} us, union {union(gem):.0f} us -> no GEMM-class kernel in flight for {t1 - t0 - union(gem):.0f} us")
+print(f"B={B}: no kernel at all in flight for {t1 - t0 - union(ev):.0f} us of the step")
 streams = {}
 for e in ev:
     streams.setdefault(e["args"].get("stream"), []).append(e)
 for s, es in sorted(streams.items(), key=lambda x: -sum(e["dur"] for e in x[1])):
     print(f"  stream {s}: {len(es)} kernels, sum {sum(e['dur'] for e in es):.0f} us, span {es[0]['ts'] - t0:.0f}..{max(e['ts'] + e['dur'] for e in es) - t0:.0f}")
+    short = [e for e in es if e["dur"] < 12]
+    print(f"      kernels under 12 us: {len(short)} launches, {sum(e['dur'] for e in short):.0f} us")
 import collections
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in ev:

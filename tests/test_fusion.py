@@ -240,3 +240,46 @@ def test_three_stream_matches_oracle():
         worst = max(worst, (p.grad.double() - r).abs().max().item() / scale)
     print(f"three-stream fp32: logits {err:.2e}, worst gradient err {worst:.2e} (all three trunks + fc, natural ReLU decisions)")
     assert worst < 5e-2      # a single flipped ReLU decision moves a gradient by a whole element at N=6; see test_stgcan.py
+
+
+@gpu
+@pytest.mark.parametrize("limit", [2, 74])
+def test_sm_limit_does_not_change_results(limit):
+    """ops.set_sm_limit only re-partitions the persistent kernels' work (grids of `limit` CTAs instead of one per SM): logits,
+    loss and gradients of the bf16 two-stream model on concurrent streams agree with the full-chip run to accumulation order."""
+    from fall_multimodal_b200 import TwoStreamSTGCAN_CNN1D, ops
+
+    dev = torch.device("cuda:0")
+    N, T, V = 16, 24, 33
+    m = TwoStreamSTGCAN_CNN1D(3, {"layout": "mediapipe33", "strategy": "spatial"}, 11, 15, 30)
+    sd = m.state_dict()
+    sd.update(O.fill_state_dict({k: tuple(v.shape) for k, v in sd.items()}, 4))
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    m.concurrent_streams = True
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    skel, sensor, target, _ = O.synthetic_batch(N, T, V, 11, sensor_len=30, sensor_ch=15, seed=8)
+    skel, sensor, target = skel.to(dev), sensor.to(dev), target.to(dev)
+
+    def run(lim):
+        m.load_state_dict(state)
+        for p in m.parameters():
+            p.grad = None
+        prev = ops.set_sm_limit(lim)
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out, loss = m.forward_loss(skel, sensor, target)
+            loss.backward()
+            torch.cuda.synchronize()
+        finally:
+            assert ops.set_sm_limit(prev) == (lim & ~1 if lim >= 2 else 0)
+        return out.float().detach(), loss.item(), torch.cat([p.grad.flatten().double() for p in m.parameters() if p.grad is not None])
+
+    o0, l0, g0 = run(0)
+    o1, l1, g1 = run(limit)
+    o2, l2, g2 = run(0)                      # noise floor: the full-chip run once more (fp32 atomics order, bf16 rounding flips)
+    noise = (g2 - g0).norm().item() / g0.norm().item()
+    err = (g1 - g0).norm().item() / g0.norm().item()
+    print(f"sm limit {limit}: logits {(o1 - o0).abs().max().item():.2e}, loss {abs(l1 - l0):.2e}, grad rel-L2 {err:.2e} (two full-chip runs: {noise:.2e})")
+    assert (o1 - o0).abs().max().item() <= 2e-2 * o0.abs().max().item() and abs(l1 - l0) < 1e-2
+    assert err <= max(1e-3, 4 * noise)

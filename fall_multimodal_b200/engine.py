@@ -68,6 +68,7 @@ class TrunkEngine:
         # they overlap the dgrad -> BatchNorm-backward -> aggregation chain of the same and later blocks.
         self.materialize_h = True  # bf16: write relu(bn1(G)) once instead of transforming it in two GEMM prologues
         self.overlap_wgrad = False  # measured: no gain, two persistent GEMM CTAs cannot share an SM
+        self.side_params = True     # tiny parameter-gradient-only launches (SE weight products, conv-bias / edge-importance sums) on a side stream
         self.fused_gcn = True        # bf16, C % 64 == 0: csrc/gcn.cu instead of agg_fwd + 1x1 tapconv + colstats
         self.fused_gcn_wgrad = True   # weight gradient re-derives the aggregated operand (no saved Xa)
         self.fused_gcn_bwd = True     # dx / d(edge importance): GEMM + transposed aggregation in one kernel (no P tensor)
@@ -342,7 +343,7 @@ class TrunkEngine:
         # world size at the end they are this rank's share, so the data-parallel gradient average reproduces the global sum
         glob = []
         ws = None
-        if self.overlap_wgrad:
+        if self.overlap_wgrad or self.side_params:
             key = (str(dev), cur.cuda_stream)
             if key not in self._wstreams:
                 self._wstreams[key] = torch.cuda.Stream(device=dev)
@@ -350,7 +351,7 @@ class TrunkEngine:
         keep = []  # operands of side-stream launches stay referenced until the join below
 
         def wgrad_async(*args, **kw):
-            if ws is None:
+            if ws is None or not self.overlap_wgrad:
                 return ops.wgrad(*args, **kw)
             ws.wait_stream(cur)
             keep.append(args)

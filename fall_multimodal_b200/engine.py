@@ -367,6 +367,12 @@ class TrunkEngine:
             with torch.cuda.stream(ws):
                 return fn(*args)
 
+        def rep_sum(t, c):
+            """fp32 total of the NR fp64 replica rows of a per-channel accumulator (conv-bias gradients)."""
+            out = t.view(NR, c).sum(0).float()
+            out.record_stream(cur)      # allocated on the side stream, consumed on the main one after the join
+            return out
+
         # premasked: dY already carries the ReLU mask of this block's output - the fused graph-conv backward of the block
         # above read that output anyway (edge gradient) and stored dx * (x > 0); Y is then never read again down here
         premasked = False
@@ -429,7 +435,7 @@ class TrunkEngine:
             sum_dU = arena.f64(NR * Cout)
             sum_dR = arena.f64(NR * Cout) if R is not None else None
             ops.bn2_bwd_apply(dY, Ym, U, R, k1, k2, k3, r1, r2, r3, dU, dR, dPre, sum_dU, sum_dR)
-            grads[pre + "tcn.2.bias"] = sum_dU.view(NR, Cout).sum(0).float()
+            grads[pre + "tcn.2.bias"] = side(rep_sum, sum_dU, Cout)
 
             # ---- temporal conv: wgrad + dgrad ----
             Wt = P[pre + "tcn.2.weight"]
@@ -492,7 +498,7 @@ class TrunkEngine:
                 dWr = arena.f32(Cout, Cin, 1, 1)
                 wgrad_async(x, dR, dWr, shifts=[0], istride=s, s_m=0, s_c2=1, s_co=Cin)
                 grads[pre + "residual.0.weight"] = dWr
-                grads[pre + "residual.0.bias"] = sum_dR.view(NR, Cout).sum(0).float()
+                grads[pre + "residual.0.bias"] = side(rep_sum, sum_dR, Cout)
                 grads[pre + "residual.1.weight"], grads[pre + "residual.1.bias"] = dgr, dbr
                 addend = torch.zeros_like(x)
                 ops.tapconv(dR, pp["wr_d"], addend, shifts=[0], tj=To, ostride=s, ooff=0)

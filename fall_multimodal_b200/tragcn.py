@@ -424,10 +424,24 @@ class _GraphGRUScanP(Function):
             lib = L.load()
             XCg = torch.empty(2, T, B, V, Cp, dtype=dt, device=dev)
             XCu = torch.empty(2, T, B, V, Cp, dtype=dt, device=dev)
-            for blk, out in ((xcg, XCg), (xcu, XCu)):
-                L.check(lib.fmm_gruscan_export_xc(blk.data_ptr(), xb.data_ptr(), out.data_ptr(), T, B, V, KS, xb_slices, slot0, Din, Cp,
-                                                  L.stream()), "gruscan_export_xc")
-            if os.environ.get("FMM_GRUSCAN_BWD", "1") == "0":      # host-driven BPTT over the exported gate values (dev aid)
+
+            def export_states():
+                for blk, out in ((xcg, XCg), (xcu, XCu)):
+                    L.check(lib.fmm_gruscan_export_xc(blk.data_ptr(), xb.data_ptr(), out.data_ptr(), T, B, V, KS, xb_slices, slot0, Din, Cp,
+                                                      L.stream()), "gruscan_export_xc")
+
+            host_bptt = os.environ.get("FMM_GRUSCAN_BWD", "1") == "0"
+            cur = torch.cuda.current_stream(dev)
+            side = None
+            if host_bptt or os.environ.get("FMM_GRUSCAN_SIDE_EXPORT", "1") == "0":
+                export_states()
+            else:
+                # the row-layout copies of the saved states feed only the weight gradients after the sweep: they are queued on a side
+                # stream BEHIND the backward scan's launch and run on the SMs the scan's 15 resident clusters leave free
+                side = _side_stream(dev, cur)
+                fork = torch.cuda.Event()
+                fork.record(cur)
+            if host_bptt:      # host-driven BPTT over the exported gate values (dev aid)
                 ZR = torch.empty(T, B, V, 2 * H, dtype=dt, device=dev)
                 LG = torch.empty(T, B, V, 2 * H, dtype=dt, device=dev)
                 HC = torch.empty(T, B, V, H, dtype=dt, device=dev)
@@ -447,11 +461,17 @@ class _GraphGRUScanP(Function):
             err = torch.zeros(1, dtype=torch.int32, device=dev)
             _scan_call(2, B, T, V, NC, fs=fs, dhout=dH, dh_strides=(T * V * H, V * H, H), dxu=dxu, dxgz=dxgz, dxgr=dxgr, W=Wh, Lw=Lh, cs=cs, S=S,
                        err=err)
+            if side is not None:
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    export_states()
             dPLu = torch.empty(2, T, B, V, H, dtype=dt, device=dev)
             dPLg = torch.empty(2, T, B, V, 2 * H, dtype=dt, device=dev)
             L.check(lib.fmm_gruscan_export_dg(dxu.data_ptr(), dxgz.data_ptr(), dxgr.data_ptr(), dPLu.data_ptr(), dPLg.data_ptr(), T, B, V,
                                               L.stream()), "gruscan_export_dg")
-            del dxu, dxgz, dxgr, xcg, xcu, fs, xb
+            del dxu, dxgz, dxgr, fs
+            if side is None:
+                del xcg, xcu, xb
             # input gradients of both stages for every step: [0] graph path (before the transposed mix), [1] Linear path
             Cin = Din + H
             Wg_d, Wu_d = Wg.clone(), Wu.clone()
@@ -476,6 +496,8 @@ class _GraphGRUScanP(Function):
                     d32 += dXg[1, ..., H:Cin]
                     d32 += dXu[1, ..., H:Cin]
                     dX.copy_(d32.permute(1, 0, 2, 3))
+            if side is not None:
+                cur.wait_stream(side)       # (xcg / xcu / xb stay referenced by this frame until here)
             dS, dWg, dWu = _bptt_tail(XCg, XCu, dXg[0], dXu[0], dPLg, dPLu, T, B, V, Cp, H)
         return dX, dS, dWg, dWu, None
 
@@ -483,6 +505,17 @@ class _GraphGRUScanP(Function):
 # ------------------------------------------------------------------------------------------------
 # time-axis transformer pieces (TA.py:40-69)
 # ------------------------------------------------------------------------------------------------
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev, cur):
+    """One side stream per (device, launching stream)."""
+    key = (str(dev), cur.cuda_stream)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 def _rows(x):
     return x.numel() // x.shape[-1]
 

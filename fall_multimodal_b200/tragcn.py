@@ -1085,6 +1085,9 @@ class TARGCN(nn.Module):
         self.end_conv = nn.Conv2d(6, horizon * output_dim, kernel_size=(1, rnn_units), bias=True)
         self.fc = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(output_dim, num_classes))
         self.compute_dtype = None
+        self.wave_split = True       # see wave_chunks
+        self.wave_cap = None         # clips per wave (None: resident clusters x clips per cluster, queried from the library)
+        self._chunk_streams = {}
 
     def features(self, source):
         if not source.is_cuda:
@@ -1100,9 +1103,46 @@ class TARGCN(nn.Module):
         feat = _Head.apply(out, W, None)
         return feat, beff, dt
 
-    def forward(self, source):
+    def _forward_one(self, source):
         feat, beff, dt = self.features(source)
         with torch.autocast("cuda", enabled=False):
             f = feat.float() + beff
             out = _Linear.apply(f.to(dt), self.fc[2].weight, self.fc[2].bias, False, torch.float32)
         return out.to(dt) if dt == torch.bfloat16 else out
+
+    def wave_chunks(self, B: int):
+        """Batch split that keeps every persistent scan launch within ONE wave of resident clusters: the model has no coupling
+        across clips (LayerNorm, per-clip attention), so a batch that needs a partial extra wave (512 clips = 15 clusters of 32 + 1)
+        runs as [full waves..., remainder] on concurrent streams - the remainder's single cluster scans while the big chunk is in
+        its attention / GEMM phases instead of keeping 140 SMs idle for a whole extra sweep. None: no split."""
+        import os
+        if not self.wave_split or os.environ.get("FMM_TARGCN_CHUNKS", "1") == "0" or _compute_dtype(self) != torch.bfloat16:
+            return None
+        if self.hidden_dim != 64 or self.num_node > 32:
+            return None
+        cap = self.wave_cap
+        if cap is None:
+            n = L.load().fmm_gruscan_max_clusters(self.num_node)
+            cap = n * gruscan_geometry(self.num_node)[0] if n > 0 else 0
+        if cap <= 0 or B <= cap or B % cap == 0:
+            return None
+        return [cap] * (B // cap) + [B % cap]
+
+    def forward(self, source):
+        sizes = self.wave_chunks(source.shape[0]) if source.is_cuda else None
+        if sizes is None:
+            return self._forward_one(source)
+        cur = torch.cuda.current_stream(source.device)
+        key = str(source.device)
+        if len(self._chunk_streams.get(key, ())) < len(sizes):
+            self._chunk_streams[key] = [torch.cuda.Stream(device=source.device) for _ in sizes]
+        outs = []
+        for chunk, st in zip(torch.split(source, sizes), self._chunk_streams[key]):
+            st.wait_stream(cur)
+            chunk.record_stream(st)
+            with torch.cuda.stream(st):
+                outs.append(self._forward_one(chunk))
+        for o, st in zip(outs, self._chunk_streams[key]):
+            cur.wait_stream(st)
+            o.record_stream(cur)
+        return torch.cat(outs, 0)

@@ -212,3 +212,44 @@ def test_targcn_inference_no_grad_and_errors():
         m(x)  # CPU tensor: no fallback
     with pytest.raises(ValueError):
         m(x[:, :5].to(dev))
+
+
+@pytest.mark.gpu
+def test_targcn_wave_chunks_match_unsplit_batch():
+    """TARGCN.wave_chunks: a batch that needs a partial extra wave of the persistent scan runs as [full waves..., remainder] on
+    concurrent streams; nothing couples clips, so logits and gradients equal the unsplit batch (bf16 scan path; wave_cap forced
+    to 32 clips so that 80 clips split as 32 + 32 + 16)."""
+    import fall_multimodal_b200 as fmm
+    from oracle import tragcn_oracle as TO
+
+    dev = torch.device("cuda:0")
+    V, T, B = 25, 12, 80
+    m = fmm.TARGCN(num_nodes=V, adj=None, seq_len=T)
+    g = torch.Generator().manual_seed(5)
+    m.load_state_dict({k: (v if k.endswith("PE.pe") else torch.randn(v.shape, generator=g) * (0.3 if "node_emb" in k else 0.08))
+                       for k, v in m.state_dict().items()})
+    m = m.to(dev).train()
+    x, tgt = TO.synthetic_clips(B, T, V, seed=2)
+    x, tgt = x.to(dev), tgt.to(dev)
+
+    def run(split):
+        m.wave_split, m.wave_cap = split, 32
+        for p in m.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            assert m.wave_chunks(B) == ([32, 32, 16] if split else None)
+            assert m.wave_chunks(64) is None and m.wave_chunks(20) is None
+            out = m(x)
+        torch.nn.CrossEntropyLoss()(out.float(), tgt).backward()
+        torch.cuda.synchronize()
+        return out.float().detach(), torch.cat([p.grad.flatten().double() for p in m.parameters() if p.grad is not None])
+
+    o0, g0 = run(False)
+    o1, g1 = run(True)
+    o2, g2 = run(False)
+    noise = (g2 - g0).norm().item() / g0.norm().item()
+    e_out = (o1 - o0).abs().max().item() / o0.abs().max().item()
+    e_g = (g1 - g0).norm().item() / g0.norm().item()
+    print(f"wave chunks: logits {e_out:.2e}, gradient rel-L2 {e_g:.2e} (two unsplit runs: {noise:.2e})")
+    assert e_out < 1e-2                       # per-clip arithmetic is the same; bf16 rounding of the per-chunk weight staging only
+    assert e_g < max(2e-2, 4 * noise)         # weight gradients: per-chunk bf16/fp32 partial sums added in fp32

@@ -35,11 +35,7 @@ int fmm_device_supported(void); /* 1 iff the current device is sm_100 */
 /* grid budget of the persistent kernels: 0 = all SMs (default), n = at most n (even) CTAs per launch, e.g. SMs / 2 while the two
  * trunks of a fusion model run on concurrent streams; process-wide, read at launch time; returns the previous value */
 int fmm_set_sm_limit(int n);
-/* dev aid: per-wait-site blocked cycles of the GEMM kernels' mbarrier waits (enable>=0: reset + set; out32: 32 counters) */
-int fmm_debug_wait_profile(int enable, unsigned long long* out32);
-/* dev aid: cycles for `iters` back-to-back tcgen05.mma (M=128,K=16) per CTA: out2 = {issue cycles, issue+drain cycles} */
-int fmm_debug_mma_probe(int N, int iters, int a_mn, int b_mn, int distinct_acc, int ctas, unsigned long long* out2_dev,
-                        cudaStream_t stream);
+/* (the two measurement aids fmm_debug_* are declared in fmm_b200_debug.h: not part of the product interface) */
 
 /* ---------------------------------------------------------------------------------------------
  * tcgen05 GEMM engines

@@ -1,5 +1,5 @@
 """CPU tests of the C-ABI boundary: the shared library builds, loads, and exports exactly the
-entry points include/fmm_b200.h declares (no compute calls: there is no GPU here)."""
+entry points include/fmm_b200.h (+ the measurement aids of include/fmm_b200_debug.h) declare (no compute calls: there is no GPU here)."""
 import ctypes
 import os
 import re
@@ -9,10 +9,18 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "fmm_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(fmm_[a-z0-9_]+)\s*\(", text)))
+def declared_symbols(headers=("fmm_b200.h", "fmm_b200_debug.h")):
+    names = set()
+    for h in headers:
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names.update(re.findall(r"\b(fmm_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_product_header_has_no_debug_entry_points():
+    assert not [n for n in declared_symbols(("fmm_b200.h",)) if n.startswith("fmm_debug_")]
+    assert sorted(declared_symbols(("fmm_b200_debug.h",))) == ["fmm_debug_mma_probe", "fmm_debug_wait_profile"]
 
 
 @pytest.fixture(scope="module")
@@ -27,7 +35,7 @@ def test_header_symbols_are_exported(lib):
     names = declared_symbols()
     assert len(names) >= 26
     missing = [n for n in names if not hasattr(lib, n)]
-    assert not missing, f"declared in include/fmm_b200.h but not exported: {missing}"
+    assert not missing, f"declared in include/*.h but not exported: {missing}"
 
 
 def test_binding_table_matches_header():

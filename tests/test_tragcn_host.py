@@ -68,3 +68,20 @@ def test_targcn_refuses_cpu_tensors():
     m = TARGCN(num_nodes=14, seq_len=8)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(2, 8, 14, 3))
+
+
+def test_wave_chunks_split_rule():
+    """TARGCN.wave_chunks (host logic): split only when the batch needs a PARTIAL extra wave of the persistent scans."""
+    import torch
+    import fall_multimodal_b200 as fmm
+
+    m = fmm.TARGCN(num_nodes=25, adj=None, seq_len=8)
+    m.compute_dtype = torch.bfloat16
+    m.wave_cap = 480                                  # 15 resident clusters x 32 clips (what the library reports on a B200)
+    assert m.wave_chunks(512) == [480, 32]
+    assert m.wave_chunks(1000) == [480, 480, 40]
+    assert m.wave_chunks(480) is None and m.wave_chunks(960) is None and m.wave_chunks(100) is None
+    m.wave_split = False
+    assert m.wave_chunks(512) is None
+    m.wave_split, m.compute_dtype = True, torch.float32   # the fp32 parity mode runs the per-step kernels: nothing to align
+    assert m.wave_chunks(512) is None

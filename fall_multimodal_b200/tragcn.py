@@ -506,6 +506,7 @@ class _GraphGRUScanP(Function):
 # time-axis transformer pieces (TA.py:40-69)
 # ------------------------------------------------------------------------------------------------
 _SIDE_STREAMS = {}
+_WAVE_CAP = {}
 
 
 def _side_stream(dev, cur):
@@ -1122,8 +1123,11 @@ class TARGCN(nn.Module):
             return None
         cap = self.wave_cap
         if cap is None:
-            n = L.load().fmm_gruscan_max_clusters(self.num_node)
-            cap = n * gruscan_geometry(self.num_node)[0] if n > 0 else 0
+            key = (torch.cuda.current_device(), self.num_node)
+            if key not in _WAVE_CAP:       # occupancy query once per (device, joint count)
+                n = L.load().fmm_gruscan_max_clusters(self.num_node)
+                _WAVE_CAP[key] = n * gruscan_geometry(self.num_node)[0] if n > 0 else 0
+            cap = _WAVE_CAP[key]
         if cap <= 0 or B <= cap or B % cap == 0:
             return None
         return [cap] * (B // cap) + [B % cap]

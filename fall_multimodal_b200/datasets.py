@@ -46,31 +46,60 @@ def video_kfold(videos: Sequence[str], n_splits: int = 10, seed: int = 42):
 
 
 class ResidentSplit:
-    """One side of a fold, resident on ``device`` in the model layouts: skel (N,3,T,V), sensor (N,T,S), label (N,C)."""
+    """One side of a fold, resident on ``device`` in the model layouts: skel (N,3,T,V), sensor (N,T,S), label (N,C).
+
+    The device copies are made on first use and dropped by ``release()``: the list ``build_cv_splits`` returns holds every fold,
+    but only the folds a worker is actually iterating occupy device memory (a cv worker uses one fold at a time)."""
 
     def __init__(self, features, sensors, labels, index, device, batch_size: int, shuffle: bool, drop_last: bool, seed: int = 42):
-        idx = torch.as_tensor(np.asarray(index), dtype=torch.long)
-        self.skel = torch.as_tensor(features)[idx].permute(0, 3, 1, 2).contiguous().to(device)     # F2/dataset.py:27
-        self.sensor = torch.as_tensor(sensors)[idx].contiguous().to(device)
-        self.label = torch.as_tensor(labels)[idx].contiguous().to(device)
+        self._src = (features, sensors, labels)
+        self._idx = torch.as_tensor(np.asarray(index), dtype=torch.long)
+        self.device = device
+        self._dev = None
         self.batch_size, self.shuffle, self.drop_last = batch_size, shuffle, drop_last
         self._gen = torch.Generator(device="cpu").manual_seed(seed)
 
+    def _resident(self):
+        if self._dev is None:
+            features, sensors, labels = self._src
+            idx = self._idx
+            self._dev = (torch.as_tensor(features)[idx].permute(0, 3, 1, 2).contiguous().to(self.device),     # F2/dataset.py:27
+                         torch.as_tensor(sensors)[idx].contiguous().to(self.device),
+                         torch.as_tensor(labels)[idx].contiguous().to(self.device))
+        return self._dev
+
+    def release(self):
+        """Drop the device copies (they are rebuilt on the next use)."""
+        self._dev = None
+
+    @property
+    def skel(self):
+        return self._resident()[0]
+
+    @property
+    def sensor(self):
+        return self._resident()[1]
+
+    @property
+    def label(self):
+        return self._resident()[2]
+
     def __len__(self):
-        n = self.skel.shape[0]
+        n = self.num_samples
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     @property
     def num_samples(self):
-        return self.skel.shape[0]
+        return int(self._idx.numel())
 
     def __iter__(self) -> Iterator:
-        n = self.skel.shape[0]
+        skel, sensor, label = self._resident()
+        n = skel.shape[0]
         order = torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
-        order = order.to(self.skel.device)
+        order = order.to(skel.device)
         for b in range(len(self)):
             sel = order[b * self.batch_size:(b + 1) * self.batch_size]
-            yield self.skel[sel], self.sensor[sel], self.label[sel]
+            yield skel[sel], sensor[sel], label[sel]
 
 
 def build_cv_splits(paths: Sequence[str], device, batch_size: int = 16, n_splits: int = 10, seed: int = 42):

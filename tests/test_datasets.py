@@ -58,3 +58,19 @@ def test_resident_split_iteration(tmp_path):
     folds, C = build_cv_splits(paths, "cpu", batch_size=8, n_splits=4)
     assert C == 11 and len(folds) == 4 and folds[0]["test"] is folds[0]["valid"]
     assert folds[0]["train"].num_samples + folds[0]["valid"].num_samples == len(videos)
+
+
+def test_resident_split_is_lazy_and_releasable():
+    """Folds share the host arrays; a split copies to its device on first use only and release() drops the copy."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    feats, sens = rng.standard_normal((12, 5, 14, 3)).astype("float32"), rng.standard_normal((12, 5, 6)).astype("float32")
+    labels = np.eye(3, dtype="float32")[rng.integers(0, 3, 12)]
+    sp = ResidentSplit(feats, sens, labels, [1, 3, 5, 7, 9], "cpu", batch_size=2, shuffle=False, drop_last=False)
+    assert sp._dev is None and sp.num_samples == 5 and len(sp) == 3          # nothing copied yet
+    batches = list(sp)
+    assert sp._dev is not None and batches[0][0].shape == (2, 3, 5, 14) and batches[-1][0].shape[0] == 1
+    assert np.allclose(batches[0][1].numpy(), sens[[1, 3]])
+    sp.release()
+    assert sp._dev is None
+    assert sp.skel.shape == (5, 3, 5, 14) and sp._dev is not None            # rebuilt on demand
